@@ -1,0 +1,176 @@
+/*
+ * paa_b200.h -- C ABI of libpaa_b200.so: the PAA assign + loss path and the PAA post-processing
+ * path as hand-written sm_100a CUDA kernels.
+ *
+ * Drop-in boundary.  In the reference (JunhoPark0314/PAA) this path is Python that sits on the
+ * pybind11 module `paa_core._C` (paa_core/csrc/vision.cpp:10-27).  This library replaces, for the
+ * path only:
+ *
+ *   paa_assign / paa_loss / paa_assign_loss
+ *       everything PAALossComputation.__call__ does between its arguments and its three returned
+ *       losses (paa_core/modeling/rpn/paa/loss.py:267-359), i.e. boxlist_iou
+ *       (structures/boxlist_ops.py:81-116), Matcher (modeling/matcher.py:42-113), BoxCoder
+ *       encode/decode (modeling/rpn/atss/atss.py:33-50,68-96), concat_box_prediction_layers
+ *       (modeling/rpn/utils.py:17-45; never materialised here), `_C.sigmoid_focalloss_forward`
+ *       / `_backward` (csrc/SigmoidFocalLoss.h:10-41, csrc/cuda/SigmoidFocalLoss_cuda.cu:20-101),
+ *       GIoULoss (loss.py:46-87), compute_paa (loss.py:128-236) including the
+ *       sklearn.mixture.GaussianMixture fit (loss.py:197-203), compute_ious (loss.py:258-265), the
+ *       two normalisers (loss.py:321-322,338) and the autograd backward of the three losses.
+ *   paa_postprocess
+ *       PAAPostProcessor.forward (paa_core/modeling/rpn/paa/inference.py:84-159) including
+ *       `_C.ml_nms` (csrc/ml_nms.h:10-27, csrc/cuda/ml_nms.cu:26-136), the kthvalue cut
+ *       (inference.py:114-122) and score voting (inference.py:123-157).
+ *
+ * Conventions: plain C, device pointers and sizes only (no torch / pybind types); every call
+ * enqueues work on the caller's stream and returns without synchronising the host; the library
+ * never allocates device memory -- the caller passes a workspace of *_workspace_bytes(); return
+ * value 0 = OK, >0 = cudaError_t, <0 = PAA_ERR_*; paa_last_error() gives a thread-local message.
+ * One caller thread per (device, stream); calls on different streams must use different
+ * workspaces.  All floating tensors are float32, head tensors are NCHW-contiguous.
+ */
+#ifndef PAA_B200_H_
+#define PAA_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PAA_ABI_VERSION 1
+#define PAA_MAX_LEVELS 8
+#define PAA_MAX_IMAGES 256      /* images per call (per rank) */
+#define PAA_MAX_CANDIDATES 128  /* num_levels * topk must not exceed this */
+
+#define PAA_ERR_BAD_ARGUMENT (-1)
+#define PAA_ERR_WORKSPACE    (-2)
+#define PAA_ERR_EMPTY_TARGET (-3)   /* an image without GT: matcher.py:53-58 raises ValueError */
+#define PAA_ERR_UNSUPPORTED  (-4)
+
+/* One FPN level of the head outputs (paa.py:90-108) and its anchors
+ * (anchor_generator.py:112-125).  hw = H*W; with anchors_per_loc = a the level holds hw*a anchors,
+ * anchor i sits at location i / a with channel block i % a (rpn/utils.py:10-14). */
+typedef struct PaaLevel {
+    const float* box_cls;         /* [N, a*C, H, W] */
+    const float* box_regression;  /* [N, a*4, H, W] */
+    const float* iou_pred;        /* [N, a*1, H, W] or NULL (USE_IOU_PRED False) */
+    const float* anchors;         /* [hw*a, 4] xyxy; image i reads anchors + i*anchor_image_stride */
+    float* grad_box_cls;          /* same shapes as the inputs; all three NULL = no gradients */
+    float* grad_box_regression;
+    float* grad_iou_pred;
+    int32_t hw;
+    int32_t reserved;
+} PaaLevel;
+
+typedef struct PaaLossArgs {
+    int32_t num_images;           /* N on this rank */
+    int32_t num_levels;           /* <= PAA_MAX_LEVELS */
+    int32_t num_classes;          /* C = NUM_CLASSES - 1 (80) */
+    int32_t anchors_per_loc;      /* 1 for every PAA config */
+    int32_t topk;                 /* cfg.MODEL.PAA.TOPK (9) */
+    int32_t use_iou_pred;         /* cfg.MODEL.PAA.USE_IOU_PRED */
+    int32_t world_size;           /* WORLD_SIZE as read by loss.py:18-19 */
+    int32_t reserved0;
+    float gamma, alpha;           /* focal loss, cfg.MODEL.PAA.LOSS_GAMMA / LOSS_ALPHA */
+    float iou_threshold;          /* Matcher high == low threshold (loss.py:38-40) */
+    float reg_loss_weight;        /* cfg.MODEL.PAA.REG_LOSS_WEIGHT */
+    float iou_loss_weight;        /* cfg.MODEL.PAA.IOU_LOSS_WEIGHT */
+    float reserved1;
+    int64_t anchor_image_stride;  /* in floats; 0 when all images share the anchor tensors */
+    PaaLevel levels[PAA_MAX_LEVELS];
+    const float* gt_boxes;        /* device [sum G, 4] xyxy */
+    const int64_t* gt_labels;     /* device [sum G], 1..C */
+    int32_t gt_offsets[PAA_MAX_IMAGES + 1];  /* HOST values: image i owns GT [off[i], off[i+1]) */
+    void* workspace;              /* device, >= paa_loss_workspace_bytes(), 256-byte aligned */
+    size_t workspace_bytes;
+    /* outputs (device) */
+    double* normalisers;          /* [2] = {num_pos, sum of positives' IoU} of THIS rank after
+                                     paa_assign; the caller all-reduces (SUM) it in place across
+                                     ranks before paa_loss (loss.py:321,338) */
+    float* losses;                /* [3] = loss_cls, loss_reg, loss_iou_pred */
+    const float* grad_losses;     /* [3] upstream d/d(loss) or NULL for ones */
+    /* optional debug / parity outputs (device, nullable) */
+    int32_t* dbg_matched_idx;     /* [N, A]  Matcher result (-1 or GT index within the image) */
+    int32_t* dbg_iou_labels;      /* [N, A]  IoU-based class label (0 = background) */
+    float* dbg_combined_loss;     /* [N, A]  anchor score; only IoU-positive entries are defined */
+    int32_t* dbg_cand_idx;        /* [sum G, num_levels*topk] sorted candidates (anchor index in image) */
+    int32_t* dbg_cand_cnt;        /* [sum G] */
+    int32_t* dbg_num_pos;         /* [sum G] length of the positive prefix */
+    double* dbg_gmm;              /* [sum G, 8] = w0,w1,mu0,mu1,var0,var1,n_iter,converged */
+    int32_t* dbg_paa_labels;      /* [N, A] final class label (0 = negative) */
+    const float* teacher_combined_loss;  /* [N, A] if non-NULL, candidate selection and the GMM consume
+                                            this instead of the kernel's own anchor scores
+                                            (stage-wise parity protocol) */
+} PaaLossArgs;
+
+typedef struct PaaPostArgs {
+    int32_t num_images;
+    int32_t num_levels;
+    int32_t num_classes;          /* C = 80 foreground classes; labels are 1..C */
+    int32_t anchors_per_loc;
+    int32_t pre_nms_top_n;        /* cfg.MODEL.PAA.PRE_NMS_TOP_N (1000) per level */
+    int32_t detections_per_img;   /* cfg.TEST.DETECTIONS_PER_IMG (100); <=0 disables the cut */
+    int32_t score_voting;         /* cfg.MODEL.PAA.INFERENCE_SCORE_VOTING */
+    int32_t skip_nms;             /* bbox_aug_enabled && !bbox_aug_vote (inference.py:96-97) */
+    float pre_nms_thresh;         /* cfg.MODEL.PAA.INFERENCE_TH (0.05) */
+    float nms_thresh;             /* cfg.MODEL.PAA.NMS_TH (0.6) */
+    int64_t anchor_image_stride;
+    PaaLevel levels[PAA_MAX_LEVELS];  /* grad_* unused */
+    float image_wh[PAA_MAX_IMAGES][2];  /* HOST values: BoxList.size = (width, height) per image */
+    void* workspace;
+    size_t workspace_bytes;
+    /* outputs (device).  cap = num_levels * pre_nms_top_n rows per image */
+    float* out_boxes;             /* [N, cap, 4] */
+    float* out_scores;            /* [N, cap] */
+    int64_t* out_labels;          /* [N, cap] 1-based */
+    int32_t* out_count;           /* [N] valid rows per image */
+    /* optional debug outputs */
+    float* dbg_pre_boxes;         /* [N, cap, 4] pre-NMS candidates, level-major */
+    float* dbg_pre_scores;        /* [N, cap] */
+    int32_t* dbg_pre_labels;      /* [N, cap] */
+    int32_t* dbg_pre_count;       /* [N, num_levels] candidates kept per level */
+    uint8_t* dbg_nms_keep;        /* [N, cap] 1 = survived NMS (before the detections_per_img cut) */
+} PaaPostArgs;
+
+int paa_abi_version(void);
+const char* paa_last_error(void);
+
+/* Workspace sizes (bytes) for the given problem; pure host functions. */
+size_t paa_loss_workspace_bytes(int num_images, int anchors_per_image, int num_gt_total,
+                                int num_levels, int topk);
+size_t paa_postprocess_workspace_bytes(int num_images, int anchors_per_image, int num_classes,
+                                       int num_levels, int pre_nms_top_n);
+
+/* Stages 1-4: IoU matching, anchor scores, per-GT top-k + GMM, PAA labels, this rank's
+ * normalisers.  `stream` is a cudaStream_t. */
+int paa_assign(const PaaLossArgs* args, void* stream);
+/* Stage 5: the three losses and (if grad pointers are set) their gradients, using
+ * args->normalisers as already reduced over ranks. */
+int paa_loss(const PaaLossArgs* args, void* stream);
+/* Both, for world_size == 1. */
+int paa_assign_loss(const PaaLossArgs* args, void* stream);
+/* Rescales gradients written by paa_loss by upstream grads that differ from the ones used then:
+ * grad_x *= new_grad_losses[j] / old_grad_losses[j]; both are device [3]. */
+int paa_rescale_grads(const PaaLossArgs* args, const float* old_grad_losses,
+                      const float* new_grad_losses, void* stream);
+
+int paa_postprocess(const PaaPostArgs* args, void* stream);
+
+/* Stand-alone kernels behind the reference's `_C` entry points, for callers that use them
+ * directly (boxlist_ml_nms, SigmoidFocalLoss). */
+/* csrc/ml_nms.h:10-27: keep[n] (1 = kept) in input order; workspace >= paa_ml_nms_workspace_bytes(n). */
+size_t paa_ml_nms_workspace_bytes(int n);
+int paa_ml_nms(const float* boxes, const float* scores, const float* labels, int n, float thresh,
+               uint8_t* keep, int32_t* num_keep, void* workspace, size_t workspace_bytes, void* stream);
+/* csrc/SigmoidFocalLoss.h:10-41 on [n, C] row-major logits with int32 targets. */
+int paa_sigmoid_focal_loss_forward(const float* logits, const int32_t* targets, int n, int num_classes,
+                                   float gamma, float alpha, float* losses, void* stream);
+int paa_sigmoid_focal_loss_backward(const float* logits, const int32_t* targets, const float* d_losses,
+                                    int n, int num_classes, float gamma, float alpha, float* d_logits,
+                                    void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PAA_B200_H_ */

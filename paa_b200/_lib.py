@@ -1,0 +1,123 @@
+"""ctypes binding of libpaa_b200.so -- mirrors include/paa_b200.h field for field.
+
+There is no fallback: if the library is missing or does not load, importing a product module that
+needs it raises.  Build it with ``python -m paa_b200.build`` (needs nvcc) or
+``__graft_entry__.build()``.
+"""
+import ctypes as C
+import os
+
+from paa_b200 import build as _build
+
+MAX_LEVELS = 8
+MAX_IMAGES = 256
+MAX_CANDIDATES = 128
+ABI_VERSION = 1
+
+ERR_BAD_ARGUMENT, ERR_WORKSPACE, ERR_EMPTY_TARGET, ERR_UNSUPPORTED = -1, -2, -3, -4
+
+_fp = C.POINTER(C.c_float)
+
+
+class PaaLevel(C.Structure):
+    _fields_ = [("box_cls", C.c_void_p), ("box_regression", C.c_void_p), ("iou_pred", C.c_void_p),
+                ("anchors", C.c_void_p), ("grad_box_cls", C.c_void_p), ("grad_box_regression", C.c_void_p),
+                ("grad_iou_pred", C.c_void_p), ("hw", C.c_int32), ("reserved", C.c_int32)]
+
+
+class PaaLossArgs(C.Structure):
+    _fields_ = [("num_images", C.c_int32), ("num_levels", C.c_int32), ("num_classes", C.c_int32),
+                ("anchors_per_loc", C.c_int32), ("topk", C.c_int32), ("use_iou_pred", C.c_int32),
+                ("world_size", C.c_int32), ("reserved0", C.c_int32),
+                ("gamma", C.c_float), ("alpha", C.c_float), ("iou_threshold", C.c_float),
+                ("reg_loss_weight", C.c_float), ("iou_loss_weight", C.c_float), ("reserved1", C.c_float),
+                ("anchor_image_stride", C.c_int64),
+                ("levels", PaaLevel * MAX_LEVELS),
+                ("gt_boxes", C.c_void_p), ("gt_labels", C.c_void_p),
+                ("gt_offsets", C.c_int32 * (MAX_IMAGES + 1)),
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+                ("normalisers", C.c_void_p), ("losses", C.c_void_p), ("grad_losses", C.c_void_p),
+                ("dbg_matched_idx", C.c_void_p), ("dbg_iou_labels", C.c_void_p),
+                ("dbg_combined_loss", C.c_void_p), ("dbg_cand_idx", C.c_void_p),
+                ("dbg_cand_cnt", C.c_void_p), ("dbg_num_pos", C.c_void_p), ("dbg_gmm", C.c_void_p),
+                ("dbg_paa_labels", C.c_void_p), ("teacher_combined_loss", C.c_void_p)]
+
+
+class PaaPostArgs(C.Structure):
+    _fields_ = [("num_images", C.c_int32), ("num_levels", C.c_int32), ("num_classes", C.c_int32),
+                ("anchors_per_loc", C.c_int32), ("pre_nms_top_n", C.c_int32),
+                ("detections_per_img", C.c_int32), ("score_voting", C.c_int32), ("skip_nms", C.c_int32),
+                ("pre_nms_thresh", C.c_float), ("nms_thresh", C.c_float),
+                ("anchor_image_stride", C.c_int64),
+                ("levels", PaaLevel * MAX_LEVELS),
+                ("image_wh", (C.c_float * 2) * MAX_IMAGES),
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+                ("out_boxes", C.c_void_p), ("out_scores", C.c_void_p), ("out_labels", C.c_void_p),
+                ("out_count", C.c_void_p),
+                ("dbg_pre_boxes", C.c_void_p), ("dbg_pre_scores", C.c_void_p),
+                ("dbg_pre_labels", C.c_void_p), ("dbg_pre_count", C.c_void_p),
+                ("dbg_nms_keep", C.c_void_p)]
+
+
+# name -> (restype, argtypes); every symbol include/paa_b200.h declares
+SYMBOLS = {
+    "paa_abi_version": (C.c_int, []),
+    "paa_last_error": (C.c_char_p, []),
+    "paa_loss_workspace_bytes": (C.c_size_t, [C.c_int] * 5),
+    "paa_postprocess_workspace_bytes": (C.c_size_t, [C.c_int] * 5),
+    "paa_assign": (C.c_int, [C.POINTER(PaaLossArgs), C.c_void_p]),
+    "paa_loss": (C.c_int, [C.POINTER(PaaLossArgs), C.c_void_p]),
+    "paa_assign_loss": (C.c_int, [C.POINTER(PaaLossArgs), C.c_void_p]),
+    "paa_rescale_grads": (C.c_int, [C.POINTER(PaaLossArgs), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "paa_postprocess": (C.c_int, [C.POINTER(PaaPostArgs), C.c_void_p]),
+    "paa_ml_nms_workspace_bytes": (C.c_size_t, [C.c_int]),
+    "paa_ml_nms": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_void_p,
+                             C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "paa_sigmoid_focal_loss_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float,
+                                                 C.c_float, C.c_void_p, C.c_void_p]),
+    "paa_sigmoid_focal_loss_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                                  C.c_float, C.c_float, C.c_void_p, C.c_void_p]),
+}
+
+_lib = None
+
+
+class PaaLibraryError(RuntimeError):
+    pass
+
+
+def library_path():
+    return os.environ.get("PAA_B200_LIB", _build.LIB_PATH)
+
+
+def load():
+    """Loads the shared library once and types every entry point.  Raises if it is not there."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not os.path.exists(path):
+        raise PaaLibraryError(
+            "libpaa_b200.so not found at %s -- build it with `python -m paa_b200.build` "
+            "(there is no CPU or PyTorch fallback for this path)" % path)
+    lib = C.CDLL(path)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)       # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    if lib.paa_abi_version() != ABI_VERSION:
+        raise PaaLibraryError("libpaa_b200.so ABI %d != binding %d" % (lib.paa_abi_version(), ABI_VERSION))
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    """Turns a non-zero return code into the exception the reference would raise at that point."""
+    if rc == 0:
+        return
+    msg = load().paa_last_error().decode("utf-8", "replace")
+    if rc == ERR_EMPTY_TARGET:
+        raise ValueError(msg)                      # matcher.py:53-58
+    if rc in (ERR_BAD_ARGUMENT, ERR_UNSUPPORTED, ERR_WORKSPACE):
+        raise RuntimeError("%s: %s" % (what, msg))
+    raise RuntimeError("%s: CUDA error %d: %s" % (what, rc, msg))

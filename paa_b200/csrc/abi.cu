@@ -1,0 +1,263 @@
+// extern "C" entry points of libpaa_b200.so (see include/paa_b200.h).
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "kernels.h"
+#include "post.h"
+
+namespace paa {
+
+static thread_local char g_error[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+
+static int tiles_of(int n_anchor) { return (n_anchor + PAA_TILE - 1) / PAA_TILE; }
+
+// Validates the caller's description of the head tensors and builds the kernel-side view.
+static int build_geometry(int num_images, int num_levels, int num_classes, int anchors_per_loc,
+                          long long anchor_image_stride, const PaaLevel* levels, bool need_iou,
+                          Geometry* geo) {
+    if (num_images < 1 || num_images > PAA_MAX_IMAGES) {
+        set_error("num_images=%d outside [1, %d]", num_images, PAA_MAX_IMAGES);
+        return PAA_ERR_BAD_ARGUMENT;
+    }
+    if (num_levels < 1 || num_levels > PAA_MAX_LEVELS) {
+        set_error("num_levels=%d outside [1, %d]", num_levels, PAA_MAX_LEVELS);
+        return PAA_ERR_BAD_ARGUMENT;
+    }
+    if (num_classes < 1 || anchors_per_loc < 1) {
+        set_error("num_classes=%d / anchors_per_loc=%d must be positive", num_classes, anchors_per_loc);
+        return PAA_ERR_BAD_ARGUMENT;
+    }
+    memset(geo, 0, sizeof(*geo));
+    geo->num_levels = num_levels;
+    geo->num_images = num_images;
+    geo->C = num_classes;
+    geo->apl = anchors_per_loc;
+    geo->anchor_image_stride = anchor_image_stride;
+    int a_off = 0, t_off = 0;
+    for (int l = 0; l < num_levels; ++l) {
+        const PaaLevel& s = levels[l];
+        if (s.hw < 1 || !s.box_cls || !s.box_regression || !s.anchors || (need_iou && !s.iou_pred)) {
+            set_error("level %d: null tensor or hw=%d", l, s.hw);
+            return PAA_ERR_BAD_ARGUMENT;
+        }
+        LevelView& v = geo->lv[l];
+        v.cls = s.box_cls;
+        v.reg = s.box_regression;
+        v.iou = s.iou_pred;
+        v.anchors = s.anchors;
+        v.g_cls = s.grad_box_cls;
+        v.g_reg = s.grad_box_regression;
+        v.g_iou = s.grad_iou_pred;
+        v.hw = s.hw;
+        v.n_anchor = s.hw * anchors_per_loc;
+        v.a_off = a_off;
+        v.tile_off = t_off;
+        a_off += v.n_anchor;
+        t_off += tiles_of(v.n_anchor);
+    }
+    geo->A = a_off;
+    geo->tiles_per_image = t_off;
+    return 0;
+}
+
+static int tiles_upper_bound(int anchors_per_image, int num_levels) {
+    return (anchors_per_image + PAA_TILE - 1) / PAA_TILE + num_levels;
+}
+
+struct LossPlan {
+    Geometry geo;
+    GtOffsets go;
+    LossScalars sc;
+    LossDebug dbg;
+    LossWorkspace ws;
+    int sumG;
+};
+
+static int plan_loss(const PaaLossArgs* a, LossPlan* p) {
+    if (!a) {
+        set_error("null PaaLossArgs");
+        return PAA_ERR_BAD_ARGUMENT;
+    }
+    int rc = build_geometry(a->num_images, a->num_levels, a->num_classes, a->anchors_per_loc,
+                            a->anchor_image_stride, a->levels, a->use_iou_pred != 0, &p->geo);
+    if (rc) return rc;
+    if (a->topk < 1 || a->topk > 32 || a->num_levels * a->topk > PAA_MAX_CANDIDATES) {
+        set_error("topk=%d unsupported (1..32, num_levels*topk <= %d)", a->topk, PAA_MAX_CANDIDATES);
+        return PAA_ERR_UNSUPPORTED;
+    }
+    if (a->world_size < 1) {
+        set_error("world_size=%d", a->world_size);
+        return PAA_ERR_BAD_ARGUMENT;
+    }
+    if (a->gt_offsets[0] != 0) {
+        set_error("gt_offsets[0] must be 0");
+        return PAA_ERR_BAD_ARGUMENT;
+    }
+    for (int i = 0; i < a->num_images; ++i) {
+        p->go.v[i] = a->gt_offsets[i];
+        if (a->gt_offsets[i + 1] <= a->gt_offsets[i]) {
+            // matcher.py:53-58: "No ground-truth boxes available for one of the images during training"
+            set_error("No ground-truth boxes available for one of the images during training (image %d)", i);
+            return PAA_ERR_EMPTY_TARGET;
+        }
+    }
+    p->go.v[a->num_images] = a->gt_offsets[a->num_images];
+    p->sumG = a->gt_offsets[a->num_images];
+    if (!a->gt_boxes || !a->gt_labels || !a->workspace || !a->normalisers || !a->losses) {
+        set_error("null gt_boxes / gt_labels / workspace / normalisers / losses");
+        return PAA_ERR_BAD_ARGUMENT;
+    }
+    p->ws = carve_loss_workspace(a->workspace, a->num_images, p->geo.A, p->sumG, p->geo.tiles_per_image,
+                                 loss_grid_blocks(a->num_images, p->geo.tiles_per_image));
+    if (p->ws.total_bytes > a->workspace_bytes) {
+        set_error("workspace too small: need %zu bytes, got %zu", p->ws.total_bytes, a->workspace_bytes);
+        return PAA_ERR_WORKSPACE;
+    }
+    if ((reinterpret_cast<uintptr_t>(a->workspace) & 255u) != 0) {
+        set_error("workspace must be 256-byte aligned");
+        return PAA_ERR_BAD_ARGUMENT;
+    }
+    p->sc.gamma = a->gamma;
+    p->sc.alpha = a->alpha;
+    p->sc.iou_threshold = a->iou_threshold;
+    p->sc.reg_loss_weight = a->reg_loss_weight;
+    p->sc.iou_loss_weight = a->iou_loss_weight;
+    p->sc.topk = a->topk;
+    p->sc.use_iou_pred = a->use_iou_pred;
+    p->sc.world_size = a->world_size;
+    p->dbg.matched_idx = a->dbg_matched_idx;
+    p->dbg.iou_labels = a->dbg_iou_labels;
+    p->dbg.combined_loss = a->dbg_combined_loss;
+    p->dbg.cand_idx = a->dbg_cand_idx;
+    p->dbg.cand_cnt = a->dbg_cand_cnt;
+    p->dbg.num_pos = a->dbg_num_pos;
+    p->dbg.gmm = a->dbg_gmm;
+    p->dbg.paa_labels = a->dbg_paa_labels;
+    return 0;
+}
+
+}  // namespace paa
+
+using namespace paa;
+
+extern "C" {
+
+int paa_abi_version(void) { return PAA_ABI_VERSION; }
+
+const char* paa_last_error(void) { return g_error; }
+
+size_t paa_loss_workspace_bytes(int num_images, int anchors_per_image, int num_gt_total, int num_levels,
+                                int topk) {
+    (void)topk;
+    if (num_images < 1 || anchors_per_image < 1 || num_levels < 1) return 0;
+    const int tiles = tiles_upper_bound(anchors_per_image, num_levels);
+    LossWorkspace w = carve_loss_workspace(nullptr, num_images, anchors_per_image, num_gt_total, tiles,
+                                           loss_grid_blocks(num_images, tiles));
+    return w.total_bytes;
+}
+
+int paa_assign(const PaaLossArgs* args, void* stream_) {
+    LossPlan p;
+    int rc = plan_loss(args, &p);
+    if (rc) return rc;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    PAA_CUDA_CHECK(cudaMemsetAsync(args->workspace, 0, p.ws.zero_bytes, stream));
+    if ((rc = launch_iou_best(p.geo, p.go, args->gt_boxes, p.ws, stream))) return rc;
+    if ((rc = launch_match_score(p.geo, p.go, args->gt_boxes, args->gt_labels, p.sc, p.ws, p.dbg, stream)))
+        return rc;
+    const float* score_src = args->teacher_combined_loss ? args->teacher_combined_loss : p.ws.score;
+    if ((rc = launch_select_gmm(p.geo, p.go, p.sumG, args->gt_boxes, args->gt_labels, p.sc, p.ws, score_src,
+                                args->normalisers, p.dbg, stream)))
+        return rc;
+    if (args->dbg_paa_labels)
+        PAA_CUDA_CHECK(cudaMemcpyAsync(args->dbg_paa_labels, p.ws.paa_label,
+                                       sizeof(int) * (size_t)args->num_images * p.geo.A,
+                                       cudaMemcpyDeviceToDevice, stream));
+    return 0;
+}
+
+int paa_loss(const PaaLossArgs* args, void* stream_) {
+    LossPlan p;
+    int rc = plan_loss(args, &p);
+    if (rc) return rc;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    bool write_grads = false;
+    for (int l = 0; l < args->num_levels; ++l)
+        write_grads = write_grads || args->levels[l].grad_box_cls || args->levels[l].grad_box_regression ||
+                      args->levels[l].grad_iou_pred;
+    return launch_final_loss(p.geo, p.go, args->gt_boxes, p.sc, p.ws, args->normalisers, args->grad_losses,
+                             args->losses, write_grads, stream);
+}
+
+int paa_assign_loss(const PaaLossArgs* args, void* stream) {
+    int rc = paa_assign(args, stream);
+    if (rc) return rc;
+    return paa_loss(args, stream);
+}
+
+int paa_rescale_grads(const PaaLossArgs* args, const float* old_grad_losses, const float* new_grad_losses,
+                      void* stream_) {
+    LossPlan p;
+    int rc = plan_loss(args, &p);
+    if (rc) return rc;
+    if (!old_grad_losses || !new_grad_losses) {
+        set_error("null grad_losses");
+        return PAA_ERR_BAD_ARGUMENT;
+    }
+    return launch_rescale_grads(p.geo, old_grad_losses, new_grad_losses, static_cast<cudaStream_t>(stream_));
+}
+
+int paa_sigmoid_focal_loss_forward(const float* logits, const int32_t* targets, int n, int num_classes,
+                                   float gamma, float alpha, float* losses, void* stream) {
+    if (n < 0 || num_classes < 1 || (n > 0 && (!logits || !targets || !losses))) {
+        set_error("bad arguments to paa_sigmoid_focal_loss_forward");
+        return PAA_ERR_BAD_ARGUMENT;
+    }
+    return launch_focal_forward(logits, targets, n, num_classes, gamma, alpha, losses,
+                                static_cast<cudaStream_t>(stream));
+}
+
+int paa_sigmoid_focal_loss_backward(const float* logits, const int32_t* targets, const float* d_losses, int n,
+                                    int num_classes, float gamma, float alpha, float* d_logits, void* stream) {
+    if (n < 0 || num_classes < 1 || (n > 0 && (!logits || !targets || !d_losses || !d_logits))) {
+        set_error("bad arguments to paa_sigmoid_focal_loss_backward");
+        return PAA_ERR_BAD_ARGUMENT;
+    }
+    return launch_focal_backward(logits, targets, d_losses, n, num_classes, gamma, alpha, d_logits,
+                                 static_cast<cudaStream_t>(stream));
+}
+
+size_t paa_postprocess_workspace_bytes(int num_images, int anchors_per_image, int num_classes, int num_levels,
+                                       int pre_nms_top_n) {
+    return post_workspace_bytes(num_images, anchors_per_image, num_classes, num_levels, pre_nms_top_n);
+}
+
+int paa_postprocess(const PaaPostArgs* args, void* stream) {
+    if (!args) {
+        set_error("null PaaPostArgs");
+        return PAA_ERR_BAD_ARGUMENT;
+    }
+    Geometry geo;
+    int rc = build_geometry(args->num_images, args->num_levels, args->num_classes, args->anchors_per_loc,
+                            args->anchor_image_stride, args->levels, false, &geo);
+    if (rc) return rc;
+    return run_postprocess(geo, args, static_cast<cudaStream_t>(stream));
+}
+
+size_t paa_ml_nms_workspace_bytes(int n) { return ml_nms_workspace_bytes(n); }
+
+int paa_ml_nms(const float* boxes, const float* scores, const float* labels, int n, float thresh,
+               uint8_t* keep, int32_t* num_keep, void* workspace, size_t workspace_bytes, void* stream) {
+    return run_ml_nms(boxes, scores, labels, n, thresh, keep, num_keep, workspace, workspace_bytes,
+                      static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

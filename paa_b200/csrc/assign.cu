@@ -1,0 +1,620 @@
+// PAA anchor assignment on sm_100a: IoU matching, anchor scores, per-GT top-k + GMM.
+//
+// Replaces, for the images of one rank and without ever materialising the [G, A] IoU matrix:
+//   prepare_iou_based_targets   paa_core/modeling/rpn/paa/loss.py:89-126
+//     boxlist_iou               paa_core/structures/boxlist_ops.py:81-116
+//     Matcher(thr, thr, True)   paa_core/modeling/matcher.py:42-113
+//   anchor scores               loss.py:293-306 (focal sum + GIoU on IoU-positive anchors)
+//   compute_paa                 loss.py:128-236 incl. sklearn GaussianMixture (loss.py:197-203;
+//                               scikit-learn 1.9.0 semantics restated in oracle/gmm_oracle.py)
+//   normalisers                 loss.py:320-322,331-333,338 (this rank's partial sums)
+//
+// Data layout: head tensors are consumed in place as NCHW (one anchor per location makes the class
+// stride H*W, so a warp reading 32 consecutive anchors of one class is one 128-byte line); all
+// per-anchor intermediates are flat [N*A] arrays in the caller's workspace.
+#include "kernels.h"
+
+namespace paa {
+
+// ---------------------------------------------------------------------------------------------
+// K1: every anchor's best GT (first maximum) and every GT's maximal IoU.
+// One block = one tile of 128 consecutive anchors of one level of one image.  GT boxes are staged
+// in shared memory in chunks; a warp only evaluates the GTs whose box intersects the warp's
+// bounding box (non-intersecting pairs have IoU exactly +0 and can neither raise a maximum nor
+// win the first-maximum rule against the initial (0, GT 0)).
+// ---------------------------------------------------------------------------------------------
+constexpr int kGtChunk = 256;
+
+__global__ void __launch_bounds__(PAA_TILE)
+iou_best_kernel(const Geometry geo, const GtOffsets go, const float* __restrict__ gt_boxes,
+                unsigned* __restrict__ gtmax, uint2* __restrict__ best, float4* __restrict__ tile_bbox) {
+    __shared__ float4 s_gt[kGtChunk];
+    __shared__ float s_area[kGtChunk];
+    __shared__ unsigned s_max[kGtChunk];
+    __shared__ float4 s_wbox[PAA_TILE / PAA_WARP];
+
+    const int n = blockIdx.x / geo.tiles_per_image;
+    const int tile = blockIdx.x - n * geo.tiles_per_image;
+    int first;
+    const int l = tile_level(geo, tile, &first);
+    const LevelView& lv = geo.lv[l];
+    const int i = first + threadIdx.x;
+    const bool valid = i < lv.n_anchor;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    float4 a = make_float4(INFINITY, INFINITY, -INFINITY, -INFINITY);
+    if (valid) a = ldg4(lv.anchors + (size_t)n * geo.anchor_image_stride + (size_t)i * 4);
+    const float area_a = area_plus1(a);
+    const float wx1 = warp_min(a.x), wy1 = warp_min(a.y), wx2 = warp_max(a.z), wy2 = warp_max(a.w);
+    if (lane == 0) s_wbox[warp] = make_float4(wx1, wy1, wx2, wy2);
+
+    const int gbase = go.v[n];
+    const int G = go.v[n + 1] - gbase;
+    float best_v = 0.0f;
+    int best_g = 0;
+
+    for (int c0 = 0; c0 < G; c0 += kGtChunk) {
+        const int cnt = min(kGtChunk, G - c0);
+        for (int t = threadIdx.x; t < cnt; t += PAA_TILE) {
+            float4 b = ldg4(gt_boxes + (size_t)(gbase + c0 + t) * 4);
+            s_gt[t] = b;
+            s_area[t] = area_plus1(b);
+            s_max[t] = 0u;
+        }
+        __syncthreads();
+        for (int g0 = 0; g0 < cnt; g0 += PAA_WARP) {
+            const int g = g0 + lane;
+            bool hit = false;
+            if (g < cnt) {
+                float4 b = s_gt[g];
+                float w = __fadd_rn(__fsub_rn(fminf(b.z, wx2), fmaxf(b.x, wx1)), 1.0f);
+                float h = __fadd_rn(__fsub_rn(fminf(b.w, wy2), fmaxf(b.y, wy1)), 1.0f);
+                hit = (w > 0.0f) && (h > 0.0f);
+            }
+            unsigned m = __ballot_sync(PAA_FULL, hit);
+            while (m) {
+                const int j = g0 + __ffs(m) - 1;
+                m &= m - 1;
+                float q = 0.0f;
+                if (valid) q = iou_plus1(s_gt[j], s_area[j], a, area_a);
+                if (q > best_v) {
+                    best_v = q;
+                    best_g = c0 + j;
+                }
+                unsigned wm = __reduce_max_sync(PAA_FULL, __float_as_uint(q));
+                if (lane == 0 && wm != 0u) atomicMax(&s_max[j], wm);
+            }
+        }
+        __syncthreads();
+        for (int t = threadIdx.x; t < cnt; t += PAA_TILE)
+            if (s_max[t] != 0u) atomicMax(&gtmax[gbase + c0 + t], s_max[t]);
+        __syncthreads();
+    }
+    if (valid) best[(size_t)n * geo.A + lv.a_off + i] = make_uint2(__float_as_uint(best_v), (unsigned)best_g);
+    if (threadIdx.x == 0) {
+        float4 bb = s_wbox[0];
+#pragma unroll
+        for (int w = 1; w < PAA_TILE / PAA_WARP; ++w) {
+            bb.x = fminf(bb.x, s_wbox[w].x);
+            bb.y = fminf(bb.y, s_wbox[w].y);
+            bb.z = fmaxf(bb.z, s_wbox[w].z);
+            bb.w = fmaxf(bb.w, s_wbox[w].w);
+        }
+        tile_bbox[(size_t)n * geo.tiles_per_image + tile] = bb;
+    }
+}
+
+int launch_iou_best(const Geometry& geo, const GtOffsets& go, const float* gt_boxes,
+                    const LossWorkspace& ws, cudaStream_t stream) {
+    int grid = geo.num_images * geo.tiles_per_image;
+    iou_best_kernel<<<grid, PAA_TILE, 0, stream>>>(geo, go, gt_boxes, ws.gtmax, ws.best, ws.tile_bbox);
+    PAA_LAUNCH_CHECK("iou_best_kernel");
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2: Matcher decision + IoU-based label + anchor score of IoU-positive anchors.
+//   matched = argmax GT if max IoU >= thr, else -1, except that an anchor which is some GT's best
+//   anchor (IoU == that GT's maximum, ties included) keeps its argmax GT (matcher.py:83-113).
+//   Only GTs whose maximum is below thr can restore anything, so those are listed first.
+//   score   = sum_c focal(logit_c | IoU label) + (1 - GIoU(decode(pred), decode(encode(gt))))
+//   (loss.py:293-306; anchors without an IoU-positive label are never candidates, their 1e8 filler
+//   is not materialised).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float focal_sum_accurate(const float* __restrict__ p, int stride, int C, int label,
+                                                    float gamma, float alpha) {
+    float sum = 0.0f;
+    const bool g2 = (gamma == 2.0f);
+#pragma unroll 8
+    for (int c = 0; c < C; ++c) {
+        const float x = __ldg(p + (size_t)c * stride);
+        const float e = expf(-fabsf(x));
+        const float l1p = log1pf(e);
+        const float inv = 1.0f / (1.0f + e);
+        const float pr = (x >= 0.0f) ? inv : e * inv;          // sigmoid(x)
+        const float qr = (x >= 0.0f) ? e * inv : inv;          // 1 - sigmoid(x)
+        float term;
+        if (c + 1 == label) {
+            const float nlogp = fmaxf(-x, 0.0f) + l1p;         // -log(p)
+            const float mod = g2 ? qr * qr : powf(qr, gamma);
+            term = alpha * mod * nlogp;
+        } else {
+            const float nlogq = fmaxf(x, 0.0f) + l1p;          // -log(1-p)
+            const float mod = g2 ? pr * pr : powf(pr, gamma);
+            term = (1.0f - alpha) * mod * nlogq;
+        }
+        sum += term;
+    }
+    return sum;
+}
+
+__global__ void __launch_bounds__(PAA_TILE)
+match_score_kernel(const Geometry geo, const GtOffsets go, const float* __restrict__ gt_boxes,
+                   const int64_t* __restrict__ gt_labels, const unsigned* __restrict__ gtmax,
+                   const uint2* __restrict__ best, const LossScalars sc, int* __restrict__ matched,
+                   float* __restrict__ score, int* __restrict__ paa_label, int* __restrict__ img_flags,
+                   const LossDebug dbg) {
+    __shared__ int s_lq[PAA_TILE];
+    __shared__ int s_nlq;
+
+    const int n = blockIdx.x / geo.tiles_per_image;
+    const int tile = blockIdx.x - n * geo.tiles_per_image;
+    int first;
+    const int l = tile_level(geo, tile, &first);
+    const LevelView& lv = geo.lv[l];
+    const int i = first + threadIdx.x;
+    const bool valid = i < lv.n_anchor;
+    const int gbase = go.v[n];
+    const int G = go.v[n + 1] - gbase;
+    const float thr = sc.iou_threshold;
+
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint2 bv = make_uint2(0u, 0u);
+    const size_t flat = (size_t)n * geo.A + lv.a_off + (valid ? i : 0);
+    if (valid) {
+        a = ldg4(lv.anchors + (size_t)n * geo.anchor_image_stride + (size_t)i * 4);
+        bv = best[flat];
+    }
+    const float area_a = area_plus1(a);
+    const float bval = __uint_as_float(bv.x);
+    int m = (bval >= thr) ? (int)bv.y : -1;
+    if (!(bval >= thr) && !(bval < thr)) m = (int)bv.y;   // NaN: neither below nor restored -> keeps argmax
+
+    // low-quality GTs (max IoU below thr) restore their best anchors
+    for (int c0 = 0; c0 < G; c0 += PAA_TILE) {
+        if (threadIdx.x == 0) s_nlq = 0;
+        __syncthreads();
+        const int g = c0 + threadIdx.x;
+        if (g < G) {
+            const unsigned u = gtmax[gbase + g];
+            if (__uint_as_float(u) < thr) s_lq[atomicAdd(&s_nlq, 1)] = g;
+            if (u == 0u && tile == 0) atomicOr(&img_flags[n], 1);
+        }
+        __syncthreads();
+        const int nlq = s_nlq;
+        if (valid && m < 0) {
+            for (int k = 0; k < nlq; ++k) {
+                const int gg = s_lq[k];
+                const float4 b = ldg4(gt_boxes + (size_t)(gbase + gg) * 4);
+                const float q = iou_plus1(b, area_plus1(b), a, area_a);
+                if (q == __uint_as_float(gtmax[gbase + gg])) m = (int)bv.y;
+            }
+        }
+        __syncthreads();
+    }
+    if (!valid) return;
+
+    int label = 0;
+    if (m >= 0) label = (int)gt_labels[gbase + m];
+    matched[flat] = m;
+    paa_label[flat] = 0;
+    if (dbg.matched_idx) dbg.matched_idx[flat] = m;
+    if (dbg.iou_labels) dbg.iou_labels[flat] = label;
+
+    float s = 1.0e8f;   // loss.py:15,301-306 filler, only visible through the debug output
+    if (m >= 0 && label > 0) {
+        const float* cls = lv.cls + head_offset(n, i, 0, geo.C, geo.apl, lv.hw);
+        const float fsum = focal_sum_accurate(cls, lv.hw, geo.C, label, sc.gamma, sc.alpha);
+        const float* rp = lv.reg + head_offset(n, i, 0, 4, geo.apl, lv.hw);
+        const float4 d = make_float4(__ldg(rp), __ldg(rp + lv.hw), __ldg(rp + 2 * (size_t)lv.hw),
+                                     __ldg(rp + 3 * (size_t)lv.hw));
+        const AnchorFrame f = anchor_frame(a);
+        const float4 pred = decode_box(d, f);
+        const float4 gt = ldg4(gt_boxes + (size_t)(gbase + m) * 4);
+        const float4 tgt = decode_box(encode_box(gt, f), f);
+        s = __fadd_rn(fsum, giou_loss_boxes(pred, tgt));
+        score[flat] = s;
+    }
+    if (dbg.combined_loss) dbg.combined_loss[flat] = s;
+}
+
+int launch_match_score(const Geometry& geo, const GtOffsets& go, const float* gt_boxes,
+                       const int64_t* gt_labels, const LossScalars& sc, const LossWorkspace& ws,
+                       const LossDebug& dbg, cudaStream_t stream) {
+    int grid = geo.num_images * geo.tiles_per_image;
+    match_score_kernel<<<grid, PAA_TILE, 0, stream>>>(geo, go, gt_boxes, gt_labels, ws.gtmax, ws.best, sc,
+                                                      ws.matched, ws.score, ws.paa_label, ws.img_flags, dbg);
+    PAA_LAUNCH_CHECK("match_score_kernel");
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3: one warp per GT -- per-level top-k candidates, sort, two-component GMM, labels, partial
+// normalisers.  loss.py:151-236 + sklearn GaussianMixture.fit/predict/score_samples.
+// ---------------------------------------------------------------------------------------------
+constexpr int kSelWarps = 4;                // GTs per block
+constexpr unsigned long long kEmptyKey = ~0ull;
+
+__device__ __forceinline__ unsigned ordered_bits(float v) {
+    unsigned u = __float_as_uint(v);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float from_ordered_bits(unsigned u) {
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+// sklearn/utils/_array_api.py:1338-1366 for two entries.
+__device__ __forceinline__ double logsumexp2(double a0, double a1) {
+    if (a0 == a1) return (log1p(0.0) + 0.6931471805599453094) + a0;   // m = 2, masked sum = 0
+    const double hi = fmax(a0, a1), lo = fmin(a0, a1);
+    return (log1p(exp(lo - hi)) + 0.0) + hi;                          // m = 1, log(m) = 0
+}
+
+struct GmmState {
+    double w0, w1, mu0, mu1;
+    float pc0, pc1, var0, var1;
+    bool first;                    // precisions still the float64 initial values (1.0)
+};
+
+// a_k = log N(x | mu_k, pc_k) + log w_k with the dtype flow of _estimate_log_gaussian_prob
+// (sklearn/mixture/_gaussian_mixture.py:490-553): float32 product x*pc and float32 log-det once the
+// precisions have been re-estimated, float32 buffer for the squared distance, float64 elsewhere.
+__device__ __forceinline__ void weighted_log_prob(float x, const GmmState& s, double lw0, double lw1,
+                                                  float ld0, float ld1, double* a0, double* a1) {
+    const float LOG2PI = 1.8378770664093453f;
+    double xs0, xs1;
+    if (s.first) {
+        xs0 = (double)x;
+        xs1 = (double)x;
+    } else {
+        xs0 = (double)__fmul_rn(x, s.pc0);
+        xs1 = (double)__fmul_rn(x, s.pc1);
+    }
+    const double y0 = xs0 - s.mu0 * (double)s.pc0;
+    const double y1 = xs1 - s.mu1 * (double)s.pc1;
+    const float q0 = __double2float_rn(y0 * y0);
+    const float q1 = __double2float_rn(y1 * y1);
+    const float lp0 = __fmul_rn(-0.5f, __fadd_rn(LOG2PI, q0));
+    const float lp1 = __fmul_rn(-0.5f, __fadd_rn(LOG2PI, q1));
+    if (s.first) {                    // float32 array + float64 log-det (log 1.0 = 0)
+        *a0 = ((double)lp0 + 0.0) + lw0;
+        *a1 = ((double)lp1 + 0.0) + lw1;
+    } else {                          // float32 log-det, float32 add
+        *a0 = (double)__fadd_rn(lp0, ld0) + lw0;
+        *a1 = (double)__fadd_rn(lp1, ld1) + lw1;
+    }
+}
+
+// Fits the mixture on the warp's n sorted samples (lane holds x[lane + 32*k]) and returns the length
+// of the positive prefix (loss.py:206-217).  out8 (nullable, lane 0 writes) receives the parameters.
+template <int SPL>
+__device__ int gmm_positive_prefix(const float (&x)[SPL], int n, int lane, double* out8) {
+    GmmState s;
+    s.w0 = 0.5;
+    s.w1 = 0.5;
+    s.mu0 = (double)__shfl_sync(PAA_FULL, x[0], 0);                       // min (sorted ascending)
+    {
+        const int last = n - 1;
+        float xl = 0.f;
+#pragma unroll
+        for (int k = 0; k < SPL; ++k) {
+            float v = __shfl_sync(PAA_FULL, x[k], last & 31);
+            if ((last >> 5) == k) xl = v;
+        }
+        s.mu1 = (double)xl;                                               // max
+    }
+    s.pc0 = s.pc1 = 1.0f;
+    s.var0 = s.var1 = 1.0f;
+    s.first = true;
+    double lower = -INFINITY;
+    int n_iter = 0;
+    bool converged = false;
+    const double EPS10 = 10.0 * 2.220446049250313e-16;
+    for (int it = 1; it <= 100; ++it) {
+        n_iter = it;
+        const double lw0 = log(s.w0), lw1 = log(s.w1);
+        const float ld0 = s.first ? 0.f : __double2float_rn(log((double)s.pc0));
+        const float ld1 = s.first ? 0.f : __double2float_rn(log((double)s.pc1));
+        double r0[SPL], r1[SPL];
+        double s_r0 = 0, s_r1 = 0, s_r0x = 0, s_r1x = 0, s_lpn = 0;
+#pragma unroll
+        for (int k = 0; k < SPL; ++k) {
+            r0[k] = r1[k] = 0.0;
+            if (lane + 32 * k < n) {
+                double a0, a1;
+                weighted_log_prob(x[k], s, lw0, lw1, ld0, ld1, &a0, &a1);
+                const double lpn = logsumexp2(a0, a1);
+                r0[k] = exp(a0 - lpn);
+                r1[k] = exp(a1 - lpn);
+                s_r0 += r0[k];
+                s_r1 += r1[k];
+                s_r0x += r0[k] * (double)x[k];
+                s_r1x += r1[k] * (double)x[k];
+                s_lpn += lpn;
+            }
+        }
+        s_r0 = warp_sum(s_r0);
+        s_r1 = warp_sum(s_r1);
+        s_r0x = warp_sum(s_r0x);
+        s_r1x = warp_sum(s_r1x);
+        s_lpn = warp_sum(s_lpn);
+        const double nk0 = s_r0 + EPS10, nk1 = s_r1 + EPS10;
+        s.mu0 = s_r0x / nk0;
+        s.mu1 = s_r1x / nk1;
+        double c0 = 0, c1 = 0;
+#pragma unroll
+        for (int k = 0; k < SPL; ++k) {
+            if (lane + 32 * k < n) {
+                const double d0 = (double)x[k] - s.mu0, d1 = (double)x[k] - s.mu1;
+                c0 += (r0[k] * d0) * d0;
+                c1 += (r1[k] * d1) * d1;
+            }
+        }
+        c0 = warp_sum(c0);
+        c1 = warp_sum(c1);
+        s.var0 = __fadd_rn(__double2float_rn(c0 / nk0), 1e-6f);
+        s.var1 = __fadd_rn(__double2float_rn(c1 / nk1), 1e-6f);
+        const double nsum = nk0 + nk1;
+        s.w0 = nk0 / nsum;
+        s.w1 = nk1 / nsum;
+        s.pc0 = __fdiv_rn(1.0f, __fsqrt_rn(s.var0));
+        s.pc1 = __fdiv_rn(1.0f, __fsqrt_rn(s.var1));
+        s.first = false;
+        const double lb = s_lpn / (double)n;
+        const double change = lb - lower;
+        lower = lb;
+        if (fabs(change) < 1e-3) {
+            converged = true;
+            break;
+        }
+    }
+    // final E-step: predict (argmax, ties -> 0) and score_samples
+    const double lw0 = log(s.w0), lw1 = log(s.w1);
+    const float ld0 = __double2float_rn(log((double)s.pc0));
+    const float ld1 = __double2float_rn(log((double)s.pc1));
+    double best_score = -INFINITY;
+    int best_idx = 0x7fffffff;
+    bool any_fg = false;
+#pragma unroll
+    for (int k = 0; k < SPL; ++k) {
+        if (lane + 32 * k < n) {
+            double a0, a1;
+            weighted_log_prob(x[k], s, lw0, lw1, ld0, ld1, &a0, &a1);
+            if (!(a1 > a0)) {                 // component 0 == foreground (loss.py:206)
+                const double sc = logsumexp2(a0, a1);
+                any_fg = true;
+                if (sc > best_score) {        // k ascending => first index among equals kept
+                    best_score = sc;
+                    best_idx = lane + 32 * k;
+                }
+            }
+        }
+    }
+    // warp arg-max with smallest index among equal scores
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double os = __shfl_xor_sync(PAA_FULL, best_score, o);
+        const int oi = __shfl_xor_sync(PAA_FULL, best_idx, o);
+        if (os > best_score || (os == best_score && oi < best_idx)) {
+            best_score = os;
+            best_idx = oi;
+        }
+    }
+    any_fg = __any_sync(PAA_FULL, any_fg);
+    if (out8 && lane == 0) {
+        out8[0] = s.w0;
+        out8[1] = s.w1;
+        out8[2] = s.mu0;
+        out8[3] = s.mu1;
+        out8[4] = (double)s.var0;
+        out8[5] = (double)s.var1;
+        out8[6] = (double)n_iter;
+        out8[7] = converged ? 1.0 : 0.0;
+    }
+    return any_fg ? best_idx + 1 : n;
+}
+
+template <int SPL>
+__global__ void __launch_bounds__(kSelWarps * PAA_WARP)
+select_gmm_kernel(const Geometry geo, const GtOffsets go, int num_gt_total,
+                  const float* __restrict__ gt_boxes, const int64_t* __restrict__ gt_labels,
+                  const LossScalars sc, const float4* __restrict__ tile_bbox,
+                  const int* __restrict__ matched, const float* __restrict__ score,
+                  const int* __restrict__ img_flags, int* __restrict__ paa_label,
+                  int* __restrict__ part_npos, double* __restrict__ part_siou,
+                  unsigned* __restrict__ ticket, double* __restrict__ local_norm,
+                  double* __restrict__ normalisers, const LossDebug dbg) {
+    __shared__ unsigned long long s_key[kSelWarps][PAA_MAX_CANDIDATES];
+    __shared__ unsigned long long s_sorted[kSelWarps][PAA_MAX_CANDIDATES];
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gi = blockIdx.x * kSelWarps + warp;
+    const int K = sc.topk;
+    const int cap = geo.num_levels * K;
+    int n_pos = 0;
+    double siou = 0.0;
+    if (gi < num_gt_total) {
+        // image of this GT
+        int n = 0;
+        for (int k = 1; k < geo.num_images; ++k)
+            if (gi >= go.v[k]) n = k;
+        const int g_local = gi - go.v[n];
+        const float4 gt = ldg4(gt_boxes + (size_t)gi * 4);
+        const int cls_label = (int)gt_labels[gi];
+        const bool nocull = (img_flags[n] & 1) || !(sc.iou_threshold > 0.0f);
+        const int* mrow = matched + (size_t)n * geo.A;
+        const float* srow = score + (size_t)n * geo.A;
+        unsigned long long* keys = s_key[warp];
+        int n_cand = 0;
+
+        if (cls_label > 0) {        // loss.py:166 requires a positive IoU label
+            for (int l = 0; l < geo.num_levels; ++l) {
+                const LevelView& lv = geo.lv[l];
+                const int t_end = (l + 1 < geo.num_levels) ? geo.lv[l + 1].tile_off : geo.tiles_per_image;
+                unsigned long long mine = kEmptyKey;   // lane j < K holds the j-th smallest key so far
+                for (int t0 = lv.tile_off; t0 < t_end; t0 += PAA_WARP) {
+                    const int t = t0 + lane;
+                    bool hit = false;
+                    if (t < t_end) {
+                        if (nocull) {
+                            hit = true;
+                        } else {
+                            const float4 bb = tile_bbox[(size_t)n * geo.tiles_per_image + t];
+                            float w = __fadd_rn(__fsub_rn(fminf(gt.z, bb.z), fmaxf(gt.x, bb.x)), 1.0f);
+                            float h = __fadd_rn(__fsub_rn(fminf(gt.w, bb.w), fmaxf(gt.y, bb.y)), 1.0f);
+                            hit = (w > 0.0f) && (h > 0.0f);
+                        }
+                    }
+                    unsigned tm = __ballot_sync(PAA_FULL, hit);
+                    while (tm) {
+                        const int tt = t0 + __ffs(tm) - 1;
+                        tm &= tm - 1;
+                        const int base = (tt - lv.tile_off) * PAA_TILE;
+                        int mv[PAA_TILE / PAA_WARP];
+#pragma unroll
+                        for (int r = 0; r < PAA_TILE / PAA_WARP; ++r) {
+                            const int i = base + r * PAA_WARP + lane;
+                            mv[r] = (i < lv.n_anchor) ? __ldg(mrow + lv.a_off + i) : -2;
+                        }
+#pragma unroll
+                        for (int r = 0; r < PAA_TILE / PAA_WARP; ++r) {
+                            const int i = base + r * PAA_WARP + lane;
+                            const bool is = (mv[r] == g_local);
+                            unsigned long long key = kEmptyKey;
+                            if (is) key = ((unsigned long long)ordered_bits(srow[lv.a_off + i]) << 32) |
+                                          (unsigned)(lv.a_off + i);
+                            unsigned hm = __ballot_sync(PAA_FULL, is);
+                            while (hm) {
+                                const int src = __ffs(hm) - 1;
+                                hm &= hm - 1;
+                                const unsigned long long nk = __shfl_sync(PAA_FULL, key, src);
+                                const unsigned less = __ballot_sync(PAA_FULL, lane < K && mine < nk);
+                                const int pos = __popc(less);
+                                const unsigned long long up = __shfl_up_sync(PAA_FULL, mine, 1);
+                                if (pos < K) {
+                                    if (lane == pos) mine = nk;
+                                    else if (lane > pos && lane < K) mine = up;
+                                }
+                            }
+                        }
+                    }
+                }
+                // append this level's candidates (ascending key) to the warp's list
+                const unsigned have = __ballot_sync(PAA_FULL, lane < K && mine != kEmptyKey);
+                const int cnt = __popc(have);
+                if (lane < cnt) keys[n_cand + lane] = mine;
+                n_cand += cnt;
+            }
+        }
+        __syncwarp();
+
+        // sort all candidates by (loss, index): rank by counting, n_cand <= cap <= 128
+        unsigned long long* sorted = s_sorted[warp];
+        for (int j = lane; j < n_cand; j += PAA_WARP) {
+            const unsigned long long kj = keys[j];
+            int rank = 0;
+            for (int q = 0; q < n_cand; ++q) rank += (keys[q] < kj) ? 1 : 0;
+            sorted[rank] = kj;
+        }
+        __syncwarp();
+
+        if (n_cand == 1) {
+            n_pos = 1;                                     // loss.py:218-219
+        } else if (n_cand > 1) {
+            float x[SPL];
+#pragma unroll
+            for (int k = 0; k < SPL; ++k) {
+                const int j = lane + 32 * k;
+                x[k] = (j < n_cand) ? from_ordered_bits((unsigned)(sorted[j] >> 32)) : 0.f;
+            }
+            n_pos = gmm_positive_prefix<SPL>(x, n_cand, lane, dbg.gmm ? dbg.gmm + (size_t)gi * 8 : nullptr);
+        }
+        if (dbg.gmm && n_cand <= 1 && lane < 8) dbg.gmm[(size_t)gi * 8 + lane] = 0.0;
+
+        // labels of the positive prefix + this GT's share of the IoU normaliser (loss.py:228-230,331-333)
+        for (int j = lane; j < n_cand; j += PAA_WARP) {
+            const int aidx = (int)(sorted[j] & 0xffffffffu);
+            if (dbg.cand_idx) dbg.cand_idx[(size_t)gi * cap + j] = aidx;
+            if (j < n_pos) {
+                paa_label[(size_t)n * geo.A + aidx] = cls_label;
+                if (dbg.paa_labels) dbg.paa_labels[(size_t)n * geo.A + aidx] = cls_label;
+                if (sc.use_iou_pred) {
+                    const int l = anchor_level(geo, aidx);
+                    const LevelView& lv = geo.lv[l];
+                    const int i = aidx - lv.a_off;
+                    const float4 a = ldg4(lv.anchors + (size_t)n * geo.anchor_image_stride + (size_t)i * 4);
+                    const AnchorFrame f = anchor_frame(a);
+                    const float* rp = lv.reg + head_offset(n, i, 0, 4, geo.apl, lv.hw);
+                    const float4 d = make_float4(__ldg(rp), __ldg(rp + lv.hw), __ldg(rp + 2 * (size_t)lv.hw),
+                                                 __ldg(rp + 3 * (size_t)lv.hw));
+                    const float4 pred = decode_box(d, f);
+                    const float4 tgt = decode_box(encode_box(gt, f), f);
+                    siou += (double)iou_plus1(tgt, area_plus1(tgt), pred, area_plus1(pred));
+                }
+            }
+        }
+        siou = warp_sum(siou);
+        if (lane == 0) {
+            part_npos[gi] = n_pos;
+            part_siou[gi] = siou;
+            if (dbg.cand_cnt) dbg.cand_cnt[gi] = n_cand;
+            if (dbg.num_pos) dbg.num_pos[gi] = n_pos;
+        }
+    }
+
+    // the last warp to finish folds the per-GT partials in a fixed order (deterministic sums)
+    const unsigned total_warps = gridDim.x * kSelWarps;
+    unsigned my_ticket = 0;
+    if (lane == 0) {
+        __threadfence();
+        my_ticket = atomicAdd(&ticket[0], 1u);
+    }
+    my_ticket = __shfl_sync(PAA_FULL, my_ticket, 0);
+    if (my_ticket == total_warps - 1) {
+        __threadfence();
+        double cnt = 0.0, sum = 0.0;
+        for (int g = lane; g < num_gt_total; g += PAA_WARP) {
+            cnt += (double)__ldcg(part_npos + g);
+            sum += __ldcg(part_siou + g);
+        }
+        cnt = warp_sum(cnt);
+        sum = warp_sum(sum);
+        if (lane == 0) {
+            local_norm[0] = cnt;
+            local_norm[1] = sum;
+            normalisers[0] = cnt;
+            normalisers[1] = sum;
+        }
+    }
+}
+
+int launch_select_gmm(const Geometry& geo, const GtOffsets& go, int num_gt_total, const float* gt_boxes,
+                      const int64_t* gt_labels, const LossScalars& sc, const LossWorkspace& ws,
+                      const float* score_src, double* normalisers, const LossDebug& dbg,
+                      cudaStream_t stream) {
+    const int cap = geo.num_levels * sc.topk;
+    const int grid = (num_gt_total + kSelWarps - 1) / kSelWarps;
+    const int threads = kSelWarps * PAA_WARP;
+#define PAA_SEL_LAUNCH(SPL)                                                                           \
+    select_gmm_kernel<SPL><<<grid, threads, 0, stream>>>(geo, go, num_gt_total, gt_boxes, gt_labels, sc, \
+        ws.tile_bbox, ws.matched, score_src, ws.img_flags, ws.paa_label, ws.part_npos, ws.part_siou,  \
+        ws.ticket, ws.local_norm, normalisers, dbg)
+    if (cap <= 32) PAA_SEL_LAUNCH(1);
+    else if (cap <= 64) PAA_SEL_LAUNCH(2);
+    else PAA_SEL_LAUNCH(4);
+#undef PAA_SEL_LAUNCH
+    PAA_LAUNCH_CHECK("select_gmm_kernel");
+    return 0;
+}
+
+}  // namespace paa

@@ -1,0 +1,46 @@
+// Internal launcher declarations (one per kernel family).  Not a public header.
+#pragma once
+#include "common.cuh"
+#include "layout.h"
+
+namespace paa {
+
+struct LossScalars {
+    float gamma, alpha, iou_threshold, reg_loss_weight, iou_loss_weight;
+    int topk, use_iou_pred, world_size;
+};
+
+struct LossDebug {
+    int* matched_idx;
+    int* iou_labels;
+    float* combined_loss;
+    int* cand_idx;
+    int* cand_cnt;
+    int* num_pos;
+    double* gmm;
+    int* paa_labels;
+};
+
+// assign.cu
+int launch_iou_best(const Geometry& geo, const GtOffsets& go, const float* gt_boxes,
+                    const LossWorkspace& ws, cudaStream_t stream);
+int launch_match_score(const Geometry& geo, const GtOffsets& go, const float* gt_boxes,
+                       const int64_t* gt_labels, const LossScalars& sc, const LossWorkspace& ws,
+                       const LossDebug& dbg, cudaStream_t stream);
+int launch_select_gmm(const Geometry& geo, const GtOffsets& go, int num_gt_total, const float* gt_boxes,
+                      const int64_t* gt_labels, const LossScalars& sc, const LossWorkspace& ws,
+                      const float* score_src, double* normalisers, const LossDebug& dbg,
+                      cudaStream_t stream);
+
+// loss.cu
+int loss_grid_blocks(int num_images, int tiles_per_image);
+int launch_final_loss(const Geometry& geo, const GtOffsets& go, const float* gt_boxes,
+                      const LossScalars& sc, const LossWorkspace& ws, const double* normalisers,
+                      const float* grad_losses, float* losses, bool write_grads, cudaStream_t stream);
+int launch_rescale_grads(const Geometry& geo, const float* old_g, const float* new_g, cudaStream_t stream);
+int launch_focal_forward(const float* logits, const int* targets, int n, int C, float gamma, float alpha,
+                         float* losses, cudaStream_t stream);
+int launch_focal_backward(const float* logits, const int* targets, const float* d_losses, int n, int C,
+                          float gamma, float alpha, float* d_logits, cudaStream_t stream);
+
+}  // namespace paa

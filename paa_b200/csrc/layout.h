@@ -1,0 +1,60 @@
+// Host-side workspace carving shared by the entry points.  Not a public header.
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+
+namespace paa {
+
+inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+// Workspace of the assign+loss path.  The first `zero_bytes` are cleared by one memset at the start
+// of paa_assign (per-GT IoU maxima, image flags, the completion ticket); everything else is fully
+// overwritten by the kernels before it is read.
+struct LossWorkspace {
+    // zeroed region
+    unsigned* gtmax;        // [sumG]   bit pattern of the per-GT maximal IoU
+    int* img_flags;         // [N]      bit0: some GT of the image overlaps no anchor (culling off)
+    unsigned* ticket;       // [4]      completion counters
+    size_t zero_bytes;
+    // plain region
+    uint2* best;            // [N*A]    (IoU bits, GT index) of every anchor's best GT
+    int* matched;           // [N*A]
+    float* score;           // [N*A]    anchor score (combined loss) of IoU-positive anchors
+    int* paa_label;         // [N*A]
+    float4* tile_bbox;      // [N*T]
+    int* part_npos;         // [sumG]
+    double* part_siou;      // [sumG]
+    double* local_norm;     // [2]      this rank's {num_pos, sum_iou} (before the all-reduce)
+    double* block_part;     // [blocks*3] per-block partial loss sums of the final kernel
+    size_t total_bytes;
+};
+
+inline LossWorkspace carve_loss_workspace(void* base, int N, int A, int sumG, int tiles_per_image,
+                                          int loss_blocks) {
+    LossWorkspace w;
+    char* p = static_cast<char*>(base);
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        char* q = p ? p + off : nullptr;
+        off += align_up(bytes);
+        return q;
+    };
+    w.gtmax = reinterpret_cast<unsigned*>(take(sizeof(unsigned) * (size_t)(sumG > 0 ? sumG : 1)));
+    w.img_flags = reinterpret_cast<int*>(take(sizeof(int) * (size_t)N));
+    w.ticket = reinterpret_cast<unsigned*>(take(sizeof(unsigned) * 4));
+    w.zero_bytes = off;
+    size_t NA = (size_t)N * A;
+    w.best = reinterpret_cast<uint2*>(take(sizeof(uint2) * NA));
+    w.matched = reinterpret_cast<int*>(take(sizeof(int) * NA));
+    w.score = reinterpret_cast<float*>(take(sizeof(float) * NA));
+    w.paa_label = reinterpret_cast<int*>(take(sizeof(int) * NA));
+    w.tile_bbox = reinterpret_cast<float4*>(take(sizeof(float4) * (size_t)N * tiles_per_image));
+    w.part_npos = reinterpret_cast<int*>(take(sizeof(int) * (size_t)(sumG > 0 ? sumG : 1)));
+    w.part_siou = reinterpret_cast<double*>(take(sizeof(double) * (size_t)(sumG > 0 ? sumG : 1)));
+    w.local_norm = reinterpret_cast<double*>(take(sizeof(double) * 2));
+    w.block_part = reinterpret_cast<double*>(take(sizeof(double) * 3 * (size_t)loss_blocks));
+    w.total_bytes = off;
+    return w;
+}
+
+}  // namespace paa

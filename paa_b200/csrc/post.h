@@ -1,0 +1,15 @@
+// Internal declarations of the post-processing path.  Not a public header.
+#pragma once
+#include "common.cuh"
+
+namespace paa {
+
+size_t post_workspace_bytes(int num_images, int anchors_per_image, int num_classes, int num_levels,
+                            int pre_nms_top_n);
+int run_postprocess(const Geometry& geo, const PaaPostArgs* args, cudaStream_t stream);
+
+size_t ml_nms_workspace_bytes(int n);
+int run_ml_nms(const float* boxes, const float* scores, const float* labels, int n, float thresh,
+               uint8_t* keep, int32_t* num_keep, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
+}  // namespace paa

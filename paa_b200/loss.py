@@ -1,0 +1,274 @@
+"""PAALossComputation -- the reference's training-side entry point for the PAA hot path, backed by
+libpaa_b200.so.
+
+Mirror of paa_core/modeling/rpn/paa/loss.py: same constructor ``(cfg, box_coder)``, same call
+signature ``(box_cls, box_regression, iou_pred, targets, anchors, locations)``, same return value
+(a list of 0-dim float32 losses ``[loss_cls, loss_reg(, loss_iou_pred)]`` that back-propagate into
+the three prediction lists), same exceptions (``ValueError`` for an image without ground truth,
+matcher.py:53-58; ``RuntimeError`` when a target's image size differs from its anchors',
+boxlist_ops.py:95-97).  The Python here only extracts device pointers and sizes; all arithmetic is
+in the CUDA kernels reached through the C ABI of include/paa_b200.h.  There is no CPU path.
+
+Multi-GPU: ranks own disjoint images.  Like the reference (loss.py:18-28) the world size is the
+``WORLD_SIZE`` environment variable; with more than one rank the two normalisers are summed with a
+single 2-element all-reduce between ``paa_assign`` and ``paa_loss`` (the reference issues two
+all-reduces followed by ``.item()`` host syncs, loss.py:321,338).
+"""
+import ctypes as C
+import os
+
+import torch
+
+from paa_b200 import _lib
+from paa_b200.box_coder import coder_regression_type
+from paa_b200.config import scalar
+
+
+def get_num_gpus():
+    return int(os.environ["WORLD_SIZE"]) if "WORLD_SIZE" in os.environ else 1   # loss.py:18-19
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _head(t, name):
+    if not t.is_cuda:
+        raise RuntimeError("paa_b200 has no CPU path: %s is on %s" % (name, t.device))
+    if t.dtype != torch.float32:
+        raise RuntimeError("%s must be float32, got %s" % (name, t.dtype))
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def gather_levels(box_cls, box_regression, iou_pred, anchors):
+    """Validates the head lists / anchor lists and returns contiguous tensors plus layout facts.
+    anchors: list[N] of list[L] BoxList (anchor_generator.py:112-125)."""
+    L = len(box_cls)
+    if L == 0 or len(box_regression) != L or (iou_pred is not None and len(iou_pred) != L):
+        raise RuntimeError("box_cls / box_regression / iou_pred must list the same levels")
+    if L > _lib.MAX_LEVELS:
+        raise RuntimeError("at most %d levels are supported" % _lib.MAX_LEVELS)
+    N = box_cls[0].shape[0]
+    if len(anchors) != N:
+        raise RuntimeError("anchors lists %d images, heads have batch %d" % (len(anchors), N))
+    apl = box_regression[0].shape[1] // 4
+    num_classes = box_cls[0].shape[1] // apl
+    cls = [_head(t, "box_cls") for t in box_cls]
+    reg = [_head(t, "box_regression") for t in box_regression]
+    iou = None if iou_pred is None else [_head(t, "iou_pred") for t in iou_pred]
+    hw = []
+    for l in range(L):
+        n, ch, h, w = cls[l].shape
+        if n != N or ch != apl * num_classes or reg[l].shape != (N, apl * 4, h, w) or \
+                (iou is not None and iou[l].shape != (N, apl, h, w)):
+            raise RuntimeError("level %d: inconsistent head shapes" % l)
+        if len(anchors[0][l].bbox) != h * w * apl:
+            raise RuntimeError("level %d: %d anchors for a %dx%d map with %d per location"
+                               % (l, len(anchors[0][l].bbox), h, w, apl))
+        hw.append(h * w)
+    # every image normally shares the anchor tensors of the batch (anchor_generator.py:114-124)
+    shared = all(anchors[i][l].bbox.data_ptr() == anchors[0][l].bbox.data_ptr()
+                 for i in range(1, N) for l in range(L))
+    A = sum(hw) * apl
+    if shared:
+        anc = [anchors[0][l].bbox for l in range(L)]
+        anc = [a if (a.is_contiguous() and a.dtype == torch.float32) else a.contiguous().float() for a in anc]
+        for a in anc:
+            if not a.is_cuda:
+                raise RuntimeError("paa_b200 has no CPU path: anchors are on %s" % a.device)
+        level_ptrs = [a.data_ptr() for a in anc]
+        stride = 0
+        keep = anc
+    else:
+        stacked = torch.stack([torch.cat([anchors[i][l].bbox for l in range(L)], dim=0)
+                               for i in range(N)], dim=0).float().contiguous()      # [N, A, 4]
+        if not stacked.is_cuda:
+            raise RuntimeError("paa_b200 has no CPU path: anchors are on %s" % stacked.device)
+        offs, o = [], 0
+        for l in range(L):
+            offs.append(o)
+            o += hw[l] * apl
+        level_ptrs = [stacked.data_ptr() + 16 * off for off in offs]
+        stride = A * 4
+        keep = [stacked]
+    return dict(L=L, N=N, apl=apl, C=num_classes, hw=hw, A=A, cls=cls, reg=reg, iou=iou,
+                anchor_ptrs=level_ptrs, anchor_stride=stride, keep=keep)
+
+
+class _PAALossFunction(torch.autograd.Function):
+    """losses[3] = f(heads); the gradients are produced by the same kernel pass as the losses and
+    handed out in backward (rescaled on the device if the upstream gradients are not ones)."""
+
+    @staticmethod
+    def forward(ctx, owner, targets, anchors, n_levels, has_iou, *heads):
+        box_cls = list(heads[:n_levels])
+        box_reg = list(heads[n_levels:2 * n_levels])
+        iou_pred = list(heads[2 * n_levels:3 * n_levels]) if has_iou else None
+        need_grad = any(ctx.needs_input_grad[5:])
+        losses, grads, call = owner._run(box_cls, box_reg, iou_pred, targets, anchors, need_grad)
+        ctx.owner = owner
+        ctx.call = call
+        ctx.grads = grads
+        ctx.n_levels = n_levels
+        ctx.has_iou = has_iou
+        return losses
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_losses):
+        grads = ctx.grads
+        if grads is None:
+            return (None,) * (5 + ctx.n_levels * (3 if ctx.has_iou else 2))
+        ctx.owner._rescale(ctx.call, grad_losses.contiguous().float())
+        out = list(grads["cls"]) + list(grads["reg"]) + (list(grads["iou"]) if ctx.has_iou else [])
+        return (None, None, None, None, None) + tuple(out)
+
+
+class PAALossComputation(object):
+    """Drop-in for paa_core.modeling.rpn.paa.loss.PAALossComputation (loss.py:31-359)."""
+
+    def __init__(self, cfg, box_coder):
+        self.cfg = cfg
+        paa = cfg.MODEL.PAA
+        self.gamma = scalar(paa.LOSS_GAMMA)
+        self.alpha = scalar(paa.LOSS_ALPHA)
+        self.iou_threshold = float(paa.IOU_THRESHOLD)
+        self.topk = int(paa.TOPK)
+        self.box_coder = box_coder
+        self.fpn_strides = [8, 16, 32, 64, 128]
+        self.reg_loss_type = paa.REG_LOSS_TYPE
+        self.iou_loss_weight = float(paa.IOU_LOSS_WEIGHT)
+        self.reg_loss_weight = float(paa.REG_LOSS_WEIGHT)
+        if "iou" not in self.reg_loss_type:
+            # the reference's only other branch ('smoothl1') is dead code (loss.py:246-251 passes
+            # arguments smooth_l1_loss does not take)
+            raise NotImplementedError("REG_LOSS_TYPE %r: only 'iou' is supported" % (self.reg_loss_type,))
+        if coder_regression_type(box_coder) != "BOX":
+            raise NotImplementedError("only the 'BOX' BoxCoder regression type is supported")
+        self._lib = _lib.load()          # raises if the CUDA library is missing
+        self.debug = False               # True: keep per-stage parity outputs of the last call
+        self.last_debug = None
+        self.teacher_combined_loss = None   # [N, A] float32 cuda tensor: stage-wise parity protocol
+        self._workspace = None
+        self._ones = None
+
+    # -- plumbing -------------------------------------------------------------------------------
+    def _workspace_for(self, device, nbytes):
+        ws = self._workspace
+        if ws is None or ws.device != device or ws.numel() < nbytes:
+            ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=device)
+            self._workspace = ws
+        return ws
+
+    def _run(self, box_cls, box_reg, iou_pred, targets, anchors, need_grad):
+        lv = gather_levels(box_cls, box_reg, iou_pred, anchors)
+        N, L, A = lv["N"], lv["L"], lv["A"]
+        device = lv["cls"][0].device
+        if len(targets) != N:
+            raise RuntimeError("targets lists %d images, heads have batch %d" % (len(targets), N))
+        if N > _lib.MAX_IMAGES:
+            raise RuntimeError("at most %d images per call" % _lib.MAX_IMAGES)
+        offsets = [0]
+        for i, t in enumerate(targets):
+            assert t.mode == "xyxy"                                   # loss.py:97
+            if tuple(t.size) != tuple(anchors[i][0].size):            # boxlist_ops.py:95-97
+                raise RuntimeError("boxlists should have same image size, got {}, {}".format(t, anchors[i][0]))
+            offsets.append(offsets[-1] + len(t))
+        gt_boxes = torch.cat([t.bbox for t in targets], dim=0).to(device=device, dtype=torch.float32).contiguous()
+        gt_labels = torch.cat([t.get_field("labels") for t in targets], dim=0).to(device=device,
+                                                                                dtype=torch.int64).contiguous()
+        sum_g = offsets[-1]
+        has_iou = iou_pred is not None
+        world = get_num_gpus()
+
+        args = _lib.PaaLossArgs()
+        args.num_images, args.num_levels, args.num_classes = N, L, lv["C"]
+        args.anchors_per_loc, args.topk = lv["apl"], self.topk
+        args.use_iou_pred, args.world_size = int(has_iou), world
+        args.gamma, args.alpha, args.iou_threshold = self.gamma, self.alpha, self.iou_threshold
+        args.reg_loss_weight, args.iou_loss_weight = self.reg_loss_weight, self.iou_loss_weight
+        args.anchor_image_stride = lv["anchor_stride"]
+        grads = None
+        if need_grad:
+            grads = dict(cls=[torch.empty_like(t) for t in lv["cls"]],
+                         reg=[torch.empty_like(t) for t in lv["reg"]],
+                         iou=[torch.empty_like(t) for t in lv["iou"]] if has_iou else None)
+        for l in range(L):
+            s = args.levels[l]
+            s.box_cls, s.box_regression = lv["cls"][l].data_ptr(), lv["reg"][l].data_ptr()
+            s.iou_pred = lv["iou"][l].data_ptr() if has_iou else None
+            s.anchors = lv["anchor_ptrs"][l]
+            s.hw = lv["hw"][l]
+            if grads is not None:
+                s.grad_box_cls, s.grad_box_regression = grads["cls"][l].data_ptr(), grads["reg"][l].data_ptr()
+                s.grad_iou_pred = grads["iou"][l].data_ptr() if has_iou else None
+        args.gt_boxes, args.gt_labels = gt_boxes.data_ptr(), gt_labels.data_ptr()
+        for i, o in enumerate(offsets):
+            args.gt_offsets[i] = o
+        nbytes = self._lib.paa_loss_workspace_bytes(N, A, sum_g, L, self.topk)
+        ws = self._workspace_for(device, nbytes)
+        base = (ws.data_ptr() + 255) // 256 * 256
+        args.workspace, args.workspace_bytes = base, ws.numel() - (base - ws.data_ptr())
+        normalisers = torch.empty(2, dtype=torch.float64, device=device)
+        losses = torch.empty(3, dtype=torch.float32, device=device)
+        args.normalisers, args.losses, args.grad_losses = normalisers.data_ptr(), losses.data_ptr(), None
+        dbg = None
+        if self.debug:
+            cap = L * self.topk
+            dbg = dict(matched_idx=torch.empty((N, A), dtype=torch.int32, device=device),
+                       iou_labels=torch.empty((N, A), dtype=torch.int32, device=device),
+                       combined_loss=torch.empty((N, A), dtype=torch.float32, device=device),
+                       cand_idx=torch.full((sum_g, cap), -1, dtype=torch.int32, device=device),
+                       cand_cnt=torch.zeros(sum_g, dtype=torch.int32, device=device),
+                       num_pos=torch.zeros(sum_g, dtype=torch.int32, device=device),
+                       gmm=torch.zeros((sum_g, 8), dtype=torch.float64, device=device),
+                       paa_labels=torch.empty((N, A), dtype=torch.int32, device=device))
+            args.dbg_matched_idx, args.dbg_iou_labels = dbg["matched_idx"].data_ptr(), dbg["iou_labels"].data_ptr()
+            args.dbg_combined_loss, args.dbg_cand_idx = dbg["combined_loss"].data_ptr(), dbg["cand_idx"].data_ptr()
+            args.dbg_cand_cnt, args.dbg_num_pos = dbg["cand_cnt"].data_ptr(), dbg["num_pos"].data_ptr()
+            args.dbg_gmm, args.dbg_paa_labels = dbg["gmm"].data_ptr(), dbg["paa_labels"].data_ptr()
+        teacher = self.teacher_combined_loss
+        if teacher is not None:
+            teacher = teacher.to(device=device, dtype=torch.float32).contiguous()
+            assert teacher.shape == (N, A)
+            args.teacher_combined_loss = teacher.data_ptr()
+        stream = torch.cuda.current_stream(device).cuda_stream
+        with torch.cuda.device(device):
+            if world > 1:
+                import torch.distributed as dist
+                _lib.check(self._lib.paa_assign(C.byref(args), stream), "paa_assign")
+                dist.all_reduce(normalisers, op=dist.ReduceOp.SUM)      # loss.py:321,338 in one message
+                _lib.check(self._lib.paa_loss(C.byref(args), stream), "paa_loss")
+            else:
+                _lib.check(self._lib.paa_assign_loss(C.byref(args), stream), "paa_assign_loss")
+        if dbg is not None:
+            dbg["normalisers"] = normalisers
+            dbg["gt_offsets"] = offsets
+            self.last_debug = dbg
+        # keep every tensor whose pointer the kernels use alive until the stream work is enqueued
+        call = dict(args=args, keep=(lv, gt_boxes, gt_labels, ws, normalisers, teacher), device=device)
+        return losses, grads, call
+
+    def _rescale(self, call, grad_losses):
+        device = call["device"]
+        if self._ones is None or self._ones.device != device:
+            self._ones = torch.ones(3, dtype=torch.float32, device=device)
+        stream = torch.cuda.current_stream(device).cuda_stream
+        with torch.cuda.device(device):
+            _lib.check(self._lib.paa_rescale_grads(C.byref(call["args"]), self._ones.data_ptr(),
+                                                   grad_losses.data_ptr(), stream), "paa_rescale_grads")
+
+    # -- the reference's interface --------------------------------------------------------------
+    def __call__(self, box_cls, box_regression, iou_pred, targets, anchors, locations=None):
+        n_levels = len(box_cls)
+        has_iou = iou_pred is not None
+        heads = list(box_cls) + list(box_regression) + (list(iou_pred) if has_iou else [])
+        losses = _PAALossFunction.apply(self, targets, anchors, n_levels, has_iou, *heads)
+        res = [losses[0], losses[1]]
+        if has_iou:
+            res.append(losses[2])
+        return res
+
+
+def make_paa_loss_evaluator(cfg, box_coder):
+    return PAALossComputation(cfg, box_coder)      # loss.py:362-364

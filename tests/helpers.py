@@ -29,3 +29,57 @@ def flat_levels(ts):
     """list of [N,C,H,W] -> numpy [N, A, C] in the reference's flattened anchor order."""
     return np.concatenate([t.detach().cpu().permute(0, 2, 3, 1).reshape(t.shape[0], -1, t.shape[1]).numpy()
                            for t in ts], axis=1)
+
+
+def to_device_inputs(batch, device="cuda", requires_grad=False):
+    """SyntheticBatch -> (box_cls, box_regression, iou_pred, targets, anchors) in the reference's API
+    shapes, on the device, with the per-level anchor tensors shared by all images like
+    anchor_generator.py:112-125 does."""
+    from paa_b200.structures import BoxList
+    cls = [t.to(device).requires_grad_(requires_grad) for t in batch.box_cls]
+    reg = [t.to(device).requires_grad_(requires_grad) for t in batch.box_regression]
+    iou = [t.to(device).requires_grad_(requires_grad) for t in batch.iou_pred]
+    anc = [a.to(device) for a in batch.anchors]
+    targets, anchors = [], []
+    for i in range(batch.num_images):
+        t = BoxList(batch.gt_boxes[i].to(device), batch.image_sizes[i], mode="xyxy")
+        t.add_field("labels", batch.gt_labels[i].to(device))
+        targets.append(t)
+        anchors.append([BoxList(a, batch.image_sizes[i], mode="xyxy") for a in anc])
+    return cls, reg, iou, targets, anchors
+
+
+def topk_tie_exempt(oracle_asg, rel=1e-5):
+    """Exemption (i) of SURVEY.md 8c: (image, gt) pairs for which, on some level, the k-th and
+    (k+1)-th smallest oracle loss among the GT's anchors are closer than `rel` relative, so the
+    top-k membership is decided by rounding noise."""
+    exempt = set()
+    prm = oracle_asg.params
+    N, A = oracle_asg.N, oracle_asg.A
+    loss = oracle_asg.combined_loss.numpy()
+    matched = oracle_asg.matched_idx.numpy()
+    for i in range(N):
+        n_gt = int(matched[i].max()) + 1
+        start = 0
+        for n_l in oracle_asg.level_sizes:
+            m = matched[i, start:start + n_l]
+            v = loss[i, start:start + n_l]
+            for g in range(n_gt):
+                x = np.sort(v[m == g])
+                if x.shape[0] > prm.topk:
+                    a, b = x[prm.topk - 1], x[prm.topk]
+                    if abs(b - a) <= rel * max(abs(a), abs(b)):
+                        exempt.add((i, g))
+            start += n_l
+    return exempt
+
+
+def gmm_tie_exempt(oracle_asg, abs_tol=1e-5):
+    """Exemption (ii): GTs whose two best foreground scores are within abs_tol (structural ties)."""
+    from oracle import gmm_oracle
+    exempt = set()
+    for i, recs in enumerate(oracle_asg.gmm_records):
+        for r in recs:
+            if r.get("fit") is not None and gmm_oracle.structural_tie_margin(r["fit"]) < abs_tol:
+                exempt.add((i, r["gt"]))
+    return exempt

@@ -170,6 +170,24 @@ int paa_sigmoid_focal_loss_backward(const float* logits, const int32_t* targets,
                                     int n, int num_classes, float gamma, float alpha, float* d_logits,
                                     void* stream);
 
+/* Measurement aid (not on the reference's interface): while enabled, every launch of the chosen kernel
+ * is bracketed by CUDA events on its own stream; paa_kernel_timing_end waits for them and returns the
+ * summed device time and the number of launches.  Do not enable during CUDA-graph capture. */
+#define PAA_KERNEL_IOU_BEST     1
+#define PAA_KERNEL_MATCH_SCORE  2
+#define PAA_KERNEL_SELECT_GMM   3
+#define PAA_KERNEL_FINAL_LOSS   4
+#define PAA_KERNEL_POST_CANDIDATES 10
+#define PAA_KERNEL_POST_FILTER  11
+#define PAA_KERNEL_POST_SELECT  12
+#define PAA_KERNEL_POST_RANK    13
+#define PAA_KERNEL_POST_NMS_MASK 14
+#define PAA_KERNEL_POST_NMS_SCAN 15
+#define PAA_KERNEL_POST_FINISH  16
+#define PAA_KERNEL_POST_VOTE    17
+int paa_kernel_timing_begin(int kernel_id);
+int paa_kernel_timing_end(float* total_ms, int32_t* launches);
+
 #ifdef __cplusplus
 }
 #endif

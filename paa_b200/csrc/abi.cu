@@ -17,6 +17,28 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+// ---- per-kernel event timing (measurement aid) ------------------------------------------------
+static const int kMaxTimed = 4096;
+static int g_timed_kernel = 0;
+static int g_timed_count = 0;
+static cudaEvent_t g_ev0[kMaxTimed], g_ev1[kMaxTimed];
+static int g_ev_created = 0;
+
+KernelTimer::KernelTimer(int kernel_id, cudaStream_t stream) : stream_(stream), slot_(-1) {
+    if (kernel_id != g_timed_kernel || g_timed_count >= kMaxTimed) return;
+    slot_ = g_timed_count++;
+    while (g_ev_created <= slot_) {
+        cudaEventCreate(&g_ev0[g_ev_created]);
+        cudaEventCreate(&g_ev1[g_ev_created]);
+        ++g_ev_created;
+    }
+    cudaEventRecord(g_ev0[slot_], stream_);
+}
+
+KernelTimer::~KernelTimer() {
+    if (slot_ >= 0) cudaEventRecord(g_ev1[slot_], stream_);
+}
+
 static int tiles_of(int n_anchor) { return (n_anchor + PAA_TILE - 1) / PAA_TILE; }
 
 // Validates the caller's description of the head tensors and builds the kernel-side view.
@@ -250,6 +272,27 @@ int paa_postprocess(const PaaPostArgs* args, void* stream) {
                             args->anchor_image_stride, args->levels, false, &geo);
     if (rc) return rc;
     return run_postprocess(geo, args, static_cast<cudaStream_t>(stream));
+}
+
+int paa_kernel_timing_begin(int kernel_id) {
+    g_timed_kernel = kernel_id;
+    g_timed_count = 0;
+    return 0;
+}
+
+int paa_kernel_timing_end(float* total_ms, int32_t* launches) {
+    float total = 0.0f;
+    for (int i = 0; i < g_timed_count; ++i) {
+        PAA_CUDA_CHECK(cudaEventSynchronize(g_ev1[i]));
+        float ms = 0.0f;
+        PAA_CUDA_CHECK(cudaEventElapsedTime(&ms, g_ev0[i], g_ev1[i]));
+        total += ms;
+    }
+    if (total_ms) *total_ms = total;
+    if (launches) *launches = g_timed_count;
+    g_timed_kernel = 0;
+    g_timed_count = 0;
+    return 0;
 }
 
 size_t paa_ml_nms_workspace_bytes(int n) { return ml_nms_workspace_bytes(n); }

@@ -107,6 +107,7 @@ iou_best_kernel(const Geometry geo, const GtOffsets go, const float* __restrict_
 int launch_iou_best(const Geometry& geo, const GtOffsets& go, const float* gt_boxes,
                     const LossWorkspace& ws, cudaStream_t stream) {
     int grid = geo.num_images * geo.tiles_per_image;
+    KernelTimer timer(PAA_KERNEL_IOU_BEST, stream);
     iou_best_kernel<<<grid, PAA_TILE, 0, stream>>>(geo, go, gt_boxes, ws.gtmax, ws.best, ws.tile_bbox);
     PAA_LAUNCH_CHECK("iou_best_kernel");
     return 0;
@@ -121,29 +122,27 @@ int launch_iou_best(const Geometry& geo, const GtOffsets& go, const float* gt_bo
 //   (loss.py:293-306; anchors without an IoU-positive label are never candidates, their 1e8 filler
 //   is not materialised).
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ float focal_sum_accurate(const float* __restrict__ p, int stride, int C, int label,
-                                                    float gamma, float alpha) {
-    float sum = 0.0f;
+// sum_c focal(x_c | label) for one anchor; `p` points at class 0, consecutive classes are `stride` apart.
+// Loads are issued eight at a time before any of them is consumed.
+__device__ __forceinline__ float focal_sum(const float* __restrict__ p, int stride, int C, int label,
+                                           float gamma, float alpha) {
     const bool g2 = (gamma == 2.0f);
-#pragma unroll 8
-    for (int c = 0; c < C; ++c) {
-        const float x = __ldg(p + (size_t)c * stride);
-        const float e = expf(-fabsf(x));
-        const float l1p = log1pf(e);
-        const float inv = 1.0f / (1.0f + e);
-        const float pr = (x >= 0.0f) ? inv : e * inv;          // sigmoid(x)
-        const float qr = (x >= 0.0f) ? e * inv : inv;          // 1 - sigmoid(x)
-        float term;
-        if (c + 1 == label) {
-            const float nlogp = fmaxf(-x, 0.0f) + l1p;         // -log(p)
-            const float mod = g2 ? qr * qr : powf(qr, gamma);
-            term = alpha * mod * nlogp;
-        } else {
-            const float nlogq = fmaxf(x, 0.0f) + l1p;          // -log(1-p)
-            const float mod = g2 ? pr * pr : powf(pr, gamma);
-            term = (1.0f - alpha) * mod * nlogq;
+    const float oma = 1.0f - alpha;
+    float sum = 0.0f;
+    for (int c0 = 0; c0 < C; c0 += 8) {
+        float x[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] = (c0 + j < C) ? __ldg(p + (size_t)(c0 + j) * stride) : 0.0f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (c0 + j < C) {
+                const SigmoidParts sp = sigmoid_parts(x[j]);
+                float term, grad;
+                if (c0 + j + 1 == label) focal_positive(x[j], sp, gamma, g2, alpha, &term, &grad);
+                else focal_negative(x[j], sp, gamma, g2, oma, &term, &grad);
+                sum += term;
+            }
         }
-        sum += term;
     }
     return sum;
 }
@@ -214,7 +213,7 @@ match_score_kernel(const Geometry geo, const GtOffsets go, const float* __restri
     float s = 1.0e8f;   // loss.py:15,301-306 filler, only visible through the debug output
     if (m >= 0 && label > 0) {
         const float* cls = lv.cls + head_offset(n, i, 0, geo.C, geo.apl, lv.hw);
-        const float fsum = focal_sum_accurate(cls, lv.hw, geo.C, label, sc.gamma, sc.alpha);
+        const float fsum = focal_sum(cls, lv.hw, geo.C, label, sc.gamma, sc.alpha);
         const float* rp = lv.reg + head_offset(n, i, 0, 4, geo.apl, lv.hw);
         const float4 d = make_float4(__ldg(rp), __ldg(rp + lv.hw), __ldg(rp + 2 * (size_t)lv.hw),
                                      __ldg(rp + 3 * (size_t)lv.hw));
@@ -232,6 +231,7 @@ int launch_match_score(const Geometry& geo, const GtOffsets& go, const float* gt
                        const int64_t* gt_labels, const LossScalars& sc, const LossWorkspace& ws,
                        const LossDebug& dbg, cudaStream_t stream) {
     int grid = geo.num_images * geo.tiles_per_image;
+    KernelTimer timer(PAA_KERNEL_MATCH_SCORE, stream);
     match_score_kernel<<<grid, PAA_TILE, 0, stream>>>(geo, go, gt_boxes, gt_labels, ws.gtmax, ws.best, sc,
                                                       ws.matched, ws.score, ws.paa_label, ws.img_flags, dbg);
     PAA_LAUNCH_CHECK("match_score_kernel");
@@ -258,6 +258,24 @@ __device__ __forceinline__ double logsumexp2(double a0, double a1) {
     if (a0 == a1) return (log1p(0.0) + 0.6931471805599453094) + a0;   // m = 2, masked sum = 0
     const double hi = fmax(a0, a1), lo = fmin(a0, a1);
     return (log1p(exp(lo - hi)) + 0.0) + hi;                          // m = 1, log(m) = 0
+}
+// Same, also returning the responsibilities exp(a_k - lse).  They are formed as 1/(1+s) and s/(1+s)
+// with s = exp(lo - hi): one exp and one division instead of three exps; the results differ from
+// sklearn's exp(a_k - lse) by a few 1e-16 relative, far below anything the float32 roundings of
+// the next E-step can see.
+__device__ __forceinline__ double logsumexp2_resp(double a0, double a1, double* r0, double* r1) {
+    if (a0 == a1) {
+        *r0 = 0.5;
+        *r1 = 0.5;
+        return (log1p(0.0) + 0.6931471805599453094) + a0;
+    }
+    const bool first_hi = a0 > a1;
+    const double hi = first_hi ? a0 : a1, lo = first_hi ? a1 : a0;
+    const double s = exp(lo - hi);
+    const double rh = 1.0 / (1.0 + s), rl = s * rh;
+    *r0 = first_hi ? rh : rl;
+    *r1 = first_hi ? rl : rh;
+    return (log1p(s) + 0.0) + hi;
 }
 
 struct GmmState {
@@ -333,9 +351,7 @@ __device__ int gmm_positive_prefix(const float (&x)[SPL], int n, int lane, doubl
             if (lane + 32 * k < n) {
                 double a0, a1;
                 weighted_log_prob(x[k], s, lw0, lw1, ld0, ld1, &a0, &a1);
-                const double lpn = logsumexp2(a0, a1);
-                r0[k] = exp(a0 - lpn);
-                r1[k] = exp(a1 - lpn);
+                const double lpn = logsumexp2_resp(a0, a1, &r0[k], &r1[k]);
                 s_r0 += r0[k];
                 s_r1 += r1[k];
                 s_r0x += r0[k] * (double)x[k];
@@ -605,6 +621,7 @@ int launch_select_gmm(const Geometry& geo, const GtOffsets& go, int num_gt_total
     const int cap = geo.num_levels * sc.topk;
     const int grid = (num_gt_total + kSelWarps - 1) / kSelWarps;
     const int threads = kSelWarps * PAA_WARP;
+    KernelTimer timer(PAA_KERNEL_SELECT_GMM, stream);
 #define PAA_SEL_LAUNCH(SPL)                                                                           \
     select_gmm_kernel<SPL><<<grid, threads, 0, stream>>>(geo, go, num_gt_total, gt_boxes, gt_labels, sc, \
         ws.tile_bbox, ws.matched, score_src, ws.img_flags, ws.paa_label, ws.part_npos, ws.part_siou,  \

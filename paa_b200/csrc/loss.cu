@@ -15,7 +15,8 @@ namespace paa {
 
 constexpr int kFinalThreads = PAA_TILE;
 
-int loss_grid_blocks(int num_images, int tiles_per_image) { return num_images * tiles_per_image; }
+// upper bound of blocks the final kernel launches (sizes the partial-sum buffer); 64 class chunks cover C <= 1024
+int loss_grid_blocks(int num_images, int tiles_per_image) { return num_images * tiles_per_image * 64; }
 
 struct GradScales {
     float cls, reg, bce;     // d(total)/d(sum) factors
@@ -107,15 +108,27 @@ __device__ __forceinline__ float giou_loss_and_grad(float4 d, const AnchorFrame&
     return loss;
 }
 
-// One thread = one anchor (all of them): 80 logits in, 80 gradients out.
+// One block = 128 consecutive anchors of one level of one image x one chunk of kClsChunk classes;
+// one thread = one anchor.  Every logit of the chunk is read once (a warp reads one 128-byte line per
+// class) and its gradient written once.  All classes are first treated as negatives; the single
+// positive class of a positive anchor is patched afterwards.  The chunk-0 block of a tile also
+// handles the regression / IoU-prediction losses and gradients of its anchors.
+constexpr int kClsChunk = 16;
+constexpr int kClsBatch = 8;
+
+int loss_class_chunks(int C) { return (C + kClsChunk - 1) / kClsChunk; }
+
+template <bool kGrads>
 __global__ void __launch_bounds__(kFinalThreads)
 final_loss_kernel(const Geometry geo, const GtOffsets go, const float* __restrict__ gt_boxes,
                   const LossScalars sc, const int* __restrict__ paa_label, const int* __restrict__ matched,
                   const double* __restrict__ norm, const double* __restrict__ local_norm,
-                  const float* __restrict__ gout, double* __restrict__ block_part, const int write_grads) {
+                  const float* __restrict__ gout, double* __restrict__ block_part, const int n_chunks) {
     __shared__ double s_part[kFinalThreads / PAA_WARP][3];
-    const int n = blockIdx.x / geo.tiles_per_image;
-    const int tile = blockIdx.x - n * geo.tiles_per_image;
+    const int chunk = blockIdx.x % n_chunks;
+    const int bt = blockIdx.x / n_chunks;
+    const int n = bt / geo.tiles_per_image;
+    const int tile = bt - n * geo.tiles_per_image;
     int first;
     const int l = tile_level(geo, tile, &first);
     const LevelView& lv = geo.lv[l];
@@ -123,77 +136,82 @@ final_loss_kernel(const Geometry geo, const GtOffsets go, const float* __restric
     const bool valid = i < lv.n_anchor;
     const GradScales gs = make_scales(sc, norm, local_norm, gout);
     const bool g2 = (sc.gamma == 2.0f);
-    const float alpha = sc.alpha, gamma = sc.gamma;
+    const float alpha = sc.alpha, gamma = sc.gamma, oma = 1.0f - sc.alpha;
+    const int c_begin = chunk * kClsChunk;
+    const int c_end = min(geo.C, c_begin + kClsChunk);
 
     float cls_sum = 0.f, reg_sum = 0.f, bce_sum = 0.f;
     if (valid) {
         const size_t flat = (size_t)n * geo.A + lv.a_off + i;
         const int label = paa_label[flat];
         const size_t off = head_offset(n, i, 0, geo.C, geo.apl, lv.hw);
-        const float* cls = lv.cls + off;
-        float* gcls = (write_grads && lv.g_cls) ? lv.g_cls + off : nullptr;
-        const int stride = lv.hw;
-#pragma unroll 8
-        for (int c = 0; c < geo.C; ++c) {
-            const float x = __ldg(cls + (size_t)c * stride);
-            const float e = expf(-fabsf(x));
-            const float l1p = log1pf(e);
-            const float inv = 1.0f / (1.0f + e);
-            const float pr = (x >= 0.0f) ? inv : e * inv;
-            const float qr = (x >= 0.0f) ? e * inv : inv;
-            float term, grad;
-            if (c + 1 == label) {
-                const float nlogp = fmaxf(-x, 0.0f) + l1p;
-                const float mod = g2 ? qr * qr : powf(qr, gamma);
-                term = alpha * mod * nlogp;
-                grad = -alpha * mod * (qr + gamma * pr * nlogp);   // -a (1-p)^g (1 - p - g p log p)
-            } else {
-                const float nlogq = fmaxf(x, 0.0f) + l1p;
-                const float mod = g2 ? pr * pr : powf(pr, gamma);
-                term = (1.0f - alpha) * mod * nlogq;
-                grad = (1.0f - alpha) * mod * (gamma * qr * nlogq + pr);
+        const float* __restrict__ cls = lv.cls + off;
+        float* __restrict__ gcls = lv.g_cls ? lv.g_cls + off : nullptr;
+        const size_t stride = lv.hw;
+        for (int c0 = c_begin; c0 < c_end; c0 += kClsBatch) {
+            float x[kClsBatch];
+#pragma unroll
+            for (int j = 0; j < kClsBatch; ++j) x[j] = (c0 + j < c_end) ? __ldg(cls + (size_t)(c0 + j) * stride) : 0.0f;
+#pragma unroll
+            for (int j = 0; j < kClsBatch; ++j) {
+                if (c0 + j < c_end) {
+                    const SigmoidParts sp = sigmoid_parts(x[j]);
+                    float term, grad;
+                    focal_negative(x[j], sp, gamma, g2, oma, &term, &grad);
+                    cls_sum += term;
+                    if (kGrads && gcls) gcls[(size_t)(c0 + j) * stride] = grad * gs.cls;
+                }
             }
-            cls_sum += term;
-            if (gcls) gcls[(size_t)c * stride] = grad * gs.cls;
+        }
+        if (label > 0 && label - 1 >= c_begin && label - 1 < c_end) {
+            const float xp = __ldg(cls + (size_t)(label - 1) * stride);
+            const SigmoidParts sp = sigmoid_parts(xp);
+            float tn, gn, tp, gp;
+            focal_negative(xp, sp, gamma, g2, oma, &tn, &gn);
+            focal_positive(xp, sp, gamma, g2, alpha, &tp, &gp);
+            cls_sum += tp - tn;
+            if (kGrads && gcls) gcls[(size_t)(label - 1) * stride] = gp * gs.cls;
         }
 
-        float4 gd = make_float4(0.f, 0.f, 0.f, 0.f);
-        float giou_g = 0.f;
-        if (label > 0) {
-            const int m = matched[flat];
-            const float4 a = ldg4(lv.anchors + (size_t)n * geo.anchor_image_stride + (size_t)i * 4);
-            const AnchorFrame f = anchor_frame(a);
-            const float* rp = lv.reg + head_offset(n, i, 0, 4, geo.apl, lv.hw);
-            const float4 d = make_float4(__ldg(rp), __ldg(rp + lv.hw), __ldg(rp + 2 * (size_t)lv.hw),
-                                         __ldg(rp + 3 * (size_t)lv.hw));
-            const float4 gt = ldg4(gt_boxes + (size_t)(go.v[n] + m) * 4);
-            const float4 tgt = decode_box(encode_box(gt, f), f);
-            float w = 1.0f;
-            if (sc.use_iou_pred) {
-                const float4 pred = decode_box(d, f);
-                const float q = iou_plus1(tgt, area_plus1(tgt), pred, area_plus1(pred));
-                const float xi = __ldg(lv.iou + head_offset(n, i, 0, 1, geo.apl, lv.hw));
-                const float ei = expf(-fabsf(xi));
-                bce_sum = fmaxf(xi, 0.0f) - xi * q + log1pf(ei);
-                const float sig = (xi >= 0.0f) ? 1.0f / (1.0f + ei) : ei / (1.0f + ei);
-                giou_g = (sig - q) * gs.bce;
-                if (gs.weighted) w = q;
+        if (chunk == 0) {
+            float4 gd = make_float4(0.f, 0.f, 0.f, 0.f);
+            float giou_g = 0.f;
+            if (label > 0) {
+                const int m = matched[flat];
+                const float4 a = ldg4(lv.anchors + (size_t)n * geo.anchor_image_stride + (size_t)i * 4);
+                const AnchorFrame f = anchor_frame(a);
+                const float* rp = lv.reg + head_offset(n, i, 0, 4, geo.apl, lv.hw);
+                const float4 d = make_float4(__ldg(rp), __ldg(rp + lv.hw), __ldg(rp + 2 * (size_t)lv.hw),
+                                             __ldg(rp + 3 * (size_t)lv.hw));
+                const float4 gt = ldg4(gt_boxes + (size_t)(go.v[n] + m) * 4);
+                const float4 tgt = decode_box(encode_box(gt, f), f);
+                float w = 1.0f;
+                if (sc.use_iou_pred) {
+                    const float4 pred = decode_box(d, f);
+                    const float q = iou_plus1(tgt, area_plus1(tgt), pred, area_plus1(pred));
+                    const float xi = __ldg(lv.iou + head_offset(n, i, 0, 1, geo.apl, lv.hw));
+                    const float ei = expf(-fabsf(xi));
+                    bce_sum = fmaxf(xi, 0.0f) - xi * q + log1pf(ei);
+                    const float sig = (xi >= 0.0f) ? 1.0f / (1.0f + ei) : ei / (1.0f + ei);
+                    giou_g = (sig - q) * gs.bce;
+                    if (gs.weighted) w = q;
+                }
+                float4 gdd;
+                const float gl = giou_loss_and_grad(d, f, tgt, &gdd);
+                reg_sum = gl * w;
+                const float k = w * gs.reg;
+                gd = make_float4(gdd.x * k, gdd.y * k, gdd.z * k, gdd.w * k);
             }
-            float4 gdd;
-            const float gl = giou_loss_and_grad(d, f, tgt, &gdd);
-            reg_sum = gl * w;
-            const float k = w * gs.reg;
-            gd = make_float4(gdd.x * k, gdd.y * k, gdd.z * k, gdd.w * k);
-        }
-        if (write_grads) {
-            if (lv.g_reg) {
-                float* gr = lv.g_reg + head_offset(n, i, 0, 4, geo.apl, lv.hw);
-                gr[0] = gd.x;
-                gr[lv.hw] = gd.y;
-                gr[2 * (size_t)lv.hw] = gd.z;
-                gr[3 * (size_t)lv.hw] = gd.w;
+            if (kGrads) {
+                if (lv.g_reg) {
+                    float* gr = lv.g_reg + head_offset(n, i, 0, 4, geo.apl, lv.hw);
+                    gr[0] = gd.x;
+                    gr[lv.hw] = gd.y;
+                    gr[2 * (size_t)lv.hw] = gd.z;
+                    gr[3 * (size_t)lv.hw] = gd.w;
+                }
+                if (lv.g_iou) lv.g_iou[head_offset(n, i, 0, 1, geo.apl, lv.hw)] = giou_g;
             }
-            if (lv.g_iou) lv.g_iou[head_offset(n, i, 0, 1, geo.apl, lv.hw)] = giou_g;
         }
     }
     // block partial sums (double, fixed order)
@@ -252,10 +270,19 @@ finish_loss_kernel(const double* __restrict__ block_part, int blocks, const Loss
 int launch_final_loss(const Geometry& geo, const GtOffsets& go, const float* gt_boxes,
                       const LossScalars& sc, const LossWorkspace& ws, const double* normalisers,
                       const float* grad_losses, float* losses, bool write_grads, cudaStream_t stream) {
-    const int grid = loss_grid_blocks(geo.num_images, geo.tiles_per_image);
-    final_loss_kernel<<<grid, kFinalThreads, 0, stream>>>(geo, go, gt_boxes, sc, ws.paa_label, ws.matched,
-                                                          normalisers, ws.local_norm, grad_losses,
-                                                          ws.block_part, write_grads ? 1 : 0);
+    const int n_chunks = loss_class_chunks(geo.C);
+    const int grid = geo.num_images * geo.tiles_per_image * n_chunks;
+    {
+        KernelTimer timer(PAA_KERNEL_FINAL_LOSS, stream);
+        if (write_grads)
+            final_loss_kernel<true><<<grid, kFinalThreads, 0, stream>>>(
+                geo, go, gt_boxes, sc, ws.paa_label, ws.matched, normalisers, ws.local_norm, grad_losses,
+                ws.block_part, n_chunks);
+        else
+            final_loss_kernel<false><<<grid, kFinalThreads, 0, stream>>>(
+                geo, go, gt_boxes, sc, ws.paa_label, ws.matched, normalisers, ws.local_norm, grad_losses,
+                ws.block_part, n_chunks);
+    }
     PAA_LAUNCH_CHECK("final_loss_kernel");
     finish_loss_kernel<<<1, 256, 0, stream>>>(ws.block_part, grid, sc, normalisers, losses);
     PAA_LAUNCH_CHECK("finish_loss_kernel");
@@ -266,15 +293,35 @@ int launch_final_loss(const Geometry& geo, const GtOffsets& go, const float* gt_
 // grad *= new/old per loss, for a backward() whose upstream gradients differ from the ones the
 // fused forward assumed.
 // ---------------------------------------------------------------------------------------------
-__global__ void rescale_kernel(float* __restrict__ p, size_t count, const float* __restrict__ old_g,
-                               const float* __restrict__ new_g, int which) {
-    const float r = new_g[which] / old_g[which];
-    if (r == 1.0f) return;
-    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < count; k += (size_t)gridDim.x * blockDim.x)
-        p[k] *= r;
+struct RescaleJob {
+    float* ptr[3 * PAA_MAX_LEVELS];
+    unsigned long long count[3 * PAA_MAX_LEVELS];
+    int which[3 * PAA_MAX_LEVELS];
+    int n;
+};
+
+// One launch for all gradient tensors; returns at once when every ratio is 1 (the usual
+// `sum(losses).backward()`).
+__global__ void __launch_bounds__(256)
+rescale_kernel(const RescaleJob job, const float* __restrict__ old_g, const float* __restrict__ new_g) {
+    float r[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) r[k] = new_g[k] / old_g[k];
+    if (r[0] == 1.0f && r[1] == 1.0f && r[2] == 1.0f) return;
+    for (int j = 0; j < job.n; ++j) {
+        const float rr = r[job.which[j]];
+        if (rr == 1.0f) continue;
+        float* p = job.ptr[j];
+        const size_t count = job.count[j];
+        for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < count;
+             k += (size_t)gridDim.x * blockDim.x)
+            p[k] *= rr;
+    }
 }
 
 int launch_rescale_grads(const Geometry& geo, const float* old_g, const float* new_g, cudaStream_t stream) {
+    RescaleJob job;
+    job.n = 0;
     for (int l = 0; l < geo.num_levels; ++l) {
         const LevelView& lv = geo.lv[l];
         const size_t per = (size_t)geo.num_images * geo.apl * lv.hw;
@@ -282,12 +329,15 @@ int launch_rescale_grads(const Geometry& geo, const float* old_g, const float* n
         const size_t cnt[3] = {per * geo.C, per * 4, per};
         for (int k = 0; k < 3; ++k) {
             if (!ptr[k]) continue;
-            int grid = (int)((cnt[k] + 1023) / 1024);
-            if (grid > 148 * 8) grid = 148 * 8;
-            rescale_kernel<<<grid, 256, 0, stream>>>(ptr[k], cnt[k], old_g, new_g, k);
-            PAA_LAUNCH_CHECK("rescale_kernel");
+            job.ptr[job.n] = ptr[k];
+            job.count[job.n] = cnt[k];
+            job.which[job.n] = k;
+            ++job.n;
         }
     }
+    if (job.n == 0) return 0;
+    rescale_kernel<<<148 * 4, 256, 0, stream>>>(job, old_g, new_g);
+    PAA_LAUNCH_CHECK("rescale_kernel");
     return 0;
 }
 

@@ -258,6 +258,17 @@ class PAALossComputation(object):
             _lib.check(self._lib.paa_rescale_grads(C.byref(call["args"]), self._ones.data_ptr(),
                                                    grad_losses.data_ptr(), stream), "paa_rescale_grads")
 
+    def forward_backward(self, box_cls, box_regression, iou_pred, targets, anchors, grad_losses=None):
+        """Fused training step without autograd bookkeeping: returns ``(losses[3], grads)`` where
+        ``grads`` is ``dict(cls=[...], reg=[...], iou=[...] or None)`` holding d(sum_j g_j * loss_j)/d(head)
+        for ``grad_losses = g`` (ones when omitted).  Same kernels as ``__call__`` + ``backward``; every
+        call on it is a plain stream-ordered launch, so a whole step can be captured in a CUDA graph."""
+        iou = list(iou_pred) if iou_pred is not None else None
+        losses, grads, call = self._run(list(box_cls), list(box_regression), iou, targets, anchors, True)
+        if grad_losses is not None:
+            self._rescale(call, grad_losses.contiguous().float())
+        return losses, grads
+
     # -- the reference's interface --------------------------------------------------------------
     def __call__(self, box_cls, box_regression, iou_pred, targets, anchors, locations=None):
         n_levels = len(box_cls)

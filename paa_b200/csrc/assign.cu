@@ -33,8 +33,9 @@ iou_best_kernel(const Geometry geo, const GtOffsets go, const float* __restrict_
     __shared__ unsigned s_max[kGtChunk];
     __shared__ float4 s_wbox[PAA_TILE / PAA_WARP];
 
-    const int n = blockIdx.x / geo.tiles_per_image;
-    const int tile = blockIdx.x - n * geo.tiles_per_image;
+    // heaviest tiles first: the coarse levels (last tiles of an image) intersect every GT
+    const int n = blockIdx.x % geo.num_images;
+    const int tile = geo.tiles_per_image - 1 - blockIdx.x / geo.num_images;
     int first;
     const int l = tile_level(geo, tile, &first);
     const LevelView& lv = geo.lv[l];
@@ -128,23 +129,25 @@ __device__ __forceinline__ float focal_sum(const float* __restrict__ p, int stri
                                            float gamma, float alpha) {
     const bool g2 = (gamma == 2.0f);
     const float oma = 1.0f - alpha;
-    float sum = 0.0f;
+    float neg = 0.0f;         // sum_c p^g * softplus(x_c): every class as a negative first
+    const unsigned st = (unsigned)stride;
     for (int c0 = 0; c0 < C; c0 += 8) {
         float x[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) x[j] = (c0 + j < C) ? __ldg(p + (size_t)(c0 + j) * stride) : 0.0f;
+        for (int j = 0; j < 8; ++j) x[j] = (c0 + j < C) ? __ldg(p + (unsigned)(c0 + j) * st) : -100.0f;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            if (c0 + j < C) {
-                const SigmoidParts sp = sigmoid_parts(x[j]);
-                float term, grad;
-                if (c0 + j + 1 == label) focal_positive(x[j], sp, gamma, g2, alpha, &term, &grad);
-                else focal_negative(x[j], sp, gamma, g2, oma, &term, &grad);
-                sum += term;
-            }
+        for (int j = 0; j < 8; ++j) {      // a padded logit of -100 contributes exactly 0
+            const SigmoidParts sp = sigmoid_parts(x[j]);
+            neg = fmaf(focal_pow(sp.p, gamma, g2), fmaxf(x[j], 0.0f) + sp.l1p, neg);
         }
     }
-    return sum;
+    // patch the labelled class: remove its negative term, add the positive one
+    const float xl = __ldg(p + (unsigned)(label - 1) * st);
+    const SigmoidParts sp = sigmoid_parts(xl);
+    float tn, gn, tp, gp;
+    focal_negative(xl, sp, gamma, g2, oma, &tn, &gn);
+    focal_positive(xl, sp, gamma, g2, alpha, &tp, &gp);
+    return fmaf(oma, neg, tp - tn);
 }
 
 __global__ void __launch_bounds__(PAA_TILE)
@@ -505,10 +508,14 @@ select_gmm_kernel(const Geometry geo, const GtOffsets go, int num_gt_total,
 #pragma unroll
                         for (int r = 0; r < PAA_TILE / PAA_WARP; ++r) {
                             const int i = base + r * PAA_WARP + lane;
-                            const bool is = (mv[r] == g_local);
+                            bool is = (mv[r] == g_local);
                             unsigned long long key = kEmptyKey;
                             if (is) key = ((unsigned long long)ordered_bits(srow[lv.a_off + i]) << 32) |
                                           (unsigned)(lv.a_off + i);
+                            // keys that cannot enter the current top-K are dropped before the serial
+                            // insertion (the K-th key only ever decreases, so a stale bound is safe)
+                            const unsigned long long kth = __shfl_sync(PAA_FULL, mine, K - 1);
+                            is = is && (key < kth);
                             unsigned hm = __ballot_sync(PAA_FULL, is);
                             while (hm) {
                                 const int src = __ffs(hm) - 1;

@@ -15,8 +15,8 @@ namespace paa {
 
 constexpr int kFinalThreads = PAA_TILE;
 
-// upper bound of blocks the final kernel launches (sizes the partial-sum buffer); 64 class chunks cover C <= 1024
-int loss_grid_blocks(int num_images, int tiles_per_image) { return num_images * tiles_per_image * 64; }
+// upper bound of blocks the final kernel launches (sizes the partial-sum buffer)
+int loss_grid_blocks(int num_images, int tiles_per_image) { (void)num_images; (void)tiles_per_image; return 148 * 16; }
 
 struct GradScales {
     float cls, reg, bce;     // d(total)/d(sum) factors
@@ -26,13 +26,14 @@ struct GradScales {
 __device__ __forceinline__ GradScales make_scales(const LossScalars& sc, const double* __restrict__ norm,
                                                   const double* __restrict__ local_norm,
                                                   const float* __restrict__ gout) {
-    const double world = (double)sc.world_size;
-    const float num_pos_avg = (float)fmax(norm[0] / world, 1.0);       // loss.py:322
+    // num_pos is an exact integer in float (< 2^24); the sums are float32 in the reference as well
+    const float world = (float)sc.world_size;
+    const float num_pos_avg = fmaxf((float)norm[0] / world, 1.0f);     // loss.py:322
     const float g0 = gout ? gout[0] : 1.0f, g1 = gout ? gout[1] : 1.0f, g2 = gout ? gout[2] : 1.0f;
     GradScales s;
     s.cls = g0 / num_pos_avg;
     if (sc.use_iou_pred) {
-        const float reg_norm = (float)(norm[1] / world);               // loss.py:338,354
+        const float reg_norm = (float)norm[1] / world;                 // loss.py:338,354
         s.reg = g1 * sc.reg_loss_weight / reg_norm;
         s.bce = g2 * sc.iou_loss_weight / num_pos_avg;
         s.weighted = local_norm[1] > 0.0;
@@ -108,69 +109,91 @@ __device__ __forceinline__ float giou_loss_and_grad(float4 d, const AnchorFrame&
     return loss;
 }
 
-// One block = 128 consecutive anchors of one level of one image x one chunk of kClsChunk classes;
-// one thread = one anchor.  Every logit of the chunk is read once (a warp reads one 128-byte line per
+// Work item = 128 consecutive anchors of one level of one image x one chunk of kClsChunk classes;
+// one thread = one anchor.  Blocks are persistent (grid = SM count x resident blocks) and walk the
+// items round-robin, so partial sums are reduced once per block and the item -> block map is static
+// (bit-reproducible sums).  Every logit of a chunk is read once (a warp reads one 128-byte line per
 // class) and its gradient written once.  All classes are first treated as negatives; the single
-// positive class of a positive anchor is patched afterwards.  The chunk-0 block of a tile also
-// handles the regression / IoU-prediction losses and gradients of its anchors.
+// positive class of a positive anchor is patched afterwards.  The chunk-0 item of a tile also handles
+// the regression / IoU-prediction losses and gradients of its anchors.
 constexpr int kClsChunk = 16;
 constexpr int kClsBatch = 8;
+constexpr int kFinalBlocksPerSM = 8;
 
 int loss_class_chunks(int C) { return (C + kClsChunk - 1) / kClsChunk; }
 
-template <bool kGrads>
-__global__ void __launch_bounds__(kFinalThreads)
+// negative-class focal term without its (1-alpha) factor, and the gradient with `k` = (1-alpha) * scale
+template <bool kG2>
+__device__ __forceinline__ void neg_term_grad(float x, float gamma, float k, float* sum, float* grad) {
+    const SigmoidParts s = sigmoid_parts(x);
+    const float nlogq = fmaxf(x, 0.0f) + s.l1p;
+    const float mod = kG2 ? s.p * s.p : __powf(s.p, gamma);
+    *sum = fmaf(mod, nlogq, *sum);
+    const float gq = kG2 ? s.q + s.q : gamma * s.q;
+    *grad = (mod * fmaf(gq, nlogq, s.p)) * k;
+}
+
+template <bool kGrads, bool kG2>
+__global__ void __launch_bounds__(kFinalThreads, kFinalBlocksPerSM)
 final_loss_kernel(const Geometry geo, const GtOffsets go, const float* __restrict__ gt_boxes,
                   const LossScalars sc, const int* __restrict__ paa_label, const int* __restrict__ matched,
                   const double* __restrict__ norm, const double* __restrict__ local_norm,
-                  const float* __restrict__ gout, double* __restrict__ block_part, const int n_chunks) {
+                  const float* __restrict__ gout, double* __restrict__ block_part, const int n_chunks,
+                  const int n_items) {
     __shared__ double s_part[kFinalThreads / PAA_WARP][3];
-    const int chunk = blockIdx.x % n_chunks;
-    const int bt = blockIdx.x / n_chunks;
-    const int n = bt / geo.tiles_per_image;
-    const int tile = bt - n * geo.tiles_per_image;
-    int first;
-    const int l = tile_level(geo, tile, &first);
-    const LevelView& lv = geo.lv[l];
-    const int i = first + threadIdx.x;
-    const bool valid = i < lv.n_anchor;
     const GradScales gs = make_scales(sc, norm, local_norm, gout);
-    const bool g2 = (sc.gamma == 2.0f);
     const float alpha = sc.alpha, gamma = sc.gamma, oma = 1.0f - sc.alpha;
-    const int c_begin = chunk * kClsChunk;
-    const int c_end = min(geo.C, c_begin + kClsChunk);
+    const float kneg = oma * gs.cls;
+    float neg_sum = 0.f, fix_sum = 0.f, reg_sum = 0.f, bce_sum = 0.f;
 
-    float cls_sum = 0.f, reg_sum = 0.f, bce_sum = 0.f;
-    if (valid) {
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int chunk = item % n_chunks;
+        const int bt = item / n_chunks;
+        const int n = bt / geo.tiles_per_image;
+        const int tile = bt - n * geo.tiles_per_image;
+        int first;
+        const int l = tile_level(geo, tile, &first);
+        const LevelView& lv = geo.lv[l];
+        const int i = first + threadIdx.x;
+        if (i >= lv.n_anchor) continue;
+        const int c_begin = chunk * kClsChunk;
+        const int c_end = min(geo.C, c_begin + kClsChunk);
         const size_t flat = (size_t)n * geo.A + lv.a_off + i;
-        const int label = paa_label[flat];
-        const size_t off = head_offset(n, i, 0, geo.C, geo.apl, lv.hw);
+        const int label = __ldg(paa_label + flat);
+        const size_t off = head_offset(n, i, c_begin, geo.C, geo.apl, lv.hw);
         const float* __restrict__ cls = lv.cls + off;
         float* __restrict__ gcls = lv.g_cls ? lv.g_cls + off : nullptr;
-        const size_t stride = lv.hw;
-        for (int c0 = c_begin; c0 < c_end; c0 += kClsBatch) {
-            float x[kClsBatch];
+        const unsigned stride = (unsigned)lv.hw;
+        const bool write = kGrads && gcls != nullptr;
+        if (c_end - c_begin == kClsChunk) {
 #pragma unroll
-            for (int j = 0; j < kClsBatch; ++j) x[j] = (c0 + j < c_end) ? __ldg(cls + (size_t)(c0 + j) * stride) : 0.0f;
+            for (int b0 = 0; b0 < kClsChunk; b0 += kClsBatch) {
+                float x[kClsBatch];
 #pragma unroll
-            for (int j = 0; j < kClsBatch; ++j) {
-                if (c0 + j < c_end) {
-                    const SigmoidParts sp = sigmoid_parts(x[j]);
-                    float term, grad;
-                    focal_negative(x[j], sp, gamma, g2, oma, &term, &grad);
-                    cls_sum += term;
-                    if (kGrads && gcls) gcls[(size_t)(c0 + j) * stride] = grad * gs.cls;
+                for (int j = 0; j < kClsBatch; ++j) x[j] = __ldg(cls + (unsigned)(b0 + j) * stride);
+#pragma unroll
+                for (int j = 0; j < kClsBatch; ++j) {
+                    float g;
+                    neg_term_grad<kG2>(x[j], gamma, kneg, &neg_sum, &g);
+                    if (write) gcls[(unsigned)(b0 + j) * stride] = g;
                 }
+            }
+        } else {
+            for (int c = 0; c < c_end - c_begin; ++c) {
+                float g;
+                neg_term_grad<kG2>(__ldg(cls + (unsigned)c * stride), gamma, kneg, &neg_sum, &g);
+                if (write) gcls[(unsigned)c * stride] = g;
             }
         }
         if (label > 0 && label - 1 >= c_begin && label - 1 < c_end) {
-            const float xp = __ldg(cls + (size_t)(label - 1) * stride);
+            const unsigned po = (unsigned)(label - 1 - c_begin) * stride;
+            const float xp = __ldg(cls + po);
             const SigmoidParts sp = sigmoid_parts(xp);
             float tn, gn, tp, gp;
-            focal_negative(xp, sp, gamma, g2, oma, &tn, &gn);
-            focal_positive(xp, sp, gamma, g2, alpha, &tp, &gp);
-            cls_sum += tp - tn;
-            if (kGrads && gcls) gcls[(size_t)(label - 1) * stride] = gp * gs.cls;
+            focal_negative(xp, sp, gamma, kG2, oma, &tn, &gn);
+            focal_positive(xp, sp, gamma, kG2, alpha, &tp, &gp);
+            fix_sum += tp - tn;
+            if (write) gcls[po] = gp * gs.cls;
         }
 
         if (chunk == 0) {
@@ -191,14 +214,14 @@ final_loss_kernel(const Geometry geo, const GtOffsets go, const float* __restric
                     const float q = iou_plus1(tgt, area_plus1(tgt), pred, area_plus1(pred));
                     const float xi = __ldg(lv.iou + head_offset(n, i, 0, 1, geo.apl, lv.hw));
                     const float ei = expf(-fabsf(xi));
-                    bce_sum = fmaxf(xi, 0.0f) - xi * q + log1pf(ei);
+                    bce_sum += fmaxf(xi, 0.0f) - xi * q + log1pf(ei);
                     const float sig = (xi >= 0.0f) ? 1.0f / (1.0f + ei) : ei / (1.0f + ei);
                     giou_g = (sig - q) * gs.bce;
                     if (gs.weighted) w = q;
                 }
                 float4 gdd;
                 const float gl = giou_loss_and_grad(d, f, tgt, &gdd);
-                reg_sum = gl * w;
+                reg_sum += gl * w;
                 const float k = w * gs.reg;
                 gd = make_float4(gdd.x * k, gdd.y * k, gdd.z * k, gdd.w * k);
             }
@@ -215,6 +238,7 @@ final_loss_kernel(const Geometry geo, const GtOffsets go, const float* __restric
         }
     }
     // block partial sums (double, fixed order)
+    const float cls_sum = fmaf(oma, neg_sum, fix_sum);
     double a0 = warp_sum((double)cls_sum), a1 = warp_sum((double)reg_sum), a2 = warp_sum((double)bce_sum);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (lane == 0) {
@@ -271,17 +295,21 @@ int launch_final_loss(const Geometry& geo, const GtOffsets& go, const float* gt_
                       const LossScalars& sc, const LossWorkspace& ws, const double* normalisers,
                       const float* grad_losses, float* losses, bool write_grads, cudaStream_t stream) {
     const int n_chunks = loss_class_chunks(geo.C);
-    const int grid = geo.num_images * geo.tiles_per_image * n_chunks;
+    const int n_items = geo.num_images * geo.tiles_per_image * n_chunks;
+    int grid = 148 * kFinalBlocksPerSM;
+    if (grid > n_items) grid = n_items;
     {
         KernelTimer timer(PAA_KERNEL_FINAL_LOSS, stream);
-        if (write_grads)
-            final_loss_kernel<true><<<grid, kFinalThreads, 0, stream>>>(
-                geo, go, gt_boxes, sc, ws.paa_label, ws.matched, normalisers, ws.local_norm, grad_losses,
-                ws.block_part, n_chunks);
-        else
-            final_loss_kernel<false><<<grid, kFinalThreads, 0, stream>>>(
-                geo, go, gt_boxes, sc, ws.paa_label, ws.matched, normalisers, ws.local_norm, grad_losses,
-                ws.block_part, n_chunks);
+        const bool g2 = (sc.gamma == 2.0f);
+#define PAA_FINAL(G, T)                                                                                \
+    final_loss_kernel<G, T><<<grid, kFinalThreads, 0, stream>>>(geo, go, gt_boxes, sc, ws.paa_label,   \
+        ws.matched, normalisers, ws.local_norm, grad_losses, ws.block_part, n_chunks, n_items)
+        if (write_grads) {
+            if (g2) PAA_FINAL(true, true); else PAA_FINAL(true, false);
+        } else {
+            if (g2) PAA_FINAL(false, true); else PAA_FINAL(false, false);
+        }
+#undef PAA_FINAL
     }
     PAA_LAUNCH_CHECK("final_loss_kernel");
     finish_loss_kernel<<<1, 256, 0, stream>>>(ws.block_part, grid, sc, normalisers, losses);

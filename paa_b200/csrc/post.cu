@@ -1,7 +1,1044 @@
+// PAA post-processing on sm_100a: candidate selection, label-aware NMS, top-D cut, score voting.
+//
+// Replaces PAAPostProcessor.forward (paa_core/modeling/rpn/paa/inference.py:84-159), entirely on the
+// device and batched over the images of the call:
+//   forward_for_single_feature_map  inference.py:36-82   (threshold, per-level top-k, decode, clip)
+//   boxlist_ml_nms / _C.ml_nms       boxlist_ops.py:35-59, csrc/cuda/ml_nms.cu:13-136
+//   kthvalue cut                     inference.py:114-122
+//   score voting                     inference.py:123-157
+//
+// Pipeline (one launch each, no host round trip):
+//   candidates : one pass over the logits (NCHW, coalesced); every (anchor, class) with
+//                sigmoid(x) > thr is appended to its (image, level) list as (score, index) and
+//                counted into a 2048-bin score histogram of that list
+//   threshold  : per (image, level) the histogram bin that holds the k-th best score
+//   filter     : streams the lists once: entries above the bin are selected, entries inside it are
+//                remembered as the boundary set
+//   select     : per (image, level) finishes the top-k from the boundary set (exact radix select),
+//                orders the k survivors by candidate index, decodes + clips their boxes
+//   rank       : per image sorts the <= L*k boxes by (label, score desc) by counting
+//   segments   : start of every label run in the sorted order
+//   nms_mask   : 64x64 suppression bit tiles, only where row and column runs share a label
+//   nms_scan   : one warp per label run walks its boxes in score order (greedy suppression)
+//   finish     : top-D score cut, compaction in pre-NMS index order, output rows
+//   vote       : one warp per output row averages the same-class pre-NMS boxes
 #include "post.h"
+
 namespace paa {
-size_t post_workspace_bytes(int, int, int, int, int) { return 0; }
-int run_postprocess(const Geometry&, const PaaPostArgs*, cudaStream_t) { set_error("not built yet"); return PAA_ERR_UNSUPPORTED; }
-size_t ml_nms_workspace_bytes(int) { return 0; }
-int run_ml_nms(const float*, const float*, const float*, int, float, uint8_t*, int32_t*, void*, size_t, cudaStream_t) { set_error("not built yet"); return PAA_ERR_UNSUPPORTED; }
+
+constexpr int kHistBins = 2048;
+constexpr int kCandClsChunk = 16;
+constexpr int kMaxTopN = 4096;
+constexpr int kFilterBlocks = 32;      // blocks per (image, level) list in the filter pass
+
+struct PostWorkspace {
+    // cleared at the start of every call
+    int* cand_count;      // [N*L]
+    int* sel_count;       // [N*L]
+    int* bnd_count;       // [N*L]
+    int* hist;            // [N*L*kHistBins]
+    size_t zero_bytes;
+    // fully written before read
+    uint2* cand;          // [N * A*C]  (score bits, anchor*C + class) per (image, level) list
+    unsigned* bnd;        // [N * A*C]  positions (within the list) of boundary-bin entries
+    int* thr_bin;         // [N*L]
+    int* n_above;         // [N*L]
+    int* k_sel;           // [N*L]
+    uint2* sel;           // [N*capN]   selected raw entries per (image, level), stride topn
+    int* pre_cnt;         // [N*L]      boxes kept per level after decode / clip / size filter
+    float4* pre_box;      // [N*capN]   level-major, stride topn per level
+    float* pre_score;     // [N*capN]
+    int* pre_label;       // [N*capN]
+    int* total;           // [N]        boxes per image
+    float4* s_box;        // [N*capN]   sorted by (label, score desc, position)
+    float* s_score;
+    int* s_label;
+    int* s_pos;           // position (level*topn + j) of the sorted box
+    int* seg_start;       // [N*(capN+1)]
+    int* n_seg;           // [N]
+    unsigned long long* mask;   // [N * capN * nbw]
+    unsigned char* keep_sorted; // [N*capN]
+    int* out_rank;        // [N*capN]   sorted index of every output row (for voting)
+    unsigned char* flag_by_pos; // [N*capN] survivor flag by pre-NMS position
+    int* rank_by_pos;     // [N*capN]   sorted index by pre-NMS position
+    size_t total_bytes;
+};
+
+static PostWorkspace carve_post(void* base, int N, int A, int C, int L, int topn) {
+    PostWorkspace w;
+    char* p = static_cast<char*>(base);
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        char* q = p ? p + off : nullptr;
+        off += (bytes + 255) / 256 * 256;
+        return q;
+    };
+    const size_t NL = (size_t)N * L, capN = (size_t)L * topn, NAC = (size_t)N * A * C;
+    const size_t nbw = (capN + 63) / 64;
+    w.cand_count = (int*)take(NL * 4);
+    w.sel_count = (int*)take(NL * 4);
+    w.bnd_count = (int*)take(NL * 4);
+    w.hist = (int*)take(NL * kHistBins * 4);
+    w.zero_bytes = off;
+    w.cand = (uint2*)take(NAC * 8);
+    w.bnd = (unsigned*)take(NAC * 4);
+    w.thr_bin = (int*)take(NL * 4);
+    w.n_above = (int*)take(NL * 4);
+    w.k_sel = (int*)take(NL * 4);
+    w.sel = (uint2*)take((size_t)N * capN * 8);
+    w.pre_cnt = (int*)take(NL * 4);
+    w.pre_box = (float4*)take((size_t)N * capN * 16);
+    w.pre_score = (float*)take((size_t)N * capN * 4);
+    w.pre_label = (int*)take((size_t)N * capN * 4);
+    w.total = (int*)take((size_t)N * 4);
+    w.s_box = (float4*)take((size_t)N * capN * 16);
+    w.s_score = (float*)take((size_t)N * capN * 4);
+    w.s_label = (int*)take((size_t)N * capN * 4);
+    w.s_pos = (int*)take((size_t)N * capN * 4);
+    w.seg_start = (int*)take((size_t)N * (capN + 1) * 4);
+    w.n_seg = (int*)take((size_t)N * 4);
+    w.mask = (unsigned long long*)take((size_t)N * capN * nbw * 8);
+    w.keep_sorted = (unsigned char*)take((size_t)N * capN);
+    w.out_rank = (int*)take((size_t)N * capN * 4);
+    w.flag_by_pos = (unsigned char*)take((size_t)N * capN);
+    w.rank_by_pos = (int*)take((size_t)N * capN * 4);
+    w.total_bytes = off;
+    return w;
 }
+
+size_t post_workspace_bytes(int num_images, int anchors_per_image, int num_classes, int num_levels,
+                            int pre_nms_top_n) {
+    if (num_images < 1 || anchors_per_image < 1 || num_classes < 1 || num_levels < 1 || pre_nms_top_n < 1)
+        return 0;
+    return carve_post(nullptr, num_images, anchors_per_image, num_classes, num_levels, pre_nms_top_n).total_bytes;
+}
+
+struct ImageSizes {
+    float wh[PAA_MAX_IMAGES][2];
+};
+
+__device__ __forceinline__ int score_bin(float s) {
+    int b = (int)(s * (float)kHistBins);
+    return b < 0 ? 0 : (b >= kHistBins ? kHistBins - 1 : b);
+}
+
+// ---------------------------------------------------------------------------------------------
+// candidates
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(PAA_TILE)
+post_candidates_kernel(const Geometry geo, const float thr, const float logit_gate, uint2* __restrict__ cand,
+                       int* __restrict__ cand_count, int* __restrict__ hist) {
+    __shared__ uint2 s_buf[PAA_TILE * kCandClsChunk];
+    __shared__ int s_hist[kHistBins];
+    __shared__ int s_cnt, s_base;
+
+    const int n = blockIdx.x / geo.tiles_per_image;
+    const int tile = blockIdx.x - n * geo.tiles_per_image;
+    int first;
+    const int l = tile_level(geo, tile, &first);
+    const LevelView& lv = geo.lv[l];
+    const int i = first + threadIdx.x;
+    const bool valid = i < lv.n_anchor;
+    const int lane = threadIdx.x & 31;
+    const int seg = n * geo.num_levels + l;
+    uint2* list = cand + ((size_t)n * geo.A + lv.a_off) * geo.C;
+
+    for (int b = threadIdx.x; b < kHistBins; b += PAA_TILE) s_hist[b] = 0;
+    float q = 1.0f;
+    const bool has_iou = lv.iou != nullptr;
+    if (valid && has_iou) {
+        const float xi = __ldg(lv.iou + head_offset(n, i, 0, 1, geo.apl, lv.hw));
+        q = 1.0f / (1.0f + expf(-xi));                                   // inference.py:55
+    }
+    const float* cls = lv.cls + (valid ? head_offset(n, i, 0, geo.C, geo.apl, lv.hw) : 0);
+    const unsigned stride = (unsigned)lv.hw;
+    bool any_in_block = false;
+
+    for (int c0 = 0; c0 < geo.C; c0 += kCandClsChunk) {
+        if (threadIdx.x == 0) s_cnt = 0;
+        __syncthreads();
+        const int c1 = min(geo.C, c0 + kCandClsChunk);
+        for (int cb = c0; cb < c1; cb += 8) {
+            float x[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                x[j] = (valid && cb + j < c1) ? __ldg(cls + (unsigned)(cb + j) * stride) : -INFINITY;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                bool is = false;
+                float score = 0.0f;
+                if (x[j] > logit_gate) {                                   // cheap gate, exact test below
+                    const float p = 1.0f / (1.0f + expf(-x[j]));           // inference.py:43
+                    if (p > thr) {                                         // inference.py:48
+                        is = true;
+                        score = has_iou ? sqrtf(__fmul_rn(p, q)) : p;      // inference.py:56
+                    }
+                }
+                const unsigned m = __ballot_sync(PAA_FULL, is);
+                if (m) {
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(&s_cnt, __popc(m));
+                    base = __shfl_sync(PAA_FULL, base, 0);
+                    if (is) {
+                        const int slot = base + __popc(m & ((1u << lane) - 1u));
+                        s_buf[slot] = make_uint2(__float_as_uint(score), (unsigned)(i * geo.C + cb + j));
+                        atomicAdd(&s_hist[score_bin(score)], 1);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        const int cnt = s_cnt;
+        if (cnt > 0) {
+            any_in_block = true;
+            if (threadIdx.x == 0) s_base = atomicAdd(&cand_count[seg], cnt);
+            __syncthreads();
+            const int gb = s_base;
+            for (int t = threadIdx.x; t < cnt; t += PAA_TILE) list[gb + t] = s_buf[t];
+        }
+        __syncthreads();
+    }
+    if (any_in_block) {
+        int* gh = hist + (size_t)seg * kHistBins;
+        for (int b = threadIdx.x; b < kHistBins; b += PAA_TILE) {
+            const int v = s_hist[b];
+            if (v) atomicAdd(&gh[b], v);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// threshold bin per (image, level)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+post_threshold_kernel(const int* __restrict__ cand_count, const int* __restrict__ hist, int topn,
+                      int* __restrict__ thr_bin, int* __restrict__ n_above, int* __restrict__ k_sel) {
+    __shared__ int s_suffix[256];
+    const int seg = blockIdx.x;
+    const int count = cand_count[seg];
+    const int k = min(count, topn);                                      // inference.py:49-50
+    if (count <= topn) {
+        if (threadIdx.x == 0) {
+            thr_bin[seg] = -1;
+            n_above[seg] = count;
+            k_sel[seg] = k;
+        }
+        return;
+    }
+    constexpr int per = kHistBins / 256;
+    const int* h = hist + (size_t)seg * kHistBins;
+    int local[per];
+    int mine = 0;
+#pragma unroll
+    for (int j = 0; j < per; ++j) {
+        local[j] = h[threadIdx.x * per + j];
+        mine += local[j];
+    }
+    s_suffix[threadIdx.x] = mine;
+    __syncthreads();
+    // suffix sums over threads (bins are ascending in score)
+    for (int off = 1; off < 256; off <<= 1) {
+        int v = (threadIdx.x + off < 256) ? s_suffix[threadIdx.x + off] : 0;
+        __syncthreads();
+        s_suffix[threadIdx.x] += v;
+        __syncthreads();
+    }
+    const int incl = s_suffix[threadIdx.x];                 // entries in bins >= my first bin
+    const int excl = incl - mine;                           // entries in bins above my range
+    if (excl < k && incl >= k) {
+        int above = excl;
+        for (int j = per - 1; j >= 0; --j) {
+            if (above + local[j] >= k) {
+                thr_bin[seg] = threadIdx.x * per + j;
+                n_above[seg] = above;
+                k_sel[seg] = k;
+                break;
+            }
+            above += local[j];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// filter: selected (above the bin) and boundary (inside the bin) entries
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+post_filter_kernel(const Geometry geo, const uint2* __restrict__ cand, const int* __restrict__ cand_count,
+                   const int* __restrict__ thr_bin, int topn, uint2* __restrict__ sel,
+                   int* __restrict__ sel_count, unsigned* __restrict__ bnd, int* __restrict__ bnd_count) {
+    const int seg = blockIdx.x / kFilterBlocks;
+    const int part = blockIdx.x - seg * kFilterBlocks;
+    const int n = seg / geo.num_levels, l = seg - n * geo.num_levels;
+    const int count = cand_count[seg];
+    const int tb = thr_bin[seg];
+    const size_t list_off = ((size_t)n * geo.A + geo.lv[l].a_off) * geo.C;
+    const uint2* list = cand + list_off;
+    unsigned* blist = bnd + list_off;
+    uint2* out = sel + (size_t)seg * topn;
+    const int lane = threadIdx.x & 31;
+    for (int e0 = part * 256; e0 < count; e0 += kFilterBlocks * 256) {
+        const int e = e0 + threadIdx.x;
+        bool is_sel = false, is_bnd = false;
+        uint2 v = make_uint2(0u, 0u);
+        if (e < count) {
+            v = list[e];
+            const int b = score_bin(__uint_as_float(v.x));
+            is_sel = b > tb;
+            is_bnd = b == tb;
+        }
+        unsigned m = __ballot_sync(PAA_FULL, is_sel);
+        if (m) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&sel_count[seg], __popc(m));
+            base = __shfl_sync(PAA_FULL, base, 0);
+            if (is_sel) out[base + __popc(m & ((1u << lane) - 1u))] = v;
+        }
+        m = __ballot_sync(PAA_FULL, is_bnd);
+        if (m) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&bnd_count[seg], __popc(m));
+            base = __shfl_sync(PAA_FULL, base, 0);
+            if (is_bnd) blist[base + __popc(m & ((1u << lane) - 1u))] = (unsigned)e;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// select: finish top-k, canonical order, decode + clip
+// ---------------------------------------------------------------------------------------------
+constexpr int kSelectThreads = 1024;
+
+// key of a candidate for "better first": higher score, then lower candidate index
+__device__ __forceinline__ unsigned long long better_key(uint2 v) {
+    return ((unsigned long long)v.x << 32) | (unsigned long long)(0xffffffffu - v.y);
+}
+
+__global__ void __launch_bounds__(kSelectThreads)
+post_select_kernel(const Geometry geo, const ImageSizes sizes, const uint2* __restrict__ cand,
+                   const unsigned* __restrict__ bnd, const int* __restrict__ bnd_count,
+                   const int* __restrict__ n_above, const int* __restrict__ k_sel,
+                   const int* __restrict__ thr_bin, int topn, float min_size, uint2* __restrict__ sel,
+                   int* __restrict__ pre_cnt, float4* __restrict__ pre_box, float* __restrict__ pre_score,
+                   int* __restrict__ pre_label) {
+    __shared__ unsigned s_idx[kMaxTopN];
+    __shared__ unsigned s_sc[kMaxTopN];
+    __shared__ int s_hist[256];
+    __shared__ unsigned long long s_prefix;
+    __shared__ int s_need, s_fill;
+    __shared__ unsigned char s_keep[kMaxTopN];
+
+    const int seg = blockIdx.x;
+    const int n = seg / geo.num_levels, l = seg - n * geo.num_levels;
+    const LevelView& lv = geo.lv[l];
+    const size_t list_off = ((size_t)n * geo.A + lv.a_off) * geo.C;
+    const uint2* list = cand + list_off;
+    const unsigned* blist = bnd + list_off;
+    uint2* mysel = sel + (size_t)seg * topn;
+    const int k = k_sel[seg];
+    const int above = n_above[seg];
+    const int B = (thr_bin[seg] >= 0) ? bnd_count[seg] : 0;
+    const int need = k - above;                 // entries still to take from the boundary bin
+
+    if (B > 0 && need > 0) {
+        // exact radix select (8 bits x 8 passes, most significant first) of the `need` best keys
+        if (threadIdx.x == 0) {
+            s_prefix = 0ull;
+            s_need = need;
+        }
+        __syncthreads();
+        for (int pass = 0; pass < 8; ++pass) {
+            const int shift = 56 - 8 * pass;
+            for (int b = threadIdx.x; b < 256; b += kSelectThreads) s_hist[b] = 0;
+            __syncthreads();
+            const unsigned long long prefix = s_prefix;
+            const unsigned long long hi_mask = (pass == 0) ? 0ull : (~0ull << (shift + 8));
+            for (int e = threadIdx.x; e < B; e += kSelectThreads) {
+                const unsigned long long key = better_key(list[blist[e]]);
+                if ((key & hi_mask) == prefix) atomicAdd(&s_hist[(int)((key >> shift) & 0xff)], 1);
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                int remaining = s_need;
+                int d = 255;
+                for (; d > 0; --d) {
+                    if (s_hist[d] >= remaining) break;
+                    remaining -= s_hist[d];
+                }
+                s_need = remaining;           // still needed among keys with this digit
+                s_prefix = prefix | ((unsigned long long)d << shift);
+            }
+            __syncthreads();
+        }
+        // keys are unique, so exactly `need` of them are >= the selected key
+        const unsigned long long tkey = s_prefix;
+        if (threadIdx.x == 0) s_fill = 0;
+        __syncthreads();
+        for (int e = threadIdx.x; e < B; e += kSelectThreads) {
+            const uint2 v = list[blist[e]];
+            if (better_key(v) >= tkey) mysel[above + atomicAdd(&s_fill, 1)] = v;
+        }
+        __syncthreads();
+    }
+
+    // canonical order: ascending candidate index (the order nonzero() enumerates them, inference.py:66)
+    for (int t = threadIdx.x; t < k; t += kSelectThreads) {
+        const uint2 v = mysel[t];
+        s_sc[t] = v.x;
+        s_idx[t] = v.y;
+    }
+    __syncthreads();
+    const float img_w = sizes.wh[n][0], img_h = sizes.wh[n][1];
+    int dropped = 0;
+    for (int t0 = 0; t0 < k; t0 += kSelectThreads) {
+        const int t = t0 + threadIdx.x;
+        bool drop = false;
+        if (t < k) {
+            const unsigned my_idx = s_idx[t];
+            int rank = 0;
+            for (int q = 0; q < k; ++q) rank += (s_idx[q] < my_idx) ? 1 : 0;
+            const int i = (int)(my_idx / (unsigned)geo.C);
+            const float4 a = ldg4(lv.anchors + (size_t)n * geo.anchor_image_stride + (size_t)i * 4);
+            const float* rp = lv.reg + head_offset(n, i, 0, 4, geo.apl, lv.hw);
+            const float4 d = make_float4(__ldg(rp), __ldg(rp + lv.hw), __ldg(rp + 2 * (size_t)lv.hw),
+                                         __ldg(rp + 3 * (size_t)lv.hw));
+            float4 box = decode_box(d, anchor_frame(a));                  // inference.py:71-74
+            box.x = fminf(fmaxf(box.x, 0.0f), img_w - 1.0f);              // bounding_box.py:214-219
+            box.y = fminf(fmaxf(box.y, 0.0f), img_h - 1.0f);
+            box.z = fminf(fmaxf(box.z, 0.0f), img_w - 1.0f);
+            box.w = fminf(fmaxf(box.w, 0.0f), img_h - 1.0f);
+            const float ws = __fadd_rn(__fsub_rn(box.z, box.x), 1.0f);    // boxlist_ops.py:62-76
+            const float hs = __fadd_rn(__fsub_rn(box.w, box.y), 1.0f);
+            drop = !((ws >= min_size) && (hs >= min_size));
+            s_keep[rank] = drop ? 0 : 1;
+            const size_t o = (size_t)seg * topn + rank;
+            pre_box[o] = box;
+            pre_score[o] = __uint_as_float(s_sc[t]);
+            pre_label[o] = (int)(my_idx % (unsigned)geo.C) + 1;           // inference.py:69
+        }
+        dropped += __syncthreads_count(drop);
+    }
+    if (threadIdx.x == 0) {
+        int cnt = k;
+        if (dropped > 0) {
+            // remove_small_boxes dropped something (non-finite boxes only when min_size == 0): close the
+            // gaps in order.  Serial on purpose -- this path is not expected to run.
+            cnt = 0;
+            const size_t o = (size_t)seg * topn;
+            for (int r = 0; r < k; ++r) {
+                if (!s_keep[r]) continue;
+                if (cnt != r) {
+                    pre_box[o + cnt] = pre_box[o + r];
+                    pre_score[o + cnt] = pre_score[o + r];
+                    pre_label[o + cnt] = pre_label[o + r];
+                }
+                ++cnt;
+            }
+        }
+        pre_cnt[seg] = cnt;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// rank: per image, order all boxes by (label asc, score desc, position asc) by counting
+// ---------------------------------------------------------------------------------------------
+constexpr int kRankThreads = 256;
+constexpr unsigned long long kNoKey = ~0ull;
+
+__device__ __forceinline__ unsigned long long nms_key(int label, float score, int pos) {
+    const unsigned sb = ~__float_as_uint(score);          // scores are >= 0: descending score = ascending ~bits
+    return ((unsigned long long)(unsigned)label << 48) | ((unsigned long long)sb << 16) | (unsigned long long)pos;
+}
+
+__global__ void __launch_bounds__(kRankThreads)
+post_rank_kernel(int L, int topn, const int* __restrict__ pre_cnt, const float4* __restrict__ pre_box,
+                 const float* __restrict__ pre_score, const int* __restrict__ pre_label,
+                 float4* __restrict__ s_box, float* __restrict__ s_score, int* __restrict__ s_label,
+                 int* __restrict__ s_pos, int* __restrict__ total) {
+    __shared__ unsigned long long s_keys[kRankThreads];
+    __shared__ int s_cnt[PAA_MAX_LEVELS];
+    const int n = blockIdx.y;
+    const int capN = L * topn;
+    if (threadIdx.x < L) s_cnt[threadIdx.x] = pre_cnt[n * L + threadIdx.x];
+    __syncthreads();
+    const int pos = blockIdx.x * kRankThreads + threadIdx.x;
+    const size_t base = (size_t)n * capN;
+    unsigned long long mine = kNoKey;
+    if (pos < capN && (pos % topn) < s_cnt[pos / topn])
+        mine = nms_key(pre_label[base + pos], pre_score[base + pos], pos);
+    int rank = 0;
+    for (int q0 = 0; q0 < capN; q0 += kRankThreads) {
+        const int q = q0 + threadIdx.x;
+        unsigned long long k = kNoKey;
+        if (q < capN && (q % topn) < s_cnt[q / topn]) k = nms_key(pre_label[base + q], pre_score[base + q], q);
+        __syncthreads();
+        s_keys[threadIdx.x] = k;
+        __syncthreads();
+        if (mine != kNoKey) {
+#pragma unroll 8
+            for (int j = 0; j < kRankThreads; ++j) rank += (s_keys[j] < mine) ? 1 : 0;
+        }
+    }
+    if (mine != kNoKey) {
+        s_box[base + rank] = pre_box[base + pos];
+        s_score[base + rank] = pre_score[base + pos];
+        s_label[base + rank] = pre_label[base + pos];
+        s_pos[base + rank] = pos;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        int t = 0;
+        for (int l = 0; l < L; ++l) t += s_cnt[l];
+        total[n] = t;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// segments: first sorted index of every run of equal labels (one block per image)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+post_segments_kernel(int capN, const int* __restrict__ total, const int* __restrict__ s_label,
+                     int* __restrict__ seg_start, int* __restrict__ n_seg) {
+    __shared__ int s_warp[32];
+    __shared__ int s_running;
+    const int n = blockIdx.x;
+    const int cnt = total[n];
+    const int* lab = s_label + (size_t)n * capN;
+    int* out = seg_start + (size_t)n * (capN + 1);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_running = 0;
+    __syncthreads();
+    for (int r0 = 0; r0 < cnt; r0 += 1024) {
+        const int r = r0 + threadIdx.x;
+        const bool head = (r < cnt) && (r == 0 || lab[r] != lab[r - 1]);
+        const unsigned m = __ballot_sync(PAA_FULL, head);
+        if (lane == 0) s_warp[warp] = __popc(m);
+        __syncthreads();
+        int before = s_running;
+        for (int w = 0; w < warp; ++w) before += s_warp[w];
+        if (head) out[before + __popc(m & ((1u << lane) - 1u))] = r;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int t = 0;
+            for (int w = 0; w < 32; ++w) t += s_warp[w];
+            s_running += t;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        out[s_running] = cnt;
+        n_seg[n] = s_running;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// nms_mask: bit (i, j) set when sorted box j > i has the same label and IoU(+1) > thr
+// (csrc/cuda/ml_nms.cu:13-24,55-70).  Tiles whose row and column label ranges are disjoint are
+// skipped and never read by the scan.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(64)
+post_nms_mask_kernel(int capN, int nbw, float thr, const int* __restrict__ total,
+                     const float4* __restrict__ s_box, const int* __restrict__ s_label,
+                     unsigned long long* __restrict__ mask) {
+    const int n = blockIdx.z;
+    const int rb = blockIdx.y, cb = blockIdx.x;
+    if (cb < rb) return;
+    const int cnt = total[n];
+    const int r0 = rb * 64, c0 = cb * 64;
+    if (r0 >= cnt || c0 >= cnt) return;
+    const size_t base = (size_t)n * capN;
+    const int r_last = min(cnt, r0 + 64) - 1;
+    if (s_label[base + c0] > s_label[base + r_last]) return;      // sorted by label: no shared label
+    __shared__ float4 s_cb[64];
+    __shared__ float s_ca[64];
+    __shared__ int s_cl[64];
+    const int csize = min(64, cnt - c0);
+    if (threadIdx.x < csize) {
+        const float4 b = s_box[base + c0 + threadIdx.x];
+        s_cb[threadIdx.x] = b;
+        s_ca[threadIdx.x] = area_plus1(b);
+        s_cl[threadIdx.x] = s_label[base + c0 + threadIdx.x];
+    }
+    __syncthreads();
+    const int r = r0 + threadIdx.x;
+    if (r < cnt) {
+        const float4 a = s_box[base + r];
+        const float aa = area_plus1(a);
+        const int al = s_label[base + r];
+        unsigned long long bits = 0ull;
+        const int start = (rb == cb) ? threadIdx.x + 1 : 0;
+        for (int j = start; j < csize; ++j) {
+            if (s_cl[j] != al) continue;
+            if (iou_plus1(a, aa, s_cb[j], s_ca[j]) > thr) bits |= 1ull << j;
+        }
+        mask[(base + r) * nbw + cb] = bits;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// nms_scan: greedy suppression inside one label run, boxes visited in descending score
+// (csrc/cuda/ml_nms.cu:116-128).  One warp per run; its removed-bits live in shared memory.
+// ---------------------------------------------------------------------------------------------
+constexpr int kScanWarps = 4;
+
+__global__ void __launch_bounds__(kScanWarps * 32)
+post_nms_scan_kernel(int capN, int nbw, int segs_per_image, const int* __restrict__ seg_start,
+                     const int* __restrict__ n_seg, const unsigned long long* __restrict__ mask,
+                     unsigned char* __restrict__ keep_sorted) {
+    extern __shared__ unsigned long long s_removed[];       // [kScanWarps][nbw]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gw = blockIdx.x * kScanWarps + warp;
+    const int n = gw / segs_per_image;
+    const int s = gw - n * segs_per_image;
+    if (s >= n_seg[n]) return;
+    const int* ss = seg_start + (size_t)n * (capN + 1);
+    const int a = ss[s], b = ss[s + 1];
+    const int w_lo = a >> 6, w_hi = (b - 1) >> 6;
+    unsigned long long* rem = s_removed + (size_t)warp * nbw;
+    for (int w = w_lo + lane; w <= w_hi; w += 32) rem[w] = 0ull;
+    __syncwarp();
+    const size_t base = (size_t)n * capN;
+    for (int i = a; i < b; ++i) {
+        const bool dead = (rem[i >> 6] >> (i & 63)) & 1ull;
+        if (!dead) {
+            const unsigned long long* row = mask + (base + i) * nbw;
+            for (int w = (i >> 6) + lane; w <= w_hi; w += 32) rem[w] |= row[w];
+        }
+        if (lane == 0) keep_sorted[base + i] = dead ? 0 : 1;
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// finish: top-D cut (inference.py:114-122), compaction in ascending pre-NMS position
+// (csrc/cuda/ml_nms.cu:132-135 + boxlist[keep]), output rows.  One block per image.
+// ---------------------------------------------------------------------------------------------
+constexpr int kFinishThreads = 1024;
+
+__global__ void __launch_bounds__(kFinishThreads)
+post_finish_kernel(int L, int topn, int det_per_img, int skip_nms, const int* __restrict__ pre_cnt,
+                   const int* __restrict__ total, const float4* __restrict__ pre_box,
+                   const float* __restrict__ pre_score, const int* __restrict__ pre_label,
+                   const int* __restrict__ s_pos, const unsigned char* __restrict__ keep_sorted,
+                   unsigned char* __restrict__ flag_by_pos, int* __restrict__ rank_by_pos,
+                   float* __restrict__ out_boxes, float* __restrict__ out_scores,
+                   long long* __restrict__ out_labels, int* __restrict__ out_count, int* __restrict__ out_rank,
+                   unsigned char* __restrict__ dbg_keep) {
+    __shared__ int s_hist[256];
+    __shared__ int s_warp[32];
+    __shared__ int s_running, s_need;
+    __shared__ unsigned s_prefix;
+    const int n = blockIdx.x;
+    const int capN = L * topn;
+    const size_t base = (size_t)n * capN;
+    const int cnt = total[n];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char* flag = flag_by_pos + base;
+    int* rpos = rank_by_pos + base;
+
+    // survivors by position
+    for (int p = threadIdx.x; p < capN; p += kFinishThreads) flag[p] = 0;
+    __syncthreads();
+    int kept_local = 0;
+    for (int r = threadIdx.x; r < cnt; r += kFinishThreads) {
+        const int p = s_pos[base + r];
+        const unsigned char k = skip_nms ? 1 : keep_sorted[base + r];
+        flag[p] = k;
+        rpos[p] = r;
+        kept_local += k;
+    }
+    __syncthreads();
+    // block sum of kept_local
+    int wsum = kept_local;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wsum += __shfl_xor_sync(PAA_FULL, wsum, o);
+    if (lane == 0) s_warp[warp] = wsum;
+    __syncthreads();
+    int n_kept = 0;
+    for (int w = 0; w < kFinishThreads / 32; ++w) n_kept += s_warp[w];
+    __syncthreads();
+    if (dbg_keep) {
+        for (int l = 0, o = 0; l < L; ++l) {        // debug output is compact level-major
+            const int c = pre_cnt[n * L + l];
+            for (int j = threadIdx.x; j < c; j += kFinishThreads) dbg_keep[base + o + j] = flag[l * topn + j];
+            o += c;
+        }
+    }
+
+    // more than D survivors: keep those whose score is >= the D-th largest (ties keep more)
+    unsigned thr_bits = 0u;
+    if (!skip_nms && det_per_img > 0 && n_kept > det_per_img) {
+        if (threadIdx.x == 0) {
+            s_prefix = 0u;
+            s_need = det_per_img;
+        }
+        __syncthreads();
+        for (int pass = 0; pass < 4; ++pass) {
+            const int shift = 24 - 8 * pass;
+            for (int b = threadIdx.x; b < 256; b += kFinishThreads) s_hist[b] = 0;
+            __syncthreads();
+            const unsigned prefix = s_prefix;
+            const unsigned hi_mask = (pass == 0) ? 0u : (~0u << (shift + 8));
+            for (int p = threadIdx.x; p < capN; p += kFinishThreads) {
+                if (!flag[p]) continue;
+                const unsigned key = __float_as_uint(pre_score[base + p]);
+                if ((key & hi_mask) == prefix) atomicAdd(&s_hist[(key >> shift) & 0xff], 1);
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                int remaining = s_need;
+                int d = 255;
+                for (; d > 0; --d) {
+                    if (s_hist[d] >= remaining) break;
+                    remaining -= s_hist[d];
+                }
+                s_need = remaining;
+                s_prefix = prefix | ((unsigned)d << shift);
+            }
+            __syncthreads();
+        }
+        thr_bits = s_prefix;       // bit pattern of the D-th largest surviving score
+    }
+
+    // ordered compaction over positions
+    if (threadIdx.x == 0) s_running = 0;
+    __syncthreads();
+    for (int p0 = 0; p0 < capN; p0 += kFinishThreads) {
+        const int p = p0 + threadIdx.x;
+        bool take = false;
+        if (p < capN && flag[p]) take = __float_as_uint(pre_score[base + p]) >= thr_bits;
+        const unsigned m = __ballot_sync(PAA_FULL, take);
+        if (lane == 0) s_warp[warp] = __popc(m);
+        __syncthreads();
+        int before = s_running;
+        for (int w = 0; w < warp; ++w) before += s_warp[w];
+        if (take) {
+            const int row = before + __popc(m & ((1u << lane) - 1u));
+            const float4 b = pre_box[base + p];
+            float* ob = out_boxes + (base + row) * 4;
+            ob[0] = b.x;
+            ob[1] = b.y;
+            ob[2] = b.z;
+            ob[3] = b.w;
+            out_scores[base + row] = pre_score[base + p];
+            out_labels[base + row] = (long long)pre_label[base + p];
+            out_rank[base + row] = rpos[p];
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int t = 0;
+            for (int w = 0; w < kFinishThreads / 32; ++w) t += s_warp[w];
+            s_running += t;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out_count[n] = s_running;
+}
+
+// ---------------------------------------------------------------------------------------------
+// vote: every output box becomes the weighted mean of all pre-NMS boxes of its class with
+// IoU(+1) > 0.01, weight exp(-(1-IoU)^2 / 0.025) * score (inference.py:123-157).  One warp per row.
+// ---------------------------------------------------------------------------------------------
+constexpr int kVoteWarps = 4;
+constexpr int kVoteBlocksPerImage = 32;
+
+__global__ void __launch_bounds__(kVoteWarps * 32)
+post_vote_kernel(int capN, const int* __restrict__ out_count, const int* __restrict__ out_rank,
+                 const int* __restrict__ seg_start, const int* __restrict__ n_seg,
+                 const float4* __restrict__ s_box, const float* __restrict__ s_score,
+                 float* __restrict__ out_boxes) {
+    const int n = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    const int gw = blockIdx.x * kVoteWarps + (threadIdx.x >> 5);
+    const size_t base = (size_t)n * capN;
+    const int rows = out_count[n];
+    const int* ss = seg_start + (size_t)n * (capN + 1);
+    const int ns = n_seg[n];
+    for (int row = gw; row < rows; row += kVoteBlocksPerImage * kVoteWarps) {
+        const int r = out_rank[base + row];
+        // run containing sorted index r: last start <= r
+        int lo = 0, hi = ns - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (ss[mid] <= r) lo = mid; else hi = mid - 1;
+        }
+        const int a = ss[lo], b = ss[lo + 1];
+        const float4 det = s_box[base + r];
+        const float det_area = area_plus1(det);
+        float sx1 = 0.f, sy1 = 0.f, sx2 = 0.f, sy2 = 0.f, sp = 0.f;
+        for (int j = a + lane; j < b; j += 32) {
+            const float4 c = s_box[base + j];
+            const float q = iou_plus1(det, det_area, c, area_plus1(c));
+            if (q > 0.01f) {
+                const float t = __fsub_rn(1.0f, q);
+                const float p = __fmul_rn(expf(__fdiv_rn(-__fmul_rn(t, t), 0.025f)), s_score[base + j]);
+                sx1 = fmaf(c.x, p, sx1);
+                sy1 = fmaf(c.y, p, sy1);
+                sx2 = fmaf(c.z, p, sx2);
+                sy2 = fmaf(c.w, p, sy2);
+                sp += p;
+            }
+        }
+        sx1 = warp_sum(sx1);
+        sy1 = warp_sum(sy1);
+        sx2 = warp_sum(sx2);
+        sy2 = warp_sum(sy2);
+        sp = warp_sum(sp);
+        if (lane == 0) {
+            float* ob = out_boxes + (base + row) * 4;
+            ob[0] = sx1 / sp;
+            ob[1] = sy1 / sp;
+            ob[2] = sx2 / sp;
+            ob[3] = sy2 / sp;
+        }
+    }
+}
+
+// compact copies of the strided pre-NMS arrays for the debug outputs
+__global__ void post_debug_pre_kernel(int L, int topn, const int* __restrict__ pre_cnt,
+                                      const float4* __restrict__ pre_box, const float* __restrict__ pre_score,
+                                      const int* __restrict__ pre_label, float* __restrict__ d_box,
+                                      float* __restrict__ d_score, int* __restrict__ d_label,
+                                      int* __restrict__ d_count) {
+    const int n = blockIdx.x;
+    const size_t base = (size_t)n * L * topn;
+    int o = 0;
+    for (int l = 0; l < L; ++l) {
+        const int c = pre_cnt[n * L + l];
+        for (int j = threadIdx.x; j < c; j += blockDim.x) {
+            const size_t src = base + (size_t)l * topn + j, dst = base + o + j;
+            if (d_box) {
+                const float4 b = pre_box[src];
+                d_box[dst * 4 + 0] = b.x;
+                d_box[dst * 4 + 1] = b.y;
+                d_box[dst * 4 + 2] = b.z;
+                d_box[dst * 4 + 3] = b.w;
+            }
+            if (d_score) d_score[dst] = pre_score[src];
+            if (d_label) d_label[dst] = pre_label[src];
+        }
+        if (d_count && threadIdx.x == 0) d_count[n * L + l] = c;
+        o += c;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+int run_postprocess(const Geometry& geo, const PaaPostArgs* a, cudaStream_t stream) {
+    const int N = a->num_images, L = a->num_levels, topn = a->pre_nms_top_n, C = a->num_classes;
+    if (topn < 1 || topn > kMaxTopN) {
+        set_error("pre_nms_top_n=%d outside [1, %d]", topn, kMaxTopN);
+        return PAA_ERR_UNSUPPORTED;
+    }
+    const int capN = L * topn;
+    if (capN > 65535) {
+        set_error("num_levels*pre_nms_top_n=%d exceeds 65535", capN);
+        return PAA_ERR_UNSUPPORTED;
+    }
+    if ((size_t)geo.A * C >= (1ull << 31)) {
+        set_error("anchors*classes per image too large");
+        return PAA_ERR_UNSUPPORTED;
+    }
+    if (!a->workspace || !a->out_boxes || !a->out_scores || !a->out_labels || !a->out_count) {
+        set_error("null workspace / output pointer");
+        return PAA_ERR_BAD_ARGUMENT;
+    }
+    if (!(a->pre_nms_thresh > 0.0f && a->pre_nms_thresh < 1.0f)) {
+        set_error("pre_nms_thresh=%g outside (0, 1)", (double)a->pre_nms_thresh);
+        return PAA_ERR_BAD_ARGUMENT;
+    }
+    PostWorkspace w = carve_post(a->workspace, N, geo.A, C, L, topn);
+    if (w.total_bytes > a->workspace_bytes) {
+        set_error("workspace too small: need %zu bytes, got %zu", w.total_bytes, a->workspace_bytes);
+        return PAA_ERR_WORKSPACE;
+    }
+    ImageSizes sizes;
+    for (int i = 0; i < N; ++i) {
+        sizes.wh[i][0] = a->image_wh[i][0];
+        sizes.wh[i][1] = a->image_wh[i][1];
+    }
+    const int nbw = (capN + 63) / 64;
+    PAA_CUDA_CHECK(cudaMemsetAsync(a->workspace, 0, w.zero_bytes, stream));
+    // a logit can only pass sigmoid(x) > thr if x > logit(thr); gate a little below that and test exactly
+    const float gate = logf(a->pre_nms_thresh / (1.0f - a->pre_nms_thresh)) - 1e-3f;
+    {
+        KernelTimer t(PAA_KERNEL_POST_CANDIDATES, stream);
+        post_candidates_kernel<<<N * geo.tiles_per_image, PAA_TILE, 0, stream>>>(geo, a->pre_nms_thresh, gate,
+                                                                                 w.cand, w.cand_count, w.hist);
+    }
+    PAA_LAUNCH_CHECK("post_candidates_kernel");
+    post_threshold_kernel<<<N * L, 256, 0, stream>>>(w.cand_count, w.hist, topn, w.thr_bin, w.n_above, w.k_sel);
+    PAA_LAUNCH_CHECK("post_threshold_kernel");
+    {
+        KernelTimer t(PAA_KERNEL_POST_FILTER, stream);
+        post_filter_kernel<<<N * L * kFilterBlocks, 256, 0, stream>>>(geo, w.cand, w.cand_count, w.thr_bin, topn,
+                                                                      w.sel, w.sel_count, w.bnd, w.bnd_count);
+    }
+    PAA_LAUNCH_CHECK("post_filter_kernel");
+    {
+        KernelTimer t(PAA_KERNEL_POST_SELECT, stream);
+        post_select_kernel<<<N * L, kSelectThreads, 0, stream>>>(geo, sizes, w.cand, w.bnd, w.bnd_count, w.n_above,
+                                                                 w.k_sel, w.thr_bin, topn, 0.0f, w.sel, w.pre_cnt,
+                                                                 w.pre_box, w.pre_score, w.pre_label);
+    }
+    PAA_LAUNCH_CHECK("post_select_kernel");
+    if (a->dbg_pre_boxes || a->dbg_pre_scores || a->dbg_pre_labels || a->dbg_pre_count) {
+        post_debug_pre_kernel<<<N, 256, 0, stream>>>(L, topn, w.pre_cnt, w.pre_box, w.pre_score, w.pre_label,
+                                                     a->dbg_pre_boxes, a->dbg_pre_scores, a->dbg_pre_labels,
+                                                     a->dbg_pre_count);
+        PAA_LAUNCH_CHECK("post_debug_pre_kernel");
+    }
+    {
+        KernelTimer t(PAA_KERNEL_POST_RANK, stream);
+        dim3 grid((capN + kRankThreads - 1) / kRankThreads, N);
+        post_rank_kernel<<<grid, kRankThreads, 0, stream>>>(L, topn, w.pre_cnt, w.pre_box, w.pre_score, w.pre_label,
+                                                            w.s_box, w.s_score, w.s_label, w.s_pos, w.total);
+    }
+    PAA_LAUNCH_CHECK("post_rank_kernel");
+    post_segments_kernel<<<N, 1024, 0, stream>>>(capN, w.total, w.s_label, w.seg_start, w.n_seg);
+    PAA_LAUNCH_CHECK("post_segments_kernel");
+    if (!a->skip_nms) {
+        {
+            KernelTimer t(PAA_KERNEL_POST_NMS_MASK, stream);
+            dim3 grid(nbw, nbw, N);
+            post_nms_mask_kernel<<<grid, 64, 0, stream>>>(capN, nbw, a->nms_thresh, w.total, w.s_box, w.s_label,
+                                                          w.mask);
+        }
+        PAA_LAUNCH_CHECK("post_nms_mask_kernel");
+        {
+            KernelTimer t(PAA_KERNEL_POST_NMS_SCAN, stream);
+            const int segs = capN < C ? capN : C;          // labels are 1..C: at most C runs per image
+            const int warps = N * segs;
+            const size_t smem = (size_t)kScanWarps * nbw * sizeof(unsigned long long);
+            post_nms_scan_kernel<<<(warps + kScanWarps - 1) / kScanWarps, kScanWarps * 32, smem, stream>>>(
+                capN, nbw, segs, w.seg_start, w.n_seg, w.mask, w.keep_sorted);
+        }
+        PAA_LAUNCH_CHECK("post_nms_scan_kernel");
+    }
+    {
+        KernelTimer t(PAA_KERNEL_POST_FINISH, stream);
+        unsigned char* flag = w.flag_by_pos;
+        int* rpos = w.rank_by_pos;
+        post_finish_kernel<<<N, kFinishThreads, 0, stream>>>(
+            L, topn, a->detections_per_img, a->skip_nms, w.pre_cnt, w.total, w.pre_box, w.pre_score, w.pre_label,
+            w.s_pos, w.keep_sorted, flag, rpos, a->out_boxes, a->out_scores,
+            reinterpret_cast<long long*>(a->out_labels), a->out_count, w.out_rank, a->dbg_nms_keep);
+    }
+    PAA_LAUNCH_CHECK("post_finish_kernel");
+    if (a->score_voting && !a->skip_nms) {
+        KernelTimer t(PAA_KERNEL_POST_VOTE, stream);
+        dim3 grid(kVoteBlocksPerImage, N);
+        post_vote_kernel<<<grid, kVoteWarps * 32, 0, stream>>>(capN, a->out_count, w.out_rank, w.seg_start, w.n_seg,
+                                                               w.s_box, w.s_score, a->out_boxes);
+        PAA_LAUNCH_CHECK("post_vote_kernel");
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// stand-alone label-aware NMS behind `_C.ml_nms` (csrc/ml_nms.h:10-27)
+// ---------------------------------------------------------------------------------------------
+struct MlNmsWorkspace {
+    int* cnt;             // [1]
+    float4* box;          // [n]
+    int* label;           // [n]
+    float4* s_box;
+    float* s_score;
+    int* s_label;
+    int* s_pos;
+    int* total;
+    int* seg_start;       // [n+1]
+    int* n_seg;
+    unsigned long long* mask;
+    unsigned char* keep_sorted;
+    size_t total_bytes;
+};
+
+static MlNmsWorkspace carve_ml_nms(void* base, int n) {
+    MlNmsWorkspace w;
+    char* p = static_cast<char*>(base);
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        char* q = p ? p + off : nullptr;
+        off += (bytes + 255) / 256 * 256;
+        return q;
+    };
+    const size_t nn = n > 0 ? n : 1, nbw = (nn + 63) / 64;
+    w.cnt = (int*)take(4);
+    w.box = (float4*)take(nn * 16);
+    w.label = (int*)take(nn * 4);
+    w.s_box = (float4*)take(nn * 16);
+    w.s_score = (float*)take(nn * 4);
+    w.s_label = (int*)take(nn * 4);
+    w.s_pos = (int*)take(nn * 4);
+    w.total = (int*)take(4);
+    w.seg_start = (int*)take((nn + 1) * 4);
+    w.n_seg = (int*)take(4);
+    w.mask = (unsigned long long*)take(nn * nbw * 8);
+    w.keep_sorted = (unsigned char*)take(nn);
+    w.total_bytes = off;
+    return w;
+}
+
+size_t ml_nms_workspace_bytes(int n) { return carve_ml_nms(nullptr, n).total_bytes; }
+
+__global__ void ml_nms_prepare_kernel(int n, const float* __restrict__ boxes, const float* __restrict__ labels,
+                                      float4* __restrict__ box, int* __restrict__ label, int* __restrict__ cnt) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) *cnt = n;
+    if (i < n) {
+        box[i] = make_float4(boxes[i * 4], boxes[i * 4 + 1], boxes[i * 4 + 2], boxes[i * 4 + 3]);
+        label[i] = (int)labels[i];
+    }
+}
+
+__global__ void ml_nms_scatter_kernel(int n, const int* __restrict__ s_pos, const unsigned char* __restrict__ ks,
+                                      unsigned char* __restrict__ keep, int* __restrict__ num_keep) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    int k = 0;
+    if (r < n) {
+        k = ks[r];
+        keep[s_pos[r]] = (unsigned char)k;
+    }
+    const unsigned m = __ballot_sync(PAA_FULL, k != 0);
+    if ((threadIdx.x & 31) == 0 && m && num_keep) atomicAdd(num_keep, __popc(m));
+}
+
+int run_ml_nms(const float* boxes, const float* scores, const float* labels, int n, float thresh,
+               uint8_t* keep, int32_t* num_keep, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    if (n < 0 || n > 65535) {
+        set_error("paa_ml_nms: n=%d outside [0, 65535]", n);
+        return PAA_ERR_UNSUPPORTED;
+    }
+    if (num_keep) PAA_CUDA_CHECK(cudaMemsetAsync(num_keep, 0, sizeof(int32_t), stream));
+    if (n == 0) return 0;
+    if (!boxes || !scores || !labels || !keep || !workspace) {
+        set_error("paa_ml_nms: null pointer");
+        return PAA_ERR_BAD_ARGUMENT;
+    }
+    MlNmsWorkspace w = carve_ml_nms(workspace, n);
+    if (w.total_bytes > workspace_bytes) {
+        set_error("paa_ml_nms: workspace too small: need %zu bytes, got %zu", w.total_bytes, workspace_bytes);
+        return PAA_ERR_WORKSPACE;
+    }
+    const int nbw = (n + 63) / 64;
+    ml_nms_prepare_kernel<<<(n + 255) / 256, 256, 0, stream>>>(n, boxes, labels, w.box, w.label, w.cnt);
+    PAA_LAUNCH_CHECK("ml_nms_prepare_kernel");
+    dim3 rgrid((n + kRankThreads - 1) / kRankThreads, 1);
+    post_rank_kernel<<<rgrid, kRankThreads, 0, stream>>>(1, n, w.cnt, w.box, scores, w.label, w.s_box, w.s_score,
+                                                         w.s_label, w.s_pos, w.total);
+    PAA_LAUNCH_CHECK("post_rank_kernel");
+    post_segments_kernel<<<1, 1024, 0, stream>>>(n, w.total, w.s_label, w.seg_start, w.n_seg);
+    PAA_LAUNCH_CHECK("post_segments_kernel");
+    dim3 mgrid(nbw, nbw, 1);
+    post_nms_mask_kernel<<<mgrid, 64, 0, stream>>>(n, nbw, thresh, w.total, w.s_box, w.s_label, w.mask);
+    PAA_LAUNCH_CHECK("post_nms_mask_kernel");
+    const size_t smem = (size_t)kScanWarps * nbw * sizeof(unsigned long long);
+    post_nms_scan_kernel<<<(n + kScanWarps - 1) / kScanWarps, kScanWarps * 32, smem, stream>>>(
+        n, nbw, n, w.seg_start, w.n_seg, w.mask, w.keep_sorted);
+    PAA_LAUNCH_CHECK("post_nms_scan_kernel");
+    ml_nms_scatter_kernel<<<(n + 255) / 256, 256, 0, stream>>>(n, w.s_pos, w.keep_sorted, keep, num_keep);
+    PAA_LAUNCH_CHECK("ml_nms_scatter_kernel");
+    return 0;
+}
+
+}  // namespace paa

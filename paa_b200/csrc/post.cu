@@ -580,13 +580,15 @@ post_nms_mask_kernel(int capN, int nbw, float thr, const int* __restrict__ total
 constexpr int kScanWarps = 4;
 
 __global__ void __launch_bounds__(kScanWarps * 32)
-post_nms_scan_kernel(int capN, int nbw, int segs_per_image, const int* __restrict__ seg_start,
+post_nms_scan_kernel(int capN, int nbw, int segs_per_image, int num_images,
+                     const int* __restrict__ seg_start,
                      const int* __restrict__ n_seg, const unsigned long long* __restrict__ mask,
                      unsigned char* __restrict__ keep_sorted) {
     extern __shared__ unsigned long long s_removed[];       // [kScanWarps][nbw]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gw = blockIdx.x * kScanWarps + warp;
     const int n = gw / segs_per_image;
+    if (n >= num_images) return;
     const int s = gw - n * segs_per_image;
     if (s >= n_seg[n]) return;
     const int* ss = seg_start + (size_t)n * (capN + 1);
@@ -910,7 +912,7 @@ int run_postprocess(const Geometry& geo, const PaaPostArgs* a, cudaStream_t stre
             const int warps = N * segs;
             const size_t smem = (size_t)kScanWarps * nbw * sizeof(unsigned long long);
             post_nms_scan_kernel<<<(warps + kScanWarps - 1) / kScanWarps, kScanWarps * 32, smem, stream>>>(
-                capN, nbw, segs, w.seg_start, w.n_seg, w.mask, w.keep_sorted);
+                capN, nbw, segs, N, w.seg_start, w.n_seg, w.mask, w.keep_sorted);
         }
         PAA_LAUNCH_CHECK("post_nms_scan_kernel");
     }
@@ -1034,7 +1036,7 @@ int run_ml_nms(const float* boxes, const float* scores, const float* labels, int
     PAA_LAUNCH_CHECK("post_nms_mask_kernel");
     const size_t smem = (size_t)kScanWarps * nbw * sizeof(unsigned long long);
     post_nms_scan_kernel<<<(n + kScanWarps - 1) / kScanWarps, kScanWarps * 32, smem, stream>>>(
-        n, nbw, n, w.seg_start, w.n_seg, w.mask, w.keep_sorted);
+        n, nbw, n, 1, w.seg_start, w.n_seg, w.mask, w.keep_sorted);
     PAA_LAUNCH_CHECK("post_nms_scan_kernel");
     ml_nms_scatter_kernel<<<(n + 255) / 256, 256, 0, stream>>>(n, w.s_pos, w.keep_sorted, keep, num_keep);
     PAA_LAUNCH_CHECK("ml_nms_scatter_kernel");

@@ -13,6 +13,7 @@
 // stride H*W, so a warp reading 32 consecutive anchors of one class is one 128-byte line); all
 // per-anchor intermediates are flat [N*A] arrays in the caller's workspace.
 #include "kernels.h"
+#include "fastmath64.cuh"
 
 namespace paa {
 
@@ -27,11 +28,10 @@ constexpr int kGtChunk = 256;
 
 __global__ void __launch_bounds__(PAA_TILE)
 iou_best_kernel(const Geometry geo, const GtOffsets go, const float* __restrict__ gt_boxes,
-                unsigned* __restrict__ gtmax, uint2* __restrict__ best, float4* __restrict__ tile_bbox) {
+                unsigned* __restrict__ gtmax, uint2* __restrict__ best) {
     __shared__ float4 s_gt[kGtChunk];
     __shared__ float s_area[kGtChunk];
     __shared__ unsigned s_max[kGtChunk];
-    __shared__ float4 s_wbox[PAA_TILE / PAA_WARP];
 
     // heaviest tiles first: the coarse levels (last tiles of an image) intersect every GT
     const int n = blockIdx.x % geo.num_images;
@@ -41,13 +41,12 @@ iou_best_kernel(const Geometry geo, const GtOffsets go, const float* __restrict_
     const LevelView& lv = geo.lv[l];
     const int i = first + threadIdx.x;
     const bool valid = i < lv.n_anchor;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
 
     float4 a = make_float4(INFINITY, INFINITY, -INFINITY, -INFINITY);
     if (valid) a = ldg4(lv.anchors + (size_t)n * geo.anchor_image_stride + (size_t)i * 4);
     const float area_a = area_plus1(a);
     const float wx1 = warp_min(a.x), wy1 = warp_min(a.y), wx2 = warp_max(a.z), wy2 = warp_max(a.w);
-    if (lane == 0) s_wbox[warp] = make_float4(wx1, wy1, wx2, wy2);
 
     const int gbase = go.v[n];
     const int G = go.v[n + 1] - gbase;
@@ -92,24 +91,13 @@ iou_best_kernel(const Geometry geo, const GtOffsets go, const float* __restrict_
         __syncthreads();
     }
     if (valid) best[(size_t)n * geo.A + lv.a_off + i] = make_uint2(__float_as_uint(best_v), (unsigned)best_g);
-    if (threadIdx.x == 0) {
-        float4 bb = s_wbox[0];
-#pragma unroll
-        for (int w = 1; w < PAA_TILE / PAA_WARP; ++w) {
-            bb.x = fminf(bb.x, s_wbox[w].x);
-            bb.y = fminf(bb.y, s_wbox[w].y);
-            bb.z = fmaxf(bb.z, s_wbox[w].z);
-            bb.w = fmaxf(bb.w, s_wbox[w].w);
-        }
-        tile_bbox[(size_t)n * geo.tiles_per_image + tile] = bb;
-    }
 }
 
 int launch_iou_best(const Geometry& geo, const GtOffsets& go, const float* gt_boxes,
                     const LossWorkspace& ws, cudaStream_t stream) {
     int grid = geo.num_images * geo.tiles_per_image;
     KernelTimer timer(PAA_KERNEL_IOU_BEST, stream);
-    iou_best_kernel<<<grid, PAA_TILE, 0, stream>>>(geo, go, gt_boxes, ws.gtmax, ws.best, ws.tile_bbox);
+    iou_best_kernel<<<grid, PAA_TILE, 0, stream>>>(geo, go, gt_boxes, ws.gtmax, ws.best);
     PAA_LAUNCH_CHECK("iou_best_kernel");
     return 0;
 }
@@ -154,10 +142,12 @@ __global__ void __launch_bounds__(PAA_TILE)
 match_score_kernel(const Geometry geo, const GtOffsets go, const float* __restrict__ gt_boxes,
                    const int64_t* __restrict__ gt_labels, const unsigned* __restrict__ gtmax,
                    const uint2* __restrict__ best, const LossScalars sc, int* __restrict__ matched,
-                   float* __restrict__ score, int* __restrict__ paa_label, int* __restrict__ img_flags,
+                   float* __restrict__ score, int* __restrict__ paa_label, uint4* __restrict__ tile_gtmask,
                    const LossDebug dbg) {
     __shared__ int s_lq[PAA_TILE];
     __shared__ int s_nlq;
+    __shared__ unsigned s_mask[4];
+    if (threadIdx.x < 4) s_mask[threadIdx.x] = 0u;
 
     const int n = blockIdx.x / geo.tiles_per_image;
     const int tile = blockIdx.x - n * geo.tiles_per_image;
@@ -190,7 +180,6 @@ match_score_kernel(const Geometry geo, const GtOffsets go, const float* __restri
         if (g < G) {
             const unsigned u = gtmax[gbase + g];
             if (__uint_as_float(u) < thr) s_lq[atomicAdd(&s_nlq, 1)] = g;
-            if (u == 0u && tile == 0) atomicOr(&img_flags[n], 1);
         }
         __syncthreads();
         const int nlq = s_nlq;
@@ -204,6 +193,12 @@ match_score_kernel(const Geometry geo, const GtOffsets go, const float* __restri
         }
         __syncthreads();
     }
+    // which GTs (index mod 128) have matched anchors in this tile: lets the per-GT selection kernel
+    // skip every tile that cannot contain one of its anchors, with no false negatives
+    if (valid && m >= 0) atomicOr(&s_mask[(m & 127) >> 5], 1u << (m & 31));
+    __syncthreads();
+    if (threadIdx.x == 0)
+        tile_gtmask[(size_t)n * geo.tiles_per_image + tile] = make_uint4(s_mask[0], s_mask[1], s_mask[2], s_mask[3]);
     if (!valid) return;
 
     int label = 0;
@@ -236,7 +231,7 @@ int launch_match_score(const Geometry& geo, const GtOffsets& go, const float* gt
     int grid = geo.num_images * geo.tiles_per_image;
     KernelTimer timer(PAA_KERNEL_MATCH_SCORE, stream);
     match_score_kernel<<<grid, PAA_TILE, 0, stream>>>(geo, go, gt_boxes, gt_labels, ws.gtmax, ws.best, sc,
-                                                      ws.matched, ws.score, ws.paa_label, ws.img_flags, dbg);
+                                                      ws.matched, ws.score, ws.paa_label, ws.tile_gtmask, dbg);
     PAA_LAUNCH_CHECK("match_score_kernel");
     return 0;
 }
@@ -274,11 +269,11 @@ __device__ __forceinline__ double logsumexp2_resp(double a0, double a1, double* 
     }
     const bool first_hi = a0 > a1;
     const double hi = first_hi ? a0 : a1, lo = first_hi ? a1 : a0;
-    const double s = exp(lo - hi);
+    const double s = exp_nonpos(lo - hi);
     const double rh = 1.0 / (1.0 + s), rl = s * rh;
     *r0 = first_hi ? rh : rl;
     *r1 = first_hi ? rl : rh;
-    return (log1p(s) + 0.0) + hi;
+    return (log1p_unit(s) + 0.0) + hi;
 }
 
 struct GmmState {
@@ -343,9 +338,9 @@ __device__ int gmm_positive_prefix(const float (&x)[SPL], int n, int lane, doubl
     const double EPS10 = 10.0 * 2.220446049250313e-16;
     for (int it = 1; it <= 100; ++it) {
         n_iter = it;
-        const double lw0 = log(s.w0), lw1 = log(s.w1);
-        const float ld0 = s.first ? 0.f : __double2float_rn(log((double)s.pc0));
-        const float ld1 = s.first ? 0.f : __double2float_rn(log((double)s.pc1));
+        const double lw0 = log_pos(s.w0), lw1 = log_pos(s.w1);
+        const float ld0 = s.first ? 0.f : __double2float_rn(log_pos((double)s.pc0));
+        const float ld1 = s.first ? 0.f : __double2float_rn(log_pos((double)s.pc1));
         double r0[SPL], r1[SPL];
         double s_r0 = 0, s_r1 = 0, s_r0x = 0, s_r1x = 0, s_lpn = 0;
 #pragma unroll
@@ -447,9 +442,9 @@ template <int SPL>
 __global__ void __launch_bounds__(kSelWarps * PAA_WARP)
 select_gmm_kernel(const Geometry geo, const GtOffsets go, int num_gt_total,
                   const float* __restrict__ gt_boxes, const int64_t* __restrict__ gt_labels,
-                  const LossScalars sc, const float4* __restrict__ tile_bbox,
+                  const LossScalars sc, const uint4* __restrict__ tile_gtmask,
                   const int* __restrict__ matched, const float* __restrict__ score,
-                  const int* __restrict__ img_flags, int* __restrict__ paa_label,
+                  int* __restrict__ paa_label,
                   int* __restrict__ part_npos, double* __restrict__ part_siou,
                   unsigned* __restrict__ ticket, double* __restrict__ local_norm,
                   double* __restrict__ normalisers, const LossDebug dbg) {
@@ -470,7 +465,8 @@ select_gmm_kernel(const Geometry geo, const GtOffsets go, int num_gt_total,
         const int g_local = gi - go.v[n];
         const float4 gt = ldg4(gt_boxes + (size_t)gi * 4);
         const int cls_label = (int)gt_labels[gi];
-        const bool nocull = (img_flags[n] & 1) || !(sc.iou_threshold > 0.0f);
+        const unsigned gbit = 1u << (g_local & 31);
+        const int gword = (g_local & 127) >> 5;
         const int* mrow = matched + (size_t)n * geo.A;
         const float* srow = score + (size_t)n * geo.A;
         unsigned long long* keys = s_key[warp];
@@ -485,14 +481,9 @@ select_gmm_kernel(const Geometry geo, const GtOffsets go, int num_gt_total,
                     const int t = t0 + lane;
                     bool hit = false;
                     if (t < t_end) {
-                        if (nocull) {
-                            hit = true;
-                        } else {
-                            const float4 bb = tile_bbox[(size_t)n * geo.tiles_per_image + t];
-                            float w = __fadd_rn(__fsub_rn(fminf(gt.z, bb.z), fmaxf(gt.x, bb.x)), 1.0f);
-                            float h = __fadd_rn(__fsub_rn(fminf(gt.w, bb.w), fmaxf(gt.y, bb.y)), 1.0f);
-                            hit = (w > 0.0f) && (h > 0.0f);
-                        }
+                        const uint4 gm = __ldg(tile_gtmask + (size_t)n * geo.tiles_per_image + t);
+                        const unsigned word = gword == 0 ? gm.x : (gword == 1 ? gm.y : (gword == 2 ? gm.z : gm.w));
+                        hit = (word & gbit) != 0u;
                     }
                     unsigned tm = __ballot_sync(PAA_FULL, hit);
                     while (tm) {
@@ -500,18 +491,20 @@ select_gmm_kernel(const Geometry geo, const GtOffsets go, int num_gt_total,
                         tm &= tm - 1;
                         const int base = (tt - lv.tile_off) * PAA_TILE;
                         int mv[PAA_TILE / PAA_WARP];
+                        float sv[PAA_TILE / PAA_WARP];
 #pragma unroll
-                        for (int r = 0; r < PAA_TILE / PAA_WARP; ++r) {
+                        for (int r = 0; r < PAA_TILE / PAA_WARP; ++r) {     // 8 independent loads in flight
                             const int i = base + r * PAA_WARP + lane;
-                            mv[r] = (i < lv.n_anchor) ? __ldg(mrow + lv.a_off + i) : -2;
+                            const bool in = i < lv.n_anchor;
+                            mv[r] = in ? __ldg(mrow + lv.a_off + i) : -2;
+                            sv[r] = in ? __ldg(srow + lv.a_off + i) : 0.0f;
                         }
 #pragma unroll
                         for (int r = 0; r < PAA_TILE / PAA_WARP; ++r) {
                             const int i = base + r * PAA_WARP + lane;
                             bool is = (mv[r] == g_local);
                             unsigned long long key = kEmptyKey;
-                            if (is) key = ((unsigned long long)ordered_bits(srow[lv.a_off + i]) << 32) |
-                                          (unsigned)(lv.a_off + i);
+                            if (is) key = ((unsigned long long)ordered_bits(sv[r]) << 32) | (unsigned)(lv.a_off + i);
                             // keys that cannot enter the current top-K are dropped before the serial
                             // insertion (the K-th key only ever decreases, so a stale bound is safe)
                             const unsigned long long kth = __shfl_sync(PAA_FULL, mine, K - 1);
@@ -631,7 +624,7 @@ int launch_select_gmm(const Geometry& geo, const GtOffsets& go, int num_gt_total
     KernelTimer timer(PAA_KERNEL_SELECT_GMM, stream);
 #define PAA_SEL_LAUNCH(SPL)                                                                           \
     select_gmm_kernel<SPL><<<grid, threads, 0, stream>>>(geo, go, num_gt_total, gt_boxes, gt_labels, sc, \
-        ws.tile_bbox, ws.matched, score_src, ws.img_flags, ws.paa_label, ws.part_npos, ws.part_siou,  \
+        ws.tile_gtmask, ws.matched, score_src, ws.paa_label, ws.part_npos, ws.part_siou,              \
         ws.ticket, ws.local_norm, normalisers, dbg)
     if (cap <= 32) PAA_SEL_LAUNCH(1);
     else if (cap <= 64) PAA_SEL_LAUNCH(2);

@@ -21,7 +21,7 @@ struct LossWorkspace {
     int* matched;           // [N*A]
     float* score;           // [N*A]    anchor score (combined loss) of IoU-positive anchors
     int* paa_label;         // [N*A]
-    float4* tile_bbox;      // [N*T]
+    uint4* tile_gtmask;     // [N*T]    bit (g mod 128): GT g has a matched anchor in the tile
     int* part_npos;         // [sumG]
     double* part_siou;      // [sumG]
     double* local_norm;     // [2]      this rank's {num_pos, sum_iou} (before the all-reduce)
@@ -48,7 +48,7 @@ inline LossWorkspace carve_loss_workspace(void* base, int N, int A, int sumG, in
     w.matched = reinterpret_cast<int*>(take(sizeof(int) * NA));
     w.score = reinterpret_cast<float*>(take(sizeof(float) * NA));
     w.paa_label = reinterpret_cast<int*>(take(sizeof(int) * NA));
-    w.tile_bbox = reinterpret_cast<float4*>(take(sizeof(float4) * (size_t)N * tiles_per_image));
+    w.tile_gtmask = reinterpret_cast<uint4*>(take(sizeof(uint4) * (size_t)N * tiles_per_image));
     w.part_npos = reinterpret_cast<int*>(take(sizeof(int) * (size_t)(sumG > 0 ? sumG : 1)));
     w.part_siou = reinterpret_cast<double*>(take(sizeof(double) * (size_t)(sumG > 0 ? sumG : 1)));
     w.local_norm = reinterpret_cast<double*>(take(sizeof(double) * 2));

@@ -61,6 +61,8 @@ struct PostWorkspace {
     int* out_rank;        // [N*capN]   sorted index of every output row (for voting)
     unsigned char* flag_by_pos; // [N*capN] survivor flag by pre-NMS position
     int* rank_by_pos;     // [N*capN]   sorted index by pre-NMS position
+    int* g_pos;           // [N*capN]   positions grouped by label (arbitrary order inside a label)
+    float* g_score;       // [N*capN]
     size_t total_bytes;
 };
 
@@ -102,6 +104,8 @@ static PostWorkspace carve_post(void* base, int N, int A, int C, int L, int topn
     w.out_rank = (int*)take((size_t)N * capN * 4);
     w.flag_by_pos = (unsigned char*)take((size_t)N * capN);
     w.rank_by_pos = (int*)take((size_t)N * capN * 4);
+    w.g_pos = (int*)take((size_t)N * capN * 4);
+    w.g_score = (float*)take((size_t)N * capN * 4);
     w.total_bytes = off;
     return w;
 }
@@ -492,6 +496,86 @@ post_rank_kernel(int L, int topn, const int* __restrict__ pre_cnt, const float4*
 }
 
 // ---------------------------------------------------------------------------------------------
+// Fused-path ordering for labels known to lie in [0, C]: group the boxes of an image by label with a
+// shared-memory histogram (which is also the table of label runs), then rank every box inside its own
+// run only -- O(n * run length) instead of O(n^2).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+post_group_kernel(int L, int topn, int C, const int* __restrict__ pre_cnt, const float* __restrict__ pre_score,
+                  const int* __restrict__ pre_label, int* __restrict__ g_pos, float* __restrict__ g_score,
+                  int* __restrict__ seg_start, int* __restrict__ n_seg, int* __restrict__ total) {
+    extern __shared__ int s_lab[];          // [C+2] run starts, then [C+2] fill cursors
+    __shared__ int s_cnt[PAA_MAX_LEVELS];
+    const int n = blockIdx.x;
+    const int capN = L * topn;
+    const size_t base = (size_t)n * capN;
+    int* s_start = s_lab;
+    int* s_cur = s_lab + (C + 2);
+    if (threadIdx.x < L) s_cnt[threadIdx.x] = pre_cnt[n * L + threadIdx.x];
+    for (int c = threadIdx.x; c < C + 2; c += 1024) s_start[c] = 0;
+    __syncthreads();
+    for (int pos = threadIdx.x; pos < capN; pos += 1024)
+        if ((pos % topn) < s_cnt[pos / topn]) {
+            const int lab = min(max(pre_label[base + pos], 0), C);
+            atomicAdd(&s_start[lab + 1], 1);                     // counts shifted by one: scan gives starts
+        }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int c = 0; c < C + 2; ++c) {                        // s_start[c] = first sorted index of label c
+            run += s_start[c];
+            s_start[c] = run;
+        }
+    }
+    __syncthreads();
+    int* ss = seg_start + (size_t)n * (capN + 1);
+    for (int c = threadIdx.x; c < C + 2; c += 1024) {
+        s_cur[c] = s_start[c];
+        ss[c] = s_start[c];
+    }
+    if (threadIdx.x == 0) {
+        n_seg[n] = C + 1;
+        total[n] = s_start[C + 1];
+    }
+    __syncthreads();
+    for (int pos = threadIdx.x; pos < capN; pos += 1024)
+        if ((pos % topn) < s_cnt[pos / topn]) {
+            const int lab = min(max(pre_label[base + pos], 0), C);
+            const int slot = atomicAdd(&s_cur[lab], 1);
+            g_pos[base + slot] = pos;
+            g_score[base + slot] = pre_score[base + pos];
+        }
+}
+
+__global__ void __launch_bounds__(256)
+post_class_rank_kernel(int capN, const int* __restrict__ total, const int* __restrict__ seg_start,
+                       const int* __restrict__ g_pos, const float* __restrict__ g_score,
+                       const float4* __restrict__ pre_box, const int* __restrict__ pre_label,
+                       float4* __restrict__ s_box, float* __restrict__ s_score, int* __restrict__ s_label,
+                       int* __restrict__ s_pos) {
+    const int n = blockIdx.y;
+    const int e = blockIdx.x * 256 + threadIdx.x;
+    if (e >= total[n]) return;
+    const size_t base = (size_t)n * capN;
+    const int pos = g_pos[base + e];
+    const float sc = g_score[base + e];
+    const int lab = pre_label[base + pos];
+    const int* ss = seg_start + (size_t)n * (capN + 1);
+    const int a = ss[lab], b = ss[lab + 1];
+    int rank = 0;
+    for (int j = a; j < b; ++j) {                                // better = higher score, then lower position
+        const float sj = g_score[base + j];
+        const int pj = g_pos[base + j];
+        rank += (sj > sc || (sj == sc && pj < pos)) ? 1 : 0;
+    }
+    const size_t o = base + a + rank;
+    s_box[o] = pre_box[base + pos];
+    s_score[o] = sc;
+    s_label[o] = lab;
+    s_pos[o] = pos;
+}
+
+// ---------------------------------------------------------------------------------------------
 // segments: first sorted index of every run of equal labels (one block per image)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024)
@@ -534,57 +618,73 @@ post_segments_kernel(int capN, const int* __restrict__ total, const int* __restr
 // (csrc/cuda/ml_nms.cu:13-24,55-70).  Tiles whose row and column label ranges are disjoint are
 // skipped and never read by the scan.
 // ---------------------------------------------------------------------------------------------
+// One block per (image, 64-row block); it walks the column blocks to its right for as long as their
+// first label does not exceed the row block's last label (boxes are sorted by label).
 __global__ void __launch_bounds__(64)
 post_nms_mask_kernel(int capN, int nbw, float thr, const int* __restrict__ total,
                      const float4* __restrict__ s_box, const int* __restrict__ s_label,
                      unsigned long long* __restrict__ mask) {
-    const int n = blockIdx.z;
-    const int rb = blockIdx.y, cb = blockIdx.x;
-    if (cb < rb) return;
-    const int cnt = total[n];
-    const int r0 = rb * 64, c0 = cb * 64;
-    if (r0 >= cnt || c0 >= cnt) return;
-    const size_t base = (size_t)n * capN;
-    const int r_last = min(cnt, r0 + 64) - 1;
-    if (s_label[base + c0] > s_label[base + r_last]) return;      // sorted by label: no shared label
     __shared__ float4 s_cb[64];
     __shared__ float s_ca[64];
     __shared__ int s_cl[64];
-    const int csize = min(64, cnt - c0);
-    if (threadIdx.x < csize) {
-        const float4 b = s_box[base + c0 + threadIdx.x];
-        s_cb[threadIdx.x] = b;
-        s_ca[threadIdx.x] = area_plus1(b);
-        s_cl[threadIdx.x] = s_label[base + c0 + threadIdx.x];
-    }
-    __syncthreads();
+    const int n = blockIdx.y;
+    const int rb = blockIdx.x;
+    const int cnt = total[n];
+    const int r0 = rb * 64;
+    if (r0 >= cnt) return;
+    const size_t base = (size_t)n * capN;
+    const int last_label = s_label[base + min(cnt, r0 + 64) - 1];
     const int r = r0 + threadIdx.x;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    int al = -1;
     if (r < cnt) {
-        const float4 a = s_box[base + r];
-        const float aa = area_plus1(a);
-        const int al = s_label[base + r];
-        unsigned long long bits = 0ull;
-        const int start = (rb == cb) ? threadIdx.x + 1 : 0;
-        for (int j = start; j < csize; ++j) {
-            if (s_cl[j] != al) continue;
-            if (iou_plus1(a, aa, s_cb[j], s_ca[j]) > thr) bits |= 1ull << j;
+        a = s_box[base + r];
+        al = s_label[base + r];
+    }
+    const float aa = area_plus1(a);
+    for (int cb = rb; cb * 64 < cnt; ++cb) {
+        const int c0 = cb * 64;
+        if (s_label[base + c0] > last_label) break;               // no shared label from here on
+        const int csize = min(64, cnt - c0);
+        __syncthreads();
+        if (threadIdx.x < csize) {
+            const float4 b = s_box[base + c0 + threadIdx.x];
+            s_cb[threadIdx.x] = b;
+            s_ca[threadIdx.x] = area_plus1(b);
+            s_cl[threadIdx.x] = s_label[base + c0 + threadIdx.x];
         }
-        mask[(base + r) * nbw + cb] = bits;
+        __syncthreads();
+        if (r < cnt) {
+            unsigned long long bits = 0ull;
+            const int start = (rb == cb) ? threadIdx.x + 1 : 0;
+            for (int j = start; j < csize; ++j) {
+                if (s_cl[j] != al) continue;
+                if (iou_plus1(a, aa, s_cb[j], s_ca[j]) > thr) bits |= 1ull << j;
+            }
+            mask[(base + r) * nbw + cb] = bits;
+        }
     }
 }
 
 // ---------------------------------------------------------------------------------------------
 // nms_scan: greedy suppression inside one label run, boxes visited in descending score
-// (csrc/cuda/ml_nms.cu:116-128).  One warp per run; its removed-bits live in shared memory.
+// (csrc/cuda/ml_nms.cu:116-128).  One warp per run, one 64-box word at a time: the word's incoming
+// removed-bits are OR-ed from the rows kept in earlier words of the run, the 64 x 64 diagonal block is
+// held in registers (two rows per lane) and resolved with shuffles -- no memory access in the serial part.
 // ---------------------------------------------------------------------------------------------
 constexpr int kScanWarps = 4;
+
+__device__ __forceinline__ unsigned long long warp_or64(unsigned long long v) {
+    const unsigned lo = __reduce_or_sync(PAA_FULL, (unsigned)v);
+    const unsigned hi = __reduce_or_sync(PAA_FULL, (unsigned)(v >> 32));
+    return ((unsigned long long)hi << 32) | lo;
+}
 
 __global__ void __launch_bounds__(kScanWarps * 32)
 post_nms_scan_kernel(int capN, int nbw, int segs_per_image, int num_images,
                      const int* __restrict__ seg_start,
                      const int* __restrict__ n_seg, const unsigned long long* __restrict__ mask,
                      unsigned char* __restrict__ keep_sorted) {
-    extern __shared__ unsigned long long s_removed[];       // [kScanWarps][nbw]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gw = blockIdx.x * kScanWarps + warp;
     const int n = gw / segs_per_image;
@@ -593,18 +693,27 @@ post_nms_scan_kernel(int capN, int nbw, int segs_per_image, int num_images,
     if (s >= n_seg[n]) return;
     const int* ss = seg_start + (size_t)n * (capN + 1);
     const int a = ss[s], b = ss[s + 1];
-    const int w_lo = a >> 6, w_hi = (b - 1) >> 6;
-    unsigned long long* rem = s_removed + (size_t)warp * nbw;
-    for (int w = w_lo + lane; w <= w_hi; w += 32) rem[w] = 0ull;
-    __syncwarp();
+    if (b <= a) return;
     const size_t base = (size_t)n * capN;
-    for (int i = a; i < b; ++i) {
-        const bool dead = (rem[i >> 6] >> (i & 63)) & 1ull;
-        if (!dead) {
-            const unsigned long long* row = mask + (base + i) * nbw;
-            for (int w = (i >> 6) + lane; w <= w_hi; w += 32) rem[w] |= row[w];
+    const int w_lo = a >> 6, w_hi = (b - 1) >> 6;
+    for (int w = w_lo; w <= w_hi; ++w) {
+        const int lo_i = max(a, w * 64), hi_i = min(b, w * 64 + 64);
+        // removed bits contributed by the rows kept in earlier words of this run
+        unsigned long long R = 0ull;
+        for (int i = a + lane; i < lo_i; i += 32)
+            if (keep_sorted[base + i]) R |= mask[(base + i) * nbw + w];
+        R = warp_or64(R);
+        const int r0 = w * 64 + lane, r1 = r0 + 32;
+        const unsigned long long d0 = (r0 >= lo_i && r0 < hi_i) ? mask[(base + r0) * nbw + w] : 0ull;
+        const unsigned long long d1 = (r1 >= lo_i && r1 < hi_i) ? mask[(base + r1) * nbw + w] : 0ull;
+        unsigned long long K = 0ull;
+        for (int j = lo_i - w * 64; j < hi_i - w * 64; ++j) {
+            if ((R >> j) & 1ull) continue;                      // warp-uniform
+            K |= 1ull << j;
+            R |= (j < 32) ? __shfl_sync(PAA_FULL, d0, j) : __shfl_sync(PAA_FULL, d1, j - 32);
         }
-        if (lane == 0) keep_sorted[base + i] = dead ? 0 : 1;
+        if (r0 >= lo_i && r0 < hi_i) keep_sorted[base + r0] = (unsigned char)((K >> lane) & 1ull);
+        if (r1 >= lo_i && r1 < hi_i) keep_sorted[base + r1] = (unsigned char)((K >> (lane + 32)) & 1ull);
         __syncwarp();
     }
 }
@@ -889,29 +998,42 @@ int run_postprocess(const Geometry& geo, const PaaPostArgs* a, cudaStream_t stre
                                                      a->dbg_pre_count);
         PAA_LAUNCH_CHECK("post_debug_pre_kernel");
     }
-    {
+    const bool grouped = capN >= C + 1 && (size_t)(2 * (C + 2)) * sizeof(int) <= 40 * 1024;
+    if (grouped) {
+        // labels are 1..C: group by label, rank inside the label run (O(n * run) instead of O(n^2))
         KernelTimer t(PAA_KERNEL_POST_RANK, stream);
-        dim3 grid((capN + kRankThreads - 1) / kRankThreads, N);
-        post_rank_kernel<<<grid, kRankThreads, 0, stream>>>(L, topn, w.pre_cnt, w.pre_box, w.pre_score, w.pre_label,
-                                                            w.s_box, w.s_score, w.s_label, w.s_pos, w.total);
+        post_group_kernel<<<N, 1024, 2 * (C + 2) * sizeof(int), stream>>>(L, topn, C, w.pre_cnt, w.pre_score,
+                                                                          w.pre_label, w.g_pos, w.g_score,
+                                                                          w.seg_start, w.n_seg, w.total);
+        dim3 grid((capN + 255) / 256, N);
+        post_class_rank_kernel<<<grid, 256, 0, stream>>>(capN, w.total, w.seg_start, w.g_pos, w.g_score, w.pre_box,
+                                                         w.pre_label, w.s_box, w.s_score, w.s_label, w.s_pos);
+        PAA_LAUNCH_CHECK("post_group_kernel/post_class_rank_kernel");
+    } else {
+        {
+            KernelTimer t(PAA_KERNEL_POST_RANK, stream);
+            dim3 grid((capN + kRankThreads - 1) / kRankThreads, N);
+            post_rank_kernel<<<grid, kRankThreads, 0, stream>>>(L, topn, w.pre_cnt, w.pre_box, w.pre_score,
+                                                                w.pre_label, w.s_box, w.s_score, w.s_label, w.s_pos,
+                                                                w.total);
+        }
+        PAA_LAUNCH_CHECK("post_rank_kernel");
+        post_segments_kernel<<<N, 1024, 0, stream>>>(capN, w.total, w.s_label, w.seg_start, w.n_seg);
+        PAA_LAUNCH_CHECK("post_segments_kernel");
     }
-    PAA_LAUNCH_CHECK("post_rank_kernel");
-    post_segments_kernel<<<N, 1024, 0, stream>>>(capN, w.total, w.s_label, w.seg_start, w.n_seg);
-    PAA_LAUNCH_CHECK("post_segments_kernel");
     if (!a->skip_nms) {
         {
             KernelTimer t(PAA_KERNEL_POST_NMS_MASK, stream);
-            dim3 grid(nbw, nbw, N);
+            dim3 grid(nbw, N);
             post_nms_mask_kernel<<<grid, 64, 0, stream>>>(capN, nbw, a->nms_thresh, w.total, w.s_box, w.s_label,
                                                           w.mask);
         }
         PAA_LAUNCH_CHECK("post_nms_mask_kernel");
         {
             KernelTimer t(PAA_KERNEL_POST_NMS_SCAN, stream);
-            const int segs = capN < C ? capN : C;          // labels are 1..C: at most C runs per image
+            const int segs = grouped ? C + 1 : (capN < C ? capN : C);   // label runs per image (upper bound)
             const int warps = N * segs;
-            const size_t smem = (size_t)kScanWarps * nbw * sizeof(unsigned long long);
-            post_nms_scan_kernel<<<(warps + kScanWarps - 1) / kScanWarps, kScanWarps * 32, smem, stream>>>(
+            post_nms_scan_kernel<<<(warps + kScanWarps - 1) / kScanWarps, kScanWarps * 32, 0, stream>>>(
                 capN, nbw, segs, N, w.seg_start, w.n_seg, w.mask, w.keep_sorted);
         }
         PAA_LAUNCH_CHECK("post_nms_scan_kernel");
@@ -1031,11 +1153,10 @@ int run_ml_nms(const float* boxes, const float* scores, const float* labels, int
     PAA_LAUNCH_CHECK("post_rank_kernel");
     post_segments_kernel<<<1, 1024, 0, stream>>>(n, w.total, w.s_label, w.seg_start, w.n_seg);
     PAA_LAUNCH_CHECK("post_segments_kernel");
-    dim3 mgrid(nbw, nbw, 1);
+    dim3 mgrid(nbw, 1);
     post_nms_mask_kernel<<<mgrid, 64, 0, stream>>>(n, nbw, thresh, w.total, w.s_box, w.s_label, w.mask);
     PAA_LAUNCH_CHECK("post_nms_mask_kernel");
-    const size_t smem = (size_t)kScanWarps * nbw * sizeof(unsigned long long);
-    post_nms_scan_kernel<<<(n + kScanWarps - 1) / kScanWarps, kScanWarps * 32, smem, stream>>>(
+    post_nms_scan_kernel<<<(n + kScanWarps - 1) / kScanWarps, kScanWarps * 32, 0, stream>>>(
         n, nbw, n, 1, w.seg_start, w.n_seg, w.mask, w.keep_sorted);
     PAA_LAUNCH_CHECK("post_nms_scan_kernel");
     ml_nms_scatter_kernel<<<(n + 255) / 256, 256, 0, stream>>>(n, w.s_pos, w.keep_sorted, keep, num_keep);

@@ -28,8 +28,15 @@ def get_num_gpus():
     return int(os.environ["WORLD_SIZE"]) if "WORLD_SIZE" in os.environ else 1   # loss.py:18-19
 
 
-def _ptr(t):
-    return None if t is None else t.data_ptr()
+def reduce_normalisers(normalisers):
+    """The path's only exchange step: sums the 2-element ``{num_pos, sum IoU}`` tensor over ranks in
+    place (loss.py:22-28 applied once to both normalisers, loss.py:321,338).  Stream-ordered; no host
+    synchronisation.  A no-op for a single process."""
+    if get_num_gpus() <= 1:
+        return normalisers
+    import torch.distributed as dist
+    dist.all_reduce(normalisers, op=dist.ReduceOp.SUM)
+    return normalisers
 
 
 def _head(t, name):
@@ -235,9 +242,8 @@ class PAALossComputation(object):
         stream = torch.cuda.current_stream(device).cuda_stream
         with torch.cuda.device(device):
             if world > 1:
-                import torch.distributed as dist
                 _lib.check(self._lib.paa_assign(C.byref(args), stream), "paa_assign")
-                dist.all_reduce(normalisers, op=dist.ReduceOp.SUM)      # loss.py:321,338 in one message
+                reduce_normalisers(normalisers)                         # loss.py:321,338 in one message
                 _lib.check(self._lib.paa_loss(C.byref(args), stream), "paa_loss")
             else:
                 _lib.check(self._lib.paa_assign_loss(C.byref(args), stream), "paa_assign_loss")

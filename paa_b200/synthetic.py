@@ -168,13 +168,24 @@ def make_batch(seed: int, num_images: int, image_hw: Tuple[int, int] = (800, 133
 
 def make_inference_batch(seed: int, num_images: int, image_hw: Tuple[int, int] = (800, 1333),
                          cls_mean: float = -3.0, cls_std: float = 1.5, n_objects: int = 12,
-                         strides=STRIDES) -> SyntheticBatch:
+                         strides=STRIDES, candidates_per_level=None) -> SyntheticBatch:
     """Post-processing-shaped batch (config C4): dense candidates on every level plus a few
     object-like clusters so that NMS has overlapping same-class boxes to suppress and score voting
     has neighbours to average."""
     b = make_batch(seed, num_images, image_hw, gt_per_image=n_objects, trained_like=True,
                    cls_mean=cls_mean, cls_std=cls_std, strides=strides)
     b.meta["inference"] = True
+    if candidates_per_level is not None:
+        # detector-like sparsity: shift every level so that about `candidates_per_level` of its
+        # (location, class) logits pass sigmoid(x) > 0.05 -- a few thousand on P3 (0.3 % of 1.3 M) up to
+        # most of P7 -- instead of the same dense fraction everywhere
+        gate = math.log(0.05 / 0.95)
+        for l, t in enumerate(b.box_cls):
+            n_el = t.shape[1] * t.shape[2] * t.shape[3]
+            frac = min(0.9, candidates_per_level / float(n_el))
+            z = float(torch.special.ndtri(torch.tensor(1.0 - frac, dtype=torch.float64)))
+            t.add_((gate - z * cls_std) - cls_mean).clamp_(-12.0, 12.0)
+        b.meta["candidates_per_level"] = candidates_per_level
     return b
 
 

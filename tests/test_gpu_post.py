@@ -110,9 +110,12 @@ def test_nms_random_against_oracle_including_single_class_crowd():
         assert np.array_equal(got.cpu().numpy(), want), (n, n_cls)
 
 
-def test_c4_against_oracle_full_resolution():
-    """Config C4 shape (800x1333, 1000 candidates/level, voting on) for 2 images against the oracle."""
-    b = synthetic.make_inference_batch(seed=4000, num_images=2, image_hw=(800, 1333))
+@pytest.mark.parametrize("per_level", [None, 4000])
+def test_c4_against_oracle_full_resolution(per_level):
+    """Config C4 shape (800x1333, 1000 candidates/level, voting on) for 2 images against the oracle,
+    dense (49 % of logits are candidates) and detector-like sparse (~4000 per level)."""
+    b = synthetic.make_inference_batch(seed=4000, num_images=2, image_hw=(800, 1333),
+                                       candidates_per_level=per_level)
     want = post_oracle.postprocess(b.box_cls, b.box_regression, b.iou_pred, b.anchors, b.image_sizes)
     pp = _postprocessor()
     pp.debug = True

@@ -139,7 +139,7 @@ class ClockSampler(object):
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index, period_s=0.02):
+    def __init__(self, gpu_index, period_s=0.002):
         self.gpu_index = gpu_index
         self.period_s = period_s
         self.sm, self.reasons, self.max_mhz = [], set(), None

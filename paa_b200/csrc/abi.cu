@@ -115,6 +115,10 @@ static int plan_loss(const PaaLossArgs* a, LossPlan* p) {
         set_error("topk=%d unsupported (1..32, num_levels*topk <= %d)", a->topk, PAA_MAX_CANDIDATES);
         return PAA_ERR_UNSUPPORTED;
     }
+    if (a->num_classes > 1024) {
+        set_error("num_classes=%d unsupported (<= 1024)", a->num_classes);
+        return PAA_ERR_UNSUPPORTED;
+    }
     if (a->world_size < 1) {
         set_error("world_size=%d", a->world_size);
         return PAA_ERR_BAD_ARGUMENT;
@@ -133,6 +137,18 @@ static int plan_loss(const PaaLossArgs* a, LossPlan* p) {
     }
     p->go.v[a->num_images] = a->gt_offsets[a->num_images];
     p->sumG = a->gt_offsets[a->num_images];
+    // images with many GT boxes cost proportionally more in the IoU kernel: schedule them first
+    for (int i = 0; i < a->num_images; ++i) p->go.by_load[i] = (unsigned char)i;
+    for (int i = 1; i < a->num_images; ++i) {          // insertion sort, N <= 256
+        const unsigned char key = p->go.by_load[i];
+        const int kg = p->go.v[key + 1] - p->go.v[key];
+        int j = i - 1;
+        while (j >= 0 && (p->go.v[p->go.by_load[j] + 1] - p->go.v[p->go.by_load[j]]) < kg) {
+            p->go.by_load[j + 1] = p->go.by_load[j];
+            --j;
+        }
+        p->go.by_load[j + 1] = key;
+    }
     if (!a->gt_boxes || !a->gt_labels || !a->workspace || !a->normalisers || !a->losses) {
         set_error("null gt_boxes / gt_labels / workspace / normalisers / losses");
         return PAA_ERR_BAD_ARGUMENT;

@@ -33,8 +33,9 @@ iou_best_kernel(const Geometry geo, const GtOffsets go, const float* __restrict_
     __shared__ float s_area[kGtChunk];
     __shared__ unsigned s_max[kGtChunk];
 
-    // heaviest tiles first: the coarse levels (last tiles of an image) intersect every GT
-    const int n = blockIdx.x % geo.num_images;
+    // heaviest blocks first: the coarse levels (last tiles of an image) intersect every GT, and the
+    // cost of a block grows with the GT count of its image
+    const int n = go.by_load[blockIdx.x % geo.num_images];
     const int tile = geo.tiles_per_image - 1 - blockIdx.x / geo.num_images;
     int first;
     const int l = tile_level(geo, tile, &first);
@@ -270,7 +271,7 @@ __device__ __forceinline__ double logsumexp2_resp(double a0, double a1, double* 
     const bool first_hi = a0 > a1;
     const double hi = first_hi ? a0 : a1, lo = first_hi ? a1 : a0;
     const double s = exp_nonpos(lo - hi);
-    const double rh = 1.0 / (1.0 + s), rl = s * rh;
+    const double rh = div_fast(1.0, 1.0 + s), rl = s * rh;
     *r0 = first_hi ? rh : rl;
     *r1 = first_hi ? rl : rh;
     return (log1p_unit(s) + 0.0) + hi;
@@ -363,8 +364,8 @@ __device__ int gmm_positive_prefix(const float (&x)[SPL], int n, int lane, doubl
         s_r1x = warp_sum(s_r1x);
         s_lpn = warp_sum(s_lpn);
         const double nk0 = s_r0 + EPS10, nk1 = s_r1 + EPS10;
-        s.mu0 = s_r0x / nk0;
-        s.mu1 = s_r1x / nk1;
+        s.mu0 = div_fast(s_r0x, nk0);
+        s.mu1 = div_fast(s_r1x, nk1);
         double c0 = 0, c1 = 0;
 #pragma unroll
         for (int k = 0; k < SPL; ++k) {
@@ -376,15 +377,15 @@ __device__ int gmm_positive_prefix(const float (&x)[SPL], int n, int lane, doubl
         }
         c0 = warp_sum(c0);
         c1 = warp_sum(c1);
-        s.var0 = __fadd_rn(__double2float_rn(c0 / nk0), 1e-6f);
-        s.var1 = __fadd_rn(__double2float_rn(c1 / nk1), 1e-6f);
+        s.var0 = __fadd_rn(__double2float_rn(div_fast(c0, nk0)), 1e-6f);
+        s.var1 = __fadd_rn(__double2float_rn(div_fast(c1, nk1)), 1e-6f);
         const double nsum = nk0 + nk1;
-        s.w0 = nk0 / nsum;
-        s.w1 = nk1 / nsum;
+        s.w0 = div_fast(nk0, nsum);
+        s.w1 = div_fast(nk1, nsum);
         s.pc0 = __fdiv_rn(1.0f, __fsqrt_rn(s.var0));
         s.pc1 = __fdiv_rn(1.0f, __fsqrt_rn(s.var1));
         s.first = false;
-        const double lb = s_lpn / (double)n;
+        const double lb = div_fast(s_lpn, (double)n);
         const double change = lb - lower;
         lower = lb;
         if (fabs(change) < 1e-3) {

@@ -40,6 +40,22 @@ PAA_HD uint64_t f64_bits(double d) {
 #endif
 }
 
+// a / b for positive normal b: reciprocal seed (MUFU.RCP64H, ~20 bits) + two Newton steps + one residual
+// correction.  ~9 dependent instructions instead of the ~25 (plus slow-path branch) of the IEEE
+// division routine; the quotient is within 1 ulp of a/b.
+PAA_HD double div_fast(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+    r = fma(fma(-b, r, 1.0), r, r);
+    r = fma(fma(-b, r, 1.0), r, r);
+    const double q = a * r;
+    return fma(fma(-b, q, a), r, q);
+#else
+    return a / b;
+#endif
+}
+
 // exp(d) for d <= 0.  Returns 0 below -708 (the result would be < 3e-308 and only ever feeds sums of O(1)).
 PAA_HD double exp_nonpos(double d) {
     if (!(d > -708.0)) return 0.0;
@@ -81,7 +97,7 @@ PAA_HD double two_atanh_small(double z) {
 // 2 atanh(z) with z = s / (2 + s) <= 1/3, no range split (no cancellation), w = z^2 <= 1/9,
 // 2z * sum_{k<=17} w^k/(2k+1)  (remainder < 2e-19)
 PAA_HD double log1p_unit(double s) {
-    const double z = s / (s + 2.0);
+    const double z = div_fast(s, s + 2.0);
     const double w = z * z, w2 = w * w, w4 = w2 * w2, w8 = w4 * w4, w16 = w8 * w8;
     const double a0 = fma(w, 3.3333333333333331e-01, 1.0);
     const double a1 = fma(w, 1.4285714285714285e-01, 2.0000000000000001e-01);
@@ -107,7 +123,7 @@ PAA_HD double log_pos(double x) {
         m *= 0.5;
         e += 1;
     }
-    const double t = two_atanh_small((m - 1.0) / (m + 1.0));
+    const double t = two_atanh_small(div_fast(m - 1.0, m + 1.0));
     const double ef = (double)e;
     return fma(ef, 6.93147180369123816490e-01, fma(ef, 1.90821492927058770002e-10, t));
 }

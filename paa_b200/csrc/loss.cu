@@ -15,8 +15,9 @@ namespace paa {
 
 constexpr int kFinalThreads = PAA_TILE;
 
-// upper bound of blocks the final kernel launches (sizes the partial-sum buffer)
-int loss_grid_blocks(int num_images, int tiles_per_image) { (void)num_images; (void)tiles_per_image; return 148 * 16; }
+// upper bound of blocks the final kernel launches (sizes the partial-sum buffer): one per (128-anchor run,
+// class chunk); 64 chunks cover C <= 1024
+int loss_grid_blocks(int num_images, int tiles_per_image) { return num_images * tiles_per_image * 64; }
 
 struct GradScales {
     float cls, reg, bce;     // d(total)/d(sum) factors
@@ -109,18 +110,27 @@ __device__ __forceinline__ float giou_loss_and_grad(float4 d, const AnchorFrame&
     return loss;
 }
 
-// Work item = 128 consecutive anchors of one level of one image x one chunk of kClsChunk classes;
-// one thread = one anchor.  Blocks are persistent (grid = SM count x resident blocks) and walk the
-// items round-robin, so partial sums are reduced once per block and the item -> block map is static
-// (bit-reproducible sums).  Every logit of a chunk is read once (a warp reads one 128-byte line per
-// class) and its gradient written once.  All classes are first treated as negatives; the single
-// positive class of a positive anchor is patched afterwards.  The chunk-0 item of a tile also handles
-// the regression / IoU-prediction losses and gradients of its anchors.
+// Work item = a run of consecutive anchors of one level of one image x one chunk of kClsChunk classes.
+// On levels whose H*W is a multiple of 4 a thread owns 4 consecutive anchors and moves float4s (one
+// address computation and one LDG.128 / STG.128 per 4 logits); other levels (the small coarse ones) use
+// one anchor per thread.  One block per item, largest items first; every block leaves its partial sums
+// in its own slot, so the final fold is order-fixed and bit-reproducible.  Every logit of a chunk is
+// read once and its gradient written once.  All classes are first treated as negatives; the single
+// positive class of a positive anchor is patched afterwards.  The chunk-0 item of a run also handles the
+// regression / IoU-prediction losses and gradients of its anchors.
 constexpr int kClsChunk = 16;
-constexpr int kClsBatch = 8;
-constexpr int kFinalBlocksPerSM = 8;
+constexpr int kVecBatch = 4;       // classes in flight per thread on the float4 path (4 x 16 B)
+constexpr int kClsBatch = 8;       // classes in flight per thread on the scalar path
+constexpr int kFinalBlocksPerSM = 6;
 
 int loss_class_chunks(int C) { return (C + kClsChunk - 1) / kClsChunk; }
+
+struct FinalPlan {
+    int item_off[PAA_MAX_LEVELS + 1];   // per image: first item of each level (items = runs x chunks)
+    int vec[PAA_MAX_LEVELS];            // 1: float4 path
+    int n_chunks;
+    int items_per_image;
+};
 
 // negative-class focal term without its (1-alpha) factor, and the gradient with `k` = (1-alpha) * scale
 template <bool kG2>
@@ -133,112 +143,218 @@ __device__ __forceinline__ void neg_term_grad(float x, float gamma, float k, flo
     *grad = (mod * fmaf(gq, nlogq, s.p)) * k;
 }
 
+struct FinalCtx {
+    float alpha, gamma, oma, kneg;
+    GradScales gs;
+};
+
+// swaps the (already written) negative-class result of the labelled class for the positive-class one
+template <bool kGrads, bool kG2>
+__device__ __forceinline__ void patch_positive(const float* __restrict__ cls, float* __restrict__ gcls,
+                                               unsigned elem_off, const FinalCtx& cx, float* fix_sum) {
+    const float xp = __ldg(cls + elem_off);
+    const SigmoidParts sp = sigmoid_parts(xp);
+    float tn, gn, tp, gp;
+    focal_negative(xp, sp, cx.gamma, kG2, cx.oma, &tn, &gn);
+    focal_positive(xp, sp, cx.gamma, kG2, cx.alpha, &tp, &gp);
+    *fix_sum += tp - tn;
+    if (kGrads && gcls) gcls[elem_off] = gp * cx.gs.cls;
+}
+
+// regression + IoU-prediction losses / gradients of one positive anchor (loss.py:328-349)
+__device__ __forceinline__ void positive_box_terms(const Geometry& geo, const LevelView& lv, const GtOffsets& go,
+                                                   const float* __restrict__ gt_boxes, const LossScalars& sc,
+                                                   const FinalCtx& cx, int n, int i, int m, float4 d, float xi,
+                                                   float* reg_sum, float* bce_sum, float4* gd, float* gi) {
+    const float4 a = ldg4(lv.anchors + (size_t)n * geo.anchor_image_stride + (size_t)i * 4);
+    const AnchorFrame f = anchor_frame(a);
+    const float4 gt = ldg4(gt_boxes + (size_t)(go.v[n] + m) * 4);
+    const float4 tgt = decode_box(encode_box(gt, f), f);
+    float w = 1.0f;
+    if (sc.use_iou_pred) {
+        const float4 pred = decode_box(d, f);
+        const float q = iou_plus1(tgt, area_plus1(tgt), pred, area_plus1(pred));
+        const float ei = expf(-fabsf(xi));
+        *bce_sum += fmaxf(xi, 0.0f) - xi * q + log1pf(ei);
+        const float sig = (xi >= 0.0f) ? 1.0f / (1.0f + ei) : ei / (1.0f + ei);
+        *gi = (sig - q) * cx.gs.bce;
+        if (cx.gs.weighted) w = q;
+    }
+    float4 gdd;
+    const float gl = giou_loss_and_grad(d, f, tgt, &gdd);
+    *reg_sum += gl * w;
+    const float k = w * cx.gs.reg;
+    *gd = make_float4(gdd.x * k, gdd.y * k, gdd.z * k, gdd.w * k);
+}
+
 template <bool kGrads, bool kG2>
 __global__ void __launch_bounds__(kFinalThreads, kFinalBlocksPerSM)
-final_loss_kernel(const Geometry geo, const GtOffsets go, const float* __restrict__ gt_boxes,
-                  const LossScalars sc, const int* __restrict__ paa_label, const int* __restrict__ matched,
+final_loss_kernel(const Geometry geo, const GtOffsets go, const FinalPlan plan,
+                  const float* __restrict__ gt_boxes, const LossScalars sc,
+                  const int* __restrict__ paa_label, const int* __restrict__ matched,
                   const double* __restrict__ norm, const double* __restrict__ local_norm,
-                  const float* __restrict__ gout, double* __restrict__ block_part, const int n_chunks,
-                  const int n_items) {
+                  const float* __restrict__ gout, double* __restrict__ block_part) {
     __shared__ double s_part[kFinalThreads / PAA_WARP][3];
-    const GradScales gs = make_scales(sc, norm, local_norm, gout);
-    const float alpha = sc.alpha, gamma = sc.gamma, oma = 1.0f - sc.alpha;
-    const float kneg = oma * gs.cls;
+    FinalCtx cx;
+    cx.gs = make_scales(sc, norm, local_norm, gout);
+    cx.alpha = sc.alpha;
+    cx.gamma = sc.gamma;
+    cx.oma = 1.0f - sc.alpha;
+    cx.kneg = cx.oma * cx.gs.cls;
     float neg_sum = 0.f, fix_sum = 0.f, reg_sum = 0.f, bce_sum = 0.f;
 
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int chunk = item % n_chunks;
-        const int bt = item / n_chunks;
-        const int n = bt / geo.tiles_per_image;
-        const int tile = bt - n * geo.tiles_per_image;
-        int first;
-        const int l = tile_level(geo, tile, &first);
-        const LevelView& lv = geo.lv[l];
-        const int i = first + threadIdx.x;
-        if (i >= lv.n_anchor) continue;
-        const int c_begin = chunk * kClsChunk;
-        const int c_end = min(geo.C, c_begin + kClsChunk);
-        const size_t flat = (size_t)n * geo.A + lv.a_off + i;
-        const int label = __ldg(paa_label + flat);
-        const size_t off = head_offset(n, i, c_begin, geo.C, geo.apl, lv.hw);
-        const float* __restrict__ cls = lv.cls + off;
-        float* __restrict__ gcls = lv.g_cls ? lv.g_cls + off : nullptr;
-        const unsigned stride = (unsigned)lv.hw;
-        const bool write = kGrads && gcls != nullptr;
-        if (c_end - c_begin == kClsChunk) {
+    // item -> (image, level, run, chunk); all images' large items come first
+    const int q = blockIdx.x / geo.num_images;
+    const int n = blockIdx.x - q * geo.num_images;
+    int l = 0;
+#pragma unroll 1
+    for (int k = 1; k < geo.num_levels; ++k)
+        if (q >= plan.item_off[k]) l = k;
+    const int local = q - plan.item_off[l];
+    const int chunk = local % plan.n_chunks;
+    const int run = local / plan.n_chunks;
+    const LevelView& lv = geo.lv[l];
+    const int c_begin = chunk * kClsChunk;
+    const int c_end = min(geo.C, c_begin + kClsChunk);
+    const unsigned stride = (unsigned)lv.hw;
+    const size_t img_flat = (size_t)n * geo.A + lv.a_off;
+
+    if (plan.vec[l]) {
+        // ---- float4 path: 4 consecutive anchors per thread (apl == 1, hw % 4 == 0) ----------------
+        const int i0 = (run * kFinalThreads + threadIdx.x) * 4;
+        if (i0 < lv.n_anchor) {
+            const size_t off = ((size_t)n * geo.C + c_begin) * stride + i0;
+            const float4* __restrict__ cls4 = reinterpret_cast<const float4*>(lv.cls + off);
+            float4* __restrict__ g4 = lv.g_cls ? reinterpret_cast<float4*>(lv.g_cls + off) : nullptr;
+            const unsigned stride4 = stride >> 2;
+            const bool write = kGrads && g4 != nullptr;
+            const int nc = c_end - c_begin;
+            for (int b0 = 0; b0 < nc; b0 += kVecBatch) {
+                float4 x[kVecBatch];
 #pragma unroll
-            for (int b0 = 0; b0 < kClsChunk; b0 += kClsBatch) {
+                for (int j = 0; j < kVecBatch; ++j)
+                    x[j] = (b0 + j < nc) ? __ldg(cls4 + (unsigned)(b0 + j) * stride4)
+                                         : make_float4(-100.f, -100.f, -100.f, -100.f);
+#pragma unroll
+                for (int j = 0; j < kVecBatch; ++j) {
+                    float4 g;
+                    neg_term_grad<kG2>(x[j].x, cx.gamma, cx.kneg, &neg_sum, &g.x);
+                    neg_term_grad<kG2>(x[j].y, cx.gamma, cx.kneg, &neg_sum, &g.y);
+                    neg_term_grad<kG2>(x[j].z, cx.gamma, cx.kneg, &neg_sum, &g.z);
+                    neg_term_grad<kG2>(x[j].w, cx.gamma, cx.kneg, &neg_sum, &g.w);
+                    if (write && b0 + j < nc) g4[(unsigned)(b0 + j) * stride4] = g;
+                }
+            }
+            int label[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) label[k] = __ldg(paa_label + img_flat + i0 + k);
+            const float* cls = lv.cls + off;
+            float* gcls = lv.g_cls ? lv.g_cls + off : nullptr;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (label[k] > 0 && label[k] - 1 >= c_begin && label[k] - 1 < c_end)
+                    patch_positive<kGrads, kG2>(cls, gcls, (unsigned)(label[k] - 1 - c_begin) * stride + k, cx,
+                                                &fix_sum);
+            if (chunk == 0) {
+                float4 gx = make_float4(0.f, 0.f, 0.f, 0.f), gy = gx, gw = gx, gh = gx, gi = gx;
+                if (label[0] > 0 || label[1] > 0 || label[2] > 0 || label[3] > 0) {
+                    const float* rp = lv.reg + (size_t)n * 4 * stride + i0;
+                    const float4 dx = __ldg(reinterpret_cast<const float4*>(rp));
+                    const float4 dy = __ldg(reinterpret_cast<const float4*>(rp + stride));
+                    const float4 dw = __ldg(reinterpret_cast<const float4*>(rp + 2 * (size_t)stride));
+                    const float4 dh = __ldg(reinterpret_cast<const float4*>(rp + 3 * (size_t)stride));
+                    float4 xi = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (sc.use_iou_pred) xi = __ldg(reinterpret_cast<const float4*>(lv.iou + (size_t)n * stride + i0));
+                    const float dxs[4] = {dx.x, dx.y, dx.z, dx.w}, dys[4] = {dy.x, dy.y, dy.z, dy.w};
+                    const float dws[4] = {dw.x, dw.y, dw.z, dw.w}, dhs[4] = {dh.x, dh.y, dh.z, dh.w};
+                    const float xis[4] = {xi.x, xi.y, xi.z, xi.w};
+                    float ox[4] = {0.f, 0.f, 0.f, 0.f}, oy[4] = {0.f, 0.f, 0.f, 0.f}, ow[4] = {0.f, 0.f, 0.f, 0.f},
+                          oh[4] = {0.f, 0.f, 0.f, 0.f}, oi[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if (label[k] > 0) {
+                            float4 gd = make_float4(0.f, 0.f, 0.f, 0.f);
+                            float g1 = 0.f;
+                            positive_box_terms(geo, lv, go, gt_boxes, sc, cx, n, i0 + k,
+                                               matched[img_flat + i0 + k],
+                                               make_float4(dxs[k], dys[k], dws[k], dhs[k]), xis[k], &reg_sum,
+                                               &bce_sum, &gd, &g1);
+                            ox[k] = gd.x;
+                            oy[k] = gd.y;
+                            ow[k] = gd.z;
+                            oh[k] = gd.w;
+                            oi[k] = g1;
+                        }
+                    }
+                    gx = make_float4(ox[0], ox[1], ox[2], ox[3]);
+                    gy = make_float4(oy[0], oy[1], oy[2], oy[3]);
+                    gw = make_float4(ow[0], ow[1], ow[2], ow[3]);
+                    gh = make_float4(oh[0], oh[1], oh[2], oh[3]);
+                    gi = make_float4(oi[0], oi[1], oi[2], oi[3]);
+                }
+                if (kGrads) {
+                    if (lv.g_reg) {
+                        float* gr = lv.g_reg + (size_t)n * 4 * stride + i0;
+                        *reinterpret_cast<float4*>(gr) = gx;
+                        *reinterpret_cast<float4*>(gr + stride) = gy;
+                        *reinterpret_cast<float4*>(gr + 2 * (size_t)stride) = gw;
+                        *reinterpret_cast<float4*>(gr + 3 * (size_t)stride) = gh;
+                    }
+                    if (lv.g_iou) *reinterpret_cast<float4*>(lv.g_iou + (size_t)n * stride + i0) = gi;
+                }
+            }
+        }
+    } else {
+        // ---- scalar path: one anchor per thread ----------------------------------------------------
+        const int i = run * kFinalThreads + threadIdx.x;
+        if (i < lv.n_anchor) {
+            const size_t flat = img_flat + i;
+            const int label = __ldg(paa_label + flat);
+            const size_t off = head_offset(n, i, c_begin, geo.C, geo.apl, lv.hw);
+            const float* __restrict__ cls = lv.cls + off;
+            float* __restrict__ gcls = lv.g_cls ? lv.g_cls + off : nullptr;
+            const bool write = kGrads && gcls != nullptr;
+            const int nc = c_end - c_begin;
+            for (int b0 = 0; b0 < nc; b0 += kClsBatch) {
                 float x[kClsBatch];
 #pragma unroll
-                for (int j = 0; j < kClsBatch; ++j) x[j] = __ldg(cls + (unsigned)(b0 + j) * stride);
+                for (int j = 0; j < kClsBatch; ++j)
+                    x[j] = (b0 + j < nc) ? __ldg(cls + (unsigned)(b0 + j) * stride) : -100.0f;
 #pragma unroll
                 for (int j = 0; j < kClsBatch; ++j) {
                     float g;
-                    neg_term_grad<kG2>(x[j], gamma, kneg, &neg_sum, &g);
-                    if (write) gcls[(unsigned)(b0 + j) * stride] = g;
+                    neg_term_grad<kG2>(x[j], cx.gamma, cx.kneg, &neg_sum, &g);
+                    if (write && b0 + j < nc) gcls[(unsigned)(b0 + j) * stride] = g;
                 }
             }
-        } else {
-            for (int c = 0; c < c_end - c_begin; ++c) {
-                float g;
-                neg_term_grad<kG2>(__ldg(cls + (unsigned)c * stride), gamma, kneg, &neg_sum, &g);
-                if (write) gcls[(unsigned)c * stride] = g;
-            }
-        }
-        if (label > 0 && label - 1 >= c_begin && label - 1 < c_end) {
-            const unsigned po = (unsigned)(label - 1 - c_begin) * stride;
-            const float xp = __ldg(cls + po);
-            const SigmoidParts sp = sigmoid_parts(xp);
-            float tn, gn, tp, gp;
-            focal_negative(xp, sp, gamma, kG2, oma, &tn, &gn);
-            focal_positive(xp, sp, gamma, kG2, alpha, &tp, &gp);
-            fix_sum += tp - tn;
-            if (write) gcls[po] = gp * gs.cls;
-        }
-
-        if (chunk == 0) {
-            float4 gd = make_float4(0.f, 0.f, 0.f, 0.f);
-            float giou_g = 0.f;
-            if (label > 0) {
-                const int m = matched[flat];
-                const float4 a = ldg4(lv.anchors + (size_t)n * geo.anchor_image_stride + (size_t)i * 4);
-                const AnchorFrame f = anchor_frame(a);
-                const float* rp = lv.reg + head_offset(n, i, 0, 4, geo.apl, lv.hw);
-                const float4 d = make_float4(__ldg(rp), __ldg(rp + lv.hw), __ldg(rp + 2 * (size_t)lv.hw),
-                                             __ldg(rp + 3 * (size_t)lv.hw));
-                const float4 gt = ldg4(gt_boxes + (size_t)(go.v[n] + m) * 4);
-                const float4 tgt = decode_box(encode_box(gt, f), f);
-                float w = 1.0f;
-                if (sc.use_iou_pred) {
-                    const float4 pred = decode_box(d, f);
-                    const float q = iou_plus1(tgt, area_plus1(tgt), pred, area_plus1(pred));
-                    const float xi = __ldg(lv.iou + head_offset(n, i, 0, 1, geo.apl, lv.hw));
-                    const float ei = expf(-fabsf(xi));
-                    bce_sum += fmaxf(xi, 0.0f) - xi * q + log1pf(ei);
-                    const float sig = (xi >= 0.0f) ? 1.0f / (1.0f + ei) : ei / (1.0f + ei);
-                    giou_g = (sig - q) * gs.bce;
-                    if (gs.weighted) w = q;
+            if (label > 0 && label - 1 >= c_begin && label - 1 < c_end)
+                patch_positive<kGrads, kG2>(cls, gcls, (unsigned)(label - 1 - c_begin) * stride, cx, &fix_sum);
+            if (chunk == 0) {
+                float4 gd = make_float4(0.f, 0.f, 0.f, 0.f);
+                float gi = 0.f;
+                if (label > 0) {
+                    const float* rp = lv.reg + head_offset(n, i, 0, 4, geo.apl, lv.hw);
+                    const float4 d = make_float4(__ldg(rp), __ldg(rp + lv.hw), __ldg(rp + 2 * (size_t)lv.hw),
+                                                 __ldg(rp + 3 * (size_t)lv.hw));
+                    const float xi = sc.use_iou_pred ? __ldg(lv.iou + head_offset(n, i, 0, 1, geo.apl, lv.hw)) : 0.f;
+                    positive_box_terms(geo, lv, go, gt_boxes, sc, cx, n, i, matched[flat], d, xi, &reg_sum, &bce_sum,
+                                       &gd, &gi);
                 }
-                float4 gdd;
-                const float gl = giou_loss_and_grad(d, f, tgt, &gdd);
-                reg_sum += gl * w;
-                const float k = w * gs.reg;
-                gd = make_float4(gdd.x * k, gdd.y * k, gdd.z * k, gdd.w * k);
-            }
-            if (kGrads) {
-                if (lv.g_reg) {
-                    float* gr = lv.g_reg + head_offset(n, i, 0, 4, geo.apl, lv.hw);
-                    gr[0] = gd.x;
-                    gr[lv.hw] = gd.y;
-                    gr[2 * (size_t)lv.hw] = gd.z;
-                    gr[3 * (size_t)lv.hw] = gd.w;
+                if (kGrads) {
+                    if (lv.g_reg) {
+                        float* gr = lv.g_reg + head_offset(n, i, 0, 4, geo.apl, lv.hw);
+                        gr[0] = gd.x;
+                        gr[lv.hw] = gd.y;
+                        gr[2 * (size_t)lv.hw] = gd.z;
+                        gr[3 * (size_t)lv.hw] = gd.w;
+                    }
+                    if (lv.g_iou) lv.g_iou[head_offset(n, i, 0, 1, geo.apl, lv.hw)] = gi;
                 }
-                if (lv.g_iou) lv.g_iou[head_offset(n, i, 0, 1, geo.apl, lv.hw)] = giou_g;
             }
         }
     }
     // block partial sums (double, fixed order)
-    const float cls_sum = fmaf(oma, neg_sum, fix_sum);
+    const float cls_sum = fmaf(cx.oma, neg_sum, fix_sum);
     double a0 = warp_sum((double)cls_sum), a1 = warp_sum((double)reg_sum), a2 = warp_sum((double)bce_sum);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (lane == 0) {
@@ -294,16 +410,30 @@ finish_loss_kernel(const double* __restrict__ block_part, int blocks, const Loss
 int launch_final_loss(const Geometry& geo, const GtOffsets& go, const float* gt_boxes,
                       const LossScalars& sc, const LossWorkspace& ws, const double* normalisers,
                       const float* grad_losses, float* losses, bool write_grads, cudaStream_t stream) {
-    const int n_chunks = loss_class_chunks(geo.C);
-    const int n_items = geo.num_images * geo.tiles_per_image * n_chunks;
-    int grid = 148 * kFinalBlocksPerSM;
-    if (grid > n_items) grid = n_items;
+    FinalPlan plan;
+    plan.n_chunks = loss_class_chunks(geo.C);
+    int items = 0;
+    for (int l = 0; l < geo.num_levels; ++l) {
+        const LevelView& lv = geo.lv[l];
+        // float4 path: one anchor per location, rows of 4 anchors never straddle a class plane, and every
+        // tensor of the level is 16-byte aligned
+        auto aligned = [](const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+        const bool vec = geo.apl == 1 && (lv.hw % 4) == 0 && aligned(lv.cls) && aligned(lv.reg) && aligned(lv.iou) &&
+                         aligned(lv.g_cls) && aligned(lv.g_reg) && aligned(lv.g_iou);
+        plan.vec[l] = vec ? 1 : 0;
+        plan.item_off[l] = items;
+        const int per_run = vec ? kFinalThreads * 4 : kFinalThreads;
+        items += ((lv.n_anchor + per_run - 1) / per_run) * plan.n_chunks;
+    }
+    for (int l = geo.num_levels; l <= PAA_MAX_LEVELS; ++l) plan.item_off[l] = items;
+    plan.items_per_image = items;
+    const int grid = geo.num_images * items;
     {
         KernelTimer timer(PAA_KERNEL_FINAL_LOSS, stream);
         const bool g2 = (sc.gamma == 2.0f);
-#define PAA_FINAL(G, T)                                                                                \
-    final_loss_kernel<G, T><<<grid, kFinalThreads, 0, stream>>>(geo, go, gt_boxes, sc, ws.paa_label,   \
-        ws.matched, normalisers, ws.local_norm, grad_losses, ws.block_part, n_chunks, n_items)
+#define PAA_FINAL(G, T)                                                                                  \
+    final_loss_kernel<G, T><<<grid, kFinalThreads, 0, stream>>>(geo, go, plan, gt_boxes, sc, ws.paa_label, \
+        ws.matched, normalisers, ws.local_norm, grad_losses, ws.block_part)
         if (write_grads) {
             if (g2) PAA_FINAL(true, true); else PAA_FINAL(true, false);
         } else {

@@ -126,8 +126,8 @@ __device__ __forceinline__ float focal_sum(const float* __restrict__ p, int stri
         for (int j = 0; j < 8; ++j) x[j] = (c0 + j < C) ? __ldg(p + (unsigned)(c0 + j) * st) : -100.0f;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {      // a padded logit of -100 contributes exactly 0
-            const SigmoidParts sp = sigmoid_parts(x[j]);
-            neg = fmaf(focal_pow(sp.p, gamma, g2), fmaxf(x[j], 0.0f) + sp.l1p, neg);
+            const SigmoidLean sl = sigmoid_lean(x[j]);
+            neg = fmaf(focal_pow(sl.p, gamma, g2), sl.sp, neg);
         }
     }
     // patch the labelled class: remove its negative term, add the positive one

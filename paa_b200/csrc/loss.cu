@@ -13,11 +13,9 @@
 
 namespace paa {
 
-constexpr int kFinalThreads = PAA_TILE;
 
-// upper bound of blocks the final kernel launches (sizes the partial-sum buffer): one per (128-anchor run,
-// class chunk); 64 chunks cover C <= 1024
-int loss_grid_blocks(int num_images, int tiles_per_image) { return num_images * tiles_per_image * 64; }
+// partial-sum slots: the bulk kernel's persistent blocks, then one per 128-anchor tile
+int loss_grid_blocks(int num_images, int tiles_per_image) { return 148 * 5 + num_images * tiles_per_image; }
 
 struct GradScales {
     float cls, reg, bce;     // d(total)/d(sum) factors
@@ -110,56 +108,118 @@ __device__ __forceinline__ float giou_loss_and_grad(float4 d, const AnchorFrame&
     return loss;
 }
 
-// Work item = a run of consecutive anchors of one level of one image x one chunk of kClsChunk classes.
-// On levels whose H*W is a multiple of 4 a thread owns 4 consecutive anchors and moves float4s (one
-// address computation and one LDG.128 / STG.128 per 4 logits); other levels (the small coarse ones) use
-// one anchor per thread.  One block per item, largest items first; every block leaves its partial sums
-// in its own slot, so the final fold is order-fixed and bit-reproducible.  Every logit of a chunk is
-// read once and its gradient written once.  All classes are first treated as negatives; the single
-// positive class of a positive anchor is patched afterwards.  The chunk-0 item of a run also handles the
-// regression / IoU-prediction losses and gradients of its anchors.
-constexpr int kClsChunk = 16;
-constexpr int kVecBatch = 4;       // classes in flight per thread on the float4 path (4 x 16 B)
-constexpr int kClsBatch = 8;       // classes in flight per thread on the scalar path
-constexpr int kFinalBlocksPerSM = 6;
+// The final pass is split by what the work depends on:
+//
+//   bulk_focal_kernel      every logit of every anchor as a NEGATIVE class: loss term + gradient.  This is
+//                          79/80 of the arithmetic and all of the traffic, and it does not care which anchor
+//                          or class an element belongs to -- so each level's [N, C, H, W] tensor is streamed
+//                          as one flat array, front to back, float4 per lane, 4 float4 in flight per thread
+//                          (the access pattern of a memcpy: whole DRAM pages, no strides).
+//   positive_terms_kernel  one thread per anchor: the single positive class of every PAA-positive anchor is
+//                          patched (loss term and gradient element), its regression / IoU-prediction losses
+//                          and gradients are computed, and the regression / IoU gradients of all other
+//                          anchors are zeroed.  Reads 4 B and writes 20 B per anchor.
+//
+// Both leave per-block partial sums in fixed slots; finish_loss_kernel folds them in a fixed order.
+constexpr int kBulkThreads = 256;
+constexpr int kBulkVecs = 4;                                   // float4 per thread per iteration
+constexpr int kBulkChunk = kBulkThreads * kBulkVecs;           // float4 per block iteration (16 KB)
+constexpr int kBulkBlocksPerSM = 5;
+constexpr int kBulkMaxBlocks = 148 * kBulkBlocksPerSM;
 
-int loss_class_chunks(int C) { return (C + kClsChunk - 1) / kClsChunk; }
-
-struct FinalPlan {
-    int item_off[PAA_MAX_LEVELS + 1];   // per image: first item of each level (items = runs x chunks)
-    int vec[PAA_MAX_LEVELS];            // 1: float4 path
-    int n_chunks;
-    int items_per_image;
+struct BulkPlan {
+    const float* src[PAA_MAX_LEVELS];
+    float* dst[PAA_MAX_LEVELS];
+    unsigned long long count[PAA_MAX_LEVELS];      // floats in the level's tensor
+    unsigned chunk_off[PAA_MAX_LEVELS + 1];        // first chunk of each level in the virtual concatenation
+    int n;
 };
 
 // negative-class focal term without its (1-alpha) factor, and the gradient with `k` = (1-alpha) * scale
 template <bool kG2>
 __device__ __forceinline__ void neg_term_grad(float x, float gamma, float k, float* sum, float* grad) {
-    const SigmoidParts s = sigmoid_parts(x);
-    const float nlogq = fmaxf(x, 0.0f) + s.l1p;
+    const SigmoidLean s = sigmoid_lean(x);
     const float mod = kG2 ? s.p * s.p : __powf(s.p, gamma);
-    *sum = fmaf(mod, nlogq, *sum);
+    *sum = fmaf(mod, s.sp, *sum);
     const float gq = kG2 ? s.q + s.q : gamma * s.q;
-    *grad = (mod * fmaf(gq, nlogq, s.p)) * k;
+    *grad = (mod * fmaf(gq, s.sp, s.p)) * k;
+}
+
+template <bool kGrads, bool kG2>
+__global__ void __launch_bounds__(kBulkThreads, kBulkBlocksPerSM)
+bulk_focal_kernel(const BulkPlan plan, const LossScalars sc, const double* __restrict__ norm,
+                  const double* __restrict__ local_norm, const float* __restrict__ gout,
+                  double* __restrict__ block_part) {
+    __shared__ double s_part[kBulkThreads / PAA_WARP];
+    const GradScales gs = make_scales(sc, norm, local_norm, gout);
+    const float gamma = sc.gamma, oma = 1.0f - sc.alpha;
+    const float kneg = oma * gs.cls;
+    float neg_sum = 0.f;
+    const unsigned n_chunks = plan.chunk_off[plan.n];
+    for (unsigned ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
+        int l = 0;
+#pragma unroll 1
+        for (int k = 1; k < plan.n; ++k)
+            if (ch >= plan.chunk_off[k]) l = k;
+        const unsigned long long count = plan.count[l];
+        const unsigned long long n4 = count >> 2;                                  // whole float4s
+        const unsigned long long base4 = (unsigned long long)(ch - plan.chunk_off[l]) * kBulkChunk;
+        const float4* __restrict__ src4 = reinterpret_cast<const float4*>(plan.src[l]);
+        float4* __restrict__ dst4 = reinterpret_cast<float4*>(plan.dst[l]);
+        const bool write = kGrads && dst4 != nullptr;
+        if (base4 + kBulkChunk <= n4) {
+            float4 x[kBulkVecs];
+#pragma unroll
+            for (int j = 0; j < kBulkVecs; ++j) x[j] = __ldcs(src4 + base4 + j * kBulkThreads + threadIdx.x);
+#pragma unroll
+            for (int j = 0; j < kBulkVecs; ++j) {
+                float4 g;
+                neg_term_grad<kG2>(x[j].x, gamma, kneg, &neg_sum, &g.x);
+                neg_term_grad<kG2>(x[j].y, gamma, kneg, &neg_sum, &g.y);
+                neg_term_grad<kG2>(x[j].z, gamma, kneg, &neg_sum, &g.z);
+                neg_term_grad<kG2>(x[j].w, gamma, kneg, &neg_sum, &g.w);
+                if (write) __stcs(dst4 + base4 + j * kBulkThreads + threadIdx.x, g);
+            }
+        } else {
+            // last chunk of a level: guarded float4s, then the (count % 4) scalar tail
+            for (int j = 0; j < kBulkVecs; ++j) {
+                const unsigned long long i4 = base4 + j * kBulkThreads + threadIdx.x;
+                if (i4 < n4) {
+                    const float4 x = __ldcs(src4 + i4);
+                    float4 g;
+                    neg_term_grad<kG2>(x.x, gamma, kneg, &neg_sum, &g.x);
+                    neg_term_grad<kG2>(x.y, gamma, kneg, &neg_sum, &g.y);
+                    neg_term_grad<kG2>(x.z, gamma, kneg, &neg_sum, &g.z);
+                    neg_term_grad<kG2>(x.w, gamma, kneg, &neg_sum, &g.w);
+                    if (write) __stcs(dst4 + i4, g);
+                }
+            }
+            const unsigned long long tail = (n4 << 2) + threadIdx.x;
+            if (threadIdx.x < 4 && tail < count) {
+                float g;
+                neg_term_grad<kG2>(plan.src[l][tail], gamma, kneg, &neg_sum, &g);
+                if (write) plan.dst[l][tail] = g;
+            }
+        }
+    }
+    double a = warp_sum((double)(oma * neg_sum));
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) s_part[warp] = a;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < kBulkThreads / PAA_WARP; ++w) t += s_part[w];
+        block_part[(size_t)blockIdx.x * 3 + 0] = t;
+        block_part[(size_t)blockIdx.x * 3 + 1] = 0.0;
+        block_part[(size_t)blockIdx.x * 3 + 2] = 0.0;
+    }
 }
 
 struct FinalCtx {
     float alpha, gamma, oma, kneg;
     GradScales gs;
 };
-
-// swaps the (already written) negative-class result of the labelled class for the positive-class one
-template <bool kGrads, bool kG2>
-__device__ __forceinline__ void patch_positive(const float* __restrict__ cls, float* __restrict__ gcls,
-                                               unsigned elem_off, const FinalCtx& cx, float* fix_sum) {
-    const float xp = __ldg(cls + elem_off);
-    const SigmoidParts sp = sigmoid_parts(xp);
-    float tn, gn, tp, gp;
-    focal_negative(xp, sp, cx.gamma, kG2, cx.oma, &tn, &gn);
-    focal_positive(xp, sp, cx.gamma, kG2, cx.alpha, &tp, &gp);
-    *fix_sum += tp - tn;
-    if (kGrads && gcls) gcls[elem_off] = gp * cx.gs.cls;
-}
 
 // regression + IoU-prediction losses / gradients of one positive anchor (loss.py:328-349)
 __device__ __forceinline__ void positive_box_terms(const Geometry& geo, const LevelView& lv, const GtOffsets& go,
@@ -187,175 +247,67 @@ __device__ __forceinline__ void positive_box_terms(const Geometry& geo, const Le
     *gd = make_float4(gdd.x * k, gdd.y * k, gdd.z * k, gdd.w * k);
 }
 
+// One thread per anchor, one block per 128-anchor tile (same tiling as the assignment kernels).
+// Runs after bulk_focal_kernel on the same stream: it overwrites the labelled class's gradient element.
 template <bool kGrads, bool kG2>
-__global__ void __launch_bounds__(kFinalThreads, kFinalBlocksPerSM)
-final_loss_kernel(const Geometry geo, const GtOffsets go, const FinalPlan plan,
-                  const float* __restrict__ gt_boxes, const LossScalars sc,
-                  const int* __restrict__ paa_label, const int* __restrict__ matched,
-                  const double* __restrict__ norm, const double* __restrict__ local_norm,
-                  const float* __restrict__ gout, double* __restrict__ block_part) {
-    __shared__ double s_part[kFinalThreads / PAA_WARP][3];
-    FinalCtx cx;
-    cx.gs = make_scales(sc, norm, local_norm, gout);
-    cx.alpha = sc.alpha;
-    cx.gamma = sc.gamma;
-    cx.oma = 1.0f - sc.alpha;
-    cx.kneg = cx.oma * cx.gs.cls;
-    float neg_sum = 0.f, fix_sum = 0.f, reg_sum = 0.f, bce_sum = 0.f;
-
-    // item -> (image, level, run, chunk); all images' large items come first
-    const int q = blockIdx.x / geo.num_images;
-    const int n = blockIdx.x - q * geo.num_images;
-    int l = 0;
-#pragma unroll 1
-    for (int k = 1; k < geo.num_levels; ++k)
-        if (q >= plan.item_off[k]) l = k;
-    const int local = q - plan.item_off[l];
-    const int chunk = local % plan.n_chunks;
-    const int run = local / plan.n_chunks;
+__global__ void __launch_bounds__(PAA_TILE)
+positive_terms_kernel(const Geometry geo, const GtOffsets go, const float* __restrict__ gt_boxes,
+                      const LossScalars sc, const int* __restrict__ paa_label, const int* __restrict__ matched,
+                      const double* __restrict__ norm, const double* __restrict__ local_norm,
+                      const float* __restrict__ gout, double* __restrict__ block_part) {
+    __shared__ double s_part[PAA_TILE / PAA_WARP][3];
+    const int n = blockIdx.x / geo.tiles_per_image;
+    const int tile = blockIdx.x - n * geo.tiles_per_image;
+    int first;
+    const int l = tile_level(geo, tile, &first);
     const LevelView& lv = geo.lv[l];
-    const int c_begin = chunk * kClsChunk;
-    const int c_end = min(geo.C, c_begin + kClsChunk);
-    const unsigned stride = (unsigned)lv.hw;
-    const size_t img_flat = (size_t)n * geo.A + lv.a_off;
-
-    if (plan.vec[l]) {
-        // ---- float4 path: 4 consecutive anchors per thread (apl == 1, hw % 4 == 0) ----------------
-        const int i0 = (run * kFinalThreads + threadIdx.x) * 4;
-        if (i0 < lv.n_anchor) {
-            const size_t off = ((size_t)n * geo.C + c_begin) * stride + i0;
-            const float4* __restrict__ cls4 = reinterpret_cast<const float4*>(lv.cls + off);
-            float4* __restrict__ g4 = lv.g_cls ? reinterpret_cast<float4*>(lv.g_cls + off) : nullptr;
-            const unsigned stride4 = stride >> 2;
-            const bool write = kGrads && g4 != nullptr;
-            const int nc = c_end - c_begin;
-            for (int b0 = 0; b0 < nc; b0 += kVecBatch) {
-                float4 x[kVecBatch];
-#pragma unroll
-                for (int j = 0; j < kVecBatch; ++j)
-                    x[j] = (b0 + j < nc) ? __ldg(cls4 + (unsigned)(b0 + j) * stride4)
-                                         : make_float4(-100.f, -100.f, -100.f, -100.f);
-#pragma unroll
-                for (int j = 0; j < kVecBatch; ++j) {
-                    float4 g;
-                    neg_term_grad<kG2>(x[j].x, cx.gamma, cx.kneg, &neg_sum, &g.x);
-                    neg_term_grad<kG2>(x[j].y, cx.gamma, cx.kneg, &neg_sum, &g.y);
-                    neg_term_grad<kG2>(x[j].z, cx.gamma, cx.kneg, &neg_sum, &g.z);
-                    neg_term_grad<kG2>(x[j].w, cx.gamma, cx.kneg, &neg_sum, &g.w);
-                    if (write && b0 + j < nc) g4[(unsigned)(b0 + j) * stride4] = g;
-                }
-            }
-            int label[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) label[k] = __ldg(paa_label + img_flat + i0 + k);
-            const float* cls = lv.cls + off;
-            float* gcls = lv.g_cls ? lv.g_cls + off : nullptr;
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if (label[k] > 0 && label[k] - 1 >= c_begin && label[k] - 1 < c_end)
-                    patch_positive<kGrads, kG2>(cls, gcls, (unsigned)(label[k] - 1 - c_begin) * stride + k, cx,
-                                                &fix_sum);
-            if (chunk == 0) {
-                float4 gx = make_float4(0.f, 0.f, 0.f, 0.f), gy = gx, gw = gx, gh = gx, gi = gx;
-                if (label[0] > 0 || label[1] > 0 || label[2] > 0 || label[3] > 0) {
-                    const float* rp = lv.reg + (size_t)n * 4 * stride + i0;
-                    const float4 dx = __ldg(reinterpret_cast<const float4*>(rp));
-                    const float4 dy = __ldg(reinterpret_cast<const float4*>(rp + stride));
-                    const float4 dw = __ldg(reinterpret_cast<const float4*>(rp + 2 * (size_t)stride));
-                    const float4 dh = __ldg(reinterpret_cast<const float4*>(rp + 3 * (size_t)stride));
-                    float4 xi = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (sc.use_iou_pred) xi = __ldg(reinterpret_cast<const float4*>(lv.iou + (size_t)n * stride + i0));
-                    const float dxs[4] = {dx.x, dx.y, dx.z, dx.w}, dys[4] = {dy.x, dy.y, dy.z, dy.w};
-                    const float dws[4] = {dw.x, dw.y, dw.z, dw.w}, dhs[4] = {dh.x, dh.y, dh.z, dh.w};
-                    const float xis[4] = {xi.x, xi.y, xi.z, xi.w};
-                    float ox[4] = {0.f, 0.f, 0.f, 0.f}, oy[4] = {0.f, 0.f, 0.f, 0.f}, ow[4] = {0.f, 0.f, 0.f, 0.f},
-                          oh[4] = {0.f, 0.f, 0.f, 0.f}, oi[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        if (label[k] > 0) {
-                            float4 gd = make_float4(0.f, 0.f, 0.f, 0.f);
-                            float g1 = 0.f;
-                            positive_box_terms(geo, lv, go, gt_boxes, sc, cx, n, i0 + k,
-                                               matched[img_flat + i0 + k],
-                                               make_float4(dxs[k], dys[k], dws[k], dhs[k]), xis[k], &reg_sum,
-                                               &bce_sum, &gd, &g1);
-                            ox[k] = gd.x;
-                            oy[k] = gd.y;
-                            ow[k] = gd.z;
-                            oh[k] = gd.w;
-                            oi[k] = g1;
-                        }
-                    }
-                    gx = make_float4(ox[0], ox[1], ox[2], ox[3]);
-                    gy = make_float4(oy[0], oy[1], oy[2], oy[3]);
-                    gw = make_float4(ow[0], ow[1], ow[2], ow[3]);
-                    gh = make_float4(oh[0], oh[1], oh[2], oh[3]);
-                    gi = make_float4(oi[0], oi[1], oi[2], oi[3]);
-                }
-                if (kGrads) {
-                    if (lv.g_reg) {
-                        float* gr = lv.g_reg + (size_t)n * 4 * stride + i0;
-                        *reinterpret_cast<float4*>(gr) = gx;
-                        *reinterpret_cast<float4*>(gr + stride) = gy;
-                        *reinterpret_cast<float4*>(gr + 2 * (size_t)stride) = gw;
-                        *reinterpret_cast<float4*>(gr + 3 * (size_t)stride) = gh;
-                    }
-                    if (lv.g_iou) *reinterpret_cast<float4*>(lv.g_iou + (size_t)n * stride + i0) = gi;
-                }
-            }
+    const int i = first + threadIdx.x;
+    float fix_sum = 0.f, reg_sum = 0.f, bce_sum = 0.f;
+    if (i < lv.n_anchor) {
+        const size_t flat = (size_t)n * geo.A + lv.a_off + i;
+        const int label = __ldg(paa_label + flat);
+        float4 gd = make_float4(0.f, 0.f, 0.f, 0.f);
+        float gi = 0.f;
+        if (label > 0) {
+            FinalCtx cx;
+            cx.gs = make_scales(sc, norm, local_norm, gout);
+            cx.alpha = sc.alpha;
+            cx.gamma = sc.gamma;
+            cx.oma = 1.0f - sc.alpha;
+            cx.kneg = cx.oma * cx.gs.cls;
+            // classification: swap the negative-class result of the labelled class for the positive one
+            const size_t off = head_offset(n, i, label - 1, geo.C, geo.apl, lv.hw);
+            const float xp = __ldg(lv.cls + off);
+            const SigmoidParts sp = sigmoid_parts(xp);
+            float tn_acc = 0.f, g_unused;
+            neg_term_grad<kG2>(xp, cx.gamma, cx.kneg, &tn_acc, &g_unused);      // exactly what the bulk pass added
+            float tn, gn, tp, gp;
+            focal_negative(xp, sp, cx.gamma, kG2, cx.oma, &tn, &gn);
+            focal_positive(xp, sp, cx.gamma, kG2, cx.alpha, &tp, &gp);
+            (void)tn;
+            (void)gn;
+            fix_sum = tp - cx.oma * tn_acc;
+            if (kGrads && lv.g_cls) lv.g_cls[off] = gp * cx.gs.cls;
+            // box regression + IoU prediction
+            const float* rp = lv.reg + head_offset(n, i, 0, 4, geo.apl, lv.hw);
+            const float4 d = make_float4(__ldg(rp), __ldg(rp + lv.hw), __ldg(rp + 2 * (size_t)lv.hw),
+                                         __ldg(rp + 3 * (size_t)lv.hw));
+            const float xi = sc.use_iou_pred ? __ldg(lv.iou + head_offset(n, i, 0, 1, geo.apl, lv.hw)) : 0.f;
+            positive_box_terms(geo, lv, go, gt_boxes, sc, cx, n, i, matched[flat], d, xi, &reg_sum, &bce_sum, &gd,
+                               &gi);
         }
-    } else {
-        // ---- scalar path: one anchor per thread ----------------------------------------------------
-        const int i = run * kFinalThreads + threadIdx.x;
-        if (i < lv.n_anchor) {
-            const size_t flat = img_flat + i;
-            const int label = __ldg(paa_label + flat);
-            const size_t off = head_offset(n, i, c_begin, geo.C, geo.apl, lv.hw);
-            const float* __restrict__ cls = lv.cls + off;
-            float* __restrict__ gcls = lv.g_cls ? lv.g_cls + off : nullptr;
-            const bool write = kGrads && gcls != nullptr;
-            const int nc = c_end - c_begin;
-            for (int b0 = 0; b0 < nc; b0 += kClsBatch) {
-                float x[kClsBatch];
-#pragma unroll
-                for (int j = 0; j < kClsBatch; ++j)
-                    x[j] = (b0 + j < nc) ? __ldg(cls + (unsigned)(b0 + j) * stride) : -100.0f;
-#pragma unroll
-                for (int j = 0; j < kClsBatch; ++j) {
-                    float g;
-                    neg_term_grad<kG2>(x[j], cx.gamma, cx.kneg, &neg_sum, &g);
-                    if (write && b0 + j < nc) gcls[(unsigned)(b0 + j) * stride] = g;
-                }
+        if (kGrads) {
+            if (lv.g_reg) {
+                float* gr = lv.g_reg + head_offset(n, i, 0, 4, geo.apl, lv.hw);
+                gr[0] = gd.x;
+                gr[lv.hw] = gd.y;
+                gr[2 * (size_t)lv.hw] = gd.z;
+                gr[3 * (size_t)lv.hw] = gd.w;
             }
-            if (label > 0 && label - 1 >= c_begin && label - 1 < c_end)
-                patch_positive<kGrads, kG2>(cls, gcls, (unsigned)(label - 1 - c_begin) * stride, cx, &fix_sum);
-            if (chunk == 0) {
-                float4 gd = make_float4(0.f, 0.f, 0.f, 0.f);
-                float gi = 0.f;
-                if (label > 0) {
-                    const float* rp = lv.reg + head_offset(n, i, 0, 4, geo.apl, lv.hw);
-                    const float4 d = make_float4(__ldg(rp), __ldg(rp + lv.hw), __ldg(rp + 2 * (size_t)lv.hw),
-                                                 __ldg(rp + 3 * (size_t)lv.hw));
-                    const float xi = sc.use_iou_pred ? __ldg(lv.iou + head_offset(n, i, 0, 1, geo.apl, lv.hw)) : 0.f;
-                    positive_box_terms(geo, lv, go, gt_boxes, sc, cx, n, i, matched[flat], d, xi, &reg_sum, &bce_sum,
-                                       &gd, &gi);
-                }
-                if (kGrads) {
-                    if (lv.g_reg) {
-                        float* gr = lv.g_reg + head_offset(n, i, 0, 4, geo.apl, lv.hw);
-                        gr[0] = gd.x;
-                        gr[lv.hw] = gd.y;
-                        gr[2 * (size_t)lv.hw] = gd.z;
-                        gr[3 * (size_t)lv.hw] = gd.w;
-                    }
-                    if (lv.g_iou) lv.g_iou[head_offset(n, i, 0, 1, geo.apl, lv.hw)] = gi;
-                }
-            }
+            if (lv.g_iou) lv.g_iou[head_offset(n, i, 0, 1, geo.apl, lv.hw)] = gi;
         }
     }
-    // block partial sums (double, fixed order)
-    const float cls_sum = fmaf(cx.oma, neg_sum, fix_sum);
-    double a0 = warp_sum((double)cls_sum), a1 = warp_sum((double)reg_sum), a2 = warp_sum((double)bce_sum);
+    double a0 = warp_sum((double)fix_sum), a1 = warp_sum((double)reg_sum), a2 = warp_sum((double)bce_sum);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (lane == 0) {
         s_part[warp][0] = a0;
@@ -366,21 +318,27 @@ final_loss_kernel(const Geometry geo, const GtOffsets go, const FinalPlan plan,
     if (threadIdx.x < 3) {
         double t = 0.0;
 #pragma unroll
-        for (int w = 0; w < kFinalThreads / PAA_WARP; ++w) t += s_part[w][threadIdx.x];
+        for (int w = 0; w < PAA_TILE / PAA_WARP; ++w) t += s_part[w][threadIdx.x];
         block_part[(size_t)blockIdx.x * 3 + threadIdx.x] = t;
     }
 }
 
 // Folds the per-block partials in a fixed order and applies the normalisers (loss.py:354-358).
 __global__ void __launch_bounds__(256)
-finish_loss_kernel(const double* __restrict__ block_part, int blocks, const LossScalars sc,
-                   const double* __restrict__ norm, float* __restrict__ losses) {
+finish_loss_kernel(const double* __restrict__ part_a, int blocks_a, const double* __restrict__ part_b,
+                   int blocks_b, const LossScalars sc, const double* __restrict__ norm,
+                   float* __restrict__ losses) {
     __shared__ double s[8][3];
     double a[3] = {0.0, 0.0, 0.0};
-    for (int b = threadIdx.x; b < blocks; b += 256) {
-        a[0] += block_part[(size_t)b * 3 + 0];
-        a[1] += block_part[(size_t)b * 3 + 1];
-        a[2] += block_part[(size_t)b * 3 + 2];
+    for (int b = threadIdx.x; b < blocks_a; b += 256) {
+        a[0] += part_a[(size_t)b * 3 + 0];
+        a[1] += part_a[(size_t)b * 3 + 1];
+        a[2] += part_a[(size_t)b * 3 + 2];
+    }
+    for (int b = threadIdx.x; b < blocks_b; b += 256) {
+        a[0] += part_b[(size_t)b * 3 + 0];
+        a[1] += part_b[(size_t)b * 3 + 1];
+        a[2] += part_b[(size_t)b * 3 + 2];
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -410,39 +368,58 @@ finish_loss_kernel(const double* __restrict__ block_part, int blocks, const Loss
 int launch_final_loss(const Geometry& geo, const GtOffsets& go, const float* gt_boxes,
                       const LossScalars& sc, const LossWorkspace& ws, const double* normalisers,
                       const float* grad_losses, float* losses, bool write_grads, cudaStream_t stream) {
-    FinalPlan plan;
-    plan.n_chunks = loss_class_chunks(geo.C);
-    int items = 0;
+    BulkPlan plan;
+    plan.n = geo.num_levels;
+    unsigned chunks = 0;
     for (int l = 0; l < geo.num_levels; ++l) {
         const LevelView& lv = geo.lv[l];
-        // float4 path: one anchor per location, rows of 4 anchors never straddle a class plane, and every
-        // tensor of the level is 16-byte aligned
-        auto aligned = [](const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
-        const bool vec = geo.apl == 1 && (lv.hw % 4) == 0 && aligned(lv.cls) && aligned(lv.reg) && aligned(lv.iou) &&
-                         aligned(lv.g_cls) && aligned(lv.g_reg) && aligned(lv.g_iou);
-        plan.vec[l] = vec ? 1 : 0;
-        plan.item_off[l] = items;
-        const int per_run = vec ? kFinalThreads * 4 : kFinalThreads;
-        items += ((lv.n_anchor + per_run - 1) / per_run) * plan.n_chunks;
+        plan.src[l] = lv.cls;
+        plan.dst[l] = lv.g_cls;
+        plan.count[l] = (unsigned long long)geo.num_images * geo.apl * geo.C * lv.hw;
+        plan.chunk_off[l] = chunks;
+        const unsigned long long n4 = (plan.count[l] + 3) / 4;
+        chunks += (unsigned)((n4 + kBulkChunk - 1) / kBulkChunk);
+        if ((reinterpret_cast<uintptr_t>(lv.cls) & 15u) || (reinterpret_cast<uintptr_t>(lv.g_cls) & 15u)) {
+            set_error("level %d: box_cls / grad_box_cls must be 16-byte aligned", l);
+            return PAA_ERR_BAD_ARGUMENT;
+        }
     }
-    for (int l = geo.num_levels; l <= PAA_MAX_LEVELS; ++l) plan.item_off[l] = items;
-    plan.items_per_image = items;
-    const int grid = geo.num_images * items;
+    for (int l = geo.num_levels; l <= PAA_MAX_LEVELS; ++l) plan.chunk_off[l] = chunks;
+    for (int l = geo.num_levels; l < PAA_MAX_LEVELS; ++l) {
+        plan.src[l] = nullptr;
+        plan.dst[l] = nullptr;
+        plan.count[l] = 0;
+    }
+    int bulk_grid = kBulkMaxBlocks;
+    if ((unsigned)bulk_grid > chunks) bulk_grid = (int)chunks;
+    const int tile_grid = geo.num_images * geo.tiles_per_image;
+    const bool g2 = (sc.gamma == 2.0f);
+    double* bulk_part = ws.block_part;
+    double* tile_part = ws.block_part + (size_t)kBulkMaxBlocks * 3;
     {
         KernelTimer timer(PAA_KERNEL_FINAL_LOSS, stream);
-        const bool g2 = (sc.gamma == 2.0f);
-#define PAA_FINAL(G, T)                                                                                  \
-    final_loss_kernel<G, T><<<grid, kFinalThreads, 0, stream>>>(geo, go, plan, gt_boxes, sc, ws.paa_label, \
-        ws.matched, normalisers, ws.local_norm, grad_losses, ws.block_part)
+#define PAA_BULK(G, T)                                                                                       \
+    bulk_focal_kernel<G, T><<<bulk_grid, kBulkThreads, 0, stream>>>(plan, sc, normalisers, ws.local_norm,    \
+                                                                    grad_losses, bulk_part)
         if (write_grads) {
-            if (g2) PAA_FINAL(true, true); else PAA_FINAL(true, false);
+            if (g2) PAA_BULK(true, true); else PAA_BULK(true, false);
         } else {
-            if (g2) PAA_FINAL(false, true); else PAA_FINAL(false, false);
+            if (g2) PAA_BULK(false, true); else PAA_BULK(false, false);
         }
-#undef PAA_FINAL
+#undef PAA_BULK
     }
-    PAA_LAUNCH_CHECK("final_loss_kernel");
-    finish_loss_kernel<<<1, 256, 0, stream>>>(ws.block_part, grid, sc, normalisers, losses);
+    PAA_LAUNCH_CHECK("bulk_focal_kernel");
+#define PAA_POS(G, T)                                                                                        \
+    positive_terms_kernel<G, T><<<tile_grid, PAA_TILE, 0, stream>>>(geo, go, gt_boxes, sc, ws.paa_label,     \
+        ws.matched, normalisers, ws.local_norm, grad_losses, tile_part)
+    if (write_grads) {
+        if (g2) PAA_POS(true, true); else PAA_POS(true, false);
+    } else {
+        if (g2) PAA_POS(false, true); else PAA_POS(false, false);
+    }
+#undef PAA_POS
+    PAA_LAUNCH_CHECK("positive_terms_kernel");
+    finish_loss_kernel<<<1, 256, 0, stream>>>(bulk_part, bulk_grid, tile_part, tile_grid, sc, normalisers, losses);
     PAA_LAUNCH_CHECK("finish_loss_kernel");
     return 0;
 }

@@ -241,6 +241,7 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         import torch.distributed as dist
+        os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout: one JSON line only
         dist.init_process_group("nccl", device_id=dev)
     n_img = args.images_per_gpu
     batch = synthetic.make_batch(seed=SEED_BASE + rank, num_images=n_img, image_hw=IMAGE_HW,
@@ -438,10 +439,15 @@ def run_ours(args):
         except Exception as e:  # noqa: BLE001
             line["post"] = {"unavailable": str(e)[:200]}
     if rank == 0:
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
+        # Leave without tearing NCCL down: destroying the process group while a captured CUDA graph still
+        # references its communicator can block forever, and there is nothing left to clean up.
+        torch.cuda.synchronize()
         torch.distributed.barrier()
-        torch.distributed.destroy_process_group()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
     return 0
 
 

@@ -1,6 +1,7 @@
 // extern "C" entry points of libpaa_b200.so (see include/paa_b200.h).
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "kernels.h"
@@ -154,7 +155,7 @@ static int plan_loss(const PaaLossArgs* a, LossPlan* p) {
         return PAA_ERR_BAD_ARGUMENT;
     }
     p->ws = carve_loss_workspace(a->workspace, a->num_images, p->geo.A, p->sumG, p->geo.tiles_per_image,
-                                 loss_grid_blocks(a->num_images, p->geo.tiles_per_image));
+                                 loss_grid_blocks(a->num_images, p->geo.tiles_per_image), a->num_levels);
     if (p->ws.total_bytes > a->workspace_bytes) {
         set_error("workspace too small: need %zu bytes, got %zu", p->ws.total_bytes, a->workspace_bytes);
         return PAA_ERR_WORKSPACE;
@@ -171,6 +172,12 @@ static int plan_loss(const PaaLossArgs* a, LossPlan* p) {
     p->sc.topk = a->topk;
     p->sc.use_iou_pred = a->use_iou_pred;
     p->sc.world_size = a->world_size;
+    {
+        // test hook: a smaller pool forces the overflow path of the candidate selection
+        const char* e = getenv("PAA_SEG_CAP");
+        int cap = e ? atoi(e) : kSegCap;
+        p->sc.seg_cap = cap < 1 ? 1 : (cap > kSegCap ? kSegCap : cap);
+    }
     p->dbg.matched_idx = a->dbg_matched_idx;
     p->dbg.iou_labels = a->dbg_iou_labels;
     p->dbg.combined_loss = a->dbg_combined_loss;
@@ -198,7 +205,7 @@ size_t paa_loss_workspace_bytes(int num_images, int anchors_per_image, int num_g
     if (num_images < 1 || anchors_per_image < 1 || num_levels < 1) return 0;
     const int tiles = tiles_upper_bound(anchors_per_image, num_levels);
     LossWorkspace w = carve_loss_workspace(nullptr, num_images, anchors_per_image, num_gt_total, tiles,
-                                           loss_grid_blocks(num_images, tiles));
+                                           loss_grid_blocks(num_images, tiles), num_levels);
     return w.total_bytes;
 }
 
@@ -209,9 +216,10 @@ int paa_assign(const PaaLossArgs* args, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     PAA_CUDA_CHECK(cudaMemsetAsync(args->workspace, 0, p.ws.zero_bytes, stream));
     if ((rc = launch_iou_best(p.geo, p.go, args->gt_boxes, p.ws, stream))) return rc;
-    if ((rc = launch_match_score(p.geo, p.go, args->gt_boxes, args->gt_labels, p.sc, p.ws, p.dbg, stream)))
-        return rc;
     const float* score_src = args->teacher_combined_loss ? args->teacher_combined_loss : p.ws.score;
+    if ((rc = launch_match_score(p.geo, p.go, args->gt_boxes, args->gt_labels, p.sc, p.ws,
+                                 args->teacher_combined_loss, p.dbg, stream)))
+        return rc;
     if ((rc = launch_select_gmm(p.geo, p.go, p.sumG, args->gt_boxes, args->gt_labels, p.sc, p.ws, score_src,
                                 args->normalisers, p.dbg, stream)))
         return rc;

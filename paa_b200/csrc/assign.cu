@@ -112,31 +112,45 @@ int launch_iou_best(const Geometry& geo, const GtOffsets& go, const float* gt_bo
 //   (loss.py:293-306; anchors without an IoU-positive label are never candidates, their 1e8 filler
 //   is not materialised).
 // ---------------------------------------------------------------------------------------------
+// order-preserving map float -> unsigned (and back), so that (score, anchor) pairs compare as integers
+__device__ __forceinline__ unsigned ordered_bits(float v) {
+    unsigned u = __float_as_uint(v);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float from_ordered_bits(unsigned u) {
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
 // sum_c focal(x_c | label) for one anchor; `p` points at class 0, consecutive classes are `stride` apart.
-// Loads are issued eight at a time before any of them is consumed.
+// Loads are issued eight at a time before any of them is consumed.  Every class is first taken as a
+// negative (lean math), then the labelled class's negative term is swapped for the positive one
+// (accurate path for that single term).
+__device__ __forceinline__ float neg_term_only(float x, float gamma, bool g2) {
+    const SigmoidLean sl = sigmoid_lean(x);
+    return focal_pow(sl.p, gamma, g2) * sl.sp;
+}
+
 __device__ __forceinline__ float focal_sum(const float* __restrict__ p, int stride, int C, int label,
                                            float gamma, float alpha) {
     const bool g2 = (gamma == 2.0f);
     const float oma = 1.0f - alpha;
-    float neg = 0.0f;         // sum_c p^g * softplus(x_c): every class as a negative first
+    float neg = 0.0f;
     const unsigned st = (unsigned)stride;
+    float xl = 0.0f;
     for (int c0 = 0; c0 < C; c0 += 8) {
         float x[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) x[j] = (c0 + j < C) ? __ldg(p + (unsigned)(c0 + j) * st) : -100.0f;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {      // a padded logit of -100 contributes exactly 0
-            const SigmoidLean sl = sigmoid_lean(x[j]);
-            neg = fmaf(focal_pow(sl.p, gamma, g2), sl.sp, neg);
+            neg += neg_term_only(x[j], gamma, g2);
+            if (c0 + j + 1 == label) xl = x[j];
         }
     }
-    // patch the labelled class: remove its negative term, add the positive one
-    const float xl = __ldg(p + (unsigned)(label - 1) * st);
     const SigmoidParts sp = sigmoid_parts(xl);
-    float tn, gn, tp, gp;
-    focal_negative(xl, sp, gamma, g2, oma, &tn, &gn);
+    float tp, gp;
     focal_positive(xl, sp, gamma, g2, alpha, &tp, &gp);
-    return fmaf(oma, neg, tp - tn);
+    return fmaf(oma, neg - neg_term_only(xl, gamma, g2), tp);
 }
 
 __global__ void __launch_bounds__(PAA_TILE)
@@ -144,7 +158,8 @@ match_score_kernel(const Geometry geo, const GtOffsets go, const float* __restri
                    const int64_t* __restrict__ gt_labels, const unsigned* __restrict__ gtmax,
                    const uint2* __restrict__ best, const LossScalars sc, int* __restrict__ matched,
                    float* __restrict__ score, int* __restrict__ paa_label, uint4* __restrict__ tile_gtmask,
-                   const LossDebug dbg) {
+                   int* __restrict__ seg_count, unsigned long long* __restrict__ seg_pool,
+                   const float* __restrict__ teacher_score, const LossDebug dbg) {
     __shared__ int s_lq[PAA_TILE];
     __shared__ int s_nlq;
     __shared__ unsigned s_mask[4];
@@ -222,17 +237,26 @@ match_score_kernel(const Geometry geo, const GtOffsets go, const float* __restri
         const float4 tgt = decode_box(encode_box(gt, f), f);
         s = __fadd_rn(fsum, giou_loss_boxes(pred, tgt));
         score[flat] = s;
+        // hand the anchor to its (GT, level) candidate pool: the per-GT selection then reads one short
+        // contiguous list instead of searching the image for its anchors
+        const float key_score = teacher_score ? teacher_score[flat] : s;
+        const int seg = (gbase + m) * geo.num_levels + l;
+        const int slot = atomicAdd(&seg_count[seg], 1);
+        if (slot < sc.seg_cap)
+            seg_pool[(size_t)seg * kSegCap + slot] =
+                ((unsigned long long)ordered_bits(key_score) << 32) | (unsigned)(lv.a_off + i);
     }
     if (dbg.combined_loss) dbg.combined_loss[flat] = s;
 }
 
 int launch_match_score(const Geometry& geo, const GtOffsets& go, const float* gt_boxes,
                        const int64_t* gt_labels, const LossScalars& sc, const LossWorkspace& ws,
-                       const LossDebug& dbg, cudaStream_t stream) {
+                       const float* teacher_score, const LossDebug& dbg, cudaStream_t stream) {
     int grid = geo.num_images * geo.tiles_per_image;
     KernelTimer timer(PAA_KERNEL_MATCH_SCORE, stream);
     match_score_kernel<<<grid, PAA_TILE, 0, stream>>>(geo, go, gt_boxes, gt_labels, ws.gtmax, ws.best, sc,
-                                                      ws.matched, ws.score, ws.paa_label, ws.tile_gtmask, dbg);
+                                                      ws.matched, ws.score, ws.paa_label, ws.tile_gtmask,
+                                                      ws.seg_count, ws.seg_pool, teacher_score, dbg);
     PAA_LAUNCH_CHECK("match_score_kernel");
     return 0;
 }
@@ -243,14 +267,6 @@ int launch_match_score(const Geometry& geo, const GtOffsets& go, const float* gt
 // ---------------------------------------------------------------------------------------------
 constexpr int kSelWarps = 4;                // GTs per block
 constexpr unsigned long long kEmptyKey = ~0ull;
-
-__device__ __forceinline__ unsigned ordered_bits(float v) {
-    unsigned u = __float_as_uint(v);
-    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
-__device__ __forceinline__ float from_ordered_bits(unsigned u) {
-    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
-}
 
 // sklearn/utils/_array_api.py:1338-1366 for two entries.
 __device__ __forceinline__ double logsumexp2(double a0, double a1) {
@@ -342,43 +358,44 @@ __device__ int gmm_positive_prefix(const float (&x)[SPL], int n, int lane, doubl
         const double lw0 = log_pos(s.w0), lw1 = log_pos(s.w1);
         const float ld0 = s.first ? 0.f : __double2float_rn(log_pos((double)s.pc0));
         const float ld1 = s.first ? 0.f : __double2float_rn(log_pos((double)s.pc1));
-        double r0[SPL], r1[SPL];
-        double s_r0 = 0, s_r1 = 0, s_r0x = 0, s_r1x = 0, s_lpn = 0;
+        // One reduction round per iteration: moments are taken about the PREVIOUS means (p0, p1), from
+        // which the new mean and the variance about the new mean follow exactly:
+        //   sum r x = A + p S,   sum r (x - mu)^2 = B - 2 d A + d^2 S   with d = mu - p.
+        // (sklearn evaluates sum r (x - mu)^2 directly; the two agree to ~1e-14 relative, far below the
+        // float32 rounding of the variance that follows.)
+        const double p0 = s.mu0, p1 = s.mu1;
+        double S0 = 0, S1 = 0, A0 = 0, A1 = 0, B0 = 0, B1 = 0, s_lpn = 0;
 #pragma unroll
         for (int k = 0; k < SPL; ++k) {
-            r0[k] = r1[k] = 0.0;
             if (lane + 32 * k < n) {
-                double a0, a1;
+                double a0, a1, r0, r1;
                 weighted_log_prob(x[k], s, lw0, lw1, ld0, ld1, &a0, &a1);
-                const double lpn = logsumexp2_resp(a0, a1, &r0[k], &r1[k]);
-                s_r0 += r0[k];
-                s_r1 += r1[k];
-                s_r0x += r0[k] * (double)x[k];
-                s_r1x += r1[k] * (double)x[k];
-                s_lpn += lpn;
+                s_lpn += logsumexp2_resp(a0, a1, &r0, &r1);
+                const double e0 = (double)x[k] - p0, e1 = (double)x[k] - p1;
+                const double t0 = r0 * e0, t1 = r1 * e1;
+                S0 += r0;
+                S1 += r1;
+                A0 += t0;
+                A1 += t1;
+                B0 = fma(t0, e0, B0);
+                B1 = fma(t1, e1, B1);
             }
         }
-        s_r0 = warp_sum(s_r0);
-        s_r1 = warp_sum(s_r1);
-        s_r0x = warp_sum(s_r0x);
-        s_r1x = warp_sum(s_r1x);
+        S0 = warp_sum(S0);
+        S1 = warp_sum(S1);
+        A0 = warp_sum(A0);
+        A1 = warp_sum(A1);
+        B0 = warp_sum(B0);
+        B1 = warp_sum(B1);
         s_lpn = warp_sum(s_lpn);
-        const double nk0 = s_r0 + EPS10, nk1 = s_r1 + EPS10;
-        s.mu0 = div_fast(s_r0x, nk0);
-        s.mu1 = div_fast(s_r1x, nk1);
-        double c0 = 0, c1 = 0;
-#pragma unroll
-        for (int k = 0; k < SPL; ++k) {
-            if (lane + 32 * k < n) {
-                const double d0 = (double)x[k] - s.mu0, d1 = (double)x[k] - s.mu1;
-                c0 += (r0[k] * d0) * d0;
-                c1 += (r1[k] * d1) * d1;
-            }
-        }
-        c0 = warp_sum(c0);
-        c1 = warp_sum(c1);
-        s.var0 = __fadd_rn(__double2float_rn(div_fast(c0, nk0)), 1e-6f);
-        s.var1 = __fadd_rn(__double2float_rn(div_fast(c1, nk1)), 1e-6f);
+        const double nk0 = S0 + EPS10, nk1 = S1 + EPS10;
+        s.mu0 = div_fast(fma(p0, S0, A0), nk0);
+        s.mu1 = div_fast(fma(p1, S1, A1), nk1);
+        const double d0 = s.mu0 - p0, d1 = s.mu1 - p1;
+        const double c0 = fma(d0, fma(d0, S0, -2.0 * A0), B0);
+        const double c1 = fma(d1, fma(d1, S1, -2.0 * A1), B1);
+        s.var0 = __fadd_rn(__double2float_rn(div_fast(fmax(c0, 0.0), nk0)), 1e-6f);
+        s.var1 = __fadd_rn(__double2float_rn(div_fast(fmax(c1, 0.0), nk1)), 1e-6f);
         const double nsum = nk0 + nk1;
         s.w0 = div_fast(nk0, nsum);
         s.w1 = div_fast(nk1, nsum);
@@ -439,12 +456,35 @@ __device__ int gmm_positive_prefix(const float (&x)[SPL], int n, int lane, doubl
     return any_fg ? best_idx + 1 : n;
 }
 
+// Offers `key` (valid on lanes where `is`) to the warp's running top-K list: lane j < K holds the j-th
+// smallest key so far.  Keys that cannot enter the list are dropped before the serial insertion (the
+// K-th key only ever decreases, so comparing against a stale bound is safe).
+__device__ __forceinline__ void topk_offer(unsigned long long& mine, unsigned long long key, bool is, int K,
+                                           int lane) {
+    const unsigned long long kth = __shfl_sync(PAA_FULL, mine, K - 1);
+    is = is && (key < kth);
+    unsigned hm = __ballot_sync(PAA_FULL, is);
+    while (hm) {
+        const int src = __ffs(hm) - 1;
+        hm &= hm - 1;
+        const unsigned long long nk = __shfl_sync(PAA_FULL, key, src);
+        const unsigned less = __ballot_sync(PAA_FULL, lane < K && mine < nk);
+        const int pos = __popc(less);
+        const unsigned long long up = __shfl_up_sync(PAA_FULL, mine, 1);
+        if (pos < K) {
+            if (lane == pos) mine = nk;
+            else if (lane > pos && lane < K) mine = up;
+        }
+    }
+}
+
 template <int SPL>
 __global__ void __launch_bounds__(kSelWarps * PAA_WARP)
 select_gmm_kernel(const Geometry geo, const GtOffsets go, int num_gt_total,
                   const float* __restrict__ gt_boxes, const int64_t* __restrict__ gt_labels,
                   const LossScalars sc, const uint4* __restrict__ tile_gtmask,
                   const int* __restrict__ matched, const float* __restrict__ score,
+                  const int* __restrict__ seg_count, const unsigned long long* __restrict__ seg_pool,
                   int* __restrict__ paa_label,
                   int* __restrict__ part_npos, double* __restrict__ part_siou,
                   unsigned* __restrict__ ticket, double* __restrict__ local_norm,
@@ -473,11 +513,32 @@ select_gmm_kernel(const Geometry geo, const GtOffsets go, int num_gt_total,
         unsigned long long* keys = s_key[warp];
         int n_cand = 0;
 
+#ifdef PAA_PROFILE_GMM
+        const long long prof_t0 = clock64();
+#endif
         if (cls_label > 0) {        // loss.py:166 requires a positive IoU label
             for (int l = 0; l < geo.num_levels; ++l) {
                 const LevelView& lv = geo.lv[l];
                 const int t_end = (l + 1 < geo.num_levels) ? geo.lv[l + 1].tile_off : geo.tiles_per_image;
                 unsigned long long mine = kEmptyKey;   // lane j < K holds the j-th smallest key so far
+                const int seg = gi * geo.num_levels + l;
+                const int seg_n = __ldg(seg_count + seg);
+                if (seg_n <= sc.seg_cap) {
+                    // normal case: the anchors matched to this (GT, level) were pooled by match_score_kernel
+                    const unsigned long long* pool = seg_pool + (size_t)seg * kSegCap;
+                    for (int j0 = 0; j0 < seg_n; j0 += 4 * PAA_WARP) {
+                        unsigned long long k4[4];
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) {
+                            const int j = j0 + r * PAA_WARP + lane;
+                            k4[r] = (j < seg_n) ? __ldg(pool + j) : kEmptyKey;
+                        }
+#pragma unroll
+                        for (int r = 0; r < 4; ++r)
+                            if (j0 + r * PAA_WARP < seg_n) topk_offer(mine, k4[r], k4[r] != kEmptyKey, K, lane);
+                    }
+                } else
+                // overflowed pool: search the tiles of this level that contain anchors of this GT
                 for (int t0 = lv.tile_off; t0 < t_end; t0 += PAA_WARP) {
                     const int t = t0 + lane;
                     bool hit = false;
@@ -506,23 +567,7 @@ select_gmm_kernel(const Geometry geo, const GtOffsets go, int num_gt_total,
                             bool is = (mv[r] == g_local);
                             unsigned long long key = kEmptyKey;
                             if (is) key = ((unsigned long long)ordered_bits(sv[r]) << 32) | (unsigned)(lv.a_off + i);
-                            // keys that cannot enter the current top-K are dropped before the serial
-                            // insertion (the K-th key only ever decreases, so a stale bound is safe)
-                            const unsigned long long kth = __shfl_sync(PAA_FULL, mine, K - 1);
-                            is = is && (key < kth);
-                            unsigned hm = __ballot_sync(PAA_FULL, is);
-                            while (hm) {
-                                const int src = __ffs(hm) - 1;
-                                hm &= hm - 1;
-                                const unsigned long long nk = __shfl_sync(PAA_FULL, key, src);
-                                const unsigned less = __ballot_sync(PAA_FULL, lane < K && mine < nk);
-                                const int pos = __popc(less);
-                                const unsigned long long up = __shfl_up_sync(PAA_FULL, mine, 1);
-                                if (pos < K) {
-                                    if (lane == pos) mine = nk;
-                                    else if (lane > pos && lane < K) mine = up;
-                                }
-                            }
+                            topk_offer(mine, key, is, K, lane);
                         }
                     }
                 }
@@ -545,6 +590,9 @@ select_gmm_kernel(const Geometry geo, const GtOffsets go, int num_gt_total,
         }
         __syncwarp();
 
+#ifdef PAA_PROFILE_GMM
+        const long long prof_t1 = clock64();
+#endif
         if (n_cand == 1) {
             n_pos = 1;                                     // loss.py:218-219
         } else if (n_cand > 1) {
@@ -557,6 +605,12 @@ select_gmm_kernel(const Geometry geo, const GtOffsets go, int num_gt_total,
             n_pos = gmm_positive_prefix<SPL>(x, n_cand, lane, dbg.gmm ? dbg.gmm + (size_t)gi * 8 : nullptr);
         }
         if (dbg.gmm && n_cand <= 1 && lane < 8) dbg.gmm[(size_t)gi * 8 + lane] = 0.0;
+#ifdef PAA_PROFILE_GMM        // measurement build only: cycles of scan+sort / EM in the w0 / w1 debug slots
+        if (dbg.gmm && lane == 0) {
+            dbg.gmm[(size_t)gi * 8 + 0] = (double)(prof_t1 - prof_t0);
+            dbg.gmm[(size_t)gi * 8 + 1] = (double)(clock64() - prof_t1);
+        }
+#endif
 
         // labels of the positive prefix + this GT's share of the IoU normaliser (loss.py:228-230,331-333)
         for (int j = lane; j < n_cand; j += PAA_WARP) {
@@ -625,7 +679,8 @@ int launch_select_gmm(const Geometry& geo, const GtOffsets& go, int num_gt_total
     KernelTimer timer(PAA_KERNEL_SELECT_GMM, stream);
 #define PAA_SEL_LAUNCH(SPL)                                                                           \
     select_gmm_kernel<SPL><<<grid, threads, 0, stream>>>(geo, go, num_gt_total, gt_boxes, gt_labels, sc, \
-        ws.tile_gtmask, ws.matched, score_src, ws.paa_label, ws.part_npos, ws.part_siou,              \
+        ws.tile_gtmask, ws.matched, score_src, ws.seg_count, ws.seg_pool, ws.paa_label, ws.part_npos,  \
+        ws.part_siou,                                                                                  \
         ws.ticket, ws.local_norm, normalisers, dbg)
     if (cap <= 32) PAA_SEL_LAUNCH(1);
     else if (cap <= 64) PAA_SEL_LAUNCH(2);

@@ -8,6 +8,7 @@ namespace paa {
 struct LossScalars {
     float gamma, alpha, iou_threshold, reg_loss_weight, iou_loss_weight;
     int topk, use_iou_pred, world_size;
+    int seg_cap;       // usable entries of a (GT, level) candidate pool, <= kSegCap (PAA_SEG_CAP shrinks it for tests)
 };
 
 struct LossDebug {
@@ -26,7 +27,7 @@ int launch_iou_best(const Geometry& geo, const GtOffsets& go, const float* gt_bo
                     const LossWorkspace& ws, cudaStream_t stream);
 int launch_match_score(const Geometry& geo, const GtOffsets& go, const float* gt_boxes,
                        const int64_t* gt_labels, const LossScalars& sc, const LossWorkspace& ws,
-                       const LossDebug& dbg, cudaStream_t stream);
+                       const float* teacher_score, const LossDebug& dbg, cudaStream_t stream);
 int launch_select_gmm(const Geometry& geo, const GtOffsets& go, int num_gt_total, const float* gt_boxes,
                       const int64_t* gt_labels, const LossScalars& sc, const LossWorkspace& ws,
                       const float* score_src, double* normalisers, const LossDebug& dbg,

@@ -15,6 +15,7 @@ struct LossWorkspace {
     unsigned* gtmax;        // [sumG]   bit pattern of the per-GT maximal IoU
     int* img_flags;         // [N]      bit0: some GT of the image overlaps no anchor (culling off)
     unsigned* ticket;       // [4]      completion counters
+    int* seg_count;         // [sumG*L] anchors matched to (GT, level)
     size_t zero_bytes;
     // plain region
     uint2* best;            // [N*A]    (IoU bits, GT index) of every anchor's best GT
@@ -26,11 +27,16 @@ struct LossWorkspace {
     double* part_siou;      // [sumG]
     double* local_norm;     // [2]      this rank's {num_pos, sum_iou} (before the all-reduce)
     double* block_part;     // [blocks*3] per-block partial loss sums of the final kernel
+    unsigned long long* seg_pool;   // [sumG*L*kSegCap] (score bits, anchor) keys of the anchors matched to (GT, level)
     size_t total_bytes;
 };
 
+// Capacity of one (GT, level) candidate pool.  The anchors IoU-matched to one GT on one level number a few
+// hundred at most for PAA's anchor layout; a segment that overflows falls back to scanning the tiles.
+constexpr int kSegCap = 1024;
+
 inline LossWorkspace carve_loss_workspace(void* base, int N, int A, int sumG, int tiles_per_image,
-                                          int loss_blocks) {
+                                          int loss_blocks, int L) {
     LossWorkspace w;
     char* p = static_cast<char*>(base);
     size_t off = 0;
@@ -42,6 +48,7 @@ inline LossWorkspace carve_loss_workspace(void* base, int N, int A, int sumG, in
     w.gtmax = reinterpret_cast<unsigned*>(take(sizeof(unsigned) * (size_t)(sumG > 0 ? sumG : 1)));
     w.img_flags = reinterpret_cast<int*>(take(sizeof(int) * (size_t)N));
     w.ticket = reinterpret_cast<unsigned*>(take(sizeof(unsigned) * 4));
+    w.seg_count = reinterpret_cast<int*>(take(sizeof(int) * (size_t)(sumG > 0 ? sumG : 1) * L));
     w.zero_bytes = off;
     size_t NA = (size_t)N * A;
     w.best = reinterpret_cast<uint2*>(take(sizeof(uint2) * NA));
@@ -53,6 +60,8 @@ inline LossWorkspace carve_loss_workspace(void* base, int N, int A, int sumG, in
     w.part_siou = reinterpret_cast<double*>(take(sizeof(double) * (size_t)(sumG > 0 ? sumG : 1)));
     w.local_norm = reinterpret_cast<double*>(take(sizeof(double) * 2));
     w.block_part = reinterpret_cast<double*>(take(sizeof(double) * 3 * (size_t)loss_blocks));
+    w.seg_pool = reinterpret_cast<unsigned long long*>(
+        take(sizeof(unsigned long long) * (size_t)(sumG > 0 ? sumG : 1) * L * kSegCap));
     w.total_bytes = off;
     return w;
 }

@@ -208,3 +208,17 @@ def test_upstream_gradient_scaling():
     for k, t in enumerate(cls + reg + iou):
         w = (2.0, 3.0, 0.5)[k // L]
         torch.testing.assert_close(t.grad, g1[k] * w, rtol=1e-6, atol=1e-12)
+
+
+def test_candidate_pool_overflow_falls_back_to_tile_scan(monkeypatch):
+    """A (GT, level) pool that overflows is re-collected by scanning the tiles: identical labels."""
+    b = synthetic.make_batch(seed=9, num_images=2, image_hw=(416, 512), gt_per_image=(3, 9))
+    ev = _evaluator()
+    ev.debug = True
+    _run(ev, b, requires_grad=False)
+    want = {k: ev.last_debug[k].clone() for k in ("paa_labels", "cand_idx", "num_pos")}
+    assert int(ev.last_debug["cand_cnt"].max()) > 8
+    monkeypatch.setenv("PAA_SEG_CAP", "4")
+    _run(ev, b, requires_grad=False)
+    for k, v in want.items():
+        assert torch.equal(ev.last_debug[k], v), k

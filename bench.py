@@ -345,7 +345,7 @@ def run_ours(args):
 
     # other kernels' share (one eager pass each; reported, not part of `value`)
     shares = {}
-    for name in ("iou_best", "match_score", "select_gmm"):
+    for name in ("pass1", "match_score", "select_gmm"):
         lib.paa_kernel_timing_begin(_lib.KERNEL_IDS[name])
         for k in range(3):
             flush_buf.zero_()
@@ -420,7 +420,7 @@ def run_ours(args):
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 12,
                 "ms_per_step": max(e2e_ms, e2e_wall_ms) / args.steps},
-        # our kernels per step: iou_best, match_score, select_gmm, bulk_focal, positive_terms, finish_loss
+        # our kernels per step: assign_pass1, match_score, select_gmm, bulk_focal, positive_terms, finish_loss
         "gpu_launches": 6 * args.steps,
         "roofline": roofline,
         "step_ms_min_med_max": [min(step_ms), statistics.median(step_ms), max(step_ms)],

@@ -173,7 +173,7 @@ int paa_sigmoid_focal_loss_backward(const float* logits, const int32_t* targets,
 /* Measurement aid (not on the reference's interface): while enabled, every launch of the chosen kernel
  * is bracketed by CUDA events on its own stream; paa_kernel_timing_end waits for them and returns the
  * summed device time and the number of launches.  Do not enable during CUDA-graph capture. */
-#define PAA_KERNEL_IOU_BEST     1
+#define PAA_KERNEL_PASS1        1   /* assign_pass1_kernel: IoU matching + class sums of the logits */
 #define PAA_KERNEL_MATCH_SCORE  2
 #define PAA_KERNEL_SELECT_GMM   3
 #define PAA_KERNEL_FINAL_LOSS   4

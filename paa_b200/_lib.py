@@ -81,7 +81,7 @@ SYMBOLS = {
     "paa_kernel_timing_end": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
 }
 
-KERNEL_IDS = dict(iou_best=1, match_score=2, select_gmm=3, final_loss=4, post_candidates=10, post_filter=11,
+KERNEL_IDS = dict(pass1=1, match_score=2, select_gmm=3, final_loss=4, post_candidates=10, post_filter=11,
                   post_select=12, post_rank=13, post_nms_mask=14, post_nms_scan=15, post_finish=16, post_vote=17)
 
 _lib = None

@@ -215,7 +215,7 @@ int paa_assign(const PaaLossArgs* args, void* stream_) {
     if (rc) return rc;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     PAA_CUDA_CHECK(cudaMemsetAsync(args->workspace, 0, p.ws.zero_bytes, stream));
-    if ((rc = launch_iou_best(p.geo, p.go, args->gt_boxes, p.ws, stream))) return rc;
+    if ((rc = launch_assign_pass1(p.geo, p.go, args->gt_boxes, p.sc, p.ws, stream))) return rc;
     const float* score_src = args->teacher_combined_loss ? args->teacher_combined_loss : p.ws.score;
     if ((rc = launch_match_score(p.geo, p.go, args->gt_boxes, args->gt_labels, p.sc, p.ws,
                                  args->teacher_combined_loss, p.dbg, stream)))

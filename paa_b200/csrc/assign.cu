@@ -18,30 +18,79 @@
 namespace paa {
 
 // ---------------------------------------------------------------------------------------------
-// K1: every anchor's best GT (first maximum) and every GT's maximal IoU.
-// One block = one tile of 128 consecutive anchors of one level of one image.  GT boxes are staged
-// in shared memory in chunks; a warp only evaluates the GTs whose box intersects the warp's
-// bounding box (non-intersecting pairs have IoU exactly +0 and can neither raise a maximum nor
-// win the first-maximum rule against the initial (0, GT 0)).
+// K1: the first pass of the assignment, two independent jobs in ONE launch (horizontal fusion):
+//
+//  (a) IoU matching -- every anchor's best GT (first maximum) and every GT's maximal IoU.  A block takes
+//      two tiles of 128 consecutive anchors of one image.  GT boxes are staged in shared memory in
+//      chunks; a warp only evaluates the GTs whose box intersects the warp's bounding box
+//      (non-intersecting pairs have IoU exactly +0 and can neither raise a maximum nor win the
+//      first-maximum rule against the initial (0, GT 0)).  Issue/latency-bound, touches no head tensor.
+//  (b) class sums -- negsum[n, a] = sum_c p_c^gamma * softplus(x_c) for EVERY anchor, all classes taken
+//      as negatives.  The anchor score of an IoU-positive anchor is this sum with the labelled class's
+//      term swapped for the positive one (match_score_kernel), so this streaming pass is the only one
+//      over the logits that the assignment needs.  Memory-bound (every logit read once).
+//      Fast path (one anchor per location, H*W a multiple of 4, 16-byte aligned base): a block takes 256
+//      consecutive anchors of one level of one image as 64 float4 columns x 4 class groups.  A thread
+//      walks its group's C/4 class rows of one column, four loads in flight; a warp reads 512 contiguous
+//      bytes per row.  The four partial sums of a column are combined in a fixed order through shared
+//      memory.  Generic path: one thread per anchor, classes in order.  (40 registers, six blocks per SM:
+//      measured better than deeper per-thread prefetching at four blocks per SM.)
+//
+// Blocks of the two jobs alternate in the grid, so every SM holds both kinds at once and the matching
+// arithmetic runs in the shadow of the logit stream.  (As two launches on two streams the second kernel
+// only got the SM resources the first one left over, i.e. its tail.)
 // ---------------------------------------------------------------------------------------------
 constexpr int kGtChunk = 256;
+constexpr int kPassThreads = 256;
+constexpr int kSumCols = 64;                 // float4 columns per block (fast path of the class sums)
+constexpr int kSumGroups = kPassThreads / kSumCols;
 
-__global__ void __launch_bounds__(PAA_TILE)
-iou_best_kernel(const Geometry geo, const GtOffsets go, const float* __restrict__ gt_boxes,
-                unsigned* __restrict__ gtmax, uint2* __restrict__ best) {
-    __shared__ float4 s_gt[kGtChunk];
-    __shared__ float s_area[kGtChunk];
-    __shared__ unsigned s_max[kGtChunk];
+struct Pass1Plan {
+    unsigned item_off[PAA_MAX_LEVELS + 1];   // class sums: first work item of each level
+    unsigned chunks[PAA_MAX_LEVELS];         //             chunks per image
+    unsigned char vec[PAA_MAX_LEVELS];       //             float4 path
+    unsigned sum_blocks, iou_blocks;         // iou_blocks = num_images * ceil(tiles_per_image / 2)
+    int pairs_per_image;
+};
 
+// One negative-class focal term without its (1-alpha) factor: p^gamma * softplus(x).
+__device__ __forceinline__ float neg_term_only(float x, float gamma, bool g2) {
+    const SigmoidLean sl = sigmoid_lean(x);
+    return focal_pow(sl.p, gamma, g2) * sl.sp;
+}
+
+template <bool kG2>
+__device__ __forceinline__ void add_terms(float4& acc, float4 x, float gamma) {
+    acc.x += neg_term_only(x.x, gamma, kG2);
+    acc.y += neg_term_only(x.y, gamma, kG2);
+    acc.z += neg_term_only(x.z, gamma, kG2);
+    acc.w += neg_term_only(x.w, gamma, kG2);
+}
+
+union Pass1Smem {
+    struct {
+        float4 gt[kGtChunk];
+        float area[kGtChunk];
+        unsigned max[kGtChunk];
+    } iou;
+    float4 part[kSumGroups - 1][kSumCols];
+};
+
+__device__ __forceinline__ void iou_best_block(const Geometry& geo, const GtOffsets& go, unsigned q,
+                                               int pairs_per_image, const float* __restrict__ gt_boxes,
+                                               unsigned* __restrict__ gtmax, uint2* __restrict__ best,
+                                               Pass1Smem& sm) {
     // heaviest blocks first: the coarse levels (last tiles of an image) intersect every GT, and the
     // cost of a block grows with the GT count of its image
-    const int n = go.by_load[blockIdx.x % geo.num_images];
-    const int tile = geo.tiles_per_image - 1 - blockIdx.x / geo.num_images;
-    int first;
-    const int l = tile_level(geo, tile, &first);
+    const int n = go.by_load[q % geo.num_images];
+    const int pair = pairs_per_image - 1 - (int)(q / geo.num_images);
+    const int tile = 2 * pair + (threadIdx.x >> 7);
+    const bool tile_ok = tile < geo.tiles_per_image;
+    int first = 0;
+    const int l = tile_ok ? tile_level(geo, tile, &first) : 0;
     const LevelView& lv = geo.lv[l];
-    const int i = first + threadIdx.x;
-    const bool valid = i < lv.n_anchor;
+    const int i = first + (threadIdx.x & (PAA_TILE - 1));
+    const bool valid = tile_ok && i < lv.n_anchor;
     const int lane = threadIdx.x & 31;
 
     float4 a = make_float4(INFINITY, INFINITY, -INFINITY, -INFINITY);
@@ -56,18 +105,18 @@ iou_best_kernel(const Geometry geo, const GtOffsets go, const float* __restrict_
 
     for (int c0 = 0; c0 < G; c0 += kGtChunk) {
         const int cnt = min(kGtChunk, G - c0);
-        for (int t = threadIdx.x; t < cnt; t += PAA_TILE) {
+        for (int t = threadIdx.x; t < cnt; t += kPassThreads) {
             float4 b = ldg4(gt_boxes + (size_t)(gbase + c0 + t) * 4);
-            s_gt[t] = b;
-            s_area[t] = area_plus1(b);
-            s_max[t] = 0u;
+            sm.iou.gt[t] = b;
+            sm.iou.area[t] = area_plus1(b);
+            sm.iou.max[t] = 0u;
         }
         __syncthreads();
         for (int g0 = 0; g0 < cnt; g0 += PAA_WARP) {
             const int g = g0 + lane;
             bool hit = false;
             if (g < cnt) {
-                float4 b = s_gt[g];
+                float4 b = sm.iou.gt[g];
                 float w = __fadd_rn(__fsub_rn(fminf(b.z, wx2), fmaxf(b.x, wx1)), 1.0f);
                 float h = __fadd_rn(__fsub_rn(fminf(b.w, wy2), fmaxf(b.y, wy1)), 1.0f);
                 hit = (w > 0.0f) && (h > 0.0f);
@@ -76,30 +125,147 @@ iou_best_kernel(const Geometry geo, const GtOffsets go, const float* __restrict_
             while (m) {
                 const int j = g0 + __ffs(m) - 1;
                 m &= m - 1;
-                float q = 0.0f;
-                if (valid) q = iou_plus1(s_gt[j], s_area[j], a, area_a);
-                if (q > best_v) {
-                    best_v = q;
+                float qv = 0.0f;
+                if (valid) qv = iou_plus1(sm.iou.gt[j], sm.iou.area[j], a, area_a);
+                if (qv > best_v) {
+                    best_v = qv;
                     best_g = c0 + j;
                 }
-                unsigned wm = __reduce_max_sync(PAA_FULL, __float_as_uint(q));
-                if (lane == 0 && wm != 0u) atomicMax(&s_max[j], wm);
+                unsigned wm = __reduce_max_sync(PAA_FULL, __float_as_uint(qv));
+                if (lane == 0 && wm != 0u) atomicMax(&sm.iou.max[j], wm);
             }
         }
         __syncthreads();
-        for (int t = threadIdx.x; t < cnt; t += PAA_TILE)
-            if (s_max[t] != 0u) atomicMax(&gtmax[gbase + c0 + t], s_max[t]);
+        for (int t = threadIdx.x; t < cnt; t += kPassThreads)
+            if (sm.iou.max[t] != 0u) atomicMax(&gtmax[gbase + c0 + t], sm.iou.max[t]);
         __syncthreads();
     }
     if (valid) best[(size_t)n * geo.A + lv.a_off + i] = make_uint2(__float_as_uint(best_v), (unsigned)best_g);
 }
 
-int launch_iou_best(const Geometry& geo, const GtOffsets& go, const float* gt_boxes,
-                    const LossWorkspace& ws, cudaStream_t stream) {
-    int grid = geo.num_images * geo.tiles_per_image;
-    KernelTimer timer(PAA_KERNEL_IOU_BEST, stream);
-    iou_best_kernel<<<grid, PAA_TILE, 0, stream>>>(geo, go, gt_boxes, ws.gtmax, ws.best);
-    PAA_LAUNCH_CHECK("iou_best_kernel");
+template <bool kG2>
+__device__ __forceinline__ void class_sum_block(const Geometry& geo, const Pass1Plan& plan, unsigned b,
+                                                float gamma, float* __restrict__ negsum, Pass1Smem& sm) {
+    int l = 0;
+#pragma unroll
+    for (int k = 1; k < PAA_MAX_LEVELS; ++k)
+        if (k < geo.num_levels && b >= plan.item_off[k]) l = k;
+    const LevelView& lv = geo.lv[l];
+    const unsigned item = b - plan.item_off[l];
+    const int n = (int)(item / plan.chunks[l]);
+    const int chunk = (int)(item - (unsigned)n * plan.chunks[l]);
+    const int C = geo.C;
+    if (plan.vec[l]) {
+        const int col = threadIdx.x & (kSumCols - 1), grp = threadIdx.x / kSumCols;
+        const int i = (chunk * kSumCols + col) * 4;                       // first of this column's 4 anchors
+        const bool in = i < lv.n_anchor;
+        const int cg = (C + kSumGroups - 1) / kSumGroups;
+        const int c_begin = grp * cg, c_end = min(C, c_begin + cg);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (in) {
+            const unsigned st = (unsigned)lv.hw >> 2;                     // float4 per class row
+            const float4* p = reinterpret_cast<const float4*>(lv.cls + (size_t)n * C * lv.hw + i);
+            int c0 = c_begin;
+            for (; c0 + 4 <= c_end; c0 += 4) {
+                float4 x[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) x[j] = __ldg(p + (size_t)(c0 + j) * st);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) add_terms<kG2>(acc, x[j], gamma);
+            }
+            for (; c0 < c_end; ++c0) add_terms<kG2>(acc, __ldg(p + (size_t)c0 * st), gamma);
+        }
+        if (grp > 0) sm.part[grp - 1][col] = acc;
+        __syncthreads();
+        if (grp == 0 && in) {
+#pragma unroll
+            for (int g = 0; g < kSumGroups - 1; ++g) {
+                const float4 o = sm.part[g][col];
+                acc.x += o.x;
+                acc.y += o.y;
+                acc.z += o.z;
+                acc.w += o.w;
+            }
+            const size_t flat = (size_t)n * geo.A + lv.a_off + i;
+            if ((flat & 3) == 0) {
+                *reinterpret_cast<float4*>(negsum + flat) = acc;
+            } else {
+                negsum[flat] = acc.x;
+                negsum[flat + 1] = acc.y;
+                negsum[flat + 2] = acc.z;
+                negsum[flat + 3] = acc.w;
+            }
+        }
+    } else {
+        const int i = chunk * kPassThreads + threadIdx.x;
+        if (i >= lv.n_anchor) return;
+        const float* p = lv.cls + head_offset(n, i, 0, C, geo.apl, lv.hw);
+        const unsigned st = (unsigned)lv.hw;
+        float acc = 0.f;
+        int c0 = 0;
+        for (; c0 + 8 <= C; c0 += 8) {
+            float x[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) x[j] = __ldg(p + (size_t)(c0 + j) * st);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc += neg_term_only(x[j], gamma, kG2);
+        }
+        for (; c0 < C; ++c0) acc += neg_term_only(__ldg(p + (size_t)c0 * st), gamma, kG2);
+        negsum[(size_t)n * geo.A + lv.a_off + i] = acc;
+    }
+}
+
+template <bool kG2>
+__global__ void __launch_bounds__(kPassThreads, 6)
+assign_pass1_kernel(const Geometry geo, const GtOffsets go, const Pass1Plan plan, float gamma,
+                    const float* __restrict__ gt_boxes, unsigned* __restrict__ gtmax,
+                    uint2* __restrict__ best, float* __restrict__ negsum) {
+    __shared__ Pass1Smem sm;
+    // the first 2*min(sum_blocks, iou_blocks) blocks alternate between the jobs, the rest belong to the longer one
+    const unsigned m = min(plan.sum_blocks, plan.iou_blocks);
+    const unsigned b = blockIdx.x;
+    bool is_iou;
+    unsigned idx;
+    if (b < 2 * m) {
+        is_iou = (b & 1u) == 0u;
+        idx = b >> 1;
+    } else {
+        is_iou = plan.iou_blocks > plan.sum_blocks;
+        idx = b - m;
+    }
+    if (is_iou) iou_best_block(geo, go, idx, plan.pairs_per_image, gt_boxes, gtmax, best, sm);
+    else class_sum_block<kG2>(geo, plan, idx, gamma, negsum, sm);
+}
+
+int launch_assign_pass1(const Geometry& geo, const GtOffsets& go, const float* gt_boxes, const LossScalars& sc,
+                        const LossWorkspace& ws, cudaStream_t stream) {
+    Pass1Plan plan;
+    unsigned items = 0;
+    for (int l = 0; l < PAA_MAX_LEVELS; ++l) {
+        plan.item_off[l] = items;
+        plan.chunks[l] = 0;
+        plan.vec[l] = 0;
+        if (l >= geo.num_levels) continue;
+        const LevelView& lv = geo.lv[l];
+        const bool vec = geo.apl == 1 && (lv.hw & 3) == 0 && (reinterpret_cast<uintptr_t>(lv.cls) & 15u) == 0;
+        const int per_block = vec ? kSumCols * 4 : kPassThreads;
+        plan.vec[l] = vec ? 1 : 0;
+        plan.chunks[l] = (unsigned)((lv.n_anchor + per_block - 1) / per_block);
+        items += plan.chunks[l] * (unsigned)geo.num_images;
+    }
+    plan.item_off[PAA_MAX_LEVELS] = items;
+    plan.sum_blocks = items;
+    plan.pairs_per_image = (geo.tiles_per_image + 1) / 2;
+    plan.iou_blocks = (unsigned)geo.num_images * (unsigned)plan.pairs_per_image;
+    const unsigned grid = plan.sum_blocks + plan.iou_blocks;
+    KernelTimer timer(PAA_KERNEL_PASS1, stream);
+    if (sc.gamma == 2.0f)
+        assign_pass1_kernel<true><<<grid, kPassThreads, 0, stream>>>(geo, go, plan, sc.gamma, gt_boxes, ws.gtmax,
+                                                                     ws.best, ws.negsum);
+    else
+        assign_pass1_kernel<false><<<grid, kPassThreads, 0, stream>>>(geo, go, plan, sc.gamma, gt_boxes, ws.gtmax,
+                                                                      ws.best, ws.negsum);
+    PAA_LAUNCH_CHECK("assign_pass1_kernel");
     return 0;
 }
 
@@ -108,7 +274,8 @@ int launch_iou_best(const Geometry& geo, const GtOffsets& go, const float* gt_bo
 //   matched = argmax GT if max IoU >= thr, else -1, except that an anchor which is some GT's best
 //   anchor (IoU == that GT's maximum, ties included) keeps its argmax GT (matcher.py:83-113).
 //   Only GTs whose maximum is below thr can restore anything, so those are listed first.
-//   score   = sum_c focal(logit_c | IoU label) + (1 - GIoU(decode(pred), decode(encode(gt))))
+//   score   = sum_c focal(logit_c | IoU label) + (1 - GIoU(decode(pred), decode(encode(gt))));
+//             the class sum comes from class_sum_kernel (K0)
 //   (loss.py:293-306; anchors without an IoU-positive label are never candidates, their 1e8 filler
 //   is not materialised).
 // ---------------------------------------------------------------------------------------------
@@ -121,43 +288,11 @@ __device__ __forceinline__ float from_ordered_bits(unsigned u) {
     return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
 }
 
-// sum_c focal(x_c | label) for one anchor; `p` points at class 0, consecutive classes are `stride` apart.
-// Loads are issued eight at a time before any of them is consumed.  Every class is first taken as a
-// negative (lean math), then the labelled class's negative term is swapped for the positive one
-// (accurate path for that single term).
-__device__ __forceinline__ float neg_term_only(float x, float gamma, bool g2) {
-    const SigmoidLean sl = sigmoid_lean(x);
-    return focal_pow(sl.p, gamma, g2) * sl.sp;
-}
-
-__device__ __forceinline__ float focal_sum(const float* __restrict__ p, int stride, int C, int label,
-                                           float gamma, float alpha) {
-    const bool g2 = (gamma == 2.0f);
-    const float oma = 1.0f - alpha;
-    float neg = 0.0f;
-    const unsigned st = (unsigned)stride;
-    float xl = 0.0f;
-    for (int c0 = 0; c0 < C; c0 += 8) {
-        float x[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) x[j] = (c0 + j < C) ? __ldg(p + (unsigned)(c0 + j) * st) : -100.0f;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {      // a padded logit of -100 contributes exactly 0
-            neg += neg_term_only(x[j], gamma, g2);
-            if (c0 + j + 1 == label) xl = x[j];
-        }
-    }
-    const SigmoidParts sp = sigmoid_parts(xl);
-    float tp, gp;
-    focal_positive(xl, sp, gamma, g2, alpha, &tp, &gp);
-    return fmaf(oma, neg - neg_term_only(xl, gamma, g2), tp);
-}
-
 __global__ void __launch_bounds__(PAA_TILE)
 match_score_kernel(const Geometry geo, const GtOffsets go, const float* __restrict__ gt_boxes,
                    const int64_t* __restrict__ gt_labels, const unsigned* __restrict__ gtmax,
-                   const uint2* __restrict__ best, const LossScalars sc, int* __restrict__ matched,
-                   float* __restrict__ score, int* __restrict__ paa_label, uint4* __restrict__ tile_gtmask,
+                   const uint2* __restrict__ best, const float* __restrict__ negsum, const LossScalars sc,
+                   int* __restrict__ matched, float* __restrict__ score, int* __restrict__ paa_label, uint4* __restrict__ tile_gtmask,
                    int* __restrict__ seg_count, unsigned long long* __restrict__ seg_pool,
                    const float* __restrict__ teacher_score, const LossDebug dbg) {
     __shared__ int s_lq[PAA_TILE];
@@ -226,8 +361,13 @@ match_score_kernel(const Geometry geo, const GtOffsets go, const float* __restri
 
     float s = 1.0e8f;   // loss.py:15,301-306 filler, only visible through the debug output
     if (m >= 0 && label > 0) {
-        const float* cls = lv.cls + head_offset(n, i, 0, geo.C, geo.apl, lv.hw);
-        const float fsum = focal_sum(cls, lv.hw, geo.C, label, sc.gamma, sc.alpha);
+        // sum_c focal(x_c | label): every class as a negative (class_sum_kernel), then the labelled class's
+        // negative term swapped for the positive one (accurate path for that single term)
+        const float xl = __ldg(lv.cls + head_offset(n, i, label - 1, geo.C, geo.apl, lv.hw));
+        const bool g2 = (sc.gamma == 2.0f);
+        float tp, gp;
+        focal_positive(xl, sigmoid_parts(xl), sc.gamma, g2, sc.alpha, &tp, &gp);
+        const float fsum = fmaf(1.0f - sc.alpha, __ldg(negsum + flat) - neg_term_only(xl, sc.gamma, g2), tp);
         const float* rp = lv.reg + head_offset(n, i, 0, 4, geo.apl, lv.hw);
         const float4 d = make_float4(__ldg(rp), __ldg(rp + lv.hw), __ldg(rp + 2 * (size_t)lv.hw),
                                      __ldg(rp + 3 * (size_t)lv.hw));
@@ -254,18 +394,18 @@ int launch_match_score(const Geometry& geo, const GtOffsets& go, const float* gt
                        const float* teacher_score, const LossDebug& dbg, cudaStream_t stream) {
     int grid = geo.num_images * geo.tiles_per_image;
     KernelTimer timer(PAA_KERNEL_MATCH_SCORE, stream);
-    match_score_kernel<<<grid, PAA_TILE, 0, stream>>>(geo, go, gt_boxes, gt_labels, ws.gtmax, ws.best, sc,
-                                                      ws.matched, ws.score, ws.paa_label, ws.tile_gtmask,
+    match_score_kernel<<<grid, PAA_TILE, 0, stream>>>(geo, go, gt_boxes, gt_labels, ws.gtmax, ws.best, ws.negsum,
+                                                      sc, ws.matched, ws.score, ws.paa_label, ws.tile_gtmask,
                                                       ws.seg_count, ws.seg_pool, teacher_score, dbg);
     PAA_LAUNCH_CHECK("match_score_kernel");
     return 0;
 }
 
 // ---------------------------------------------------------------------------------------------
-// K3: one warp per GT -- per-level top-k candidates, sort, two-component GMM, labels, partial
-// normalisers.  loss.py:151-236 + sklearn GaussianMixture.fit/predict/score_samples.
+// K3: one block per GT -- warp l collects the top-k candidates of level l, then warp 0 sorts them,
+// fits the two-component GMM, labels the positive prefix and leaves the GT's partial normalisers.
+// loss.py:151-236 + sklearn GaussianMixture.fit/predict/score_samples.
 // ---------------------------------------------------------------------------------------------
-constexpr int kSelWarps = 4;                // GTs per block
 constexpr unsigned long long kEmptyKey = ~0ull;
 
 // sklearn/utils/_array_api.py:1338-1366 for two entries.
@@ -274,67 +414,58 @@ __device__ __forceinline__ double logsumexp2(double a0, double a1) {
     const double hi = fmax(a0, a1), lo = fmin(a0, a1);
     return (log1p(exp(lo - hi)) + 0.0) + hi;                          // m = 1, log(m) = 0
 }
-// Same, also returning the responsibilities exp(a_k - lse).  They are formed as 1/(1+s) and s/(1+s)
-// with s = exp(lo - hi): one exp and one division instead of three exps; the results differ from
-// sklearn's exp(a_k - lse) by a few 1e-16 relative, far below anything the float32 roundings of
-// the next E-step can see.
-__device__ __forceinline__ double logsumexp2_resp(double a0, double a1, double* r0, double* r1) {
-    if (a0 == a1) {
-        *r0 = 0.5;
-        *r1 = 0.5;
-        return (log1p(0.0) + 0.6931471805599453094) + a0;
-    }
-    const bool first_hi = a0 > a1;
-    const double hi = first_hi ? a0 : a1, lo = first_hi ? a1 : a0;
-    const double s = exp_nonpos(lo - hi);
-    const double rh = div_fast(1.0, 1.0 + s), rl = s * rh;
-    *r0 = first_hi ? rh : rl;
-    *r1 = first_hi ? rl : rh;
-    return (log1p_unit(s) + 0.0) + hi;
-}
 
+// Mixture parameters as every lane holds them between iterations.  lw = log(w), ld = float32(log(pc)).
 struct GmmState {
-    double w0, w1, mu0, mu1;
-    float pc0, pc1, var0, var1;
-    bool first;                    // precisions still the float64 initial values (1.0)
+    double mu0, mu1, lw0, lw1;
+    float pc0, pc1, ld0, ld1;
 };
 
 // a_k = log N(x | mu_k, pc_k) + log w_k with the dtype flow of _estimate_log_gaussian_prob
 // (sklearn/mixture/_gaussian_mixture.py:490-553): float32 product x*pc and float32 log-det once the
 // precisions have been re-estimated, float32 buffer for the squared distance, float64 elsewhere.
-__device__ __forceinline__ void weighted_log_prob(float x, const GmmState& s, double lw0, double lw1,
-                                                  float ld0, float ld1, double* a0, double* a1) {
+// The initial float64 precisions (1.0) need no special case: x * 1.0f and lp + 0.0f are exact.
+__device__ __forceinline__ void weighted_log_prob(float x, const GmmState& s, double* a0, double* a1) {
     const float LOG2PI = 1.8378770664093453f;
-    double xs0, xs1;
-    if (s.first) {
-        xs0 = (double)x;
-        xs1 = (double)x;
-    } else {
-        xs0 = (double)__fmul_rn(x, s.pc0);
-        xs1 = (double)__fmul_rn(x, s.pc1);
-    }
-    const double y0 = xs0 - s.mu0 * (double)s.pc0;
-    const double y1 = xs1 - s.mu1 * (double)s.pc1;
+    const double y0 = (double)__fmul_rn(x, s.pc0) - s.mu0 * (double)s.pc0;
+    const double y1 = (double)__fmul_rn(x, s.pc1) - s.mu1 * (double)s.pc1;
     const float q0 = __double2float_rn(y0 * y0);
     const float q1 = __double2float_rn(y1 * y1);
     const float lp0 = __fmul_rn(-0.5f, __fadd_rn(LOG2PI, q0));
     const float lp1 = __fmul_rn(-0.5f, __fadd_rn(LOG2PI, q1));
-    if (s.first) {                    // float32 array + float64 log-det (log 1.0 = 0)
-        *a0 = ((double)lp0 + 0.0) + lw0;
-        *a1 = ((double)lp1 + 0.0) + lw1;
-    } else {                          // float32 log-det, float32 add
-        *a0 = (double)__fadd_rn(lp0, ld0) + lw0;
-        *a1 = (double)__fadd_rn(lp1, ld1) + lw1;
-    }
+    *a0 = (double)__fadd_rn(lp0, s.ld0) + s.lw0;
+    *a1 = (double)__fadd_rn(lp1, s.ld1) + s.lw1;
+}
+
+__device__ __forceinline__ double warp_prod(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v *= __shfl_xor_sync(PAA_FULL, v, o);
+    return v;
 }
 
 // Fits the mixture on the warp's n sorted samples (lane holds x[lane + 32*k]) and returns the length
 // of the positive prefix (loss.py:206-217).  out8 (nullable, lane 0 writes) receives the parameters.
+//
+// The fit is a serial chain of float64 operations with nothing to overlap it with, so an iteration is
+// organised for the shortest chain and the fewest issued instructions:
+//  * E-step, one sample per lane: s = exp(lo - hi), responsibilities 1/(1+s) and s/(1+s) (one exp and one
+//    reciprocal instead of sklearn's three exps; they differ from exp(a_k - lse) by a few 1e-16, far
+//    below what the float32 roundings of the next E-step can see).
+//  * The mean log-likelihood that drives the stopping rule is sum(hi) + log(prod(1 + s)): one logarithm
+//    per iteration instead of one log1p per sample (the product of <= 128 factors in [1, 2] is exact to
+//    ~1e-14 relative, the rule compares against 1e-3).
+//  * One reduction round: moments are taken about the PREVIOUS means (p0, p1), from which the new mean and
+//    the variance about the new mean follow exactly:
+//        sum r x = A + p S,   sum r (x - mu)^2 = B - 2 d A + d^2 S   with d = mu - p.
+//    (sklearn evaluates sum r (x - mu)^2 directly; the two agree to ~1e-14 relative, far below the
+//    float32 rounding of the variance that follows.)
+//  * M-step in lanes: even lanes update component 0 and odd lanes component 1 with one instruction stream,
+//    and the iteration's five logarithms (log pc_k in lanes 0-1, log w_k in lanes 2-3, log prod in lane 4)
+//    are one call.
 template <int SPL>
 __device__ int gmm_positive_prefix(const float (&x)[SPL], int n, int lane, double* out8) {
     GmmState s;
-    s.w0 = 0.5;
-    s.w1 = 0.5;
+    s.lw0 = s.lw1 = -0.6931471805599453094;                              // log 0.5
     s.mu0 = (double)__shfl_sync(PAA_FULL, x[0], 0);                       // min (sorted ascending)
     {
         const int last = n - 1;
@@ -347,30 +478,32 @@ __device__ int gmm_positive_prefix(const float (&x)[SPL], int n, int lane, doubl
         s.mu1 = (double)xl;                                               // max
     }
     s.pc0 = s.pc1 = 1.0f;
-    s.var0 = s.var1 = 1.0f;
-    s.first = true;
+    s.ld0 = s.ld1 = 0.0f;
+    double w_mine = 0.5;            // lane-parity copies of the last M-step, for the debug output only
+    float var_mine = 1.0f;
     double lower = -INFINITY;
     int n_iter = 0;
     bool converged = false;
     const double EPS10 = 10.0 * 2.220446049250313e-16;
+    const double inv_n = 1.0 / (double)n;
+    const bool odd = (lane & 1) != 0;
     for (int it = 1; it <= 100; ++it) {
         n_iter = it;
-        const double lw0 = log_pos(s.w0), lw1 = log_pos(s.w1);
-        const float ld0 = s.first ? 0.f : __double2float_rn(log_pos((double)s.pc0));
-        const float ld1 = s.first ? 0.f : __double2float_rn(log_pos((double)s.pc1));
-        // One reduction round per iteration: moments are taken about the PREVIOUS means (p0, p1), from
-        // which the new mean and the variance about the new mean follow exactly:
-        //   sum r x = A + p S,   sum r (x - mu)^2 = B - 2 d A + d^2 S   with d = mu - p.
-        // (sklearn evaluates sum r (x - mu)^2 directly; the two agree to ~1e-14 relative, far below the
-        // float32 rounding of the variance that follows.)
         const double p0 = s.mu0, p1 = s.mu1;
-        double S0 = 0, S1 = 0, A0 = 0, A1 = 0, B0 = 0, B1 = 0, s_lpn = 0;
+        double S0 = 0, S1 = 0, A0 = 0, A1 = 0, B0 = 0, B1 = 0, H = 0, P = 1.0;
 #pragma unroll
         for (int k = 0; k < SPL; ++k) {
             if (lane + 32 * k < n) {
-                double a0, a1, r0, r1;
-                weighted_log_prob(x[k], s, lw0, lw1, ld0, ld1, &a0, &a1);
-                s_lpn += logsumexp2_resp(a0, a1, &r0, &r1);
+                double a0, a1;
+                weighted_log_prob(x[k], s, &a0, &a1);
+                const bool first_hi = a0 >= a1;
+                const double hi = first_hi ? a0 : a1, lo = first_hi ? a1 : a0;
+                const double sx = exp_nonpos(lo - hi);
+                const double u = 1.0 + sx;
+                const double rh = rcp_fast(u), rl = sx * rh;
+                const double r0 = first_hi ? rh : rl, r1 = first_hi ? rl : rh;
+                H += hi;
+                P *= u;
                 const double e0 = (double)x[k] - p0, e1 = (double)x[k] - p1;
                 const double t0 = r0 * e0, t1 = r1 * e1;
                 S0 += r0;
@@ -387,22 +520,33 @@ __device__ int gmm_positive_prefix(const float (&x)[SPL], int n, int lane, doubl
         A1 = warp_sum(A1);
         B0 = warp_sum(B0);
         B1 = warp_sum(B1);
-        s_lpn = warp_sum(s_lpn);
-        const double nk0 = S0 + EPS10, nk1 = S1 + EPS10;
-        s.mu0 = div_fast(fma(p0, S0, A0), nk0);
-        s.mu1 = div_fast(fma(p1, S1, A1), nk1);
-        const double d0 = s.mu0 - p0, d1 = s.mu1 - p1;
-        const double c0 = fma(d0, fma(d0, S0, -2.0 * A0), B0);
-        const double c1 = fma(d1, fma(d1, S1, -2.0 * A1), B1);
-        s.var0 = __fadd_rn(__double2float_rn(div_fast(fmax(c0, 0.0), nk0)), 1e-6f);
-        s.var1 = __fadd_rn(__double2float_rn(div_fast(fmax(c1, 0.0), nk1)), 1e-6f);
-        const double nsum = nk0 + nk1;
-        s.w0 = div_fast(nk0, nsum);
-        s.w1 = div_fast(nk1, nsum);
-        s.pc0 = __fdiv_rn(1.0f, __fsqrt_rn(s.var0));
-        s.pc1 = __fdiv_rn(1.0f, __fsqrt_rn(s.var1));
-        s.first = false;
-        const double lb = div_fast(s_lpn, (double)n);
+        H = warp_sum(H);
+        P = warp_prod(P);
+        // M-step of this lane's component
+        const double S = odd ? S1 : S0, A = odd ? A1 : A0, B = odd ? B1 : B0, p = odd ? p1 : p0;
+        const double nk = S + EPS10;
+        const double nsum = (S0 + EPS10) + (S1 + EPS10);
+        const double rn = rcp_fast(nk);
+        const double num = fma(p, S, A);
+        double mu = num * rn;
+        mu = fma(fma(-nk, mu, num), rn, mu);
+        const double d = mu - p;
+        const double c = fma(d, fma(d, S, -2.0 * A), B);
+        const float var = __fadd_rn(__double2float_rn(fmax(c, 0.0) * rn), 1e-6f);
+        const float pc = __fdiv_rn(1.0f, __fsqrt_rn(var));
+        const double w = nk * rcp_fast(nsum);
+        const double lg = log_pos(lane < 2 ? (double)pc : (lane < 4 ? w : P));
+        s.mu0 = __shfl_sync(PAA_FULL, mu, 0);
+        s.mu1 = __shfl_sync(PAA_FULL, mu, 1);
+        s.pc0 = __shfl_sync(PAA_FULL, pc, 0);
+        s.pc1 = __shfl_sync(PAA_FULL, pc, 1);
+        s.ld0 = __double2float_rn(__shfl_sync(PAA_FULL, lg, 0));
+        s.ld1 = __double2float_rn(__shfl_sync(PAA_FULL, lg, 1));
+        s.lw0 = __shfl_sync(PAA_FULL, lg, 2);
+        s.lw1 = __shfl_sync(PAA_FULL, lg, 3);
+        const double lb = (H + __shfl_sync(PAA_FULL, lg, 4)) * inv_n;
+        w_mine = w;
+        var_mine = var;
         const double change = lb - lower;
         lower = lb;
         if (fabs(change) < 1e-3) {
@@ -411,9 +555,6 @@ __device__ int gmm_positive_prefix(const float (&x)[SPL], int n, int lane, doubl
         }
     }
     // final E-step: predict (argmax, ties -> 0) and score_samples
-    const double lw0 = log(s.w0), lw1 = log(s.w1);
-    const float ld0 = __double2float_rn(log((double)s.pc0));
-    const float ld1 = __double2float_rn(log((double)s.pc1));
     double best_score = -INFINITY;
     int best_idx = 0x7fffffff;
     bool any_fg = false;
@@ -421,7 +562,7 @@ __device__ int gmm_positive_prefix(const float (&x)[SPL], int n, int lane, doubl
     for (int k = 0; k < SPL; ++k) {
         if (lane + 32 * k < n) {
             double a0, a1;
-            weighted_log_prob(x[k], s, lw0, lw1, ld0, ld1, &a0, &a1);
+            weighted_log_prob(x[k], s, &a0, &a1);
             if (!(a1 > a0)) {                 // component 0 == foreground (loss.py:206)
                 const double sc = logsumexp2(a0, a1);
                 any_fg = true;
@@ -443,15 +584,19 @@ __device__ int gmm_positive_prefix(const float (&x)[SPL], int n, int lane, doubl
         }
     }
     any_fg = __any_sync(PAA_FULL, any_fg);
-    if (out8 && lane == 0) {
-        out8[0] = s.w0;
-        out8[1] = s.w1;
-        out8[2] = s.mu0;
-        out8[3] = s.mu1;
-        out8[4] = (double)s.var0;
-        out8[5] = (double)s.var1;
-        out8[6] = (double)n_iter;
-        out8[7] = converged ? 1.0 : 0.0;
+    if (out8) {
+        const double w1 = __shfl_sync(PAA_FULL, w_mine, 1);
+        const float v1 = __shfl_sync(PAA_FULL, var_mine, 1);
+        if (lane == 0) {
+            out8[0] = w_mine;
+            out8[1] = w1;
+            out8[2] = s.mu0;
+            out8[3] = s.mu1;
+            out8[4] = (double)var_mine;
+            out8[5] = (double)v1;
+            out8[6] = (double)n_iter;
+            out8[7] = converged ? 1.0 : 0.0;
+        }
     }
     return any_fg ? best_idx + 1 : n;
 }
@@ -478,8 +623,25 @@ __device__ __forceinline__ void topk_offer(unsigned long long& mine, unsigned lo
     }
 }
 
+// Starts the list from one batch of up to 32 keys (one per lane, kEmptyKey where there is none): every
+// lane ranks its key against the other 31 with independent shuffles (no serial insertion), the keys
+// are scattered by rank through `scratch` (32 entries of this warp).  Valid keys are distinct.
+__device__ __forceinline__ unsigned long long topk_first_batch(unsigned long long key, int K, int lane,
+                                                               unsigned long long* scratch) {
+    int rank = 0;
+#pragma unroll
+    for (int j = 0; j < PAA_WARP; ++j) rank += (__shfl_sync(PAA_FULL, key, j) < key) ? 1 : 0;
+    scratch[lane] = kEmptyKey;
+    __syncwarp();
+    if (key != kEmptyKey) scratch[rank] = key;
+    __syncwarp();
+    const unsigned long long mine = (lane < K) ? scratch[lane] : kEmptyKey;
+    __syncwarp();
+    return mine;
+}
+
 template <int SPL>
-__global__ void __launch_bounds__(kSelWarps * PAA_WARP)
+__global__ void __launch_bounds__(PAA_MAX_LEVELS * PAA_WARP)
 select_gmm_kernel(const Geometry geo, const GtOffsets go, int num_gt_total,
                   const float* __restrict__ gt_boxes, const int64_t* __restrict__ gt_labels,
                   const LossScalars sc, const uint4* __restrict__ tile_gtmask,
@@ -489,56 +651,63 @@ select_gmm_kernel(const Geometry geo, const GtOffsets go, int num_gt_total,
                   int* __restrict__ part_npos, double* __restrict__ part_siou,
                   unsigned* __restrict__ ticket, double* __restrict__ local_norm,
                   double* __restrict__ normalisers, const LossDebug dbg) {
-    __shared__ unsigned long long s_key[kSelWarps][PAA_MAX_CANDIDATES];
-    __shared__ unsigned long long s_sorted[kSelWarps][PAA_MAX_CANDIDATES];
+    __shared__ unsigned long long s_level[PAA_MAX_LEVELS][PAA_WARP];   // per-level top-K, ascending
+    __shared__ int s_cnt[PAA_MAX_LEVELS];
+    __shared__ unsigned long long s_key[PAA_MAX_CANDIDATES];
+    __shared__ unsigned long long s_sorted[PAA_MAX_CANDIDATES];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int gi = blockIdx.x * kSelWarps + warp;
+    const int gi = blockIdx.x;
     const int K = sc.topk;
     const int cap = geo.num_levels * K;
-    int n_pos = 0;
-    double siou = 0.0;
-    if (gi < num_gt_total) {
-        // image of this GT
-        int n = 0;
-        for (int k = 1; k < geo.num_images; ++k)
-            if (gi >= go.v[k]) n = k;
-        const int g_local = gi - go.v[n];
-        const float4 gt = ldg4(gt_boxes + (size_t)gi * 4);
-        const int cls_label = (int)gt_labels[gi];
-        const unsigned gbit = 1u << (g_local & 31);
-        const int gword = (g_local & 127) >> 5;
-        const int* mrow = matched + (size_t)n * geo.A;
-        const float* srow = score + (size_t)n * geo.A;
-        unsigned long long* keys = s_key[warp];
-        int n_cand = 0;
+    // image of this GT
+    int n = 0;
+    for (int k = 1; k < geo.num_images; ++k)
+        if (gi >= go.v[k]) n = k;
+    const int g_local = gi - go.v[n];
+    const int cls_label = (int)gt_labels[gi];
 
 #ifdef PAA_PROFILE_GMM
-        const long long prof_t0 = clock64();
+    const long long prof_t0 = clock64();
 #endif
-        if (cls_label > 0) {        // loss.py:166 requires a positive IoU label
-            for (int l = 0; l < geo.num_levels; ++l) {
-                const LevelView& lv = geo.lv[l];
-                const int t_end = (l + 1 < geo.num_levels) ? geo.lv[l + 1].tile_off : geo.tiles_per_image;
-                unsigned long long mine = kEmptyKey;   // lane j < K holds the j-th smallest key so far
-                const int seg = gi * geo.num_levels + l;
-                const int seg_n = __ldg(seg_count + seg);
-                if (seg_n <= sc.seg_cap) {
-                    // normal case: the anchors matched to this (GT, level) were pooled by match_score_kernel
-                    const unsigned long long* pool = seg_pool + (size_t)seg * kSegCap;
-                    for (int j0 = 0; j0 < seg_n; j0 += 4 * PAA_WARP) {
-                        unsigned long long k4[4];
+    // ---- phase 1: warp l = level l (loss.py:160-172) ------------------------------------------------
+    {
+        const int l = warp;
+        unsigned long long mine = kEmptyKey;   // lane j < K holds the j-th smallest key so far
+        if (cls_label > 0) {                   // loss.py:166 requires a positive IoU label
+            const LevelView& lv = geo.lv[l];
+            const int seg = gi * geo.num_levels + l;
+            const int seg_n = __ldg(seg_count + seg);
+            if (seg_n <= sc.seg_cap) {
+                // normal case: the anchors matched to this (GT, level) were pooled by match_score_kernel
+                const unsigned long long* pool = seg_pool + (size_t)seg * kSegCap;
+                unsigned long long k4[4];
 #pragma unroll
-                        for (int r = 0; r < 4; ++r) {
-                            const int j = j0 + r * PAA_WARP + lane;
-                            k4[r] = (j < seg_n) ? __ldg(pool + j) : kEmptyKey;
-                        }
+                for (int r = 0; r < 4; ++r) {
+                    const int j = r * PAA_WARP + lane;
+                    k4[r] = (j < seg_n) ? __ldg(pool + j) : kEmptyKey;
+                }
+                if (seg_n > 0) mine = topk_first_batch(k4[0], K, lane, s_level[l]);
 #pragma unroll
-                        for (int r = 0; r < 4; ++r)
-                            if (j0 + r * PAA_WARP < seg_n) topk_offer(mine, k4[r], k4[r] != kEmptyKey, K, lane);
+                for (int r = 1; r < 4; ++r)
+                    if (r * PAA_WARP < seg_n) topk_offer(mine, k4[r], k4[r] != kEmptyKey, K, lane);
+                for (int j0 = 4 * PAA_WARP; j0 < seg_n; j0 += 4 * PAA_WARP) {
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const int j = j0 + r * PAA_WARP + lane;
+                        k4[r] = (j < seg_n) ? __ldg(pool + j) : kEmptyKey;
                     }
-                } else
+#pragma unroll
+                    for (int r = 0; r < 4; ++r)
+                        if (j0 + r * PAA_WARP < seg_n) topk_offer(mine, k4[r], k4[r] != kEmptyKey, K, lane);
+                }
+            } else {
                 // overflowed pool: search the tiles of this level that contain anchors of this GT
+                const unsigned gbit = 1u << (g_local & 31);
+                const int gword = (g_local & 127) >> 5;
+                const int* mrow = matched + (size_t)n * geo.A;
+                const float* srow = score + (size_t)n * geo.A;
+                const int t_end = (l + 1 < geo.num_levels) ? geo.lv[l + 1].tile_off : geo.tiles_per_image;
                 for (int t0 = lv.tile_off; t0 < t_end; t0 += PAA_WARP) {
                     const int t = t0 + lane;
                     bool hit = false;
@@ -564,94 +733,102 @@ select_gmm_kernel(const Geometry geo, const GtOffsets go, int num_gt_total,
 #pragma unroll
                         for (int r = 0; r < PAA_TILE / PAA_WARP; ++r) {
                             const int i = base + r * PAA_WARP + lane;
-                            bool is = (mv[r] == g_local);
+                            const bool is = (mv[r] == g_local);
                             unsigned long long key = kEmptyKey;
                             if (is) key = ((unsigned long long)ordered_bits(sv[r]) << 32) | (unsigned)(lv.a_off + i);
                             topk_offer(mine, key, is, K, lane);
                         }
                     }
                 }
-                // append this level's candidates (ascending key) to the warp's list
-                const unsigned have = __ballot_sync(PAA_FULL, lane < K && mine != kEmptyKey);
-                const int cnt = __popc(have);
-                if (lane < cnt) keys[n_cand + lane] = mine;
-                n_cand += cnt;
             }
         }
-        __syncwarp();
+        const unsigned have = __ballot_sync(PAA_FULL, lane < K && mine != kEmptyKey);
+        if (lane < K) s_level[l][lane] = mine;
+        if (lane == 0) s_cnt[l] = __popc(have);
+    }
+    __syncthreads();
+    if (warp != 0) return;
 
-        // sort all candidates by (loss, index): rank by counting, n_cand <= cap <= 128
-        unsigned long long* sorted = s_sorted[warp];
-        for (int j = lane; j < n_cand; j += PAA_WARP) {
-            const unsigned long long kj = keys[j];
-            int rank = 0;
-            for (int q = 0; q < n_cand; ++q) rank += (keys[q] < kj) ? 1 : 0;
-            sorted[rank] = kj;
-        }
-        __syncwarp();
+    // ---- phase 2 (warp 0): concatenate the levels, sort, fit, label --------------------------------
+    int n_cand = 0;
+    for (int l = 0; l < geo.num_levels; ++l) {
+        const int cnt = s_cnt[l];
+        if (lane < cnt) s_key[n_cand + lane] = s_level[l][lane];
+        n_cand += cnt;
+    }
+    __syncwarp();
+    // sort all candidates by (loss, index): rank by counting, n_cand <= cap <= 128
+    for (int j = lane; j < n_cand; j += PAA_WARP) {
+        const unsigned long long kj = s_key[j];
+        int rank = 0;
+        for (int q = 0; q < n_cand; ++q) rank += (s_key[q] < kj) ? 1 : 0;
+        s_sorted[rank] = kj;
+    }
+    __syncwarp();
 
 #ifdef PAA_PROFILE_GMM
-        const long long prof_t1 = clock64();
+    const long long prof_t1 = clock64();
 #endif
-        if (n_cand == 1) {
-            n_pos = 1;                                     // loss.py:218-219
-        } else if (n_cand > 1) {
-            float x[SPL];
+    int n_pos = 0;
+    if (n_cand == 1) {
+        n_pos = 1;                                     // loss.py:218-219
+    } else if (n_cand > 1) {
+        float x[SPL];
 #pragma unroll
-            for (int k = 0; k < SPL; ++k) {
-                const int j = lane + 32 * k;
-                x[k] = (j < n_cand) ? from_ordered_bits((unsigned)(sorted[j] >> 32)) : 0.f;
-            }
-            n_pos = gmm_positive_prefix<SPL>(x, n_cand, lane, dbg.gmm ? dbg.gmm + (size_t)gi * 8 : nullptr);
+        for (int k = 0; k < SPL; ++k) {
+            const int j = lane + 32 * k;
+            x[k] = (j < n_cand) ? from_ordered_bits((unsigned)(s_sorted[j] >> 32)) : 0.f;
         }
-        if (dbg.gmm && n_cand <= 1 && lane < 8) dbg.gmm[(size_t)gi * 8 + lane] = 0.0;
+        n_pos = gmm_positive_prefix<SPL>(x, n_cand, lane, dbg.gmm ? dbg.gmm + (size_t)gi * 8 : nullptr);
+    }
+    if (dbg.gmm && n_cand <= 1 && lane < 8) dbg.gmm[(size_t)gi * 8 + lane] = 0.0;
 #ifdef PAA_PROFILE_GMM        // measurement build only: cycles of scan+sort / EM in the w0 / w1 debug slots
-        if (dbg.gmm && lane == 0) {
-            dbg.gmm[(size_t)gi * 8 + 0] = (double)(prof_t1 - prof_t0);
-            dbg.gmm[(size_t)gi * 8 + 1] = (double)(clock64() - prof_t1);
-        }
+    if (dbg.gmm && lane == 0) {
+        dbg.gmm[(size_t)gi * 8 + 0] = (double)(prof_t1 - prof_t0);
+        dbg.gmm[(size_t)gi * 8 + 1] = (double)(clock64() - prof_t1);
+    }
 #endif
 
-        // labels of the positive prefix + this GT's share of the IoU normaliser (loss.py:228-230,331-333)
-        for (int j = lane; j < n_cand; j += PAA_WARP) {
-            const int aidx = (int)(sorted[j] & 0xffffffffu);
-            if (dbg.cand_idx) dbg.cand_idx[(size_t)gi * cap + j] = aidx;
-            if (j < n_pos) {
-                paa_label[(size_t)n * geo.A + aidx] = cls_label;
-                if (dbg.paa_labels) dbg.paa_labels[(size_t)n * geo.A + aidx] = cls_label;
-                if (sc.use_iou_pred) {
-                    const int l = anchor_level(geo, aidx);
-                    const LevelView& lv = geo.lv[l];
-                    const int i = aidx - lv.a_off;
-                    const float4 a = ldg4(lv.anchors + (size_t)n * geo.anchor_image_stride + (size_t)i * 4);
-                    const AnchorFrame f = anchor_frame(a);
-                    const float* rp = lv.reg + head_offset(n, i, 0, 4, geo.apl, lv.hw);
-                    const float4 d = make_float4(__ldg(rp), __ldg(rp + lv.hw), __ldg(rp + 2 * (size_t)lv.hw),
-                                                 __ldg(rp + 3 * (size_t)lv.hw));
-                    const float4 pred = decode_box(d, f);
-                    const float4 tgt = decode_box(encode_box(gt, f), f);
-                    siou += (double)iou_plus1(tgt, area_plus1(tgt), pred, area_plus1(pred));
-                }
+    // labels of the positive prefix + this GT's share of the IoU normaliser (loss.py:228-230,331-333)
+    double siou = 0.0;
+    const float4 gt = ldg4(gt_boxes + (size_t)gi * 4);
+    for (int j = lane; j < n_cand; j += PAA_WARP) {
+        const int aidx = (int)(s_sorted[j] & 0xffffffffu);
+        if (dbg.cand_idx) dbg.cand_idx[(size_t)gi * cap + j] = aidx;
+        if (j < n_pos) {
+            paa_label[(size_t)n * geo.A + aidx] = cls_label;
+            if (dbg.paa_labels) dbg.paa_labels[(size_t)n * geo.A + aidx] = cls_label;
+            if (sc.use_iou_pred) {
+                const int l = anchor_level(geo, aidx);
+                const LevelView& lv = geo.lv[l];
+                const int i = aidx - lv.a_off;
+                const float4 a = ldg4(lv.anchors + (size_t)n * geo.anchor_image_stride + (size_t)i * 4);
+                const AnchorFrame f = anchor_frame(a);
+                const float* rp = lv.reg + head_offset(n, i, 0, 4, geo.apl, lv.hw);
+                const float4 d = make_float4(__ldg(rp), __ldg(rp + lv.hw), __ldg(rp + 2 * (size_t)lv.hw),
+                                             __ldg(rp + 3 * (size_t)lv.hw));
+                const float4 pred = decode_box(d, f);
+                const float4 tgt = decode_box(encode_box(gt, f), f);
+                siou += (double)iou_plus1(tgt, area_plus1(tgt), pred, area_plus1(pred));
             }
-        }
-        siou = warp_sum(siou);
-        if (lane == 0) {
-            part_npos[gi] = n_pos;
-            part_siou[gi] = siou;
-            if (dbg.cand_cnt) dbg.cand_cnt[gi] = n_cand;
-            if (dbg.num_pos) dbg.num_pos[gi] = n_pos;
         }
     }
+    siou = warp_sum(siou);
+    if (lane == 0) {
+        part_npos[gi] = n_pos;
+        part_siou[gi] = siou;
+        if (dbg.cand_cnt) dbg.cand_cnt[gi] = n_cand;
+        if (dbg.num_pos) dbg.num_pos[gi] = n_pos;
+    }
 
-    // the last warp to finish folds the per-GT partials in a fixed order (deterministic sums)
-    const unsigned total_warps = gridDim.x * kSelWarps;
+    // the last block to finish folds the per-GT partials in a fixed order (deterministic sums)
     unsigned my_ticket = 0;
     if (lane == 0) {
         __threadfence();
         my_ticket = atomicAdd(&ticket[0], 1u);
     }
     my_ticket = __shfl_sync(PAA_FULL, my_ticket, 0);
-    if (my_ticket == total_warps - 1) {
+    if (my_ticket == gridDim.x - 1) {
         __threadfence();
         double cnt = 0.0, sum = 0.0;
         for (int g = lane; g < num_gt_total; g += PAA_WARP) {
@@ -674,8 +851,8 @@ int launch_select_gmm(const Geometry& geo, const GtOffsets& go, int num_gt_total
                       const float* score_src, double* normalisers, const LossDebug& dbg,
                       cudaStream_t stream) {
     const int cap = geo.num_levels * sc.topk;
-    const int grid = (num_gt_total + kSelWarps - 1) / kSelWarps;
-    const int threads = kSelWarps * PAA_WARP;
+    const int grid = num_gt_total;
+    const int threads = geo.num_levels * PAA_WARP;
     KernelTimer timer(PAA_KERNEL_SELECT_GMM, stream);
 #define PAA_SEL_LAUNCH(SPL)                                                                           \
     select_gmm_kernel<SPL><<<grid, threads, 0, stream>>>(geo, go, num_gt_total, gt_boxes, gt_labels, sc, \

@@ -23,8 +23,8 @@ struct LossDebug {
 };
 
 // assign.cu
-int launch_iou_best(const Geometry& geo, const GtOffsets& go, const float* gt_boxes,
-                    const LossWorkspace& ws, cudaStream_t stream);
+int launch_assign_pass1(const Geometry& geo, const GtOffsets& go, const float* gt_boxes, const LossScalars& sc,
+                        const LossWorkspace& ws, cudaStream_t stream);
 int launch_match_score(const Geometry& geo, const GtOffsets& go, const float* gt_boxes,
                        const int64_t* gt_labels, const LossScalars& sc, const LossWorkspace& ws,
                        const float* teacher_score, const LossDebug& dbg, cudaStream_t stream);

@@ -21,6 +21,7 @@ struct LossWorkspace {
     uint2* best;            // [N*A]    (IoU bits, GT index) of every anchor's best GT
     int* matched;           // [N*A]
     float* score;           // [N*A]    anchor score (combined loss) of IoU-positive anchors
+    float* negsum;          // [N*A]    sum over classes of every logit's negative-class focal term (no (1-alpha))
     int* paa_label;         // [N*A]
     uint4* tile_gtmask;     // [N*T]    bit (g mod 128): GT g has a matched anchor in the tile
     int* part_npos;         // [sumG]
@@ -54,6 +55,7 @@ inline LossWorkspace carve_loss_workspace(void* base, int N, int A, int sumG, in
     w.best = reinterpret_cast<uint2*>(take(sizeof(uint2) * NA));
     w.matched = reinterpret_cast<int*>(take(sizeof(int) * NA));
     w.score = reinterpret_cast<float*>(take(sizeof(float) * NA));
+    w.negsum = reinterpret_cast<float*>(take(sizeof(float) * NA));
     w.paa_label = reinterpret_cast<int*>(take(sizeof(int) * NA));
     w.tile_gtmask = reinterpret_cast<uint4*>(take(sizeof(uint4) * (size_t)N * tiles_per_image));
     w.part_npos = reinterpret_cast<int*>(take(sizeof(int) * (size_t)(sumG > 0 ? sumG : 1)));

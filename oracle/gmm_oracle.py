@@ -148,6 +148,18 @@ def positive_prefix_length(fit):
     return int(np.nonzero(fg & (score == best))[0].min()) + 1
 
 
+def component_margin(fit, x):
+    """Smallest |a_0 - a_1| over the samples, a_k the weighted log-probabilities of the fitted components
+    (float64, from the fitted parameters).  A value near 0 means `predict` (argmax, loss.py:202,206) is
+    decided by rounding noise for that sample -- e.g. two candidates whose components collapse onto the
+    same mean.  Tests exempt such a GT from mask-exactness (exemption (ii-b))."""
+    x = np.asarray(x, np.float64).reshape(-1)
+    w, mu, var = (np.asarray(fit[k], np.float64).reshape(2) for k in ("weights", "means", "variances"))
+    a = [-0.5 * (np.log(2.0 * np.pi) + (x - mu[k]) ** 2 / var[k]) - 0.5 * np.log(var[k]) + np.log(w[k])
+         for k in (0, 1)]
+    return float(np.min(np.abs(a[0] - a[1])))
+
+
 def structural_tie_margin(fit):
     """Gap between the two best foreground scores (inf if fewer than two foreground samples).
     Tests exempt a GT from mask-exactness when this is below 1e-5 (exemption (ii))."""

@@ -381,7 +381,12 @@ match_score_kernel(const Geometry geo, const GtOffsets go, const float* __restri
         // contiguous list instead of searching the image for its anchors
         const float key_score = teacher_score ? teacher_score[flat] : s;
         const int seg = (gbase + m) * geo.num_levels + l;
-        const int slot = atomicAdd(&seg_count[seg], 1);
+        // consecutive anchors mostly share their GT: one atomic per (warp, segment) instead of one per anchor
+        const unsigned peers = __match_any_sync(__activemask(), seg);
+        const int leader = __ffs(peers) - 1, lane_id = threadIdx.x & 31;
+        int slot = 0;
+        if (lane_id == leader) slot = atomicAdd(&seg_count[seg], __popc(peers));
+        slot = __shfl_sync(peers, slot, leader) + __popc(peers & ((1u << lane_id) - 1u));
         if (slot < sc.seg_cap)
             seg_pool[(size_t)seg * kSegCap + slot] =
                 ((unsigned long long)ordered_bits(key_score) << 32) | (unsigned)(lv.a_off + i);
@@ -415,9 +420,10 @@ __device__ __forceinline__ double logsumexp2(double a0, double a1) {
     return (log1p(exp(lo - hi)) + 0.0) + hi;                          // m = 1, log(m) = 0
 }
 
-// Mixture parameters as every lane holds them between iterations.  lw = log(w), ld = float32(log(pc)).
+// Mixture parameters as every lane holds them between iterations: mpc = mu * pc, lw = log(w),
+// ld = float32(log(pc)).
 struct GmmState {
-    double mu0, mu1, lw0, lw1;
+    double mu0, mu1, mpc0, mpc1, lw0, lw1;
     float pc0, pc1, ld0, ld1;
 };
 
@@ -427,8 +433,8 @@ struct GmmState {
 // The initial float64 precisions (1.0) need no special case: x * 1.0f and lp + 0.0f are exact.
 __device__ __forceinline__ void weighted_log_prob(float x, const GmmState& s, double* a0, double* a1) {
     const float LOG2PI = 1.8378770664093453f;
-    const double y0 = (double)__fmul_rn(x, s.pc0) - s.mu0 * (double)s.pc0;
-    const double y1 = (double)__fmul_rn(x, s.pc1) - s.mu1 * (double)s.pc1;
+    const double y0 = (double)__fmul_rn(x, s.pc0) - s.mpc0;
+    const double y1 = (double)__fmul_rn(x, s.pc1) - s.mpc1;
     const float q0 = __double2float_rn(y0 * y0);
     const float q1 = __double2float_rn(y1 * y1);
     const float lp0 = __fmul_rn(-0.5f, __fadd_rn(LOG2PI, q0));
@@ -443,11 +449,38 @@ __device__ __forceinline__ double warp_prod(double v) {
     return v;
 }
 
+// Sums seven per-lane quantities over the warp with 9 + 7 64-bit shuffles instead of 35: each of the
+// first three butterfly rounds halves the number of quantities a lane still carries (it keeps the half
+// selected by its lane bit and hands the other half to its partner), two more rounds finish the one
+// quantity left, and the totals are broadcast from the lanes that own them (quantity q: lanes 4q..4q+3).
+// v[7] is a padding slot.
+__device__ __forceinline__ void warp_sum7(double (&v)[8], int lane) {
+    const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0, b2 = (lane & 4) != 0;
+    double w[4], x[2];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const double send = b4 ? v[j] : v[4 + j], keep = b4 ? v[4 + j] : v[j];
+        w[j] = keep + __shfl_xor_sync(PAA_FULL, send, 16);
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const double send = b3 ? w[j] : w[2 + j], keep = b3 ? w[2 + j] : w[j];
+        x[j] = keep + __shfl_xor_sync(PAA_FULL, send, 8);
+    }
+    const double send = b2 ? x[0] : x[1], keep = b2 ? x[1] : x[0];
+    double y = keep + __shfl_xor_sync(PAA_FULL, send, 4);
+    y += __shfl_xor_sync(PAA_FULL, y, 2);
+    y += __shfl_xor_sync(PAA_FULL, y, 1);
+#pragma unroll
+    for (int q = 0; q < 7; ++q) v[q] = __shfl_sync(PAA_FULL, y, 4 * q);
+}
+
 // Fits the mixture on the warp's n sorted samples (lane holds x[lane + 32*k]) and returns the length
 // of the positive prefix (loss.py:206-217).  out8 (nullable, lane 0 writes) receives the parameters.
 //
-// The fit is a serial chain of float64 operations with nothing to overlap it with, so an iteration is
-// organised for the shortest chain and the fewest issued instructions:
+// The fit is a serial chain of float64 operations with nothing to overlap it with (measured on B200:
+// DFMA 8 cycles, 64-bit shuffle 24, IEEE float32 sqrt / div ~60 each), so an iteration is organised for
+// the shortest chain and the fewest issued instructions:
 //  * E-step, one sample per lane: s = exp(lo - hi), responsibilities 1/(1+s) and s/(1+s) (one exp and one
 //    reciprocal instead of sklearn's three exps; they differ from exp(a_k - lse) by a few 1e-16, far
 //    below what the float32 roundings of the next E-step can see).
@@ -455,13 +488,17 @@ __device__ __forceinline__ double warp_prod(double v) {
 //    per iteration instead of one log1p per sample (the product of <= 128 factors in [1, 2] is exact to
 //    ~1e-14 relative, the rule compares against 1e-3).
 //  * One reduction round: moments are taken about the PREVIOUS means (p0, p1), from which the new mean and
-//    the variance about the new mean follow exactly:
-//        sum r x = A + p S,   sum r (x - mu)^2 = B - 2 d A + d^2 S   with d = mu - p.
+//    the variance about the new mean follow exactly: with d = mu - p = (A - p eps) / nk,
+//        mu = p + d,   sum r (x - mu)^2 = B - 2 d A + d^2 S.
 //    (sklearn evaluates sum r (x - mu)^2 directly; the two agree to ~1e-14 relative, far below the
 //    float32 rounding of the variance that follows.)
-//  * M-step in lanes: even lanes update component 0 and odd lanes component 1 with one instruction stream,
-//    and the iteration's five logarithms (log pc_k in lanes 0-1, log w_k in lanes 2-3, log prod in lane 4)
-//    are one call.
+//  * The iteration's five logarithms are one call: log var_k in lanes 0-1, log w_k in lanes 2-3,
+//    log prod in lane 4.  float32(log pc_k) is recovered from log var_k, which is known 120 cycles before
+//    pc_k = 1 / sqrt(var_k) has gone through its two IEEE float32 roundings:
+//        log pc = -log(var)/2 + log1p(e)/2,   e = pc^2 var - 1  (|e| <= 2^-22, one exact fma).
+//  * The loop is rotated: the next E-step's log-probabilities are issued before the branch on the
+//    stopping rule, so the rule's own chain (log prod -> mean -> difference) is off the critical path; on
+//    exit they are exactly the final E-step's.
 template <int SPL>
 __device__ int gmm_positive_prefix(const float (&x)[SPL], int n, int lane, double* out8) {
     GmmState s;
@@ -477,94 +514,101 @@ __device__ int gmm_positive_prefix(const float (&x)[SPL], int n, int lane, doubl
         }
         s.mu1 = (double)xl;                                               // max
     }
+    s.mpc0 = s.mu0;
+    s.mpc1 = s.mu1;
     s.pc0 = s.pc1 = 1.0f;
     s.ld0 = s.ld1 = 0.0f;
-    double w_mine = 0.5;            // lane-parity copies of the last M-step, for the debug output only
-    float var_mine = 1.0f;
+    double w0 = 0.5, w1 = 0.5;      // last M-step's weights / variances, for the debug output only
+    float var0 = 1.0f, var1 = 1.0f;
     double lower = -INFINITY;
     int n_iter = 0;
     bool converged = false;
     const double EPS10 = 10.0 * 2.220446049250313e-16;
     const double inv_n = 1.0 / (double)n;
-    const bool odd = (lane & 1) != 0;
-    for (int it = 1; it <= 100; ++it) {
-        n_iter = it;
+    double a0[SPL], a1[SPL];
+    for (;;) {
+#pragma unroll
+        for (int k = 0; k < SPL; ++k) weighted_log_prob(x[k], s, &a0[k], &a1[k]);
+        if (converged || n_iter == 100) break;
+        ++n_iter;
         const double p0 = s.mu0, p1 = s.mu1;
-        double S0 = 0, S1 = 0, A0 = 0, A1 = 0, B0 = 0, B1 = 0, H = 0, P = 1.0;
+        double v[8];          // S0 S1 A0 A1 B0 B1 H pad
+        double P = 1.0;
 #pragma unroll
         for (int k = 0; k < SPL; ++k) {
-            if (lane + 32 * k < n) {
-                double a0, a1;
-                weighted_log_prob(x[k], s, &a0, &a1);
-                const bool first_hi = a0 >= a1;
-                const double hi = first_hi ? a0 : a1, lo = first_hi ? a1 : a0;
-                const double sx = exp_nonpos(lo - hi);
-                const double u = 1.0 + sx;
-                const double rh = rcp_fast(u), rl = sx * rh;
-                const double r0 = first_hi ? rh : rl, r1 = first_hi ? rl : rh;
-                H += hi;
-                P *= u;
-                const double e0 = (double)x[k] - p0, e1 = (double)x[k] - p1;
-                const double t0 = r0 * e0, t1 = r1 * e1;
-                S0 += r0;
-                S1 += r1;
-                A0 += t0;
-                A1 += t1;
-                B0 = fma(t0, e0, B0);
-                B1 = fma(t1, e1, B1);
+            if (k > 0 && n <= 32 * k) break;                  // warp-uniform
+            const bool first_hi = a0[k] >= a1[k];
+            const double hi = first_hi ? a0[k] : a1[k], lo = first_hi ? a1[k] : a0[k];
+            const double sx = exp_nonpos(lo - hi);
+            const double u = 1.0 + sx;
+            const double rh = rcp_fast(u), rl = sx * rh;
+            const bool valid = lane + 32 * k < n;
+            const double r0 = valid ? (first_hi ? rh : rl) : 0.0;
+            const double r1 = valid ? (first_hi ? rl : rh) : 0.0;
+            const double e0 = (double)x[k] - p0, e1 = (double)x[k] - p1;
+            const double t0 = r0 * e0, t1 = r1 * e1;
+            if (k == 0) {
+                v[0] = r0;
+                v[1] = r1;
+                v[2] = t0;
+                v[3] = t1;
+                v[4] = t0 * e0;
+                v[5] = t1 * e1;
+                v[6] = valid ? hi : 0.0;
+                P = valid ? u : 1.0;
+            } else {
+                v[0] += r0;
+                v[1] += r1;
+                v[2] += t0;
+                v[3] += t1;
+                v[4] = fma(t0, e0, v[4]);
+                v[5] = fma(t1, e1, v[5]);
+                v[6] += valid ? hi : 0.0;
+                P *= valid ? u : 1.0;
             }
         }
-        S0 = warp_sum(S0);
-        S1 = warp_sum(S1);
-        A0 = warp_sum(A0);
-        A1 = warp_sum(A1);
-        B0 = warp_sum(B0);
-        B1 = warp_sum(B1);
-        H = warp_sum(H);
+        v[7] = 0.0;
         P = warp_prod(P);
-        // M-step of this lane's component
-        const double S = odd ? S1 : S0, A = odd ? A1 : A0, B = odd ? B1 : B0, p = odd ? p1 : p0;
-        const double nk = S + EPS10;
-        const double nsum = (S0 + EPS10) + (S1 + EPS10);
-        const double rn = rcp_fast(nk);
-        const double num = fma(p, S, A);
-        double mu = num * rn;
-        mu = fma(fma(-nk, mu, num), rn, mu);
-        const double d = mu - p;
-        const double c = fma(d, fma(d, S, -2.0 * A), B);
-        const float var = __fadd_rn(__double2float_rn(fmax(c, 0.0) * rn), 1e-6f);
-        const float pc = __fdiv_rn(1.0f, __fsqrt_rn(var));
-        const double w = nk * rcp_fast(nsum);
-        const double lg = log_pos(lane < 2 ? (double)pc : (lane < 4 ? w : P));
-        s.mu0 = __shfl_sync(PAA_FULL, mu, 0);
-        s.mu1 = __shfl_sync(PAA_FULL, mu, 1);
-        s.pc0 = __shfl_sync(PAA_FULL, pc, 0);
-        s.pc1 = __shfl_sync(PAA_FULL, pc, 1);
-        s.ld0 = __double2float_rn(__shfl_sync(PAA_FULL, lg, 0));
-        s.ld1 = __double2float_rn(__shfl_sync(PAA_FULL, lg, 1));
+        warp_sum7(v, lane);
+        // M-step, both components in every lane (two independent chains fill each other's latency)
+        const double nk0 = v[0] + EPS10, nk1 = v[1] + EPS10;
+        const double rn0 = rcp_fast(nk0), rn1 = rcp_fast(nk1), rs = rcp_fast(nk0 + nk1);
+        const double d0 = fma(-p0, EPS10, v[2]) * rn0, d1 = fma(-p1, EPS10, v[3]) * rn1;
+        const double c0 = fma(d0, fma(d0, v[0], -2.0 * v[2]), v[4]);
+        const double c1 = fma(d1, fma(d1, v[1], -2.0 * v[3]), v[5]);
+        var0 = __fadd_rn(__double2float_rn(fmax(c0, 0.0) * rn0), 1e-6f);
+        var1 = __fadd_rn(__double2float_rn(fmax(c1, 0.0) * rn1), 1e-6f);
+        w0 = nk0 * rs;
+        w1 = nk1 * rs;
+        const double arg = lane == 0 ? (double)var0
+                                     : (lane == 1 ? (double)var1 : (lane == 2 ? w0 : (lane == 3 ? w1 : P)));
+        const double lg = log_pos(arg);
+        s.mu0 = p0 + d0;
+        s.mu1 = p1 + d1;
+        s.pc0 = __fdiv_rn(1.0f, __fsqrt_rn(var0));
+        s.pc1 = __fdiv_rn(1.0f, __fsqrt_rn(var1));
+        const double pd0 = (double)s.pc0, pd1 = (double)s.pc1;
+        s.mpc0 = s.mu0 * pd0;
+        s.mpc1 = s.mu1 * pd1;
+        const double e0 = fma(pd0 * pd0, (double)var0, -1.0), e1 = fma(pd1 * pd1, (double)var1, -1.0);
+        const double h0 = (0.5 * e0) * fma(-0.5, e0, 1.0), h1 = (0.5 * e1) * fma(-0.5, e1, 1.0);
+        s.ld0 = __double2float_rn(fma(-0.5, __shfl_sync(PAA_FULL, lg, 0), h0));
+        s.ld1 = __double2float_rn(fma(-0.5, __shfl_sync(PAA_FULL, lg, 1), h1));
         s.lw0 = __shfl_sync(PAA_FULL, lg, 2);
         s.lw1 = __shfl_sync(PAA_FULL, lg, 3);
-        const double lb = (H + __shfl_sync(PAA_FULL, lg, 4)) * inv_n;
-        w_mine = w;
-        var_mine = var;
-        const double change = lb - lower;
+        const double lb = (v[6] + __shfl_sync(PAA_FULL, lg, 4)) * inv_n;
+        converged = fabs(lb - lower) < 1e-3;
         lower = lb;
-        if (fabs(change) < 1e-3) {
-            converged = true;
-            break;
-        }
     }
-    // final E-step: predict (argmax, ties -> 0) and score_samples
+    // a0 / a1 are the final E-step: predict (argmax, ties -> 0) and score_samples
     double best_score = -INFINITY;
     int best_idx = 0x7fffffff;
     bool any_fg = false;
 #pragma unroll
     for (int k = 0; k < SPL; ++k) {
         if (lane + 32 * k < n) {
-            double a0, a1;
-            weighted_log_prob(x[k], s, &a0, &a1);
-            if (!(a1 > a0)) {                 // component 0 == foreground (loss.py:206)
-                const double sc = logsumexp2(a0, a1);
+            if (!(a1[k] > a0[k])) {           // component 0 == foreground (loss.py:206)
+                const double sc = logsumexp2(a0[k], a1[k]);
                 any_fg = true;
                 if (sc > best_score) {        // k ascending => first index among equals kept
                     best_score = sc;
@@ -584,19 +628,15 @@ __device__ int gmm_positive_prefix(const float (&x)[SPL], int n, int lane, doubl
         }
     }
     any_fg = __any_sync(PAA_FULL, any_fg);
-    if (out8) {
-        const double w1 = __shfl_sync(PAA_FULL, w_mine, 1);
-        const float v1 = __shfl_sync(PAA_FULL, var_mine, 1);
-        if (lane == 0) {
-            out8[0] = w_mine;
-            out8[1] = w1;
-            out8[2] = s.mu0;
-            out8[3] = s.mu1;
-            out8[4] = (double)var_mine;
-            out8[5] = (double)v1;
-            out8[6] = (double)n_iter;
-            out8[7] = converged ? 1.0 : 0.0;
-        }
+    if (out8 && lane == 0) {
+        out8[0] = w0;
+        out8[1] = w1;
+        out8[2] = s.mu0;
+        out8[3] = s.mu1;
+        out8[4] = (double)var0;
+        out8[5] = (double)var1;
+        out8[6] = (double)n_iter;
+        out8[7] = converged ? 1.0 : 0.0;
     }
     return any_fg ? best_idx + 1 : n;
 }
@@ -641,7 +681,8 @@ __device__ __forceinline__ unsigned long long topk_first_batch(unsigned long lon
 }
 
 template <int SPL>
-__global__ void __launch_bounds__(PAA_MAX_LEVELS * PAA_WARP)
+// (64 registers: with the usual five levels six blocks fit an SM, so ~900 GTs are one wave)
+__global__ void __launch_bounds__(PAA_MAX_LEVELS * PAA_WARP, 4)
 select_gmm_kernel(const Geometry geo, const GtOffsets go, int num_gt_total,
                   const float* __restrict__ gt_boxes, const int64_t* __restrict__ gt_labels,
                   const LossScalars sc, const uint4* __restrict__ tile_gtmask,
@@ -769,16 +810,38 @@ select_gmm_kernel(const Geometry geo, const GtOffsets go, int num_gt_total,
 #ifdef PAA_PROFILE_GMM
     const long long prof_t1 = clock64();
 #endif
+    // this lane's candidates (sorted order), with the anchors and regression outputs the IoU normaliser
+    // will need: the loads are issued before the fit and consumed after it
+    int aidx[SPL];
+    float x[SPL];
+    float4 pa[SPL], pd[SPL];
+    const float4 gt = ldg4(gt_boxes + (size_t)gi * 4);
+#pragma unroll
+    for (int k = 0; k < SPL; ++k) {
+        const int j = lane + 32 * k;
+        aidx[k] = -1;
+        x[k] = 0.f;
+        pa[k] = make_float4(0.f, 0.f, 1.f, 1.f);
+        pd[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (j < n_cand) {
+            const unsigned long long key = s_sorted[j];
+            aidx[k] = (int)(key & 0xffffffffu);
+            x[k] = from_ordered_bits((unsigned)(key >> 32));
+            if (sc.use_iou_pred) {
+                const int l = anchor_level(geo, aidx[k]);
+                const LevelView& lv = geo.lv[l];
+                const int i = aidx[k] - lv.a_off;
+                pa[k] = ldg4(lv.anchors + (size_t)n * geo.anchor_image_stride + (size_t)i * 4);
+                const float* rp = lv.reg + head_offset(n, i, 0, 4, geo.apl, lv.hw);
+                pd[k] = make_float4(__ldg(rp), __ldg(rp + lv.hw), __ldg(rp + 2 * (size_t)lv.hw),
+                                    __ldg(rp + 3 * (size_t)lv.hw));
+            }
+        }
+    }
     int n_pos = 0;
     if (n_cand == 1) {
         n_pos = 1;                                     // loss.py:218-219
     } else if (n_cand > 1) {
-        float x[SPL];
-#pragma unroll
-        for (int k = 0; k < SPL; ++k) {
-            const int j = lane + 32 * k;
-            x[k] = (j < n_cand) ? from_ordered_bits((unsigned)(s_sorted[j] >> 32)) : 0.f;
-        }
         n_pos = gmm_positive_prefix<SPL>(x, n_cand, lane, dbg.gmm ? dbg.gmm + (size_t)gi * 8 : nullptr);
     }
     if (dbg.gmm && n_cand <= 1 && lane < 8) dbg.gmm[(size_t)gi * 8 + lane] = 0.0;
@@ -791,25 +854,20 @@ select_gmm_kernel(const Geometry geo, const GtOffsets go, int num_gt_total,
 
     // labels of the positive prefix + this GT's share of the IoU normaliser (loss.py:228-230,331-333)
     double siou = 0.0;
-    const float4 gt = ldg4(gt_boxes + (size_t)gi * 4);
-    for (int j = lane; j < n_cand; j += PAA_WARP) {
-        const int aidx = (int)(s_sorted[j] & 0xffffffffu);
-        if (dbg.cand_idx) dbg.cand_idx[(size_t)gi * cap + j] = aidx;
-        if (j < n_pos) {
-            paa_label[(size_t)n * geo.A + aidx] = cls_label;
-            if (dbg.paa_labels) dbg.paa_labels[(size_t)n * geo.A + aidx] = cls_label;
-            if (sc.use_iou_pred) {
-                const int l = anchor_level(geo, aidx);
-                const LevelView& lv = geo.lv[l];
-                const int i = aidx - lv.a_off;
-                const float4 a = ldg4(lv.anchors + (size_t)n * geo.anchor_image_stride + (size_t)i * 4);
-                const AnchorFrame f = anchor_frame(a);
-                const float* rp = lv.reg + head_offset(n, i, 0, 4, geo.apl, lv.hw);
-                const float4 d = make_float4(__ldg(rp), __ldg(rp + lv.hw), __ldg(rp + 2 * (size_t)lv.hw),
-                                             __ldg(rp + 3 * (size_t)lv.hw));
-                const float4 pred = decode_box(d, f);
-                const float4 tgt = decode_box(encode_box(gt, f), f);
-                siou += (double)iou_plus1(tgt, area_plus1(tgt), pred, area_plus1(pred));
+#pragma unroll
+    for (int k = 0; k < SPL; ++k) {
+        const int j = lane + 32 * k;
+        if (j < n_cand) {
+            if (dbg.cand_idx) dbg.cand_idx[(size_t)gi * cap + j] = aidx[k];
+            if (j < n_pos) {
+                paa_label[(size_t)n * geo.A + aidx[k]] = cls_label;
+                if (dbg.paa_labels) dbg.paa_labels[(size_t)n * geo.A + aidx[k]] = cls_label;
+                if (sc.use_iou_pred) {
+                    const AnchorFrame f = anchor_frame(pa[k]);
+                    const float4 pred = decode_box(pd[k], f);
+                    const float4 tgt = decode_box(encode_box(gt, f), f);
+                    siou += (double)iou_plus1(tgt, area_plus1(tgt), pred, area_plus1(pred));
+                }
             }
         }
     }

@@ -134,10 +134,9 @@ PAA_HD double log_pos(double x) {
     uint64_t u = f64_bits(x);
     int e = (int)(u >> 52) - 1023;
     double m = f64_from_bits((u & 0x000fffffffffffffull) | 0x3ff0000000000000ull);   // [1, 2)
-    if (m > 1.4142135623730951) {
-        m *= 0.5;
-        e += 1;
-    }
+    const bool big = m > 1.4142135623730951;          // selects, not a branch: lanes carry different arguments
+    m = big ? m * 0.5 : m;
+    e = big ? e + 1 : e;
     const double t = two_atanh_small(div_fast(m - 1.0, m + 1.0));
     const double ef = (double)e;
     return fma(ef, 6.93147180369123816490e-01, fma(ef, 1.90821492927058770002e-10, t));

@@ -75,11 +75,16 @@ def topk_tie_exempt(oracle_asg, rel=1e-5):
 
 
 def gmm_tie_exempt(oracle_asg, abs_tol=1e-5):
-    """Exemption (ii): GTs whose two best foreground scores are within abs_tol (structural ties)."""
+    """Exemption (ii): GTs whose two best foreground scores are within abs_tol (structural ties), and
+    (ii-b) GTs with a sample whose two weighted component log-probabilities are within abs_tol (the
+    foreground / background call of `predict` is rounding noise, e.g. two coinciding components)."""
     from oracle import gmm_oracle
     exempt = set()
     for i, recs in enumerate(oracle_asg.gmm_records):
         for r in recs:
-            if r.get("fit") is not None and gmm_oracle.structural_tie_margin(r["fit"]) < abs_tol:
+            if r.get("fit") is None:
+                continue
+            if (gmm_oracle.structural_tie_margin(r["fit"]) < abs_tol
+                    or gmm_oracle.component_margin(r["fit"], r["sorted_loss"]) < abs_tol):
                 exempt.add((i, r["gt"]))
     return exempt

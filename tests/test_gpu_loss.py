@@ -97,9 +97,8 @@ def test_end_to_end_losses_and_grads_against_recorded_reference(name):
         assert diff <= exempt, (name, diff - exempt)
 
 
-def test_c1_against_oracle_full_resolution():
-    """Config C1 (2 x 800x1333, 20 GT/img) against the oracle run on this machine's CPU."""
-    b = synthetic.make_batch(seed=1000, num_images=2, image_hw=(800, 1333), gt_per_image=20)
+def _assert_matches_oracle(b, max_exempt):
+    """Free-running comparison of one batch with the oracle run on this machine's CPU."""
     ref_losses, ref_grads, asg = paa_oracle.assign_and_loss(b.box_cls, b.box_regression, b.iou_pred,
                                                             b.gt_boxes, b.gt_labels, b.anchors)
     ev = _evaluator()
@@ -113,13 +112,20 @@ def test_c1_against_oracle_full_resolution():
     exempt = topk_tie_exempt(asg, rel=1e-4) | gmm_tie_exempt(asg, abs_tol=1e-4)
     diff = {(i, int(asg.matched_idx[i][a])) for i, a in zip(*np.nonzero(got != asg.paa_labels.numpy()))}
     assert diff <= exempt, diff - exempt
-    assert len(diff) <= 2
+    assert len(diff) <= max_exempt
     if not diff:
         np.testing.assert_allclose([float(x) for x in losses], [float(x) for x in ref_losses], rtol=RTOL)
         np.testing.assert_allclose(flat_levels([t.grad for t in cls]), flat_levels(ref_grads.box_cls),
                                    rtol=RTOL, atol=1e-9)
         np.testing.assert_allclose(flat_levels([t.grad for t in reg]), flat_levels(ref_grads.box_regression),
                                    rtol=1e-3, atol=1e-7)
+    return len(diff)
+
+
+def test_c1_against_oracle_full_resolution():
+    """Config C1 (2 x 800x1333, 20 GT/img) against the oracle run on this machine's CPU."""
+    b = synthetic.make_batch(seed=1000, num_images=2, image_hw=(800, 1333), gt_per_image=20)
+    _assert_matches_oracle(b, max_exempt=2)
 
 
 def test_without_iou_pred():
@@ -135,11 +141,25 @@ def test_without_iou_pred():
         np.testing.assert_allclose([float(x) for x in losses], [float(x) for x in ref_losses], rtol=RTOL)
 
 
-def test_full_size_properties_c2():
-    """Size-independent checks at the bench shape (16 images, up to 100 GT): determinism, positives are
-    candidates matched to their GT, every GT with candidates gets >= 1 positive, and the batch splits
-    into halves with identical labels and additive normalisers."""
-    b = synthetic.make_batch(seed=2000, num_images=16, image_hw=(800, 1333), gt_per_image=(1, 100))
+def test_c3_dense_crowd_against_oracle():
+    """Config C3's shape (1333x1333 -> 37 606 anchors, 500 GT) on one image against the oracle."""
+    b = synthetic.make_batch(seed=3000, num_images=1, image_hw=(1333, 1333), gt_per_image=500)
+    assert b.num_anchors == 37606
+    _assert_matches_oracle(b, max_exempt=8)
+
+
+def test_c5_multiscale_against_oracle():
+    """Config C5's shape: images of different sizes padded to the batch maximum (per-image BoxList.size)."""
+    hw = synthetic.multiscale_hw(5000, 3)
+    b = synthetic.make_batch(seed=5000, num_images=3, image_hw=(0, 0), gt_per_image=(1, 30), per_image_hw=hw)
+    assert len(set(b.image_sizes)) > 1
+    _assert_matches_oracle(b, max_exempt=2)
+
+
+def _check_full_size_properties(b):
+    """Size-independent checks: determinism, positives are candidates matched to their GT, every GT with
+    candidates gets >= 1 positive, and the batch splits into halves with identical labels and additive
+    normalisers."""
     ev = _evaluator()
     ev.debug = True
     cls, reg, iou, targets, anchors = to_device_inputs(b)
@@ -175,6 +195,25 @@ def test_full_size_properties_c2():
         assert torch.equal(dh["paa_labels"], d1["paa_labels"][sl])
         norm_sum += dh["normalisers"].cpu().numpy()
     np.testing.assert_allclose(norm_sum, d1["normalisers"].cpu().numpy(), rtol=1e-12)
+
+
+def test_full_size_properties_c2():
+    """The bench shape: 16 images of 800x1333, 1..100 GT each."""
+    _check_full_size_properties(synthetic.make_batch(seed=2000, num_images=16, image_hw=(800, 1333),
+                                                     gt_per_image=(1, 100)))
+
+
+def test_full_size_properties_c3():
+    """Dense crowd, one rank's share: 4 images of 1333x1333 with 500 GT each."""
+    _check_full_size_properties(synthetic.make_batch(seed=3001, num_images=4, image_hw=(1333, 1333),
+                                                     gt_per_image=500))
+
+
+def test_full_size_properties_c5():
+    """Multi-scale, one rank's share: 8 images of different sizes padded to the batch maximum."""
+    hw = synthetic.multiscale_hw(5001, 8)
+    _check_full_size_properties(synthetic.make_batch(seed=5001, num_images=8, image_hw=(0, 0),
+                                                     gt_per_image=(1, 100), per_image_hw=hw))
 
 
 def test_error_behaviour():

@@ -27,7 +27,6 @@
 namespace paa {
 
 constexpr int kHistBins = 2048;
-constexpr int kCandClsChunk = 16;
 constexpr int kMaxTopN = 4096;
 constexpr int kFilterBlocks = 32;      // blocks per (image, level) list in the filter pass
 
@@ -127,87 +126,189 @@ __device__ __forceinline__ int score_bin(float s) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// candidates
+// candidates: one streaming pass over the logits.
+//
+// Which anchor or class a logit belongs to only matters for the few that pass the threshold, so each
+// image's [C, H*W] block of a level is read as one flat array (the access pattern of a memcpy), a float4
+// per lane, four float4 in flight per thread and the next chunk's four already issued.  The gate is a
+// plain compare against logit(thr) (no transcendental) that leaves a 16-bit mask per thread; only a
+// passing element pays for its sigmoid, the IoU-prediction sigmoid of its anchor, the index arithmetic and
+// the append, in a loop that takes one gated element per lane per trip (usually zero or one trip).  A 4096-element chunk never
+// crosses an image; its candidates are collected in shared memory (one warp-aggregated counter update
+// per element position) and appended to the (image, level) list with one global atomic per chunk; the
+// 2048-bin score histogram of the list is updated with fire-and-forget reductions.  Chunks are dealt to
+// the blocks round-robin, so the small dense levels (most of P6 / P7 passes the threshold) spread over
+// the whole grid.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(PAA_TILE)
-post_candidates_kernel(const Geometry geo, const float thr, const float logit_gate, uint2* __restrict__ cand,
-                       int* __restrict__ cand_count, int* __restrict__ hist) {
-    __shared__ uint2 s_buf[PAA_TILE * kCandClsChunk];
+constexpr int kCandThreads = 256;
+constexpr int kCandVecs = 4;                                     // float4 per thread per chunk
+constexpr int kCandChunk = kCandThreads * kCandVecs * 4;        // elements per chunk (= buffer capacity)
+constexpr int kCandBlocksPerSM = 5;
+
+struct CandPlan {
+    unsigned chunk_off[PAA_MAX_LEVELS + 1];     // first chunk of each level in the global chunk order
+    unsigned chunks_per_image[PAA_MAX_LEVELS];
+    unsigned char vec[PAA_MAX_LEVELS];          // 16-byte loads allowed
+    unsigned total;
+};
+
+struct CandChunk {
+    int l, n, seg;
+    unsigned e_base, per_image;
+    const float* src;
+};
+
+__device__ __forceinline__ CandChunk cand_chunk(const Geometry& geo, const CandPlan& plan, unsigned ch) {
+    CandChunk k;
+    k.l = 0;
+#pragma unroll
+    for (int q = 1; q < PAA_MAX_LEVELS; ++q)
+        if (q < geo.num_levels && ch >= plan.chunk_off[q]) k.l = q;
+    const unsigned rel = ch - plan.chunk_off[k.l];
+    k.n = (int)(rel / plan.chunks_per_image[k.l]);
+    k.e_base = (rel - (unsigned)k.n * plan.chunks_per_image[k.l]) * kCandChunk;
+    k.seg = k.n * geo.num_levels + k.l;
+    k.per_image = (unsigned)(geo.apl * geo.C) * (unsigned)geo.lv[k.l].hw;      // elements of one image
+    k.src = geo.lv[k.l].cls + (size_t)k.n * k.per_image;
+    return k;
+}
+
+__device__ __forceinline__ void cand_load(const CandChunk& k, bool vec, float4 (&x)[kCandVecs]) {
+#pragma unroll
+    for (int j = 0; j < kCandVecs; ++j) {
+        const unsigned e = k.e_base + (unsigned)(j * kCandThreads + threadIdx.x) * 4u;
+        if (vec && e + 4u <= k.per_image) {
+            x[j] = __ldcs(reinterpret_cast<const float4*>(k.src + e));
+        } else {
+            x[j].x = (e < k.per_image) ? __ldg(k.src + e) : -INFINITY;
+            x[j].y = (e + 1u < k.per_image) ? __ldg(k.src + e + 1u) : -INFINITY;
+            x[j].z = (e + 2u < k.per_image) ? __ldg(k.src + e + 2u) : -INFINITY;
+            x[j].w = (e + 3u < k.per_image) ? __ldg(k.src + e + 3u) : -INFINITY;
+        }
+    }
+}
+
+// n / d and n % d for n < 2^24 * d through one float multiply and a +-1 fix-up (d > 0, inv = 1.0f / d).
+__device__ __forceinline__ void divmod_small(unsigned n, unsigned d, float inv, unsigned* q, unsigned* r) {
+    unsigned qq = (unsigned)((float)n * inv);
+    int rr = (int)(n - qq * d);
+    if (rr < 0) {
+        --qq;
+        rr += (int)d;
+    } else if (rr >= (int)d) {
+        ++qq;
+        rr -= (int)d;
+    }
+    *q = qq;
+    *r = (unsigned)rr;
+}
+
+__global__ void __launch_bounds__(kCandThreads, kCandBlocksPerSM)
+post_candidates_kernel(const Geometry geo, const CandPlan plan, const float thr, const float logit_gate,
+                       uint2* __restrict__ cand, int* __restrict__ cand_count, int* __restrict__ hist) {
+    __shared__ uint2 s_buf[kCandChunk];
     __shared__ int s_hist[kHistBins];
     __shared__ int s_cnt, s_base;
-
-    const int n = blockIdx.x / geo.tiles_per_image;
-    const int tile = blockIdx.x - n * geo.tiles_per_image;
-    int first;
-    const int l = tile_level(geo, tile, &first);
-    const LevelView& lv = geo.lv[l];
-    const int i = first + threadIdx.x;
-    const bool valid = i < lv.n_anchor;
     const int lane = threadIdx.x & 31;
-    const int seg = n * geo.num_levels + l;
-    uint2* list = cand + ((size_t)n * geo.A + lv.a_off) * geo.C;
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
 
-    for (int b = threadIdx.x; b < kHistBins; b += PAA_TILE) s_hist[b] = 0;
-    float q = 1.0f;
-    const bool has_iou = lv.iou != nullptr;
-    if (valid && has_iou) {
-        const float xi = __ldg(lv.iou + head_offset(n, i, 0, 1, geo.apl, lv.hw));
-        q = 1.0f / (1.0f + expf(-xi));                                   // inference.py:55
-    }
-    const float* cls = lv.cls + (valid ? head_offset(n, i, 0, geo.C, geo.apl, lv.hw) : 0);
-    const unsigned stride = (unsigned)lv.hw;
-    bool any_in_block = false;
-
-    for (int c0 = 0; c0 < geo.C; c0 += kCandClsChunk) {
-        if (threadIdx.x == 0) s_cnt = 0;
-        __syncthreads();
-        const int c1 = min(geo.C, c0 + kCandClsChunk);
-        for (int cb = c0; cb < c1; cb += 8) {
-            float x[8];
+    unsigned ch = blockIdx.x;
+    if (ch >= plan.total) return;
+    CandChunk cur = cand_chunk(geo, plan, ch);
+    float4 x[kCandVecs], nx[kCandVecs];
+    cand_load(cur, plan.vec[cur.l] != 0, x);
+    const float inv_c = 1.0f / (float)geo.C;
+    for (;;) {
+        const unsigned ch_next = ch + gridDim.x;
+        const bool more = ch_next < plan.total;
+        CandChunk nxt = cur;
+        if (more) {
+            nxt = cand_chunk(geo, plan, ch_next);
+            cand_load(nxt, plan.vec[nxt.l] != 0, nx);
+        }
+        const LevelView& lv = geo.lv[cur.l];
+        const unsigned hw = (unsigned)lv.hw;
+        const bool has_iou = lv.iou != nullptr;
+        const float inv_hw = 1.0f / (float)hw;
+        // bit 4j+t: element t of float4 j passes the gate (16 compares, no transcendental)
+        unsigned mask = 0u;
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-                x[j] = (valid && cb + j < c1) ? __ldg(cls + (unsigned)(cb + j) * stride) : -INFINITY;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                bool is = false;
-                float score = 0.0f;
-                if (x[j] > logit_gate) {                                   // cheap gate, exact test below
-                    const float p = 1.0f / (1.0f + expf(-x[j]));           // inference.py:43
-                    if (p > thr) {                                         // inference.py:48
-                        is = true;
-                        score = has_iou ? sqrtf(__fmul_rn(p, q)) : p;      // inference.py:56
+        for (int j = 0; j < kCandVecs; ++j) {
+            mask |= (x[j].x > logit_gate ? 1u : 0u) << (4 * j);
+            mask |= (x[j].y > logit_gate ? 1u : 0u) << (4 * j + 1);
+            mask |= (x[j].z > logit_gate ? 1u : 0u) << (4 * j + 2);
+            mask |= (x[j].w > logit_gate ? 1u : 0u) << (4 * j + 3);
+        }
+        // one gated element per lane per trip (one copy of the expensive path in the instruction stream)
+#pragma unroll 1
+        while (__any_sync(PAA_FULL, mask != 0u)) {
+            const bool has = mask != 0u;
+            const int b = has ? __ffs(mask) - 1 : 0;
+            mask &= mask - 1u;
+            const int j = b >> 2, t = b & 3;
+            const float4 xs = j == 0 ? x[0] : (j == 1 ? x[1] : (j == 2 ? x[2] : x[3]));
+            const float xval = t == 0 ? xs.x : (t == 1 ? xs.y : (t == 2 ? xs.z : xs.w));
+            bool is = false;
+            float score = 0.0f;
+            unsigned entry = 0u;
+            if (has) {
+                const float p = 1.0f / (1.0f + expf(-xval));                   // inference.py:43
+                if (p > thr) {                                                 // inference.py:48
+                    const unsigned e = cur.e_base + (unsigned)(j * kCandThreads + threadIdx.x) * 4u + (unsigned)t;
+                    unsigned chn, loc, a, c;
+                    divmod_small(e, hw, inv_hw, &chn, &loc);
+                    divmod_small(chn, (unsigned)geo.C, inv_c, &a, &c);
+                    entry = (loc * (unsigned)geo.apl + a) * (unsigned)geo.C + c;   // anchor * C + class
+                    score = p;
+                    if (has_iou) {
+                        const float xi = __ldg(lv.iou + ((size_t)cur.n * geo.apl + a) * hw + loc);
+                        const float q = 1.0f / (1.0f + expf(-xi));             // inference.py:55
+                        score = sqrtf(__fmul_rn(p, q));                        // inference.py:56
                     }
-                }
-                const unsigned m = __ballot_sync(PAA_FULL, is);
-                if (m) {
-                    int base = 0;
-                    if (lane == 0) base = atomicAdd(&s_cnt, __popc(m));
-                    base = __shfl_sync(PAA_FULL, base, 0);
-                    if (is) {
-                        const int slot = base + __popc(m & ((1u << lane) - 1u));
-                        s_buf[slot] = make_uint2(__float_as_uint(score), (unsigned)(i * geo.C + cb + j));
-                        atomicAdd(&s_hist[score_bin(score)], 1);
-                    }
+                    is = true;
                 }
             }
+            const unsigned m = __ballot_sync(PAA_FULL, is);
+            if (m) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&s_cnt, __popc(m));
+                base = __shfl_sync(PAA_FULL, base, 0);
+                if (is) s_buf[base + __popc(m & ((1u << lane) - 1u))] = make_uint2(__float_as_uint(score), entry);
+            }
         }
+        // append this chunk's candidates to its (image, level) list and count them into its histogram
         __syncthreads();
         const int cnt = s_cnt;
         if (cnt > 0) {
-            any_in_block = true;
-            if (threadIdx.x == 0) s_base = atomicAdd(&cand_count[seg], cnt);
+            int* gh = hist + (size_t)cur.seg * kHistBins;
+            if (threadIdx.x == 0) s_base = atomicAdd(&cand_count[cur.seg], cnt);
+            const bool dense = cnt > 2 * kCandThreads;
+            if (dense)
+                for (int b = threadIdx.x; b < kHistBins; b += kCandThreads) s_hist[b] = 0;
             __syncthreads();
-            const int gb = s_base;
-            for (int t = threadIdx.x; t < cnt; t += PAA_TILE) list[gb + t] = s_buf[t];
+            uint2* list = cand + ((size_t)cur.n * geo.A + lv.a_off) * geo.C + s_base;
+            for (int t = threadIdx.x; t < cnt; t += kCandThreads) {
+                const uint2 v = s_buf[t];
+                list[t] = v;
+                const int bin = score_bin(__uint_as_float(v.x));
+                if (dense) atomicAdd(&s_hist[bin], 1);
+                else atomicAdd(&gh[bin], 1);
+            }
+            __syncthreads();
+            if (dense)
+                for (int b = threadIdx.x; b < kHistBins; b += kCandThreads) {
+                    const int v = s_hist[b];
+                    if (v) atomicAdd(&gh[b], v);
+                }
+            if (threadIdx.x == 0) s_cnt = 0;
+            __syncthreads();
         }
-        __syncthreads();
-    }
-    if (any_in_block) {
-        int* gh = hist + (size_t)seg * kHistBins;
-        for (int b = threadIdx.x; b < kHistBins; b += PAA_TILE) {
-            const int v = s_hist[b];
-            if (v) atomicAdd(&gh[b], v);
-        }
+        if (!more) break;
+        ch = ch_next;
+        cur = nxt;
+#pragma unroll
+        for (int j = 0; j < kCandVecs; ++j) x[j] = nx[j];
     }
 }
 
@@ -972,9 +1073,26 @@ int run_postprocess(const Geometry& geo, const PaaPostArgs* a, cudaStream_t stre
     // a logit can only pass sigmoid(x) > thr if x > logit(thr); gate a little below that and test exactly
     const float gate = logf(a->pre_nms_thresh / (1.0f - a->pre_nms_thresh)) - 1e-3f;
     {
+        CandPlan plan;
+        unsigned chunks = 0;
+        for (int l = 0; l < PAA_MAX_LEVELS; ++l) {
+            plan.chunk_off[l] = chunks;
+            plan.chunks_per_image[l] = 1;
+            plan.vec[l] = 0;
+            if (l >= L) continue;
+            const LevelView& lv = geo.lv[l];
+            const unsigned long long per_image = (unsigned long long)geo.apl * C * lv.hw;
+            plan.chunks_per_image[l] = (unsigned)((per_image + kCandChunk - 1) / kCandChunk);
+            plan.vec[l] = ((per_image & 3ull) == 0 && (reinterpret_cast<uintptr_t>(lv.cls) & 15u) == 0) ? 1 : 0;
+            chunks += plan.chunks_per_image[l] * (unsigned)N;
+        }
+        plan.chunk_off[PAA_MAX_LEVELS] = chunks;
+        plan.total = chunks;
+        unsigned grid = 148u * kCandBlocksPerSM;
+        if (grid > chunks) grid = chunks;
         KernelTimer t(PAA_KERNEL_POST_CANDIDATES, stream);
-        post_candidates_kernel<<<N * geo.tiles_per_image, PAA_TILE, 0, stream>>>(geo, a->pre_nms_thresh, gate,
-                                                                                 w.cand, w.cand_count, w.hist);
+        post_candidates_kernel<<<grid, kCandThreads, 0, stream>>>(geo, plan, a->pre_nms_thresh, gate, w.cand,
+                                                                  w.cand_count, w.hist);
     }
     PAA_LAUNCH_CHECK("post_candidates_kernel");
     post_threshold_kernel<<<N * L, 256, 0, stream>>>(w.cand_count, w.hist, topn, w.thr_bin, w.n_above, w.k_sel);

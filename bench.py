@@ -446,8 +446,17 @@ def run_ours(args):
         peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)"
     else:
         peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
+    # DRAM bytes of one launch of the same kernel from the committed ncu --set full capture (profiles/)
+    traffic = None
+    traffic_path = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if os.path.exists(traffic_path) and n_img == 16:
+        try:
+            k = json.load(open(traffic_path))["kernels"]["bulk_focal_kernel<1, 1>"]
+            traffic = k["dram_read_bytes"] + k["dram_write_bytes"]
+        except (KeyError, ValueError):
+            traffic = None
     roofline = {"bound": "hbm", "kernel": "bulk_focal_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "kernel_us": 1000.0 * kernel_ms, "algorithmic_bytes_per_launch": kernel_bytes_per_image * n_img,
                 "whole_step_frac_of_hbm_roofline": (A * 696 * n_img / ((total_ms / args.steps) / 1000.0) / 1e9) / peak,
                 "per_kernel_us": shares}

@@ -1,7 +1,9 @@
 """NMS + score-voting images/sec (second half of BASELINE.json's metric), config C4 of SURVEY.md 8d:
-8 images per GPU (batch 64 over 8 GPUs) of 800x1333, >= 1000 candidates per level above 0.05,
-80 classes, NMS 0.6, score voting on, 100 detections per image.  Imported by bench.py (rank 0)
-and runnable on its own:  python bench_post.py
+a batch of 64 images of 800x1333, >= 1000 candidates per level above 0.05, 80 classes, NMS 0.6, score
+voting on, 100 detections per image.  The headline number runs the whole 64-image batch on one GPU (it
+fits); the 8-image figure (one rank's share when the batch is spread over 8 GPUs) and the dense stress
+variant are reported beside it.  Imported by bench.py (rank 0) and runnable on its own:
+python bench_post.py
 """
 import ctypes
 import json
@@ -20,7 +22,8 @@ POST_KERNELS = ("post_candidates", "post_filter", "post_select", "post_rank", "p
                 "post_finish", "post_vote")
 
 
-def measure_post(dev, steps=10, warmup=3, images=8, with_cpu=True, candidates_per_level=4000, with_dense=True):
+def measure_post(dev, steps=10, warmup=3, images=64, with_cpu=True, candidates_per_level=4000, with_dense=True,
+                 with_share=True):
     """candidates_per_level: expected (location, class) pairs above 0.05 per level (detector-like
     sparsity, every level still has > 1000 so the per-level cap of 1000 is active everywhere);
     None = the dense variant where ~49 % of ALL logits are candidates (stress case, reported too)."""
@@ -104,10 +107,17 @@ def measure_post(dev, steps=10, warmup=3, images=8, with_cpu=True, candidates_pe
         res["cpu_baseline"] = {"value": 1.0 / (time.perf_counter() - t0), "unit": "images/s",
                                "cores": torch.get_num_threads(), "kind": "port",
                                "sample": "1 image of the batch, one run"}
+    del cls, reg, iou, anc, anchors, batch, graph, out
+    torch.cuda.empty_cache()
+    keep = ("value", "unit", "images_per_gpu", "ms_per_step", "per_kernel_us", "config")
+    if with_share and images > 8:
+        d = measure_post(dev, steps=steps, warmup=warmup, images=8, with_cpu=False,
+                         candidates_per_level=candidates_per_level, with_dense=False, with_share=False)
+        res["one_rank_share_of_8"] = {k: d[k] for k in keep}
     if with_dense and candidates_per_level is not None:
-        d = measure_post(dev, steps=max(3, steps // 2), warmup=warmup, images=images, with_cpu=False,
-                         candidates_per_level=None, with_dense=False)
-        res["dense_variant"] = {k: d[k] for k in ("value", "unit", "ms_per_step", "per_kernel_us", "config")}
+        d = measure_post(dev, steps=max(3, steps // 2), warmup=warmup, images=8, with_cpu=False,
+                         candidates_per_level=None, with_dense=False, with_share=False)
+        res["dense_variant"] = {k: d[k] for k in keep}
     return res
 
 

@@ -324,22 +324,34 @@ positive_terms_kernel(const Geometry geo, const GtOffsets go, const float* __res
 }
 
 // Folds the per-block partials in a fixed order and applies the normalisers (loss.py:354-358).
-__global__ void __launch_bounds__(256)
+// One block of 512 threads; every thread issues its (up to four) independent loads before adding, so the
+// fold costs a couple of memory round trips instead of one per 256 partials.
+constexpr int kFinishThreads = 512;
+
+__device__ __forceinline__ void fold_partials(const double* __restrict__ part, int blocks, double (&a)[3]) {
+    for (int b0 = threadIdx.x; b0 < blocks; b0 += 4 * kFinishThreads) {
+        double v[4][3];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int b = b0 + u * kFinishThreads;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) v[u][k] = (b < blocks) ? __ldcg(part + (size_t)b * 3 + k) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) a[k] += v[u][k];
+    }
+}
+
+__global__ void __launch_bounds__(kFinishThreads)
 finish_loss_kernel(const double* __restrict__ part_a, int blocks_a, const double* __restrict__ part_b,
                    int blocks_b, const LossScalars sc, const double* __restrict__ norm,
                    float* __restrict__ losses) {
-    __shared__ double s[8][3];
+    __shared__ double s[kFinishThreads / PAA_WARP][3];
     double a[3] = {0.0, 0.0, 0.0};
-    for (int b = threadIdx.x; b < blocks_a; b += 256) {
-        a[0] += part_a[(size_t)b * 3 + 0];
-        a[1] += part_a[(size_t)b * 3 + 1];
-        a[2] += part_a[(size_t)b * 3 + 2];
-    }
-    for (int b = threadIdx.x; b < blocks_b; b += 256) {
-        a[0] += part_b[(size_t)b * 3 + 0];
-        a[1] += part_b[(size_t)b * 3 + 1];
-        a[2] += part_b[(size_t)b * 3 + 2];
-    }
+    fold_partials(part_a, blocks_a, a);
+    fold_partials(part_b, blocks_b, a);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -349,7 +361,7 @@ finish_loss_kernel(const double* __restrict__ part_a, int blocks_a, const double
     __syncthreads();
     if (threadIdx.x == 0) {
         double t[3] = {0.0, 0.0, 0.0};
-        for (int w = 0; w < 8; ++w)
+        for (int w = 0; w < kFinishThreads / PAA_WARP; ++w)
             for (int k = 0; k < 3; ++k) t[k] += s[w][k];
         const double world = (double)sc.world_size;
         const float num_pos_avg = (float)fmax(norm[0] / world, 1.0);
@@ -419,7 +431,7 @@ int launch_final_loss(const Geometry& geo, const GtOffsets& go, const float* gt_
     }
 #undef PAA_POS
     PAA_LAUNCH_CHECK("positive_terms_kernel");
-    finish_loss_kernel<<<1, 256, 0, stream>>>(bulk_part, bulk_grid, tile_part, tile_grid, sc, normalisers, losses);
+    finish_loss_kernel<<<1, kFinishThreads, 0, stream>>>(bulk_part, bulk_grid, tile_part, tile_grid, sc, normalisers, losses);
     PAA_LAUNCH_CHECK("finish_loss_kernel");
     return 0;
 }

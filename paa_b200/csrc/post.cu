@@ -131,19 +131,22 @@ __device__ __forceinline__ int score_bin(float s) {
 // Which anchor or class a logit belongs to only matters for the few that pass the threshold, so each
 // image's [C, H*W] block of a level is read as one flat array (the access pattern of a memcpy), a float4
 // per lane, four float4 in flight per thread and the next chunk's four already issued.  The gate is a
-// plain compare against logit(thr) (no transcendental) that leaves a 16-bit mask per thread; only a
-// passing element pays for its sigmoid, the IoU-prediction sigmoid of its anchor, the index arithmetic and
-// the append, in a loop that takes one gated element per lane per trip (usually zero or one trip).  A 4096-element chunk never
-// crosses an image; its candidates are collected in shared memory (one warp-aggregated counter update
-// per element position) and appended to the (image, level) list with one global atomic per chunk; the
-// 2048-bin score histogram of the list is updated with fire-and-forget reductions.  Chunks are dealt to
-// the blocks round-robin, so the small dense levels (most of P6 / P7 passes the threshold) spread over
-// the whole grid.
+// plain compare against logit(thr) (no transcendental) that leaves a 16-bit mask per thread.  Gated
+// elements (a fraction of a percent on the fine levels) are pushed, with their position, into a queue in
+// shared memory that lives across the block's chunks; whenever the queue holds a few warps' worth of work
+// (and at the end) it is drained by ALL threads of the block: sigmoid, exact threshold test, the
+// IoU-prediction sigmoid of the anchor, index arithmetic, and the append to the (image, level) list (one
+// global atomic per (warp, list)) with its 2048-bin score histogram.  The expensive path therefore runs on
+// full warps instead of on the one or two lanes of a warp that happen to hold a candidate.
+// Chunks (4096 elements, never crossing an image) are dealt to the blocks round-robin, so the small dense
+// levels (most of P6 / P7 passes the threshold) spread over the whole grid.
 // ---------------------------------------------------------------------------------------------
 constexpr int kCandThreads = 256;
 constexpr int kCandVecs = 4;                                     // float4 per thread per chunk
-constexpr int kCandChunk = kCandThreads * kCandVecs * 4;        // elements per chunk (= buffer capacity)
-constexpr int kCandBlocksPerSM = 5;
+constexpr int kCandChunk = kCandThreads * kCandVecs * 4;        // elements per chunk
+constexpr int kCandDrainAt = 512;                                // drain when at least this many are queued
+constexpr int kCandQueue = kCandDrainAt + kCandChunk;            // queue capacity
+constexpr int kCandBlocksPerSM = 4;
 
 struct CandPlan {
     unsigned chunk_off[PAA_MAX_LEVELS + 1];     // first chunk of each level in the global chunk order
@@ -153,7 +156,7 @@ struct CandPlan {
 };
 
 struct CandChunk {
-    int l, n, seg;
+    int l, n;
     unsigned e_base, per_image;
     const float* src;
 };
@@ -167,7 +170,6 @@ __device__ __forceinline__ CandChunk cand_chunk(const Geometry& geo, const CandP
     const unsigned rel = ch - plan.chunk_off[k.l];
     k.n = (int)(rel / plan.chunks_per_image[k.l]);
     k.e_base = (rel - (unsigned)k.n * plan.chunks_per_image[k.l]) * kCandChunk;
-    k.seg = k.n * geo.num_levels + k.l;
     k.per_image = (unsigned)(geo.apl * geo.C) * (unsigned)geo.lv[k.l].hw;      // elements of one image
     k.src = geo.lv[k.l].cls + (size_t)k.n * k.per_image;
     return k;
@@ -206,19 +208,69 @@ __device__ __forceinline__ void divmod_small(unsigned n, unsigned d, float inv, 
 __global__ void __launch_bounds__(kCandThreads, kCandBlocksPerSM)
 post_candidates_kernel(const Geometry geo, const CandPlan plan, const float thr, const float logit_gate,
                        uint2* __restrict__ cand, int* __restrict__ cand_count, int* __restrict__ hist) {
-    __shared__ uint2 s_buf[kCandChunk];
-    __shared__ int s_hist[kHistBins];
-    __shared__ int s_cnt, s_base;
+    __shared__ float q_x[kCandQueue];              // gated logit
+    __shared__ unsigned q_e[kCandQueue];           // its element index inside the image's [C, H*W] block
+    __shared__ unsigned short q_where[kCandQueue]; // (image << 3) | level
+    __shared__ int q_cnt;
     const int lane = threadIdx.x & 31;
-    if (threadIdx.x == 0) s_cnt = 0;
+    if (threadIdx.x == 0) q_cnt = 0;
     __syncthreads();
+    const float inv_c = 1.0f / (float)geo.C;
+
+    // all threads: exact test + score + append for every queued element (block-uniform call)
+    auto drain = [&]() {
+        const int total = q_cnt;
+        for (int t0 = 0; t0 < total; t0 += kCandThreads) {
+            const int t = t0 + threadIdx.x;
+            bool is = false;
+            float score = 0.0f;
+            unsigned entry = 0u;
+            int seg = -1, n = 0, l = 0;
+            if (t < total) {
+                const float xval = q_x[t];
+                const float p = 1.0f / (1.0f + expf(-xval));                   // inference.py:43
+                if (p > thr) {                                                 // inference.py:48
+                    const unsigned where = q_where[t];
+                    n = (int)(where >> 3);
+                    l = (int)(where & 7u);
+                    const LevelView& lv = geo.lv[l];
+                    const unsigned hw = (unsigned)lv.hw;
+                    unsigned chn, loc, a, c;
+                    divmod_small(q_e[t], hw, 1.0f / (float)hw, &chn, &loc);
+                    divmod_small(chn, (unsigned)geo.C, inv_c, &a, &c);
+                    entry = (loc * (unsigned)geo.apl + a) * (unsigned)geo.C + c;   // anchor * C + class
+                    score = p;
+                    if (lv.iou != nullptr) {
+                        const float xi = __ldg(lv.iou + ((size_t)n * geo.apl + a) * hw + loc);
+                        const float q = 1.0f / (1.0f + expf(-xi));             // inference.py:55
+                        score = sqrtf(__fmul_rn(p, q));                        // inference.py:56
+                    }
+                    seg = n * geo.num_levels + l;
+                    is = true;
+                }
+            }
+            // one global atomic per (warp, list); queue neighbours mostly share their list
+            const unsigned act = __ballot_sync(PAA_FULL, is);
+            if (is) {
+                const unsigned peers = __match_any_sync(act, seg);
+                const int leader = __ffs(peers) - 1;
+                int pos = 0;
+                if (lane == leader) pos = atomicAdd(&cand_count[seg], __popc(peers));
+                pos = __shfl_sync(peers, pos, leader) + __popc(peers & ((1u << lane) - 1u));
+                cand[((size_t)n * geo.A + geo.lv[l].a_off) * geo.C + pos] = make_uint2(__float_as_uint(score), entry);
+                atomicAdd(&hist[(size_t)seg * kHistBins + score_bin(score)], 1);
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) q_cnt = 0;
+        __syncthreads();
+    };
 
     unsigned ch = blockIdx.x;
     if (ch >= plan.total) return;
     CandChunk cur = cand_chunk(geo, plan, ch);
     float4 x[kCandVecs], nx[kCandVecs];
     cand_load(cur, plan.vec[cur.l] != 0, x);
-    const float inv_c = 1.0f / (float)geo.C;
     for (;;) {
         const unsigned ch_next = ch + gridDim.x;
         const bool more = ch_next < plan.total;
@@ -227,10 +279,6 @@ post_candidates_kernel(const Geometry geo, const CandPlan plan, const float thr,
             nxt = cand_chunk(geo, plan, ch_next);
             cand_load(nxt, plan.vec[nxt.l] != 0, nx);
         }
-        const LevelView& lv = geo.lv[cur.l];
-        const unsigned hw = (unsigned)lv.hw;
-        const bool has_iou = lv.iou != nullptr;
-        const float inv_hw = 1.0f / (float)hw;
         // bit 4j+t: element t of float4 j passes the gate (16 compares, no transcendental)
         unsigned mask = 0u;
 #pragma unroll
@@ -240,70 +288,33 @@ post_candidates_kernel(const Geometry geo, const CandPlan plan, const float thr,
             mask |= (x[j].z > logit_gate ? 1u : 0u) << (4 * j + 2);
             mask |= (x[j].w > logit_gate ? 1u : 0u) << (4 * j + 3);
         }
-        // one gated element per lane per trip (one copy of the expensive path in the instruction stream)
+        if (__any_sync(PAA_FULL, mask != 0u)) {
+            // queue slots for the warp's gated elements: warp scan of the per-lane counts, one shared atomic
+            const int mine = __popc(mask);
+            int incl = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(PAA_FULL, incl, o);
+                if (lane >= o) incl += v;
+            }
+            int base = 0;
+            if (lane == 31) base = atomicAdd(&q_cnt, incl);
+            int slot = __shfl_sync(PAA_FULL, base, 31) + incl - mine;
+            const unsigned short where = (unsigned short)((cur.n << 3) | cur.l);
 #pragma unroll 1
-        while (__any_sync(PAA_FULL, mask != 0u)) {
-            const bool has = mask != 0u;
-            const int b = has ? __ffs(mask) - 1 : 0;
-            mask &= mask - 1u;
-            const int j = b >> 2, t = b & 3;
-            const float4 xs = j == 0 ? x[0] : (j == 1 ? x[1] : (j == 2 ? x[2] : x[3]));
-            const float xval = t == 0 ? xs.x : (t == 1 ? xs.y : (t == 2 ? xs.z : xs.w));
-            bool is = false;
-            float score = 0.0f;
-            unsigned entry = 0u;
-            if (has) {
-                const float p = 1.0f / (1.0f + expf(-xval));                   // inference.py:43
-                if (p > thr) {                                                 // inference.py:48
-                    const unsigned e = cur.e_base + (unsigned)(j * kCandThreads + threadIdx.x) * 4u + (unsigned)t;
-                    unsigned chn, loc, a, c;
-                    divmod_small(e, hw, inv_hw, &chn, &loc);
-                    divmod_small(chn, (unsigned)geo.C, inv_c, &a, &c);
-                    entry = (loc * (unsigned)geo.apl + a) * (unsigned)geo.C + c;   // anchor * C + class
-                    score = p;
-                    if (has_iou) {
-                        const float xi = __ldg(lv.iou + ((size_t)cur.n * geo.apl + a) * hw + loc);
-                        const float q = 1.0f / (1.0f + expf(-xi));             // inference.py:55
-                        score = sqrtf(__fmul_rn(p, q));                        // inference.py:56
-                    }
-                    is = true;
-                }
-            }
-            const unsigned m = __ballot_sync(PAA_FULL, is);
-            if (m) {
-                int base = 0;
-                if (lane == 0) base = atomicAdd(&s_cnt, __popc(m));
-                base = __shfl_sync(PAA_FULL, base, 0);
-                if (is) s_buf[base + __popc(m & ((1u << lane) - 1u))] = make_uint2(__float_as_uint(score), entry);
+            while (mask) {
+                const int b = __ffs(mask) - 1;
+                mask &= mask - 1u;
+                const int j = b >> 2, t = b & 3;
+                const float4 xs = j == 0 ? x[0] : (j == 1 ? x[1] : (j == 2 ? x[2] : x[3]));
+                q_x[slot] = t == 0 ? xs.x : (t == 1 ? xs.y : (t == 2 ? xs.z : xs.w));
+                q_e[slot] = cur.e_base + (unsigned)(j * kCandThreads + threadIdx.x) * 4u + (unsigned)t;
+                q_where[slot] = where;
+                ++slot;
             }
         }
-        // append this chunk's candidates to its (image, level) list and count them into its histogram
         __syncthreads();
-        const int cnt = s_cnt;
-        if (cnt > 0) {
-            int* gh = hist + (size_t)cur.seg * kHistBins;
-            if (threadIdx.x == 0) s_base = atomicAdd(&cand_count[cur.seg], cnt);
-            const bool dense = cnt > 2 * kCandThreads;
-            if (dense)
-                for (int b = threadIdx.x; b < kHistBins; b += kCandThreads) s_hist[b] = 0;
-            __syncthreads();
-            uint2* list = cand + ((size_t)cur.n * geo.A + lv.a_off) * geo.C + s_base;
-            for (int t = threadIdx.x; t < cnt; t += kCandThreads) {
-                const uint2 v = s_buf[t];
-                list[t] = v;
-                const int bin = score_bin(__uint_as_float(v.x));
-                if (dense) atomicAdd(&s_hist[bin], 1);
-                else atomicAdd(&gh[bin], 1);
-            }
-            __syncthreads();
-            if (dense)
-                for (int b = threadIdx.x; b < kHistBins; b += kCandThreads) {
-                    const int v = s_hist[b];
-                    if (v) atomicAdd(&gh[b], v);
-                }
-            if (threadIdx.x == 0) s_cnt = 0;
-            __syncthreads();
-        }
+        if (q_cnt >= kCandDrainAt || !more) drain();      // q_cnt is stable between the barriers
         if (!more) break;
         ch = ch_next;
         cur = nxt;

@@ -38,10 +38,12 @@
 extern "C" {
 #endif
 
-#define PAA_ABI_VERSION 1
+#define PAA_ABI_VERSION 2
 #define PAA_MAX_LEVELS 8
 #define PAA_MAX_IMAGES 256      /* images per call (per rank) */
 #define PAA_MAX_CANDIDATES 128  /* num_levels * topk must not exceed this */
+#define PAA_MAX_PEERS 16        /* ranks in a peer-memory normaliser exchange */
+#define PAA_PEER_BUFFER_DOUBLES 256  /* size of every rank's exchange buffer */
 
 #define PAA_ERR_BAD_ARGUMENT (-1)
 #define PAA_ERR_WORKSPACE    (-2)
@@ -102,6 +104,17 @@ typedef struct PaaLossArgs {
     const float* teacher_combined_loss;  /* [N, A] if non-NULL, candidate selection and the GMM consume
                                             this instead of the kernel's own anchor scores
                                             (stage-wise parity protocol) */
+    /* Optional peer-memory exchange of the two normalisers (replaces the caller's all-reduce between
+     * paa_assign and paa_loss; loss.py:22-28,321,338).  peer_norm[r] is rank r's exchange buffer
+     * (PAA_PEER_BUFFER_DOUBLES doubles, zeroed once, persistent across calls) as mapped into THIS process
+     * (NVLink peer mapping / symmetric memory); peer_norm[rank] is this rank's own buffer.  paa_assign's last
+     * kernel stores this rank's {num_pos, sum_iou} into every rank's buffer, paa_loss first waits (on its own
+     * buffer only) until all world_size contributions of the step have arrived and leaves their sum, added
+     * in rank order, in `normalisers`.  All ranks must make the same sequence of calls.  peer_norm[0] NULL
+     * = disabled. */
+    int32_t rank;
+    int32_t reserved2;
+    double* peer_norm[PAA_MAX_PEERS];
 } PaaLossArgs;
 
 typedef struct PaaPostArgs {

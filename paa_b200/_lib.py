@@ -11,8 +11,10 @@ from paa_b200 import build as _build
 
 MAX_LEVELS = 8
 MAX_IMAGES = 256
+MAX_PEERS = 16
+PEER_BUFFER_DOUBLES = 256
 MAX_CANDIDATES = 128
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 ERR_BAD_ARGUMENT, ERR_WORKSPACE, ERR_EMPTY_TARGET, ERR_UNSUPPORTED = -1, -2, -3, -4
 
@@ -40,7 +42,8 @@ class PaaLossArgs(C.Structure):
                 ("dbg_matched_idx", C.c_void_p), ("dbg_iou_labels", C.c_void_p),
                 ("dbg_combined_loss", C.c_void_p), ("dbg_cand_idx", C.c_void_p),
                 ("dbg_cand_cnt", C.c_void_p), ("dbg_num_pos", C.c_void_p), ("dbg_gmm", C.c_void_p),
-                ("dbg_paa_labels", C.c_void_p), ("teacher_combined_loss", C.c_void_p)]
+                ("dbg_paa_labels", C.c_void_p), ("teacher_combined_loss", C.c_void_p),
+                ("rank", C.c_int32), ("reserved2", C.c_int32), ("peer_norm", C.c_void_p * MAX_PEERS)]
 
 
 class PaaPostArgs(C.Structure):

@@ -96,6 +96,7 @@ static int tiles_upper_bound(int anchors_per_image, int num_levels) {
 }
 
 struct LossPlan {
+    PeerExchange px;
     Geometry geo;
     GtOffsets go;
     LossScalars sc;
@@ -178,6 +179,23 @@ static int plan_loss(const PaaLossArgs* a, LossPlan* p) {
         int cap = e ? atoi(e) : kSegCap;
         p->sc.seg_cap = cap < 1 ? 1 : (cap > kSegCap ? kSegCap : cap);
     }
+    memset(&p->px, 0, sizeof(p->px));
+    if (a->peer_norm[0] != nullptr && a->world_size > 1) {
+        if (a->world_size > PAA_MAX_PEERS || a->rank < 0 || a->rank >= a->world_size) {
+            set_error("peer exchange: rank %d / world_size %d unsupported (<= %d ranks)", a->rank, a->world_size,
+                      PAA_MAX_PEERS);
+            return PAA_ERR_UNSUPPORTED;
+        }
+        for (int r = 0; r < a->world_size; ++r) {
+            if (!a->peer_norm[r]) {
+                set_error("peer exchange: peer_norm[%d] is null", r);
+                return PAA_ERR_BAD_ARGUMENT;
+            }
+            p->px.buf[r] = a->peer_norm[r];
+        }
+        p->px.rank = a->rank;
+        p->px.world = a->world_size;
+    }
     p->dbg.matched_idx = a->dbg_matched_idx;
     p->dbg.iou_labels = a->dbg_iou_labels;
     p->dbg.combined_loss = a->dbg_combined_loss;
@@ -221,7 +239,7 @@ int paa_assign(const PaaLossArgs* args, void* stream_) {
                                  args->teacher_combined_loss, p.dbg, stream)))
         return rc;
     if ((rc = launch_select_gmm(p.geo, p.go, p.sumG, args->gt_boxes, args->gt_labels, p.sc, p.ws, score_src,
-                                args->normalisers, p.dbg, stream)))
+                                args->normalisers, p.px, p.dbg, stream)))
         return rc;
     if (args->dbg_paa_labels)
         PAA_CUDA_CHECK(cudaMemcpyAsync(args->dbg_paa_labels, p.ws.paa_label,
@@ -235,6 +253,7 @@ int paa_loss(const PaaLossArgs* args, void* stream_) {
     int rc = plan_loss(args, &p);
     if (rc) return rc;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (p.px.world > 1 && (rc = launch_norm_wait(p.px, args->normalisers, stream))) return rc;
     bool write_grads = false;
     for (int l = 0; l < args->num_levels; ++l)
         write_grads = write_grads || args->levels[l].grad_box_cls || args->levels[l].grad_box_regression ||

@@ -691,7 +691,7 @@ select_gmm_kernel(const Geometry geo, const GtOffsets go, int num_gt_total,
                   int* __restrict__ paa_label,
                   int* __restrict__ part_npos, double* __restrict__ part_siou,
                   unsigned* __restrict__ ticket, double* __restrict__ local_norm,
-                  double* __restrict__ normalisers, const LossDebug dbg) {
+                  double* __restrict__ normalisers, const PeerExchange px, const LossDebug dbg) {
     __shared__ unsigned long long s_level[PAA_MAX_LEVELS][PAA_WARP];   // per-level top-K, ascending
     __shared__ int s_cnt[PAA_MAX_LEVELS];
     __shared__ unsigned long long s_key[PAA_MAX_CANDIDATES];
@@ -901,12 +901,72 @@ select_gmm_kernel(const Geometry geo, const GtOffsets go, int num_gt_total,
             normalisers[0] = cnt;
             normalisers[1] = sum;
         }
+        // publish this rank's pair to every rank's exchange buffer over NVLink (lane r -> rank r): data,
+        // system-scope fence, then the epoch that makes it visible to norm_wait_kernel over there
+        if (px.world > 1) {
+            double* own = px.buf[px.rank];
+            unsigned long long epoch = 0;
+            if (lane == 0) {
+                epoch = (unsigned long long)own[kPeerEpochOffset] + 1ull;
+                own[kPeerEpochOffset] = (double)epoch;
+            }
+            epoch = __shfl_sync(PAA_FULL, epoch, 0);
+            if (lane < px.world) {
+                volatile double* dst = px.buf[lane] + ((size_t)(epoch & 1ull) * kPeerMaxRanks + px.rank) * 4;
+                dst[0] = cnt;
+                dst[1] = sum;
+                __threadfence_system();
+                dst[2] = (double)epoch;
+            }
+        }
     }
+}
+
+// First kernel of paa_loss when the peer exchange is on: lane r waits for rank r's contribution of this
+// step in THIS rank's buffer (local memory, written remotely), then the totals are added in rank order --
+// the same order on every rank, so all ranks normalise by bit-identical values.  A contribution that does
+// not arrive within ~2 s turns the normalisers into NaN instead of hanging the stream.
+__global__ void __launch_bounds__(PAA_WARP)
+norm_wait_kernel(const PeerExchange px, double* __restrict__ normalisers) {
+    const int lane = threadIdx.x;
+    const double* own = px.buf[px.rank];
+    const unsigned long long epoch = (unsigned long long)own[kPeerEpochOffset];   // set by select_gmm_kernel
+    double cnt = 0.0, sum = 0.0;
+    bool ok = true;
+    if (lane < px.world) {
+        const volatile double* src = own + ((size_t)(epoch & 1ull) * kPeerMaxRanks + lane) * 4;
+        const long long t0 = clock64();
+        while (src[2] != (double)epoch) {
+            if (clock64() - t0 > 4000000000ll) {
+                ok = false;
+                break;
+            }
+        }
+        __threadfence_system();
+        cnt = src[0];
+        sum = src[1];
+    }
+    ok = __all_sync(PAA_FULL, ok);
+    double tc = 0.0, ts = 0.0;
+    for (int r = 0; r < px.world; ++r) {
+        tc += __shfl_sync(PAA_FULL, cnt, r);
+        ts += __shfl_sync(PAA_FULL, sum, r);
+    }
+    if (lane == 0) {
+        normalisers[0] = ok ? tc : __longlong_as_double(0x7ff8000000000000ll);
+        normalisers[1] = ok ? ts : __longlong_as_double(0x7ff8000000000000ll);
+    }
+}
+
+int launch_norm_wait(const PeerExchange& px, double* normalisers, cudaStream_t stream) {
+    norm_wait_kernel<<<1, PAA_WARP, 0, stream>>>(px, normalisers);
+    PAA_LAUNCH_CHECK("norm_wait_kernel");
+    return 0;
 }
 
 int launch_select_gmm(const Geometry& geo, const GtOffsets& go, int num_gt_total, const float* gt_boxes,
                       const int64_t* gt_labels, const LossScalars& sc, const LossWorkspace& ws,
-                      const float* score_src, double* normalisers, const LossDebug& dbg,
+                      const float* score_src, double* normalisers, const PeerExchange& px, const LossDebug& dbg,
                       cudaStream_t stream) {
     const int cap = geo.num_levels * sc.topk;
     const int grid = num_gt_total;
@@ -916,7 +976,7 @@ int launch_select_gmm(const Geometry& geo, const GtOffsets& go, int num_gt_total
     select_gmm_kernel<SPL><<<grid, threads, 0, stream>>>(geo, go, num_gt_total, gt_boxes, gt_labels, sc, \
         ws.tile_gtmask, ws.matched, score_src, ws.seg_count, ws.seg_pool, ws.paa_label, ws.part_npos,  \
         ws.part_siou,                                                                                  \
-        ws.ticket, ws.local_norm, normalisers, dbg)
+        ws.ticket, ws.local_norm, normalisers, px, dbg)
     if (cap <= 32) PAA_SEL_LAUNCH(1);
     else if (cap <= 64) PAA_SEL_LAUNCH(2);
     else PAA_SEL_LAUNCH(4);

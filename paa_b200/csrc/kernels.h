@@ -11,6 +11,16 @@ struct LossScalars {
     int seg_cap;       // usable entries of a (GT, level) candidate pool, <= kSegCap (PAA_SEG_CAP shrinks it for tests)
 };
 
+// Peer-memory exchange of the loss normalisers (include/paa_b200.h, PaaLossArgs::peer_norm).
+// Buffer layout (doubles): slot (parity p, rank r) at (p * kPeerMaxRanks + r) * 4 = {num_pos, sum_iou, epoch, -};
+// the owner's call counter at kPeerEpochOffset.
+constexpr int kPeerMaxRanks = PAA_MAX_PEERS;
+constexpr int kPeerEpochOffset = 2 * kPeerMaxRanks * 4;
+struct PeerExchange {
+    double* buf[PAA_MAX_PEERS];
+    int rank, world;       // world == 0: disabled
+};
+
 struct LossDebug {
     int* matched_idx;
     int* iou_labels;
@@ -30,8 +40,9 @@ int launch_match_score(const Geometry& geo, const GtOffsets& go, const float* gt
                        const float* teacher_score, const LossDebug& dbg, cudaStream_t stream);
 int launch_select_gmm(const Geometry& geo, const GtOffsets& go, int num_gt_total, const float* gt_boxes,
                       const int64_t* gt_labels, const LossScalars& sc, const LossWorkspace& ws,
-                      const float* score_src, double* normalisers, const LossDebug& dbg,
+                      const float* score_src, double* normalisers, const PeerExchange& px, const LossDebug& dbg,
                       cudaStream_t stream);
+int launch_norm_wait(const PeerExchange& px, double* normalisers, cudaStream_t stream);
 
 // loss.cu
 int loss_grid_blocks(int num_images, int tiles_per_image);

@@ -39,6 +39,49 @@ def reduce_normalisers(normalisers):
     return normalisers
 
 
+class PeerNormExchange(object):
+    """Per-device state of the peer-memory exchange of the two loss normalisers (include/paa_b200.h,
+    ``PaaLossArgs.peer_norm``): one small symmetric-memory buffer per rank, mapped into every rank of the
+    default process group over NVLink.  With it the step's only cross-rank traffic -- 16 bytes per rank --
+    is written by the last block of the assignment kernel straight into the peers' memory and read by the
+    first kernel of the loss pass: no collective launch on the stream (an NCCL all-reduce of this size costs
+    ~14 us of a ~165 us step on B200).  Falls back to ``dist.all_reduce`` where symmetric memory is not
+    available (``PAA_NORM_EXCHANGE=nccl`` forces the fallback)."""
+    _by_device = {}
+
+    def __init__(self, device):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        self.world = dist.get_world_size()
+        self.rank = dist.get_rank()
+        if self.world > _lib.MAX_PEERS:
+            raise RuntimeError("more than %d ranks" % _lib.MAX_PEERS)
+        self.buffer = symm_mem.empty(_lib.PEER_BUFFER_DOUBLES, dtype=torch.float64, device=device)
+        self.buffer.zero_()
+        self.handle = symm_mem.rendezvous(self.buffer, group=dist.group.WORLD.group_name)
+        self.ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        torch.cuda.synchronize(device)
+        dist.barrier()                      # every rank's buffer is zeroed before anyone writes into it
+
+    @classmethod
+    def get(cls, device):
+        """The exchange for `device`, or None when it cannot be used (then the caller all-reduces)."""
+        key = (device.type, device.index)
+        if key not in cls._by_device:
+            state = None
+            if os.environ.get("PAA_NORM_EXCHANGE", "peer") != "nccl":
+                try:
+                    import torch.distributed as dist
+                    if dist.is_available() and dist.is_initialized() and dist.get_world_size() == get_num_gpus():
+                        state = cls(device)
+                except Exception as e:  # noqa: BLE001 - symmetric memory unavailable: use NCCL
+                    import warnings
+                    warnings.warn("paa_b200: peer-memory normaliser exchange unavailable (%s); using all_reduce" % (e,))
+                    state = None
+            cls._by_device[key] = state
+        return cls._by_device[key]
+
+
 def _head(t, name):
     if not t.is_cuda:
         raise RuntimeError("paa_b200 has no CPU path: %s is on %s" % (name, t.device))
@@ -242,8 +285,14 @@ class PAALossComputation(object):
         stream = torch.cuda.current_stream(device).cuda_stream
         with torch.cuda.device(device):
             if world > 1:
+                peer = PeerNormExchange.get(device)
+                if peer is not None:
+                    args.rank = peer.rank
+                    for r, ptr in enumerate(peer.ptrs):
+                        args.peer_norm[r] = ptr
                 _lib.check(self._lib.paa_assign(C.byref(args), stream), "paa_assign")
-                reduce_normalisers(normalisers)                         # loss.py:321,338 in one message
+                if peer is None:
+                    reduce_normalisers(normalisers)                     # loss.py:321,338 in one message
                 _lib.check(self._lib.paa_loss(C.byref(args), stream), "paa_loss")
             else:
                 _lib.check(self._lib.paa_assign_loss(C.byref(args), stream), "paa_assign_loss")

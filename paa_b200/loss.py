@@ -60,23 +60,33 @@ class PeerNormExchange(object):
         self.buffer.zero_()
         self.handle = symm_mem.rendezvous(self.buffer, group=dist.group.WORLD.group_name)
         self.ptrs = [int(p) for p in self.handle.buffer_ptrs]
-        torch.cuda.synchronize(device)
-        dist.barrier()                      # every rank's buffer is zeroed before anyone writes into it
+        torch.cuda.synchronize(device)      # zeroed before the collective in get() lets anyone write into it
 
     @classmethod
     def get(cls, device):
-        """The exchange for `device`, or None when it cannot be used (then the caller all-reduces)."""
+        """The exchange for `device`, or None when it cannot be used (then the caller all-reduces).  The
+        decision is collective: if the set-up fails on any rank, every rank falls back."""
         key = (device.type, device.index)
         if key not in cls._by_device:
             state = None
-            if os.environ.get("PAA_NORM_EXCHANGE", "peer") != "nccl":
+            import torch.distributed as dist
+            usable = (os.environ.get("PAA_NORM_EXCHANGE", "peer") != "nccl" and dist.is_available()
+                      and dist.is_initialized() and dist.get_world_size() == get_num_gpus()
+                      and dist.get_world_size() <= _lib.MAX_PEERS)
+            if usable:
+                why = ""
                 try:
-                    import torch.distributed as dist
-                    if dist.is_available() and dist.is_initialized() and dist.get_world_size() == get_num_gpus():
-                        state = cls(device)
-                except Exception as e:  # noqa: BLE001 - symmetric memory unavailable: use NCCL
-                    import warnings
-                    warnings.warn("paa_b200: peer-memory normaliser exchange unavailable (%s); using all_reduce" % (e,))
+                    state = cls(device)
+                except Exception as e:  # noqa: BLE001 - symmetric memory unavailable on this rank
+                    why = str(e)
+                    state = None
+                ok = torch.tensor([1 if state is not None else 0], dtype=torch.int32, device=device)
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+                if int(ok.item()) == 0:
+                    if state is None:
+                        import warnings
+                        warnings.warn("paa_b200: peer-memory normaliser exchange unavailable (%s); "
+                                      "using all_reduce" % (why,))
                     state = None
             cls._by_device[key] = state
         return cls._by_device[key]

@@ -470,7 +470,8 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 12,
                 "ms_per_step": max(e2e_ms, e2e_wall_ms) / args.steps},
         # our kernels per step: assign_pass1, match_score, select_gmm, bulk_focal, positive_terms, finish_loss
-        "gpu_launches": 6 * args.steps,
+        # (+ norm_wait_kernel with more than one rank)
+        "gpu_launches": (6 + (1 if world > 1 else 0)) * args.steps,
         "roofline": roofline,
         "step_ms_min_med_max": [min(step_ms), statistics.median(step_ms), max(step_ms)],
     }

@@ -419,10 +419,55 @@ post_filter_kernel(const Geometry geo, const uint2* __restrict__ cand, const int
     }
 }
 
+// One step of a most-significant-digit-first radix select over a 256-bin histogram in shared memory:
+// the largest digit d >= 1 with hist[d] + hist[d+1] + ... + hist[255] >= need, or 0 when there is none, and how
+// many entries are still needed among the keys with that digit.  Executed by ONE warp (lane handles eight
+// bins, warp scan over lanes) instead of a serial walk over 255 bins.
+__device__ __forceinline__ void radix_pick_digit(const int* s_hist, int need, int lane, int* digit, int* remaining) {
+    int v[8];
+    int loc = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int bin = 255 - (8 * lane + j);
+        v[j] = bin >= 1 ? s_hist[bin] : 0;                 // digit 0 is the fall-through, not a candidate
+        loc += v[j];
+    }
+    int incl = loc;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(PAA_FULL, incl, o);
+        if (lane >= o) incl += t;
+    }
+    const int excl = incl - loc;                           // entries in the bins above this lane's eight
+    const bool crossing = (excl < need) && (need <= incl);
+    const unsigned m = __ballot_sync(PAA_FULL, crossing);
+    const int total = __shfl_sync(PAA_FULL, incl, 31);
+    int d = 0, rem = need - total;                         // no crossing: digit 0
+    if (m) {
+        const int src = __ffs(m) - 1;
+        if (lane == src) {
+            rem = need - excl;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int bin = 255 - (8 * lane + j);
+                if (d == 0 && bin >= 1) {
+                    if (v[j] >= rem) d = bin;
+                    else rem -= v[j];
+                }
+            }
+        }
+        d = __shfl_sync(PAA_FULL, d, src);
+        rem = __shfl_sync(PAA_FULL, rem, src);
+    }
+    *digit = d;
+    *remaining = rem;
+}
+
 // ---------------------------------------------------------------------------------------------
 // select: finish top-k, canonical order, decode + clip
 // ---------------------------------------------------------------------------------------------
 constexpr int kSelectThreads = 1024;
+constexpr int kSelectCached = 2;            // boundary keys a thread keeps in registers
 
 // key of a candidate for "better first": higher score, then lower candidate index
 __device__ __forceinline__ unsigned long long better_key(uint2 v) {
@@ -456,7 +501,17 @@ post_select_kernel(const Geometry geo, const ImageSizes sizes, const uint2* __re
     const int need = k - above;                 // entries still to take from the boundary bin
 
     if (B > 0 && need > 0) {
-        // exact radix select (8 bits x 8 passes, most significant first) of the `need` best keys
+        // exact radix select (8 bits x 8 passes, most significant first) of the `need` best keys; a thread
+        // keeps its first kSelectCached boundary keys in registers so that the passes do not go back to memory
+        unsigned long long ck[kSelectCached];
+        uint2 cv[kSelectCached];
+#pragma unroll
+        for (int c = 0; c < kSelectCached; ++c) {
+            const int e = threadIdx.x + c * kSelectThreads;
+            cv[c] = make_uint2(0u, 0u);
+            if (e < B) cv[c] = list[blist[e]];
+            ck[c] = better_key(cv[c]);
+        }
         if (threadIdx.x == 0) {
             s_prefix = 0ull;
             s_need = need;
@@ -468,20 +523,22 @@ post_select_kernel(const Geometry geo, const ImageSizes sizes, const uint2* __re
             __syncthreads();
             const unsigned long long prefix = s_prefix;
             const unsigned long long hi_mask = (pass == 0) ? 0ull : (~0ull << (shift + 8));
-            for (int e = threadIdx.x; e < B; e += kSelectThreads) {
+#pragma unroll
+            for (int c = 0; c < kSelectCached; ++c)
+                if (threadIdx.x + c * kSelectThreads < B && (ck[c] & hi_mask) == prefix)
+                    atomicAdd(&s_hist[(int)((ck[c] >> shift) & 0xff)], 1);
+            for (int e = threadIdx.x + kSelectCached * kSelectThreads; e < B; e += kSelectThreads) {
                 const unsigned long long key = better_key(list[blist[e]]);
                 if ((key & hi_mask) == prefix) atomicAdd(&s_hist[(int)((key >> shift) & 0xff)], 1);
             }
             __syncthreads();
-            if (threadIdx.x == 0) {
-                int remaining = s_need;
-                int d = 255;
-                for (; d > 0; --d) {
-                    if (s_hist[d] >= remaining) break;
-                    remaining -= s_hist[d];
+            if (threadIdx.x < 32) {
+                int d, remaining;
+                radix_pick_digit(s_hist, s_need, threadIdx.x, &d, &remaining);
+                if (threadIdx.x == 0) {
+                    s_need = remaining;           // still needed among keys with this digit
+                    s_prefix = prefix | ((unsigned long long)d << shift);
                 }
-                s_need = remaining;           // still needed among keys with this digit
-                s_prefix = prefix | ((unsigned long long)d << shift);
             }
             __syncthreads();
         }
@@ -489,29 +546,51 @@ post_select_kernel(const Geometry geo, const ImageSizes sizes, const uint2* __re
         const unsigned long long tkey = s_prefix;
         if (threadIdx.x == 0) s_fill = 0;
         __syncthreads();
-        for (int e = threadIdx.x; e < B; e += kSelectThreads) {
+#pragma unroll
+        for (int c = 0; c < kSelectCached; ++c)
+            if (threadIdx.x + c * kSelectThreads < B && ck[c] >= tkey) mysel[above + atomicAdd(&s_fill, 1)] = cv[c];
+        for (int e = threadIdx.x + kSelectCached * kSelectThreads; e < B; e += kSelectThreads) {
             const uint2 v = list[blist[e]];
             if (better_key(v) >= tkey) mysel[above + atomicAdd(&s_fill, 1)] = v;
         }
         __syncthreads();
     }
 
-    // canonical order: ascending candidate index (the order nonzero() enumerates them, inference.py:66)
-    for (int t = threadIdx.x; t < k; t += kSelectThreads) {
-        const uint2 v = mysel[t];
+    // canonical order: ascending candidate index (the order nonzero() enumerates them, inference.py:66).
+    // Bitonic sort of the (index, score) pairs in shared memory, padded to a power of two with index ~0.
+    int n2 = 32;
+    while (n2 < k) n2 <<= 1;
+    for (int t = threadIdx.x; t < n2; t += kSelectThreads) {
+        uint2 v = make_uint2(0u, 0xffffffffu);
+        if (t < k) v = mysel[t];
         s_sc[t] = v.x;
         s_idx[t] = v.y;
     }
     __syncthreads();
+    for (int size = 2; size <= n2; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int i = threadIdx.x; i < (n2 >> 1); i += kSelectThreads) {
+                const int pos = 2 * i - (i & (stride - 1));
+                const unsigned a = s_idx[pos], b = s_idx[pos + stride];
+                const bool ascending = (pos & size) == 0;
+                if ((a > b) == ascending) {
+                    s_idx[pos] = b;
+                    s_idx[pos + stride] = a;
+                    const unsigned sa = s_sc[pos];
+                    s_sc[pos] = s_sc[pos + stride];
+                    s_sc[pos + stride] = sa;
+                }
+            }
+            __syncthreads();
+        }
+    }
     const float img_w = sizes.wh[n][0], img_h = sizes.wh[n][1];
     int dropped = 0;
     for (int t0 = 0; t0 < k; t0 += kSelectThreads) {
-        const int t = t0 + threadIdx.x;
+        const int t = t0 + threadIdx.x;            // = rank of the candidate
         bool drop = false;
         if (t < k) {
             const unsigned my_idx = s_idx[t];
-            int rank = 0;
-            for (int q = 0; q < k; ++q) rank += (s_idx[q] < my_idx) ? 1 : 0;
             const int i = (int)(my_idx / (unsigned)geo.C);
             const float4 a = ldg4(lv.anchors + (size_t)n * geo.anchor_image_stride + (size_t)i * 4);
             const float* rp = lv.reg + head_offset(n, i, 0, 4, geo.apl, lv.hw);
@@ -525,8 +604,8 @@ post_select_kernel(const Geometry geo, const ImageSizes sizes, const uint2* __re
             const float ws = __fadd_rn(__fsub_rn(box.z, box.x), 1.0f);    // boxlist_ops.py:62-76
             const float hs = __fadd_rn(__fsub_rn(box.w, box.y), 1.0f);
             drop = !((ws >= min_size) && (hs >= min_size));
-            s_keep[rank] = drop ? 0 : 1;
-            const size_t o = (size_t)seg * topn + rank;
+            s_keep[t] = drop ? 0 : 1;
+            const size_t o = (size_t)seg * topn + t;
             pre_box[o] = box;
             pre_score[o] = __uint_as_float(s_sc[t]);
             pre_label[o] = (int)(my_idx % (unsigned)geo.C) + 1;           // inference.py:69
@@ -906,15 +985,13 @@ post_finish_kernel(int L, int topn, int det_per_img, int skip_nms, const int* __
                 if ((key & hi_mask) == prefix) atomicAdd(&s_hist[(key >> shift) & 0xff], 1);
             }
             __syncthreads();
-            if (threadIdx.x == 0) {
-                int remaining = s_need;
-                int d = 255;
-                for (; d > 0; --d) {
-                    if (s_hist[d] >= remaining) break;
-                    remaining -= s_hist[d];
+            if (threadIdx.x < 32) {
+                int d, remaining;
+                radix_pick_digit(s_hist, s_need, threadIdx.x, &d, &remaining);
+                if (threadIdx.x == 0) {
+                    s_need = remaining;
+                    s_prefix = prefix | ((unsigned)d << shift);
                 }
-                s_need = remaining;
-                s_prefix = prefix | ((unsigned)d << shift);
             }
             __syncthreads();
         }

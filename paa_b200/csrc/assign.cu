@@ -122,17 +122,41 @@ __device__ __forceinline__ void iou_best_block(const Geometry& geo, const GtOffs
                 hit = (w > 0.0f) && (h > 0.0f);
             }
             unsigned m = __ballot_sync(PAA_FULL, hit);
+            // four hit GTs per trip: their IoUs, warp maxima and shared-memory updates are independent chains
+            // (a coarse-level warp of a crowded image walks hundreds of hits; one at a time that walk is the
+            // tail of the whole kernel).  The first-maximum rule is kept by folding them in ascending order.
             while (m) {
-                const int j = g0 + __ffs(m) - 1;
-                m &= m - 1;
-                float qv = 0.0f;
-                if (valid) qv = iou_plus1(sm.iou.gt[j], sm.iou.area[j], a, area_a);
-                if (qv > best_v) {
-                    best_v = qv;
-                    best_g = c0 + j;
+                int js[4];
+                float qv[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    js[u] = -1;
+                    if (m) {
+                        js[u] = g0 + __ffs(m) - 1;
+                        m &= m - 1;
+                    }
                 }
-                unsigned wm = __reduce_max_sync(PAA_FULL, __float_as_uint(qv));
-                if (lane == 0 && wm != 0u) atomicMax(&sm.iou.max[j], wm);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int j = js[u] >= 0 ? js[u] : 0;
+                    const float v = iou_plus1_flat(sm.iou.gt[j], sm.iou.area[j], a, area_a);
+                    qv[u] = (js[u] >= 0 && valid) ? v : 0.0f;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (qv[u] > best_v) {
+                        best_v = qv[u];
+                        best_g = c0 + js[u];
+                    }
+                }
+                unsigned wm[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) wm[u] = __reduce_max_sync(PAA_FULL, __float_as_uint(qv[u]));
+                if (lane == 0) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (js[u] >= 0 && wm[u] != 0u) atomicMax(&sm.iou.max[js[u]], wm[u]);
+                }
             }
         }
         __syncthreads();

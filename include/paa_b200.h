@@ -183,6 +183,20 @@ int paa_sigmoid_focal_loss_backward(const float* logits, const int32_t* targets,
                                     int n, int num_classes, float gamma, float alpha, float* d_logits,
                                     void* stream);
 
+/* ---- operators on either side of the path ----------------------------------------- */
+/* AnchorGenerator.grid_anchors (anchor_generator.py:73-95) for one level: out[(y*W + x)*a + k] =
+ * cell_anchors[k] + (x*stride, y*stride, x*stride, y*stride), float32 like torch.arange(0, W*stride, stride).
+ * cell_anchors [a, 4] and out [H*W*a, 4] are device pointers (out 16-byte aligned). */
+int paa_grid_anchors(const float* cell_anchors, int anchors_per_loc, int grid_h, int grid_w, float stride,
+                     float* out_anchors, void* stream);
+/* AnchorGenerator.add_visibility_to (anchor_generator.py:97-110): out[i] = anchor i lies inside the image
+ * grown by straddle_thresh (all ones when straddle_thresh < 0). */
+int paa_anchor_visibility(const float* anchors, int64_t n, float image_w, float image_h, float straddle_thresh,
+                          uint8_t* out, void* stream);
+/* boxlist_iou (structures/boxlist_ops.py:81-116): out [n1, n2] row-major, "+1" convention, the reference's
+ * float32 operation order (bit-exact).  Callers check the BoxList sizes (boxlist_ops.py:95-97). */
+int paa_boxlist_iou(const float* boxes1, int n1, const float* boxes2, int n2, float* out, void* stream);
+
 /* Measurement aid (not on the reference's interface): while enabled, every launch of the chosen kernel
  * is bracketed by CUDA events on its own stream; paa_kernel_timing_end waits for them and returns the
  * summed device time and the number of launches.  Do not enable during CUDA-graph capture. */

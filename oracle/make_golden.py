@@ -190,8 +190,47 @@ def record_nms_kats():
     return out
 
 
+ANCHOR_CASES = [
+    # name, PAA cfg overrides, padded (H, W) of the batch, per-image (h, w)
+    ("paa_default", dict(), (96, 128), [(96, 128), (80, 100)]),
+    ("multi_ratio_scale", dict(ASPECT_RATIOS=(0.5, 1.0, 2.0), SCALES_PER_OCTAVE=3, STRADDLE_THRESH=8,
+                               ANCHOR_SIZES=(32, 64, 128), ANCHOR_STRIDES=(8, 16, 32)), (64, 96), [(64, 96), (50, 70)]),
+    ("no_straddle_check", dict(STRADDLE_THRESH=-1), (64, 64), [(64, 64)]),
+]
+
+
+def record_anchor_cases():
+    """Anchors (and their visibility fields) produced by the reference's own AnchorGenerator
+    (modeling/rpn/anchor_generator.py:112-125,192-212) on CPU feature maps of the given sizes."""
+    from types import SimpleNamespace
+    ref = ref_shim.load_reference()
+    out = {}
+    for name, over, padded, sizes in ANCHOR_CASES:
+        cfg = ref_shim.make_cfg(**over)
+        gen = ref.make_anchor_generator_paa(cfg)
+        strides = cfg.MODEL.PAA.ANCHOR_STRIDES
+        grids = synthetic.level_grids(padded[0], padded[1], strides)
+        fmaps = [torch.zeros((len(sizes), 1, h, w)) for (h, w) in grids]
+        anchors = gen(SimpleNamespace(image_sizes=sizes), fmaps)
+        out[name + "_grids"] = np.asarray(grids, np.int64)
+        for i, per_image in enumerate(anchors):
+            for l, bl in enumerate(per_image):
+                if i == 0:
+                    out["%s_l%d" % (name, l)] = bl.bbox.numpy().astype(np.float32)
+                out["%s_vis_i%d_l%d" % (name, i, l)] = bl.get_field("visibility").numpy().astype(np.uint8)
+    return out
+
+
 def main():
     os.makedirs(GOLDEN_DIR, exist_ok=True)
+    if "--anchors-only" in sys.argv:
+        a = record_anchor_cases()
+        np.savez_compressed(os.path.join(GOLDEN_DIR, "anchors.npz"), **a)
+        print("anchors", len(a), "arrays")
+        return 0
+    a = record_anchor_cases()
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "anchors.npz"), **a)
+    print("anchors", len(a), "arrays")
     kats = record_nms_kats()
     np.savez_compressed(os.path.join(GOLDEN_DIR, "nms_kat.npz"), **kats)
     print("nms_kat", int(kats["n_cases"]), "cases")

@@ -23,7 +23,10 @@ from oracle.paa_oracle import decode, iou_matrix
 
 def default_params(**kw):
     p = dict(pre_nms_thresh=0.05, pre_nms_top_n=1000, nms_thresh=0.6, detections_per_img=100,
-             num_classes=81, score_voting=True, min_size=0, skip_nms=False)
+             num_classes=81, score_voting=True, min_size=0, skip_nms=False,
+             # "atss": rpn/atss/inference.py:33-80 -- per-level top-k on sigmoid(cls) * sigmoid(centerness),
+             # square root taken on the selected scores; no score voting (set score_voting=False with it)
+             flavour="paa")
     p.update(kw)
     return SimpleNamespace(**p)
 
@@ -35,13 +38,18 @@ def level_candidates(box_cls, box_regression, iou_pred, anchors, image_sizes, pr
     reg = box_regression.permute(0, 2, 3, 1).reshape(N, -1, 4)                  # :45-46
     cand = prob > prm.pre_nms_thresh                                            # :48
     k_per_im = cand.reshape(N, -1).sum(1).clamp(max=prm.pre_nms_top_n)          # :49-50
+    atss = getattr(prm, "flavour", "paa") == "atss"
     if iou_pred is not None:
         q = iou_pred.permute(0, 2, 3, 1).reshape(N, -1).sigmoid()               # :54-55
-        prob = (prob * q[:, :, None]).sqrt()                                    # :56
+        prob = prob * q[:, :, None]                                             # atss/inference.py:53
+        if not atss:
+            prob = prob.sqrt()                                                  # :56
     out = []
     for i in range(N):
         s = prob[i][cand[i]]                                                    # :62
         s, pick = s.topk(int(k_per_im[i]), sorted=False)                        # :64
+        if atss:
+            s = torch.sqrt(s)                                                   # atss/inference.py:75
         where = cand[i].nonzero()[pick, :]                                      # :66
         loc = where[:, 0]
         labels = where[:, 1] + 1                                                # :69

@@ -7,10 +7,11 @@ the factories of paa_core/modeling/rpn/paa/{loss,inference}.py that ``PAAModule.
 """
 from paa_b200.box_coder import BoxCoder
 from paa_b200.config import default_cfg
-from paa_b200.structures import BoxList, cat_boxlist
+from paa_b200.structures import BoxList, boxlist_iou, cat_boxlist
 
-__all__ = ["BoxCoder", "BoxList", "cat_boxlist", "default_cfg", "make_paa_loss_evaluator",
-           "make_paa_postprocessor", "PAALossComputation", "PAAPostProcessor"]
+__all__ = ["BoxCoder", "BoxList", "boxlist_iou", "cat_boxlist", "default_cfg", "make_paa_loss_evaluator",
+           "make_paa_postprocessor", "PAALossComputation", "PAAPostProcessor", "make_anchor_generator_paa",
+           "AnchorGenerator", "make_atss_postprocessor", "ATSSPostProcessor"]
 
 
 def __getattr__(name):
@@ -19,7 +20,10 @@ def __getattr__(name):
     if name in ("make_paa_loss_evaluator", "PAALossComputation"):
         from paa_b200 import loss
         return getattr(loss, name)
-    if name in ("make_paa_postprocessor", "PAAPostProcessor"):
+    if name in ("make_paa_postprocessor", "PAAPostProcessor", "make_atss_postprocessor", "ATSSPostProcessor"):
         from paa_b200 import inference
         return getattr(inference, name)
+    if name in ("make_anchor_generator_paa", "AnchorGenerator"):
+        from paa_b200 import anchor_generator
+        return getattr(anchor_generator, name)
     raise AttributeError(name)

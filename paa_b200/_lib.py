@@ -80,6 +80,10 @@ SYMBOLS = {
                                                  C.c_float, C.c_void_p, C.c_void_p]),
     "paa_sigmoid_focal_loss_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                                   C.c_float, C.c_float, C.c_void_p, C.c_void_p]),
+    "paa_grid_anchors": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p]),
+    "paa_anchor_visibility": (C.c_int, [C.c_void_p, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_void_p,
+                                        C.c_void_p]),
+    "paa_boxlist_iou": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "paa_kernel_timing_begin": (C.c_int, [C.c_int]),
     "paa_kernel_timing_end": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
 }

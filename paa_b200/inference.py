@@ -137,6 +137,41 @@ def make_paa_postprocessor(config, box_coder):
     )
 
 
+class ATSSPostProcessor(PAAPostProcessor):
+    """``paa_core/modeling/rpn/atss/inference.py:9-119`` on the same kernels: the ATSS head's
+    third output is a centerness map where PAA's is an IoU prediction, both enter the score as
+    ``sqrt(sigmoid(cls) * sigmoid(third))``, the threshold is applied to ``sigmoid(cls)`` alone, and there is no
+    score voting.  (ATSS ranks the per-level top-k by the product and takes the square root afterwards,
+    atss/inference.py:53-75; the square root is monotone, so the selected set is the same unless two distinct
+    products at the k-th place round to the same float32 root.)"""
+
+    def __init__(self, pre_nms_thresh, pre_nms_top_n, nms_thresh, fpn_post_nms_top_n, min_size, num_classes,
+                 box_coder, bbox_aug_enabled=False, bbox_aug_vote=False):
+        super(ATSSPostProcessor, self).__init__(pre_nms_thresh, pre_nms_top_n, nms_thresh, fpn_post_nms_top_n,
+                                                min_size, num_classes, box_coder, bbox_aug_enabled, bbox_aug_vote,
+                                                score_voting=False)
+
+    def forward(self, box_cls, box_regression, centerness, anchors):
+        if centerness is None:
+            raise RuntimeError("ATSSPostProcessor needs the centerness maps")
+        return super(ATSSPostProcessor, self).forward(box_cls, box_regression, centerness, anchors)
+
+
+def make_atss_postprocessor(config, box_coder):
+    """atss/inference.py:122-137."""
+    return ATSSPostProcessor(
+        pre_nms_thresh=config.MODEL.ATSS.INFERENCE_TH,
+        pre_nms_top_n=config.MODEL.ATSS.PRE_NMS_TOP_N,
+        nms_thresh=config.MODEL.ATSS.NMS_TH,
+        fpn_post_nms_top_n=config.TEST.DETECTIONS_PER_IMG,
+        min_size=0,
+        num_classes=config.MODEL.ATSS.NUM_CLASSES,
+        bbox_aug_enabled=config.TEST.BBOX_AUG.ENABLED,
+        box_coder=box_coder,
+        bbox_aug_vote=config.TEST.BBOX_AUG.VOTE,
+    )
+
+
 def ml_nms(boxes, scores, labels, nms_thresh):
     """Device replacement for ``paa_core._C.ml_nms`` (csrc/ml_nms.h:10-27): indices of the kept boxes,
     ascending.  boxes [n,4] float32 cuda, scores [n], labels [n] (any float/int dtype, integer valued)."""

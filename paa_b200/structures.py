@@ -96,3 +96,24 @@ def cat_boxlist(bboxes):
     for f in fields:
         out.add_field(f, torch.cat([b.get_field(f) for b in bboxes], dim=0))
     return out
+
+
+def boxlist_iou(boxlist1, boxlist2):
+    """Pairwise IoU of two BoxLists on the device, ``[N, M]`` (boxlist_ops.py:81-116: "+1" convention,
+    the reference's float32 operation order, so equality tests against it are bit-exact).  The consumer of
+    this in the reference is the COCO evaluation and the test-time-augmentation voting."""
+    if boxlist1.size != boxlist2.size:
+        raise RuntimeError("boxlists should have same image size, got {}, {}".format(boxlist1, boxlist2))
+    from paa_b200 import _lib
+    lib = _lib.load()
+    b1 = boxlist1.convert("xyxy").bbox
+    b2 = boxlist2.convert("xyxy").bbox
+    if not b1.is_cuda or not b2.is_cuda:
+        raise RuntimeError("paa_b200 has no CPU path: boxlist_iou needs CUDA tensors")
+    b1 = b1.to(torch.float32).contiguous()
+    b2 = b2.to(device=b1.device, dtype=torch.float32).contiguous()
+    out = torch.empty((b1.shape[0], b2.shape[0]), dtype=torch.float32, device=b1.device)
+    with torch.cuda.device(b1.device):
+        _lib.check(lib.paa_boxlist_iou(b1.data_ptr(), b1.shape[0], b2.data_ptr(), b2.shape[0], out.data_ptr(),
+                                       torch.cuda.current_stream(b1.device).cuda_stream), "paa_boxlist_iou")
+    return out

@@ -233,6 +233,15 @@ int paa_assign(const PaaLossArgs* args, void* stream_) {
     if (rc) return rc;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     PAA_CUDA_CHECK(cudaMemsetAsync(args->workspace, 0, p.ws.zero_bytes, stream));
+    {
+        // the coarse levels' best-GT keys are merged with atomicMax when their GT list is cut into parts
+        const int hl = first_heavy_level(p.geo);
+        if (hl < p.geo.num_levels && gt_parts(p.go, args->num_images) > 1) {
+            const size_t a0 = (size_t)p.geo.lv[hl].a_off, n_heavy = (size_t)p.geo.A - a0;
+            PAA_CUDA_CHECK(cudaMemset2DAsync(reinterpret_cast<char*>(p.ws.best) + a0 * 8, (size_t)p.geo.A * 8, 0,
+                                             n_heavy * 8, (size_t)args->num_images, stream));
+        }
+    }
     if ((rc = launch_assign_pass1(p.geo, p.go, args->gt_boxes, p.sc, p.ws, stream))) return rc;
     const float* score_src = args->teacher_combined_loss ? args->teacher_combined_loss : p.ws.score;
     if ((rc = launch_match_score(p.geo, p.go, args->gt_boxes, args->gt_labels, p.sc, p.ws,

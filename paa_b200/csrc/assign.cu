@@ -49,9 +49,22 @@ struct Pass1Plan {
     unsigned item_off[PAA_MAX_LEVELS + 1];   // class sums: first work item of each level
     unsigned chunks[PAA_MAX_LEVELS];         //             chunks per image
     unsigned char vec[PAA_MAX_LEVELS];       //             float4 path
-    unsigned sum_blocks, iou_blocks;         // iou_blocks = num_images * ceil(tiles_per_image / 2)
-    int pairs_per_image;
+    unsigned sum_blocks, iou_blocks;
+    // IoU matching: tiles below `light_tiles` (fine levels) go two to a block over all GTs of the image; the
+    // tiles of the coarse levels, whose anchors overlap every GT, are additionally cut into `parts` ranges of
+    // the GT list (their per-anchor results meet in an atomicMax), so that no warp walks hundreds of GTs alone
+    int light_tiles, light_pairs, heavy_pairs, parts;
 };
+
+// (IoU bits, GT) of an anchor's best GT as one 64-bit key whose integer order is "larger IoU, then smaller GT
+// index" -- the first-maximum rule of torch.max(dim=0) (matcher.py:47) under atomicMax.  Key 0 = no GT seen.
+__device__ __forceinline__ unsigned long long pack_best(float v, int g) {
+    return ((unsigned long long)__float_as_uint(v) << 32) | (unsigned long long)(0xffffffffu - (unsigned)g);
+}
+__device__ __forceinline__ void unpack_best(unsigned long long key, float* v, int* g) {
+    *v = __uint_as_float((unsigned)(key >> 32));
+    *g = key == 0ull ? 0 : (int)(0xffffffffu - (unsigned)(key & 0xffffffffull));
+}
 
 // One negative-class focal term without its (1-alpha) factor: p^gamma * softplus(x).
 __device__ __forceinline__ float neg_term_only(float x, float gamma, bool g2) {
@@ -77,15 +90,30 @@ union Pass1Smem {
 };
 
 __device__ __forceinline__ void iou_best_block(const Geometry& geo, const GtOffsets& go, unsigned q,
-                                               int pairs_per_image, const float* __restrict__ gt_boxes,
-                                               unsigned* __restrict__ gtmax, uint2* __restrict__ best,
+                                               const Pass1Plan& plan, const float* __restrict__ gt_boxes,
+                                               unsigned* __restrict__ gtmax, unsigned long long* __restrict__ best,
                                                Pass1Smem& sm) {
     // heaviest blocks first: the coarse levels (last tiles of an image) intersect every GT, and the
     // cost of a block grows with the GT count of its image
-    const int n = go.by_load[q % geo.num_images];
-    const int pair = pairs_per_image - 1 - (int)(q / geo.num_images);
-    const int tile = 2 * pair + (threadIdx.x >> 7);
-    const bool tile_ok = tile < geo.tiles_per_image;
+    const unsigned heavy_items = (unsigned)geo.num_images * (unsigned)plan.heavy_pairs * (unsigned)plan.parts;
+    int n, tile0, tile_end, part = 0, parts = 1;
+    bool split = false;
+    if (q < heavy_items) {
+        n = go.by_load[q % geo.num_images];
+        const unsigned r = q / geo.num_images;
+        parts = plan.parts;
+        part = (int)(r % (unsigned)parts);
+        tile0 = plan.light_tiles + 2 * (plan.heavy_pairs - 1 - (int)(r / (unsigned)parts));
+        tile_end = geo.tiles_per_image;
+        split = parts > 1;
+    } else {
+        const unsigned r = q - heavy_items;
+        n = go.by_load[r % geo.num_images];
+        tile0 = 2 * (plan.light_pairs - 1 - (int)(r / geo.num_images));
+        tile_end = plan.light_tiles;
+    }
+    const int tile = tile0 + (threadIdx.x >> 7);
+    const bool tile_ok = tile < tile_end;
     int first = 0;
     const int l = tile_ok ? tile_level(geo, tile, &first) : 0;
     const LevelView& lv = geo.lv[l];
@@ -99,11 +127,13 @@ __device__ __forceinline__ void iou_best_block(const Geometry& geo, const GtOffs
     const float wx1 = warp_min(a.x), wy1 = warp_min(a.y), wx2 = warp_max(a.z), wy2 = warp_max(a.w);
 
     const int gbase = go.v[n];
-    const int G = go.v[n + 1] - gbase;
+    const int G_all = go.v[n + 1] - gbase;
+    const int g_lo = (int)(((long long)G_all * part) / parts), G = (int)(((long long)G_all * (part + 1)) / parts);
     float best_v = 0.0f;
     int best_g = 0;
+    const bool crowded = G_all > 128;
 
-    for (int c0 = 0; c0 < G; c0 += kGtChunk) {
+    for (int c0 = g_lo; c0 < G; c0 += kGtChunk) {
         const int cnt = min(kGtChunk, G - c0);
         for (int t = threadIdx.x; t < cnt; t += kPassThreads) {
             float4 b = ldg4(gt_boxes + (size_t)(gbase + c0 + t) * 4);
@@ -122,9 +152,25 @@ __device__ __forceinline__ void iou_best_block(const Geometry& geo, const GtOffs
                 hit = (w > 0.0f) && (h > 0.0f);
             }
             unsigned m = __ballot_sync(PAA_FULL, hit);
-            // four hit GTs per trip: their IoUs, warp maxima and shared-memory updates are independent chains
-            // (a coarse-level warp of a crowded image walks hundreds of hits; one at a time that walk is the
-            // tail of the whole kernel).  The first-maximum rule is kept by folding them in ascending order.
+            if (!crowded) {
+                // the usual image (up to ~100 GTs): a handful of hits per warp, one at a time
+                while (m) {
+                    const int j = g0 + __ffs(m) - 1;
+                    m &= m - 1;
+                    float qv = 0.0f;
+                    if (valid) qv = iou_plus1(sm.iou.gt[j], sm.iou.area[j], a, area_a);
+                    if (qv > best_v) {
+                        best_v = qv;
+                        best_g = c0 + j;
+                    }
+                    unsigned wm = __reduce_max_sync(PAA_FULL, __float_as_uint(qv));
+                    if (lane == 0 && wm != 0u) atomicMax(&sm.iou.max[j], wm);
+                }
+                continue;
+            }
+            // crowded image: four hit GTs per trip -- their IoUs (branch-free form), warp maxima and
+            // shared-memory updates are independent chains, so the walk over hundreds of hits is no longer one
+            // long dependent chain.  The first-maximum rule is kept by folding them in ascending order.
             while (m) {
                 int js[4];
                 float qv[4];
@@ -164,7 +210,11 @@ __device__ __forceinline__ void iou_best_block(const Geometry& geo, const GtOffs
             if (sm.iou.max[t] != 0u) atomicMax(&gtmax[gbase + c0 + t], sm.iou.max[t]);
         __syncthreads();
     }
-    if (valid) best[(size_t)n * geo.A + lv.a_off + i] = make_uint2(__float_as_uint(best_v), (unsigned)best_g);
+    if (valid) {
+        unsigned long long* dst = best + (size_t)n * geo.A + lv.a_off + i;
+        if (!split) *dst = pack_best(best_v, best_g);
+        else if (best_v > 0.0f) atomicMax(dst, pack_best(best_v, best_g));     // pre-zeroed by paa_assign
+    }
 }
 
 template <bool kG2>
@@ -243,7 +293,7 @@ template <bool kG2>
 __global__ void __launch_bounds__(kPassThreads, 6)
 assign_pass1_kernel(const Geometry geo, const GtOffsets go, const Pass1Plan plan, float gamma,
                     const float* __restrict__ gt_boxes, unsigned* __restrict__ gtmax,
-                    uint2* __restrict__ best, float* __restrict__ negsum) {
+                    unsigned long long* __restrict__ best, float* __restrict__ negsum) {
     __shared__ Pass1Smem sm;
     // the first 2*min(sum_blocks, iou_blocks) blocks alternate between the jobs, the rest belong to the longer one
     const unsigned m = min(plan.sum_blocks, plan.iou_blocks);
@@ -257,8 +307,24 @@ assign_pass1_kernel(const Geometry geo, const GtOffsets go, const Pass1Plan plan
         is_iou = plan.iou_blocks > plan.sum_blocks;
         idx = b - m;
     }
-    if (is_iou) iou_best_block(geo, go, idx, plan.pairs_per_image, gt_boxes, gtmax, best, sm);
+    if (is_iou) iou_best_block(geo, go, idx, plan, gt_boxes, gtmax, best, sm);
     else class_sum_block<kG2>(geo, plan, idx, gamma, negsum, sm);
+}
+
+// Levels from this one on are "coarse": few, large anchors that overlap (nearly) every GT of the image.
+int first_heavy_level(const Geometry& geo) {
+    int l = geo.num_levels;
+    while (l > 0 && geo.lv[l - 1].n_anchor <= 2048) --l;
+    return l;
+}
+
+// Number of GT-list parts for the coarse tiles: about 128 GTs per part for the busiest image, at most 8
+// (one part, i.e. no split and no atomics, for the usual <= 100 GTs per image).
+int gt_parts(const GtOffsets& go, int num_images) {
+    int gmax = 1;
+    for (int i = 0; i < num_images; ++i) gmax = gmax > go.v[i + 1] - go.v[i] ? gmax : go.v[i + 1] - go.v[i];
+    int p = (gmax + 127) / 128;
+    return p < 1 ? 1 : (p > 8 ? 8 : p);
 }
 
 int launch_assign_pass1(const Geometry& geo, const GtOffsets& go, const float* gt_boxes, const LossScalars& sc,
@@ -279,16 +345,20 @@ int launch_assign_pass1(const Geometry& geo, const GtOffsets& go, const float* g
     }
     plan.item_off[PAA_MAX_LEVELS] = items;
     plan.sum_blocks = items;
-    plan.pairs_per_image = (geo.tiles_per_image + 1) / 2;
-    plan.iou_blocks = (unsigned)geo.num_images * (unsigned)plan.pairs_per_image;
+    const int heavy_level = first_heavy_level(geo);
+    plan.light_tiles = heavy_level < geo.num_levels ? geo.lv[heavy_level].tile_off : geo.tiles_per_image;
+    plan.light_pairs = (plan.light_tiles + 1) / 2;
+    plan.heavy_pairs = (geo.tiles_per_image - plan.light_tiles + 1) / 2;
+    plan.parts = gt_parts(go, geo.num_images);
+    plan.iou_blocks = (unsigned)geo.num_images * (unsigned)(plan.light_pairs + plan.heavy_pairs * plan.parts);
     const unsigned grid = plan.sum_blocks + plan.iou_blocks;
     KernelTimer timer(PAA_KERNEL_PASS1, stream);
     if (sc.gamma == 2.0f)
-        assign_pass1_kernel<true><<<grid, kPassThreads, 0, stream>>>(geo, go, plan, sc.gamma, gt_boxes, ws.gtmax,
-                                                                     ws.best, ws.negsum);
+        assign_pass1_kernel<true><<<grid, kPassThreads, 0, stream>>>(
+            geo, go, plan, sc.gamma, gt_boxes, ws.gtmax, reinterpret_cast<unsigned long long*>(ws.best), ws.negsum);
     else
-        assign_pass1_kernel<false><<<grid, kPassThreads, 0, stream>>>(geo, go, plan, sc.gamma, gt_boxes, ws.gtmax,
-                                                                      ws.best, ws.negsum);
+        assign_pass1_kernel<false><<<grid, kPassThreads, 0, stream>>>(
+            geo, go, plan, sc.gamma, gt_boxes, ws.gtmax, reinterpret_cast<unsigned long long*>(ws.best), ws.negsum);
     PAA_LAUNCH_CHECK("assign_pass1_kernel");
     return 0;
 }
@@ -315,7 +385,8 @@ __device__ __forceinline__ float from_ordered_bits(unsigned u) {
 __global__ void __launch_bounds__(PAA_TILE)
 match_score_kernel(const Geometry geo, const GtOffsets go, const float* __restrict__ gt_boxes,
                    const int64_t* __restrict__ gt_labels, const unsigned* __restrict__ gtmax,
-                   const uint2* __restrict__ best, const float* __restrict__ negsum, const LossScalars sc,
+                   const unsigned long long* __restrict__ best, const float* __restrict__ negsum,
+                   const LossScalars sc,
                    int* __restrict__ matched, float* __restrict__ score, int* __restrict__ paa_label, uint4* __restrict__ tile_gtmask,
                    int* __restrict__ seg_count, unsigned long long* __restrict__ seg_pool,
                    const float* __restrict__ teacher_score, const LossDebug dbg) {
@@ -336,16 +407,16 @@ match_score_kernel(const Geometry geo, const GtOffsets go, const float* __restri
     const float thr = sc.iou_threshold;
 
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-    uint2 bv = make_uint2(0u, 0u);
+    float bval = 0.0f;
+    int bgt = 0;
     const size_t flat = (size_t)n * geo.A + lv.a_off + (valid ? i : 0);
     if (valid) {
         a = ldg4(lv.anchors + (size_t)n * geo.anchor_image_stride + (size_t)i * 4);
-        bv = best[flat];
+        unpack_best(best[flat], &bval, &bgt);
     }
     const float area_a = area_plus1(a);
-    const float bval = __uint_as_float(bv.x);
-    int m = (bval >= thr) ? (int)bv.y : -1;
-    if (!(bval >= thr) && !(bval < thr)) m = (int)bv.y;   // NaN: neither below nor restored -> keeps argmax
+    int m = (bval >= thr) ? bgt : -1;
+    if (!(bval >= thr) && !(bval < thr)) m = bgt;          // NaN: neither below nor restored -> keeps argmax
 
     // low-quality GTs (max IoU below thr) restore their best anchors
     for (int c0 = 0; c0 < G; c0 += PAA_TILE) {
@@ -363,7 +434,7 @@ match_score_kernel(const Geometry geo, const GtOffsets go, const float* __restri
                 const int gg = s_lq[k];
                 const float4 b = ldg4(gt_boxes + (size_t)(gbase + gg) * 4);
                 const float q = iou_plus1(b, area_plus1(b), a, area_a);
-                if (q == __uint_as_float(gtmax[gbase + gg])) m = (int)bv.y;
+                if (q == __uint_as_float(gtmax[gbase + gg])) m = bgt;
             }
         }
         __syncthreads();
@@ -423,7 +494,8 @@ int launch_match_score(const Geometry& geo, const GtOffsets& go, const float* gt
                        const float* teacher_score, const LossDebug& dbg, cudaStream_t stream) {
     int grid = geo.num_images * geo.tiles_per_image;
     KernelTimer timer(PAA_KERNEL_MATCH_SCORE, stream);
-    match_score_kernel<<<grid, PAA_TILE, 0, stream>>>(geo, go, gt_boxes, gt_labels, ws.gtmax, ws.best, ws.negsum,
+    match_score_kernel<<<grid, PAA_TILE, 0, stream>>>(geo, go, gt_boxes, gt_labels, ws.gtmax,
+                                                      reinterpret_cast<const unsigned long long*>(ws.best), ws.negsum,
                                                       sc, ws.matched, ws.score, ws.paa_label, ws.tile_gtmask,
                                                       ws.seg_count, ws.seg_pool, teacher_score, dbg);
     PAA_LAUNCH_CHECK("match_score_kernel");

@@ -33,6 +33,8 @@ struct LossDebug {
 };
 
 // assign.cu
+int first_heavy_level(const Geometry& geo);
+int gt_parts(const GtOffsets& go, int num_images);
 int launch_assign_pass1(const Geometry& geo, const GtOffsets& go, const float* gt_boxes, const LossScalars& sc,
                         const LossWorkspace& ws, cudaStream_t stream);
 int launch_match_score(const Geometry& geo, const GtOffsets& go, const float* gt_boxes,

@@ -814,16 +814,18 @@ select_gmm_kernel(const Geometry geo, const GtOffsets go, int num_gt_total,
         if (cls_label > 0) {                   // loss.py:166 requires a positive IoU label
             const LevelView& lv = geo.lv[l];
             const int seg = gi * geo.num_levels + l;
+            // the pool's first 128 slots are fetched together with its fill count (slots past the count hold
+            // stale keys and are masked once the count is known): one memory round trip instead of two
+            const unsigned long long* pool = seg_pool + (size_t)seg * kSegCap;
             const int seg_n = __ldg(seg_count + seg);
+            unsigned long long k4[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) k4[r] = __ldg(pool + r * PAA_WARP + lane);
             if (seg_n <= sc.seg_cap) {
                 // normal case: the anchors matched to this (GT, level) were pooled by match_score_kernel
-                const unsigned long long* pool = seg_pool + (size_t)seg * kSegCap;
-                unsigned long long k4[4];
 #pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    const int j = r * PAA_WARP + lane;
-                    k4[r] = (j < seg_n) ? __ldg(pool + j) : kEmptyKey;
-                }
+                for (int r = 0; r < 4; ++r)
+                    if (r * PAA_WARP + lane >= seg_n) k4[r] = kEmptyKey;
                 if (seg_n > 0) mine = topk_first_batch(k4[0], K, lane, s_level[l]);
 #pragma unroll
                 for (int r = 1; r < 4; ++r)
@@ -984,10 +986,23 @@ select_gmm_kernel(const Geometry geo, const GtOffsets go, int num_gt_total,
     my_ticket = __shfl_sync(PAA_FULL, my_ticket, 0);
     if (my_ticket == gridDim.x - 1) {
         __threadfence();
+        // eight independent loads per lane in flight (this runs after the slowest fit: it is pure kernel tail);
+        // the order of the additions is fixed, so the totals are reproducible
         double cnt = 0.0, sum = 0.0;
-        for (int g = lane; g < num_gt_total; g += PAA_WARP) {
-            cnt += (double)__ldcg(part_npos + g);
-            sum += __ldcg(part_siou + g);
+        for (int g0 = lane; g0 < num_gt_total; g0 += 8 * PAA_WARP) {
+            int c[8];
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int g = g0 + u * PAA_WARP;
+                c[u] = g < num_gt_total ? __ldcg(part_npos + g) : 0;
+                v[u] = g < num_gt_total ? __ldcg(part_siou + g) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                cnt += (double)c[u];
+                sum += v[u];
+            }
         }
         cnt = warp_sum(cnt);
         sum = warp_sum(sum);

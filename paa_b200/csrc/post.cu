@@ -144,7 +144,7 @@ __device__ __forceinline__ int score_bin(float s) {
 constexpr int kCandThreads = 256;
 constexpr int kCandVecs = 4;                                     // float4 per thread per chunk
 constexpr int kCandChunk = kCandThreads * kCandVecs * 4;        // elements per chunk
-constexpr int kCandDrainAt = 512;                                // drain when at least this many are queued
+constexpr int kCandDrainAt = 384;                                // drain when at least this many are queued
 constexpr int kCandQueue = kCandDrainAt + kCandChunk;            // queue capacity
 constexpr int kCandBlocksPerSM = 4;
 
@@ -211,15 +211,26 @@ post_candidates_kernel(const Geometry geo, const CandPlan plan, const float thr,
     __shared__ float q_x[kCandQueue];              // gated logit
     __shared__ unsigned q_e[kCandQueue];           // its element index inside the image's [C, H*W] block
     __shared__ unsigned short q_where[kCandQueue]; // (image << 3) | level
+    __shared__ unsigned s_hist2[kHistBins / 2];    // score histogram of one list (big drains), two 16-bit bins a word
     __shared__ int q_cnt;
     const int lane = threadIdx.x & 31;
     if (threadIdx.x == 0) q_cnt = 0;
     __syncthreads();
     const float inv_c = 1.0f / (float)geo.C;
 
-    // all threads: exact test + score + append for every queued element (block-uniform call)
+    // all threads: exact test + score + append for every queued element (block-uniform call).  A big drain
+    // (a dense chunk: thousands of candidates of ONE list) counts its scores into a shared-memory histogram
+    // that is added to the list's global one at the end; small drains update the global histogram directly.
     auto drain = [&]() {
         const int total = q_cnt;
+        const bool big = total >= 4 * kCandThreads;
+        int hist_seg = -1;
+        if (big) {
+            const unsigned where0 = q_where[0];
+            hist_seg = (int)(where0 >> 3) * geo.num_levels + (int)(where0 & 7u);
+            for (int b = threadIdx.x; b < kHistBins / 2; b += kCandThreads) s_hist2[b] = 0u;
+            __syncthreads();
+        }
         for (int t0 = 0; t0 < total; t0 += kCandThreads) {
             const int t = t0 + threadIdx.x;
             bool is = false;
@@ -258,10 +269,20 @@ post_candidates_kernel(const Geometry geo, const CandPlan plan, const float thr,
                 if (lane == leader) pos = atomicAdd(&cand_count[seg], __popc(peers));
                 pos = __shfl_sync(peers, pos, leader) + __popc(peers & ((1u << lane) - 1u));
                 cand[((size_t)n * geo.A + geo.lv[l].a_off) * geo.C + pos] = make_uint2(__float_as_uint(score), entry);
-                atomicAdd(&hist[(size_t)seg * kHistBins + score_bin(score)], 1);
+                const int bin = score_bin(score);
+                if (seg == hist_seg) atomicAdd(&s_hist2[bin >> 1], 1u << (16 * (bin & 1)));   // <= kCandQueue < 65536 per bin
+                else atomicAdd(&hist[(size_t)seg * kHistBins + bin], 1);
             }
         }
         __syncthreads();
+        if (big) {
+            int* gh = hist + (size_t)hist_seg * kHistBins;
+            for (int b = threadIdx.x; b < kHistBins / 2; b += kCandThreads) {
+                const unsigned v = s_hist2[b];
+                if (v & 0xffffu) atomicAdd(&gh[2 * b], (int)(v & 0xffffu));
+                if (v >> 16) atomicAdd(&gh[2 * b + 1], (int)(v >> 16));
+            }
+        }
         if (threadIdx.x == 0) q_cnt = 0;
         __syncthreads();
     };
@@ -280,13 +301,19 @@ post_candidates_kernel(const Geometry geo, const CandPlan plan, const float thr,
             cand_load(nxt, plan.vec[nxt.l] != 0, nx);
         }
         // bit 4j+t: element t of float4 j passes the gate (16 compares, no transcendental)
-        unsigned mask = 0u;
+        // (most threads hold no gated element at all: one maximum over the 16 values decides that first)
+        float mx = -INFINITY;
 #pragma unroll
-        for (int j = 0; j < kCandVecs; ++j) {
-            mask |= (x[j].x > logit_gate ? 1u : 0u) << (4 * j);
-            mask |= (x[j].y > logit_gate ? 1u : 0u) << (4 * j + 1);
-            mask |= (x[j].z > logit_gate ? 1u : 0u) << (4 * j + 2);
-            mask |= (x[j].w > logit_gate ? 1u : 0u) << (4 * j + 3);
+        for (int j = 0; j < kCandVecs; ++j) mx = fmaxf(mx, fmaxf(fmaxf(x[j].x, x[j].y), fmaxf(x[j].z, x[j].w)));
+        unsigned mask = 0u;
+        if (mx > logit_gate) {
+#pragma unroll
+            for (int j = 0; j < kCandVecs; ++j) {
+                mask |= (x[j].x > logit_gate ? 1u : 0u) << (4 * j);
+                mask |= (x[j].y > logit_gate ? 1u : 0u) << (4 * j + 1);
+                mask |= (x[j].z > logit_gate ? 1u : 0u) << (4 * j + 2);
+                mask |= (x[j].w > logit_gate ? 1u : 0u) << (4 * j + 3);
+            }
         }
         if (__any_sync(PAA_FULL, mask != 0u)) {
             // queue slots for the warp's gated elements: warp scan of the per-lane counts, one shared atomic
@@ -1179,8 +1206,8 @@ int run_postprocess(const Geometry& geo, const PaaPostArgs* a, cudaStream_t stre
         unsigned grid = 148u * kCandBlocksPerSM;
         if (grid > chunks) grid = chunks;
         KernelTimer t(PAA_KERNEL_POST_CANDIDATES, stream);
-        post_candidates_kernel<<<grid, kCandThreads, 0, stream>>>(geo, plan, a->pre_nms_thresh, gate, w.cand,
-                                                                  w.cand_count, w.hist);
+        post_candidates_kernel<<<grid, kCandThreads, 0, stream>>>(geo, plan, a->pre_nms_thresh, gate,
+                                                                               w.cand, w.cand_count, w.hist);
     }
     PAA_LAUNCH_CHECK("post_candidates_kernel");
     post_threshold_kernel<<<N * L, 256, 0, stream>>>(w.cand_count, w.hist, topn, w.thr_bin, w.n_above, w.k_sel);

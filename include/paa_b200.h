@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define PAA_ABI_VERSION 2
+#define PAA_ABI_VERSION 3
 #define PAA_MAX_LEVELS 8
 #define PAA_MAX_IMAGES 256      /* images per call (per rank) */
 #define PAA_MAX_CANDIDATES 128  /* num_levels * topk must not exceed this */
@@ -144,7 +144,18 @@ typedef struct PaaPostArgs {
     int32_t* dbg_pre_labels;      /* [N, cap] */
     int32_t* dbg_pre_count;       /* [N, num_levels] candidates kept per level */
     uint8_t* dbg_nms_keep;        /* [N, cap] 1 = survived NMS (before the detections_per_img cut) */
+    /* How a selected (anchor, regression) pair becomes a box (0 keeps PAA / ATSS behaviour):
+     *   PAA_DECODE_ATSS_BOX  rpn/atss/atss.py:68-96 ('BOX' BoxCoder: /10, /5, x2 = cx + (w-1)/2)
+     *   PAA_DECODE_LEGACY    modeling/box_coder.py:51-95 (RetinaNet: weights, x2 = cx + w/2 - 1)
+     *   PAA_DECODE_LTRB      rpn/fcos/inference.py:93-98 (FCOS: "anchors" are points (x, y, x, y), the four
+     *                        regression channels are distances to the left / top / right / bottom edge) */
+    int32_t box_decode;
+    float decode_weights[4];      /* PAA_DECODE_LEGACY: wx, wy, ww, wh */
+    float decode_clip;            /* PAA_DECODE_LEGACY: bbox_xform_clip (log(1000/16)) */
 } PaaPostArgs;
+#define PAA_DECODE_ATSS_BOX 0
+#define PAA_DECODE_LEGACY   1
+#define PAA_DECODE_LTRB     2
 
 int paa_abi_version(void);
 const char* paa_last_error(void);

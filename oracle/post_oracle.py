@@ -26,21 +26,45 @@ def default_params(**kw):
              num_classes=81, score_voting=True, min_size=0, skip_nms=False,
              # "atss": rpn/atss/inference.py:33-80 -- per-level top-k on sigmoid(cls) * sigmoid(centerness),
              # square root taken on the selected scores; no score voting (set score_voting=False with it)
-             flavour="paa")
+             # "retinanet": rpn/retinanet/inference.py:60-127 -- no third map, RPN BoxCoder (modeling/box_coder.py:51-95)
+             # "fcos": rpn/fcos/inference.py:48-104 -- anchors are points (x, y, x, y), ltrb distances, product
+             #         top-k then square root
+             flavour="paa", decode_weights=(10.0, 10.0, 5.0, 5.0))
     p.update(kw)
     return SimpleNamespace(**p)
 
 
+def decode_legacy(rel_codes, boxes, weights, clip=None):
+    """modeling/box_coder.py:51-95 (TO_REMOVE = 1; x2 = cx + w/2 - 1)."""
+    import math
+    clip = math.log(1000.0 / 16) if clip is None else clip
+    w = boxes[:, 2] - boxes[:, 0] + 1
+    h = boxes[:, 3] - boxes[:, 1] + 1
+    cx = boxes[:, 0] + 0.5 * w
+    cy = boxes[:, 1] + 0.5 * h
+    wx, wy, ww, wh = weights
+    dx, dy = rel_codes[:, 0] / wx, rel_codes[:, 1] / wy
+    dw = torch.clamp(rel_codes[:, 2] / ww, max=clip)
+    dh = torch.clamp(rel_codes[:, 3] / wh, max=clip)
+    pcx, pcy = dx * w + cx, dy * h + cy
+    pw, ph = torch.exp(dw) * w, torch.exp(dh) * h
+    return torch.stack([pcx - 0.5 * pw, pcy - 0.5 * ph, pcx + 0.5 * pw - 1, pcy + 0.5 * ph - 1], dim=1)
+
+
 def level_candidates(box_cls, box_regression, iou_pred, anchors, image_sizes, prm):
     """inference.py:36-82 for one level -> per image (boxes [k,4], scores [k], labels [k])."""
-    N, C, H, W = box_cls.shape
-    prob = box_cls.permute(0, 2, 3, 1).reshape(N, -1, C).sigmoid()              # :42-43
-    reg = box_regression.permute(0, 2, 3, 1).reshape(N, -1, 4)                  # :45-46
+    N, _, H, W = box_cls.shape
+    A = box_regression.shape[1] // 4                                            # anchors per location
+    C = box_cls.shape[1] // A
+    # permute_and_flatten (rpn/utils.py:10-14): [N, A*C, H, W] -> [N, H*W*A, C]
+    prob = box_cls.view(N, A, C, H, W).permute(0, 3, 4, 1, 2).reshape(N, -1, C).sigmoid()   # :42-43
+    reg = box_regression.view(N, A, 4, H, W).permute(0, 3, 4, 1, 2).reshape(N, -1, 4)       # :45-46
     cand = prob > prm.pre_nms_thresh                                            # :48
     k_per_im = cand.reshape(N, -1).sum(1).clamp(max=prm.pre_nms_top_n)          # :49-50
-    atss = getattr(prm, "flavour", "paa") == "atss"
+    flavour = getattr(prm, "flavour", "paa")
+    atss = flavour in ("atss", "fcos")
     if iou_pred is not None:
-        q = iou_pred.permute(0, 2, 3, 1).reshape(N, -1).sigmoid()               # :54-55
+        q = iou_pred.view(N, A, 1, H, W).permute(0, 3, 4, 1, 2).reshape(N, -1).sigmoid()   # :54-55
         prob = prob * q[:, :, None]                                             # atss/inference.py:53
         if not atss:
             prob = prob.sqrt()                                                  # :56
@@ -53,7 +77,14 @@ def level_candidates(box_cls, box_regression, iou_pred, anchors, image_sizes, pr
         where = cand[i].nonzero()[pick, :]                                      # :66
         loc = where[:, 0]
         labels = where[:, 1] + 1                                                # :69
-        boxes = decode(reg[i][loc, :].view(-1, 4), anchors[loc, :].view(-1, 4))  # :71-74
+        if flavour == "retinanet":
+            boxes = decode_legacy(reg[i][loc, :].view(-1, 4), anchors[loc, :].view(-1, 4), prm.decode_weights)
+        elif flavour == "fcos":
+            pts, d = anchors[loc, :].view(-1, 4), reg[i][loc, :].view(-1, 4)
+            boxes = torch.stack([pts[:, 0] - d[:, 0], pts[:, 1] - d[:, 1], pts[:, 2] + d[:, 2], pts[:, 3] + d[:, 3]],
+                                dim=1)                                          # fcos/inference.py:93-98
+        else:
+            boxes = decode(reg[i][loc, :].view(-1, 4), anchors[loc, :].view(-1, 4))  # :71-74
         w, h = image_sizes[i]
         boxes[:, 0].clamp_(min=0, max=w - 1)                                    # bounding_box.py:214-219
         boxes[:, 1].clamp_(min=0, max=h - 1)

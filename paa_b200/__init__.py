@@ -11,7 +11,8 @@ from paa_b200.structures import BoxList, boxlist_iou, cat_boxlist
 
 __all__ = ["BoxCoder", "BoxList", "boxlist_iou", "cat_boxlist", "default_cfg", "make_paa_loss_evaluator",
            "make_paa_postprocessor", "PAALossComputation", "PAAPostProcessor", "make_anchor_generator_paa",
-           "AnchorGenerator", "make_atss_postprocessor", "ATSSPostProcessor"]
+           "AnchorGenerator", "make_atss_postprocessor", "ATSSPostProcessor", "make_retinanet_postprocessor",
+           "RetinaNetPostProcessor", "make_fcos_postprocessor", "FCOSPostProcessor"]
 
 
 def __getattr__(name):
@@ -20,7 +21,9 @@ def __getattr__(name):
     if name in ("make_paa_loss_evaluator", "PAALossComputation"):
         from paa_b200 import loss
         return getattr(loss, name)
-    if name in ("make_paa_postprocessor", "PAAPostProcessor", "make_atss_postprocessor", "ATSSPostProcessor"):
+    if name in ("make_paa_postprocessor", "PAAPostProcessor", "make_atss_postprocessor", "ATSSPostProcessor",
+                "make_retinanet_postprocessor", "RetinaNetPostProcessor", "make_fcos_postprocessor",
+                "FCOSPostProcessor"):
         from paa_b200 import inference
         return getattr(inference, name)
     if name in ("make_anchor_generator_paa", "AnchorGenerator"):

@@ -14,7 +14,7 @@ MAX_IMAGES = 256
 MAX_PEERS = 16
 PEER_BUFFER_DOUBLES = 256
 MAX_CANDIDATES = 128
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 ERR_BAD_ARGUMENT, ERR_WORKSPACE, ERR_EMPTY_TARGET, ERR_UNSUPPORTED = -1, -2, -3, -4
 
@@ -59,7 +59,10 @@ class PaaPostArgs(C.Structure):
                 ("out_count", C.c_void_p),
                 ("dbg_pre_boxes", C.c_void_p), ("dbg_pre_scores", C.c_void_p),
                 ("dbg_pre_labels", C.c_void_p), ("dbg_pre_count", C.c_void_p),
-                ("dbg_nms_keep", C.c_void_p)]
+                ("dbg_nms_keep", C.c_void_p),
+                ("box_decode", C.c_int32), ("decode_weights", C.c_float * 4), ("decode_clip", C.c_float)]
+
+DECODE_ATSS_BOX, DECODE_LEGACY, DECODE_LTRB = 0, 1, 2
 
 
 # name -> (restype, argtypes); every symbol include/paa_b200.h declares

@@ -120,6 +120,11 @@ struct ImageSizes {
     float wh[PAA_MAX_IMAGES][2];
 };
 
+struct DecodeSpec {
+    int mode;                 // PAA_DECODE_*
+    float wx, wy, ww, wh, clip;
+};
+
 __device__ __forceinline__ int score_bin(float s) {
     int b = (int)(s * (float)kHistBins);
     return b < 0 ? 0 : (b >= kHistBins ? kHistBins - 1 : b);
@@ -505,7 +510,8 @@ __global__ void __launch_bounds__(kSelectThreads)
 post_select_kernel(const Geometry geo, const ImageSizes sizes, const uint2* __restrict__ cand,
                    const unsigned* __restrict__ bnd, const int* __restrict__ bnd_count,
                    const int* __restrict__ n_above, const int* __restrict__ k_sel,
-                   const int* __restrict__ thr_bin, int topn, float min_size, uint2* __restrict__ sel,
+                   const int* __restrict__ thr_bin, int topn, float min_size, const DecodeSpec dec,
+                   uint2* __restrict__ sel,
                    int* __restrict__ pre_cnt, float4* __restrict__ pre_box, float* __restrict__ pre_score,
                    int* __restrict__ pre_label) {
     __shared__ unsigned s_idx[kMaxTopN];
@@ -623,7 +629,11 @@ post_select_kernel(const Geometry geo, const ImageSizes sizes, const uint2* __re
             const float* rp = lv.reg + head_offset(n, i, 0, 4, geo.apl, lv.hw);
             const float4 d = make_float4(__ldg(rp), __ldg(rp + lv.hw), __ldg(rp + 2 * (size_t)lv.hw),
                                          __ldg(rp + 3 * (size_t)lv.hw));
-            float4 box = decode_box(d, anchor_frame(a));                  // inference.py:71-74
+            float4 box;
+            if (dec.mode == PAA_DECODE_LEGACY) box = decode_box_legacy(d, a, dec.wx, dec.wy, dec.ww, dec.wh, dec.clip);
+            else if (dec.mode == PAA_DECODE_LTRB)                         // fcos/inference.py:93-98
+                box = make_float4(__fsub_rn(a.x, d.x), __fsub_rn(a.y, d.y), __fadd_rn(a.z, d.z), __fadd_rn(a.w, d.w));
+            else box = decode_box(d, anchor_frame(a));                    // inference.py:71-74
             box.x = fminf(fmaxf(box.x, 0.0f), img_w - 1.0f);              // bounding_box.py:214-219
             box.y = fminf(fmaxf(box.y, 0.0f), img_h - 1.0f);
             box.z = fminf(fmaxf(box.z, 0.0f), img_w - 1.0f);
@@ -1184,6 +1194,18 @@ int run_postprocess(const Geometry& geo, const PaaPostArgs* a, cudaStream_t stre
         sizes.wh[i][1] = a->image_wh[i][1];
     }
     const int nbw = (capN + 63) / 64;
+    DecodeSpec dec;
+    dec.mode = a->box_decode;
+    dec.wx = a->decode_weights[0];
+    dec.wy = a->decode_weights[1];
+    dec.ww = a->decode_weights[2];
+    dec.wh = a->decode_weights[3];
+    dec.clip = a->decode_clip;
+    if (dec.mode < PAA_DECODE_ATSS_BOX || dec.mode > PAA_DECODE_LTRB ||
+        (dec.mode == PAA_DECODE_LEGACY && !(dec.wx > 0.0f && dec.wy > 0.0f && dec.ww > 0.0f && dec.wh > 0.0f))) {
+        set_error("box_decode=%d / decode_weights unsupported", dec.mode);
+        return PAA_ERR_BAD_ARGUMENT;
+    }
     PAA_CUDA_CHECK(cudaMemsetAsync(a->workspace, 0, w.zero_bytes, stream));
     // a logit can only pass sigmoid(x) > thr if x > logit(thr); gate a little below that and test exactly
     const float gate = logf(a->pre_nms_thresh / (1.0f - a->pre_nms_thresh)) - 1e-3f;
@@ -1221,7 +1243,7 @@ int run_postprocess(const Geometry& geo, const PaaPostArgs* a, cudaStream_t stre
     {
         KernelTimer t(PAA_KERNEL_POST_SELECT, stream);
         post_select_kernel<<<N * L, kSelectThreads, 0, stream>>>(geo, sizes, w.cand, w.bnd, w.bnd_count, w.n_above,
-                                                                 w.k_sel, w.thr_bin, topn, 0.0f, w.sel, w.pre_cnt,
+                                                                 w.k_sel, w.thr_bin, topn, 0.0f, dec, w.sel, w.pre_cnt,
                                                                  w.pre_box, w.pre_score, w.pre_label);
     }
     PAA_LAUNCH_CHECK("post_select_kernel");

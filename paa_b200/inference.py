@@ -45,6 +45,8 @@ class PAAPostProcessor(torch.nn.Module):
         self.debug = False
         self.last_debug = None
         self._workspace = None
+        # how (anchor, regression) becomes a box: the ATSS 'BOX' coder unless a subclass says otherwise
+        self._decode = (_lib.DECODE_ATSS_BOX, (0.0, 0.0, 0.0, 0.0), 0.0)
 
     def _workspace_for(self, device, nbytes):
         ws = self._workspace
@@ -74,6 +76,10 @@ class PAAPostProcessor(torch.nn.Module):
         args.skip_nms = int(bool(self.bbox_aug_enabled and not self.bbox_aug_vote))      # inference.py:96
         args.pre_nms_thresh, args.nms_thresh = float(self.pre_nms_thresh), float(self.nms_thresh)
         args.anchor_image_stride = lv["anchor_stride"]
+        args.box_decode = self._decode[0]
+        for k in range(4):
+            args.decode_weights[k] = float(self._decode[1][k])
+        args.decode_clip = float(self._decode[2])
         for l in range(L):
             s = args.levels[l]
             s.box_cls, s.box_regression = lv["cls"][l].data_ptr(), lv["reg"][l].data_ptr()
@@ -169,6 +175,86 @@ def make_atss_postprocessor(config, box_coder):
         bbox_aug_enabled=config.TEST.BBOX_AUG.ENABLED,
         box_coder=box_coder,
         bbox_aug_vote=config.TEST.BBOX_AUG.VOTE,
+    )
+
+
+class RetinaNetPostProcessor(PAAPostProcessor):
+    """``paa_core/modeling/rpn/retinanet/inference.py:14-173`` on the same kernels: no third head
+    output, several anchors per location, boxes decoded with the RPN ``BoxCoder`` (modeling/box_coder.py:51-95,
+    weights (10, 10, 5, 5)).  The reference runs one single-class NMS per class and concatenates the classes
+    (rows class-major, score-descending); the label-aware NMS here keeps the same set and returns it in
+    ascending pre-NMS index like the PAA post-processor -- consumers (coco_eval) do not depend on row order."""
+
+    def __init__(self, pre_nms_thresh, pre_nms_top_n, nms_thresh, fpn_post_nms_top_n, min_size, num_classes,
+                 box_coder=None):
+        import math
+        weights = tuple(getattr(box_coder, "weights", (10.0, 10.0, 5.0, 5.0)))
+        clip = float(getattr(box_coder, "bbox_xform_clip", math.log(1000.0 / 16)))
+        super(RetinaNetPostProcessor, self).__init__(pre_nms_thresh, pre_nms_top_n, nms_thresh, fpn_post_nms_top_n,
+                                                     min_size, num_classes, _BoxCoderTag(), False, False,
+                                                     score_voting=False)
+        self.box_coder = box_coder
+        self._decode = (_lib.DECODE_LEGACY, weights, clip)
+
+    def forward(self, anchors, box_cls, box_regression, targets=None):
+        """Argument order of RPNPostProcessor.forward (rpn/inference.py:123): anchors first."""
+        return super(RetinaNetPostProcessor, self).forward(box_cls, box_regression, None, anchors)
+
+
+class _BoxCoderTag(object):
+    """Stands in for a coder object where the decode is selected by `_decode` instead."""
+    regression_type = "BOX"
+
+
+def make_retinanet_postprocessor(config, rpn_box_coder, is_train=False):
+    """retinanet/inference.py:176-194."""
+    return RetinaNetPostProcessor(
+        pre_nms_thresh=config.MODEL.RETINANET.INFERENCE_TH,
+        pre_nms_top_n=config.MODEL.RETINANET.PRE_NMS_TOP_N,
+        nms_thresh=config.MODEL.RETINANET.NMS_TH,
+        fpn_post_nms_top_n=config.TEST.DETECTIONS_PER_IMG,
+        min_size=0,
+        num_classes=config.MODEL.RETINANET.NUM_CLASSES,
+        box_coder=rpn_box_coder,
+    )
+
+
+class FCOSPostProcessor(PAAPostProcessor):
+    """``paa_core/modeling/rpn/fcos/inference.py:12-147`` on the same kernels: anchor-free --
+    every location (x, y) regresses its distances to the four box edges (decoded as
+    ``(x - l, y - t, x + r, y + b)``, :93-98) and carries a centerness logit; score = sqrt(sigmoid(cls) *
+    sigmoid(centerness)), threshold on sigmoid(cls) alone."""
+
+    def __init__(self, pre_nms_thresh, pre_nms_top_n, nms_thresh, fpn_post_nms_top_n, min_size, num_classes,
+                 bbox_aug_enabled=False):
+        super(FCOSPostProcessor, self).__init__(pre_nms_thresh, pre_nms_top_n, nms_thresh, fpn_post_nms_top_n,
+                                                min_size, num_classes, _BoxCoderTag(), bbox_aug_enabled, False,
+                                                score_voting=False)
+        self._decode = (_lib.DECODE_LTRB, (0.0, 0.0, 0.0, 0.0), 0.0)
+        self._points = {}
+
+    def forward(self, locations, box_cls, box_regression, centerness, image_sizes):
+        """locations: list[L] of [H*W, 2] tensors (fcos.py compute_locations); image_sizes: [(h, w), ...]."""
+        points = []
+        for loc in locations:
+            key = (loc.data_ptr(), tuple(loc.shape))
+            if key not in self._points:
+                self._points[key] = torch.cat([loc, loc], dim=1).to(torch.float32).contiguous()   # (x, y, x, y)
+            points.append(self._points[key])
+        anchors = [[BoxList(p, (int(w), int(h)), mode="xyxy") for p in points] for (h, w) in image_sizes]
+        return super(FCOSPostProcessor, self).forward(box_cls, box_regression, centerness, anchors)
+
+
+def make_fcos_postprocessor(config):
+    """fcos/inference.py:169-184."""
+    return FCOSPostProcessor(
+        pre_nms_thresh=config.MODEL.FCOS.INFERENCE_TH,
+        pre_nms_top_n=config.MODEL.FCOS.PRE_NMS_TOP_N,
+        nms_thresh=config.MODEL.FCOS.NMS_TH,
+        fpn_post_nms_top_n=config.TEST.DETECTIONS_PER_IMG,
+        min_size=0,
+        num_classes=config.MODEL.FCOS.NUM_CLASSES,
+        bbox_aug_enabled=config.TEST.BBOX_AUG.ENABLED,
     )
 
 

@@ -198,3 +198,44 @@ def multiscale_hw(seed: int, num_images: int, max_long: int = 1333):
         r = 1.2 + 0.5 * float(torch.rand((1,), generator=gen))
         out.append((s, min(int(round(s * r)), max_long)))
     return out
+
+
+def make_retinanet_batch(seed: int, num_images: int, image_hw: Tuple[int, int] = (320, 416),
+                         cls_mean: float = -3.5, cls_std: float = 1.5, strides=STRIDES,
+                         aspect_ratios=(0.5, 1.0, 2.0), scales_per_octave: int = 3, octave: float = 2.0):
+    """RetinaNet-shaped inference inputs (rpn/retinanet/retinanet.py): A = ratios x scales anchors per location,
+    ``box_cls[l] [N, A*80, H, W]``, ``box_regression[l] [N, A*4, H, W]``, anchors ``[H*W*A, 4]`` (location-major,
+    anchor inner, rpn/utils.py:10-14) built like make_anchor_generator_retinanet."""
+    import numpy as np
+    from paa_b200.anchor_generator import generate_cell_anchors
+    gen = torch.Generator().manual_seed(seed)
+    hp, wp = padded_size(*image_hw)
+    grids = level_grids(hp, wp, strides)
+    A = len(aspect_ratios) * scales_per_octave
+    anchors, box_cls, box_reg = [], [], []
+    for (h, w), stride in zip(grids, strides):
+        sizes = tuple(octave ** (k / float(scales_per_octave)) * 4.0 * stride for k in range(scales_per_octave))
+        cell = torch.from_numpy(generate_cell_anchors(stride, sizes, aspect_ratios)).float()       # [A, 4]
+        ys = torch.arange(h, dtype=torch.float32) * stride
+        xs = torch.arange(w, dtype=torch.float32) * stride
+        shift = torch.stack((xs.view(1, w).expand(h, w), ys.view(h, 1).expand(h, w),
+                             xs.view(1, w).expand(h, w), ys.view(h, 1).expand(h, w)), dim=2).reshape(-1, 1, 4)
+        anchors.append((shift + cell.view(1, A, 4)).reshape(-1, 4).contiguous())
+        box_cls.append((torch.randn((num_images, A * NUM_FG_CLASSES, h, w), generator=gen) * cls_std + cls_mean)
+                       .clamp_(-12.0, 12.0))
+        box_reg.append(torch.randn((num_images, A * 4, h, w), generator=gen) * 0.5)
+    return SyntheticBatch(image_sizes=[(image_hw[1], image_hw[0])] * num_images, grids=grids, anchors=anchors,
+                          gt_boxes=[], gt_labels=[], box_cls=box_cls, box_regression=box_reg, iou_pred=None,
+                          meta=dict(seed=seed, padded_hw=(hp, wp), anchors_per_loc=A))
+
+
+def fcos_locations(grids, strides=STRIDES):
+    """fcos.py compute_locations: (x, y) = (col * stride + stride // 2, row * stride + stride // 2), row-major."""
+    out = []
+    for (h, w), stride in zip(grids, strides):
+        ys = torch.arange(0, h * stride, step=stride, dtype=torch.float32)
+        xs = torch.arange(0, w * stride, step=stride, dtype=torch.float32)
+        yy = ys.view(h, 1).expand(h, w).reshape(-1)
+        xx = xs.view(1, w).expand(h, w).reshape(-1)
+        out.append(torch.stack((xx, yy), dim=1) + stride // 2)
+    return out

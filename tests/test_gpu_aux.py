@@ -111,3 +111,53 @@ def test_atss_postprocessor_against_oracle():
         assert gl.shape == wl.shape and np.array_equal(gl, wl)
         np.testing.assert_allclose(gs, ws, rtol=1e-5, atol=1e-7)
         np.testing.assert_allclose(gb, wb, rtol=1e-4, atol=1e-3)
+
+
+def _same_detections(got, want, i):
+    gb, gs, gl = post_oracle.canonical_rows(got[i].bbox.cpu(), got[i].get_field("scores").cpu(),
+                                            got[i].get_field("labels").cpu())
+    wb, ws, wl = post_oracle.canonical_rows(want[i].boxes, want[i].scores, want[i].labels)
+    assert gl.shape == wl.shape and np.array_equal(gl, wl)
+    np.testing.assert_allclose(gs, ws, rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(gb, wb, rtol=1e-4, atol=1e-3)
+
+
+def test_retinanet_postprocessor_against_oracle():
+    """Nine anchors per location, RPN BoxCoder decode, no third head output."""
+    import paa_b200
+    from types import SimpleNamespace as NS
+    from paa_b200.inference import make_retinanet_postprocessor
+    b = synthetic.make_retinanet_batch(seed=43, num_images=2, image_hw=(256, 320))
+    cfg = NS(MODEL=NS(RETINANET=NS(INFERENCE_TH=0.05, PRE_NMS_TOP_N=300, NMS_TH=0.4, NUM_CLASSES=81)),
+             TEST=NS(DETECTIONS_PER_IMG=100))
+    pp = make_retinanet_postprocessor(cfg, NS(weights=(10.0, 10.0, 5.0, 5.0), bbox_xform_clip=float(np.log(1000.0 / 16))))
+    anc = [a.cuda() for a in b.anchors]
+    n_img = b.box_cls[0].shape[0]
+    anchors = [[paa_b200.BoxList(a, b.image_sizes[i]) for a in anc] for i in range(n_img)]
+    got = pp(anchors, [t.cuda() for t in b.box_cls], [t.cuda() for t in b.box_regression])
+    prm = post_oracle.default_params(pre_nms_top_n=300, nms_thresh=0.4, score_voting=False, flavour="retinanet")
+    want = post_oracle.postprocess(b.box_cls, b.box_regression, None, b.anchors, b.image_sizes, prm)
+    for i in range(n_img):
+        assert len(got[i]) > 0
+        _same_detections(got, want, i)
+
+
+def test_fcos_postprocessor_against_oracle():
+    """Anchor-free: points + distances to the four edges, centerness in the score."""
+    import paa_b200
+    from types import SimpleNamespace as NS
+    from paa_b200.inference import make_fcos_postprocessor
+    b = synthetic.make_inference_batch(seed=44, num_images=2, image_hw=(256, 320), candidates_per_level=500)
+    locs = synthetic.fcos_locations(b.grids)
+    reg = [torch.exp(t * 0.5) * 8.0 * s for t, s in zip(b.box_regression, synthetic.STRIDES)]   # positive distances
+    cfg = NS(MODEL=NS(FCOS=NS(INFERENCE_TH=0.05, PRE_NMS_TOP_N=200, NMS_TH=0.6, NUM_CLASSES=81)),
+             TEST=NS(DETECTIONS_PER_IMG=100, BBOX_AUG=NS(ENABLED=False)))
+    pp = make_fcos_postprocessor(cfg)
+    sizes = [(h, w) for (w, h) in b.image_sizes]
+    got = pp([l.cuda() for l in locs], [t.cuda() for t in b.box_cls], [t.cuda() for t in reg],
+             [t.cuda() for t in b.iou_pred], sizes)
+    prm = post_oracle.default_params(pre_nms_top_n=200, score_voting=False, flavour="fcos")
+    want = post_oracle.postprocess(b.box_cls, reg, b.iou_pred, [torch.cat([l, l], 1) for l in locs], b.image_sizes, prm)
+    for i in range(b.num_images):
+        assert len(got[i]) > 0
+        _same_detections(got, want, i)

@@ -28,9 +28,11 @@ def test_struct_layout_matches_header(tmp_path):
     """Compiles a C program against include/paa_b200.h and compares sizeof/offsetof with ctypes."""
     from paa_b200 import _lib
     fields_loss = ["num_images", "gamma", "anchor_image_stride", "levels", "gt_boxes", "gt_offsets",
-                   "workspace", "normalisers", "grad_losses", "dbg_matched_idx", "teacher_combined_loss"]
+                   "workspace", "normalisers", "grad_losses", "dbg_matched_idx", "teacher_combined_loss", "rank",
+                   "peer_norm"]
     fields_post = ["num_images", "pre_nms_thresh", "anchor_image_stride", "levels", "image_wh", "workspace",
-                   "out_boxes", "out_count", "dbg_pre_boxes", "dbg_nms_keep"]
+                   "out_boxes", "out_count", "dbg_pre_boxes", "dbg_nms_keep", "box_decode", "decode_weights",
+                   "decode_clip"]
     src = ['#include <stdio.h>', '#include <stddef.h>', '#include "paa_b200.h"', 'int main(void){',
            'printf("%zu %zu %zu\\n", sizeof(PaaLevel), sizeof(PaaLossArgs), sizeof(PaaPostArgs));']
     for f in fields_loss:

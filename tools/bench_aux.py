@@ -1,0 +1,85 @@
+"""Measurement of the operators next to the hot path: device anchor generation, boxlist_iou,
+and the ATSS / RetinaNet / FCOS post-processors on the PAA kernels.  CUDA events, L2 flushed before every
+timed call, median of 10.   python tools/bench_aux.py"""
+import json, os, statistics, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from types import SimpleNamespace as NS
+import paa_b200
+from paa_b200 import synthetic
+from paa_b200.anchor_generator import make_anchor_generator_paa
+from paa_b200.inference import make_atss_postprocessor, make_retinanet_postprocessor, make_fcos_postprocessor
+
+dev = torch.device("cuda", 0)
+torch.cuda.set_device(0)
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+
+def timed(fn, reps=10, warm=3):
+    for _ in range(warm):
+        fn()
+    ms = []
+    for _ in range(reps):
+        flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record(); fn(); e.record(); torch.cuda.synchronize()
+        ms.append(s.elapsed_time(e))
+    return statistics.median(ms)
+
+
+out = {}
+# anchors: 800x1333 grid, generated (cache bypassed) vs what the reference does on the host every forward
+cfg = paa_b200.default_cfg()
+gen = make_anchor_generator_paa(cfg)
+grids = synthetic.level_grids(*synthetic.padded_size(800, 1333))
+def gen_once():
+    gen._grid_cache = {k: v for k, v in gen._grid_cache.items() if k[0] == "cells"}
+    return gen.grid_anchors(grids, dev)
+ms = timed(gen_once)
+out["grid_anchors_800x1333"] = {"ms": ms, "anchors": 22400, "note": "5 launches (one per level), cache bypassed"}
+t0 = time.perf_counter()
+for _ in range(20):
+    [synthetic.level_anchors(g, s) for g, s in zip(grids, synthetic.STRIDES)]
+out["grid_anchors_800x1333"]["torch_cpu_ms"] = (time.perf_counter() - t0) / 20 * 1e3
+
+# boxlist_iou: 100 GT x 22400 anchors and 5000 x 5000
+for n1, n2 in ((100, 22400), (5000, 5000)):
+    g = torch.Generator().manual_seed(n1)
+    def boxes(n):
+        xy = torch.rand((n, 2), generator=g) * 1000
+        return torch.cat([xy, xy + torch.rand((n, 2), generator=g) * 300], 1)
+    a, b = paa_b200.BoxList(boxes(n1).to(dev), (1333, 800)), paa_b200.BoxList(boxes(n2).to(dev), (1333, 800))
+    ms = timed(lambda: paa_b200.boxlist_iou(a, b))
+    out["boxlist_iou_%dx%d" % (n1, n2)] = {"ms": ms, "pairs_per_s": n1 * n2 / (ms / 1e3),
+                                           "write_GBps": n1 * n2 * 4 / (ms / 1e3) / 1e9}
+
+# post-processor flavours, 8 images of 800x1333
+b = synthetic.make_inference_batch(seed=4000, num_images=8, image_hw=(800, 1333), candidates_per_level=4000)
+cls = [t.to(dev) for t in b.box_cls]; reg = [t.to(dev) for t in b.box_regression]; ctr = [t.to(dev) for t in b.iou_pred]
+anc = [a.to(dev) for a in b.anchors]
+anchors = [[paa_b200.BoxList(a, b.image_sizes[i]) for a in anc] for i in range(8)]
+atss_cfg = NS(MODEL=NS(ATSS=NS(INFERENCE_TH=0.05, PRE_NMS_TOP_N=1000, NMS_TH=0.6, NUM_CLASSES=81, REGRESSION_TYPE="BOX")),
+              TEST=NS(DETECTIONS_PER_IMG=100, BBOX_AUG=NS(ENABLED=False, VOTE=False)))
+pp = make_atss_postprocessor(atss_cfg, paa_b200.BoxCoder(atss_cfg))
+ms = timed(lambda: pp.run_device(cls, reg, ctr, anchors))
+out["atss_post_8img"] = {"ms": ms, "images_per_s": 8 / (ms / 1e3)}
+fc_cfg = NS(MODEL=NS(FCOS=NS(INFERENCE_TH=0.05, PRE_NMS_TOP_N=1000, NMS_TH=0.6, NUM_CLASSES=81)),
+            TEST=NS(DETECTIONS_PER_IMG=100, BBOX_AUG=NS(ENABLED=False)))
+fp = make_fcos_postprocessor(fc_cfg)
+locs = [l.to(dev) for l in synthetic.fcos_locations(b.grids)]
+pts = [torch.cat([l, l], 1).contiguous() for l in locs]
+fanchors = [[paa_b200.BoxList(p, b.image_sizes[i]) for p in pts] for i in range(8)]
+dist = [torch.exp(t * 0.5) * 8.0 * s for t, s in zip(reg, synthetic.STRIDES)]
+ms = timed(lambda: fp.run_device(cls, dist, ctr, fanchors))
+out["fcos_post_8img"] = {"ms": ms, "images_per_s": 8 / (ms / 1e3)}
+rb = synthetic.make_retinanet_batch(seed=4300, num_images=8, image_hw=(800, 1333), cls_mean=-5.0, cls_std=1.2)
+rcls = [t.to(dev) for t in rb.box_cls]; rreg = [t.to(dev) for t in rb.box_regression]
+ranc = [a.to(dev) for a in rb.anchors]
+ranchors = [[paa_b200.BoxList(a, rb.image_sizes[i]) for a in ranc] for i in range(8)]
+rn_cfg = NS(MODEL=NS(RETINANET=NS(INFERENCE_TH=0.05, PRE_NMS_TOP_N=1000, NMS_TH=0.4, NUM_CLASSES=81)),
+            TEST=NS(DETECTIONS_PER_IMG=100))
+rp = make_retinanet_postprocessor(rn_cfg, None)
+ms = timed(lambda: rp.run_device(rcls, rreg, None, ranchors))
+logit_bytes = sum(t.numel() * 4 for t in rcls)
+out["retinanet_post_8img_9anchors"] = {"ms": ms, "images_per_s": 8 / (ms / 1e3), "logit_MB": logit_bytes / 1e6}
+print(json.dumps(out))

@@ -208,6 +208,17 @@ int paa_anchor_visibility(const float* anchors, int64_t n, float image_w, float 
  * float32 operation order (bit-exact).  Callers check the BoxList sizes (boxlist_ops.py:95-97). */
 int paa_boxlist_iou(const float* boxes1, int n1, const float* boxes2, int n2, float* out, void* stream);
 
+/* merge_result_from_multi_scales for ONE image (engine/bbox_aug_vote.py:140-310): the detections pooled from
+ * all test-time augmentations (boxes [n,4], scores [n], labels [n] as float, n <= 65535) are merged class by
+ * class -- mode 0 'nms' (per-class NMS at nms_thresh), 1 'vote' (bbox_vote), 2 'soft-vote' (soft_bbox_vote,
+ * decayed members kept while their score stays >= soft_score_thresh) -- concatenated in class order, and cut to
+ * the rows scoring >= the max_detections-th best when there are more (max_detections <= 0: no cut).  Outputs have
+ * room for n rows (2n for soft-vote); out_count receives the number of rows. */
+size_t paa_box_vote_workspace_bytes(int n);
+int paa_box_vote(const float* boxes, const float* scores, const float* labels, int n, int mode, float vote_thresh,
+                 float nms_thresh, float soft_score_thresh, int max_detections, float* out_boxes, float* out_scores,
+                 int64_t* out_labels, int32_t* out_count, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Measurement aid (not on the reference's interface): while enabled, every launch of the chosen kernel
  * is bracketed by CUDA events on its own stream; paa_kernel_timing_end waits for them and returns the
  * summed device time and the number of launches.  Do not enable during CUDA-graph capture. */

@@ -87,6 +87,10 @@ SYMBOLS = {
     "paa_anchor_visibility": (C.c_int, [C.c_void_p, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_void_p,
                                         C.c_void_p]),
     "paa_boxlist_iou": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "paa_box_vote_workspace_bytes": (C.c_size_t, [C.c_int]),
+    "paa_box_vote": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float,
+                               C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                               C.c_void_p]),
     "paa_kernel_timing_begin": (C.c_int, [C.c_int]),
     "paa_kernel_timing_end": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
 }

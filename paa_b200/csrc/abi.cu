@@ -355,4 +355,14 @@ int paa_ml_nms(const float* boxes, const float* scores, const float* labels, int
                       static_cast<cudaStream_t>(stream));
 }
 
+size_t paa_box_vote_workspace_bytes(int n) { return box_vote_workspace_bytes(n); }
+
+int paa_box_vote(const float* boxes, const float* scores, const float* labels, int n, int mode, float vote_thresh,
+                 float nms_thresh, float soft_score_thresh, int max_detections, float* out_boxes, float* out_scores,
+                 int64_t* out_labels, int32_t* out_count, void* workspace, size_t workspace_bytes, void* stream) {
+    return run_box_vote(boxes, scores, labels, n, mode, vote_thresh, nms_thresh, soft_score_thresh, max_detections,
+                        out_boxes, out_scores, reinterpret_cast<long long*>(out_labels), out_count, workspace,
+                        workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

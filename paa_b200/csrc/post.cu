@@ -1419,4 +1419,361 @@ int run_ml_nms(const float* boxes, const float* scores, const float* labels, int
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Test-time-augmentation box merging (paa_core/engine/bbox_aug_vote.py:140-310): the
+// detections pooled from all scales / flips of one image are merged class by class.
+//   mode 0 'nms'        per-class NMS (:190-194), rows best first inside a class
+//   mode 1 'vote'       bbox_vote (:198-246)
+//   mode 2 'soft-vote'  soft_bbox_vote (:249-310)
+// One warp walks one class, exactly as the reference's while-loop does: the best remaining box is the pivot,
+// the remaining boxes with IoU(+1) >= vote_thresh to it form a group (found 32 at a time, in order), one box
+// alone passes through, several become their score-weighted mean with the pivot's score.  The arithmetic is
+// the reference's float32 numpy arithmetic: products box * score, coordinate sums accumulated row by row,
+// the score sum with numpy's pairwise rule (sequential below 8 terms, eight interleaved accumulators up to
+// 128 terms), so the merged boxes are bit-identical for groups of up to 128 boxes.
+// ---------------------------------------------------------------------------------------------
+constexpr int kVoteGroupMax = 128;
+constexpr int kVoteWarpsPerBlock = 4;
+
+// numpy's pairwise float32 sum of n <= 128 terms (numpy/core/src/umath/loops_utils.h: pairwise_sum)
+__device__ __forceinline__ float numpy_sum_f32(const float* a, int n) {
+    if (n < 8) {
+        float r = 0.0f;
+        for (int i = 0; i < n; ++i) r = __fadd_rn(r, a[i]);
+        return r;
+    }
+    float r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = a[j];
+    int i = 8;
+    for (; i < n - (n % 8); i += 8) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = __fadd_rn(r[j], a[i + j]);
+    }
+    float res = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])),
+                          __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
+    for (; i < n; ++i) res = __fadd_rn(res, a[i]);
+    return res;
+}
+
+__global__ void __launch_bounds__(kVoteWarpsPerBlock * 32)
+box_vote_kernel(const int* __restrict__ seg_start, const int* __restrict__ n_seg, const float4* __restrict__ s_box,
+                const float* __restrict__ s_score, const unsigned char* __restrict__ keep_sorted, int mode,
+                float vote_thresh, float soft_thresh, unsigned char* __restrict__ alive, float4* __restrict__ t_box,
+                float* __restrict__ t_score, int* __restrict__ t_rank, int* __restrict__ run_cnt) {
+    __shared__ float s_group[kVoteWarpsPerBlock][kVoteGroupMax];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int r = blockIdx.x * kVoteWarpsPerBlock + wib;
+    if (r >= *n_seg) return;
+    const int lo = seg_start[r], hi = seg_start[r + 1], m = hi - lo;
+    const int mult = (mode == 2) ? 2 : 1;
+    const int base = mult * lo;
+    int cnt = 0;
+    if (mode == 0) {
+        // NMS survivors, already in descending score
+        for (int c = lo; c < hi; c += 32) {
+            const int idx = c + lane;
+            const bool k = idx < hi && keep_sorted[idx] != 0;
+            const unsigned b = __ballot_sync(PAA_FULL, k);
+            if (k) {
+                const int o = base + cnt + __popc(b & ((1u << lane) - 1u));
+                t_box[o] = s_box[idx];
+                t_score[o] = s_score[idx];
+            }
+            cnt += __popc(b);
+        }
+    } else if (m <= 1) {
+        // fewer than two boxes: the class passes through (:220-221, :190-192)
+        if (m == 1 && lane == 0) {
+            t_box[base] = s_box[lo];
+            t_score[base] = s_score[lo];
+        }
+        cnt = m;
+    } else {
+        for (int c = lo + lane; c < hi; c += 32) alive[c] = 1;
+        __syncwarp();
+        int cursor = lo;
+        float* gsc = s_group[wib];
+        for (;;) {
+            // pivot: the first box still alive
+            int p = -1;
+            for (int c = cursor; c < hi && p < 0; c += 32) {
+                const unsigned b = __ballot_sync(PAA_FULL, (c + lane < hi) && alive[c + lane] != 0);
+                if (b) p = c + __ffs(b) - 1;
+            }
+            if (p < 0) break;
+            cursor = p + 1;
+            const float4 pb = s_box[p];
+            const float ps = s_score[p];
+            const float area_p = area_plus1(pb);
+            float sx = 0.f, sy = 0.f, sz = 0.f, sw = 0.f, seq = 0.f;
+            int k = 0, nd = 0;
+            for (int c = p; c < hi; c += 32) {
+                const int idx = c + lane;
+                const bool al = idx < hi && alive[idx] != 0;
+                float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
+                float sc = 0.f, o = -1.0f;
+                if (al) {
+                    bx = s_box[idx];
+                    sc = s_score[idx];
+                    o = iou_plus1(pb, area_p, bx, area_plus1(bx));
+                }
+                const bool mg = al && o >= vote_thresh;
+                unsigned b = __ballot_sync(PAA_FULL, mg);
+                if (mg) alive[idx] = 0;
+                while (b) {                 // group members in ascending index, as numpy enumerates them
+                    const int src = __ffs(b) - 1;
+                    b &= b - 1;
+                    const float gx = __shfl_sync(PAA_FULL, bx.x, src), gy = __shfl_sync(PAA_FULL, bx.y, src);
+                    const float gz = __shfl_sync(PAA_FULL, bx.z, src), gw = __shfl_sync(PAA_FULL, bx.w, src);
+                    const float gs = __shfl_sync(PAA_FULL, sc, src), go = __shfl_sync(PAA_FULL, o, src);
+                    sx = __fadd_rn(sx, __fmul_rn(gx, gs));
+                    sy = __fadd_rn(sy, __fmul_rn(gy, gs));
+                    sz = __fadd_rn(sz, __fmul_rn(gz, gs));
+                    sw = __fadd_rn(sw, __fmul_rn(gw, gs));
+                    seq = __fadd_rn(seq, gs);
+                    if (lane == 0 && k < kVoteGroupMax) gsc[k] = gs;
+                    if (mode == 2) {
+                        // decayed copy of the member; whether it is kept is only known to matter for groups of
+                        // two or more, where it follows the merged row
+                        const float dec = __fmul_rn(gs, __fsub_rn(1.0f, go));
+                        if (dec >= soft_thresh) {
+                            if (lane == 0) {
+                                t_box[base + cnt + 1 + nd] = make_float4(gx, gy, gz, gw);
+                                t_score[base + cnt + 1 + nd] = dec;
+                            }
+                            ++nd;
+                        }
+                    }
+                    ++k;
+                }
+            }
+            __syncwarp();
+            if (k <= 1) {
+                if (lane == 0) {
+                    t_box[base + cnt] = pb;
+                    t_score[base + cnt] = ps;
+                }
+                cnt += 1;
+            } else {
+                float ssum = seq;
+                if (k <= kVoteGroupMax) ssum = numpy_sum_f32(gsc, k);     // every lane reads the same values
+                if (lane == 0) {
+                    t_box[base + cnt] = make_float4(__fdiv_rn(sx, ssum), __fdiv_rn(sy, ssum), __fdiv_rn(sz, ssum),
+                                                    __fdiv_rn(sw, ssum));
+                    t_score[base + cnt] = ps;                           // the pivot carries the group's maximum
+                }
+                cnt += 1 + nd;
+            }
+            __syncwarp();
+        }
+    }
+    __syncwarp();
+    // position of every row inside its class: as produced, or by descending score for soft-vote (:303-304)
+    for (int i = lane; i < cnt; i += 32) {
+        int rank = i;
+        if (mode == 2 && m > 1) {
+            const float si = t_score[base + i];
+            rank = 0;
+            for (int q = 0; q < cnt; ++q) {
+                const float sq = t_score[base + q];
+                rank += (sq > si || (sq == si && q > i)) ? 1 : 0;      // reversed stable order on ties
+            }
+        }
+        t_rank[base + i] = rank;
+    }
+    if (lane == 0) run_cnt[r] = cnt;
+}
+
+// One block: class offsets, the max_detections cut (kthvalue, :163-172; ties keep more), output rows.
+__global__ void __launch_bounds__(1024)
+box_vote_finish_kernel(const int* __restrict__ seg_start, const int* __restrict__ n_seg,
+                       const int* __restrict__ s_label, int mult, const float4* __restrict__ t_box,
+                       const float* __restrict__ t_score, const int* __restrict__ t_rank,
+                       const int* __restrict__ run_cnt, int max_det, int* __restrict__ run_off,
+                       float4* __restrict__ u_box, float* __restrict__ u_score, int* __restrict__ u_label,
+                       float* __restrict__ out_boxes, float* __restrict__ out_scores,
+                       long long* __restrict__ out_labels, int* __restrict__ out_count) {
+    __shared__ int s_hist[256];
+    __shared__ int s_warp[32];
+    __shared__ int s_running, s_need, s_total;
+    __shared__ unsigned s_prefix;
+    const int runs = *n_seg;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {                         // a few dozen classes: serial exclusive scan
+        int t = 0;
+        for (int r = 0; r < runs; ++r) {
+            run_off[r] = t;
+            t += run_cnt[r];
+        }
+        s_total = t;
+    }
+    __syncthreads();
+    const int total = s_total;
+    // rows of all classes, class-major, in their final in-class order
+    for (int r = warp; r < runs; r += 32) {
+        const int base = mult * seg_start[r], cnt = run_cnt[r], off = run_off[r];
+        const int label = s_label[seg_start[r]];
+        for (int i = lane; i < cnt; i += 32) {
+            const int o = off + t_rank[base + i];
+            u_box[o] = t_box[base + i];
+            u_score[o] = t_score[base + i];
+            u_label[o] = label;
+        }
+    }
+    __syncthreads();
+    unsigned thr_bits = 0u;
+    if (max_det > 0 && total > max_det) {
+        if (threadIdx.x == 0) {
+            s_prefix = 0u;
+            s_need = max_det;
+        }
+        __syncthreads();
+        for (int pass = 0; pass < 4; ++pass) {
+            const int shift = 24 - 8 * pass;
+            for (int b = threadIdx.x; b < 256; b += 1024) s_hist[b] = 0;
+            __syncthreads();
+            const unsigned prefix = s_prefix;
+            const unsigned hi_mask = (pass == 0) ? 0u : (~0u << (shift + 8));
+            for (int i = threadIdx.x; i < total; i += 1024) {
+                const unsigned key = __float_as_uint(u_score[i]);
+                if ((key & hi_mask) == prefix) atomicAdd(&s_hist[(key >> shift) & 0xff], 1);
+            }
+            __syncthreads();
+            if (threadIdx.x < 32) {
+                int d, remaining;
+                radix_pick_digit(s_hist, s_need, threadIdx.x, &d, &remaining);
+                if (threadIdx.x == 0) {
+                    s_need = remaining;
+                    s_prefix = prefix | ((unsigned)d << shift);
+                }
+            }
+            __syncthreads();
+        }
+        thr_bits = s_prefix;
+    }
+    if (threadIdx.x == 0) s_running = 0;
+    __syncthreads();
+    for (int i0 = 0; i0 < total; i0 += 1024) {
+        const int i = i0 + threadIdx.x;
+        const bool take = i < total && __float_as_uint(u_score[i]) >= thr_bits;
+        const unsigned mk = __ballot_sync(PAA_FULL, take);
+        if (lane == 0) s_warp[warp] = __popc(mk);
+        __syncthreads();
+        int before = s_running;
+        for (int w = 0; w < warp; ++w) before += s_warp[w];
+        if (take) {
+            const int row = before + __popc(mk & ((1u << lane) - 1u));
+            const float4 b = u_box[i];
+            out_boxes[row * 4 + 0] = b.x;
+            out_boxes[row * 4 + 1] = b.y;
+            out_boxes[row * 4 + 2] = b.z;
+            out_boxes[row * 4 + 3] = b.w;
+            out_scores[row] = u_score[i];
+            out_labels[row] = (long long)u_label[i];
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int t = 0;
+            for (int w = 0; w < 32; ++w) t += s_warp[w];
+            s_running += t;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out_count = s_running;
+}
+
+struct VoteWorkspace {
+    MlNmsWorkspace nms;
+    unsigned char* alive;   // [n]
+    float4* t_box;          // [2n]
+    float* t_score;         // [2n]
+    int* t_rank;            // [2n]
+    int* run_cnt;           // [n]
+    int* run_off;           // [n]
+    float4* u_box;          // [2n]
+    float* u_score;         // [2n]
+    int* u_label;           // [2n]
+    size_t total_bytes;
+};
+
+static VoteWorkspace carve_vote(void* base, int n) {
+    VoteWorkspace w;
+    w.nms = carve_ml_nms(base, n);
+    char* p = static_cast<char*>(base);
+    size_t off = w.nms.total_bytes;
+    auto take = [&](size_t bytes) {
+        char* q = p ? p + off : nullptr;
+        off += (bytes + 255) / 256 * 256;
+        return q;
+    };
+    const size_t nn = n > 0 ? n : 1;
+    w.alive = (unsigned char*)take(nn);
+    w.t_box = (float4*)take(2 * nn * 16);
+    w.t_score = (float*)take(2 * nn * 4);
+    w.t_rank = (int*)take(2 * nn * 4);
+    w.run_cnt = (int*)take(nn * 4);
+    w.run_off = (int*)take(nn * 4);
+    w.u_box = (float4*)take(2 * nn * 16);
+    w.u_score = (float*)take(2 * nn * 4);
+    w.u_label = (int*)take(2 * nn * 4);
+    w.total_bytes = off;
+    return w;
+}
+
+size_t box_vote_workspace_bytes(int n) { return carve_vote(nullptr, n).total_bytes; }
+
+int run_box_vote(const float* boxes, const float* scores, const float* labels, int n, int mode, float vote_thresh,
+                 float nms_thresh, float soft_score_thresh, int max_detections, float* out_boxes, float* out_scores,
+                 long long* out_labels, int32_t* out_count, void* workspace, size_t workspace_bytes,
+                 cudaStream_t stream) {
+    if (n < 0 || n > 65535 || mode < 0 || mode > 2) {
+        set_error("paa_box_vote: n=%d outside [0, 65535] or mode=%d", n, mode);
+        return PAA_ERR_UNSUPPORTED;
+    }
+    if (!out_count) {
+        set_error("paa_box_vote: null out_count");
+        return PAA_ERR_BAD_ARGUMENT;
+    }
+    PAA_CUDA_CHECK(cudaMemsetAsync(out_count, 0, sizeof(int32_t), stream));
+    if (n == 0) return 0;
+    if (!boxes || !scores || !labels || !out_boxes || !out_scores || !out_labels || !workspace) {
+        set_error("paa_box_vote: null pointer");
+        return PAA_ERR_BAD_ARGUMENT;
+    }
+    VoteWorkspace w = carve_vote(workspace, n);
+    if (w.total_bytes > workspace_bytes) {
+        set_error("paa_box_vote: workspace too small: need %zu bytes, got %zu", w.total_bytes, workspace_bytes);
+        return PAA_ERR_WORKSPACE;
+    }
+    const int nbw = (n + 63) / 64;
+    ml_nms_prepare_kernel<<<(n + 255) / 256, 256, 0, stream>>>(n, boxes, labels, w.nms.box, w.nms.label, w.nms.cnt);
+    PAA_LAUNCH_CHECK("ml_nms_prepare_kernel");
+    dim3 rgrid((n + kRankThreads - 1) / kRankThreads, 1);
+    post_rank_kernel<<<rgrid, kRankThreads, 0, stream>>>(1, n, w.nms.cnt, w.nms.box, scores, w.nms.label, w.nms.s_box,
+                                                         w.nms.s_score, w.nms.s_label, w.nms.s_pos, w.nms.total);
+    PAA_LAUNCH_CHECK("post_rank_kernel");
+    post_segments_kernel<<<1, 1024, 0, stream>>>(n, w.nms.total, w.nms.s_label, w.nms.seg_start, w.nms.n_seg);
+    PAA_LAUNCH_CHECK("post_segments_kernel");
+    if (mode == 0) {
+        dim3 mgrid(nbw, 1);
+        post_nms_mask_kernel<<<mgrid, 64, 0, stream>>>(n, nbw, nms_thresh, w.nms.total, w.nms.s_box, w.nms.s_label,
+                                                       w.nms.mask);
+        PAA_LAUNCH_CHECK("post_nms_mask_kernel");
+        post_nms_scan_kernel<<<(n + kScanWarps - 1) / kScanWarps, kScanWarps * 32, 0, stream>>>(
+            n, nbw, n, 1, w.nms.seg_start, w.nms.n_seg, w.nms.mask, w.nms.keep_sorted);
+        PAA_LAUNCH_CHECK("post_nms_scan_kernel");
+    }
+    box_vote_kernel<<<(n + kVoteWarpsPerBlock - 1) / kVoteWarpsPerBlock, kVoteWarpsPerBlock * 32, 0, stream>>>(
+        w.nms.seg_start, w.nms.n_seg, w.nms.s_box, w.nms.s_score, w.nms.keep_sorted, mode, vote_thresh,
+        soft_score_thresh, w.alive, w.t_box, w.t_score, w.t_rank, w.run_cnt);
+    PAA_LAUNCH_CHECK("box_vote_kernel");
+    box_vote_finish_kernel<<<1, 1024, 0, stream>>>(w.nms.seg_start, w.nms.n_seg, w.nms.s_label, mode == 2 ? 2 : 1,
+                                                   w.t_box, w.t_score, w.t_rank, w.run_cnt, max_detections, w.run_off,
+                                                   w.u_box, w.u_score, w.u_label, out_boxes, out_scores, out_labels,
+                                                   out_count);
+    PAA_LAUNCH_CHECK("box_vote_finish_kernel");
+    return 0;
+}
+
 }  // namespace paa

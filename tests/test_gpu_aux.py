@@ -161,3 +161,50 @@ def test_fcos_postprocessor_against_oracle():
     for i in range(b.num_images):
         assert len(got[i]) > 0
         _same_detections(got, want, i)
+
+
+def _tta_detections(seed, n_classes_used=6, per_class=(0, 1, 2, 40, 150, 400)):
+    """Pooled multi-scale detections: clusters of overlapping boxes per class, distinct scores."""
+    g = torch.Generator().manual_seed(seed)
+    boxes, labels = [], []
+    for j, n in enumerate(per_class[:n_classes_used]):
+        if n == 0:
+            continue
+        n_obj = max(1, n // 7)
+        ctr = torch.rand((n_obj, 2), generator=g) * 500
+        size = 40 + torch.rand((n_obj, 2), generator=g) * 120
+        which = torch.randint(0, n_obj, (n,), generator=g)
+        xy = ctr[which] + torch.randn((n, 2), generator=g) * 5
+        wh = size[which] * (1 + 0.08 * torch.randn((n, 2), generator=g))
+        boxes.append(torch.cat([xy, xy + wh], 1))
+        labels.append(torch.full((n,), 3 * j + 1, dtype=torch.int64))
+    boxes, labels = torch.cat(boxes), torch.cat(labels)
+    scores = torch.randperm(boxes.shape[0], generator=g).float() / boxes.shape[0] * 0.9 + 0.06   # all distinct
+    perm = torch.randperm(boxes.shape[0], generator=g)
+    return boxes[perm], scores[perm], labels[perm]
+
+
+@pytest.mark.parametrize("nms_type", ["nms", "vote", "soft-vote"])
+@pytest.mark.parametrize("max_det", [1000, 60])
+def test_tta_merge_against_oracle(nms_type, max_det):
+    import paa_b200
+    from types import SimpleNamespace as NS
+    from oracle import vote_oracle
+    from paa_b200.bbox_aug_vote import merge_result_from_multi_scales
+    cfg = NS(MODEL=NS(RETINANET=NS(NUM_CLASSES=81, INFERENCE_TH=0.05), ATSS=NS(NMS_TH=0.6, PRE_NMS_TOP_N=max_det)))
+    lists, want = [], []
+    for seed in (11, 12):
+        b, s, l = _tta_detections(seed)
+        bl = paa_b200.BoxList(b.cuda(), (640, 640))
+        bl.add_field("scores", s.cuda())
+        bl.add_field("labels", l.cuda())
+        lists.append(bl)
+        want.append(vote_oracle.merge_multi_scale(b.numpy(), s.numpy(), l.numpy(), 81, merge_type=nms_type,
+                                                  vote_thresh=0.66, nms_thresh=0.6, max_detections=max_det,
+                                                  score_thresh=0.05))
+    got = merge_result_from_multi_scales(lists, cfg, nms_type=nms_type, vote_thresh=0.66)
+    for r, (wb, ws, wl) in zip(got, want):
+        assert len(r) == wb.shape[0]
+        np.testing.assert_array_equal(r.get_field("labels").cpu().numpy(), wl)
+        np.testing.assert_array_equal(r.get_field("scores").cpu().numpy(), ws)
+        np.testing.assert_array_equal(r.bbox.cpu().numpy(), wb)          # float32 numpy arithmetic, bit for bit

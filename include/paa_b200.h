@@ -62,7 +62,8 @@ typedef struct PaaLevel {
     float* grad_box_regression;
     float* grad_iou_pred;
     int32_t hw;
-    int32_t reserved;
+    int32_t grid_w;               /* W of the level's H x W map (hw = H*W), or 0 if unknown: lets the IoU matching
+                                     take 2-D patches of anchors per warp instead of runs of a row */
 } PaaLevel;
 
 typedef struct PaaLossArgs {

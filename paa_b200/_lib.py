@@ -24,7 +24,7 @@ _fp = C.POINTER(C.c_float)
 class PaaLevel(C.Structure):
     _fields_ = [("box_cls", C.c_void_p), ("box_regression", C.c_void_p), ("iou_pred", C.c_void_p),
                 ("anchors", C.c_void_p), ("grad_box_cls", C.c_void_p), ("grad_box_regression", C.c_void_p),
-                ("grad_iou_pred", C.c_void_p), ("hw", C.c_int32), ("reserved", C.c_int32)]
+                ("grad_iou_pred", C.c_void_p), ("hw", C.c_int32), ("grid_w", C.c_int32)]
 
 
 class PaaLossArgs(C.Structure):

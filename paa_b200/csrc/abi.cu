@@ -80,6 +80,7 @@ static int build_geometry(int num_images, int num_levels, int num_classes, int a
         v.g_reg = s.grad_box_regression;
         v.g_iou = s.grad_iou_pred;
         v.hw = s.hw;
+        v.grid_w = (s.grid_w > 0 && s.hw % s.grid_w == 0) ? s.grid_w : 0;
         v.n_anchor = s.hw * anchors_per_loc;
         v.a_off = a_off;
         v.tile_off = t_off;

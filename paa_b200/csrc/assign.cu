@@ -54,6 +54,12 @@ struct Pass1Plan {
     // tiles of the coarse levels, whose anchors overlap every GT, are additionally cut into `parts` ranges of
     // the GT list (their per-anchor results meet in an atomicMax), so that no warp walks hundreds of GTs alone
     int light_tiles, light_pairs, heavy_pairs, parts;
+    // With the grid width of the fine levels known (and one anchor per location) a block of the IoU matching
+    // takes a 32 x 8 region of a level's grid instead of two runs of 128 consecutive anchors, and a warp an
+    // 8 x 4 patch instead of 32 neighbours in a row: a compact footprint intersects ~35 % fewer GT boxes.
+    int patches;                                 // 1: fine levels are matched in patches
+    unsigned patch_off[PAA_MAX_LEVELS + 1];      // first region of each fine level (per image)
+    int patch_rx[PAA_MAX_LEVELS];                // regions per grid row
 };
 
 // (IoU bits, GT) of an anchor's best GT as one 64-bit key whose integer order is "larger IoU, then smaller GT
@@ -112,13 +118,31 @@ __device__ __forceinline__ void iou_best_block(const Geometry& geo, const GtOffs
         tile0 = 2 * (plan.light_pairs - 1 - (int)(r / geo.num_images));
         tile_end = plan.light_tiles;
     }
-    const int tile = tile0 + (threadIdx.x >> 7);
-    const bool tile_ok = tile < tile_end;
-    int first = 0;
-    const int l = tile_ok ? tile_level(geo, tile, &first) : 0;
+    int l = 0, i = 0;
+    bool valid = false;
+    if (q >= heavy_items && plan.patches) {
+        // region index inside the image, coarsest fine level first
+        const unsigned per_image = plan.patch_off[PAA_MAX_LEVELS];
+        const unsigned reg = per_image - 1u - (q - heavy_items) / geo.num_images;
+#pragma unroll
+        for (int k = 1; k < PAA_MAX_LEVELS; ++k)
+            if (k < geo.num_levels && plan.patch_off[k] <= reg && plan.patch_off[k] < per_image) l = k;
+        const int rr = (int)(reg - plan.patch_off[l]);
+        const int W = geo.lv[l].grid_w, H = geo.lv[l].hw / W;
+        const int ry = rr / plan.patch_rx[l], rx = rr - ry * plan.patch_rx[l];
+        const int w = threadIdx.x >> 5, ln = threadIdx.x & 31;
+        const int col = rx * 32 + 8 * (w & 3) + (ln & 7), row = ry * 8 + 4 * (w >> 2) + (ln >> 3);
+        valid = col < W && row < H;
+        i = row * W + col;
+    } else {
+        const int tile = tile0 + (threadIdx.x >> 7);
+        const bool tile_ok = tile < tile_end;
+        int first = 0;
+        l = tile_ok ? tile_level(geo, tile, &first) : 0;
+        i = first + (threadIdx.x & (PAA_TILE - 1));
+        valid = tile_ok && i < geo.lv[l].n_anchor;
+    }
     const LevelView& lv = geo.lv[l];
-    const int i = first + (threadIdx.x & (PAA_TILE - 1));
-    const bool valid = tile_ok && i < lv.n_anchor;
     const int lane = threadIdx.x & 31;
 
     float4 a = make_float4(INFINITY, INFINITY, -INFINITY, -INFINITY);
@@ -350,7 +374,25 @@ int launch_assign_pass1(const Geometry& geo, const GtOffsets& go, const float* g
     plan.light_pairs = (plan.light_tiles + 1) / 2;
     plan.heavy_pairs = (geo.tiles_per_image - plan.light_tiles + 1) / 2;
     plan.parts = gt_parts(go, geo.num_images);
-    plan.iou_blocks = (unsigned)geo.num_images * (unsigned)(plan.light_pairs + plan.heavy_pairs * plan.parts);
+    // fine levels in 2-D patches when their grid widths are known
+    plan.patches = geo.apl == 1 ? 1 : 0;
+    unsigned regions = 0;
+    for (int l = 0; l < PAA_MAX_LEVELS; ++l) {
+        plan.patch_off[l] = regions;
+        plan.patch_rx[l] = 1;
+        if (l >= heavy_level) continue;
+        const LevelView& lv = geo.lv[l];
+        if (lv.grid_w <= 0) {
+            plan.patches = 0;
+            continue;
+        }
+        plan.patch_rx[l] = (lv.grid_w + 31) / 32;
+        regions += (unsigned)plan.patch_rx[l] * (unsigned)((lv.hw / lv.grid_w + 7) / 8);
+    }
+    plan.patch_off[PAA_MAX_LEVELS] = regions;
+    if (regions == 0) plan.patches = 0;
+    const unsigned light_items = plan.patches ? regions : (unsigned)plan.light_pairs;
+    plan.iou_blocks = (unsigned)geo.num_images * (light_items + (unsigned)(plan.heavy_pairs * plan.parts));
     const unsigned grid = plan.sum_blocks + plan.iou_blocks;
     KernelTimer timer(PAA_KERNEL_PASS1, stream);
     if (sc.gamma == 2.0f)

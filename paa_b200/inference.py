@@ -86,6 +86,7 @@ class PAAPostProcessor(torch.nn.Module):
             s.iou_pred = lv["iou"][l].data_ptr() if lv["iou"] is not None else None
             s.anchors = lv["anchor_ptrs"][l]
             s.hw = lv["hw"][l]
+            s.grid_w = int(lv["cls"][l].shape[-1])
         for i in range(N):
             w, h = anchors[i][0].size
             args.image_wh[i][0], args.image_wh[i][1] = float(w), float(h)

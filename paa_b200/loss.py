@@ -259,6 +259,7 @@ class PAALossComputation(object):
             s.iou_pred = lv["iou"][l].data_ptr() if has_iou else None
             s.anchors = lv["anchor_ptrs"][l]
             s.hw = lv["hw"][l]
+            s.grid_w = int(lv["cls"][l].shape[-1])
             if grads is not None:
                 s.grad_box_cls, s.grad_box_regression = grads["cls"][l].data_ptr(), grads["reg"][l].data_ptr()
                 s.grad_iou_pred = grads["iou"][l].data_ptr() if has_iou else None

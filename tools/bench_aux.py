@@ -82,4 +82,26 @@ rp = make_retinanet_postprocessor(rn_cfg, None)
 ms = timed(lambda: rp.run_device(rcls, rreg, None, ranchors))
 logit_bytes = sum(t.numel() * 4 for t in rcls)
 out["retinanet_post_8img_9anchors"] = {"ms": ms, "images_per_s": 8 / (ms / 1e3), "logit_MB": logit_bytes / 1e6}
+# TTA merging: 14 augmentations x ~100 detections of one image, 20 classes present
+from paa_b200.bbox_aug_vote import merge_result_from_multi_scales
+from oracle import vote_oracle
+g = torch.Generator().manual_seed(9)
+n_obj, n_aug = 100, 14
+ctr = torch.rand((n_obj, 2), generator=g) * 900
+size = 40 + torch.rand((n_obj, 2), generator=g) * 200
+lab = torch.randint(1, 21, (n_obj,), generator=g)
+which = torch.arange(n_obj).repeat(n_aug)
+xy = ctr[which] + torch.randn((n_obj * n_aug, 2), generator=g) * 4
+wh = size[which] * (1 + 0.05 * torch.randn((n_obj * n_aug, 2), generator=g))
+tb = torch.cat([xy, xy + wh], 1)
+ts = torch.randperm(n_obj * n_aug, generator=g).float() / (n_obj * n_aug) * 0.9 + 0.06
+tl = lab[which]
+bl = paa_b200.BoxList(tb.to(dev), (1333, 800)); bl.add_field("scores", ts.to(dev)); bl.add_field("labels", tl.to(dev))
+tcfg = NS(MODEL=NS(RETINANET=NS(NUM_CLASSES=81, INFERENCE_TH=0.05), ATSS=NS(NMS_TH=0.6, PRE_NMS_TOP_N=1000)))
+for kind in ("vote", "soft-vote"):
+    ms = timed(lambda: merge_result_from_multi_scales([bl], tcfg, kind, 0.66))
+    t0 = time.perf_counter()
+    vote_oracle.merge_multi_scale(tb.numpy(), ts.numpy(), tl.numpy(), 81, merge_type=kind, vote_thresh=0.66)
+    out["tta_merge_%s_1400_boxes" % kind.replace("-", "_")] = {"ms": ms, "cpu_numpy_port_ms": (time.perf_counter() - t0) * 1e3,
+                                                              "note": "includes the host read of the result count"}
 print(json.dumps(out))

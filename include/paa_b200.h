@@ -74,7 +74,9 @@ typedef struct PaaLossArgs {
     int32_t topk;                 /* cfg.MODEL.PAA.TOPK (9) */
     int32_t use_iou_pred;         /* cfg.MODEL.PAA.USE_IOU_PRED */
     int32_t world_size;           /* WORLD_SIZE as read by loss.py:18-19 */
-    int32_t reserved0;
+    int32_t loss_flavour;         /* PAA_LOSS_PAA: regression weight / BCE target = IoU(pred, target) (paa/loss.py:331-349);
+                                     PAA_LOSS_ATSS: = centerness target (atss/loss.py:233-245,262-272), assignment by
+                                     paa_atss_assign */
     float gamma, alpha;           /* focal loss, cfg.MODEL.PAA.LOSS_GAMMA / LOSS_ALPHA */
     float iou_threshold;          /* Matcher high == low threshold (loss.py:38-40) */
     float reg_loss_weight;        /* cfg.MODEL.PAA.REG_LOSS_WEIGHT */
@@ -154,6 +156,8 @@ typedef struct PaaPostArgs {
     float decode_weights[4];      /* PAA_DECODE_LEGACY: wx, wy, ww, wh */
     float decode_clip;            /* PAA_DECODE_LEGACY: bbox_xform_clip (log(1000/16)) */
 } PaaPostArgs;
+#define PAA_LOSS_PAA  0
+#define PAA_LOSS_ATSS 1
 #define PAA_DECODE_ATSS_BOX 0
 #define PAA_DECODE_LEGACY   1
 #define PAA_DECODE_LTRB     2
@@ -194,6 +198,13 @@ int paa_sigmoid_focal_loss_forward(const float* logits, const int32_t* targets, 
 int paa_sigmoid_focal_loss_backward(const float* logits, const int32_t* targets, const float* d_losses,
                                     int n, int num_classes, float gamma, float alpha, float* d_logits,
                                     void* stream);
+
+/* ATSS anchor assignment (rpn/atss/loss.py:139-197, POSITIVE_TYPE 'ATSS') in place of paa_assign: per GT and
+ * level the `topk` anchors nearest to the GT centre, IoU threshold = mean + std of their IoUs, centre inside
+ * the GT, conflicts to the larger IoU.  Same arguments / workspace / normalisers protocol as paa_assign
+ * (normalisers = {num_pos, sum of centerness targets}); follow with paa_loss and loss_flavour = PAA_LOSS_ATSS.
+ * dbg_cand_idx receives the candidates (level-major, nearest first), dbg_gmm[g*8] the GT's IoU threshold. */
+int paa_atss_assign(const PaaLossArgs* args, void* stream);
 
 /* ---- operators on either side of the path ----------------------------------------- */
 /* AnchorGenerator.grid_anchors (anchor_generator.py:73-95) for one level: out[(y*W + x)*a + k] =

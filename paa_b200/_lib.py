@@ -30,7 +30,7 @@ class PaaLevel(C.Structure):
 class PaaLossArgs(C.Structure):
     _fields_ = [("num_images", C.c_int32), ("num_levels", C.c_int32), ("num_classes", C.c_int32),
                 ("anchors_per_loc", C.c_int32), ("topk", C.c_int32), ("use_iou_pred", C.c_int32),
-                ("world_size", C.c_int32), ("reserved0", C.c_int32),
+                ("world_size", C.c_int32), ("loss_flavour", C.c_int32),
                 ("gamma", C.c_float), ("alpha", C.c_float), ("iou_threshold", C.c_float),
                 ("reg_loss_weight", C.c_float), ("iou_loss_weight", C.c_float), ("reserved1", C.c_float),
                 ("anchor_image_stride", C.c_int64),
@@ -63,6 +63,7 @@ class PaaPostArgs(C.Structure):
                 ("box_decode", C.c_int32), ("decode_weights", C.c_float * 4), ("decode_clip", C.c_float)]
 
 DECODE_ATSS_BOX, DECODE_LEGACY, DECODE_LTRB = 0, 1, 2
+LOSS_PAA, LOSS_ATSS = 0, 1
 
 
 # name -> (restype, argtypes); every symbol include/paa_b200.h declares
@@ -73,6 +74,7 @@ SYMBOLS = {
     "paa_postprocess_workspace_bytes": (C.c_size_t, [C.c_int] * 5),
     "paa_assign": (C.c_int, [C.POINTER(PaaLossArgs), C.c_void_p]),
     "paa_loss": (C.c_int, [C.POINTER(PaaLossArgs), C.c_void_p]),
+    "paa_atss_assign": (C.c_int, [C.POINTER(PaaLossArgs), C.c_void_p]),
     "paa_assign_loss": (C.c_int, [C.POINTER(PaaLossArgs), C.c_void_p]),
     "paa_rescale_grads": (C.c_int, [C.POINTER(PaaLossArgs), C.c_void_p, C.c_void_p, C.c_void_p]),
     "paa_postprocess": (C.c_int, [C.POINTER(PaaPostArgs), C.c_void_p]),

@@ -174,6 +174,11 @@ static int plan_loss(const PaaLossArgs* a, LossPlan* p) {
     p->sc.topk = a->topk;
     p->sc.use_iou_pred = a->use_iou_pred;
     p->sc.world_size = a->world_size;
+    p->sc.flavour = a->loss_flavour;
+    if (a->loss_flavour != PAA_LOSS_PAA && a->loss_flavour != PAA_LOSS_ATSS) {
+        set_error("loss_flavour=%d", a->loss_flavour);
+        return PAA_ERR_BAD_ARGUMENT;
+    }
     {
         // test hook: a smaller pool forces the overflow path of the candidate selection
         const char* e = getenv("PAA_SEG_CAP");
@@ -250,6 +255,30 @@ int paa_assign(const PaaLossArgs* args, void* stream_) {
         return rc;
     if ((rc = launch_select_gmm(p.geo, p.go, p.sumG, args->gt_boxes, args->gt_labels, p.sc, p.ws, score_src,
                                 args->normalisers, p.px, p.dbg, stream)))
+        return rc;
+    if (args->dbg_paa_labels)
+        PAA_CUDA_CHECK(cudaMemcpyAsync(args->dbg_paa_labels, p.ws.paa_label,
+                                       sizeof(int) * (size_t)args->num_images * p.geo.A,
+                                       cudaMemcpyDeviceToDevice, stream));
+    return 0;
+}
+
+int paa_atss_assign(const PaaLossArgs* args, void* stream_) {
+    LossPlan p;
+    int rc = plan_loss(args, &p);
+    if (rc) return rc;
+    for (int l = 0; l < p.geo.num_levels; ++l)
+        if (p.geo.lv[l].n_anchor < args->topk) {
+            // torch.topk(k) on fewer than k anchors: "selected index k out of range" (atss/loss.py:159)
+            set_error("selected index k out of range: level %d has %d anchors, TOPK is %d", l, p.geo.lv[l].n_anchor,
+                      args->topk);
+            return PAA_ERR_UNSUPPORTED;
+        }
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    PAA_CUDA_CHECK(cudaMemsetAsync(args->workspace, 0, p.ws.zero_bytes, stream));
+    PAA_CUDA_CHECK(cudaMemsetAsync(p.ws.best, 0, sizeof(uint2) * (size_t)args->num_images * p.geo.A, stream));
+    if ((rc = launch_atss_assign(p.geo, p.go, p.sumG, args->gt_boxes, args->gt_labels, p.sc, p.ws, args->normalisers,
+                                 p.px, p.dbg, stream)))
         return rc;
     if (args->dbg_paa_labels)
         PAA_CUDA_CHECK(cudaMemcpyAsync(args->dbg_paa_labels, p.ws.paa_label,

@@ -8,6 +8,7 @@ namespace paa {
 struct LossScalars {
     float gamma, alpha, iou_threshold, reg_loss_weight, iou_loss_weight;
     int topk, use_iou_pred, world_size;
+    int flavour;       // PAA_LOSS_PAA / PAA_LOSS_ATSS
     int seg_cap;       // usable entries of a (GT, level) candidate pool, <= kSegCap (PAA_SEG_CAP shrinks it for tests)
 };
 
@@ -44,6 +45,10 @@ int launch_select_gmm(const Geometry& geo, const GtOffsets& go, int num_gt_total
                       const int64_t* gt_labels, const LossScalars& sc, const LossWorkspace& ws,
                       const float* score_src, double* normalisers, const PeerExchange& px, const LossDebug& dbg,
                       cudaStream_t stream);
+// atss.cu
+int launch_atss_assign(const Geometry& geo, const GtOffsets& go, int num_gt_total, const float* gt_boxes,
+                       const int64_t* gt_labels, const LossScalars& sc, const LossWorkspace& ws, double* normalisers,
+                       const PeerExchange& px, const LossDebug& dbg, cudaStream_t stream);
 int launch_norm_wait(const PeerExchange& px, double* normalisers, cudaStream_t stream);
 
 // loss.cu

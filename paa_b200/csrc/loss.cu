@@ -232,8 +232,13 @@ __device__ __forceinline__ void positive_box_terms(const Geometry& geo, const Le
     const float4 tgt = decode_box(encode_box(gt, f), f);
     float w = 1.0f;
     if (sc.use_iou_pred) {
-        const float4 pred = decode_box(d, f);
-        const float q = iou_plus1(tgt, area_plus1(tgt), pred, area_plus1(pred));
+        float q;
+        if (sc.flavour == PAA_LOSS_ATSS) {
+            q = centerness_target(tgt, f);                       // atss/loss.py:233-245
+        } else {
+            const float4 pred = decode_box(d, f);
+            q = iou_plus1(tgt, area_plus1(tgt), pred, area_plus1(pred));
+        }
         const float ei = expf(-fabsf(xi));
         *bce_sum += fmaxf(xi, 0.0f) - xi * q + log1pf(ei);
         const float sig = (xi >= 0.0f) ? 1.0f / (1.0f + ei) : ei / (1.0f + ei);

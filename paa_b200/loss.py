@@ -211,6 +211,7 @@ class PAALossComputation(object):
         self.teacher_combined_loss = None   # [N, A] float32 cuda tensor: stage-wise parity protocol
         self._workspace = None
         self._ones = None
+        self._flavour = _lib.LOSS_PAA       # which assignment / weighting the kernels apply (ATSS subclass)
 
     # -- plumbing -------------------------------------------------------------------------------
     def _workspace_for(self, device, nbytes):
@@ -245,6 +246,7 @@ class PAALossComputation(object):
         args.num_images, args.num_levels, args.num_classes = N, L, lv["C"]
         args.anchors_per_loc, args.topk = lv["apl"], self.topk
         args.use_iou_pred, args.world_size = int(has_iou), world
+        args.loss_flavour = self._flavour
         args.gamma, args.alpha, args.iou_threshold = self.gamma, self.alpha, self.iou_threshold
         args.reg_loss_weight, args.iou_loss_weight = self.reg_loss_weight, self.iou_loss_weight
         args.anchor_image_stride = lv["anchor_stride"]
@@ -294,19 +296,17 @@ class PAALossComputation(object):
             assert teacher.shape == (N, A)
             args.teacher_combined_loss = teacher.data_ptr()
         stream = torch.cuda.current_stream(device).cuda_stream
+        assign = self._lib.paa_atss_assign if self._flavour == _lib.LOSS_ATSS else self._lib.paa_assign
         with torch.cuda.device(device):
-            if world > 1:
-                peer = PeerNormExchange.get(device)
-                if peer is not None:
-                    args.rank = peer.rank
-                    for r, ptr in enumerate(peer.ptrs):
-                        args.peer_norm[r] = ptr
-                _lib.check(self._lib.paa_assign(C.byref(args), stream), "paa_assign")
-                if peer is None:
-                    reduce_normalisers(normalisers)                     # loss.py:321,338 in one message
-                _lib.check(self._lib.paa_loss(C.byref(args), stream), "paa_loss")
-            else:
-                _lib.check(self._lib.paa_assign_loss(C.byref(args), stream), "paa_assign_loss")
+            peer = PeerNormExchange.get(device) if world > 1 else None
+            if peer is not None:
+                args.rank = peer.rank
+                for r, ptr in enumerate(peer.ptrs):
+                    args.peer_norm[r] = ptr
+            _lib.check(assign(C.byref(args), stream), "paa_atss_assign" if self._flavour else "paa_assign")
+            if world > 1 and peer is None:
+                reduce_normalisers(normalisers)                         # loss.py:321,338 in one message
+            _lib.check(self._lib.paa_loss(C.byref(args), stream), "paa_loss")
         if dbg is not None:
             dbg["normalisers"] = normalisers
             dbg["gt_offsets"] = offsets
@@ -349,3 +349,43 @@ class PAALossComputation(object):
 
 def make_paa_loss_evaluator(cfg, box_coder):
     return PAALossComputation(cfg, box_coder)      # loss.py:362-364
+
+
+class ATSSLossComputation(PAALossComputation):
+    """Drop-in for paa_core.modeling.rpn.atss.loss.ATSSLossComputation with POSITIVE_TYPE 'ATSS' (atss/loss.py:
+    27-279).  Anchors are assigned by the ATSS rule (`paa_atss_assign`), the losses come from the
+    same streaming pass as PAA's with the centerness targets as regression weights / BCE targets.  Returns
+    ``(cls_loss, reg_loss * REG_LOSS_WEIGHT, centerness_loss)`` like the reference."""
+
+    def __init__(self, cfg, box_coder):
+        atss = cfg.MODEL.ATSS
+        if getattr(atss, "POSITIVE_TYPE", "ATSS") != "ATSS":
+            raise NotImplementedError("POSITIVE_TYPE %r: only 'ATSS' is supported" % (atss.POSITIVE_TYPE,))
+        if coder_regression_type(box_coder) != "BOX":
+            raise NotImplementedError("only the 'BOX' BoxCoder regression type is supported")
+        self.cfg = cfg
+        self.gamma = scalar(atss.LOSS_GAMMA)
+        self.alpha = scalar(atss.LOSS_ALPHA)
+        self.iou_threshold = 0.0                     # unused by the ATSS rule
+        self.topk = int(atss.TOPK)
+        self.box_coder = box_coder
+        self.reg_loss_type = "iou"
+        self.iou_loss_weight = 1.0                   # centerness loss carries no extra weight (atss/loss.py:273)
+        self.reg_loss_weight = float(atss.REG_LOSS_WEIGHT)
+        self._lib = _lib.load()
+        self.debug = False
+        self.last_debug = None
+        self.teacher_combined_loss = None
+        self._workspace = None
+        self._ones = None
+        self._flavour = _lib.LOSS_ATSS
+
+    def __call__(self, box_cls, box_regression, centerness, targets, anchors):
+        n_levels = len(box_cls)
+        heads = list(box_cls) + list(box_regression) + list(centerness)
+        losses = _PAALossFunction.apply(self, targets, anchors, n_levels, True, *heads)
+        return losses[0], losses[1], losses[2]
+
+
+def make_atss_loss_evaluator(cfg, box_coder):
+    return ATSSLossComputation(cfg, box_coder)       # atss/loss.py:279-281

@@ -82,6 +82,28 @@ rp = make_retinanet_postprocessor(rn_cfg, None)
 ms = timed(lambda: rp.run_device(rcls, rreg, None, ranchors))
 logit_bytes = sum(t.numel() * 4 for t in rcls)
 out["retinanet_post_8img_9anchors"] = {"ms": ms, "images_per_s": 8 / (ms / 1e3), "logit_MB": logit_bytes / 1e6}
+# ATSS training step (assignment + losses + gradients) on the C2 shape, CUDA-graph replay like bench.py
+from tests.helpers import to_device_inputs
+tb_ = synthetic.make_batch(seed=2000, num_images=16, image_hw=(800, 1333), gt_per_image=(1, 100))
+acfg = NS(MODEL=NS(ATSS=NS(LOSS_GAMMA=2.0, LOSS_ALPHA=0.25, TOPK=9, REG_LOSS_WEIGHT=2.0, POSITIVE_TYPE="ATSS",
+                           REGRESSION_TYPE="BOX")))
+aev = paa_b200.make_atss_loss_evaluator(acfg, paa_b200.BoxCoder(acfg))
+acls, areg, actr, atargets, aanchors = to_device_inputs(tb_, device=dev)
+astep = lambda: aev.forward_backward(acls, areg, actr, atargets, aanchors)
+for _ in range(3):
+    astep()
+torch.cuda.synchronize()
+side = torch.cuda.Stream(); side.wait_stream(torch.cuda.current_stream())
+with torch.cuda.stream(side):
+    astep()
+torch.cuda.current_stream().wait_stream(side); torch.cuda.synchronize()
+graph = torch.cuda.CUDAGraph()
+with torch.cuda.graph(graph):
+    astep()
+ms = timed(lambda: graph.replay())
+out["atss_loss_step_16img_800x1333"] = {"ms": ms, "images_per_s": 16 / (ms / 1e3),
+                                        "note": "paa_atss_assign + paa_loss (forward + gradients), graph replay"}
+
 # TTA merging: 14 augmentations x ~100 detections of one image, 20 classes present
 from paa_b200.bbox_aug_vote import merge_result_from_multi_scales
 from oracle import vote_oracle

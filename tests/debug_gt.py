@@ -1,5 +1,5 @@
 """Debug aid: run one synthetic batch on the GPU and through the oracle, print every GT whose positive set
-differs (candidate lists, n_iter, mixture parameters, score gaps).  python tools/debug_gt.py c3|c1|c5"""
+differs (candidate lists, n_iter, mixture parameters, score gaps).  python tests/debug_gt.py c3|c1|c5 (test infrastructure: it runs the oracle)"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch

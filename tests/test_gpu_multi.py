@@ -64,6 +64,17 @@ def _worker(rank, world, port, out):
     losses2, grads2 = ev.forward_backward(cls, reg, iou, targets, anchors)
     res["nccl_losses"] = losses2.cpu().numpy()
     res["nccl_grad0"] = grads2["cls"][0].cpu().numpy()
+    # the ATSS flavour publishes its normalisers from another kernel (atss_norm_kernel): same check
+    from types import SimpleNamespace as NS
+    acfg = NS(MODEL=NS(ATSS=NS(LOSS_GAMMA=2.0, LOSS_ALPHA=0.25, TOPK=9, REG_LOSS_WEIGHT=2.0, POSITIVE_TYPE="ATSS",
+                               REGRESSION_TYPE="BOX")))
+    ba = synthetic.make_batch(seed=710 + rank, num_images=2, image_hw=(384, 512), gt_per_image=(2, 8))
+    acls, areg, actr, atargets, aanchors = to_device_inputs(ba, device=dev)
+    aev = paa_b200.make_atss_loss_evaluator(acfg, paa_b200.BoxCoder(acfg))
+    res["atss_nccl_losses"] = aev.forward_backward(acls, areg, actr, atargets, aanchors)[0].cpu().numpy()
+    paa_loss.PeerNormExchange._by_device.pop((dev.type, dev.index), None)
+    assert paa_loss.PeerNormExchange.get(dev) is not None
+    res["atss_peer_losses"] = aev.forward_backward(acls, areg, actr, atargets, aanchors)[0].cpu().numpy()
     torch.cuda.synchronize()
     dist.barrier()
     np.savez(out % rank, **res)
@@ -100,6 +111,8 @@ def test_peer_exchange_matches_all_reduce_and_oracle(tmp_path):
         np.testing.assert_array_equal(res[r]["peer_losses"], res[r]["nccl_losses"])
         np.testing.assert_array_equal(res[r]["peer_losses"], res[r]["graph_losses"])
         np.testing.assert_array_equal(res[r]["peer_grad0"], res[r]["nccl_grad0"])
+        np.testing.assert_array_equal(res[r]["atss_peer_losses"], res[r]["atss_nccl_losses"])
+        assert np.isfinite(res[r]["atss_peer_losses"]).all()
         b = batches[r]
         ref = paa_oracle.losses(b.box_cls, b.box_regression, b.iou_pred, asgs[r], total_num_pos=tot_pos,
                                 total_sum_iou=tot_iou, world_size=2)

@@ -97,11 +97,14 @@ def test_end_to_end_losses_and_grads_against_recorded_reference(name):
         assert diff <= exempt, (name, diff - exempt)
 
 
-def _assert_matches_oracle(b, max_exempt):
+def _assert_matches_oracle(b, max_exempt, **cfg_overrides):
     """Free-running comparison of one batch with the oracle run on this machine's CPU."""
+    names = {"LOSS_GAMMA": "gamma", "LOSS_ALPHA": "alpha"}
+    oracle_kw = {names.get(k, k.lower()): v for k, v in cfg_overrides.items()}
     ref_losses, ref_grads, asg = paa_oracle.assign_and_loss(b.box_cls, b.box_regression, b.iou_pred,
-                                                            b.gt_boxes, b.gt_labels, b.anchors)
-    ev = _evaluator()
+                                                            b.gt_boxes, b.gt_labels, b.anchors,
+                                                            params=paa_oracle.default_params(**oracle_kw))
+    ev = _evaluator(**cfg_overrides)
     ev.debug = True
     losses, cls, reg, iou = _run(ev, b)
     d = ev.last_debug
@@ -139,6 +142,25 @@ def test_without_iou_pred():
     assert len(losses) == 2
     if np.array_equal(ev.last_debug["paa_labels"].cpu().numpy(), asg.paa_labels.numpy()):
         np.testing.assert_allclose([float(x) for x in losses], [float(x) for x in ref_losses], rtol=RTOL)
+
+
+@pytest.mark.parametrize("topk", [3, 20])
+def test_other_topk_values_against_oracle(topk):
+    """TOPK 3 / 20: at most 15 / 100 candidates per GT, i.e. the one- and four-samples-per-lane variants of the
+    fit (TOPK 9 uses two), and a per-level list longer than a third of a warp."""
+    b = synthetic.make_batch(seed=70 + topk, num_images=2, image_hw=(416, 512), gt_per_image=(3, 10))
+    _assert_matches_oracle(b, max_exempt=2, TOPK=topk)
+
+
+def test_other_focal_parameters_against_oracle():
+    """gamma != 2 takes the generic pow path of every focal kernel."""
+    b = synthetic.make_batch(seed=91, num_images=2, image_hw=(320, 416), gt_per_image=(2, 8))
+    _assert_matches_oracle(b, max_exempt=2, LOSS_GAMMA=1.5, LOSS_ALPHA=0.4)
+
+
+def test_single_image_single_gt():
+    b = synthetic.make_batch(seed=90, num_images=1, image_hw=(256, 320), gt_per_image=1)
+    _assert_matches_oracle(b, max_exempt=1)
 
 
 def test_c3_dense_crowd_against_oracle():

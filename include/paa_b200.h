@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define PAA_ABI_VERSION 3
+#define PAA_ABI_VERSION 4
 #define PAA_MAX_LEVELS 8
 #define PAA_MAX_IMAGES 256      /* images per call (per rank) */
 #define PAA_MAX_CANDIDATES 128  /* num_levels * topk must not exceed this */
@@ -76,12 +76,15 @@ typedef struct PaaLossArgs {
     int32_t world_size;           /* WORLD_SIZE as read by loss.py:18-19 */
     int32_t loss_flavour;         /* PAA_LOSS_PAA: regression weight / BCE target = IoU(pred, target) (paa/loss.py:331-349);
                                      PAA_LOSS_ATSS: = centerness target (atss/loss.py:233-245,262-272), assignment by
-                                     paa_atss_assign */
+                                     paa_atss_assign;
+                                     PAA_LOSS_RETINANET: labels straight from the Matcher (-1 = ignored), smooth-L1 on
+                                     the regression deltas (retinanet/loss.py:45-81), assignment by
+                                     paa_retinanet_assign; use_iou_pred must be 0 */
     float gamma, alpha;           /* focal loss, cfg.MODEL.PAA.LOSS_GAMMA / LOSS_ALPHA */
-    float iou_threshold;          /* Matcher high == low threshold (loss.py:38-40) */
+    float iou_threshold;          /* Matcher high threshold; PAA: high == low (loss.py:38-40) */
     float reg_loss_weight;        /* cfg.MODEL.PAA.REG_LOSS_WEIGHT */
     float iou_loss_weight;        /* cfg.MODEL.PAA.IOU_LOSS_WEIGHT */
-    float reserved1;
+    float bg_iou_threshold;       /* PAA_LOSS_RETINANET: Matcher low threshold (BG_IOU_THRESHOLD); else unused */
     int64_t anchor_image_stride;  /* in floats; 0 when all images share the anchor tensors */
     PaaLevel levels[PAA_MAX_LEVELS];
     const float* gt_boxes;        /* device [sum G, 4] xyxy */
@@ -118,6 +121,10 @@ typedef struct PaaLossArgs {
     int32_t rank;
     int32_t reserved2;
     double* peer_norm[PAA_MAX_PEERS];
+    /* PAA_LOSS_RETINANET only */
+    float box_code_weights[4];    /* BoxCoder weights wx, wy, ww, wh (box_coder.py:22-50; 10, 10, 5, 5) */
+    float smooth_l1_beta;         /* cfg.MODEL.RETINANET.BBOX_REG_BETA */
+    float reg_norm_weight;        /* cfg.MODEL.RETINANET.BBOX_REG_WEIGHT: loss_reg / max(1, num_pos * this) */
 } PaaLossArgs;
 
 typedef struct PaaPostArgs {
@@ -158,6 +165,7 @@ typedef struct PaaPostArgs {
 } PaaPostArgs;
 #define PAA_LOSS_PAA  0
 #define PAA_LOSS_ATSS 1
+#define PAA_LOSS_RETINANET 2
 #define PAA_DECODE_ATSS_BOX 0
 #define PAA_DECODE_LEGACY   1
 #define PAA_DECODE_LTRB     2
@@ -205,6 +213,14 @@ int paa_sigmoid_focal_loss_backward(const float* logits, const int32_t* targets,
  * (normalisers = {num_pos, sum of centerness targets}); follow with paa_loss and loss_flavour = PAA_LOSS_ATSS.
  * dbg_cand_idx receives the candidates (level-major, nearest first), dbg_gmm[g*8] the GT's IoU threshold. */
 int paa_atss_assign(const PaaLossArgs* args, void* stream);
+
+/* RetinaNet anchor labelling (rpn/loss.py:41-88 as used by rpn/retinanet/loss.py:45-56) in place of paa_assign:
+ * boxlist_iou + Matcher(iou_threshold, bg_iou_threshold, allow_low_quality_matches) per image; label = class of
+ * the matched GT, 0 below the low threshold, -1 (ignored by the focal loss) between the thresholds.  Works for any
+ * anchors_per_loc (9 in RetinaNet).  normalisers[0] = num_pos of this rank (the reference does not reduce it over
+ * ranks); follow with paa_loss and loss_flavour = PAA_LOSS_RETINANET, which returns losses = {cls, reg, 0}.
+ * dbg_matched_idx receives the Matcher result (-2 = between thresholds), dbg_iou_labels the labels. */
+int paa_retinanet_assign(const PaaLossArgs* args, void* stream);
 
 /* ---- operators on either side of the path ----------------------------------------- */
 /* AnchorGenerator.grid_anchors (anchor_generator.py:73-95) for one level: out[(y*W + x)*a + k] =

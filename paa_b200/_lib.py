@@ -14,7 +14,7 @@ MAX_IMAGES = 256
 MAX_PEERS = 16
 PEER_BUFFER_DOUBLES = 256
 MAX_CANDIDATES = 128
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 ERR_BAD_ARGUMENT, ERR_WORKSPACE, ERR_EMPTY_TARGET, ERR_UNSUPPORTED = -1, -2, -3, -4
 
@@ -32,7 +32,7 @@ class PaaLossArgs(C.Structure):
                 ("anchors_per_loc", C.c_int32), ("topk", C.c_int32), ("use_iou_pred", C.c_int32),
                 ("world_size", C.c_int32), ("loss_flavour", C.c_int32),
                 ("gamma", C.c_float), ("alpha", C.c_float), ("iou_threshold", C.c_float),
-                ("reg_loss_weight", C.c_float), ("iou_loss_weight", C.c_float), ("reserved1", C.c_float),
+                ("reg_loss_weight", C.c_float), ("iou_loss_weight", C.c_float), ("bg_iou_threshold", C.c_float),
                 ("anchor_image_stride", C.c_int64),
                 ("levels", PaaLevel * MAX_LEVELS),
                 ("gt_boxes", C.c_void_p), ("gt_labels", C.c_void_p),
@@ -43,7 +43,9 @@ class PaaLossArgs(C.Structure):
                 ("dbg_combined_loss", C.c_void_p), ("dbg_cand_idx", C.c_void_p),
                 ("dbg_cand_cnt", C.c_void_p), ("dbg_num_pos", C.c_void_p), ("dbg_gmm", C.c_void_p),
                 ("dbg_paa_labels", C.c_void_p), ("teacher_combined_loss", C.c_void_p),
-                ("rank", C.c_int32), ("reserved2", C.c_int32), ("peer_norm", C.c_void_p * MAX_PEERS)]
+                ("rank", C.c_int32), ("reserved2", C.c_int32), ("peer_norm", C.c_void_p * MAX_PEERS),
+                ("box_code_weights", C.c_float * 4), ("smooth_l1_beta", C.c_float),
+                ("reg_norm_weight", C.c_float)]
 
 
 class PaaPostArgs(C.Structure):
@@ -63,7 +65,7 @@ class PaaPostArgs(C.Structure):
                 ("box_decode", C.c_int32), ("decode_weights", C.c_float * 4), ("decode_clip", C.c_float)]
 
 DECODE_ATSS_BOX, DECODE_LEGACY, DECODE_LTRB = 0, 1, 2
-LOSS_PAA, LOSS_ATSS = 0, 1
+LOSS_PAA, LOSS_ATSS, LOSS_RETINANET = 0, 1, 2
 
 
 # name -> (restype, argtypes); every symbol include/paa_b200.h declares
@@ -75,6 +77,7 @@ SYMBOLS = {
     "paa_assign": (C.c_int, [C.POINTER(PaaLossArgs), C.c_void_p]),
     "paa_loss": (C.c_int, [C.POINTER(PaaLossArgs), C.c_void_p]),
     "paa_atss_assign": (C.c_int, [C.POINTER(PaaLossArgs), C.c_void_p]),
+    "paa_retinanet_assign": (C.c_int, [C.POINTER(PaaLossArgs), C.c_void_p]),
     "paa_assign_loss": (C.c_int, [C.POINTER(PaaLossArgs), C.c_void_p]),
     "paa_rescale_grads": (C.c_int, [C.POINTER(PaaLossArgs), C.c_void_p, C.c_void_p, C.c_void_p]),
     "paa_postprocess": (C.c_int, [C.POINTER(PaaPostArgs), C.c_void_p]),

@@ -175,9 +175,27 @@ static int plan_loss(const PaaLossArgs* a, LossPlan* p) {
     p->sc.use_iou_pred = a->use_iou_pred;
     p->sc.world_size = a->world_size;
     p->sc.flavour = a->loss_flavour;
-    if (a->loss_flavour != PAA_LOSS_PAA && a->loss_flavour != PAA_LOSS_ATSS) {
+    if (a->loss_flavour != PAA_LOSS_PAA && a->loss_flavour != PAA_LOSS_ATSS &&
+        a->loss_flavour != PAA_LOSS_RETINANET) {
         set_error("loss_flavour=%d", a->loss_flavour);
         return PAA_ERR_BAD_ARGUMENT;
+    }
+    p->sc.num_images = a->num_images;
+    p->sc.bg_threshold = a->bg_iou_threshold;
+    for (int k = 0; k < 4; ++k) p->sc.code_w[k] = a->box_code_weights[k];
+    p->sc.beta = a->smooth_l1_beta;
+    p->sc.reg_norm_weight = a->reg_norm_weight;
+    if (a->loss_flavour == PAA_LOSS_RETINANET) {
+        if (a->use_iou_pred) {
+            set_error("PAA_LOSS_RETINANET has no third head: use_iou_pred must be 0");
+            return PAA_ERR_BAD_ARGUMENT;
+        }
+        if (!(a->smooth_l1_beta > 0.0f) || !(a->bg_iou_threshold <= a->iou_threshold)) {
+            // matcher.py:35 asserts low <= high
+            set_error("PAA_LOSS_RETINANET: smooth_l1_beta=%g must be positive and bg_iou_threshold=%g <= "
+                      "iou_threshold=%g", a->smooth_l1_beta, a->bg_iou_threshold, a->iou_threshold);
+            return PAA_ERR_BAD_ARGUMENT;
+        }
     }
     {
         // test hook: a smaller pool forces the overflow path of the candidate selection
@@ -186,7 +204,7 @@ static int plan_loss(const PaaLossArgs* a, LossPlan* p) {
         p->sc.seg_cap = cap < 1 ? 1 : (cap > kSegCap ? kSegCap : cap);
     }
     memset(&p->px, 0, sizeof(p->px));
-    if (a->peer_norm[0] != nullptr && a->world_size > 1) {
+    if (a->peer_norm[0] != nullptr && a->world_size > 1 && a->loss_flavour != PAA_LOSS_RETINANET) {
         if (a->world_size > PAA_MAX_PEERS || a->rank < 0 || a->rank >= a->world_size) {
             set_error("peer exchange: rank %d / world_size %d unsupported (<= %d ranks)", a->rank, a->world_size,
                       PAA_MAX_PEERS);
@@ -279,6 +297,34 @@ int paa_atss_assign(const PaaLossArgs* args, void* stream_) {
     PAA_CUDA_CHECK(cudaMemsetAsync(p.ws.best, 0, sizeof(uint2) * (size_t)args->num_images * p.geo.A, stream));
     if ((rc = launch_atss_assign(p.geo, p.go, p.sumG, args->gt_boxes, args->gt_labels, p.sc, p.ws, args->normalisers,
                                  p.px, p.dbg, stream)))
+        return rc;
+    if (args->dbg_paa_labels)
+        PAA_CUDA_CHECK(cudaMemcpyAsync(args->dbg_paa_labels, p.ws.paa_label,
+                                       sizeof(int) * (size_t)args->num_images * p.geo.A,
+                                       cudaMemcpyDeviceToDevice, stream));
+    return 0;
+}
+
+int paa_retinanet_assign(const PaaLossArgs* args, void* stream_) {
+    LossPlan p;
+    int rc = plan_loss(args, &p);
+    if (rc) return rc;
+    if (args->loss_flavour != PAA_LOSS_RETINANET) {
+        set_error("paa_retinanet_assign needs loss_flavour = PAA_LOSS_RETINANET");
+        return PAA_ERR_BAD_ARGUMENT;
+    }
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    PAA_CUDA_CHECK(cudaMemsetAsync(args->workspace, 0, p.ws.zero_bytes, stream));
+    {
+        const int hl = first_heavy_level(p.geo);
+        if (hl < p.geo.num_levels && gt_parts(p.go, args->num_images) > 1) {
+            const size_t a0 = (size_t)p.geo.lv[hl].a_off, n_heavy = (size_t)p.geo.A - a0;
+            PAA_CUDA_CHECK(cudaMemset2DAsync(reinterpret_cast<char*>(p.ws.best) + a0 * 8, (size_t)p.geo.A * 8, 0,
+                                             n_heavy * 8, (size_t)args->num_images, stream));
+        }
+    }
+    if ((rc = launch_retinanet_assign(p.geo, p.go, args->gt_boxes, args->gt_labels, p.sc, p.ws, args->normalisers,
+                                      p.dbg, stream)))
         return rc;
     if (args->dbg_paa_labels)
         PAA_CUDA_CHECK(cudaMemcpyAsync(args->dbg_paa_labels, p.ws.paa_label,

@@ -62,16 +62,6 @@ struct Pass1Plan {
     int patch_rx[PAA_MAX_LEVELS];                // regions per grid row
 };
 
-// (IoU bits, GT) of an anchor's best GT as one 64-bit key whose integer order is "larger IoU, then smaller GT
-// index" -- the first-maximum rule of torch.max(dim=0) (matcher.py:47) under atomicMax.  Key 0 = no GT seen.
-__device__ __forceinline__ unsigned long long pack_best(float v, int g) {
-    return ((unsigned long long)__float_as_uint(v) << 32) | (unsigned long long)(0xffffffffu - (unsigned)g);
-}
-__device__ __forceinline__ void unpack_best(unsigned long long key, float* v, int* g) {
-    *v = __uint_as_float((unsigned)(key >> 32));
-    *g = key == 0ull ? 0 : (int)(0xffffffffu - (unsigned)(key & 0xffffffffull));
-}
-
 // One negative-class focal term without its (1-alpha) factor: p^gamma * softplus(x).
 __device__ __forceinline__ float neg_term_only(float x, float gamma, bool g2) {
     const SigmoidLean sl = sigmoid_lean(x);
@@ -352,7 +342,7 @@ int gt_parts(const GtOffsets& go, int num_images) {
 }
 
 int launch_assign_pass1(const Geometry& geo, const GtOffsets& go, const float* gt_boxes, const LossScalars& sc,
-                        const LossWorkspace& ws, cudaStream_t stream) {
+                        const LossWorkspace& ws, cudaStream_t stream, bool with_class_sums) {
     Pass1Plan plan;
     unsigned items = 0;
     for (int l = 0; l < PAA_MAX_LEVELS; ++l) {
@@ -368,7 +358,7 @@ int launch_assign_pass1(const Geometry& geo, const GtOffsets& go, const float* g
         items += plan.chunks[l] * (unsigned)geo.num_images;
     }
     plan.item_off[PAA_MAX_LEVELS] = items;
-    plan.sum_blocks = items;
+    plan.sum_blocks = with_class_sums ? items : 0u;      // 0: IoU matching only (no score pass, RetinaNet)
     const int heavy_level = first_heavy_level(geo);
     plan.light_tiles = heavy_level < geo.num_levels ? geo.lv[heavy_level].tile_off : geo.tiles_per_image;
     plan.light_pairs = (plan.light_tiles + 1) / 2;

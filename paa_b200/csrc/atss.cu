@@ -19,10 +19,6 @@ namespace paa {
 
 constexpr unsigned long long kNoKey64 = ~0ull;
 
-__device__ __forceinline__ unsigned long long pack_best_key(float v, int g) {
-    return ((unsigned long long)__float_as_uint(v) << 32) | (unsigned long long)(0xffffffffu - (unsigned)g);
-}
-
 // lane j < K holds the j-th smallest key so far (same scheme as the PAA candidate selection)
 __device__ __forceinline__ void nearest_offer(unsigned long long& mine, unsigned long long key, bool is, int K, int lane) {
     const unsigned long long kth = __shfl_sync(PAA_FULL, mine, K - 1);
@@ -134,7 +130,7 @@ atss_candidates_kernel(const Geometry geo, const GtOffsets go, const float* __re
         const int aidx = (int)s_cand[c / K][c % K];
         if (dbg.cand_idx) dbg.cand_idx[(size_t)gi * total + c] = aidx;
         if (s_q[c] >= thr && s_in[c] > 0.01f)          // :169,180-181
-            atomicMax(best + (size_t)n * geo.A + aidx, pack_best_key(s_q[c], g_local));
+            atomicMax(best + (size_t)n * geo.A + aidx, pack_best(s_q[c], g_local));
     }
     if (dbg.cand_cnt && lane == 0) dbg.cand_cnt[gi] = total;
 }
@@ -248,7 +244,12 @@ int launch_atss_assign(const Geometry& geo, const GtOffsets& go, int num_gt_tota
     atss_labels_kernel<<<tiles, PAA_TILE, 0, stream>>>(geo, go, gt_boxes, gt_labels, best, ws.matched, ws.paa_label,
                                                        tile_part, dbg);
     PAA_LAUNCH_CHECK("atss_labels_kernel");
-    atss_norm_kernel<<<1, 512, 0, stream>>>(tile_part, tiles, ws.local_norm, normalisers, px);
+    return launch_fold_norm(tile_part, tiles, ws.local_norm, normalisers, px, stream);
+}
+
+int launch_fold_norm(const double* tile_part, int tiles, double* local_norm, double* normalisers,
+                     const PeerExchange& px, cudaStream_t stream) {
+    atss_norm_kernel<<<1, 512, 0, stream>>>(tile_part, tiles, local_norm, normalisers, px);
     PAA_LAUNCH_CHECK("atss_norm_kernel");
     return 0;
 }

@@ -8,7 +8,10 @@ namespace paa {
 struct LossScalars {
     float gamma, alpha, iou_threshold, reg_loss_weight, iou_loss_weight;
     int topk, use_iou_pred, world_size;
-    int flavour;       // PAA_LOSS_PAA / PAA_LOSS_ATSS
+    int flavour;       // PAA_LOSS_PAA / PAA_LOSS_ATSS / PAA_LOSS_RETINANET
+    // PAA_LOSS_RETINANET: Matcher low threshold, BoxCoder weights, smooth-L1 beta, BBOX_REG_WEIGHT, images of the call
+    float bg_threshold, code_w[4], beta, reg_norm_weight;
+    int num_images;
     int seg_cap;       // usable entries of a (GT, level) candidate pool, <= kSegCap (PAA_SEG_CAP shrinks it for tests)
 };
 
@@ -37,7 +40,7 @@ struct LossDebug {
 int first_heavy_level(const Geometry& geo);
 int gt_parts(const GtOffsets& go, int num_images);
 int launch_assign_pass1(const Geometry& geo, const GtOffsets& go, const float* gt_boxes, const LossScalars& sc,
-                        const LossWorkspace& ws, cudaStream_t stream);
+                        const LossWorkspace& ws, cudaStream_t stream, bool with_class_sums = true);
 int launch_match_score(const Geometry& geo, const GtOffsets& go, const float* gt_boxes,
                        const int64_t* gt_labels, const LossScalars& sc, const LossWorkspace& ws,
                        const float* teacher_score, const LossDebug& dbg, cudaStream_t stream);
@@ -50,6 +53,13 @@ int launch_atss_assign(const Geometry& geo, const GtOffsets& go, int num_gt_tota
                        const int64_t* gt_labels, const LossScalars& sc, const LossWorkspace& ws, double* normalisers,
                        const PeerExchange& px, const LossDebug& dbg, cudaStream_t stream);
 int launch_norm_wait(const PeerExchange& px, double* normalisers, cudaStream_t stream);
+// folds per-tile {count, sum} partials into local_norm / normalisers and publishes them to the peers
+int launch_fold_norm(const double* tile_part, int tiles, double* local_norm, double* normalisers,
+                     const PeerExchange& px, cudaStream_t stream);
+// retina.cu
+int launch_retinanet_assign(const Geometry& geo, const GtOffsets& go, const float* gt_boxes, const int64_t* gt_labels,
+                            const LossScalars& sc, const LossWorkspace& ws, double* normalisers, const LossDebug& dbg,
+                            cudaStream_t stream);
 
 // loss.cu
 int loss_grid_blocks(int num_images, int tiles_per_image);

@@ -30,6 +30,15 @@ __device__ __forceinline__ GradScales make_scales(const LossScalars& sc, const d
     const float num_pos_avg = fmaxf((float)norm[0] / world, 1.0f);     // loss.py:322
     const float g0 = gout ? gout[0] : 1.0f, g1 = gout ? gout[1] : 1.0f, g2 = gout ? gout[2] : 1.0f;
     GradScales s;
+    if (sc.flavour == PAA_LOSS_RETINANET) {
+        // retinanet/loss.py:70,79: reg / max(1, num_pos * BBOX_REG_WEIGHT), cls / (num_pos + N), this rank's counts
+        const float npos = (float)norm[0];
+        s.cls = g0 / (npos + (float)sc.num_images);
+        s.reg = g1 / fmaxf(1.0f, npos * sc.reg_norm_weight);
+        s.bce = 0.0f;
+        s.weighted = false;
+        return s;
+    }
     s.cls = g0 / num_pos_avg;
     if (sc.use_iou_pred) {
         const float reg_norm = (float)norm[1] / world;                 // loss.py:338,354
@@ -252,6 +261,33 @@ __device__ __forceinline__ void positive_box_terms(const Geometry& geo, const Le
     *gd = make_float4(gdd.x * k, gdd.y * k, gdd.z * k, gdd.w * k);
 }
 
+// Smooth-L1 regression loss / gradient of one RetinaNet positive (layers/smooth_l1_loss.py:6-17 on
+// box_coder.py:22-50 targets).
+__device__ __forceinline__ float smooth_l1_term(float x, float t, float beta, float k, float* g) {
+    const float d = x - t, n = fabsf(d);
+    if (n < beta) {
+        *g = (d / beta) * k;
+        return 0.5f * n * n / beta;
+    }
+    *g = (d > 0.0f ? 1.0f : (d < 0.0f ? -1.0f : 0.0f)) * k;
+    return n - 0.5f * beta;
+}
+
+__device__ __forceinline__ void positive_smooth_l1(const Geometry& geo, const LevelView& lv, const GtOffsets& go,
+                                                   const float* __restrict__ gt_boxes, const LossScalars& sc,
+                                                   const FinalCtx& cx, int n, int i, int m, float4 d,
+                                                   float* reg_sum, float4* gd) {
+    const float4 a = ldg4(lv.anchors + (size_t)n * geo.anchor_image_stride + (size_t)i * 4);
+    const float4 gt = ldg4(gt_boxes + (size_t)(go.v[n] + m) * 4);
+    const float4 t = encode_box_legacy(gt, a, sc.code_w[0], sc.code_w[1], sc.code_w[2], sc.code_w[3]);
+    float s = 0.f;
+    s += smooth_l1_term(d.x, t.x, sc.beta, cx.gs.reg, &gd->x);
+    s += smooth_l1_term(d.y, t.y, sc.beta, cx.gs.reg, &gd->y);
+    s += smooth_l1_term(d.z, t.z, sc.beta, cx.gs.reg, &gd->z);
+    s += smooth_l1_term(d.w, t.w, sc.beta, cx.gs.reg, &gd->w);
+    *reg_sum += s;
+}
+
 // One thread per anchor, one block per 128-anchor tile (same tiling as the assignment kernels).
 // Runs after bulk_focal_kernel on the same stream: it overwrites the labelled class's gradient element.
 template <bool kGrads, bool kG2>
@@ -298,8 +334,22 @@ positive_terms_kernel(const Geometry geo, const GtOffsets go, const float* __res
             const float4 d = make_float4(__ldg(rp), __ldg(rp + lv.hw), __ldg(rp + 2 * (size_t)lv.hw),
                                          __ldg(rp + 3 * (size_t)lv.hw));
             const float xi = sc.use_iou_pred ? __ldg(lv.iou + head_offset(n, i, 0, 1, geo.apl, lv.hw)) : 0.f;
-            positive_box_terms(geo, lv, go, gt_boxes, sc, cx, n, i, matched[flat], d, xi, &reg_sum, &bce_sum, &gd,
-                               &gi);
+            if (sc.flavour == PAA_LOSS_RETINANET)
+                positive_smooth_l1(geo, lv, go, gt_boxes, sc, cx, n, i, matched[flat], d, &reg_sum, &gd);
+            else
+                positive_box_terms(geo, lv, go, gt_boxes, sc, cx, n, i, matched[flat], d, xi, &reg_sum, &bce_sum,
+                                   &gd, &gi);
+        } else if (label < 0) {
+            // ignored anchor (RetinaNet, between the Matcher thresholds): the focal loss skips all of its classes
+            // (sigmoid_focal_loss.py:50, SigmoidFocalLoss_cuda.cu:44) -- take back what the bulk pass added
+            const float oma = 1.0f - sc.alpha;
+            float acc = 0.f, g_unused;
+            for (int c = 0; c < geo.C; ++c) {
+                const size_t off = head_offset(n, i, c, geo.C, geo.apl, lv.hw);
+                neg_term_grad<kG2>(__ldg(lv.cls + off), sc.gamma, 0.0f, &acc, &g_unused);
+                if (kGrads && lv.g_cls) lv.g_cls[off] = 0.0f;
+            }
+            fix_sum = -(oma * acc);
         }
         if (kGrads) {
             if (lv.g_reg) {
@@ -370,6 +420,13 @@ finish_loss_kernel(const double* __restrict__ part_a, int blocks_a, const double
             for (int k = 0; k < 3; ++k) t[k] += s[w][k];
         const double world = (double)sc.world_size;
         const float num_pos_avg = (float)fmax(norm[0] / world, 1.0);
+        if (sc.flavour == PAA_LOSS_RETINANET) {
+            const float npos = (float)norm[0];
+            losses[0] = (float)t[0] / (npos + (float)sc.num_images);
+            losses[1] = (float)t[1] / fmaxf(1.0f, npos * sc.reg_norm_weight);
+            losses[2] = 0.0f;
+            return;
+        }
         losses[0] = (float)t[0] / num_pos_avg;
         if (sc.use_iou_pred) {
             const float reg_norm = (float)(norm[1] / world);

@@ -240,7 +240,8 @@ class PAALossComputation(object):
                                                                                 dtype=torch.int64).contiguous()
         sum_g = offsets[-1]
         has_iou = iou_pred is not None
-        world = get_num_gpus()
+        # the RetinaNet loss normalises by this rank's own counts (retinanet/loss.py:70,79): no exchange
+        world = 1 if self._flavour == _lib.LOSS_RETINANET else get_num_gpus()
 
         args = _lib.PaaLossArgs()
         args.num_images, args.num_levels, args.num_classes = N, L, lv["C"]
@@ -249,6 +250,11 @@ class PAALossComputation(object):
         args.loss_flavour = self._flavour
         args.gamma, args.alpha, args.iou_threshold = self.gamma, self.alpha, self.iou_threshold
         args.reg_loss_weight, args.iou_loss_weight = self.reg_loss_weight, self.iou_loss_weight
+        if self._flavour == _lib.LOSS_RETINANET:
+            args.bg_iou_threshold = self.bg_iou_threshold
+            for k in range(4):
+                args.box_code_weights[k] = self.box_code_weights[k]
+            args.smooth_l1_beta, args.reg_norm_weight = self.bbox_reg_beta, self.regress_norm
         args.anchor_image_stride = lv["anchor_stride"]
         grads = None
         if need_grad:
@@ -296,14 +302,16 @@ class PAALossComputation(object):
             assert teacher.shape == (N, A)
             args.teacher_combined_loss = teacher.data_ptr()
         stream = torch.cuda.current_stream(device).cuda_stream
-        assign = self._lib.paa_atss_assign if self._flavour == _lib.LOSS_ATSS else self._lib.paa_assign
+        assign_name = {_lib.LOSS_PAA: "paa_assign", _lib.LOSS_ATSS: "paa_atss_assign",
+                       _lib.LOSS_RETINANET: "paa_retinanet_assign"}[self._flavour]
+        assign = getattr(self._lib, assign_name)
         with torch.cuda.device(device):
             peer = PeerNormExchange.get(device) if world > 1 else None
             if peer is not None:
                 args.rank = peer.rank
                 for r, ptr in enumerate(peer.ptrs):
                     args.peer_norm[r] = ptr
-            _lib.check(assign(C.byref(args), stream), "paa_atss_assign" if self._flavour else "paa_assign")
+            _lib.check(assign(C.byref(args), stream), assign_name)
             if world > 1 and peer is None:
                 reduce_normalisers(normalisers)                         # loss.py:321,338 in one message
             _lib.check(self._lib.paa_loss(C.byref(args), stream), "paa_loss")
@@ -389,3 +397,68 @@ class ATSSLossComputation(PAALossComputation):
 
 def make_atss_loss_evaluator(cfg, box_coder):
     return ATSSLossComputation(cfg, box_coder)       # atss/loss.py:279-281
+
+
+def generate_retinanet_labels(matched_targets):
+    """retinanet/loss.py:84-86 (kept for the constructor's signature; the kernel applies exactly this rule)."""
+    return matched_targets.get_field("labels")
+
+
+class RetinaNetLossComputation(PAALossComputation):
+    """Drop-in for paa_core.modeling.rpn.retinanet.loss.RetinaNetLossComputation (retinanet/loss.py:19-81 on
+    rpn/loss.py:41-88) with the reference's constructor: a Matcher-like object (``high_threshold``,
+    ``low_threshold``, ``allow_low_quality_matches``), the RPN ``BoxCoder`` (``weights``), the label function and a
+    SigmoidFocalLoss-like object (``gamma``, ``alpha``).  IoU matching is the PAA kernel's, labelling is
+    `paa_retinanet_assign`, the losses come from the same streaming pass as PAA's with smooth-L1 in place of GIoU.
+    ``__call__(anchors, box_cls, box_regression, targets)`` returns ``(cls_loss, regression_loss)``."""
+
+    def __init__(self, proposal_matcher, box_coder, generate_labels_func=generate_retinanet_labels,
+                 sigmoid_focal_loss=None, bbox_reg_beta=0.11, regress_norm=1.0):
+        if not getattr(proposal_matcher, "allow_low_quality_matches", True):
+            raise NotImplementedError("only Matcher(..., allow_low_quality_matches=True) is supported")
+        name = getattr(generate_labels_func, "__name__", "")
+        if name != "generate_retinanet_labels":
+            raise NotImplementedError("only generate_retinanet_labels is supported, got %r" % (name,))
+        self.proposal_matcher = proposal_matcher
+        self.box_coder = box_coder
+        self.box_cls_loss_func = sigmoid_focal_loss
+        self.generate_labels_func = generate_labels_func
+        self.copied_fields = ["labels"]
+        self.discard_cases = ["between_thresholds"]
+        self.bbox_reg_beta = float(bbox_reg_beta)
+        self.regress_norm = float(regress_norm)
+        self.iou_threshold = float(proposal_matcher.high_threshold)
+        self.bg_iou_threshold = float(proposal_matcher.low_threshold)
+        self.box_code_weights = tuple(float(w) for w in getattr(box_coder, "weights", (10.0, 10.0, 5.0, 5.0)))
+        self.gamma = scalar(getattr(sigmoid_focal_loss, "gamma", 2.0))
+        self.alpha = scalar(getattr(sigmoid_focal_loss, "alpha", 0.25))
+        self.topk = 1                                # unused by this flavour
+        self.iou_loss_weight = 0.0
+        self.reg_loss_weight = 1.0
+        self._lib = _lib.load()
+        self.debug = False
+        self.last_debug = None
+        self.teacher_combined_loss = None
+        self._workspace = None
+        self._ones = None
+        self._flavour = _lib.LOSS_RETINANET
+
+    def forward_backward(self, anchors, box_cls, box_regression, targets, grad_losses=None):
+        return super(RetinaNetLossComputation, self).forward_backward(box_cls, box_regression, None, targets, anchors,
+                                                                      grad_losses)
+
+    def __call__(self, anchors, box_cls, box_regression, targets):
+        heads = list(box_cls) + list(box_regression)
+        losses = _PAALossFunction.apply(self, targets, anchors, len(box_cls), False, *heads)
+        return losses[0], losses[1]
+
+
+def make_retinanet_loss_evaluator(cfg, box_coder):
+    """retinanet/loss.py:89-107."""
+    from types import SimpleNamespace
+    rn = cfg.MODEL.RETINANET
+    matcher = SimpleNamespace(high_threshold=rn.FG_IOU_THRESHOLD, low_threshold=rn.BG_IOU_THRESHOLD,
+                              allow_low_quality_matches=True)
+    focal = SimpleNamespace(gamma=rn.LOSS_GAMMA, alpha=rn.LOSS_ALPHA)
+    return RetinaNetLossComputation(matcher, box_coder, generate_retinanet_labels, focal,
+                                    bbox_reg_beta=rn.BBOX_REG_BETA, regress_norm=rn.BBOX_REG_WEIGHT)

@@ -69,7 +69,7 @@ class SyntheticBatch:
 
     @property
     def num_images(self):
-        return len(self.gt_boxes)
+        return int(self.box_cls[0].shape[0])
 
     @property
     def num_anchors(self):
@@ -202,8 +202,9 @@ def multiscale_hw(seed: int, num_images: int, max_long: int = 1333):
 
 def make_retinanet_batch(seed: int, num_images: int, image_hw: Tuple[int, int] = (320, 416),
                          cls_mean: float = -3.5, cls_std: float = 1.5, strides=STRIDES,
-                         aspect_ratios=(0.5, 1.0, 2.0), scales_per_octave: int = 3, octave: float = 2.0):
-    """RetinaNet-shaped inference inputs (rpn/retinanet/retinanet.py): A = ratios x scales anchors per location,
+                         aspect_ratios=(0.5, 1.0, 2.0), scales_per_octave: int = 3, octave: float = 2.0,
+                         gt_per_image=None):
+    """RetinaNet-shaped inputs (``gt_per_image`` -- an int or a (lo, hi) range -- adds ground truth for the loss) (rpn/retinanet/retinanet.py): A = ratios x scales anchors per location,
     ``box_cls[l] [N, A*80, H, W]``, ``box_regression[l] [N, A*4, H, W]``, anchors ``[H*W*A, 4]`` (location-major,
     anchor inner, rpn/utils.py:10-14) built like make_anchor_generator_retinanet."""
     import numpy as np
@@ -224,8 +225,16 @@ def make_retinanet_batch(seed: int, num_images: int, image_hw: Tuple[int, int] =
         box_cls.append((torch.randn((num_images, A * NUM_FG_CLASSES, h, w), generator=gen) * cls_std + cls_mean)
                        .clamp_(-12.0, 12.0))
         box_reg.append(torch.randn((num_images, A * 4, h, w), generator=gen) * 0.5)
+    gt_boxes, gt_labels = [], []
+    if gt_per_image is not None:
+        for _ in range(num_images):
+            n_gt = gt_per_image if isinstance(gt_per_image, int) else \
+                int(torch.randint(gt_per_image[0], gt_per_image[1] + 1, (1,), generator=gen))
+            b, l = make_gt(gen, n_gt, image_hw[1], image_hw[0])
+            gt_boxes.append(b)
+            gt_labels.append(l)
     return SyntheticBatch(image_sizes=[(image_hw[1], image_hw[0])] * num_images, grids=grids, anchors=anchors,
-                          gt_boxes=[], gt_labels=[], box_cls=box_cls, box_regression=box_reg, iou_pred=None,
+                          gt_boxes=gt_boxes, gt_labels=gt_labels, box_cls=box_cls, box_regression=box_reg, iou_pred=None,
                           meta=dict(seed=seed, padded_hw=(hp, wp), anchors_per_loc=A))
 
 
@@ -239,3 +248,21 @@ def fcos_locations(grids, strides=STRIDES):
         xx = xs.view(1, w).expand(h, w).reshape(-1)
         out.append(torch.stack((xx, yy), dim=1) + stride // 2)
     return out
+
+
+def to_device_inputs(batch, device="cuda", requires_grad=False):
+    """SyntheticBatch -> (box_cls, box_regression, iou_pred, targets, anchors) in the reference's API
+    shapes, on the device, with the per-level anchor tensors shared by all images like
+    anchor_generator.py:112-125 does."""
+    from paa_b200.structures import BoxList
+    cls = [t.to(device).requires_grad_(requires_grad) for t in batch.box_cls]
+    reg = [t.to(device).requires_grad_(requires_grad) for t in batch.box_regression]
+    iou = None if batch.iou_pred is None else [t.to(device).requires_grad_(requires_grad) for t in batch.iou_pred]
+    anc = [a.to(device) for a in batch.anchors]
+    targets, anchors = [], []
+    for i in range(batch.num_images):
+        t = BoxList(batch.gt_boxes[i].to(device), batch.image_sizes[i], mode="xyxy")
+        t.add_field("labels", batch.gt_labels[i].to(device))
+        targets.append(t)
+        anchors.append([BoxList(a, batch.image_sizes[i], mode="xyxy") for a in anc])
+    return cls, reg, iou, targets, anchors

@@ -31,22 +31,7 @@ def flat_levels(ts):
                            for t in ts], axis=1)
 
 
-def to_device_inputs(batch, device="cuda", requires_grad=False):
-    """SyntheticBatch -> (box_cls, box_regression, iou_pred, targets, anchors) in the reference's API
-    shapes, on the device, with the per-level anchor tensors shared by all images like
-    anchor_generator.py:112-125 does."""
-    from paa_b200.structures import BoxList
-    cls = [t.to(device).requires_grad_(requires_grad) for t in batch.box_cls]
-    reg = [t.to(device).requires_grad_(requires_grad) for t in batch.box_regression]
-    iou = [t.to(device).requires_grad_(requires_grad) for t in batch.iou_pred]
-    anc = [a.to(device) for a in batch.anchors]
-    targets, anchors = [], []
-    for i in range(batch.num_images):
-        t = BoxList(batch.gt_boxes[i].to(device), batch.image_sizes[i], mode="xyxy")
-        t.add_field("labels", batch.gt_labels[i].to(device))
-        targets.append(t)
-        anchors.append([BoxList(a, batch.image_sizes[i], mode="xyxy") for a in anc])
-    return cls, reg, iou, targets, anchors
+from paa_b200.synthetic import to_device_inputs  # noqa: E402,F401  (re-exported for the tests)
 
 
 def topk_tie_exempt(oracle_asg, rel=1e-5):

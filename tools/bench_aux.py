@@ -83,7 +83,7 @@ ms = timed(lambda: rp.run_device(rcls, rreg, None, ranchors))
 logit_bytes = sum(t.numel() * 4 for t in rcls)
 out["retinanet_post_8img_9anchors"] = {"ms": ms, "images_per_s": 8 / (ms / 1e3), "logit_MB": logit_bytes / 1e6}
 # ATSS training step (assignment + losses + gradients) on the C2 shape, CUDA-graph replay like bench.py
-from tests.helpers import to_device_inputs
+from paa_b200.synthetic import to_device_inputs
 tb_ = synthetic.make_batch(seed=2000, num_images=16, image_hw=(800, 1333), gt_per_image=(1, 100))
 acfg = NS(MODEL=NS(ATSS=NS(LOSS_GAMMA=2.0, LOSS_ALPHA=0.25, TOPK=9, REG_LOSS_WEIGHT=2.0, POSITIVE_TYPE="ATSS",
                            REGRESSION_TYPE="BOX")))
@@ -103,6 +103,30 @@ with torch.cuda.graph(graph):
 ms = timed(lambda: graph.replay())
 out["atss_loss_step_16img_800x1333"] = {"ms": ms, "images_per_s": 16 / (ms / 1e3),
                                         "note": "paa_atss_assign + paa_loss (forward + gradients), graph replay"}
+
+# RetinaNet training step (IoU matching + Matcher labels + focal / smooth-L1 + gradients), 9 anchors per location
+rb = synthetic.make_retinanet_batch(seed=2100, num_images=16, image_hw=(800, 1333), gt_per_image=(1, 100))
+rcfg = NS(MODEL=NS(RETINANET=NS(LOSS_GAMMA=2.0, LOSS_ALPHA=0.25, FG_IOU_THRESHOLD=0.5, BG_IOU_THRESHOLD=0.4,
+                                BBOX_REG_BETA=0.11, BBOX_REG_WEIGHT=4.0)))
+rev = paa_b200.make_retinanet_loss_evaluator(rcfg, NS(weights=(10.0, 10.0, 5.0, 5.0)))
+rcls, rreg, _, rtargets, ranchors = to_device_inputs(rb, device=dev)
+rstep = lambda: rev.forward_backward(ranchors, rcls, rreg, rtargets)
+for _ in range(3):
+    rstep()
+torch.cuda.synchronize()
+side = torch.cuda.Stream(); side.wait_stream(torch.cuda.current_stream())
+with torch.cuda.stream(side):
+    rstep()
+torch.cuda.current_stream().wait_stream(side); torch.cuda.synchronize()
+rgraph = torch.cuda.CUDAGraph()
+with torch.cuda.graph(rgraph):
+    rstep()
+ms = timed(lambda: rgraph.replay())
+rbytes = sum(t.numel() * 4 for t in rcls)
+out["retinanet_loss_step_16img_800x1333_9anchors"] = {
+    "ms": ms, "images_per_s": 16 / (ms / 1e3), "logit_MB": rbytes / 1e6,
+    "logit_read_plus_grad_write_GBps": 2 * rbytes / (ms / 1e3) / 1e9,
+    "note": "paa_retinanet_assign + paa_loss (forward + gradients), graph replay; 201600 anchors x 80 classes per image"}
 
 # TTA merging: 14 augmentations x ~100 detections of one image, 20 classes present
 from paa_b200.bbox_aug_vote import merge_result_from_multi_scales

@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import paa_b200
 from paa_b200 import synthetic
-from tests.helpers import to_device_inputs
+from paa_b200.synthetic import to_device_inputs
 
 which = sys.argv[1] if len(sys.argv) > 1 else "c3"
 if which == "c3":      # dense crowd: 1333x1333, 500 GT/img, 4 images per GPU (batch 32 over 8)

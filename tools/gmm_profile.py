@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import paa_b200
 from paa_b200 import synthetic
-from tests.helpers import to_device_inputs
+from paa_b200.synthetic import to_device_inputs
 b = synthetic.make_batch(seed=2000, num_images=16, image_hw=(800, 1333), gt_per_image=(1, 100))
 cfg = paa_b200.default_cfg()
 ev = paa_b200.make_paa_loss_evaluator(cfg, paa_b200.BoxCoder(cfg))

@@ -9,6 +9,8 @@
 // The kernel reads each logit once (NCHW, coalesced over consecutive anchors), and writes the
 // gradient of the same element in the same pass, already divided by the all-reduced normalisers
 // that paa_assign left in device memory (no host round trip for .item(), loss.py:321,338).
+#include <cstdlib>
+
 #include "kernels.h"
 
 namespace paa {
@@ -142,7 +144,46 @@ struct BulkPlan {
     unsigned long long count[PAA_MAX_LEVELS];      // floats in the level's tensor
     unsigned chunk_off[PAA_MAX_LEVELS + 1];        // first chunk of each level in the virtual concatenation
     int n;
+    // kIgnore only (RetinaNet): one bit per anchor, set = the focal loss ignores the anchor.  Level l's bits are
+    // ordered [image][anchor slot][location] -- the order of the level's NCHW planes -- so element e of the
+    // level's tensor belongs to bit (e / hw / C) * hw + e % hw.
+    const unsigned* ign[PAA_MAX_LEVELS];
+    unsigned hw[PAA_MAX_LEVELS];
+    unsigned long long magic_hw[PAA_MAX_LEVELS];   // ceil(2^64 / hw) (hw / 4 on the float4 path)
+    unsigned long long magic_c;                    // ceil(2^64 / C)
+    unsigned C;
+    unsigned char vec4[PAA_MAX_LEVELS];            // hw % 4 == 0: the four elements of a float4 share a plane
 };
+
+// n / d for n < 2^32 with magic = ceil(2^64 / d), d >= 2: exact (error term n / 2^64 < 1 / d).
+__device__ __forceinline__ unsigned div_magic(unsigned n, unsigned long long magic) {
+    return (unsigned)__umul64hi((unsigned long long)n, magic);
+}
+
+// The ignore bit of element e of level l on the per-element path (magic_hw = ceil(2^64 / hw)).
+__device__ __forceinline__ unsigned ignore_bit(const BulkPlan& plan, int l, unsigned e) {
+    const unsigned hw = plan.hw[l];
+    const unsigned plane = div_magic(e, plan.magic_hw[l]);
+    const unsigned bit = div_magic(plane, plan.magic_c) * hw + (e - plane * hw);
+    return (__ldg(plan.ign[l] + (bit >> 5)) >> (bit & 31u)) & 1u;
+}
+
+// The ignore bits of the float4 at float4-index e4 of level l (bit k = element k).
+__device__ __forceinline__ unsigned ignore_nibble(const BulkPlan& plan, int l, unsigned long long e4) {
+    const unsigned hw = plan.hw[l];
+    const unsigned* __restrict__ bits = plan.ign[l];
+    if (plan.vec4[l]) {
+        const unsigned hw4 = hw >> 2;
+        const unsigned plane = div_magic((unsigned)e4, plan.magic_hw[l]);
+        const unsigned loc4 = (unsigned)e4 - plane * hw4;
+        const unsigned bit = div_magic(plane, plan.magic_c) * hw + (loc4 << 2);
+        return (__ldg(bits + (bit >> 5)) >> (bit & 31u)) & 0xfu;
+    }
+    unsigned nib = 0u;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) nib |= ignore_bit(plan, l, (unsigned)(e4 << 2) + k) << k;
+    return nib;
+}
 
 // negative-class focal term without its (1-alpha) factor, and the gradient with `k` = (1-alpha) * scale
 template <bool kG2>
@@ -154,7 +195,27 @@ __device__ __forceinline__ void neg_term_grad(float x, float gamma, float k, flo
     *grad = (mod * fmaf(gq, s.sp, s.p)) * k;
 }
 
-template <bool kGrads, bool kG2>
+// element of an ignored anchor: no loss term, zero gradient
+__device__ __forceinline__ float ignore_select(unsigned nib, int k, float v) { return (nib >> k) & 1u ? 0.0f : v; }
+
+template <bool kG2>
+__device__ __forceinline__ void neg_terms4(float4 x, float gamma, float kneg, unsigned nib, float* neg_sum, float4* g) {
+    float t[4] = {0.f, 0.f, 0.f, 0.f};
+    neg_term_grad<kG2>(x.x, gamma, kneg, &t[0], &g->x);
+    neg_term_grad<kG2>(x.y, gamma, kneg, &t[1], &g->y);
+    neg_term_grad<kG2>(x.z, gamma, kneg, &t[2], &g->z);
+    neg_term_grad<kG2>(x.w, gamma, kneg, &t[3], &g->w);
+    *neg_sum += ignore_select(nib, 0, t[0]);
+    *neg_sum += ignore_select(nib, 1, t[1]);
+    *neg_sum += ignore_select(nib, 2, t[2]);
+    *neg_sum += ignore_select(nib, 3, t[3]);
+    g->x = ignore_select(nib, 0, g->x);
+    g->y = ignore_select(nib, 1, g->y);
+    g->z = ignore_select(nib, 2, g->z);
+    g->w = ignore_select(nib, 3, g->w);
+}
+
+template <bool kGrads, bool kG2, bool kIgnore = false>
 __global__ void __launch_bounds__(kBulkThreads, kBulkBlocksPerSM)
 bulk_focal_kernel(const BulkPlan plan, const LossScalars sc, const double* __restrict__ norm,
                   const double* __restrict__ local_norm, const float* __restrict__ gout,
@@ -180,14 +241,26 @@ bulk_focal_kernel(const BulkPlan plan, const LossScalars sc, const double* __res
             float4 x[kBulkVecs];
 #pragma unroll
             for (int j = 0; j < kBulkVecs; ++j) x[j] = __ldcs(src4 + base4 + j * kBulkThreads + threadIdx.x);
+            if (kIgnore) {
+                unsigned nib[kBulkVecs];
 #pragma unroll
-            for (int j = 0; j < kBulkVecs; ++j) {
-                float4 g;
-                neg_term_grad<kG2>(x[j].x, gamma, kneg, &neg_sum, &g.x);
-                neg_term_grad<kG2>(x[j].y, gamma, kneg, &neg_sum, &g.y);
-                neg_term_grad<kG2>(x[j].z, gamma, kneg, &neg_sum, &g.z);
-                neg_term_grad<kG2>(x[j].w, gamma, kneg, &neg_sum, &g.w);
-                if (write) __stcs(dst4 + base4 + j * kBulkThreads + threadIdx.x, g);
+                for (int j = 0; j < kBulkVecs; ++j) nib[j] = ignore_nibble(plan, l, base4 + j * kBulkThreads + threadIdx.x);
+#pragma unroll
+                for (int j = 0; j < kBulkVecs; ++j) {
+                    float4 g;
+                    neg_terms4<kG2>(x[j], gamma, kneg, nib[j], &neg_sum, &g);
+                    if (write) __stcs(dst4 + base4 + j * kBulkThreads + threadIdx.x, g);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < kBulkVecs; ++j) {
+                    float4 g;
+                    neg_term_grad<kG2>(x[j].x, gamma, kneg, &neg_sum, &g.x);
+                    neg_term_grad<kG2>(x[j].y, gamma, kneg, &neg_sum, &g.y);
+                    neg_term_grad<kG2>(x[j].z, gamma, kneg, &neg_sum, &g.z);
+                    neg_term_grad<kG2>(x[j].w, gamma, kneg, &neg_sum, &g.w);
+                    if (write) __stcs(dst4 + base4 + j * kBulkThreads + threadIdx.x, g);
+                }
             }
         } else {
             // last chunk of a level: guarded float4s, then the (count % 4) scalar tail
@@ -196,17 +269,27 @@ bulk_focal_kernel(const BulkPlan plan, const LossScalars sc, const double* __res
                 if (i4 < n4) {
                     const float4 x = __ldcs(src4 + i4);
                     float4 g;
-                    neg_term_grad<kG2>(x.x, gamma, kneg, &neg_sum, &g.x);
-                    neg_term_grad<kG2>(x.y, gamma, kneg, &neg_sum, &g.y);
-                    neg_term_grad<kG2>(x.z, gamma, kneg, &neg_sum, &g.z);
-                    neg_term_grad<kG2>(x.w, gamma, kneg, &neg_sum, &g.w);
+                    if (kIgnore) {
+                        neg_terms4<kG2>(x, gamma, kneg, ignore_nibble(plan, l, i4), &neg_sum, &g);
+                    } else {
+                        neg_term_grad<kG2>(x.x, gamma, kneg, &neg_sum, &g.x);
+                        neg_term_grad<kG2>(x.y, gamma, kneg, &neg_sum, &g.y);
+                        neg_term_grad<kG2>(x.z, gamma, kneg, &neg_sum, &g.z);
+                        neg_term_grad<kG2>(x.w, gamma, kneg, &neg_sum, &g.w);
+                    }
                     if (write) __stcs(dst4 + i4, g);
                 }
             }
             const unsigned long long tail = (n4 << 2) + threadIdx.x;
             if (threadIdx.x < 4 && tail < count) {
-                float g;
-                neg_term_grad<kG2>(plan.src[l][tail], gamma, kneg, &neg_sum, &g);
+                float g, t = 0.f;
+                neg_term_grad<kG2>(plan.src[l][tail], gamma, kneg, &t, &g);
+                if (kIgnore) {
+                    const unsigned nib = ignore_bit(plan, l, (unsigned)tail);   // count % 4 != 0: per-element path
+                    t = ignore_select(nib, 0, t);
+                    g = ignore_select(nib, 0, g);
+                }
+                neg_sum += t;
                 if (write) plan.dst[l][tail] = g;
             }
         }
@@ -288,25 +371,37 @@ __device__ __forceinline__ void positive_smooth_l1(const Geometry& geo, const Le
     *reg_sum += s;
 }
 
-// One thread per anchor, one block per 128-anchor tile (same tiling as the assignment kernels).
-// Runs after bulk_focal_kernel on the same stream: it overwrites the labelled class's gradient element.
+// One thread per anchor, 128-anchor tiles (same tiling as the assignment kernels); a block takes
+// `tiles_per_block` consecutive tiles (1 unless the call has more than kMaxTileBlocks tiles, so that the fold of
+// the partials stays short).  Runs after bulk_focal_kernel on the same stream: it overwrites the labelled
+// class's gradient element.  `zero_fill`: this kernel also zeroes the regression / IoU gradients of the
+// non-positive anchors (coalesced for one anchor per location; with several the launcher clears them up front).
+constexpr int kMaxTileBlocks = 8192;
+
 template <bool kGrads, bool kG2>
 __global__ void __launch_bounds__(PAA_TILE)
 positive_terms_kernel(const Geometry geo, const GtOffsets go, const float* __restrict__ gt_boxes,
                       const LossScalars sc, const int* __restrict__ paa_label, const int* __restrict__ matched,
                       const double* __restrict__ norm, const double* __restrict__ local_norm,
-                      const float* __restrict__ gout, double* __restrict__ block_part) {
+                      const float* __restrict__ gout, double* __restrict__ block_part, int tiles_total,
+                      int tiles_per_block, bool zero_fill, bool patch_ignored) {
     __shared__ double s_part[PAA_TILE / PAA_WARP][3];
-    const int n = blockIdx.x / geo.tiles_per_image;
-    const int tile = blockIdx.x - n * geo.tiles_per_image;
-    int first;
-    const int l = tile_level(geo, tile, &first);
-    const LevelView& lv = geo.lv[l];
-    const int i = first + threadIdx.x;
-    float fix_sum = 0.f, reg_sum = 0.f, bce_sum = 0.f;
-    if (i < lv.n_anchor) {
-        const size_t flat = (size_t)n * geo.A + lv.a_off + i;
-        const int label = __ldg(paa_label + flat);
+    __shared__ int s_ign[PAA_TILE];                 // ignored anchors of the tile (index within the level)
+    __shared__ int s_wcnt[PAA_TILE / PAA_WARP];
+    float fix_sum = 0.f, reg_sum = 0.f, bce_sum = 0.f, ign_sum = 0.f;
+    const bool may_ignore = patch_ignored;                          // block-uniform
+    const int lane_ = threadIdx.x & 31, warp_ = threadIdx.x >> 5;
+    const int t_end = min((int)(blockIdx.x + 1) * tiles_per_block, tiles_total);
+    for (int t = blockIdx.x * tiles_per_block; t < t_end; ++t) {
+        const int n = t / geo.tiles_per_image;
+        const int tile = t - n * geo.tiles_per_image;
+        int first;
+        const int l = tile_level(geo, tile, &first);
+        const LevelView& lv = geo.lv[l];
+        const int i = first + threadIdx.x;
+        const bool valid = i < lv.n_anchor;
+        const size_t flat = (size_t)n * geo.A + lv.a_off + (valid ? i : 0);
+        const int label = valid ? __ldg(paa_label + flat) : 0;
         float4 gd = make_float4(0.f, 0.f, 0.f, 0.f);
         float gi = 0.f;
         if (label > 0) {
@@ -327,7 +422,7 @@ positive_terms_kernel(const Geometry geo, const GtOffsets go, const float* __res
             focal_positive(xp, sp, cx.gamma, kG2, cx.alpha, &tp, &gp);
             (void)tn;
             (void)gn;
-            fix_sum = tp - cx.oma * tn_acc;
+            fix_sum += tp - cx.oma * tn_acc;
             if (kGrads && lv.g_cls) lv.g_cls[off] = gp * cx.gs.cls;
             // box regression + IoU prediction
             const float* rp = lv.reg + head_offset(n, i, 0, 4, geo.apl, lv.hw);
@@ -339,19 +434,8 @@ positive_terms_kernel(const Geometry geo, const GtOffsets go, const float* __res
             else
                 positive_box_terms(geo, lv, go, gt_boxes, sc, cx, n, i, matched[flat], d, xi, &reg_sum, &bce_sum,
                                    &gd, &gi);
-        } else if (label < 0) {
-            // ignored anchor (RetinaNet, between the Matcher thresholds): the focal loss skips all of its classes
-            // (sigmoid_focal_loss.py:50, SigmoidFocalLoss_cuda.cu:44) -- take back what the bulk pass added
-            const float oma = 1.0f - sc.alpha;
-            float acc = 0.f, g_unused;
-            for (int c = 0; c < geo.C; ++c) {
-                const size_t off = head_offset(n, i, c, geo.C, geo.apl, lv.hw);
-                neg_term_grad<kG2>(__ldg(lv.cls + off), sc.gamma, 0.0f, &acc, &g_unused);
-                if (kGrads && lv.g_cls) lv.g_cls[off] = 0.0f;
-            }
-            fix_sum = -(oma * acc);
         }
-        if (kGrads) {
+        if (kGrads && valid && (zero_fill || label > 0)) {
             if (lv.g_reg) {
                 float* gr = lv.g_reg + head_offset(n, i, 0, 4, geo.apl, lv.hw);
                 gr[0] = gd.x;
@@ -361,7 +445,34 @@ positive_terms_kernel(const Geometry geo, const GtOffsets go, const float* __res
             }
             if (lv.g_iou) lv.g_iou[head_offset(n, i, 0, 1, geo.apl, lv.hw)] = gi;
         }
+        if (may_ignore) {
+            // Ignored anchors (RetinaNet, between the Matcher thresholds) when the bulk pass could not skip them
+            // itself: the focal loss ignores all of their classes (sigmoid_focal_loss.py:50,
+            // SigmoidFocalLoss_cuda.cu:44) -- take back what the bulk pass added.  Their C elements are hw floats apart, so the whole block shares them: the tile's ignored
+            // anchors are listed in anchor order (deterministic) and the (class, anchor) pairs dealt out to all
+            // threads as independent loads, instead of one thread walking C dependent cache misses.
+            const unsigned bal = __ballot_sync(PAA_FULL, label < 0);
+            if (lane_ == 0) s_wcnt[warp_] = __popc(bal);
+            __syncthreads();
+            int base = 0, total = 0;
+#pragma unroll
+            for (int w = 0; w < PAA_TILE / PAA_WARP; ++w) {
+                if (w < warp_) base += s_wcnt[w];
+                total += s_wcnt[w];
+            }
+            if (label < 0) s_ign[base + __popc(bal & ((1u << lane_) - 1u))] = i;
+            __syncthreads();
+            const int items = total * geo.C;
+            for (int it = threadIdx.x; it < items; it += PAA_TILE) {
+                const int c = it / total, k = it - c * total;
+                const size_t off = head_offset(n, s_ign[k], c, geo.C, geo.apl, lv.hw);
+                float g_unused;
+                neg_term_grad<kG2>(__ldg(lv.cls + off), sc.gamma, 0.0f, &ign_sum, &g_unused);
+                if (kGrads && lv.g_cls) lv.g_cls[off] = 0.0f;
+            }
+        }
     }
+    fix_sum -= (1.0f - sc.alpha) * ign_sum;
     double a0 = warp_sum((double)fix_sum), a1 = warp_sum((double)reg_sum), a2 = warp_sum((double)bce_sum);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (lane == 0) {
@@ -464,28 +575,70 @@ int launch_final_loss(const Geometry& geo, const GtOffsets& go, const float* gt_
         plan.dst[l] = nullptr;
         plan.count[l] = 0;
     }
+    // RetinaNet: the labelling kernel left one bit per ignored anchor (retina.cu); the bulk pass skips those
+    // elements in stream, which saves positive_terms_kernel C scattered reads and writes per ignored anchor.
+    bool bulk_ignores = sc.flavour == PAA_LOSS_RETINANET && geo.C >= 2;
+    if (getenv("PAA_RETINA_PATCH")) bulk_ignores = false;      // test hook: force the per-anchor fallback
+    for (int l = 0; l < geo.num_levels && bulk_ignores; ++l)
+        if (plan.count[l] >= (1ull << 32) || geo.lv[l].hw < 2 || geo.lv[l].hw == 4) bulk_ignores = false;
+    plan.C = (unsigned)geo.C;
+    plan.magic_c = geo.C >= 2 ? ~0ull / (unsigned)geo.C + 1ull : 0ull;
+    for (int l = 0; l < PAA_MAX_LEVELS; ++l) {
+        plan.ign[l] = nullptr;
+        plan.hw[l] = 1;
+        plan.magic_hw[l] = 0ull;
+        plan.vec4[l] = 0;
+        if (l >= geo.num_levels || !bulk_ignores) continue;
+        const LevelView& lv = geo.lv[l];
+        plan.ign[l] = reinterpret_cast<const unsigned*>(ws.tile_gtmask) + (size_t)geo.num_images * lv.tile_off * 4;
+        plan.hw[l] = (unsigned)lv.hw;
+        plan.vec4[l] = (lv.hw & 3) == 0 ? 1 : 0;
+        const unsigned d = plan.vec4[l] ? (unsigned)lv.hw >> 2 : (unsigned)lv.hw;
+        plan.magic_hw[l] = ~0ull / d + 1ull;       // ceil(2^64 / d) for d >= 2 that is not a power of two, and
+                                                   // 2^64 / d exactly when it is
+    }
     int bulk_grid = kBulkMaxBlocks;
     if ((unsigned)bulk_grid > chunks) bulk_grid = (int)chunks;
-    const int tile_grid = geo.num_images * geo.tiles_per_image;
+    const int tiles_total = geo.num_images * geo.tiles_per_image;
+    const int tiles_per_block = (tiles_total + kMaxTileBlocks - 1) / kMaxTileBlocks;
+    const int tile_grid = (tiles_total + tiles_per_block - 1) / tiles_per_block;
+    // several anchors per location: an anchor's regression channels are hw floats apart from its neighbour's, so
+    // zeroing them anchor by anchor scatters 4-byte writes; clear the tensors up front and write positives only
+    const bool zero_fill = geo.apl == 1;
+    if (write_grads && !zero_fill) {
+        for (int l = 0; l < geo.num_levels; ++l) {
+            const LevelView& lv = geo.lv[l];
+            const size_t per = (size_t)geo.num_images * geo.apl * lv.hw * sizeof(float);
+            if (lv.g_reg) PAA_CUDA_CHECK(cudaMemsetAsync(lv.g_reg, 0, per * 4, stream));
+            if (lv.g_iou) PAA_CUDA_CHECK(cudaMemsetAsync(lv.g_iou, 0, per, stream));
+        }
+    }
     const bool g2 = (sc.gamma == 2.0f);
     double* bulk_part = ws.block_part;
     double* tile_part = ws.block_part + (size_t)kBulkMaxBlocks * 3;
     {
         KernelTimer timer(PAA_KERNEL_FINAL_LOSS, stream);
-#define PAA_BULK(G, T)                                                                                       \
-    bulk_focal_kernel<G, T><<<bulk_grid, kBulkThreads, 0, stream>>>(plan, sc, normalisers, ws.local_norm,    \
-                                                                    grad_losses, bulk_part)
-        if (write_grads) {
-            if (g2) PAA_BULK(true, true); else PAA_BULK(true, false);
+#define PAA_BULK(G, T, I)                                                                                    \
+    bulk_focal_kernel<G, T, I><<<bulk_grid, kBulkThreads, 0, stream>>>(plan, sc, normalisers, ws.local_norm, \
+                                                                       grad_losses, bulk_part)
+        if (bulk_ignores) {
+            if (write_grads) {
+                if (g2) PAA_BULK(true, true, true); else PAA_BULK(true, false, true);
+            } else {
+                if (g2) PAA_BULK(false, true, true); else PAA_BULK(false, false, true);
+            }
+        } else if (write_grads) {
+            if (g2) PAA_BULK(true, true, false); else PAA_BULK(true, false, false);
         } else {
-            if (g2) PAA_BULK(false, true); else PAA_BULK(false, false);
+            if (g2) PAA_BULK(false, true, false); else PAA_BULK(false, false, false);
         }
 #undef PAA_BULK
     }
     PAA_LAUNCH_CHECK("bulk_focal_kernel");
 #define PAA_POS(G, T)                                                                                        \
     positive_terms_kernel<G, T><<<tile_grid, PAA_TILE, 0, stream>>>(geo, go, gt_boxes, sc, ws.paa_label,     \
-        ws.matched, normalisers, ws.local_norm, grad_losses, tile_part)
+        ws.matched, normalisers, ws.local_norm, grad_losses, tile_part, tiles_total, tiles_per_block, zero_fill,  \
+        sc.flavour == PAA_LOSS_RETINANET && !bulk_ignores)
     if (write_grads) {
         if (g2) PAA_POS(true, true); else PAA_POS(true, false);
     } else {

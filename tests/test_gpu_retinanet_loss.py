@@ -68,6 +68,15 @@ def test_retinanet_loss_other_parameters_and_crowded_image():
     _check(b, cfg, prm)
 
 
+def test_retinanet_fallback_that_patches_ignored_anchors_one_by_one(monkeypatch):
+    """The loss pass normally skips ignored anchors in stream through a bitmap; the fallback (used when a level's
+    tensor has 2^32 elements or more) takes their terms back per anchor instead."""
+    monkeypatch.setenv("PAA_RETINA_PATCH", "1")
+    b = synthetic.make_retinanet_batch(seed=76, num_images=2, image_hw=(320, 416), gt_per_image=(3, 9))
+    asg = _check(b, _cfg(), retinanet_oracle.default_params())
+    assert (asg.labels == -1).any()
+
+
 def test_retinanet_positives_from_the_low_quality_restore_only():
     """One GT far smaller than every anchor: no IoU reaches the thresholds, the only positives are the GT's best
     anchors restored by allow_low_quality_matches (matcher.py:83-113)."""

@@ -37,3 +37,18 @@ for _ in range(10):
     ts.append(s.elapsed_time(e))
 ts.sort()
 print("eager step median %.1f us" % (1000 * ts[len(ts) // 2]))
+side = torch.cuda.Stream(); side.wait_stream(torch.cuda.current_stream())
+with torch.cuda.stream(side):
+    step()
+torch.cuda.current_stream().wait_stream(side); torch.cuda.synchronize()
+graph = torch.cuda.CUDAGraph()
+with torch.cuda.graph(graph):
+    step()
+ts = []
+for _ in range(10):
+    flush.zero_()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record(); graph.replay(); e.record(); torch.cuda.synchronize()
+    ts.append(s.elapsed_time(e))
+ts.sort()
+print("graph replay median %.1f us" % (1000 * ts[len(ts) // 2]))

@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define PAA_ABI_VERSION 4
+#define PAA_ABI_VERSION 5
 #define PAA_MAX_LEVELS 8
 #define PAA_MAX_IMAGES 256      /* images per call (per rank) */
 #define PAA_MAX_CANDIDATES 128  /* num_levels * topk must not exceed this */
@@ -79,7 +79,11 @@ typedef struct PaaLossArgs {
                                      paa_atss_assign;
                                      PAA_LOSS_RETINANET: labels straight from the Matcher (-1 = ignored), smooth-L1 on
                                      the regression deltas (retinanet/loss.py:45-81), assignment by
-                                     paa_retinanet_assign; use_iou_pred must be 0 */
+                                     paa_retinanet_assign; use_iou_pred must be 0;
+                                     PAA_LOSS_FCOS: anchor-free (fcos/loss.py): `anchors` are the locations as points
+                                     (x, y, x, y), the regression maps are distances (l, t, r, b), IOULoss
+                                     (layers/iou_loss.py) weighted by the centerness targets, BCE on the centerness
+                                     map (passed as iou_pred), assignment by paa_fcos_assign */
     float gamma, alpha;           /* focal loss, cfg.MODEL.PAA.LOSS_GAMMA / LOSS_ALPHA */
     float iou_threshold;          /* Matcher high threshold; PAA: high == low (loss.py:38-40) */
     float reg_loss_weight;        /* cfg.MODEL.PAA.REG_LOSS_WEIGHT */
@@ -125,6 +129,12 @@ typedef struct PaaLossArgs {
     float box_code_weights[4];    /* BoxCoder weights wx, wy, ww, wh (box_coder.py:22-50; 10, 10, 5, 5) */
     float smooth_l1_beta;         /* cfg.MODEL.RETINANET.BBOX_REG_BETA */
     float reg_norm_weight;        /* cfg.MODEL.RETINANET.BBOX_REG_WEIGHT: loss_reg / max(1, num_pos * this) */
+    /* PAA_LOSS_FCOS only */
+    float fcos_strides[PAA_MAX_LEVELS];   /* cfg.MODEL.FCOS.FPN_STRIDES */
+    float fcos_center_radius;     /* cfg.MODEL.FCOS.CENTER_SAMPLING_RADIUS (0 = every location inside the GT) */
+    int32_t fcos_iou_loss_type;   /* PAA_IOU_LOSS_IOU / _LINEAR / _GIOU (cfg.MODEL.FCOS.IOU_LOSS_TYPE) */
+    int32_t fcos_norm_reg_targets;/* cfg.MODEL.FCOS.NORM_REG_TARGETS: targets divided by the level's stride */
+    int32_t reserved3;
 } PaaLossArgs;
 
 typedef struct PaaPostArgs {
@@ -166,6 +176,10 @@ typedef struct PaaPostArgs {
 #define PAA_LOSS_PAA  0
 #define PAA_LOSS_ATSS 1
 #define PAA_LOSS_RETINANET 2
+#define PAA_LOSS_FCOS 3
+#define PAA_IOU_LOSS_IOU    0
+#define PAA_IOU_LOSS_LINEAR 1
+#define PAA_IOU_LOSS_GIOU   2
 #define PAA_DECODE_ATSS_BOX 0
 #define PAA_DECODE_LEGACY   1
 #define PAA_DECODE_LTRB     2
@@ -221,6 +235,14 @@ int paa_atss_assign(const PaaLossArgs* args, void* stream);
  * ranks); follow with paa_loss and loss_flavour = PAA_LOSS_RETINANET, which returns losses = {cls, reg, 0}.
  * dbg_matched_idx receives the Matcher result (-2 = between thresholds), dbg_iou_labels the labels. */
 int paa_retinanet_assign(const PaaLossArgs* args, void* stream);
+
+/* FCOS target assignment (rpn/fcos/loss.py:105-201) in place of paa_assign: every location takes, among the GTs
+ * that contain it (or whose centre region of fcos_center_radius * stride contains it) and whose largest distance
+ * max(l, t, r, b) lies in the level's size range ((-1, 64), (64, 128), (128, 256), (256, 512), (512, inf): at most
+ * five levels), the one with the smallest area.  anchors_per_loc must be 1 and levels[l].anchors hold the points
+ * (x, y, x, y).  normalisers = {num_pos, sum of centerness targets}, exchanged over ranks like PAA's; follow with
+ * paa_loss and loss_flavour = PAA_LOSS_FCOS.  dbg_matched_idx receives the chosen GT (-1 = background). */
+int paa_fcos_assign(const PaaLossArgs* args, void* stream);
 
 /* ---- operators on either side of the path ----------------------------------------- */
 /* AnchorGenerator.grid_anchors (anchor_generator.py:73-95) for one level: out[(y*W + x)*a + k] =

@@ -13,14 +13,16 @@ __all__ = ["BoxCoder", "BoxList", "boxlist_iou", "cat_boxlist", "default_cfg", "
            "make_paa_postprocessor", "PAALossComputation", "PAAPostProcessor", "make_anchor_generator_paa",
            "AnchorGenerator", "make_atss_postprocessor", "ATSSPostProcessor", "make_retinanet_postprocessor",
            "RetinaNetPostProcessor", "make_fcos_postprocessor", "FCOSPostProcessor", "make_atss_loss_evaluator",
-           "ATSSLossComputation", "make_retinanet_loss_evaluator", "RetinaNetLossComputation"]
+           "ATSSLossComputation", "make_retinanet_loss_evaluator", "RetinaNetLossComputation",
+           "make_fcos_loss_evaluator", "FCOSLossComputation"]
 
 
 def __getattr__(name):
     # the evaluator classes load libpaa_b200.so; import them lazily so that CPU-only tooling
     # (synthetic inputs, config) does not need the library
     if name in ("make_paa_loss_evaluator", "PAALossComputation", "make_atss_loss_evaluator", "ATSSLossComputation",
-                "make_retinanet_loss_evaluator", "RetinaNetLossComputation"):
+                "make_retinanet_loss_evaluator", "RetinaNetLossComputation", "make_fcos_loss_evaluator",
+                "FCOSLossComputation"):
         from paa_b200 import loss
         return getattr(loss, name)
     if name in ("make_paa_postprocessor", "PAAPostProcessor", "make_atss_postprocessor", "ATSSPostProcessor",

@@ -14,7 +14,7 @@ MAX_IMAGES = 256
 MAX_PEERS = 16
 PEER_BUFFER_DOUBLES = 256
 MAX_CANDIDATES = 128
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 ERR_BAD_ARGUMENT, ERR_WORKSPACE, ERR_EMPTY_TARGET, ERR_UNSUPPORTED = -1, -2, -3, -4
 
@@ -45,7 +45,9 @@ class PaaLossArgs(C.Structure):
                 ("dbg_paa_labels", C.c_void_p), ("teacher_combined_loss", C.c_void_p),
                 ("rank", C.c_int32), ("reserved2", C.c_int32), ("peer_norm", C.c_void_p * MAX_PEERS),
                 ("box_code_weights", C.c_float * 4), ("smooth_l1_beta", C.c_float),
-                ("reg_norm_weight", C.c_float)]
+                ("reg_norm_weight", C.c_float), ("fcos_strides", C.c_float * MAX_LEVELS),
+                ("fcos_center_radius", C.c_float), ("fcos_iou_loss_type", C.c_int32),
+                ("fcos_norm_reg_targets", C.c_int32), ("reserved3", C.c_int32)]
 
 
 class PaaPostArgs(C.Structure):
@@ -65,7 +67,8 @@ class PaaPostArgs(C.Structure):
                 ("box_decode", C.c_int32), ("decode_weights", C.c_float * 4), ("decode_clip", C.c_float)]
 
 DECODE_ATSS_BOX, DECODE_LEGACY, DECODE_LTRB = 0, 1, 2
-LOSS_PAA, LOSS_ATSS, LOSS_RETINANET = 0, 1, 2
+LOSS_PAA, LOSS_ATSS, LOSS_RETINANET, LOSS_FCOS = 0, 1, 2, 3
+IOU_LOSS_TYPES = {"iou": 0, "linear_iou": 1, "giou": 2}
 
 
 # name -> (restype, argtypes); every symbol include/paa_b200.h declares
@@ -78,6 +81,7 @@ SYMBOLS = {
     "paa_loss": (C.c_int, [C.POINTER(PaaLossArgs), C.c_void_p]),
     "paa_atss_assign": (C.c_int, [C.POINTER(PaaLossArgs), C.c_void_p]),
     "paa_retinanet_assign": (C.c_int, [C.POINTER(PaaLossArgs), C.c_void_p]),
+    "paa_fcos_assign": (C.c_int, [C.POINTER(PaaLossArgs), C.c_void_p]),
     "paa_assign_loss": (C.c_int, [C.POINTER(PaaLossArgs), C.c_void_p]),
     "paa_rescale_grads": (C.c_int, [C.POINTER(PaaLossArgs), C.c_void_p, C.c_void_p, C.c_void_p]),
     "paa_postprocess": (C.c_int, [C.POINTER(PaaPostArgs), C.c_void_p]),

@@ -176,7 +176,7 @@ static int plan_loss(const PaaLossArgs* a, LossPlan* p) {
     p->sc.world_size = a->world_size;
     p->sc.flavour = a->loss_flavour;
     if (a->loss_flavour != PAA_LOSS_PAA && a->loss_flavour != PAA_LOSS_ATSS &&
-        a->loss_flavour != PAA_LOSS_RETINANET) {
+        a->loss_flavour != PAA_LOSS_RETINANET && a->loss_flavour != PAA_LOSS_FCOS) {
         set_error("loss_flavour=%d", a->loss_flavour);
         return PAA_ERR_BAD_ARGUMENT;
     }
@@ -185,6 +185,31 @@ static int plan_loss(const PaaLossArgs* a, LossPlan* p) {
     for (int k = 0; k < 4; ++k) p->sc.code_w[k] = a->box_code_weights[k];
     p->sc.beta = a->smooth_l1_beta;
     p->sc.reg_norm_weight = a->reg_norm_weight;
+    p->sc.fcos_iou_type = a->fcos_iou_loss_type;
+    p->sc.fcos_norm = a->fcos_norm_reg_targets;
+    for (int l = 0; l < PAA_MAX_LEVELS; ++l) {
+        p->sc.fcos_stride[l] = a->fcos_strides[l];
+        // `center - stride * radius` with a Python float product rounded to float32 (fcos/loss.py:74-78)
+        p->sc.fcos_radius[l] = (float)((double)a->fcos_strides[l] * (double)a->fcos_center_radius);
+    }
+    if (a->loss_flavour == PAA_LOSS_FCOS) {
+        if (!a->use_iou_pred || a->anchors_per_loc != 1 || a->num_levels > 5) {
+            // object_sizes_of_interest lists five levels (fcos/loss.py:106-112)
+            set_error("PAA_LOSS_FCOS needs the centerness map (use_iou_pred), anchors_per_loc = 1 and <= 5 levels");
+            return PAA_ERR_BAD_ARGUMENT;
+        }
+        if (a->fcos_iou_loss_type < PAA_IOU_LOSS_IOU || a->fcos_iou_loss_type > PAA_IOU_LOSS_GIOU ||
+            !(a->fcos_center_radius >= 0.0f)) {
+            set_error("PAA_LOSS_FCOS: fcos_iou_loss_type=%d / fcos_center_radius=%g", a->fcos_iou_loss_type,
+                      a->fcos_center_radius);
+            return PAA_ERR_BAD_ARGUMENT;
+        }
+        for (int l = 0; l < a->num_levels; ++l)
+            if (!(a->fcos_strides[l] > 0.0f)) {
+                set_error("PAA_LOSS_FCOS: fcos_strides[%d]=%g", l, a->fcos_strides[l]);
+                return PAA_ERR_BAD_ARGUMENT;
+            }
+    }
     if (a->loss_flavour == PAA_LOSS_RETINANET) {
         if (a->use_iou_pred) {
             set_error("PAA_LOSS_RETINANET has no third head: use_iou_pred must be 0");
@@ -325,6 +350,25 @@ int paa_retinanet_assign(const PaaLossArgs* args, void* stream_) {
     }
     if ((rc = launch_retinanet_assign(p.geo, p.go, args->gt_boxes, args->gt_labels, p.sc, p.ws, args->normalisers,
                                       p.dbg, stream)))
+        return rc;
+    if (args->dbg_paa_labels)
+        PAA_CUDA_CHECK(cudaMemcpyAsync(args->dbg_paa_labels, p.ws.paa_label,
+                                       sizeof(int) * (size_t)args->num_images * p.geo.A,
+                                       cudaMemcpyDeviceToDevice, stream));
+    return 0;
+}
+
+int paa_fcos_assign(const PaaLossArgs* args, void* stream_) {
+    LossPlan p;
+    int rc = plan_loss(args, &p);
+    if (rc) return rc;
+    if (args->loss_flavour != PAA_LOSS_FCOS) {
+        set_error("paa_fcos_assign needs loss_flavour = PAA_LOSS_FCOS");
+        return PAA_ERR_BAD_ARGUMENT;
+    }
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if ((rc = launch_fcos_assign(p.geo, p.go, args->gt_boxes, args->gt_labels, p.sc, p.ws, args->normalisers, p.px,
+                                 p.dbg, stream)))
         return rc;
     if (args->dbg_paa_labels)
         PAA_CUDA_CHECK(cudaMemcpyAsync(args->dbg_paa_labels, p.ws.paa_label,

@@ -12,6 +12,9 @@ struct LossScalars {
     // PAA_LOSS_RETINANET: Matcher low threshold, BoxCoder weights, smooth-L1 beta, BBOX_REG_WEIGHT, images of the call
     float bg_threshold, code_w[4], beta, reg_norm_weight;
     int num_images;
+    // PAA_LOSS_FCOS: per-level stride and centre-sampling radius in pixels (0 = off), IoU loss type, target scaling
+    float fcos_stride[PAA_MAX_LEVELS], fcos_radius[PAA_MAX_LEVELS];
+    int fcos_iou_type, fcos_norm;
     int seg_cap;       // usable entries of a (GT, level) candidate pool, <= kSegCap (PAA_SEG_CAP shrinks it for tests)
 };
 
@@ -56,6 +59,10 @@ int launch_norm_wait(const PeerExchange& px, double* normalisers, cudaStream_t s
 // folds per-tile {count, sum} partials into local_norm / normalisers and publishes them to the peers
 int launch_fold_norm(const double* tile_part, int tiles, double* local_norm, double* normalisers,
                      const PeerExchange& px, cudaStream_t stream);
+// fcos.cu
+int launch_fcos_assign(const Geometry& geo, const GtOffsets& go, const float* gt_boxes, const int64_t* gt_labels,
+                       const LossScalars& sc, const LossWorkspace& ws, double* normalisers, const PeerExchange& px,
+                       const LossDebug& dbg, cudaStream_t stream);
 // retina.cu
 int launch_retinanet_assign(const Geometry& geo, const GtOffsets& go, const float* gt_boxes, const int64_t* gt_labels,
                             const LossScalars& sc, const LossWorkspace& ws, double* normalisers, const LossDebug& dbg,

@@ -344,6 +344,53 @@ __device__ __forceinline__ void positive_box_terms(const Geometry& geo, const Le
     *gd = make_float4(gdd.x * k, gdd.y * k, gdd.z * k, gdd.w * k);
 }
 
+// FCOS positive (fcos/loss.py:253-273): IOULoss (layers/iou_loss.py:12-51) between the predicted and the target
+// distances weighted by the centerness target, BCE of the centerness logit against the same target.
+__device__ __forceinline__ void positive_fcos_terms(const Geometry& geo, const LevelView& lv, const GtOffsets& go,
+                                                    const float* __restrict__ gt_boxes, const LossScalars& sc,
+                                                    const FinalCtx& cx, int n, int l, int i, int m, float4 p, float xi,
+                                                    float* reg_sum, float* bce_sum, float4* gd, float* gi) {
+    const float4 pt = ldg4(lv.anchors + (size_t)n * geo.anchor_image_stride + (size_t)i * 4);
+    const float4 gt = ldg4(gt_boxes + (size_t)(go.v[n] + m) * 4);
+    const float4 t = fcos_ltrb(pt.x, pt.y, gt, sc.fcos_norm != 0, sc.fcos_stride[l]);
+    const float q = fcos_centerness(t);
+    const float ei = expf(-fabsf(xi));
+    *bce_sum += fmaxf(xi, 0.0f) - xi * q + log1pf(ei);
+    const float sig = (xi >= 0.0f) ? 1.0f / (1.0f + ei) : ei / (1.0f + ei);
+    *gi = (sig - q) * cx.gs.bce;
+    const float w = cx.gs.weighted ? q : 1.0f;
+    // forward (argument order of iou_loss.py: left, top, right, bottom)
+    const float t_area = (t.x + t.z) * (t.y + t.w), p_area = (p.x + p.z) * (p.y + p.w);
+    const float wi = fminf(p.x, t.x) + fminf(p.z, t.z), hi = fminf(p.w, t.w) + fminf(p.y, t.y);
+    const float gw = fmaxf(p.x, t.x) + fmaxf(p.z, t.z), gh = fmaxf(p.w, t.w) + fmaxf(p.y, t.y);
+    const float ac = gw * gh + 1e-7f;
+    const float inter = wi * hi, uni = t_area + p_area - inter;
+    const float iou = (inter + 1.0f) / (uni + 1.0f);
+    float loss, g_iou, g_uni = 0.f, g_ac = 0.f;
+    if (sc.fcos_iou_type == PAA_IOU_LOSS_IOU) {
+        loss = -logf(iou);
+        g_iou = -1.0f / iou;
+    } else if (sc.fcos_iou_type == PAA_IOU_LOSS_LINEAR) {
+        loss = 1.0f - iou;
+        g_iou = -1.0f;
+    } else {
+        loss = 1.0f - (iou - (ac - uni) / ac);          // 1 - iou + 1 - uni / ac
+        g_iou = -1.0f;
+        g_uni = -1.0f / ac;
+        g_ac = uni / (ac * ac);
+    }
+    *reg_sum += loss * w;
+    // backward
+    g_uni += g_iou * (-(inter + 1.0f) / ((uni + 1.0f) * (uni + 1.0f)));
+    const float g_inter = g_iou / (uni + 1.0f) - g_uni;
+    const float g_wi = g_inter * hi, g_hi = g_inter * wi, g_gw = g_ac * gh, g_gh = g_ac * gw;
+    const float k = w * cx.gs.reg;
+    gd->x = (g_uni * (p.y + p.w) + g_wi * pick_first(p.x, t.x, false) + g_gw * pick_first(p.x, t.x, true)) * k;
+    gd->z = (g_uni * (p.y + p.w) + g_wi * pick_first(p.z, t.z, false) + g_gw * pick_first(p.z, t.z, true)) * k;
+    gd->y = (g_uni * (p.x + p.z) + g_hi * pick_first(p.y, t.y, false) + g_gh * pick_first(p.y, t.y, true)) * k;
+    gd->w = (g_uni * (p.x + p.z) + g_hi * pick_first(p.w, t.w, false) + g_gh * pick_first(p.w, t.w, true)) * k;
+}
+
 // Smooth-L1 regression loss / gradient of one RetinaNet positive (layers/smooth_l1_loss.py:6-17 on
 // box_coder.py:22-50 targets).
 __device__ __forceinline__ float smooth_l1_term(float x, float t, float beta, float k, float* g) {
@@ -431,6 +478,9 @@ positive_terms_kernel(const Geometry geo, const GtOffsets go, const float* __res
             const float xi = sc.use_iou_pred ? __ldg(lv.iou + head_offset(n, i, 0, 1, geo.apl, lv.hw)) : 0.f;
             if (sc.flavour == PAA_LOSS_RETINANET)
                 positive_smooth_l1(geo, lv, go, gt_boxes, sc, cx, n, i, matched[flat], d, &reg_sum, &gd);
+            else if (sc.flavour == PAA_LOSS_FCOS)
+                positive_fcos_terms(geo, lv, go, gt_boxes, sc, cx, n, l, i, matched[flat], d, xi, &reg_sum, &bce_sum,
+                                    &gd, &gi);
             else
                 positive_box_terms(geo, lv, go, gt_boxes, sc, cx, n, i, matched[flat], d, xi, &reg_sum, &bce_sum,
                                    &gd, &gi);
@@ -542,6 +592,8 @@ finish_loss_kernel(const double* __restrict__ part_a, int blocks_a, const double
         if (sc.use_iou_pred) {
             const float reg_norm = (float)(norm[1] / world);
             losses[1] = (float)t[1] / reg_norm * sc.reg_loss_weight;
+            // a rank without positives returns an empty sum instead (atss/loss.py:274-277, fcos/loss.py:274-277)
+            if (sc.flavour != PAA_LOSS_PAA && t[1] == 0.0) losses[1] = 0.0f;
             losses[2] = (float)t[2] / num_pos_avg * sc.iou_loss_weight;
         } else {
             losses[1] = (float)t[1] / num_pos_avg * sc.reg_loss_weight;

@@ -255,6 +255,12 @@ class PAALossComputation(object):
             for k in range(4):
                 args.box_code_weights[k] = self.box_code_weights[k]
             args.smooth_l1_beta, args.reg_norm_weight = self.bbox_reg_beta, self.regress_norm
+        if self._flavour == _lib.LOSS_FCOS:
+            for l, stride in enumerate(self.fpn_strides[:L]):
+                args.fcos_strides[l] = float(stride)
+            args.fcos_center_radius = self.center_sampling_radius
+            args.fcos_iou_loss_type = _lib.IOU_LOSS_TYPES[self.iou_loss_type]
+            args.fcos_norm_reg_targets = int(self.norm_reg_targets)
         args.anchor_image_stride = lv["anchor_stride"]
         grads = None
         if need_grad:
@@ -303,7 +309,7 @@ class PAALossComputation(object):
             args.teacher_combined_loss = teacher.data_ptr()
         stream = torch.cuda.current_stream(device).cuda_stream
         assign_name = {_lib.LOSS_PAA: "paa_assign", _lib.LOSS_ATSS: "paa_atss_assign",
-                       _lib.LOSS_RETINANET: "paa_retinanet_assign"}[self._flavour]
+                       _lib.LOSS_RETINANET: "paa_retinanet_assign", _lib.LOSS_FCOS: "paa_fcos_assign"}[self._flavour]
         assign = getattr(self._lib, assign_name)
         with torch.cuda.device(device):
             peer = PeerNormExchange.get(device) if world > 1 else None
@@ -462,3 +468,66 @@ def make_retinanet_loss_evaluator(cfg, box_coder):
     focal = SimpleNamespace(gamma=rn.LOSS_GAMMA, alpha=rn.LOSS_ALPHA)
     return RetinaNetLossComputation(matcher, box_coder, generate_retinanet_labels, focal,
                                     bbox_reg_beta=rn.BBOX_REG_BETA, regress_norm=rn.BBOX_REG_WEIGHT)
+
+
+class _Points(object):
+    """The FCOS locations of one level as degenerate boxes (x, y, x, y): what the kernels read as `anchors`."""
+
+    def __init__(self, bbox, size):
+        self.bbox = bbox
+        self.size = size
+
+
+class FCOSLossComputation(PAALossComputation):
+    """Drop-in for paa_core.modeling.rpn.fcos.loss.FCOSLossComputation (fcos/loss.py:36-281):
+    ``FCOSLossComputation(cfg)``, ``__call__(locations, box_cls, box_regression, centerness, targets)`` ->
+    ``(cls_loss, reg_loss, centerness_loss)``.  Target assignment is `paa_fcos_assign`, the losses come from the
+    same streaming pass as PAA's with IOULoss on the (l, t, r, b) maps weighted by the centerness targets."""
+
+    def __init__(self, cfg):
+        fcos = cfg.MODEL.FCOS
+        self.cfg = cfg
+        self.gamma = scalar(fcos.LOSS_GAMMA)
+        self.alpha = scalar(fcos.LOSS_ALPHA)
+        self.fpn_strides = list(fcos.FPN_STRIDES)
+        self.center_sampling_radius = float(fcos.CENTER_SAMPLING_RADIUS)
+        self.iou_loss_type = fcos.IOU_LOSS_TYPE
+        self.norm_reg_targets = bool(fcos.NORM_REG_TARGETS)
+        if self.iou_loss_type not in _lib.IOU_LOSS_TYPES:
+            raise NotImplementedError(self.iou_loss_type)              # layers/iou_loss.py:43-44
+        self.iou_threshold = 0.0
+        self.topk = 1
+        self.iou_loss_weight = 1.0
+        self.reg_loss_weight = 1.0
+        self._lib = _lib.load()
+        self.debug = False
+        self.last_debug = None
+        self.teacher_combined_loss = None
+        self._workspace = None
+        self._ones = None
+        self._flavour = _lib.LOSS_FCOS
+        self._points = {}
+
+    def _as_points(self, locations, targets):
+        if len(locations) > len(self.fpn_strides) or len(locations) > 5:
+            raise IndexError("list index out of range")               # object_sizes_of_interest[l], fcos/loss.py:116
+        points = []
+        for loc in locations:
+            key = (loc.data_ptr(), tuple(loc.shape))
+            if key not in self._points:
+                self._points[key] = torch.cat([loc, loc], dim=1).to(torch.float32).contiguous()
+            points.append(self._points[key])
+        return [[_Points(p, t.size) for p in points] for t in targets]
+
+    def forward_backward(self, locations, box_cls, box_regression, centerness, targets, grad_losses=None):
+        return super(FCOSLossComputation, self).forward_backward(box_cls, box_regression, centerness, targets,
+                                                                 self._as_points(locations, targets), grad_losses)
+
+    def __call__(self, locations, box_cls, box_regression, centerness, targets):
+        heads = list(box_cls) + list(box_regression) + list(centerness)
+        losses = _PAALossFunction.apply(self, targets, self._as_points(locations, targets), len(box_cls), True, *heads)
+        return losses[0], losses[1], losses[2]
+
+
+def make_fcos_loss_evaluator(cfg):
+    return FCOSLossComputation(cfg)                  # fcos/loss.py:284-286

@@ -75,6 +75,24 @@ def _worker(rank, world, port, out):
     paa_loss.PeerNormExchange._by_device.pop((dev.type, dev.index), None)
     assert paa_loss.PeerNormExchange.get(dev) is not None
     res["atss_peer_losses"] = aev.forward_backward(acls, areg, actr, atargets, aanchors)[0].cpu().numpy()
+    # FCOS publishes from the same fold kernel; RetinaNet normalises by its own rank's counts (no exchange)
+    fcfg = NS(MODEL=NS(FCOS=NS(LOSS_GAMMA=2.0, LOSS_ALPHA=0.25, FPN_STRIDES=[8, 16, 32, 64, 128],
+                               CENTER_SAMPLING_RADIUS=1.5, IOU_LOSS_TYPE="giou", NORM_REG_TARGETS=True)))
+    bf = synthetic.make_batch(seed=720 + rank, num_images=2, image_hw=(320, 416), gt_per_image=(2, 8),
+                              trained_like=False)
+    bf.box_regression = [(t.abs() * 40.0 + 1.0) for t in bf.box_regression]
+    fcls, freg, fctr, ftargets, _ = to_device_inputs(bf, device=dev)
+    flocs = [p.to(dev) for p in synthetic.fcos_locations(bf.grids)]
+    fev = paa_b200.make_fcos_loss_evaluator(fcfg)
+    res["fcos_peer_losses"] = fev.forward_backward(flocs, fcls, freg, fctr, ftargets)[0].cpu().numpy()
+    paa_loss.PeerNormExchange._by_device[(dev.type, dev.index)] = None
+    res["fcos_nccl_losses"] = fev.forward_backward(flocs, fcls, freg, fctr, ftargets)[0].cpu().numpy()
+    rcfg = NS(MODEL=NS(RETINANET=NS(LOSS_GAMMA=2.0, LOSS_ALPHA=0.25, FG_IOU_THRESHOLD=0.5, BG_IOU_THRESHOLD=0.4,
+                                    BBOX_REG_BETA=0.11, BBOX_REG_WEIGHT=4.0)))
+    br = synthetic.make_retinanet_batch(seed=730 + rank, num_images=2, image_hw=(320, 416), gt_per_image=(2, 7))
+    rcls, rreg, _, rtargets, ranchors = to_device_inputs(br, device=dev)
+    rev = paa_b200.make_retinanet_loss_evaluator(rcfg, NS(weights=(10.0, 10.0, 5.0, 5.0)))
+    res["retinanet_losses"] = rev.forward_backward(ranchors, rcls, rreg, rtargets)[0].cpu().numpy()
     torch.cuda.synchronize()
     dist.barrier()
     np.savez(out % rank, **res)
@@ -113,6 +131,13 @@ def test_peer_exchange_matches_all_reduce_and_oracle(tmp_path):
         np.testing.assert_array_equal(res[r]["peer_grad0"], res[r]["nccl_grad0"])
         np.testing.assert_array_equal(res[r]["atss_peer_losses"], res[r]["atss_nccl_losses"])
         assert np.isfinite(res[r]["atss_peer_losses"]).all()
+        np.testing.assert_array_equal(res[r]["fcos_peer_losses"], res[r]["fcos_nccl_losses"])
+        assert np.isfinite(res[r]["fcos_peer_losses"]).all()
+        from oracle import retinanet_oracle
+        br = synthetic.make_retinanet_batch(seed=730 + r, num_images=2, image_hw=(320, 416), gt_per_image=(2, 7))
+        want, _, _ = retinanet_oracle.assign_and_loss(br.box_cls, br.box_regression, br.gt_boxes, br.gt_labels,
+                                                      br.anchors, with_grad=False)
+        np.testing.assert_allclose(res[r]["retinanet_losses"][:2], [float(x) for x in want], rtol=1e-4)
         b = batches[r]
         ref = paa_oracle.losses(b.box_cls, b.box_regression, b.iou_pred, asgs[r], total_num_pos=tot_pos,
                                 total_sum_iou=tot_iou, world_size=2)

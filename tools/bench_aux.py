@@ -128,6 +128,30 @@ out["retinanet_loss_step_16img_800x1333_9anchors"] = {
     "logit_read_plus_grad_write_GBps": 2 * rbytes / (ms / 1e3) / 1e9,
     "note": "paa_retinanet_assign + paa_loss (forward + gradients), graph replay; 201600 anchors x 80 classes per image"}
 
+# FCOS training step (anchor-free assignment + focal / IOULoss / centerness + gradients) on the C2 shape
+fb = synthetic.make_batch(seed=2200, num_images=16, image_hw=(800, 1333), gt_per_image=(1, 100), trained_like=False)
+fb.box_regression = [(t.abs() * 40.0 + 1.0) for t in fb.box_regression]
+fcfg = NS(MODEL=NS(FCOS=NS(LOSS_GAMMA=2.0, LOSS_ALPHA=0.25, FPN_STRIDES=[8, 16, 32, 64, 128],
+                           CENTER_SAMPLING_RADIUS=1.5, IOU_LOSS_TYPE="giou", NORM_REG_TARGETS=True)))
+fev = paa_b200.make_fcos_loss_evaluator(fcfg)
+fcls, freg, fctr, ftargets, _ = to_device_inputs(fb, device=dev)
+flocs = [p.to(dev) for p in synthetic.fcos_locations(fb.grids)]
+fstep = lambda: fev.forward_backward(flocs, fcls, freg, fctr, ftargets)
+for _ in range(3):
+    fstep()
+torch.cuda.synchronize()
+side = torch.cuda.Stream(); side.wait_stream(torch.cuda.current_stream())
+with torch.cuda.stream(side):
+    fstep()
+torch.cuda.current_stream().wait_stream(side); torch.cuda.synchronize()
+fgraph = torch.cuda.CUDAGraph()
+with torch.cuda.graph(fgraph):
+    fstep()
+ms = timed(lambda: fgraph.replay())
+out["fcos_loss_step_16img_800x1333"] = {"ms": ms, "images_per_s": 16 / (ms / 1e3),
+                                        "note": "paa_fcos_assign + paa_loss (forward + gradients), graph replay; "
+                                                "centre sampling 1.5, GIoU loss, normalised targets"}
+
 # TTA merging: 14 augmentations x ~100 detections of one image, 20 classes present
 from paa_b200.bbox_aug_vote import merge_result_from_multi_scales
 g = torch.Generator().manual_seed(9)

@@ -33,12 +33,15 @@ fcos_assign_kernel(const Geometry geo, const GtOffsets go, const float* __restri
     // object_sizes_of_interest, fcos/loss.py:106-112
     const float lo = l == 0 ? -1.0f : (float)(32 << l), hi = l >= 4 ? kFcosInf : (float)(64 << l);
     const float radius = sc.fcos_radius[l];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float x = 0.f, y = 0.f;
     if (valid) {
         const float4 p = ldg4(lv.anchors + (size_t)n * geo.anchor_image_stride + (size_t)i * 4);
         x = p.x;
         y = p.y;
     }
+    const float wx1 = warp_min(valid ? x : INFINITY), wx2 = warp_max(valid ? x : -INFINITY);
+    const float wy1 = warp_min(valid ? y : INFINITY), wy2 = warp_max(valid ? y : -INFINITY);
     // get_sample_region's "no gt" test (fcos/loss.py:68-69): the first GT's centre x summed over all locations is
     // 0 exactly when that centre is 0 -- then no location is inside any box
     bool none_inside = false;
@@ -57,29 +60,41 @@ fcos_assign_kernel(const Geometry geo, const GtOffsets go, const float* __restri
         }
         __syncthreads();
         const int cnt = min(PAA_TILE, G - c0);
-        for (int k = 0; k < cnt; ++k) {
-            const float4 b = s_box[k];
-            const float dl = __fsub_rn(x, b.x), dt = __fsub_rn(y, b.y), dr = __fsub_rn(b.z, x), db = __fsub_rn(b.w, y);
-            bool inside;
-            if (radius > 0.0f) {
-                // centre region of the GT clipped to the GT (fcos/loss.py:71-103)
-                const float cx = __fdiv_rn(__fadd_rn(b.x, b.z), 2.0f), cy = __fdiv_rn(__fadd_rn(b.y, b.w), 2.0f);
-                const float xmin = __fsub_rn(cx, radius), ymin = __fsub_rn(cy, radius);
-                const float xmax = __fadd_rn(cx, radius), ymax = __fadd_rn(cy, radius);
-                const float rx1 = xmin > b.x ? xmin : b.x, ry1 = ymin > b.y ? ymin : b.y;
-                const float rx2 = xmax > b.z ? b.z : xmax, ry2 = ymax > b.w ? b.w : ymax;
-                const float m = fminf(fminf(__fsub_rn(x, rx1), __fsub_rn(y, ry1)),
-                                      fminf(__fsub_rn(rx2, x), __fsub_rn(ry2, y)));
-                inside = m > 0.0f && !none_inside;
-            } else {
-                inside = fminf(fminf(dl, dt), fminf(dr, db)) > 0.0f;                           // :178-179
+        // lane j tests GT g0 + j against the box around the warp's locations (a location inside a GT, or inside
+        // its centre region, lies inside the GT); only the GTs that reach it are walked, in index order
+        for (int g0 = 0; g0 < cnt; g0 += PAA_WARP) {
+            bool hit = false;
+            if (g0 + lane < cnt) {
+                const float4 b = s_box[g0 + lane];
+                hit = b.x < wx2 && b.z > wx1 && b.y < wy2 && b.w > wy1;
             }
-            const float mx = fmaxf(fmaxf(dl, dt), fmaxf(dr, db));
-            const bool cared = mx >= lo && mx <= hi;                                             // :181-185
-            const float area = s_area[k];
-            if (inside && cared && area < best_area) {                                           // :187-193
-                best_area = area;
-                best = c0 + k;
+            unsigned hits = __ballot_sync(PAA_FULL, hit);
+            while (hits) {
+                const int k = g0 + __ffs(hits) - 1;
+                hits &= hits - 1;
+                const float4 b = s_box[k];
+                const float dl = __fsub_rn(x, b.x), dt = __fsub_rn(y, b.y), dr = __fsub_rn(b.z, x), db = __fsub_rn(b.w, y);
+                bool inside;
+                if (radius > 0.0f) {
+                    // centre region of the GT clipped to the GT (fcos/loss.py:71-103)
+                    const float cx = __fdiv_rn(__fadd_rn(b.x, b.z), 2.0f), cy = __fdiv_rn(__fadd_rn(b.y, b.w), 2.0f);
+                    const float xmin = __fsub_rn(cx, radius), ymin = __fsub_rn(cy, radius);
+                    const float xmax = __fadd_rn(cx, radius), ymax = __fadd_rn(cy, radius);
+                    const float rx1 = xmin > b.x ? xmin : b.x, ry1 = ymin > b.y ? ymin : b.y;
+                    const float rx2 = xmax > b.z ? b.z : xmax, ry2 = ymax > b.w ? b.w : ymax;
+                    const float m = fminf(fminf(__fsub_rn(x, rx1), __fsub_rn(y, ry1)),
+                                          fminf(__fsub_rn(rx2, x), __fsub_rn(ry2, y)));
+                    inside = m > 0.0f && !none_inside;
+                } else {
+                    inside = fminf(fminf(dl, dt), fminf(dr, db)) > 0.0f;                       // :178-179
+                }
+                const float mx = fmaxf(fmaxf(dl, dt), fmaxf(dr, db));
+                const bool cared = mx >= lo && mx <= hi;                                         // :181-185
+                const float area = s_area[k];
+                if (valid && inside && cared && area < best_area) {                              // :187-193
+                    best_area = area;
+                    best = c0 + k;
+                }
             }
         }
     }
@@ -100,7 +115,6 @@ fcos_assign_kernel(const Geometry geo, const GtOffsets go, const float* __restri
     }
     npos = warp_sum(npos);
     sctr = warp_sum(sctr);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (lane == 0) {
         s_part[warp][0] = npos;
         s_part[warp][1] = sctr;

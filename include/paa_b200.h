@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define PAA_ABI_VERSION 5
+#define PAA_ABI_VERSION 6
 #define PAA_MAX_LEVELS 8
 #define PAA_MAX_IMAGES 256      /* images per call (per rank) */
 #define PAA_MAX_CANDIDATES 128  /* num_levels * topk must not exceed this */
@@ -134,7 +134,8 @@ typedef struct PaaLossArgs {
     float fcos_center_radius;     /* cfg.MODEL.FCOS.CENTER_SAMPLING_RADIUS (0 = every location inside the GT) */
     int32_t fcos_iou_loss_type;   /* PAA_IOU_LOSS_IOU / _LINEAR / _GIOU (cfg.MODEL.FCOS.IOU_LOSS_TYPE) */
     int32_t fcos_norm_reg_targets;/* cfg.MODEL.FCOS.NORM_REG_TARGETS: targets divided by the level's stride */
-    int32_t reserved3;
+    /* PAA_LOSS_ATSS only: cfg.MODEL.ATSS.POSITIVE_TYPE (atss/loss.py:88-229) */
+    int32_t atss_positive_type;   /* PAA_ATSS_POSITIVE_ATSS / _SSC / _IOU */
 } PaaLossArgs;
 
 typedef struct PaaPostArgs {
@@ -177,6 +178,10 @@ typedef struct PaaPostArgs {
 #define PAA_LOSS_ATSS 1
 #define PAA_LOSS_RETINANET 2
 #define PAA_LOSS_FCOS 3
+#define PAA_ATSS_POSITIVE_ATSS 0   /* topk nearest anchors per level, IoU threshold mean + std (the default) */
+#define PAA_ATSS_POSITIVE_SSC  1   /* FCOS's rule on the anchor centres: inside by > 0.01, size range, min area */
+#define PAA_ATSS_POSITIVE_IOU  2   /* Matcher(iou_threshold, bg_iou_threshold) labels; positives whose centre is not
+                                      inside their GT, and anchors between the thresholds, are ignored (-1) */
 #define PAA_IOU_LOSS_IOU    0
 #define PAA_IOU_LOSS_LINEAR 1
 #define PAA_IOU_LOSS_GIOU   2
@@ -225,7 +230,9 @@ int paa_sigmoid_focal_loss_backward(const float* logits, const int32_t* targets,
  * level the `topk` anchors nearest to the GT centre, IoU threshold = mean + std of their IoUs, centre inside
  * the GT, conflicts to the larger IoU.  Same arguments / workspace / normalisers protocol as paa_assign
  * (normalisers = {num_pos, sum of centerness targets}); follow with paa_loss and loss_flavour = PAA_LOSS_ATSS.
- * dbg_cand_idx receives the candidates (level-major, nearest first), dbg_gmm[g*8] the GT's IoU threshold. */
+ * dbg_cand_idx receives the candidates (level-major, nearest first), dbg_gmm[g*8] the GT's IoU threshold.
+ * atss_positive_type selects the reference's other two rules instead (no candidates then): _SSC needs at most five
+ * levels, _IOU reads iou_threshold / bg_iou_threshold (cfg.MODEL.ATSS.FG_IOU_THRESHOLD / BG_IOU_THRESHOLD). */
 int paa_atss_assign(const PaaLossArgs* args, void* stream);
 
 /* RetinaNet anchor labelling (rpn/loss.py:41-88 as used by rpn/retinanet/loss.py:45-56) in place of paa_assign:

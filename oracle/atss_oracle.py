@@ -19,7 +19,8 @@ NEG = -100000000.0
 
 
 def default_params(**kw):
-    p = dict(gamma=2.0, alpha=0.25, topk=9, reg_loss_weight=2.0)
+    p = dict(gamma=2.0, alpha=0.25, topk=9, reg_loss_weight=2.0, positive_type="ATSS", fg_iou_threshold=0.5,
+             bg_iou_threshold=0.4)
     p.update(kw)
     return SimpleNamespace(**p)
 
@@ -60,6 +61,55 @@ def assign_image(gt_boxes, gt_labels, anchors_per_level, topk):
     return labels, arg, cand, thr, cand_iou
 
 
+INF = 100000000
+SIZE_RANGES = ((-1, 64), (64, 128), (128, 256), (256, 512), (512, INF))
+
+
+def assign_image_ssc(gt_boxes, gt_labels, anchors_per_level):
+    """POSITIVE_TYPE 'SSC' (atss/loss.py:89-128): FCOS's rule on the anchor centres -- inside the GT by more than
+    0.01, max(l, t, r, b) in the level's size range, smallest area wins (first on ties)."""
+    anchors = torch.cat(list(anchors_per_level), dim=0)
+    sizes = torch.cat([torch.tensor(SIZE_RANGES[l], dtype=torch.float32)[None].expand(len(a), -1)
+                       for l, a in enumerate(anchors_per_level)], dim=0)
+    xs = (anchors[:, 2] + anchors[:, 0]) / 2.0
+    ys = (anchors[:, 3] + anchors[:, 1]) / 2.0
+    area = P.area_plus1(gt_boxes)
+    l = xs[:, None] - gt_boxes[:, 0][None]
+    t = ys[:, None] - gt_boxes[:, 1][None]
+    r = gt_boxes[:, 2][None] - xs[:, None]
+    b = gt_boxes[:, 3][None] - ys[:, None]
+    reg = torch.stack([l, t, r, b], dim=2)
+    inside = reg.min(dim=2)[0] > 0.01
+    mx = reg.max(dim=2)[0]
+    cared = (mx >= sizes[:, [0]]) & (mx <= sizes[:, [1]])
+    a = area[None].repeat(len(anchors), 1)
+    a[inside == 0] = INF
+    a[cared == 0] = INF
+    amin, arg = a.min(dim=1)
+    labels = gt_labels[arg].clone()
+    labels[amin == INF] = 0
+    return labels, arg
+
+
+def assign_image_iou(gt_boxes, gt_labels, anchors_per_level, high, low):
+    """POSITIVE_TYPE 'IoU' (atss/loss.py:199-226): Matcher(high, low, allow_low_quality_matches) labels (-1 between
+    the thresholds), then positives whose centre is not inside the matched GT by more than 0.01 become -1 too."""
+    from oracle import retinanet_oracle as R
+    anchors = torch.cat(list(anchors_per_level), dim=0)
+    m = R.match_anchors(P.iou_matrix(gt_boxes, anchors), high, low)
+    mc = m.clamp(min=0)
+    labels = gt_labels[mc].to(torch.float32)
+    labels[m == R.BELOW_LOW_THRESHOLD] = 0
+    labels[m == R.BETWEEN_THRESHOLDS] = -1
+    g = gt_boxes[mc]
+    pos = torch.nonzero(labels > 0).squeeze(1)
+    cx = (anchors[pos, 2] + anchors[pos, 0]) / 2.0
+    cy = (anchors[pos, 3] + anchors[pos, 1]) / 2.0
+    inside = torch.stack([cx - g[pos, 0], cy - g[pos, 1], g[pos, 2] - cx, g[pos, 3] - cy], dim=1).min(dim=1)[0] > 0.01
+    labels[pos[inside == 0]] = -1
+    return labels.long(), mc, m
+
+
 def centerness_targets(reg_targets, anchors):
     """loss.py:233-245."""
     g = P.decode(reg_targets, anchors)
@@ -77,7 +127,15 @@ def assign(gt_boxes, gt_labels, anchors_per_level, params=None):
     N = len(gt_boxes)
     labels, matched, cands, thrs, reg_t = [], [], [], [], []
     for i in range(N):
-        lab, arg, cand, thr, _ = assign_image(gt_boxes[i], gt_labels[i], anchors_per_level, prm.topk)
+        if prm.positive_type == "SSC":
+            lab, arg = assign_image_ssc(gt_boxes[i], gt_labels[i], anchors_per_level)
+            cand, thr = None, None
+        elif prm.positive_type == "IoU":
+            lab, arg, _ = assign_image_iou(gt_boxes[i], gt_labels[i], anchors_per_level, prm.fg_iou_threshold,
+                                           prm.bg_iou_threshold)
+            cand, thr = None, None
+        else:
+            lab, arg, cand, thr, _ = assign_image(gt_boxes[i], gt_labels[i], anchors_per_level, prm.topk)
         labels.append(lab)
         matched.append(arg)
         cands.append(cand)

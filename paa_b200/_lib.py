@@ -14,7 +14,7 @@ MAX_IMAGES = 256
 MAX_PEERS = 16
 PEER_BUFFER_DOUBLES = 256
 MAX_CANDIDATES = 128
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 ERR_BAD_ARGUMENT, ERR_WORKSPACE, ERR_EMPTY_TARGET, ERR_UNSUPPORTED = -1, -2, -3, -4
 
@@ -47,7 +47,7 @@ class PaaLossArgs(C.Structure):
                 ("box_code_weights", C.c_float * 4), ("smooth_l1_beta", C.c_float),
                 ("reg_norm_weight", C.c_float), ("fcos_strides", C.c_float * MAX_LEVELS),
                 ("fcos_center_radius", C.c_float), ("fcos_iou_loss_type", C.c_int32),
-                ("fcos_norm_reg_targets", C.c_int32), ("reserved3", C.c_int32)]
+                ("fcos_norm_reg_targets", C.c_int32), ("atss_positive_type", C.c_int32)]
 
 
 class PaaPostArgs(C.Structure):
@@ -68,6 +68,7 @@ class PaaPostArgs(C.Structure):
 
 DECODE_ATSS_BOX, DECODE_LEGACY, DECODE_LTRB = 0, 1, 2
 LOSS_PAA, LOSS_ATSS, LOSS_RETINANET, LOSS_FCOS = 0, 1, 2, 3
+ATSS_POSITIVE_TYPES = {"ATSS": 0, "SSC": 1, "IoU": 2}
 IOU_LOSS_TYPES = {"iou": 0, "linear_iou": 1, "giou": 2}
 
 

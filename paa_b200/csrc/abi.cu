@@ -185,6 +185,22 @@ static int plan_loss(const PaaLossArgs* a, LossPlan* p) {
     for (int k = 0; k < 4; ++k) p->sc.code_w[k] = a->box_code_weights[k];
     p->sc.beta = a->smooth_l1_beta;
     p->sc.reg_norm_weight = a->reg_norm_weight;
+    p->sc.atss_type = a->loss_flavour == PAA_LOSS_ATSS ? a->atss_positive_type : PAA_ATSS_POSITIVE_ATSS;
+    if (a->loss_flavour == PAA_LOSS_ATSS) {
+        if (a->atss_positive_type < PAA_ATSS_POSITIVE_ATSS || a->atss_positive_type > PAA_ATSS_POSITIVE_IOU) {
+            set_error("POSITIVE_TYPE %d not implemented", a->atss_positive_type);      // atss/loss.py:227-228
+            return PAA_ERR_UNSUPPORTED;
+        }
+        if (a->atss_positive_type == PAA_ATSS_POSITIVE_SSC && a->num_levels > 5) {
+            set_error("ATSS POSITIVE_TYPE 'SSC' lists five size ranges (atss/loss.py:89), got %d levels", a->num_levels);
+            return PAA_ERR_BAD_ARGUMENT;
+        }
+        if (a->atss_positive_type == PAA_ATSS_POSITIVE_IOU && !(a->bg_iou_threshold <= a->iou_threshold)) {
+            set_error("ATSS POSITIVE_TYPE 'IoU': bg_iou_threshold=%g > iou_threshold=%g", a->bg_iou_threshold,
+                      a->iou_threshold);
+            return PAA_ERR_BAD_ARGUMENT;
+        }
+    }
     p->sc.fcos_iou_type = a->fcos_iou_loss_type;
     p->sc.fcos_norm = a->fcos_norm_reg_targets;
     for (int l = 0; l < PAA_MAX_LEVELS; ++l) {
@@ -310,19 +326,34 @@ int paa_atss_assign(const PaaLossArgs* args, void* stream_) {
     LossPlan p;
     int rc = plan_loss(args, &p);
     if (rc) return rc;
-    for (int l = 0; l < p.geo.num_levels; ++l)
-        if (p.geo.lv[l].n_anchor < args->topk) {
-            // torch.topk(k) on fewer than k anchors: "selected index k out of range" (atss/loss.py:159)
-            set_error("selected index k out of range: level %d has %d anchors, TOPK is %d", l, p.geo.lv[l].n_anchor,
-                      args->topk);
-            return PAA_ERR_UNSUPPORTED;
-        }
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    PAA_CUDA_CHECK(cudaMemsetAsync(args->workspace, 0, p.ws.zero_bytes, stream));
-    PAA_CUDA_CHECK(cudaMemsetAsync(p.ws.best, 0, sizeof(uint2) * (size_t)args->num_images * p.geo.A, stream));
-    if ((rc = launch_atss_assign(p.geo, p.go, p.sumG, args->gt_boxes, args->gt_labels, p.sc, p.ws, args->normalisers,
-                                 p.px, p.dbg, stream)))
-        return rc;
+    if (p.sc.atss_type == PAA_ATSS_POSITIVE_SSC) {
+        rc = launch_fcos_assign(p.geo, p.go, args->gt_boxes, args->gt_labels, p.sc, p.ws, args->normalisers, p.px,
+                                p.dbg, stream, /*ssc=*/true);
+    } else if (p.sc.atss_type == PAA_ATSS_POSITIVE_IOU) {
+        PAA_CUDA_CHECK(cudaMemsetAsync(args->workspace, 0, p.ws.zero_bytes, stream));
+        const int hl = first_heavy_level(p.geo);
+        if (hl < p.geo.num_levels && gt_parts(p.go, args->num_images) > 1) {
+            const size_t a0 = (size_t)p.geo.lv[hl].a_off, n_heavy = (size_t)p.geo.A - a0;
+            PAA_CUDA_CHECK(cudaMemset2DAsync(reinterpret_cast<char*>(p.ws.best) + a0 * 8, (size_t)p.geo.A * 8, 0,
+                                             n_heavy * 8, (size_t)args->num_images, stream));
+        }
+        rc = launch_retinanet_assign(p.geo, p.go, args->gt_boxes, args->gt_labels, p.sc, p.ws, args->normalisers,
+                                     p.dbg, stream, /*atss_iou=*/true, &p.px);
+    } else {
+        for (int l = 0; l < p.geo.num_levels; ++l)
+            if (p.geo.lv[l].n_anchor < args->topk) {
+                // torch.topk(k) on fewer than k anchors: "selected index k out of range" (atss/loss.py:159)
+                set_error("selected index k out of range: level %d has %d anchors, TOPK is %d", l,
+                          p.geo.lv[l].n_anchor, args->topk);
+                return PAA_ERR_UNSUPPORTED;
+            }
+        PAA_CUDA_CHECK(cudaMemsetAsync(args->workspace, 0, p.ws.zero_bytes, stream));
+        PAA_CUDA_CHECK(cudaMemsetAsync(p.ws.best, 0, sizeof(uint2) * (size_t)args->num_images * p.geo.A, stream));
+        rc = launch_atss_assign(p.geo, p.go, p.sumG, args->gt_boxes, args->gt_labels, p.sc, p.ws, args->normalisers,
+                                p.px, p.dbg, stream);
+    }
+    if (rc) return rc;
     if (args->dbg_paa_labels)
         PAA_CUDA_CHECK(cudaMemcpyAsync(args->dbg_paa_labels, p.ws.paa_label,
                                        sizeof(int) * (size_t)args->num_images * p.geo.A,

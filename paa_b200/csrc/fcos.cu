@@ -17,7 +17,7 @@ constexpr float kFcosInf = 100000000.0f;       // fcos/loss.py:19
 __global__ void __launch_bounds__(PAA_TILE)
 fcos_assign_kernel(const Geometry geo, const GtOffsets go, const float* __restrict__ gt_boxes,
                    const int64_t* __restrict__ gt_labels, const LossScalars sc, int* __restrict__ matched,
-                   int* __restrict__ label_out, double* __restrict__ tile_part, const LossDebug dbg) {
+                   int* __restrict__ label_out, double* __restrict__ tile_part, const LossDebug dbg, bool ssc) {
     __shared__ float4 s_box[PAA_TILE];
     __shared__ float s_area[PAA_TILE];
     __shared__ double s_part[PAA_TILE / PAA_WARP][2];
@@ -32,13 +32,18 @@ fcos_assign_kernel(const Geometry geo, const GtOffsets go, const float* __restri
     const int G = go.v[n + 1] - gbase;
     // object_sizes_of_interest, fcos/loss.py:106-112
     const float lo = l == 0 ? -1.0f : (float)(32 << l), hi = l >= 4 ? kFcosInf : (float)(64 << l);
-    const float radius = sc.fcos_radius[l];
+    const float radius = ssc ? 0.0f : sc.fcos_radius[l];
+    const float margin = ssc ? 0.01f : 0.0f;                 // atss/loss.py:116 vs fcos/loss.py:179
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float x = 0.f, y = 0.f;
     if (valid) {
         const float4 p = ldg4(lv.anchors + (size_t)n * geo.anchor_image_stride + (size_t)i * 4);
         x = p.x;
         y = p.y;
+        if (ssc) {                                           // anchor centres, atss/loss.py:97-98
+            x = __fdiv_rn(__fadd_rn(p.z, p.x), 2.0f);
+            y = __fdiv_rn(__fadd_rn(p.w, p.y), 2.0f);
+        }
     }
     const float wx1 = warp_min(valid ? x : INFINITY), wx2 = warp_max(valid ? x : -INFINITY);
     const float wy1 = warp_min(valid ? y : INFINITY), wy2 = warp_max(valid ? y : -INFINITY);
@@ -86,7 +91,7 @@ fcos_assign_kernel(const Geometry geo, const GtOffsets go, const float* __restri
                                           fminf(__fsub_rn(rx2, x), __fsub_rn(ry2, y)));
                     inside = m > 0.0f && !none_inside;
                 } else {
-                    inside = fminf(fminf(dl, dt), fminf(dr, db)) > 0.0f;                       // :178-179
+                    inside = fminf(fminf(dl, dt), fminf(dr, db)) > margin;                     // :178-179
                 }
                 const float mx = fmaxf(fmaxf(dl, dt), fmaxf(dr, db));
                 const bool cared = mx >= lo && mx <= hi;                                         // :181-185
@@ -110,7 +115,12 @@ fcos_assign_kernel(const Geometry geo, const GtOffsets go, const float* __restri
         if (label > 0) {
             const float4 g = ldg4(gt_boxes + (size_t)(gbase + best) * 4);
             npos = 1.0;
-            sctr = (double)fcos_centerness(fcos_ltrb(x, y, g, sc.fcos_norm != 0, sc.fcos_stride[l]));
+            if (ssc) {
+                const AnchorFrame f = anchor_frame(ldg4(lv.anchors + (size_t)n * geo.anchor_image_stride + (size_t)i * 4));
+                sctr = (double)centerness_target(decode_box(encode_box(g, f), f), f);      // atss/loss.py:233-245
+            } else {
+                sctr = (double)fcos_centerness(fcos_ltrb(x, y, g, sc.fcos_norm != 0, sc.fcos_stride[l]));
+            }
         }
     }
     npos = warp_sum(npos);
@@ -130,11 +140,11 @@ fcos_assign_kernel(const Geometry geo, const GtOffsets go, const float* __restri
 
 int launch_fcos_assign(const Geometry& geo, const GtOffsets& go, const float* gt_boxes, const int64_t* gt_labels,
                        const LossScalars& sc, const LossWorkspace& ws, double* normalisers, const PeerExchange& px,
-                       const LossDebug& dbg, cudaStream_t stream) {
+                       const LossDebug& dbg, cudaStream_t stream, bool ssc) {
     const int tiles = geo.num_images * geo.tiles_per_image;
     double* tile_part = ws.block_part;       // positive_terms_kernel reuses the slots after the fold
     fcos_assign_kernel<<<tiles, PAA_TILE, 0, stream>>>(geo, go, gt_boxes, gt_labels, sc, ws.matched, ws.paa_label,
-                                                       tile_part, dbg);
+                                                       tile_part, dbg, ssc);
     PAA_LAUNCH_CHECK("fcos_assign_kernel");
     return launch_fold_norm(tile_part, tiles, ws.local_norm, normalisers, px, stream);
 }

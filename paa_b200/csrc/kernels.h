@@ -15,6 +15,7 @@ struct LossScalars {
     // PAA_LOSS_FCOS: per-level stride and centre-sampling radius in pixels (0 = off), IoU loss type, target scaling
     float fcos_stride[PAA_MAX_LEVELS], fcos_radius[PAA_MAX_LEVELS];
     int fcos_iou_type, fcos_norm;
+    int atss_type;     // PAA_ATSS_POSITIVE_*
     int seg_cap;       // usable entries of a (GT, level) candidate pool, <= kSegCap (PAA_SEG_CAP shrinks it for tests)
 };
 
@@ -60,13 +61,16 @@ int launch_norm_wait(const PeerExchange& px, double* normalisers, cudaStream_t s
 int launch_fold_norm(const double* tile_part, int tiles, double* local_norm, double* normalisers,
                      const PeerExchange& px, cudaStream_t stream);
 // fcos.cu
+// `ssc`: ATSS POSITIVE_TYPE 'SSC' -- the same rule on anchor centres with a 0.01 margin, ATSS centerness sums
 int launch_fcos_assign(const Geometry& geo, const GtOffsets& go, const float* gt_boxes, const int64_t* gt_labels,
                        const LossScalars& sc, const LossWorkspace& ws, double* normalisers, const PeerExchange& px,
-                       const LossDebug& dbg, cudaStream_t stream);
+                       const LossDebug& dbg, cudaStream_t stream, bool ssc = false);
 // retina.cu
+// `atss_iou`: ATSS POSITIVE_TYPE 'IoU' -- additionally ignores positives whose centre is outside their GT, sums
+// the centerness targets and publishes both normalisers through `px`
 int launch_retinanet_assign(const Geometry& geo, const GtOffsets& go, const float* gt_boxes, const int64_t* gt_labels,
                             const LossScalars& sc, const LossWorkspace& ws, double* normalisers, const LossDebug& dbg,
-                            cudaStream_t stream);
+                            cudaStream_t stream, bool atss_iou = false, const PeerExchange* px = nullptr);
 
 // loss.cu
 int loss_grid_blocks(int num_images, int tiles_per_image);

@@ -627,9 +627,11 @@ int launch_final_loss(const Geometry& geo, const GtOffsets& go, const float* gt_
         plan.dst[l] = nullptr;
         plan.count[l] = 0;
     }
-    // RetinaNet: the labelling kernel left one bit per ignored anchor (retina.cu); the bulk pass skips those
+    // RetinaNet / ATSS 'IoU': the labelling kernel left one bit per ignored anchor (retina.cu); the bulk pass skips those
     // elements in stream, which saves positive_terms_kernel C scattered reads and writes per ignored anchor.
-    bool bulk_ignores = sc.flavour == PAA_LOSS_RETINANET && geo.C >= 2;
+    const bool has_ignored = sc.flavour == PAA_LOSS_RETINANET ||
+                             (sc.flavour == PAA_LOSS_ATSS && sc.atss_type == PAA_ATSS_POSITIVE_IOU);
+    bool bulk_ignores = has_ignored && geo.C >= 2;
     if (getenv("PAA_RETINA_PATCH")) bulk_ignores = false;      // test hook: force the per-anchor fallback
     for (int l = 0; l < geo.num_levels && bulk_ignores; ++l)
         if (plan.count[l] >= (1ull << 32) || geo.lv[l].hw < 2 || geo.lv[l].hw == 4) bulk_ignores = false;
@@ -690,7 +692,7 @@ int launch_final_loss(const Geometry& geo, const GtOffsets& go, const float* gt_
 #define PAA_POS(G, T)                                                                                        \
     positive_terms_kernel<G, T><<<tile_grid, PAA_TILE, 0, stream>>>(geo, go, gt_boxes, sc, ws.paa_label,     \
         ws.matched, normalisers, ws.local_norm, grad_losses, tile_part, tiles_total, tiles_per_block, zero_fill,  \
-        sc.flavour == PAA_LOSS_RETINANET && !bulk_ignores)
+        has_ignored && !bulk_ignores)
     if (write_grads) {
         if (g2) PAA_POS(true, true); else PAA_POS(true, false);
     } else {

@@ -25,14 +25,15 @@ retina_labels_kernel(const Geometry geo, const GtOffsets go, const float* __rest
                      const int64_t* __restrict__ gt_labels, const unsigned* __restrict__ gtmax,
                      const unsigned long long* __restrict__ best, const LossScalars sc,
                      int* __restrict__ matched, int* __restrict__ label_out, unsigned* __restrict__ ignore_bits,
-                     double* __restrict__ tile_part, const LossDebug dbg, int tiles_total, int tiles_per_block) {
+                     double* __restrict__ tile_part, const LossDebug dbg, int tiles_total, int tiles_per_block,
+                     bool atss_iou) {
     __shared__ float4 s_box[PAA_TILE];
     __shared__ float s_max[PAA_TILE];
     __shared__ int s_nlq;
-    __shared__ double s_part[PAA_TILE / PAA_WARP];
+    __shared__ double s_part[PAA_TILE / PAA_WARP][2];
     const float high = sc.iou_threshold, low = sc.bg_threshold;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double npos = 0.0;
+    double npos = 0.0, sctr = 0.0;
     int staged_image = -1, nlq = 0;
     bool overflow = false;        // more than PAA_TILE low-quality GTs: walk the whole GT list instead
 
@@ -114,6 +115,17 @@ retina_labels_kernel(const Geometry geo, const GtOffsets go, const float* __rest
         int label = 0;                                        // rpn/loss.py:68-69
         if (m >= 0) label = (int)gt_labels[gbase + m];        // generate_retinanet_labels, retinanet/loss.py:84-86
         else if (m == -2) label = -1;                         // rpn/loss.py:76-78
+        if (atss_iou && label > 0) {
+            // ATSS POSITIVE_TYPE 'IoU' (atss/loss.py:214-226): a positive whose centre is not inside its GT by more
+            // than 0.01 is ignored; the others contribute their centerness target to the second normaliser
+            const float4 a = ldg4(lv.anchors + (size_t)n * geo.anchor_image_stride + (size_t)i * 4);
+            const float4 g = ldg4(gt_boxes + (size_t)(gbase + m) * 4);
+            const AnchorFrame f = anchor_frame(a);
+            const float in = fminf(fminf(__fsub_rn(f.cx, g.x), __fsub_rn(f.cy, g.y)),
+                                   fminf(__fsub_rn(g.z, f.cx), __fsub_rn(g.w, f.cy)));
+            if (in > 0.01f) sctr += (double)centerness_target(decode_box(encode_box(g, f), f), f);
+            else label = -1;
+        }
         matched[flat] = m < 0 ? 0 : m;                        // target[matched_idxs.clamp(min=0)], rpn/loss.py:52
         label_out[flat] = label;
         if (label < 0) {
@@ -128,21 +140,24 @@ retina_labels_kernel(const Geometry geo, const GtOffsets go, const float* __rest
         npos += label > 0 ? 1.0 : 0.0;
     }
     npos = warp_sum(npos);
+    sctr = warp_sum(sctr);
     __syncthreads();
-    if (lane == 0) s_part[warp] = npos;
+    if (lane == 0) {
+        s_part[warp][0] = npos;
+        s_part[warp][1] = sctr;
+    }
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < 2) {
         double t = 0.0;
 #pragma unroll
-        for (int w = 0; w < PAA_TILE / PAA_WARP; ++w) t += s_part[w];
-        tile_part[(size_t)blockIdx.x * 2] = t;
-        tile_part[(size_t)blockIdx.x * 2 + 1] = 0.0;
+        for (int w = 0; w < PAA_TILE / PAA_WARP; ++w) t += s_part[w][threadIdx.x];
+        tile_part[(size_t)blockIdx.x * 2 + threadIdx.x] = t;
     }
 }
 
 int launch_retinanet_assign(const Geometry& geo, const GtOffsets& go, const float* gt_boxes, const int64_t* gt_labels,
                             const LossScalars& sc, const LossWorkspace& ws, double* normalisers, const LossDebug& dbg,
-                            cudaStream_t stream) {
+                            cudaStream_t stream, bool atss_iou, const PeerExchange* px) {
     int rc = launch_assign_pass1(geo, go, gt_boxes, sc, ws, stream, /*with_class_sums=*/false);
     if (rc) return rc;
     const int tiles = geo.num_images * geo.tiles_per_image;
@@ -155,11 +170,11 @@ int launch_retinanet_assign(const Geometry& geo, const GtOffsets& go, const floa
     retina_labels_kernel<<<grid, PAA_TILE, 0, stream>>>(geo, go, gt_boxes, gt_labels, ws.gtmax,
                                                         reinterpret_cast<const unsigned long long*>(ws.best), sc,
                                                         ws.matched, ws.paa_label, ignore_bits, tile_part, dbg, tiles,
-                                                        tiles_per_block);
+                                                        tiles_per_block, atss_iou);
     PAA_LAUNCH_CHECK("retina_labels_kernel");
     PeerExchange none;
     memset(&none, 0, sizeof(none));
-    return launch_fold_norm(tile_part, grid, ws.local_norm, normalisers, none, stream);
+    return launch_fold_norm(tile_part, grid, ws.local_norm, normalisers, px ? *px : none, stream);
 }
 
 }  // namespace paa

@@ -255,6 +255,9 @@ class PAALossComputation(object):
             for k in range(4):
                 args.box_code_weights[k] = self.box_code_weights[k]
             args.smooth_l1_beta, args.reg_norm_weight = self.bbox_reg_beta, self.regress_norm
+        if self._flavour == _lib.LOSS_ATSS:
+            args.atss_positive_type = _lib.ATSS_POSITIVE_TYPES[self.positive_type]
+            args.bg_iou_threshold = self.bg_iou_threshold
         if self._flavour == _lib.LOSS_FCOS:
             for l, stride in enumerate(self.fpn_strides[:L]):
                 args.fcos_strides[l] = float(stride)
@@ -366,21 +369,25 @@ def make_paa_loss_evaluator(cfg, box_coder):
 
 
 class ATSSLossComputation(PAALossComputation):
-    """Drop-in for paa_core.modeling.rpn.atss.loss.ATSSLossComputation with POSITIVE_TYPE 'ATSS' (atss/loss.py:
-    27-279).  Anchors are assigned by the ATSS rule (`paa_atss_assign`), the losses come from the
+    """Drop-in for paa_core.modeling.rpn.atss.loss.ATSSLossComputation (atss/loss.py:27-279) with
+    all three POSITIVE_TYPEs: 'ATSS' (the default rule), 'SSC' (FCOS's rule on anchor centres) and 'IoU' (Matcher
+    labels, ignored anchors).  Anchors are assigned on the device (`paa_atss_assign`), the losses come from the
     same streaming pass as PAA's with the centerness targets as regression weights / BCE targets.  Returns
     ``(cls_loss, reg_loss * REG_LOSS_WEIGHT, centerness_loss)`` like the reference."""
 
     def __init__(self, cfg, box_coder):
         atss = cfg.MODEL.ATSS
-        if getattr(atss, "POSITIVE_TYPE", "ATSS") != "ATSS":
-            raise NotImplementedError("POSITIVE_TYPE %r: only 'ATSS' is supported" % (atss.POSITIVE_TYPE,))
+        self.positive_type = getattr(atss, "POSITIVE_TYPE", "ATSS")
+        if self.positive_type not in _lib.ATSS_POSITIVE_TYPES:
+            raise NotImplementedError                                  # atss/loss.py:227-228
         if coder_regression_type(box_coder) != "BOX":
             raise NotImplementedError("only the 'BOX' BoxCoder regression type is supported")
         self.cfg = cfg
         self.gamma = scalar(atss.LOSS_GAMMA)
         self.alpha = scalar(atss.LOSS_ALPHA)
-        self.iou_threshold = 0.0                     # unused by the ATSS rule
+        # Matcher(FG, BG, True) of atss/loss.py:33: read by POSITIVE_TYPE 'IoU' only
+        self.iou_threshold = float(getattr(atss, "FG_IOU_THRESHOLD", 0.5))
+        self.bg_iou_threshold = float(getattr(atss, "BG_IOU_THRESHOLD", 0.4))
         self.topk = int(atss.TOPK)
         self.box_coder = box_coder
         self.reg_loss_type = "iou"

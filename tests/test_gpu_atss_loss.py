@@ -17,9 +17,10 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-4
 
 
-def _cfg():
-    return NS(MODEL=NS(ATSS=NS(LOSS_GAMMA=2.0, LOSS_ALPHA=0.25, TOPK=9, REG_LOSS_WEIGHT=2.0, POSITIVE_TYPE="ATSS",
-                               REGRESSION_TYPE="BOX")))
+def _cfg(positive_type="ATSS", fg=0.5, bg=0.4):
+    return NS(MODEL=NS(ATSS=NS(LOSS_GAMMA=2.0, LOSS_ALPHA=0.25, TOPK=9, REG_LOSS_WEIGHT=2.0,
+                               POSITIVE_TYPE=positive_type, REGRESSION_TYPE="BOX", FG_IOU_THRESHOLD=fg,
+                               BG_IOU_THRESHOLD=bg)))
 
 
 def _tie_exempt(b, asg, cand_gpu, off):
@@ -84,6 +85,50 @@ def test_atss_loss_against_oracle(seed, hw, gt):
                                    rtol=1e-3, atol=1e-7)
         np.testing.assert_allclose(flat_levels([t.grad for t in ctr]), flat_levels(ref_grads.centerness),
                                    rtol=1e-3, atol=1e-7)
+
+
+@pytest.mark.parametrize("seed,hw,gt,ptype,fg,bg", [
+    (65, (384, 512), (2, 7), "SSC", 0.5, 0.4),
+    (66, (800, 1333), (5, 40), "SSC", 0.5, 0.4),
+    (67, (384, 512), (2, 7), "IoU", 0.5, 0.4),
+    (68, (800, 1333), (5, 40), "IoU", 0.3, 0.2),
+    (69, (384, 512), (130, 150), "IoU", 0.5, 0.4),
+])
+def test_atss_other_positive_types_against_oracle(seed, hw, gt, ptype, fg, bg):
+    """POSITIVE_TYPE 'SSC' (FCOS's rule on anchor centres) and 'IoU' (Matcher labels; anchors between the thresholds
+    and positives whose centre is outside their GT are ignored): labels bit-exact, the rest to 1e-4."""
+    import paa_b200
+    b = synthetic.make_batch(seed=seed, num_images=2, image_hw=hw, gt_per_image=gt)
+    prm = atss_oracle.default_params(positive_type=ptype, fg_iou_threshold=fg, bg_iou_threshold=bg)
+    ref_losses, ref_grads, asg = atss_oracle.assign_and_loss(b.box_cls, b.box_regression, b.iou_pred, b.gt_boxes,
+                                                             b.gt_labels, b.anchors, prm)
+    assert asg.num_pos > 0 and (ptype != "IoU" or (asg.labels == -1).any())
+    cfg = _cfg(ptype, fg, bg)
+    ev = paa_b200.make_atss_loss_evaluator(cfg, paa_b200.BoxCoder(cfg))
+    ev.debug = True
+    cls, reg, ctr, targets, anchors = to_device_inputs(b, requires_grad=True)
+    losses = ev(cls, reg, ctr, targets, anchors)
+    sum(losses).backward()
+    torch.cuda.synchronize()
+    d = ev.last_debug
+    want = asg.labels.numpy()
+    assert np.array_equal(d["paa_labels"].cpu().numpy(), want)
+    pos = want > 0
+    assert np.array_equal(d["matched_idx"].cpu().numpy()[pos], asg.matched.numpy()[pos])
+    np.testing.assert_allclose(d["normalisers"].cpu().numpy(), [asg.num_pos, asg.sum_centerness], rtol=1e-6)
+    np.testing.assert_allclose([float(x) for x in losses], [float(x) for x in ref_losses], rtol=RTOL)
+    np.testing.assert_allclose(flat_levels([t.grad for t in cls]), flat_levels(ref_grads.box_cls), rtol=RTOL, atol=1e-9)
+    np.testing.assert_allclose(flat_levels([t.grad for t in reg]), flat_levels(ref_grads.box_regression),
+                               rtol=1e-3, atol=1e-7)
+    np.testing.assert_allclose(flat_levels([t.grad for t in ctr]), flat_levels(ref_grads.centerness),
+                               rtol=1e-3, atol=1e-7)
+
+
+def test_atss_unknown_positive_type_is_rejected():
+    import paa_b200
+    cfg = _cfg("TOPK")
+    with pytest.raises(NotImplementedError):
+        paa_b200.make_atss_loss_evaluator(cfg, paa_b200.BoxCoder(cfg))
 
 
 def test_atss_level_with_fewer_anchors_than_topk_is_rejected():

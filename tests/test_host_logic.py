@@ -1,0 +1,81 @@
+"""CPU: the host mirrors' argument handling -- constructor validation of the four loss evaluators, head / anchor
+validation (gather_levels), and the refusal to run on CPU tensors (there is no CPU path).  No kernel is launched."""
+from types import SimpleNamespace as NS
+
+import pytest
+import torch
+
+import paa_b200
+from paa_b200 import loss as L
+from paa_b200 import synthetic
+
+
+def _atss_cfg(**kw):
+    a = dict(LOSS_GAMMA=2.0, LOSS_ALPHA=0.25, TOPK=9, REG_LOSS_WEIGHT=2.0, POSITIVE_TYPE="ATSS", REGRESSION_TYPE="BOX")
+    a.update(kw)
+    return NS(MODEL=NS(ATSS=NS(**a)))
+
+
+def test_paa_evaluator_rejects_what_the_reference_cannot_run():
+    cfg = paa_b200.default_cfg(REG_LOSS_TYPE="smoothl1")          # dead code in the reference (loss.py:246-251)
+    with pytest.raises(NotImplementedError):
+        paa_b200.make_paa_loss_evaluator(cfg, paa_b200.BoxCoder(cfg))
+    cfg = paa_b200.default_cfg()
+    cfg.MODEL.ATSS.REGRESSION_TYPE = "POINT"
+    with pytest.raises(NotImplementedError):
+        paa_b200.make_paa_loss_evaluator(cfg, paa_b200.BoxCoder(cfg))
+
+
+def test_atss_positive_types():
+    for ptype, code in (("ATSS", 0), ("SSC", 1), ("IoU", 2)):
+        cfg = _atss_cfg(POSITIVE_TYPE=ptype)
+        ev = paa_b200.make_atss_loss_evaluator(cfg, paa_b200.BoxCoder(cfg))
+        assert L._lib.ATSS_POSITIVE_TYPES[ev.positive_type] == code
+        assert (ev.iou_threshold, ev.bg_iou_threshold) == (0.5, 0.4)      # defaults.py FG / BG when the cfg omits them
+    with pytest.raises(NotImplementedError):                               # atss/loss.py:227-228
+        cfg = _atss_cfg(POSITIVE_TYPE="TOPK")
+        paa_b200.make_atss_loss_evaluator(cfg, paa_b200.BoxCoder(cfg))
+
+
+def test_retinanet_evaluator_mirrors_the_reference_constructor():
+    cfg = NS(MODEL=NS(RETINANET=NS(LOSS_GAMMA=(2.0,), LOSS_ALPHA=(0.25,), FG_IOU_THRESHOLD=0.5, BG_IOU_THRESHOLD=0.4,
+                                   BBOX_REG_BETA=0.11, BBOX_REG_WEIGHT=4.0)))
+    ev = paa_b200.make_retinanet_loss_evaluator(cfg, NS(weights=(10.0, 10.0, 5.0, 5.0)))
+    assert (ev.gamma, ev.alpha, ev.iou_threshold, ev.bg_iou_threshold) == (2.0, 0.25, 0.5, 0.4)
+    assert (ev.bbox_reg_beta, ev.regress_norm, ev.box_code_weights) == (0.11, 4.0, (10.0, 10.0, 5.0, 5.0))
+    assert ev.copied_fields == ["labels"] and ev.discard_cases == ["between_thresholds"]
+    matcher = NS(high_threshold=0.5, low_threshold=0.4, allow_low_quality_matches=False)
+    with pytest.raises(NotImplementedError):
+        L.RetinaNetLossComputation(matcher, NS(weights=(1.0, 1.0, 1.0, 1.0)), L.generate_retinanet_labels,
+                                   NS(gamma=2.0, alpha=0.25))
+    matcher.allow_low_quality_matches = True
+    with pytest.raises(NotImplementedError):
+        L.RetinaNetLossComputation(matcher, NS(weights=(1.0, 1.0, 1.0, 1.0)), lambda m: m, NS(gamma=2.0, alpha=0.25))
+
+
+def test_fcos_evaluator_config():
+    f = dict(LOSS_GAMMA=2.0, LOSS_ALPHA=0.25, FPN_STRIDES=[8, 16, 32, 64, 128], CENTER_SAMPLING_RADIUS=1.5,
+             IOU_LOSS_TYPE="giou", NORM_REG_TARGETS=True)
+    ev = paa_b200.make_fcos_loss_evaluator(NS(MODEL=NS(FCOS=NS(**f))))
+    assert ev.center_sampling_radius == 1.5 and ev.norm_reg_targets and ev.iou_loss_type == "giou"
+    f["IOU_LOSS_TYPE"] = "diou"
+    with pytest.raises(NotImplementedError):                               # layers/iou_loss.py:43-44
+        paa_b200.make_fcos_loss_evaluator(NS(MODEL=NS(FCOS=NS(**f))))
+
+
+def test_there_is_no_cpu_path():
+    b = synthetic.make_batch(seed=5, num_images=1, image_hw=(128, 160), gt_per_image=2)
+    cls, reg, iou, targets, anchors = synthetic.to_device_inputs(b, device="cpu")
+    cfg = paa_b200.default_cfg()
+    ev = paa_b200.make_paa_loss_evaluator(cfg, paa_b200.BoxCoder(cfg))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        ev(cls, reg, iou, targets, anchors)
+
+
+def test_head_and_anchor_validation():
+    b = synthetic.make_batch(seed=6, num_images=2, image_hw=(128, 160), gt_per_image=2)
+    cls, reg, iou, targets, anchors = synthetic.to_device_inputs(b, device="cpu")
+    with pytest.raises(RuntimeError, match="same levels"):
+        L.gather_levels(cls, reg[:-1], iou, anchors)
+    with pytest.raises(RuntimeError, match="anchors lists"):
+        L.gather_levels(cls, reg, iou, anchors[:1])

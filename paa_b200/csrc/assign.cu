@@ -308,6 +308,7 @@ __global__ void __launch_bounds__(kPassThreads, 6)
 assign_pass1_kernel(const Geometry geo, const GtOffsets go, const Pass1Plan plan, float gamma,
                     const float* __restrict__ gt_boxes, unsigned* __restrict__ gtmax,
                     unsigned long long* __restrict__ best, float* __restrict__ negsum) {
+    pdl_launch_dependents();
     __shared__ Pass1Smem sm;
     // the first 2*min(sum_blocks, iou_blocks) blocks alternate between the jobs, the rest belong to the longer one
     const unsigned m = min(plan.sum_blocks, plan.iou_blocks);
@@ -422,6 +423,8 @@ match_score_kernel(const Geometry geo, const GtOffsets go, const float* __restri
                    int* __restrict__ matched, float* __restrict__ score, int* __restrict__ paa_label, uint4* __restrict__ tile_gtmask,
                    int* __restrict__ seg_count, unsigned long long* __restrict__ seg_pool,
                    const float* __restrict__ teacher_score, const LossDebug dbg) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ int s_lq[PAA_TILE];
     __shared__ int s_nlq;
     __shared__ unsigned s_mask[4];
@@ -526,11 +529,9 @@ int launch_match_score(const Geometry& geo, const GtOffsets& go, const float* gt
                        const float* teacher_score, const LossDebug& dbg, cudaStream_t stream) {
     int grid = geo.num_images * geo.tiles_per_image;
     KernelTimer timer(PAA_KERNEL_MATCH_SCORE, stream);
-    match_score_kernel<<<grid, PAA_TILE, 0, stream>>>(geo, go, gt_boxes, gt_labels, ws.gtmax,
-                                                      reinterpret_cast<const unsigned long long*>(ws.best), ws.negsum,
-                                                      sc, ws.matched, ws.score, ws.paa_label, ws.tile_gtmask,
-                                                      ws.seg_count, ws.seg_pool, teacher_score, dbg);
-    PAA_LAUNCH_CHECK("match_score_kernel");
+    PAA_PDL_LAUNCH(match_score_kernel, grid, PAA_TILE, stream, geo, go, gt_boxes, gt_labels, ws.gtmax,
+                   reinterpret_cast<const unsigned long long*>(ws.best), ws.negsum, sc, ws.matched, ws.score,
+                   ws.paa_label, ws.tile_gtmask, ws.seg_count, ws.seg_pool, teacher_score, dbg);
     return 0;
 }
 
@@ -820,6 +821,9 @@ select_gmm_kernel(const Geometry geo, const GtOffsets go, int num_gt_total,
                   int* __restrict__ part_npos, double* __restrict__ part_siou,
                   unsigned* __restrict__ ticket, double* __restrict__ local_norm,
                   double* __restrict__ normalisers, const PeerExchange px, const LossDebug dbg) {
+    // lets the loss pass (a programmatic dependent launch) become resident and prefetch while the slowest fits run
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ unsigned long long s_level[PAA_MAX_LEVELS][PAA_WARP];   // per-level top-K, ascending
     __shared__ int s_cnt[PAA_MAX_LEVELS];
     __shared__ unsigned long long s_key[PAA_MAX_CANDIDATES];
@@ -1071,6 +1075,7 @@ select_gmm_kernel(const Geometry geo, const GtOffsets go, int num_gt_total,
 // not arrive within ~2 s turns the normalisers into NaN instead of hanging the stream.
 __global__ void __launch_bounds__(PAA_WARP)
 norm_wait_kernel(const PeerExchange px, double* __restrict__ normalisers) {
+    pdl_launch_dependents();
     const int lane = threadIdx.x;
     const double* own = px.buf[px.rank];
     const unsigned long long epoch = (unsigned long long)own[kPeerEpochOffset];   // set by select_gmm_kernel
@@ -1116,7 +1121,7 @@ int launch_select_gmm(const Geometry& geo, const GtOffsets& go, int num_gt_total
     const int threads = geo.num_levels * PAA_WARP;
     KernelTimer timer(PAA_KERNEL_SELECT_GMM, stream);
 #define PAA_SEL_LAUNCH(SPL)                                                                           \
-    select_gmm_kernel<SPL><<<grid, threads, 0, stream>>>(geo, go, num_gt_total, gt_boxes, gt_labels, sc, \
+    PAA_PDL_LAUNCH(select_gmm_kernel<SPL>, grid, threads, stream, geo, go, num_gt_total, gt_boxes, gt_labels, sc, \
         ws.tile_gtmask, ws.matched, score_src, ws.seg_count, ws.seg_pool, ws.paa_label, ws.part_npos,  \
         ws.part_siou,                                                                                  \
         ws.ticket, ws.local_norm, normalisers, px, dbg)
@@ -1124,7 +1129,6 @@ int launch_select_gmm(const Geometry& geo, const GtOffsets& go, int num_gt_total
     else if (cap <= 64) PAA_SEL_LAUNCH(2);
     else PAA_SEL_LAUNCH(4);
 #undef PAA_SEL_LAUNCH
-    PAA_LAUNCH_CHECK("select_gmm_kernel");
     return 0;
 }
 

@@ -188,6 +188,7 @@ atss_labels_kernel(const Geometry geo, const GtOffsets go, const float* __restri
 __global__ void __launch_bounds__(512)
 atss_norm_kernel(const double* __restrict__ tile_part, int tiles, double* __restrict__ local_norm,
                  double* __restrict__ normalisers, const PeerExchange px) {
+    pdl_launch_dependents();
     __shared__ double s[16][2];
     double a[2] = {0.0, 0.0};
     for (int b = threadIdx.x; b < tiles; b += 512) {

@@ -153,6 +153,7 @@ struct BulkPlan {
     unsigned long long magic_c;                    // ceil(2^64 / C)
     unsigned C;
     unsigned char vec4[PAA_MAX_LEVELS];            // hw % 4 == 0: the four elements of a float4 share a plane
+    int l2_prefetch;                               // percentage of the chunks pulled towards the L2 before the dependency wait
 };
 
 // n / d for n < 2^32 with magic = ceil(2^64 / d), d >= 2: exact (error term n / 2^64 < 1 / d).
@@ -221,12 +222,71 @@ bulk_focal_kernel(const BulkPlan plan, const LossScalars sc, const double* __res
                   const double* __restrict__ local_norm, const float* __restrict__ gout,
                   double* __restrict__ block_part) {
     __shared__ double s_part[kBulkThreads / PAA_WARP];
-    const GradScales gs = make_scales(sc, norm, local_norm, gout);
+    pdl_launch_dependents();
     const float gamma = sc.gamma, oma = 1.0f - sc.alpha;
-    const float kneg = oma * gs.cls;
     float neg_sum = 0.f;
     const unsigned n_chunks = plan.chunk_off[plan.n];
-    for (unsigned ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
+    unsigned ch = blockIdx.x;
+    // Programmatic dependent launch: this grid may become resident while the kernel that produces the normalisers
+    // (select_gmm_kernel's slowest fits, the fold kernels) is still running.  The logits do not depend on it, so
+    // the block's first chunk is fetched before the dependency wait; everything scaled by 1 / num_pos comes after.
+    float4 x0[kBulkVecs];
+    bool first_full = false;
+    int l0 = 0;
+    unsigned long long base0 = 0;
+    if (ch < n_chunks) {
+#pragma unroll 1
+        for (int k = 1; k < plan.n; ++k)
+            if (ch >= plan.chunk_off[k]) l0 = k;
+        base0 = (unsigned long long)(ch - plan.chunk_off[l0]) * kBulkChunk;
+        first_full = base0 + kBulkChunk <= (plan.count[l0] >> 2);
+        if (first_full) {
+            const float4* __restrict__ src4 = reinterpret_cast<const float4*>(plan.src[l0]);
+#pragma unroll
+            for (int j = 0; j < kBulkVecs; ++j) x0[j] = __ldcs(src4 + base0 + j * kBulkThreads + threadIdx.x);
+        }
+    }
+    // ... and the block's later chunks are pulled towards the L2 (bulk prefetch, one instruction per 16 KB chunk,
+    // issued by one thread: the instruction takes warp-uniform operands) while the memory system idles behind the
+    // last EM fits.  Measured: the blocks sit at the wait for ~38 us of select_gmm_kernel's 54; the launch overlap is
+    // worth ~2 us of the step, the prefetch another ~1-2 us (profiles/README.md).
+    if (plan.l2_prefetch) {
+        const unsigned pf_end = (unsigned)(((unsigned long long)n_chunks * (unsigned)plan.l2_prefetch) / 100u);
+        for (unsigned c = blockIdx.x + gridDim.x; c < pf_end && threadIdx.x == 0; c += gridDim.x) {
+            int l = 0;
+#pragma unroll 1
+            for (int k = 1; k < plan.n; ++k)
+                if (c >= plan.chunk_off[k]) l = k;
+            const unsigned long long first = (unsigned long long)(c - plan.chunk_off[l]) * kBulkChunk * 4ull;   // floats
+            const unsigned long long left = plan.count[l] - first;
+            const unsigned bytes = (unsigned)((left < (unsigned long long)kBulkChunk * 4ull ? left : kBulkChunk * 4ull) * 4ull) & ~15u;
+            if (bytes)
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(plan.src[l] + first), "r"(bytes) : "memory");
+        }
+    }
+    pdl_wait();
+    const GradScales gs = make_scales(sc, norm, local_norm, gout);
+    const float kneg = oma * gs.cls;
+    if (first_full) {
+        float4* __restrict__ dst4 = reinterpret_cast<float4*>(plan.dst[l0]);
+        const bool write = kGrads && dst4 != nullptr;
+#pragma unroll
+        for (int j = 0; j < kBulkVecs; ++j) {
+            float4 g;
+            if (kIgnore) {
+                neg_terms4<kG2>(x0[j], gamma, kneg, ignore_nibble(plan, l0, base0 + j * kBulkThreads + threadIdx.x),
+                                &neg_sum, &g);
+            } else {
+                neg_term_grad<kG2>(x0[j].x, gamma, kneg, &neg_sum, &g.x);
+                neg_term_grad<kG2>(x0[j].y, gamma, kneg, &neg_sum, &g.y);
+                neg_term_grad<kG2>(x0[j].z, gamma, kneg, &neg_sum, &g.z);
+                neg_term_grad<kG2>(x0[j].w, gamma, kneg, &neg_sum, &g.w);
+            }
+            if (write) __stcs(dst4 + base0 + j * kBulkThreads + threadIdx.x, g);
+        }
+        ch += gridDim.x;
+    }
+    for (; ch < n_chunks; ch += gridDim.x) {
         int l = 0;
 #pragma unroll 1
         for (int k = 1; k < plan.n; ++k)
@@ -434,6 +494,8 @@ positive_terms_kernel(const Geometry geo, const GtOffsets go, const float* __res
                       int tiles_per_block, bool zero_fill, bool patch_ignored) {
     __shared__ double s_part[PAA_TILE / PAA_WARP][3];
     __shared__ int s_ign[PAA_TILE];                 // ignored anchors of the tile (index within the level)
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ int s_wcnt[PAA_TILE / PAA_WARP];
     float fix_sum = 0.f, reg_sum = 0.f, bce_sum = 0.f, ign_sum = 0.f;
     const bool may_ignore = patch_ignored;                          // block-uniform
@@ -565,6 +627,7 @@ finish_loss_kernel(const double* __restrict__ part_a, int blocks_a, const double
                    int blocks_b, const LossScalars sc, const double* __restrict__ norm,
                    float* __restrict__ losses) {
     __shared__ double s[kFinishThreads / PAA_WARP][3];
+    pdl_wait();
     double a[3] = {0.0, 0.0, 0.0};
     fold_partials(part_a, blocks_a, a);
     fold_partials(part_b, blocks_b, a);
@@ -651,6 +714,7 @@ int launch_final_loss(const Geometry& geo, const GtOffsets& go, const float* gt_
         plan.magic_hw[l] = ~0ull / d + 1ull;       // ceil(2^64 / d) for d >= 2 that is not a power of two, and
                                                    // 2^64 / d exactly when it is
     }
+    plan.l2_prefetch = getenv("PAA_L2_PREFETCH_PCT") ? atoi(getenv("PAA_L2_PREFETCH_PCT")) : 100;
     int bulk_grid = kBulkMaxBlocks;
     if ((unsigned)bulk_grid > chunks) bulk_grid = (int)chunks;
     const int tiles_total = geo.num_images * geo.tiles_per_image;
@@ -672,9 +736,10 @@ int launch_final_loss(const Geometry& geo, const GtOffsets& go, const float* gt_
     double* tile_part = ws.block_part + (size_t)kBulkMaxBlocks * 3;
     {
         KernelTimer timer(PAA_KERNEL_FINAL_LOSS, stream);
+        // launched as a programmatic dependent of the previous kernel on the stream (see the kernel's prologue)
 #define PAA_BULK(G, T, I)                                                                                    \
-    bulk_focal_kernel<G, T, I><<<bulk_grid, kBulkThreads, 0, stream>>>(plan, sc, normalisers, ws.local_norm, \
-                                                                       grad_losses, bulk_part)
+    PAA_PDL_LAUNCH((bulk_focal_kernel<G, T, I>), bulk_grid, kBulkThreads, stream, plan, sc, normalisers,     \
+                   ws.local_norm, grad_losses, bulk_part)
         if (bulk_ignores) {
             if (write_grads) {
                 if (g2) PAA_BULK(true, true, true); else PAA_BULK(true, false, true);
@@ -688,20 +753,18 @@ int launch_final_loss(const Geometry& geo, const GtOffsets& go, const float* gt_
         }
 #undef PAA_BULK
     }
-    PAA_LAUNCH_CHECK("bulk_focal_kernel");
 #define PAA_POS(G, T)                                                                                        \
-    positive_terms_kernel<G, T><<<tile_grid, PAA_TILE, 0, stream>>>(geo, go, gt_boxes, sc, ws.paa_label,     \
-        ws.matched, normalisers, ws.local_norm, grad_losses, tile_part, tiles_total, tiles_per_block, zero_fill,  \
-        has_ignored && !bulk_ignores)
+    PAA_PDL_LAUNCH((positive_terms_kernel<G, T>), tile_grid, PAA_TILE, stream, geo, go, gt_boxes, sc,        \
+        ws.paa_label, ws.matched, normalisers, ws.local_norm, grad_losses, tile_part, tiles_total,           \
+        tiles_per_block, zero_fill, has_ignored && !bulk_ignores)
     if (write_grads) {
         if (g2) PAA_POS(true, true); else PAA_POS(true, false);
     } else {
         if (g2) PAA_POS(false, true); else PAA_POS(false, false);
     }
 #undef PAA_POS
-    PAA_LAUNCH_CHECK("positive_terms_kernel");
-    finish_loss_kernel<<<1, kFinishThreads, 0, stream>>>(bulk_part, bulk_grid, tile_part, tile_grid, sc, normalisers, losses);
-    PAA_LAUNCH_CHECK("finish_loss_kernel");
+    PAA_PDL_LAUNCH(finish_loss_kernel, 1, kFinishThreads, stream, bulk_part, bulk_grid, tile_part, tile_grid, sc,
+                   normalisers, losses);
     return 0;
 }
 

@@ -423,8 +423,8 @@ match_score_kernel(const Geometry geo, const GtOffsets go, const float* __restri
                    int* __restrict__ matched, float* __restrict__ score, int* __restrict__ paa_label, uint4* __restrict__ tile_gtmask,
                    int* __restrict__ seg_count, unsigned long long* __restrict__ seg_pool,
                    const float* __restrict__ teacher_score, const LossDebug dbg) {
-    pdl_launch_dependents();
     pdl_wait();
+    pdl_launch_dependents();
     __shared__ int s_lq[PAA_TILE];
     __shared__ int s_nlq;
     __shared__ unsigned s_mask[4];
@@ -822,8 +822,8 @@ select_gmm_kernel(const Geometry geo, const GtOffsets go, int num_gt_total,
                   unsigned* __restrict__ ticket, double* __restrict__ local_norm,
                   double* __restrict__ normalisers, const PeerExchange px, const LossDebug dbg) {
     // lets the loss pass (a programmatic dependent launch) become resident and prefetch while the slowest fits run
-    pdl_launch_dependents();
     pdl_wait();
+    pdl_launch_dependents();
     __shared__ unsigned long long s_level[PAA_MAX_LEVELS][PAA_WARP];   // per-level top-K, ascending
     __shared__ int s_cnt[PAA_MAX_LEVELS];
     __shared__ unsigned long long s_key[PAA_MAX_CANDIDATES];

@@ -41,6 +41,7 @@ __device__ __forceinline__ void nearest_offer(unsigned long long& mine, unsigned
 __global__ void __launch_bounds__(PAA_MAX_LEVELS * PAA_WARP)
 atss_candidates_kernel(const Geometry geo, const GtOffsets go, const float* __restrict__ gt_boxes, const int K,
                        unsigned long long* __restrict__ best, const LossDebug dbg) {
+    pdl_launch_dependents();
     __shared__ unsigned s_cand[PAA_MAX_LEVELS][PAA_WARP];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gi = blockIdx.x;
@@ -140,6 +141,8 @@ atss_labels_kernel(const Geometry geo, const GtOffsets go, const float* __restri
                    const int64_t* __restrict__ gt_labels, const unsigned long long* __restrict__ best,
                    int* __restrict__ matched, int* __restrict__ paa_label, double* __restrict__ tile_part,
                    const LossDebug dbg) {
+    pdl_wait();
+    pdl_launch_dependents();
     __shared__ double s_part[PAA_TILE / PAA_WARP][2];
     const int n = blockIdx.x / geo.tiles_per_image;
     const int tile = blockIdx.x - n * geo.tiles_per_image;
@@ -188,6 +191,7 @@ atss_labels_kernel(const Geometry geo, const GtOffsets go, const float* __restri
 __global__ void __launch_bounds__(512)
 atss_norm_kernel(const double* __restrict__ tile_part, int tiles, double* __restrict__ local_norm,
                  double* __restrict__ normalisers, const PeerExchange px) {
+    pdl_wait();
     pdl_launch_dependents();
     __shared__ double s[16][2];
     double a[2] = {0.0, 0.0};
@@ -242,16 +246,14 @@ int launch_atss_assign(const Geometry& geo, const GtOffsets& go, int num_gt_tota
     const int tiles = geo.num_images * geo.tiles_per_image;
     // the per-tile partials live where positive_terms_kernel later puts its own (it runs after the fold)
     double* tile_part = ws.block_part;
-    atss_labels_kernel<<<tiles, PAA_TILE, 0, stream>>>(geo, go, gt_boxes, gt_labels, best, ws.matched, ws.paa_label,
-                                                       tile_part, dbg);
-    PAA_LAUNCH_CHECK("atss_labels_kernel");
+    PAA_PDL_LAUNCH(atss_labels_kernel, tiles, PAA_TILE, stream, geo, go, gt_boxes, gt_labels, best, ws.matched,
+                   ws.paa_label, tile_part, dbg);
     return launch_fold_norm(tile_part, tiles, ws.local_norm, normalisers, px, stream);
 }
 
 int launch_fold_norm(const double* tile_part, int tiles, double* local_norm, double* normalisers,
                      const PeerExchange& px, cudaStream_t stream) {
-    atss_norm_kernel<<<1, 512, 0, stream>>>(tile_part, tiles, local_norm, normalisers, px);
-    PAA_LAUNCH_CHECK("atss_norm_kernel");
+    PAA_PDL_LAUNCH(atss_norm_kernel, 1, 512, stream, tile_part, tiles, local_norm, normalisers, px);
     return 0;
 }
 

@@ -18,6 +18,7 @@ __global__ void __launch_bounds__(PAA_TILE)
 fcos_assign_kernel(const Geometry geo, const GtOffsets go, const float* __restrict__ gt_boxes,
                    const int64_t* __restrict__ gt_labels, const LossScalars sc, int* __restrict__ matched,
                    int* __restrict__ label_out, double* __restrict__ tile_part, const LossDebug dbg, bool ssc) {
+    pdl_launch_dependents();
     __shared__ float4 s_box[PAA_TILE];
     __shared__ float s_area[PAA_TILE];
     __shared__ double s_part[PAA_TILE / PAA_WARP][2];

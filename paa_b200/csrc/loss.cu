@@ -222,7 +222,6 @@ bulk_focal_kernel(const BulkPlan plan, const LossScalars sc, const double* __res
                   const double* __restrict__ local_norm, const float* __restrict__ gout,
                   double* __restrict__ block_part) {
     __shared__ double s_part[kBulkThreads / PAA_WARP];
-    pdl_launch_dependents();
     const float gamma = sc.gamma, oma = 1.0f - sc.alpha;
     float neg_sum = 0.f;
     const unsigned n_chunks = plan.chunk_off[plan.n];
@@ -251,7 +250,10 @@ bulk_focal_kernel(const BulkPlan plan, const LossScalars sc, const double* __res
     // last EM fits.  Measured: the blocks sit at the wait for ~38 us of select_gmm_kernel's 54; the launch overlap is
     // worth ~2 us of the step, the prefetch another ~1-2 us (profiles/README.md).
     if (plan.l2_prefetch) {
-        const unsigned pf_end = (unsigned)(((unsigned long long)n_chunks * (unsigned)plan.l2_prefetch) / 100u);
+        // no more than ~96 MB: what the 126 MB L2 can hold until the pass gets there (a 1 GB RetinaNet stream
+        // prefetched whole just evicts itself and is read twice)
+        unsigned pf_end = (unsigned)(((unsigned long long)n_chunks * (unsigned)plan.l2_prefetch) / 100u);
+        pf_end = pf_end < 6144u ? pf_end : 6144u;
         for (unsigned c = blockIdx.x + gridDim.x; c < pf_end && threadIdx.x == 0; c += gridDim.x) {
             int l = 0;
 #pragma unroll 1
@@ -265,6 +267,7 @@ bulk_focal_kernel(const BulkPlan plan, const LossScalars sc, const double* __res
         }
     }
     pdl_wait();
+    pdl_launch_dependents();        // after the wait: at most one future kernel sits resident behind the running one
     const GradScales gs = make_scales(sc, norm, local_norm, gout);
     const float kneg = oma * gs.cls;
     if (first_full) {
@@ -494,8 +497,8 @@ positive_terms_kernel(const Geometry geo, const GtOffsets go, const float* __res
                       int tiles_per_block, bool zero_fill, bool patch_ignored) {
     __shared__ double s_part[PAA_TILE / PAA_WARP][3];
     __shared__ int s_ign[PAA_TILE];                 // ignored anchors of the tile (index within the level)
-    pdl_launch_dependents();
     pdl_wait();
+    pdl_launch_dependents();
     __shared__ int s_wcnt[PAA_TILE / PAA_WARP];
     float fix_sum = 0.f, reg_sum = 0.f, bce_sum = 0.f, ign_sum = 0.f;
     const bool may_ignore = patch_ignored;                          // block-uniform

@@ -27,6 +27,7 @@ retina_labels_kernel(const Geometry geo, const GtOffsets go, const float* __rest
                      int* __restrict__ matched, int* __restrict__ label_out, unsigned* __restrict__ ignore_bits,
                      double* __restrict__ tile_part, const LossDebug dbg, int tiles_total, int tiles_per_block,
                      bool atss_iou) {
+    pdl_launch_dependents();
     __shared__ float4 s_box[PAA_TILE];
     __shared__ float s_max[PAA_TILE];
     __shared__ int s_nlq;

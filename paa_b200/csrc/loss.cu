@@ -739,6 +739,9 @@ int launch_final_loss(const Geometry& geo, const GtOffsets& go, const float* gt_
     double* tile_part = ws.block_part + (size_t)kBulkMaxBlocks * 3;
     {
         KernelTimer timer(PAA_KERNEL_FINAL_LOSS, stream);
+        // events around the launch serialise it behind its predecessor: no overlap window, so no point in pulling
+        // chunks towards the L2 ahead of the stream (it only adds work to the kernel timed alone)
+        if (timer.slot_ >= 0) plan.l2_prefetch = 0;
         // launched as a programmatic dependent of the previous kernel on the stream (see the kernel's prologue)
 #define PAA_BULK(G, T, I)                                                                                    \
     PAA_PDL_LAUNCH((bulk_focal_kernel<G, T, I>), bulk_grid, kBulkThreads, stream, plan, sc, normalisers,     \

@@ -4,6 +4,7 @@ There is no fallback: if the library is missing or does not load, importing a pr
 needs it raises.  Build it with ``python -m paa_b200.build`` (needs nvcc) or
 ``__graft_entry__.build()``.
 """
+import contextlib
 import ctypes as C
 import os
 
@@ -138,6 +139,27 @@ def load():
         raise PaaLibraryError("libpaa_b200.so ABI %d != binding %d" % (lib.paa_abi_version(), ABI_VERSION))
     _lib = lib
     return lib
+
+
+_NO_GUARD = contextlib.nullcontext()
+
+
+def stream_handle(device):
+    """``cudaStream_t`` of torch's current stream on `device` as an integer.  Takes torch's raw-stream accessor
+    (no ``torch.cuda.Stream`` object per call: this sits on the per-step host path) when it exists."""
+    import torch
+    raw = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+    if raw is not None and device.index is not None:
+        return raw(device.index)
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def device_guard(device):
+    """Context that makes `device` the current CUDA device for the library call; free when it already is."""
+    import torch
+    if device.index is None or device.index == torch.cuda.current_device():
+        return _NO_GUARD
+    return torch.cuda.device(device)
 
 
 def check(rc, what):

@@ -87,8 +87,8 @@ class AnchorGenerator(torch.nn.Module):
             return self._grid_cache[key]
         cells = self._cells_on(device)
         out = []
-        stream = torch.cuda.current_stream(device).cuda_stream
-        with torch.cuda.device(device):
+        stream = _lib.stream_handle(device)
+        with _lib.device_guard(device):
             for (h, w), stride, cell in zip(key[0], self.strides, cells):
                 a = int(cell.shape[0])
                 t = torch.empty((h * w * a, 4), dtype=torch.float32, device=device)
@@ -102,8 +102,8 @@ class AnchorGenerator(torch.nn.Module):
         key = (grid_key, level, (float(image_wh[0]), float(image_wh[1])))
         if key not in self._vis_cache:
             vis = torch.empty(anchors.shape[0], dtype=torch.uint8, device=anchors.device)
-            stream = torch.cuda.current_stream(anchors.device).cuda_stream
-            with torch.cuda.device(anchors.device):
+            stream = _lib.stream_handle(anchors.device)
+            with _lib.device_guard(anchors.device):
                 _lib.check(self._lib.paa_anchor_visibility(anchors.data_ptr(), anchors.shape[0], float(image_wh[0]),
                                                            float(image_wh[1]), float(self.straddle_thresh),
                                                            vis.data_ptr(), stream), "paa_anchor_visibility")

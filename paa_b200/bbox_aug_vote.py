@@ -53,12 +53,12 @@ def merge_result_from_multi_scales(boxlists, cfg, nms_type="nms", vote_thresh=0.
         out_count = torch.empty(1, dtype=torch.int32, device=device)
         ws = torch.empty(lib.paa_box_vote_workspace_bytes(n) + 256, dtype=torch.uint8, device=device)
         base = (ws.data_ptr() + 255) // 256 * 256
-        with torch.cuda.device(device):
+        with _lib.device_guard(device):
             _lib.check(lib.paa_box_vote(boxes.data_ptr(), scores.data_ptr(), flabels.data_ptr(), n, mode_i,
                                         float(vote_thresh), nms_t, soft_thresh, max_det, out_boxes.data_ptr(),
                                         out_scores.data_ptr(), out_labels.data_ptr(), out_count.data_ptr(), base,
                                         ws.numel() - (base - ws.data_ptr()),
-                                        torch.cuda.current_stream(device).cuda_stream), "paa_box_vote")
+                                        _lib.stream_handle(device)), "paa_box_vote")
         c = int(out_count.item())                                 # the one host sync: result size
         result = BoxList(out_boxes[:c], boxlist.size, mode="xyxy")
         result.add_field("scores", out_scores[:c])

@@ -80,16 +80,20 @@ class PAAPostProcessor(torch.nn.Module):
         for k in range(4):
             args.decode_weights[k] = float(self._decode[1][k])
         args.decode_clip = float(self._decode[2])
+        cls_l, reg_l, iou_l = lv["cls"], lv["reg"], lv["iou"]
+        anchor_ptrs, hw_l, grid_w = lv["anchor_ptrs"], lv["hw"], lv["grid_w"]
+        levels = args.levels
         for l in range(L):
-            s = args.levels[l]
-            s.box_cls, s.box_regression = lv["cls"][l].data_ptr(), lv["reg"][l].data_ptr()
-            s.iou_pred = lv["iou"][l].data_ptr() if lv["iou"] is not None else None
-            s.anchors = lv["anchor_ptrs"][l]
-            s.hw = lv["hw"][l]
-            s.grid_w = int(lv["cls"][l].shape[-1])
+            s = levels[l]
+            s.box_cls, s.box_regression = cls_l[l].data_ptr(), reg_l[l].data_ptr()
+            if iou_l is not None:
+                s.iou_pred = iou_l[l].data_ptr()
+            s.anchors, s.hw, s.grid_w = anchor_ptrs[l], hw_l[l], grid_w[l]
+        image_wh = args.image_wh
         for i in range(N):
             w, h = anchors[i][0].size
-            args.image_wh[i][0], args.image_wh[i][1] = float(w), float(h)
+            wh = image_wh[i]
+            wh[0], wh[1] = w, h
         nbytes = self._lib.paa_postprocess_workspace_bytes(N, A, Cn, L, int(self.pre_nms_top_n))
         ws = self._workspace_for(device, nbytes)
         base = (ws.data_ptr() + 255) // 256 * 256
@@ -110,8 +114,8 @@ class PAAPostProcessor(torch.nn.Module):
             args.dbg_pre_boxes, args.dbg_pre_scores = dbg["pre_boxes"].data_ptr(), dbg["pre_scores"].data_ptr()
             args.dbg_pre_labels, args.dbg_pre_count = dbg["pre_labels"].data_ptr(), dbg["pre_count"].data_ptr()
             args.dbg_nms_keep = dbg["nms_keep"].data_ptr()
-        stream = torch.cuda.current_stream(device).cuda_stream
-        with torch.cuda.device(device):
+        stream = _lib.stream_handle(device)
+        with _lib.device_guard(device):
             _lib.check(self._lib.paa_postprocess(C.byref(args), stream), "paa_postprocess")
         self.last_debug = dbg
         self._keep = (lv, ws)
@@ -119,12 +123,15 @@ class PAAPostProcessor(torch.nn.Module):
 
     def forward(self, box_cls, box_regression, iou_pred, anchors):
         boxes, scores, labels, count = self.run_device(box_cls, box_regression, iou_pred, anchors)
+        # per-image views are cut while the kernels run; only the row counts wait for the device
+        per_image = list(zip(boxes.unbind(0), labels.unbind(0), scores.unbind(0)))
         counts = count.tolist()                       # the one host sync: result sizes
         results = []
         for i, c in enumerate(counts):
-            bl = BoxList(boxes[i, :c], anchors[i][0].size, mode="xyxy")
-            bl.add_field("labels", labels[i, :c])
-            bl.add_field("scores", scores[i, :c])
+            b, l, s = per_image[i]
+            bl = BoxList(b.narrow(0, 0, c), anchors[i][0].size, mode="xyxy")
+            bl.add_field("labels", l.narrow(0, 0, c))
+            bl.add_field("scores", s.narrow(0, 0, c))
             results.append(bl)
         return results
 
@@ -277,8 +284,8 @@ def ml_nms(boxes, scores, labels, nms_thresh):
     nbytes = lib.paa_ml_nms_workspace_bytes(n)
     ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=device)
     base = (ws.data_ptr() + 255) // 256 * 256
-    stream = torch.cuda.current_stream(device).cuda_stream
-    with torch.cuda.device(device):
+    stream = _lib.stream_handle(device)
+    with _lib.device_guard(device):
         _lib.check(lib.paa_ml_nms(b.data_ptr(), s.data_ptr(), lab.data_ptr(), n, float(nms_thresh), keep.data_ptr(),
                                   num.data_ptr(), base, ws.numel() - (base - ws.data_ptr()), stream), "paa_ml_nms")
     return torch.nonzero(keep).squeeze(1)

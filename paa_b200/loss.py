@@ -92,17 +92,37 @@ class PeerNormExchange(object):
         return cls._by_device[key]
 
 
-def _head(t, name):
+def _require_cuda(t, name):
     if not t.is_cuda:
         raise RuntimeError("paa_b200 has no CPU path: %s is on %s" % (name, t.device))
+
+
+def _head(t, name):
+    _require_cuda(t, name)
     if t.dtype != torch.float32:
         raise RuntimeError("%s must be float32, got %s" % (name, t.dtype))
     return t if t.is_contiguous() else t.contiguous()
 
 
+def _anchors_shared(anchors, N, L):
+    """True when every image lists the same anchor storage (the reference's generator wraps one tensor per level
+    into a BoxList per image, anchor_generator.py:114-124)."""
+    first = anchors[0]
+    for i in range(1, N):
+        per_image = anchors[i]
+        if per_image is first:
+            continue
+        for l in range(L):
+            b, b0 = per_image[l].bbox, first[l].bbox
+            if b is not b0 and b.data_ptr() != b0.data_ptr():
+                return False
+    return True
+
+
 def gather_levels(box_cls, box_regression, iou_pred, anchors):
     """Validates the head lists / anchor lists and returns contiguous tensors plus layout facts.
-    anchors: list[N] of list[L] BoxList (anchor_generator.py:112-125)."""
+    anchors: list[N] of list[L] BoxList (anchor_generator.py:112-125).  This runs on every call of the
+    evaluators, ahead of the kernel launches: plain loops, no per-element tensor calls beyond the checks."""
     L = len(box_cls)
     if L == 0 or len(box_regression) != L or (iou_pred is not None and len(iou_pred) != L):
         raise RuntimeError("box_cls / box_regression / iou_pred must list the same levels")
@@ -116,34 +136,32 @@ def gather_levels(box_cls, box_regression, iou_pred, anchors):
     cls = [_head(t, "box_cls") for t in box_cls]
     reg = [_head(t, "box_regression") for t in box_regression]
     iou = None if iou_pred is None else [_head(t, "iou_pred") for t in iou_pred]
-    hw = []
+    hw, grid_w = [], []
+    first = anchors[0]
     for l in range(L):
         n, ch, h, w = cls[l].shape
         if n != N or ch != apl * num_classes or reg[l].shape != (N, apl * 4, h, w) or \
                 (iou is not None and iou[l].shape != (N, apl, h, w)):
             raise RuntimeError("level %d: inconsistent head shapes" % l)
-        if len(anchors[0][l].bbox) != h * w * apl:
+        if first[l].bbox.shape[0] != h * w * apl:
             raise RuntimeError("level %d: %d anchors for a %dx%d map with %d per location"
-                               % (l, len(anchors[0][l].bbox), h, w, apl))
+                               % (l, first[l].bbox.shape[0], h, w, apl))
         hw.append(h * w)
-    # every image normally shares the anchor tensors of the batch (anchor_generator.py:114-124)
-    shared = all(anchors[i][l].bbox.data_ptr() == anchors[0][l].bbox.data_ptr()
-                 for i in range(1, N) for l in range(L))
+        grid_w.append(w)
     A = sum(hw) * apl
-    if shared:
-        anc = [anchors[0][l].bbox for l in range(L)]
-        anc = [a if (a.is_contiguous() and a.dtype == torch.float32) else a.contiguous().float() for a in anc]
+    # every image normally shares the anchor tensors of the batch (anchor_generator.py:114-124)
+    if _anchors_shared(anchors, N, L):
+        anc = [first[l].bbox for l in range(L)]
+        anc = [a if (a.dtype == torch.float32 and a.is_contiguous()) else a.contiguous().float() for a in anc]
         for a in anc:
-            if not a.is_cuda:
-                raise RuntimeError("paa_b200 has no CPU path: anchors are on %s" % a.device)
+            _require_cuda(a, "anchors")
         level_ptrs = [a.data_ptr() for a in anc]
         stride = 0
         keep = anc
     else:
         stacked = torch.stack([torch.cat([anchors[i][l].bbox for l in range(L)], dim=0)
                                for i in range(N)], dim=0).float().contiguous()      # [N, A, 4]
-        if not stacked.is_cuda:
-            raise RuntimeError("paa_b200 has no CPU path: anchors are on %s" % stacked.device)
+        _require_cuda(stacked, "anchors")
         offs, o = [], 0
         for l in range(L):
             offs.append(o)
@@ -151,13 +169,16 @@ def gather_levels(box_cls, box_regression, iou_pred, anchors):
         level_ptrs = [stacked.data_ptr() + 16 * off for off in offs]
         stride = A * 4
         keep = [stacked]
-    return dict(L=L, N=N, apl=apl, C=num_classes, hw=hw, A=A, cls=cls, reg=reg, iou=iou,
+    return dict(L=L, N=N, apl=apl, C=num_classes, hw=hw, grid_w=grid_w, A=A, cls=cls, reg=reg, iou=iou,
                 anchor_ptrs=level_ptrs, anchor_stride=stride, keep=keep)
 
 
 class _PAALossFunction(torch.autograd.Function):
-    """losses[3] = f(heads); the gradients are produced by the same kernel pass as the losses and
-    handed out in backward (rescaled on the device if the upstream gradients are not ones)."""
+    """(loss_0, loss_1, loss_2) = f(heads); the gradients are produced by the same kernel pass as the losses and
+    handed out in backward (rescaled on the device if the upstream gradients are not ones).  The three losses
+    leave as separate 0-dim outputs (views of the kernel's 3-element result made here, outside autograd's
+    recording): indexing a 3-vector output instead costs three SelectBackward nodes, i.e. ~8 tiny launches per
+    step on the host path."""
 
     @staticmethod
     def forward(ctx, owner, targets, anchors, n_levels, has_iou, *heads):
@@ -171,15 +192,21 @@ class _PAALossFunction(torch.autograd.Function):
         ctx.grads = grads
         ctx.n_levels = n_levels
         ctx.has_iou = has_iou
-        return losses
+        ctx.set_materialize_grads(False)
+        return losses[0], losses[1], losses[2]
 
     @staticmethod
     @torch.autograd.function.once_differentiable
-    def backward(ctx, grad_losses):
+    def backward(ctx, *grad_losses):
         grads = ctx.grads
-        if grads is None:
-            return (None,) * (5 + ctx.n_levels * (3 if ctx.has_iou else 2))
-        ctx.owner._rescale(ctx.call, grad_losses.contiguous().float())
+        n_in = 5 + ctx.n_levels * (3 if ctx.has_iou else 2)
+        if grads is None or all(g is None for g in grad_losses):
+            return (None,) * n_in
+        if any(g is None for g in grad_losses):          # a loss the caller did not use contributes nothing
+            zero = next(g for g in grad_losses if g is not None).new_zeros(())
+            grad_losses = [zero if g is None else g for g in grad_losses]
+        g = torch.stack(grad_losses)
+        ctx.owner._rescale(ctx.call, g if g.dtype == torch.float32 else g.float())
         out = list(grads["cls"]) + list(grads["reg"]) + (list(grads["iou"]) if ctx.has_iou else [])
         return (None, None, None, None, None) + tuple(out)
 
@@ -229,16 +256,22 @@ class PAALossComputation(object):
             raise RuntimeError("targets lists %d images, heads have batch %d" % (len(targets), N))
         if N > _lib.MAX_IMAGES:
             raise RuntimeError("at most %d images per call" % _lib.MAX_IMAGES)
-        offsets = [0]
+        offsets, boxes, labels, sum_g = [0], [], [], 0
         for i, t in enumerate(targets):
             assert t.mode == "xyxy"                                   # loss.py:97
             if tuple(t.size) != tuple(anchors[i][0].size):            # boxlist_ops.py:95-97
                 raise RuntimeError("boxlists should have same image size, got {}, {}".format(t, anchors[i][0]))
-            offsets.append(offsets[-1] + len(t))
-        gt_boxes = torch.cat([t.bbox for t in targets], dim=0).to(device=device, dtype=torch.float32).contiguous()
-        gt_labels = torch.cat([t.get_field("labels") for t in targets], dim=0).to(device=device,
-                                                                                dtype=torch.int64).contiguous()
-        sum_g = offsets[-1]
+            b = t.bbox
+            sum_g += b.shape[0]
+            offsets.append(sum_g)
+            boxes.append(b)
+            labels.append(t.get_field("labels"))
+        gt_boxes = torch.cat(boxes, dim=0)
+        if gt_boxes.dtype != torch.float32 or gt_boxes.device != device:
+            gt_boxes = gt_boxes.to(device=device, dtype=torch.float32)
+        gt_labels = torch.cat(labels, dim=0)
+        if gt_labels.dtype != torch.int64 or gt_labels.device != device:
+            gt_labels = gt_labels.to(device=device, dtype=torch.int64)
         has_iou = iou_pred is not None
         # the RetinaNet loss normalises by this rank's own counts (retinanet/loss.py:70,79): no exchange
         world = 1 if self._flavour == _lib.LOSS_RETINANET else get_num_gpus()
@@ -270,19 +303,21 @@ class PAALossComputation(object):
             grads = dict(cls=[torch.empty_like(t) for t in lv["cls"]],
                          reg=[torch.empty_like(t) for t in lv["reg"]],
                          iou=[torch.empty_like(t) for t in lv["iou"]] if has_iou else None)
+        cls_l, reg_l, iou_l = lv["cls"], lv["reg"], lv["iou"]
+        anchor_ptrs, hw_l, grid_w = lv["anchor_ptrs"], lv["hw"], lv["grid_w"]
+        levels = args.levels
         for l in range(L):
-            s = args.levels[l]
-            s.box_cls, s.box_regression = lv["cls"][l].data_ptr(), lv["reg"][l].data_ptr()
-            s.iou_pred = lv["iou"][l].data_ptr() if has_iou else None
-            s.anchors = lv["anchor_ptrs"][l]
-            s.hw = lv["hw"][l]
-            s.grid_w = int(lv["cls"][l].shape[-1])
+            s = levels[l]
+            s.box_cls, s.box_regression = cls_l[l].data_ptr(), reg_l[l].data_ptr()
+            s.anchors, s.hw, s.grid_w = anchor_ptrs[l], hw_l[l], grid_w[l]
+            if has_iou:
+                s.iou_pred = iou_l[l].data_ptr()
             if grads is not None:
                 s.grad_box_cls, s.grad_box_regression = grads["cls"][l].data_ptr(), grads["reg"][l].data_ptr()
-                s.grad_iou_pred = grads["iou"][l].data_ptr() if has_iou else None
+                if has_iou:
+                    s.grad_iou_pred = grads["iou"][l].data_ptr()
         args.gt_boxes, args.gt_labels = gt_boxes.data_ptr(), gt_labels.data_ptr()
-        for i, o in enumerate(offsets):
-            args.gt_offsets[i] = o
+        args.gt_offsets[:N + 1] = offsets
         nbytes = self._lib.paa_loss_workspace_bytes(N, A, sum_g, L, self.topk)
         ws = self._workspace_for(device, nbytes)
         base = (ws.data_ptr() + 255) // 256 * 256
@@ -310,11 +345,11 @@ class PAALossComputation(object):
             teacher = teacher.to(device=device, dtype=torch.float32).contiguous()
             assert teacher.shape == (N, A)
             args.teacher_combined_loss = teacher.data_ptr()
-        stream = torch.cuda.current_stream(device).cuda_stream
+        stream = _lib.stream_handle(device)
         assign_name = {_lib.LOSS_PAA: "paa_assign", _lib.LOSS_ATSS: "paa_atss_assign",
                        _lib.LOSS_RETINANET: "paa_retinanet_assign", _lib.LOSS_FCOS: "paa_fcos_assign"}[self._flavour]
         assign = getattr(self._lib, assign_name)
-        with torch.cuda.device(device):
+        with _lib.device_guard(device):
             peer = PeerNormExchange.get(device) if world > 1 else None
             if peer is not None:
                 args.rank = peer.rank
@@ -336,8 +371,8 @@ class PAALossComputation(object):
         device = call["device"]
         if self._ones is None or self._ones.device != device:
             self._ones = torch.ones(3, dtype=torch.float32, device=device)
-        stream = torch.cuda.current_stream(device).cuda_stream
-        with torch.cuda.device(device):
+        stream = _lib.stream_handle(device)
+        with _lib.device_guard(device):
             _lib.check(self._lib.paa_rescale_grads(C.byref(call["args"]), self._ones.data_ptr(),
                                                    grad_losses.data_ptr(), stream), "paa_rescale_grads")
 
@@ -358,10 +393,7 @@ class PAALossComputation(object):
         has_iou = iou_pred is not None
         heads = list(box_cls) + list(box_regression) + (list(iou_pred) if has_iou else [])
         losses = _PAALossFunction.apply(self, targets, anchors, n_levels, has_iou, *heads)
-        res = [losses[0], losses[1]]
-        if has_iou:
-            res.append(losses[2])
-        return res
+        return list(losses) if has_iou else [losses[0], losses[1]]
 
 
 def make_paa_loss_evaluator(cfg, box_coder):

@@ -113,7 +113,7 @@ def boxlist_iou(boxlist1, boxlist2):
     b1 = b1.to(torch.float32).contiguous()
     b2 = b2.to(device=b1.device, dtype=torch.float32).contiguous()
     out = torch.empty((b1.shape[0], b2.shape[0]), dtype=torch.float32, device=b1.device)
-    with torch.cuda.device(b1.device):
+    with _lib.device_guard(b1.device):
         _lib.check(lib.paa_boxlist_iou(b1.data_ptr(), b1.shape[0], b2.data_ptr(), b2.shape[0], out.data_ptr(),
-                                       torch.cuda.current_stream(b1.device).cuda_stream), "paa_boxlist_iou")
+                                       _lib.stream_handle(b1.device)), "paa_boxlist_iou")
     return out

@@ -79,3 +79,53 @@ def test_head_and_anchor_validation():
         L.gather_levels(cls, reg[:-1], iou, anchors)
     with pytest.raises(RuntimeError, match="anchors lists"):
         L.gather_levels(cls, reg, iou, anchors[:1])
+
+
+class _RecordingOwner(object):
+    """Stands in for an evaluator behind `_PAALossFunction`: fixed losses / gradients, records the rescale vector."""
+
+    def __init__(self):
+        self.scaled = None
+
+    def _run(self, cls, reg, iou, targets, anchors, need_grad):
+        grads = None
+        if need_grad:
+            grads = dict(cls=[torch.full_like(t, 1.0) for t in cls], reg=[torch.full_like(t, 2.0) for t in reg],
+                         iou=None if iou is None else [torch.full_like(t, 3.0) for t in iou])
+        return torch.tensor([1.0, 2.0, 3.0]), grads, dict(device=None)
+
+    def _rescale(self, call, grad_losses):
+        self.scaled = grad_losses.tolist()
+
+
+def test_autograd_wiring_of_the_loss_function():
+    """The three losses leave the autograd function as separate 0-dim outputs; backward hands the rescale kernel
+    the upstream gradients of all three (zero for a loss the caller did not use) and returns one gradient per head."""
+    owner = _RecordingOwner()
+    heads = [torch.randn(2, 3, requires_grad=True) for _ in range(6)]
+    out = L._PAALossFunction.apply(owner, None, None, 2, True, *heads)
+    assert len(out) == 3 and all(t.dim() == 0 and t.requires_grad for t in out)
+    assert [float(t.detach()) for t in out] == [1.0, 2.0, 3.0]
+    grads = torch.autograd.grad(out[0] * 2 + out[1], heads)                 # the third loss is unused
+    assert owner.scaled == [2.0, 1.0, 0.0]
+    assert [float(g.flatten()[0]) for g in grads] == [1.0, 1.0, 2.0, 2.0, 3.0, 3.0]
+    out = L._PAALossFunction.apply(owner, None, None, 2, True, *heads)
+    (out[0] + out[1] + out[2]).backward()
+    assert owner.scaled == [1.0, 1.0, 1.0] and all(h.grad is not None for h in heads)
+    out = L._PAALossFunction.apply(owner, None, None, 2, False, *heads[:4])  # USE_IOU_PRED = False: two head lists
+    out[1].backward()
+    assert owner.scaled == [0.0, 1.0, 0.0]
+    with torch.no_grad():
+        out = L._PAALossFunction.apply(owner, None, None, 2, True, *heads)
+    assert not any(t.requires_grad for t in out)
+
+
+def test_anchor_sharing_is_detected_by_identity_or_address():
+    b = synthetic.make_batch(seed=7, num_images=3, image_hw=(128, 160), gt_per_image=2)
+    _, _, _, _, anchors = synthetic.to_device_inputs(b, device="cpu")
+    n_levels = len(anchors[0])
+    assert L._anchors_shared(anchors, 3, n_levels)
+    views = [[paa_b200.BoxList(a.bbox[:], a.size) for a in per_image] for per_image in anchors]   # same storage
+    assert L._anchors_shared(views, 3, n_levels)
+    views[2][1] = paa_b200.BoxList(anchors[2][1].bbox.clone(), anchors[2][1].size)               # own copy
+    assert not L._anchors_shared(views, 3, n_levels)

@@ -176,7 +176,7 @@ def gather_levels(box_cls, box_regression, iou_pred, anchors):
 class _PAALossFunction(torch.autograd.Function):
     """(loss_0, loss_1, loss_2) = f(heads); the gradients are produced by the same kernel pass as the losses and
     handed out in backward (rescaled on the device if the upstream gradients are not ones).  The three losses
-    leave as separate 0-dim outputs (views of the kernel's 3-element result made here, outside autograd's
+    leave as separate 0-dim outputs (aliases of the kernel's 3-element result made here, outside autograd's
     recording): indexing a 3-vector output instead costs three SelectBackward nodes, i.e. ~8 tiny launches per
     step on the host path."""
 
@@ -193,7 +193,8 @@ class _PAALossFunction(torch.autograd.Function):
         ctx.n_levels = n_levels
         ctx.has_iou = has_iou
         ctx.set_materialize_grads(False)
-        return losses[0], losses[1], losses[2]
+        # detached aliases, not autograd views: the caller may scale a loss in place like any op result
+        return losses[0].detach(), losses[1].detach(), losses[2].detach()
 
     @staticmethod
     @torch.autograd.function.once_differentiable

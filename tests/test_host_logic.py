@@ -118,6 +118,12 @@ def test_autograd_wiring_of_the_loss_function():
     with torch.no_grad():
         out = L._PAALossFunction.apply(owner, None, None, 2, True, *heads)
     assert not any(t.requires_grad for t in out)
+    # the outputs behave like op results, not like views: a caller may weight a loss in place
+    out = L._PAALossFunction.apply(owner, None, None, 2, True, *heads)
+    weighted = out[0]
+    weighted *= 0.5
+    (weighted + out[1]).backward()
+    assert owner.scaled == [0.5, 1.0, 0.0] and float(weighted.detach()) == 0.5
 
 
 def test_anchor_sharing_is_detected_by_identity_or_address():

@@ -369,13 +369,20 @@ class PAALossComputation(object):
         return losses, grads, call
 
     def _rescale(self, call, grad_losses):
+        """Brings the gradients written by the forward pass (upstream gradients of one) to `grad_losses`.  A call
+        whose gradients are taken again (``retain_graph=True``) is rescaled from the factors applied last time; a
+        loss that was left out then (factor 0) cannot come back -- its gradients turn NaN rather than silently 0."""
         device = call["device"]
-        if self._ones is None or self._ones.device != device:
-            self._ones = torch.ones(3, dtype=torch.float32, device=device)
+        old = call.get("applied")
+        if old is None:
+            if self._ones is None or self._ones.device != device:
+                self._ones = torch.ones(3, dtype=torch.float32, device=device)
+            old = self._ones
         stream = _lib.stream_handle(device)
         with _lib.device_guard(device):
-            _lib.check(self._lib.paa_rescale_grads(C.byref(call["args"]), self._ones.data_ptr(),
+            _lib.check(self._lib.paa_rescale_grads(C.byref(call["args"]), old.data_ptr(),
                                                    grad_losses.data_ptr(), stream), "paa_rescale_grads")
+        call["applied"] = grad_losses
 
     def forward_backward(self, box_cls, box_regression, iou_pred, targets, anchors, grad_losses=None):
         """Fused training step without autograd bookkeeping: returns ``(losses[3], grads)`` where

@@ -269,6 +269,14 @@ def test_upstream_gradient_scaling():
     for k, t in enumerate(cls + reg + iou):
         w = (2.0, 3.0, 0.5)[k // L]
         torch.testing.assert_close(t.grad, g1[k] * w, rtol=1e-6, atol=1e-12)
+    # gradients of one call taken twice (retain_graph) with different upstream weights
+    heads = cls + reg + iou
+    l = ev(cls, reg, iou, targets, anchors, None)
+    first = [g.clone() for g in torch.autograd.grad(2.0 * l[0] + 3.0 * l[1] + 0.5 * l[2], heads, retain_graph=True)]
+    second = torch.autograd.grad(l[0] + 0.25 * l[1] + 4.0 * l[2], heads)
+    for k in range(len(heads)):
+        torch.testing.assert_close(first[k], g1[k] * (2.0, 3.0, 0.5)[k // L], rtol=1e-6, atol=1e-12)
+        torch.testing.assert_close(second[k], g1[k] * (1.0, 0.25, 4.0)[k // L], rtol=2e-6, atol=1e-12)
 
 
 def test_candidate_pool_overflow_falls_back_to_tile_scan(monkeypatch):

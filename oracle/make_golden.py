@@ -50,10 +50,11 @@ def to_ref_inputs(ref, batch):
     return targets, anchors
 
 
-def run_reference_loss(batch, use_iou_pred=True, with_grad=True):
-    """Runs the reference's PAALossComputation on CPU; returns a dict of numpy arrays."""
+def run_reference_loss(batch, use_iou_pred=True, with_grad=True, **paa_overrides):
+    """Runs the reference's PAALossComputation on CPU; returns a dict of numpy arrays.  ``paa_overrides`` are
+    MODEL.PAA keys (TOPK, IOU_THRESHOLD, LOSS_GAMMA / LOSS_ALPHA as 1-tuples, REG_LOSS_WEIGHT, ...)."""
     ref = ref_shim.load_reference()
-    cfg = ref_shim.make_cfg(USE_IOU_PRED=use_iou_pred)
+    cfg = ref_shim.make_cfg(USE_IOU_PRED=use_iou_pred, **paa_overrides)
     ev = ref.loss.make_paa_loss_evaluator(cfg, ref.BoxCoder(cfg))
     targets, anchors = to_ref_inputs(ref, batch)
     fits = []

@@ -48,3 +48,52 @@ def test_post_path_live():
     assert np.array_equal(dl, el)
     np.testing.assert_allclose(ds, es, rtol=1e-6)
     np.testing.assert_allclose(db, eb, rtol=1e-5, atol=1e-3)
+
+
+def _compare_loss_path(batch, oracle_kw, ref_kw, grad_rtol=1e-6):
+    from oracle import make_golden, paa_oracle
+    from tests.helpers import flat_levels
+    ref = make_golden.run_reference_loss(batch, **ref_kw)
+    losses, grads, asg = paa_oracle.assign_and_loss(batch.box_cls, batch.box_regression, batch.iou_pred,
+                                                    batch.gt_boxes, batch.gt_labels, batch.anchors,
+                                                    params=paa_oracle.default_params(**oracle_kw))
+    assert np.array_equal(asg.matched_idx.numpy(), ref["matched_idx"])
+    assert np.array_equal(asg.combined_loss.numpy(), ref["combined_loss"])
+    assert np.array_equal(asg.paa_labels.numpy(), ref["paa_labels"])
+    np.testing.assert_allclose([float(x) for x in losses], ref["losses"], rtol=1e-7)
+    np.testing.assert_allclose(flat_levels(grads.box_cls), ref["grad_cls"], rtol=grad_rtol, atol=1e-10)
+    np.testing.assert_allclose(flat_levels(grads.box_regression), ref["grad_reg"], rtol=grad_rtol, atol=1e-10)
+    return ref
+
+
+@pytest.mark.parametrize("oracle_kw,ref_kw", [
+    (dict(topk=3), dict(TOPK=3)),
+    (dict(topk=20), dict(TOPK=20)),
+    (dict(iou_threshold=0.3), dict(IOU_THRESHOLD=0.3)),
+    (dict(gamma=1.5, alpha=0.4), dict(LOSS_GAMMA=(1.5,), LOSS_ALPHA=(0.4,))),
+    (dict(reg_loss_weight=2.0, iou_loss_weight=1.0), dict(REG_LOSS_WEIGHT=2.0, IOU_LOSS_WEIGHT=1.0)),
+], ids=["topk3", "topk20", "iou_thr0.3", "gamma1.5_alpha0.4", "loss_weights"])
+def test_loss_path_live_other_parameters(oracle_kw, ref_kw):
+    """The parameters the GPU parity tests vary (tests/test_gpu_loss.py: TOPK 3 / 20, gamma / alpha) and the other
+    cfg keys the evaluator reads (loss.py:34-47): the restatement follows the reference for each of them."""
+    from paa_b200 import synthetic
+    b = synthetic.make_batch(seed=34, num_images=2, image_hw=(288, 352), gt_per_image=(3, 10))
+    _compare_loss_path(b, oracle_kw, ref_kw)
+
+
+def test_loss_path_live_crowded_image():
+    """More ground-truth boxes in one image than the kernels keep in one shared-memory GT list (128): the recorded
+    reference still agrees with the restatement bit for bit (ties between overlapping GTs go to the first maximum,
+    matcher.py:71 / loss.py:120)."""
+    from paa_b200 import synthetic
+    b = synthetic.make_batch(seed=35, num_images=1, image_hw=(416, 544), gt_per_image=140)
+    ref = _compare_loss_path(b, {}, {})
+    assert ref["gmm_n"].shape[0] > 0
+
+
+def test_loss_path_live_c1_full_resolution():
+    """BASELINE.json configs[0] (C1): 2 images of 800x1333 (22 400 anchors), 20 GT each, on the CPU."""
+    from paa_b200 import synthetic
+    b = synthetic.make_batch(seed=1000, num_images=2, image_hw=(800, 1333), gt_per_image=20)
+    assert b.num_anchors == 22400
+    _compare_loss_path(b, {}, {})

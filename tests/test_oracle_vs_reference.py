@@ -97,3 +97,32 @@ def test_loss_path_live_c1_full_resolution():
     b = synthetic.make_batch(seed=1000, num_images=2, image_hw=(800, 1333), gt_per_image=20)
     assert b.num_anchors == 22400
     _compare_loss_path(b, {}, {})
+
+
+@pytest.mark.parametrize("ref_kw,oracle_kw", [
+    (dict(score_voting=False), dict(score_voting=False)),
+    (dict(use_iou_pred=False), dict()),
+    (dict(detections_per_img=7), dict(detections_per_img=7)),
+    (dict(pre_nms_top_n=40), dict(pre_nms_top_n=40)),
+], ids=["no_voting", "no_iou_pred", "cut_to_7", "top40_per_level"])
+def test_post_path_live_variants(ref_kw, oracle_kw):
+    """PAAPostProcessor without score voting, without the IoU-prediction map, with a tight detections-per-image cut
+    (kthvalue rule, inference.py:130-142) and a tight per-level cap: the restatement against the live reference."""
+    from oracle import make_golden, post_oracle
+    from paa_b200 import synthetic
+    b = synthetic.make_inference_batch(seed=36, num_images=2, image_hw=(320, 384), n_objects=7)
+    kw = dict(pre_nms_top_n=150)
+    kw.update(ref_kw)
+    ref = make_golden.run_reference_post(b, **kw)
+    okw = dict(pre_nms_top_n=150)
+    okw.update(oracle_kw)
+    iou = b.iou_pred if kw.get("use_iou_pred", True) else None
+    res = post_oracle.postprocess(b.box_cls, b.box_regression, iou, b.anchors, b.image_sizes,
+                                  post_oracle.default_params(**okw))
+    for i in range(2):
+        db, ds, dl = post_oracle.canonical_rows(res[i].boxes, res[i].scores, res[i].labels)
+        eb, es, el = post_oracle.canonical_rows(ref["det_boxes_%d" % i], ref["det_scores_%d" % i],
+                                                ref["det_labels_%d" % i])
+        assert np.array_equal(dl, el)
+        np.testing.assert_allclose(ds, es, rtol=1e-6)
+        np.testing.assert_allclose(db, eb, rtol=1e-5, atol=1e-3)

@@ -76,19 +76,24 @@ def dist_env():
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port of the reference path (bench.py is one of the places allowed to run it)
 # ------------------------------------------------------------------------------------------------
-def cpu_port_images_per_sec(batch, n_images, repeats, warmup=1):
+def cpu_port_images_per_sec(batch, n_images, repeats, warmup=1, time_budget_s=None):
+    """Median time of `repeats` steps of the CPU port after `warmup` untimed ones; stops early (after at least one
+    timed step) once `time_budget_s` of wall clock is spent, so that the arm stays bounded on a slow host."""
     from oracle import paa_oracle
     torch.set_num_threads(os.cpu_count() or 1)
     sl = slice(0, n_images)
     args = ([t[sl] for t in batch.box_cls], [t[sl] for t in batch.box_regression],
             [t[sl] for t in batch.iou_pred], batch.gt_boxes[sl], batch.gt_labels[sl], batch.anchors)
     times = []
+    begin = time.perf_counter()
     for it in range(warmup + repeats):
         t0 = time.perf_counter()
         paa_oracle.assign_and_loss(*args, with_grad=True)
         dt = time.perf_counter() - t0
         if it >= warmup:
             times.append(dt)
+        if time_budget_s is not None and times and time.perf_counter() - begin > time_budget_s:
+            break
     return n_images / statistics.median(times), times
 
 
@@ -100,11 +105,13 @@ def run_reference_arm(args):
     from paa_b200 import synthetic
     n = min(CPU_SAMPLE_IMAGES, args.images_per_gpu)
     batch = synthetic.make_batch(seed=SEED_BASE, num_images=n, image_hw=IMAGE_HW, gt_per_image=GT_RANGE)
-    steps = max(1, min(args.steps, 5))
-    warm = max(1, min(args.warmup, 1))
-    ips, times = cpu_port_images_per_sec(batch, n, steps, warm)
+    # K steps and W warm-up steps as asked, each a 2-image sample (~0.5-1.5 s of CPU work); a wall-clock budget
+    # keeps the whole arm within a couple of minutes on any host, and the line reports the steps actually timed
+    warm = max(1, min(args.warmup, 3))
+    ips, times = cpu_port_images_per_sec(batch, n, max(1, args.steps), warm, time_budget_s=90.0)
+    steps = len(times)
     cores = torch.get_num_threads()
-    sample = "%d of the %d images/GPU of the workload per step (seed %d), fwd+bwd, %d timed steps" % (
+    sample = "%d of the %d images/GPU of the workload per step (seed %d), fwd+bwd, %d timed steps (median)" % (
         n, args.images_per_gpu, SEED_BASE, steps)
     line = {
         "impl": "reference", "metric": METRIC, "value": ips, "unit": UNIT, "n_gpus": args.gpus,

@@ -11,14 +11,22 @@ from paa_b200 import synthetic
 pytestmark = pytest.mark.skipif(not ref_shim.reference_available(), reason="reference tree not mounted")
 
 
-@pytest.mark.parametrize("seed,hw,gt,ptype", [(61, (384, 512), (2, 7), "ATSS"), (62, (512, 640), (3, 12), "ATSS"),
-                                              (63, (384, 512), (2, 7), "SSC"), (64, (512, 640), (3, 12), "IoU")])
-def test_atss_oracle_is_the_reference(seed, hw, gt, ptype):
+@pytest.mark.parametrize("seed,hw,gt,ptype,other", [
+    (61, (384, 512), (2, 7), "ATSS", {}), (62, (512, 640), (3, 12), "ATSS", {}),
+    (63, (384, 512), (2, 7), "SSC", {}), (64, (512, 640), (3, 12), "IoU", {}),
+    # what tests/test_gpu_atss_loss.py runs the kernels with beyond the defaults
+    (68, (512, 640), (5, 40), "IoU", dict(fg_iou_threshold=0.3, bg_iou_threshold=0.2)),
+    (69, (384, 512), (130, 150), "IoU", {}),
+    (70, (384, 512), (3, 12), "ATSS", dict(topk=5, reg_loss_weight=1.0, gamma=1.5, alpha=0.4)),
+])
+def test_atss_oracle_is_the_reference(seed, hw, gt, ptype, other):
     ref = ref_shim.load_reference()
     from paa_core.modeling.rpn.atss import loss as aloss
     ns = types.SimpleNamespace
-    cfg = ns(MODEL=ns(ATSS=ns(LOSS_GAMMA=(2.0,), LOSS_ALPHA=(0.25,), FG_IOU_THRESHOLD=0.5, BG_IOU_THRESHOLD=0.4,
-                              POSITIVE_TYPE=ptype, TOPK=9, REG_LOSS_WEIGHT=2.0, REGRESSION_TYPE="BOX")))
+    prm = atss_oracle.default_params(positive_type=ptype, **other)
+    cfg = ns(MODEL=ns(ATSS=ns(LOSS_GAMMA=(prm.gamma,), LOSS_ALPHA=(prm.alpha,), FG_IOU_THRESHOLD=prm.fg_iou_threshold,
+                              BG_IOU_THRESHOLD=prm.bg_iou_threshold, POSITIVE_TYPE=ptype, TOPK=prm.topk,
+                              REG_LOSS_WEIGHT=prm.reg_loss_weight, REGRESSION_TYPE="BOX")))
     ev = aloss.ATSSLossComputation(cfg, ref.BoxCoder(cfg))
     b = synthetic.make_batch(seed=seed, num_images=2, image_hw=hw, gt_per_image=gt)
     cls = [t.clone().requires_grad_(True) for t in b.box_cls]
@@ -34,7 +42,7 @@ def test_atss_oracle_is_the_reference(seed, hw, gt, ptype):
     rl = ev(cls, reg, ctr, targets, anchors)
     sum(rl).backward()
     ol, og, asg = atss_oracle.assign_and_loss(b.box_cls, b.box_regression, b.iou_pred, b.gt_boxes, b.gt_labels,
-                                              b.anchors, atss_oracle.default_params(positive_type=ptype))
+                                              b.anchors, prm)
     assert asg.num_pos > 0 and (ptype != "IoU" or (asg.labels == -1).any())
     for i in range(b.num_images):
         assert torch.equal(labels[i].long(), asg.labels[i])

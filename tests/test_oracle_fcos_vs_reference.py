@@ -24,6 +24,9 @@ def fcos_batch(seed, hw, gt, num_images=2):
     (81, (320, 416), (2, 7), 0.0, "iou", False),
     (82, (384, 512), (3, 12), 1.5, "giou", True),
     (83, (320, 416), (2, 7), 0.0, "linear_iou", False),
+    # the other shapes tests/test_gpu_fcos_loss.py runs the kernels on: crowded images, centre sampling at full size
+    (83, (384, 512), (130, 150), 0.0, "linear_iou", False),
+    (82, (800, 1333), (5, 40), 1.5, "giou", True),
 ])
 def test_fcos_oracle_is_the_reference(seed, hw, gt, radius, loss_type, norm):
     ref_shim.load_reference()
@@ -59,3 +62,30 @@ def test_fcos_oracle_is_the_reference(seed, hw, gt, radius, loss_type, norm):
     assert [float(x) for x in rl] == [float(x) for x in ol]
     for a, g in zip(cls + reg + ctr, og.box_cls + og.box_regression + og.centerness):
         assert torch.equal(a.grad if a.grad is not None else torch.zeros_like(a), g)
+
+
+def test_fcos_oracle_without_positives_is_the_reference():
+    """A GT that contains no location: every label is background and the regression / centerness losses are the
+    empty sums of fcos/loss.py:274-277 -- the case tests/test_gpu_fcos_loss.py::test_fcos_loss_without_positives runs."""
+    ref_shim.load_reference()
+    from paa_core.modeling.rpn.fcos import loss as floss
+    from paa_core.structures.bounding_box import BoxList
+    ns = types.SimpleNamespace
+    cfg = ns(MODEL=ns(FCOS=ns(LOSS_GAMMA=(2.0,), LOSS_ALPHA=(0.25,), FPN_STRIDES=[8, 16, 32, 64, 128],
+                              CENTER_SAMPLING_RADIUS=0.0, IOU_LOSS_TYPE="iou", NORM_REG_TARGETS=False)))
+    ev = floss.make_fcos_loss_evaluator(cfg)
+    b, locations = fcos_batch(85, (320, 416), 1, num_images=1)
+    b.gt_boxes[0] = torch.tensor([[13.0, 13.0, 18.0, 18.0]])
+    cls = [t.clone().requires_grad_(True) for t in b.box_cls]
+    reg = [t.clone().requires_grad_(True) for t in b.box_regression]
+    ctr = [t.clone().requires_grad_(True) for t in b.iou_pred]
+    t = BoxList(b.gt_boxes[0], b.image_sizes[0])
+    t.add_field("labels", b.gt_labels[0])
+    rl = ev(locations, cls, reg, ctr, [t])
+    sum(rl).backward()
+    ol, og, asg = fcos_oracle.assign_and_loss(b.box_cls, b.box_regression, b.iou_pred, b.gt_boxes, b.gt_labels,
+                                              locations, fcos_oracle.default_params())
+    assert asg.num_pos == 0
+    assert [float(x.detach()) for x in rl] == [float(x) for x in ol]
+    for a, g in zip(cls, og.box_cls):
+        assert torch.equal(a.grad, g)

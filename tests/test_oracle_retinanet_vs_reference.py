@@ -12,14 +12,23 @@ from paa_b200 import synthetic
 pytestmark = pytest.mark.skipif(not ref_shim.reference_available(), reason="reference tree not mounted")
 
 
-@pytest.mark.parametrize("seed,hw,gt", [(71, (320, 416), (2, 7)), (72, (384, 512), (3, 12))])
-def test_retinanet_oracle_is_the_reference(seed, hw, gt):
+OTHER = dict(fg_iou_threshold=0.6, bg_iou_threshold=0.3, bbox_reg_beta=0.25, bbox_reg_weight=1.0, gamma=1.5, alpha=0.4)
+
+
+@pytest.mark.parametrize("seed,hw,gt,other", [(71, (320, 416), (2, 7), {}), (72, (384, 512), (3, 12), {}),
+                                              (73, (384, 512), (130, 150), OTHER), (74, (320, 416), (2, 7), OTHER)],
+                         ids=["defaults-a", "defaults-b", "other-parameters-crowded", "other-parameters"])
+def test_retinanet_oracle_is_the_reference(seed, hw, gt, other):
+    """`other`: the thresholds / beta / normaliser / focal parameters (and the > 128 GT images) that
+    tests/test_gpu_retinanet_loss.py runs the kernels with."""
     ref = ref_shim.load_reference()
     from paa_core.modeling.box_coder import BoxCoder
     from paa_core.modeling.rpn.retinanet import loss as rloss
     ns = types.SimpleNamespace
-    cfg = ns(MODEL=ns(RETINANET=ns(LOSS_GAMMA=(2.0,), LOSS_ALPHA=(0.25,), FG_IOU_THRESHOLD=0.5, BG_IOU_THRESHOLD=0.4,
-                                   BBOX_REG_BETA=0.11, BBOX_REG_WEIGHT=4.0)))
+    prm = retinanet_oracle.default_params(**other)
+    cfg = ns(MODEL=ns(RETINANET=ns(LOSS_GAMMA=(prm.gamma,), LOSS_ALPHA=(prm.alpha,),
+                                   FG_IOU_THRESHOLD=prm.fg_iou_threshold, BG_IOU_THRESHOLD=prm.bg_iou_threshold,
+                                   BBOX_REG_BETA=prm.bbox_reg_beta, BBOX_REG_WEIGHT=prm.bbox_reg_weight)))
     ev = rloss.make_retinanet_loss_evaluator(cfg, BoxCoder(weights=(10.0, 10.0, 5.0, 5.0)))
     b = synthetic.make_retinanet_batch(seed=seed, num_images=2, image_hw=hw, gt_per_image=gt)
     cls = [t.clone().requires_grad_(True) for t in b.box_cls]
@@ -34,7 +43,8 @@ def test_retinanet_oracle_is_the_reference(seed, hw, gt):
     labels, reg_targets = ev.prepare_targets([cat_boxlist(a) for a in anchors], targets)
     rl = ev(anchors, cls, reg, targets)
     sum(rl).backward()
-    ol, og, asg = retinanet_oracle.assign_and_loss(b.box_cls, b.box_regression, b.gt_boxes, b.gt_labels, b.anchors)
+    ol, og, asg = retinanet_oracle.assign_and_loss(b.box_cls, b.box_regression, b.gt_boxes, b.gt_labels, b.anchors,
+                                                   prm)
     assert (asg.labels == -1).any() and (asg.labels > 0).any()
     for i in range(b.num_images):
         assert torch.equal(labels[i].long(), asg.labels[i])

@@ -126,3 +126,17 @@ def test_post_path_live_variants(ref_kw, oracle_kw):
         assert np.array_equal(dl, el)
         np.testing.assert_allclose(ds, es, rtol=1e-6)
         np.testing.assert_allclose(db, eb, rtol=1e-5, atol=1e-3)
+
+
+def test_loss_path_live_random_shapes():
+    """Seeded sweep over ragged shapes (image sides that are not multiples of the strides, 1-3 images, 1-40 GT per
+    image, trained-like and untrained heads): matched indices, anchor scores and PAA labels bit for bit, losses and
+    gradients to rounding.  (A 300-case run of the same sweep found no difference.)"""
+    from paa_b200 import synthetic
+    rng = np.random.default_rng(2024)
+    for _ in range(24):
+        kw = dict(seed=int(rng.integers(0, 1 << 30)), num_images=int(rng.integers(1, 4)),
+                  image_hw=(int(rng.integers(4, 16)) * 32 - int(rng.integers(0, 31)),
+                            int(rng.integers(4, 16)) * 32 - int(rng.integers(0, 31))),
+                  gt_per_image=(1, int(rng.choice([1, 2, 5, 15, 40]))), trained_like=bool(rng.integers(0, 2)))
+        _compare_loss_path(synthetic.make_batch(**kw), {}, {})

@@ -72,3 +72,58 @@ def test_single_process_is_a_noop(monkeypatch):
     assert get_num_gpus() == 1
     t = torch.tensor([3.0, 1.5], dtype=torch.float64)
     assert reduce_normalisers(t) is t and t.tolist() == [3.0, 1.5]
+
+
+# ---- the reference itself under WORLD_SIZE = 2 (only where /root/reference is mounted) -----------------------
+def _rank_share(b, rank, world):
+    import dataclasses
+    per = b.num_images // world
+    sl = slice(rank * per, (rank + 1) * per)
+    return dataclasses.replace(b, image_sizes=b.image_sizes[sl], gt_boxes=b.gt_boxes[sl], gt_labels=b.gt_labels[sl],
+                               box_cls=[t[sl] for t in b.box_cls], box_regression=[t[sl] for t in b.box_regression],
+                               iou_pred=[t[sl] for t in b.iou_pred])
+
+
+def _reference_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), WORLD_SIZE=str(world), RANK=str(rank))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import make_golden
+        b = synthetic.make_batch(seed=52, num_images=4, image_hw=(224, 288), gt_per_image=(2, 9))
+        ref = make_golden.run_reference_loss(_rank_share(b, rank, world))      # loss.py:18-28,321,338 over gloo
+        np.savez(os.path.join(out_dir, "ref_rank%d.npz" % rank), losses=ref["losses"], grad_cls=ref["grad_cls"],
+                 grad_reg=ref["grad_reg"], grad_iou=ref["grad_iou"], paa_labels=ref["paa_labels"])
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_reference_under_two_ranks_matches_the_oracles_normalisation(tmp_path):
+    """The unmodified reference evaluator run by two gloo ranks on two halves of a batch (its own `reduce_sum`,
+    loss.py:22-28, averaging by WORLD_SIZE, loss.py:322,338) against the oracle's stage 5 with the summed
+    normalisers -- the rule the CUDA path's exchange implements (`PaaLossArgs.world_size`)."""
+    from oracle import ref_shim
+    if not ref_shim.reference_available():
+        pytest.skip("reference tree not mounted")
+    from tests.helpers import flat_levels
+    world = 2
+    mp.spawn(_reference_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    b = synthetic.make_batch(seed=52, num_images=4, image_hw=(224, 288), gt_per_image=(2, 9))
+    shares = [_rank_share(b, r, world) for r in range(world)]
+    asgs = [paa_oracle.assign(s.box_cls, s.box_regression, s.iou_pred, s.gt_boxes, s.gt_labels, s.anchors)
+            for s in shares]
+    total_pos = float(sum(a.num_pos for a in asgs))
+    total_iou = float(sum(a.sum_iou for a in asgs))
+    assert asgs[0].num_pos != asgs[1].num_pos            # the two ranks really normalise by a shared total
+    for r in range(world):
+        ref = np.load(tmp_path / ("ref_rank%d.npz" % r))
+        s = shares[r]
+        heads = ([t.clone().requires_grad_(True) for t in s.box_cls],
+                 [t.clone().requires_grad_(True) for t in s.box_regression],
+                 [t.clone().requires_grad_(True) for t in s.iou_pred])
+        assert np.array_equal(asgs[r].paa_labels.numpy(), ref["paa_labels"])
+        losses = paa_oracle.losses(*heads, asgs[r], total_num_pos=total_pos, total_sum_iou=total_iou, world_size=world)
+        sum(losses).backward()
+        np.testing.assert_allclose([float(x.detach()) for x in losses], ref["losses"], rtol=1e-6)
+        np.testing.assert_allclose(flat_levels([t.grad for t in heads[0]]), ref["grad_cls"], rtol=1e-5, atol=1e-10)
+        np.testing.assert_allclose(flat_levels([t.grad for t in heads[1]]), ref["grad_reg"], rtol=1e-5, atol=1e-10)

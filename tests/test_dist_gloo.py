@@ -127,3 +127,83 @@ def test_reference_under_two_ranks_matches_the_oracles_normalisation(tmp_path):
         np.testing.assert_allclose([float(x.detach()) for x in losses], ref["losses"], rtol=1e-6)
         np.testing.assert_allclose(flat_levels([t.grad for t in heads[0]]), ref["grad_cls"], rtol=1e-5, atol=1e-10)
         np.testing.assert_allclose(flat_levels([t.grad for t in heads[1]]), ref["grad_reg"], rtol=1e-5, atol=1e-10)
+
+
+def _flavour_worker(rank, world, port, out_dir):
+    """The reference's ATSS and FCOS evaluators (atss/loss.py:14-23,255-268; fcos/loss.py:22-31,250-279) on this
+    rank's half of a batch, normalisers summed over gloo."""
+    import types
+    import warnings
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), WORLD_SIZE=str(world), RANK=str(rank))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        warnings.simplefilter("ignore")
+        from oracle import ref_shim
+        from tests.test_oracle_fcos_vs_reference import fcos_batch
+        ref = ref_shim.load_reference()
+        from paa_core.modeling.rpn.atss import loss as aloss
+        from paa_core.modeling.rpn.fcos import loss as floss
+        ns = types.SimpleNamespace
+        out = {}
+        # ATSS
+        b = _rank_share(synthetic.make_batch(seed=53, num_images=4, image_hw=(384, 512), gt_per_image=(2, 9)), rank, world)
+        cfg = ns(MODEL=ns(ATSS=ns(LOSS_GAMMA=(2.0,), LOSS_ALPHA=(0.25,), FG_IOU_THRESHOLD=0.5, BG_IOU_THRESHOLD=0.4,
+                                  POSITIVE_TYPE="ATSS", TOPK=9, REG_LOSS_WEIGHT=2.0, REGRESSION_TYPE="BOX")))
+        targets = []
+        for i in range(b.num_images):
+            t = ref.BoxList(b.gt_boxes[i], b.image_sizes[i])
+            t.add_field("labels", b.gt_labels[i])
+            targets.append(t)
+        anchors = [[ref.BoxList(a, b.image_sizes[i]) for a in b.anchors] for i in range(b.num_images)]
+        with torch.no_grad():
+            rl = aloss.ATSSLossComputation(cfg, ref.BoxCoder(cfg))(b.box_cls, b.box_regression, b.iou_pred, targets,
+                                                                    anchors)
+        out["atss"] = np.array([float(x) for x in rl])
+        # FCOS
+        fb, locations = fcos_batch(54, (384, 512), (2, 9), num_images=4)
+        fb = _rank_share(fb, rank, world)
+        cfg = ns(MODEL=ns(FCOS=ns(LOSS_GAMMA=(2.0,), LOSS_ALPHA=(0.25,), FPN_STRIDES=[8, 16, 32, 64, 128],
+                                  CENTER_SAMPLING_RADIUS=1.5, IOU_LOSS_TYPE="giou", NORM_REG_TARGETS=True)))
+        targets = []
+        for i in range(fb.num_images):
+            t = ref.BoxList(fb.gt_boxes[i], fb.image_sizes[i])
+            t.add_field("labels", fb.gt_labels[i])
+            targets.append(t)
+        with torch.no_grad():
+            rl = floss.make_fcos_loss_evaluator(cfg)(locations, fb.box_cls, fb.box_regression, fb.iou_pred, targets)
+        out["fcos"] = np.array([float(x) for x in rl])
+        np.savez(os.path.join(out_dir, "flavours_rank%d.npz" % rank), **out)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_reference_atss_and_fcos_under_two_ranks_match_the_oracles_normalisation(tmp_path):
+    from oracle import atss_oracle, fcos_oracle, ref_shim
+    if not ref_shim.reference_available():
+        pytest.skip("reference tree not mounted")
+    from tests.test_oracle_fcos_vs_reference import fcos_batch
+    world = 2
+    mp.spawn(_flavour_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    got = [np.load(tmp_path / ("flavours_rank%d.npz" % r)) for r in range(world)]
+    # ATSS
+    b = synthetic.make_batch(seed=53, num_images=4, image_hw=(384, 512), gt_per_image=(2, 9))
+    shares = [_rank_share(b, r, world) for r in range(world)]
+    asgs = [atss_oracle.assign(s.gt_boxes, s.gt_labels, s.anchors, atss_oracle.default_params()) for s in shares]
+    tot_pos, tot_ctr = float(sum(a.num_pos for a in asgs)), float(sum(a.sum_centerness for a in asgs))
+    for r, s in enumerate(shares):
+        with torch.no_grad():
+            ol = atss_oracle.losses(s.box_cls, s.box_regression, s.iou_pred, asgs[r], total_num_pos=tot_pos,
+                                    total_sum_centerness=tot_ctr, world_size=world)
+        np.testing.assert_allclose([float(x) for x in ol], got[r]["atss"], rtol=1e-6)
+    # FCOS
+    fb, locations = fcos_batch(54, (384, 512), (2, 9), num_images=4)
+    prm = fcos_oracle.default_params(center_sampling_radius=1.5, iou_loss_type="giou", norm_reg_targets=True)
+    shares = [_rank_share(fb, r, world) for r in range(world)]
+    asgs = [fcos_oracle.assign(s.gt_boxes, s.gt_labels, locations, prm) for s in shares]
+    tot_pos, tot_ctr = float(sum(a.num_pos for a in asgs)), float(sum(a.sum_centerness for a in asgs))
+    for r, s in enumerate(shares):
+        with torch.no_grad():
+            ol = fcos_oracle.losses(s.box_cls, s.box_regression, s.iou_pred, asgs[r], total_num_pos=tot_pos,
+                                    total_sum_centerness=tot_ctr, world_size=world)
+        np.testing.assert_allclose([float(x) for x in ol], got[r]["fcos"], rtol=1e-6)

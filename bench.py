@@ -1,33 +1,39 @@
 #!/usr/bin/env python
-"""bench.py -- PAA assign+loss images/sec on B200 (BASELINE.json metric), one JSON line on stdout.
+"""bench.py -- BASELINE.json's metric on B200, ONE JSON line on stdout.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--metric loss|post] [--config C1|C2|C3|C5 (loss) | C4 (post)] [--scaling strong|weak]
 
-Workload (config C2 of SURVEY.md 8d, BASELINE.json configs[1]): the paa_R_50_FPN_1x training shape --
-a batch of 16 images of 800x1333 (padded 800x1344 => 22 400 anchors on P3..P7), 80 classes, 1..100
-ground-truth boxes per image, TOPK 9 -- synthetic "trained-like" head outputs (paa_b200/synthetic.py).
-The whole 16-image batch runs on every GPU (weak scaling: N GPUs process 16*N images per step), and
-each rank assigns its own images; with N > 1 the two loss normalisers cross ranks in one 2-element
-NCCL all-reduce per step.
+Metric: "PAA assign+loss images/sec at 1/2/4/8 B200; NMS+voting images/sec".  The default line is the first half
+on config C2 (BASELINE.json configs[1], the paa_R_50_FPN_1x training shape) and carries the second half (config C4)
+as its `post` object; `--metric post` prints the second half as a line of its own.
 
-A step is the training-step semantics of the path: forward (assignment + three losses) AND the
-gradients w.r.t. box_cls / box_regression / iou_pred.  `value` calls the evaluator's fused
-`forward_backward` (capturable); `e2e` calls the reference-facing `PAALossComputation.__call__` +
-`torch.autograd.grad`.  Both run the same kernels.
+Workloads (synthetic, seed = 1000 * config):
+  C1  2 images of 800x1333 (22 400 anchors on P3..P7), 20 GT each           -- the reference's CPU-runnable case
+  C2  16 images of 800x1333, 1..100 GT each, TOPK 9                         -- headline
+  C3  32 images of 1333x1333 (37 606 anchors), 500 GT each                  -- dense crowd
+  C5  64 images, short side 640..800, padded to the batch maximum           -- multi-scale
+  C4  64 images of 800x1333, ~4000 candidates above 0.05 per level, 1000 kept per level, NMS 0.6, voting
+A config names a GLOBAL batch.  Default `--scaling strong` is BASELINE's own split: the global batch is sharded
+over the N ranks exactly like the reference's DistributedSampler (data/build.py:110-115; C2: 16 images on one GPU,
+2 per GPU on eight).  The weak-scaling measurement (every rank runs the whole N=1 batch on its own data) rides
+along as `weak_scaling`; `--scaling weak` swaps the two.
 
-  value : images/s with inputs resident in HBM; the step is captured once into a CUDA graph and
-          replayed; per-step CUDA events, L2 flushed between steps (not timed), max over ranks.
-  e2e   : the same step called eagerly, with each step's inputs copied from pinned host memory and
-          the three losses read back to the host inside the timed region.
-  roofline : final_loss_kernel (reads every logit once, writes its gradient once), timed per launch
-          with CUDA events inside the library during an eager pass of the same K steps.
-  cold_clean_l2, eager_api_resident : side measurements -- the graph replay from an L2 whose flush left no
-          dirty lines, and the reference-facing eager call on resident inputs (host-bound).
-  cpu_baseline : the CPU port of the reference path (oracle/, torch CPU ops + scikit-learn) on a
-          bounded sample of the same workload, rank 0 at N=1 only.
-
-`--impl reference` times that CPU port alone (the reference's own Python cannot travel to the GPU box;
-see DESIGN.md) and prints the same JSON line with "impl": "reference".
+A step of the loss metric is the training-step semantics of the path: forward (assignment + three losses) AND the
+gradients w.r.t. box_cls / box_regression / iou_pred.
+  value    : images/s with inputs resident in HBM, the step captured once in a CUDA graph and replayed; per-step CUDA
+             events, L2 flushed between steps (256 MiB write, untimed), barrier + synchronize on both sides, max over
+             ranks.
+  e2e      : the same step through the reference-facing call (`PAALossComputation.__call__` + `torch.autograd.grad`,
+             `PAAPostProcessor.forward` + BoxLists moved to the CPU) with every step's inputs copied from pinned host
+             memory and the result read back inside the timed region.
+  roofline : the WHOLE step against the HBM roofline (algorithmic bytes of SURVEY.md 8d / step time), `kernel` = the
+             kernel with the largest event time, `per_kernel` = every kernel of the step timed per launch by CUDA
+             events inside the library during an eager pass of the same steps, with its algorithmic bytes, fraction
+             and what bounds it.
+  cpu_baseline : the CPU port of the reference path (oracle/) on a bounded sample, rank 0 at N=1 only.
+`--impl reference` times that CPU port alone (the reference's own Python cannot travel to the GPU box)
+and prints the same line with "impl": "reference"; with N > 1 rank 0 alone runs it.
 """
 import argparse
 import ctypes
@@ -45,96 +51,140 @@ if ROOT not in sys.path:
 
 import torch  # noqa: E402
 
-METRIC = "PAA assign+loss images/sec"
+LOSS_METRIC = "PAA assign+loss images/sec"
+POST_METRIC = "PAA NMS+voting images/sec"
 UNIT = "images/s"
-IMAGE_HW = (800, 1333)
-GT_RANGE = (1, 100)
-SEED_BASE = 2000            # 1000 * config index (C2) + rank, SURVEY.md 8d
-CPU_SAMPLE_IMAGES = 2       # bounded sample for the CPU arm
+NUM_CLASSES = 80
+
+# name -> global batch and how paa_b200.synthetic draws it
+CONFIGS = {
+    "C1": dict(kind="loss", images=2, make=dict(seed=1000, image_hw=(800, 1333), gt_per_image=20),
+               what="C1 reference-runnable case: %d images of 800x1333 (22400 anchors, P3-P7), 80 classes, 20 GT/img"),
+    "C2": dict(kind="loss", images=16, make=dict(seed=2000, image_hw=(800, 1333), gt_per_image=(1, 100)),
+               what="C2 paa_R_50_FPN_1x training shape: %d images of 800x1333 (22400 anchors, P3-P7), 80 classes, "
+                    "1-100 GT/img"),
+    "C3": dict(kind="loss", images=32, make=dict(seed=3000, image_hw=(1333, 1333), gt_per_image=500),
+               what="C3 dense crowd: %d images of 1333x1333 (37606 anchors), 80 classes, 500 GT/img"),
+    "C5": dict(kind="loss", images=64, make=dict(seed=5000, image_hw=(0, 0), gt_per_image=(1, 100)), multiscale=True,
+               what="C5 multi-scale R-101 2x shape: %d images, short side 640-800, padded to the batch maximum, "
+                    "80 classes, 1-100 GT/img"),
+    "C4": dict(kind="post", images=64, make=dict(seed=4000, image_hw=(800, 1333), candidates_per_level=4000),
+               what="C4 PAAPostProcessor: %d images of 800x1333, ~4000 candidates above 0.05 per level, 1000 kept per "
+                    "level, 80 classes, NMS 0.6, score voting, 100 detections/img"),
+}
+C2_BATCH_KW = dict(num_images=CONFIGS["C2"]["images"], **CONFIGS["C2"]["make"])     # tests compare this batch with the oracle
+CPU_SAMPLE_IMAGES = 2       # bounded sample for the CPU arm of the loss metric
+FLUSH_BYTES = 256 << 20
+
+# The kernels of one assign+loss step: (report name, timer id in paa_b200._lib.KERNEL_IDS, what bounds it,
+# algorithmic bytes per image as a function of (A anchors, C classes), evidence for kernels that no HBM fraction
+# describes -- static, from the committed ncu --set full capture named there).
+LOSS_KERNELS = [
+    ("assign_pass1_kernel", "pass1", "hbm", lambda A, C: A * (4 * C + 16 + 12),
+     "every logit read once (class sums) with the IoU matching in its shadow"),
+    ("match_score_kernel", "match_score", "latency", lambda A, C: A * (8 + 4 + 4 + 16 + 16 + 12),
+     "dependent L2 loads per anchor, small data"),
+    ("select_gmm_kernel", "select_gmm", "latency", lambda A, C: A * 12,
+     "one warp per GT runs a serial f64 EM chain; the slowest GT of the batch decides (ncu: warps active ~14 %, "
+     "top stalls wait / short_scoreboard)"),
+    ("bulk_focal_kernel", "final_loss", "hbm", lambda A, C: A * (4 * C + 4 * C),
+     "every logit read once, its gradient written once"),
+    ("positive_terms_kernel", "positive_terms", "hbm", lambda A, C: A * (4 + 20), "24 B per anchor"),
+    ("finish_loss_kernel", "finish_loss", "latency", lambda A, C: 0, "one block folds the partial sums"),
+]
+POST_KERNELS = [
+    ("post_candidates_kernel", "post_candidates", "hbm", lambda A, C: A * (4 * C + 4 + 16 + 16),
+     "flat stream over the logits; gated elements drained through a block queue"),
+    ("post_threshold_kernel", "post_threshold", "latency", lambda A, C: 0, "histogram walk"),
+    ("post_filter_kernel", "post_filter", "latency", lambda A, C: 0, "8 B per candidate"),
+    ("post_select_kernel", "post_select", "latency", lambda A, C: 0, "radix select + bitonic sort + decode per (image, level)"),
+    ("post_group_kernel+post_class_rank_kernel", "post_rank", "latency", lambda A, C: 0, "order by (label, score)"),
+    ("post_nms_mask_kernel", "post_nms_mask", "alu", lambda A, C: 0, "64x64 bit tiles of pair IoUs where labels match"),
+    ("post_nms_scan_kernel", "post_nms_scan", "latency", lambda A, C: 0, "one warp per label run scans greedily"),
+    ("post_finish_kernel", "post_finish", "latency", lambda A, C: 0, "top-100 cut by radix select, ordered compaction"),
+    ("post_vote_kernel", "post_vote", "alu", lambda A, C: 0, "one warp per detection votes"),
+]
 
 
-def parse_args():
+def parse_args(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--images-per-gpu", type=int, default=16)
-    ap.add_argument("--no-graph", action="store_true", help="time the eager path instead of a CUDA graph")
+    ap.add_argument("--metric", default="loss", choices=["loss", "post"])
+    ap.add_argument("--config", default=None, choices=sorted(CONFIGS))
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
+    ap.add_argument("--images-per-gpu", type=int, default=None, help="override the config's per-GPU share")
+    ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-post", action="store_true", help="skip the NMS+voting side measurement")
-    return ap.parse_args()
+    ap.add_argument("--no-post", action="store_true", help="loss metric: skip the NMS+voting object")
+    ap.add_argument("--no-side", action="store_true", help="skip the side measurements (other scaling mode, eager API)")
+    args = ap.parse_args(argv)
+    if args.config is None:
+        args.config = "C4" if args.metric == "post" else "C2"
+    if CONFIGS[args.config]["kind"] != args.metric:
+        ap.error("--config %s belongs to --metric %s" % (args.config, CONFIGS[args.config]["kind"]))
+    args.warmup = max(3, args.warmup)          # timing rule: at least three warm-up steps
+    return args
 
 
 def dist_env():
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    return rank, local_rank, world
+    return (int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")),
+            int(os.environ.get("WORLD_SIZE", "1")))
+
+
+def hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return float(json.load(open(path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    return 6650.0, "B200_PROFILING.md fallback (of fallback)"
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU arm: the oracle port of the reference path (bench.py is one of the places allowed to run it)
+# workloads
 # ------------------------------------------------------------------------------------------------
-def cpu_port_images_per_sec(batch, n_images, repeats, warmup=1, time_budget_s=None):
-    """Median time of `repeats` steps of the CPU port after `warmup` untimed ones; stops early (after at least one
-    timed step) once `time_budget_s` of wall clock is spent, so that the arm stays bounded on a slow host."""
-    from oracle import paa_oracle
-    torch.set_num_threads(os.cpu_count() or 1)
-    sl = slice(0, n_images)
-    args = ([t[sl] for t in batch.box_cls], [t[sl] for t in batch.box_regression],
-            [t[sl] for t in batch.iou_pred], batch.gt_boxes[sl], batch.gt_labels[sl], batch.anchors)
-    times = []
-    begin = time.perf_counter()
-    for it in range(warmup + repeats):
-        t0 = time.perf_counter()
-        paa_oracle.assign_and_loss(*args, with_grad=True)
-        dt = time.perf_counter() - t0
-        if it >= warmup:
-            times.append(dt)
-        if time_budget_s is not None and times and time.perf_counter() - begin > time_budget_s:
-            break
-    return n_images / statistics.median(times), times
-
-
-def run_reference_arm(args):
-    """--impl reference: the reference's CPU implementation of the path (port), rank 0 only."""
-    rank, _, world = dist_env()
-    if rank != 0:
-        return 0
+def make_global_batch(name, num_images=None, seed_offset=0):
     from paa_b200 import synthetic
-    n = min(CPU_SAMPLE_IMAGES, args.images_per_gpu)
-    batch = synthetic.make_batch(seed=SEED_BASE, num_images=n, image_hw=IMAGE_HW, gt_per_image=GT_RANGE)
-    # K steps and W warm-up steps as asked, each a 2-image sample (~0.5-1.5 s of CPU work); a wall-clock budget
-    # keeps the whole arm within a couple of minutes on any host, and the line reports the steps actually timed
-    warm = max(1, min(args.warmup, 3))
-    ips, times = cpu_port_images_per_sec(batch, n, max(1, args.steps), warm, time_budget_s=90.0)
-    steps = len(times)
-    cores = torch.get_num_threads()
-    sample = "%d of the %d images/GPU of the workload per step (seed %d), fwd+bwd, %d timed steps (median)" % (
-        n, args.images_per_gpu, SEED_BASE, steps)
-    line = {
-        "impl": "reference", "metric": METRIC, "value": ips, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": steps, "warmup": warm, "ms_per_step": 1000.0 * statistics.median(times),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic",
-        "config": workload_config(args, note="CPU port of the reference path on a bounded sample"),
-        "cpu_baseline": {"value": ips, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
-    }
-    print(json.dumps(line))
-    return 0
+    c = CONFIGS[name]
+    n = num_images or c["images"]
+    kw = dict(c["make"])
+    kw["seed"] = kw["seed"] + seed_offset
+    if c["kind"] == "post":
+        return synthetic.make_inference_batch(num_images=n, **kw)
+    if c.get("multiscale"):
+        kw["per_image_hw"] = synthetic.multiscale_hw(kw["seed"], n)
+    return synthetic.make_batch(num_images=n, **kw)
 
 
-def workload_config(args, note=None):
-    cfg = {"workload": "C2 paa_R_50_FPN_1x training shape: %d images/GPU of 800x1333 (22400 anchors, P3-P7), "
-                       "80 classes, 1-100 GT/img, topk 9, forward+gradients" % args.images_per_gpu,
-           "images_per_gpu": args.images_per_gpu, "global_batch": args.images_per_gpu * args.gpus,
-           "anchors_per_image": 22400, "gt_per_image": list(GT_RANGE), "parallelism": "dp%d" % args.gpus,
-           "l2": "flushed between timed steps (256 MiB write, untimed)"}
-    if note:
-        cfg["note"] = note
+def rank_batch(args, scaling, rank, world):
+    """This rank's images under `scaling`, and (images per GPU, global images)."""
+    from paa_b200 import synthetic
+    c = CONFIGS[args.config]
+    if args.images_per_gpu:
+        return make_global_batch(args.config, args.images_per_gpu, seed_offset=rank), args.images_per_gpu, \
+            args.images_per_gpu * world
+    if scaling == "strong":
+        if c["images"] % world:
+            raise SystemExit("config %s: %d images do not split over %d GPUs" % (args.config, c["images"], world))
+        per = c["images"] // world
+        g = make_global_batch(args.config)
+        return (g if world == 1 else synthetic.slice_batch(g, rank * per, (rank + 1) * per)), per, c["images"]
+    return make_global_batch(args.config, seed_offset=rank), c["images"], c["images"] * world
+
+
+def workload_config(args, scaling, per_gpu, total, world):
+    c = CONFIGS[args.config]
+    cfg = {"workload": (c["what"] % total) + (", topk 9, forward+gradients" if c["kind"] == "loss" else ""),
+           "config": args.config, "images_per_gpu": per_gpu, "global_batch": total,
+           "parallelism": "dp%d" % world,
+           "split": ("BASELINE's split: the global batch of %d sharded over the ranks" % c["images"]) if scaling == "strong"
+           else "weak scaling: every rank runs a whole %d-image batch of its own" % per_gpu,
+           "l2": "flushed between timed steps (256 MiB write, untimed)",
+           "collective": ("none (one rank)" if world == 1 else
+                          "nvlink-peer: 16 bytes per rank stored into every peer's symmetric-memory buffer by the last "
+                          "block of select_gmm_kernel, read by norm_wait_kernel (no NCCL call on the data path)")
+           if c["kind"] == "loss" else "none (post-processing has no exchange step)"}
     return cfg
 
 
@@ -206,7 +256,7 @@ class ClockSampler(object):
         if self.nvml is not None:
             self.thread = threading.Thread(target=self._poll_nvml, daemon=True)
             self.thread.start()
-            return
+            return self
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.Q,
@@ -216,6 +266,7 @@ class ClockSampler(object):
             self.thread.start()
         except OSError:
             self.proc = None
+        return self
 
     def stop(self):
         self.stop_flag.set()
@@ -233,329 +284,619 @@ class ClockSampler(object):
 
 
 # ------------------------------------------------------------------------------------------------
-# GPU arm
+# CPU arm: the oracle port of the reference path (bench.py is one of the places allowed to run it)
 # ------------------------------------------------------------------------------------------------
-def pin(ts):
-    return [t.contiguous().pin_memory() for t in ts]
+def host_threads():
+    n = os.cpu_count() or 1
+    torch.set_num_threads(n)      # explicit: torchrun exports OMP_NUM_THREADS=1 to its children
+    return torch.get_num_threads()
 
 
-def run_ours(args):
-    import paa_b200
-    from paa_b200 import _lib, synthetic
-    from paa_b200.structures import BoxList
-    rank, local_rank, world = dist_env()
-    if not torch.cuda.is_available():
-        raise RuntimeError("bench.py needs a CUDA device: there is no CPU path for the product")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        import torch.distributed as dist
-        os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout: one JSON line only
-        dist.init_process_group("nccl", device_id=dev)
-    n_img = args.images_per_gpu
-    batch = synthetic.make_batch(seed=SEED_BASE + rank, num_images=n_img, image_hw=IMAGE_HW,
-                                 gt_per_image=GT_RANGE)
-    L = len(batch.box_cls)
-    cfg = paa_b200.default_cfg()
-    ev = paa_b200.make_paa_loss_evaluator(cfg, paa_b200.BoxCoder(cfg))
-    lib = _lib.load()
+def _timed_repeats(fn, repeats, warmup, time_budget_s):
+    times, begin = [], time.perf_counter()
+    for it in range(warmup + repeats):
+        t0 = time.perf_counter()
+        fn()
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+        if time_budget_s is not None and times and time.perf_counter() - begin > time_budget_s:
+            break
+    return times
 
-    # host (pinned) and device copies
-    h_cls, h_reg, h_iou = pin(batch.box_cls), pin(batch.box_regression), pin(batch.iou_pred)
-    h_gtb = [t.pin_memory() for t in batch.gt_boxes]
-    h_gtl = [t.pin_memory() for t in batch.gt_labels]
-    d_anchor = [a.to(dev) for a in batch.anchors]
-    anchors = [[BoxList(a, batch.image_sizes[i]) for a in d_anchor] for i in range(n_img)]
 
-    def targets_from(boxes, labels):
+def cpu_port_loss(batch, n_images, repeats, warmup=1, time_budget_s=None):
+    """(images/s, step times) of the CPU port of PAALossComputation.__call__ + backward on the first `n_images`."""
+    from oracle import paa_oracle
+    sl = slice(0, n_images)
+    a = ([t[sl] for t in batch.box_cls], [t[sl] for t in batch.box_regression], [t[sl] for t in batch.iou_pred],
+         batch.gt_boxes[sl], batch.gt_labels[sl], batch.anchors)
+    times = _timed_repeats(lambda: paa_oracle.assign_and_loss(*a, with_grad=True), repeats, warmup, time_budget_s)
+    return n_images / statistics.median(times), times
+
+
+def cpu_port_post(batch, n_images, repeats, warmup=1, time_budget_s=None):
+    """(images/s, step times) of the CPU port of PAAPostProcessor.forward on the first `n_images`."""
+    from oracle import post_oracle
+    sl = slice(0, n_images)
+    a = ([t[sl] for t in batch.box_cls], [t[sl] for t in batch.box_regression], [t[sl] for t in batch.iou_pred],
+         batch.anchors, batch.image_sizes[sl])
+    times = _timed_repeats(lambda: post_oracle.postprocess(*a), repeats, warmup, time_budget_s)
+    return n_images / statistics.median(times), times
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's CPU implementation of the path (its port, oracle/), rank 0 only; each step
+    a bounded sample of the workload."""
+    rank, _, world = dist_env()
+    if rank != 0:
+        return 0
+    cores = host_threads()
+    c = CONFIGS[args.config]
+    per_gpu = args.images_per_gpu or (c["images"] // max(1, args.gpus) if args.scaling == "strong" else c["images"])
+    total = per_gpu * max(1, args.gpus)
+    # K steps after W warm-up steps as asked, each a bounded sample (1-2 images, ~0.5-1.5 s of CPU work); the
+    # wall-clock budget only cuts a run short on a very slow host, and the line reports the steps actually timed
+    warm = args.warmup
+    if args.metric == "post":
+        n = 1
+        batch = make_global_batch(args.config, n)
+        ips, times = cpu_port_post(batch, n, max(1, args.steps), warm, time_budget_s=150.0)
+        what = "PAAPostProcessor.forward"
+    else:
+        n = min(CPU_SAMPLE_IMAGES, per_gpu)
+        batch = make_global_batch(args.config, n)
+        ips, times = cpu_port_loss(batch, n, max(1, args.steps), warm, time_budget_s=150.0)
+        what = "PAALossComputation.__call__ + backward"
+    sample = "%s on %d image(s) drawn like the workload's (seed %d) per step, %d timed steps (median), %d threads" % (
+        what, n, c["make"]["seed"], len(times), cores)
+    line = {
+        "impl": "reference", "metric": POST_METRIC if args.metric == "post" else LOSS_METRIC, "value": ips,
+        "unit": UNIT, "n_gpus": args.gpus, "steps": len(times), "warmup": warm,
+        "ms_per_step": 1000.0 * statistics.median(times), "higher_is_better": True, "scaling": args.scaling,
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, args.scaling, per_gpu, total, max(1, args.gpus)),
+        "launch": "CPU port of the reference path (oracle/), a bounded sample of the workload per step",
+        "cpu_baseline": {"value": ips, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm: shared plumbing
+# ------------------------------------------------------------------------------------------------
+class Ctx(object):
+    def __init__(self):
+        self.rank, self.local_rank, self.world = dist_env()
+        if not torch.cuda.is_available():
+            raise RuntimeError("bench.py needs a CUDA device: there is no CPU path for the product")
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.flush = torch.empty(FLUSH_BYTES, dtype=torch.uint8, device=self.dev)
+
+    def barrier(self):
+        torch.cuda.synchronize()
+        if self.world > 1:
+            torch.distributed.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(self, values):
+        t = torch.tensor(values, dtype=torch.float64, device=self.dev)
+        if self.world > 1:
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        return [float(v) for v in t]
+
+    def min_over_ranks(self, values):
+        t = torch.tensor(values, dtype=torch.float64, device=self.dev)
+        if self.world > 1:
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MIN)
+        return [float(v) for v in t]
+
+
+def capture(step, no_graph):
+    """Warm-up on a side stream, then one capture of `step` (a callable that only enqueues stream work)."""
+    if no_graph:
+        return None
+    try:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                step()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            step()
+        torch.cuda.synchronize()
+        return graph
+    except Exception as e:  # noqa: BLE001 - report and fall back to eager timing
+        sys.stderr.write("CUDA graph capture failed (%s); timing eager launches\n" % (e,))
+        torch.cuda.synchronize()
+        return None
+
+
+def timed_steps(ctx, one_step, steps, warmup):
+    """W untimed then exactly K timed steps, per-step CUDA events on the launching stream, L2 flushed before every
+    step, barrier + synchronize on both sides.  Returns the per-step times of this rank (ms)."""
+    for _ in range(warmup):
+        ctx.flush.zero_()
+        one_step()
+    ctx.barrier()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    for k in range(steps):
+        ctx.flush.zero_()
+        starts[k].record()
+        one_step()
+        ends[k].record()
+    ctx.barrier()
+    return [s.elapsed_time(e) for s, e in zip(starts, ends)]
+
+
+def per_kernel_events(ctx, lib, kernel_table, step, reps):
+    """Average device time per launch of every kernel in `kernel_table`, one kernel at a time: the library brackets
+    each launch of the chosen kernel with CUDA events on its own stream during `reps` eager steps (L2 flushed before
+    each).  The event pair serialises the launch behind its predecessor, so these are stand-alone kernel times: under
+    the graph the dependent launches overlap and the step is shorter than their sum."""
+    from paa_b200 import _lib
+    out = {}
+    for name, key, _, _, _ in kernel_table:
+        lib.paa_kernel_timing_begin(_lib.KERNEL_IDS[key])
+        for _ in range(reps):
+            ctx.flush.zero_()
+            step()
+        ms, n = ctypes.c_float(0), ctypes.c_int32(0)
+        _lib.check(lib.paa_kernel_timing_end(ctypes.byref(ms), ctypes.byref(n)), "paa_kernel_timing_end")
+        out[name] = (1000.0 * ms.value / n.value if n.value else 0.0, n.value // max(1, reps))
+    return out
+
+
+def roofline_report(kernel_table, per_kernel, A, C, n_img, step_ms, step_bytes_per_image, traffic_file):
+    peak, peak_src = hbm_peak()
+    traffic = {}
+    path = os.path.join(ROOT, "profiles", traffic_file)
+    if os.path.exists(path):
+        try:
+            traffic = json.load(open(path))
+        except ValueError:
+            traffic = {}
+    same_shape = traffic.get("images") == n_img and traffic.get("anchors_per_image") == A
+    rows, longest = [], None
+    total_us = sum(us for us, _ in per_kernel.values()) or 1.0
+    for name, _, bound, bytes_fn, why in kernel_table:
+        us, launches = per_kernel.get(name, (0.0, 0))
+        if launches == 0:
+            continue
+        b = bytes_fn(A, C) * n_img
+        row = {"kernel": name, "us": round(us, 2), "share_of_kernel_time": round(us / total_us, 4), "bound": bound,
+               "algorithmic_bytes": b, "why": why}
+        if b and us > 0:
+            row["achieved_GBps"] = round(b / (us * 1e-6) / 1e9, 1)
+            row["frac_of_hbm_peak"] = round(b / (us * 1e-6) / 1e9 / peak, 4)
+        k = traffic.get("kernels", {}).get(name) if same_shape else None
+        if k:
+            row["traffic"] = k.get("dram_read_bytes", 0) + k.get("dram_write_bytes", 0)
+            for key in ("issue_active_pct", "warps_active_pct", "dram_throughput_pct"):
+                if key in k:
+                    row["ncu_" + key] = k[key]
+        rows.append(row)
+        if longest is None or us > longest["us"]:
+            longest = row
+    achieved = step_bytes_per_image * n_img / (step_ms * 1e-3) / 1e9
+    return {"bound": "hbm", "scope": "whole step (all kernels of the path, CUDA-graph replay)",
+            "kernel": longest["kernel"] if longest else None,
+            "kernel_us": longest["us"] if longest else None, "kernel_bound": longest["bound"] if longest else None,
+            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "algorithmic_bytes_per_step": step_bytes_per_image * n_img,
+            "traffic": (sum(r.get("traffic", 0) for r in rows) or None) if same_shape else None,
+            "traffic_source": ("static: dram__bytes_read.sum + dram__bytes_write.sum summed over the step's kernels, "
+                               "ncu --set full capture of this command, profiles/%s" % traffic_file) if same_shape and traffic
+            else "no capture of this shape committed",
+            "peak_source": peak_src, "per_kernel": rows}
+
+
+# ------------------------------------------------------------------------------------------------
+# assign + loss
+# ------------------------------------------------------------------------------------------------
+class LossRun(object):
+    """One rank's share of a loss workload: resident inputs, the evaluator, the captured step."""
+
+    def __init__(self, ctx, batch, no_graph):
+        import paa_b200
+        from paa_b200 import _lib
+        from paa_b200.structures import BoxList
+        self.ctx, self.batch = ctx, batch
+        dev = ctx.dev
+        self.n_img = batch.num_images
+        self.L = len(batch.box_cls)
+        cfg = paa_b200.default_cfg()
+        self.ev = paa_b200.make_paa_loss_evaluator(cfg, paa_b200.BoxCoder(cfg))
+        self.lib = _lib.load()
+        pin = lambda ts: [t.contiguous().pin_memory() for t in ts]       # noqa: E731
+        self.h_cls, self.h_reg, self.h_iou = pin(batch.box_cls), pin(batch.box_regression), pin(batch.iou_pred)
+        self.h_gtb = [t.pin_memory() for t in batch.gt_boxes]
+        self.h_gtl = [t.pin_memory() for t in batch.gt_labels]
+        d_anchor = [a.to(dev) for a in batch.anchors]
+        self.anchors = [[BoxList(a, batch.image_sizes[i]) for a in d_anchor] for i in range(self.n_img)]
+        self.d_cls = [t.to(dev).requires_grad_(True) for t in self.h_cls]
+        self.d_reg = [t.to(dev).requires_grad_(True) for t in self.h_reg]
+        self.d_iou = [t.to(dev).requires_grad_(True) for t in self.h_iou]
+        self.d_targets = self.targets_from([t.to(dev) for t in self.h_gtb], [t.to(dev) for t in self.h_gtl])
+        self.heads = self.d_cls + self.d_reg + self.d_iou
+        for _ in range(3):
+            self.step_resident()
+        torch.cuda.synchronize()
+        self.graph = capture(self.step_resident, no_graph)
+
+    def targets_from(self, boxes, labels):
+        from paa_b200.structures import BoxList
         out = []
-        for i in range(n_img):
-            t = BoxList(boxes[i], batch.image_sizes[i])
+        for i in range(self.n_img):
+            t = BoxList(boxes[i], self.batch.image_sizes[i])
             t.add_field("labels", labels[i])
             out.append(t)
         return out
 
-    d_cls = [t.to(dev).requires_grad_(True) for t in h_cls]
-    d_reg = [t.to(dev).requires_grad_(True) for t in h_reg]
-    d_iou = [t.to(dev).requires_grad_(True) for t in h_iou]
-    d_targets = targets_from([t.to(dev) for t in h_gtb], [t.to(dev) for t in h_gtl])
-    heads = d_cls + d_reg + d_iou
+    def step_resident(self):
+        # the fused entry point of the same evaluator: losses + gradients, no autograd bookkeeping, so the whole
+        # step is capturable; identical kernels to `ev(...)` + backward (which the e2e leg times)
+        return self.ev.forward_backward(self.d_cls, self.d_reg, self.d_iou, self.d_targets, self.anchors)
 
-    def step_resident():
-        # the fused entry point of the same evaluator: losses + gradients, no autograd bookkeeping, so the
-        # whole step is capturable; identical kernels to `ev(...)` + backward (which the e2e leg times)
-        return ev.forward_backward(d_cls, d_reg, d_iou, d_targets, anchors)
-
-    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            torch.distributed.barrier()
-            torch.cuda.synchronize()
-
-    # ---- warm-up (eager) and graph capture ------------------------------------------------------
-    for _ in range(max(3, args.warmup)):
-        out = step_resident()
-    torch.cuda.synchronize()
-    graph = None
-    if not args.no_graph:
-        try:
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                for _ in range(2):
-                    step_resident()
-            torch.cuda.current_stream().wait_stream(side)
-            torch.cuda.synchronize()
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                g_out = step_resident()
-            torch.cuda.synchronize()
-        except Exception as e:  # noqa: BLE001 - report and fall back to eager timing
-            sys.stderr.write("CUDA graph capture failed (%s); timing the eager path\n" % (e,))
-            graph = None
-            torch.cuda.synchronize()
-
-    def one_step():
-        if graph is not None:
-            graph.replay()
+    def one_step(self):
+        if self.graph is not None:
+            self.graph.replay()
         else:
-            step_resident()
+            self.step_resident()
 
-    for _ in range(args.warmup):
-        flush_buf.zero_()
-        one_step()
-    barrier()
+    def step_eager_api(self):
+        losses = self.ev(self.d_cls, self.d_reg, self.d_iou, self.d_targets, self.anchors, None)
+        return torch.autograd.grad(losses[0] + losses[1] + losses[2], self.heads)
 
-    # ---- timed: K steps, per-step events, L2 flush between ----------------------------------------
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    barrier()
-    for k in range(args.steps):
-        flush_buf.zero_()
-        starts[k].record()
-        one_step()
-        ends[k].record()
-    barrier()
-    step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
-    total_ms = sum(step_ms)
+    def eager_api_ms(self, steps):
+        """`PAALossComputation.__call__` + autograd on resident inputs, back to back, wall clock between two
+        synchronisations: what a caller pays per step when nothing else keeps the GPU busy (host-bound)."""
+        for _ in range(3):
+            self.step_eager_api()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            self.step_eager_api()
+        torch.cuda.synchronize()
+        return 1000.0 * (time.perf_counter() - t0) / steps
 
-    # ---- side measurement: the same K steps from a cold but CLEAN L2 ---------------------------------
-    # The 256 MiB flush write leaves the L2 full of dirty lines whose write-back the first kernel of the step could
-    # be paying for.  Here the write is followed by a 256 MiB read of a second buffer: the workload's data is gone
-    # from L2 just the same, but the lines it evicts are clean.  Reported next to `value`, not instead of it
-    # (measured on B200: 0.1551 against 0.1562 ms per step -- the headline does not hinge on the flush style).
-    clean_ms = None
-    if world == 1:                       # single-GPU runs only: the scaling runs carry nothing but the contract
+    def exchange_check(self):
+        """N > 1: the normalisers the peer-memory exchange delivered against an NCCL all-reduce of the ranks' own
+        pairs, on every rank.  Returns (max relative difference, 1.0 if the peer path was in use else 0.0)."""
+        from paa_b200 import loss as paa_loss
+        ev = self.ev
+        ev.debug = True
         try:
-            flush_rd = torch.zeros(64 << 20, dtype=torch.int32, device=dev)
-            c_starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-            c_ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-            for k in range(args.steps):
-                flush_buf.zero_()
-                flush_rd.sum()
-                c_starts[k].record()
-                one_step()
-                c_ends[k].record()
-            torch.cuda.synchronize()
-            clean_ms = sum(s.elapsed_time(e) for s, e in zip(c_starts, c_ends))
-            del flush_rd
-        except Exception as e:  # noqa: BLE001 - a side measurement must not take the bench line down
-            sys.stderr.write("cold_clean_l2 side measurement failed: %s\n" % (e,))
-            clean_ms = None
+            ev.forward_backward(self.d_cls, self.d_reg, self.d_iou, self.d_targets, self.anchors)
+            got = ev.last_debug["normalisers"].clone()
+            want = ev.last_debug["local_normalisers"].clone()
+        finally:
+            ev.debug = False
+        torch.distributed.all_reduce(want, op=torch.distributed.ReduceOp.SUM)
+        torch.cuda.synchronize()
+        rel = float(((got - want).abs() / want.abs().clamp(min=1e-300)).max())
+        used_peer = paa_loss.PeerNormExchange.get(self.ctx.dev) is not None
+        return rel, (1.0 if used_peer else 0.0)
 
-    # ---- roofline: the dominant kernel, per-launch CUDA events inside the library, eager pass -----
-    lib.paa_kernel_timing_begin(_lib.KERNEL_IDS["final_loss"])
-    for k in range(args.steps):
-        flush_buf.zero_()
-        step_resident()
-    k_ms, k_n = ctypes.c_float(0), ctypes.c_int32(0)
-    _lib.check(lib.paa_kernel_timing_end(ctypes.byref(k_ms), ctypes.byref(k_n)), "paa_kernel_timing_end")
-    clocks = sampler.stop()
-
-    # other kernels' share (one eager pass each; reported, not part of `value`)
-    shares = {}
-    for name in ("pass1", "match_score", "select_gmm"):
-        lib.paa_kernel_timing_begin(_lib.KERNEL_IDS[name])
-        for k in range(3):
-            flush_buf.zero_()
-            step_resident()
-        ms, n = ctypes.c_float(0), ctypes.c_int32(0)
-        lib.paa_kernel_timing_end(ctypes.byref(ms), ctypes.byref(n))
-        shares[name + "_us"] = 1000.0 * ms.value / max(1, n.value)
-    shares["final_loss_us"] = 1000.0 * k_ms.value / max(1, k_n.value)
-
-    # ---- side measurement: the reference-facing call with RESIDENT inputs, eager ----------------------
-    # `PAALossComputation.__call__` + autograd on the device tensors, back to back, wall clock between two
-    # synchronisations: what a caller pays per step when nothing else keeps the GPU busy (host-bound).
-    def step_eager_api():
-        losses = ev(d_cls, d_reg, d_iou, d_targets, anchors, None)
-        return torch.autograd.grad(losses[0] + losses[1] + losses[2], heads)
-
-    eager_ms = None
-    if world == 1:
-        try:
-            for _ in range(3):
-                step_eager_api()
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            for k in range(args.steps):
-                step_eager_api()
-            torch.cuda.synchronize()
-            eager_ms = 1000.0 * (time.perf_counter() - t0)
-        except Exception as e:  # noqa: BLE001
-            sys.stderr.write("eager_api_resident side measurement failed: %s\n" % (e,))
-            eager_ms = None
-
-    # ---- e2e: host buffers in, losses out, eager, public API -------------------------------------
-    # The step's inputs live in pinned host memory, packed the way a collate function would leave them (one
-    # block for the head outputs, one each for the boxes / labels of all images).  Every step copies them to
-    # the device on a copy stream into one of two device buffers (so the copy of step k+1 overlaps the
-    # kernels of step k), calls the reference-facing evaluator + autograd on views of that buffer, and
-    # reads the three losses back into pinned memory.
-    heads_h = h_cls + h_reg + h_iou
-    sizes = [t.numel() for t in heads_h]
-    h_pack = torch.empty(sum(sizes), dtype=torch.float32).pin_memory()
-    o = 0
-    for t, sz in zip(heads_h, sizes):
-        h_pack[o:o + sz].copy_(t.reshape(-1))
-        o += sz
-    gt_counts = [int(t.shape[0]) for t in h_gtb]
-    h_boxes = torch.cat(h_gtb, 0).contiguous().pin_memory()
-    h_labels = torch.cat(h_gtl, 0).contiguous().pin_memory()
-    h_losses = torch.empty(3, dtype=torch.float32).pin_memory()
-    h2d_bytes = sum(t.numel() * t.element_size() for t in (h_pack, h_boxes, h_labels))
-    copy_stream = torch.cuda.Stream()
-    slots = [dict(pack=torch.empty_like(h_pack, device=dev), boxes=torch.empty_like(h_boxes, device=dev),
-                  labels=torch.empty_like(h_labels, device=dev), copied=torch.cuda.Event(),
-                  free=torch.cuda.Event()) for _ in range(2)]
-    state = {"k": 0}
-
-    def enqueue_copy(k):
-        sl = slots[k % 2]
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(sl["free"])          # the step that last used this slot has finished
-            sl["pack"].copy_(h_pack, non_blocking=True)
-            sl["boxes"].copy_(h_boxes, non_blocking=True)
-            sl["labels"].copy_(h_labels, non_blocking=True)
-            sl["copied"].record(copy_stream)
-
-    def step_e2e():
-        k = state["k"]
-        state["k"] = k + 1
-        sl = slots[k % 2]
-        enqueue_copy(k + 1)                              # next step's inputs travel while this step computes
-        main = torch.cuda.current_stream()
-        main.wait_event(sl["copied"])
-        views, o = [], 0
+    def e2e(self, steps, warmup):
+        """Host buffers in, losses out, eager, public API.  The step's inputs live in pinned host memory, packed the
+        way a collate function would leave them (one block for the head outputs, one each for the boxes / labels of all
+        images).  Every step copies them to the device on a copy stream into one of two device buffers (the copy of
+        step k+1 overlaps the kernels of step k), calls the reference-facing evaluator + autograd on views of that
+        buffer, and reads the three losses back into pinned memory.  Returns (device ms, wall ms, h2d bytes, d2h)."""
+        ctx, dev, L, ev = self.ctx, self.ctx.dev, self.L, self.ev
+        heads_h = self.h_cls + self.h_reg + self.h_iou
+        sizes = [t.numel() for t in heads_h]
+        h_pack = torch.empty(sum(sizes), dtype=torch.float32).pin_memory()
+        o = 0
         for t, sz in zip(heads_h, sizes):
-            views.append(sl["pack"][o:o + sz].view(t.shape).requires_grad_(True))
+            h_pack[o:o + sz].copy_(t.reshape(-1))
             o += sz
-        cls, reg, iou = views[:L], views[L:2 * L], views[2 * L:]
-        tg = targets_from(list(sl["boxes"].split(gt_counts)), list(sl["labels"].split(gt_counts)))
-        losses = ev(cls, reg, iou, tg, anchors, None)
-        grads = torch.autograd.grad(losses[0] + losses[1] + losses[2], cls + reg + iou)
-        h_losses.copy_(torch.stack([l.detach() for l in losses]), non_blocking=True)
-        sl["free"].record(main)
-        return grads
+        gt_counts = [int(t.shape[0]) for t in self.h_gtb]
+        h_boxes = torch.cat(self.h_gtb, 0).contiguous().pin_memory()
+        h_labels = torch.cat(self.h_gtl, 0).contiguous().pin_memory()
+        h_losses = torch.empty(3, dtype=torch.float32).pin_memory()
+        h2d_bytes = sum(t.numel() * t.element_size() for t in (h_pack, h_boxes, h_labels))
+        copy_stream = torch.cuda.Stream()
+        slots = [dict(pack=torch.empty_like(h_pack, device=dev), boxes=torch.empty_like(h_boxes, device=dev),
+                      labels=torch.empty_like(h_labels, device=dev), copied=torch.cuda.Event(),
+                      free=torch.cuda.Event()) for _ in range(2)]
+        state = {"k": 0}
 
-    for sl in slots:
-        sl["free"].record(torch.cuda.current_stream())
-    enqueue_copy(0)
-    for _ in range(max(3, args.warmup)):
-        step_e2e()
-    barrier()
-    e_start = torch.cuda.Event(enable_timing=True)
-    e_end = torch.cuda.Event(enable_timing=True)
-    t0 = time.perf_counter()
-    e_start.record()
-    for k in range(args.steps):
-        step_e2e()
-    e_end.record()
-    barrier()
-    e2e_wall_ms = 1000.0 * (time.perf_counter() - t0)
-    e2e_ms = max(e_start.elapsed_time(e_end), 0.0)
+        def enqueue_copy(k):
+            sl = slots[k % 2]
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(sl["free"])          # the step that last used this slot has finished
+                sl["pack"].copy_(h_pack, non_blocking=True)
+                sl["boxes"].copy_(h_boxes, non_blocking=True)
+                sl["labels"].copy_(h_labels, non_blocking=True)
+                sl["copied"].record(copy_stream)
 
-    # ---- max over ranks ---------------------------------------------------------------------------
-    vals = torch.tensor([total_ms, e2e_ms, e2e_wall_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        torch.distributed.all_reduce(vals, op=torch.distributed.ReduceOp.MAX)
-    total_ms, e2e_ms, e2e_wall_ms = [float(v) for v in vals]
-    images = n_img * world * args.steps
-    value = images / (total_ms / 1000.0)
-    e2e_value = images / (max(e2e_ms, e2e_wall_ms) / 1000.0)
+        def step():
+            k = state["k"]
+            state["k"] = k + 1
+            sl = slots[k % 2]
+            enqueue_copy(k + 1)                              # next step's inputs travel while this step computes
+            main = torch.cuda.current_stream()
+            main.wait_event(sl["copied"])
+            views, o = [], 0
+            for t, sz in zip(heads_h, sizes):
+                views.append(sl["pack"][o:o + sz].view(t.shape).requires_grad_(True))
+                o += sz
+            cls, reg, iou = views[:L], views[L:2 * L], views[2 * L:]
+            tg = self.targets_from(list(sl["boxes"].split(gt_counts)), list(sl["labels"].split(gt_counts)))
+            losses = ev(cls, reg, iou, tg, self.anchors, None)
+            grads = torch.autograd.grad(losses[0] + losses[1] + losses[2], cls + reg + iou)
+            h_losses.copy_(torch.stack([l.detach() for l in losses]), non_blocking=True)
+            sl["free"].record(main)
+            return grads
 
-    # ---- roofline numbers -------------------------------------------------------------------------
+        for sl in slots:
+            sl["free"].record(torch.cuda.current_stream())
+        enqueue_copy(0)
+        for _ in range(warmup):
+            step()
+        ctx.barrier()
+        e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e_start.record()
+        for _ in range(steps):
+            step()
+        e_end.record()
+        ctx.barrier()
+        wall_ms = 1000.0 * (time.perf_counter() - t0)
+        return max(e_start.elapsed_time(e_end), 0.0), wall_ms, h2d_bytes, 12
+
+
+def measure_loss(ctx, args, scaling, full):
+    """One scaling mode of the loss metric on this rank; everything that enters the JSON line is already the
+    max over ranks.  `full`: also the per-kernel pass, e2e and the side measurements."""
+    batch, per_gpu, total = rank_batch(args, scaling, ctx.rank, ctx.world)
+    run = LossRun(ctx, batch, args.no_graph)
     A = batch.num_anchors
-    # algorithmic bytes of bulk_focal_kernel per image: every logit read once and its gradient
-    # written once (A*4C each); the regression / IoU-prediction gradients belong to positive_terms_kernel
-    kernel_bytes_per_image = A * (4 * 80 + 4 * 80)
-    kernel_ms = k_ms.value / max(1, k_n.value)
-    achieved = kernel_bytes_per_image * n_img / (kernel_ms / 1000.0) / 1e9 if kernel_ms > 0 else 0.0
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peak = float(json.load(open(peaks_path))["hbm_gbs"])
-        peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)"
-    else:
-        peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
-    # DRAM bytes of one launch of the same kernel from the committed ncu --set full capture (profiles/)
-    traffic = None
-    traffic_path = os.path.join(ROOT, "profiles", "r1_traffic.json")
-    if os.path.exists(traffic_path) and n_img == 16:
-        try:
-            k = json.load(open(traffic_path))["kernels"]["bulk_focal_kernel<1, 1>"]
-            traffic = k["dram_read_bytes"] + k["dram_write_bytes"]
-        except (KeyError, ValueError):
-            traffic = None
-    roofline = {"bound": "hbm", "kernel": "bulk_focal_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "kernel_us": 1000.0 * kernel_ms, "algorithmic_bytes_per_launch": kernel_bytes_per_image * n_img,
-                "whole_step_frac_of_hbm_roofline": (A * 696 * n_img / ((total_ms / args.steps) / 1000.0) / 1e9) / peak,
-                "per_kernel_us": shares}
+    sampler = ClockSampler(ctx.local_rank).start() if full else None
+    step_ms = timed_steps(ctx, run.one_step, args.steps, args.warmup)
+    clocks = sampler.stop() if sampler else None
+    total_ms, = ctx.max_over_ranks([sum(step_ms)])
+    res = {"per_gpu": per_gpu, "total": total, "A": A, "graph": run.graph is not None,
+           "ms_per_step": total_ms / args.steps, "value": total * args.steps / (total_ms / 1000.0),
+           "step_ms_min_med_max": [min(step_ms), statistics.median(step_ms), max(step_ms)], "clocks": clocks,
+           "num_gt": int(sum(int(t.shape[0]) for t in batch.gt_boxes))}
+    if ctx.world > 1:
+        rel, peer = run.exchange_check()
+        rel, = ctx.max_over_ranks([rel])
+        peer, = ctx.min_over_ranks([peer])
+        res["exchange_check"] = {"what": "normalisers delivered by the exchange vs an NCCL all-reduce of the ranks' own "
+                                         "pairs, checked on every rank (max over ranks)",
+                                 "max_rel_diff": rel, "ok": bool(rel <= 1e-12), "ranks": ctx.world,
+                                 "path": "nvlink-peer" if peer else "nccl all-reduce (peer memory unavailable)"}
+    if full:
+        per_kernel = per_kernel_events(ctx, run.lib, LOSS_KERNELS, run.step_resident, 3)
+        res["roofline"] = roofline_report(LOSS_KERNELS, per_kernel, A, NUM_CLASSES, per_gpu, res["ms_per_step"],
+                                          A * 696, "r2_traffic_loss.json")
+        res["kernel_launches_per_step"] = sum(n for _, n in per_kernel.values()) + (1 if ctx.world > 1 else 0)
+        e_ms, e_wall, h2d, d2h = run.e2e(args.steps, args.warmup)
+        e_ms, e_wall = ctx.max_over_ranks([e_ms, e_wall])
+        res["e2e"] = {"value": total * args.steps / (max(e_ms, e_wall) / 1000.0), "unit": UNIT,
+                      "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                      "ms_per_step": max(e_ms, e_wall) / args.steps,
+                      "what": "PAALossComputation.__call__ + torch.autograd.grad, inputs copied from pinned host "
+                              "memory and losses read back every step (per-rank bytes)"}
+        if ctx.world == 1 and not args.no_side:
+            try:
+                ms = run.eager_api_ms(args.steps)
+                res["eager_api_resident"] = {"value": total / (ms / 1000.0), "unit": UNIT, "ms_per_step": ms,
+                                             "what": "PAALossComputation.__call__ + torch.autograd.grad, inputs "
+                                                     "resident, no graph, wall clock between two synchronisations"}
+            except Exception as e:  # noqa: BLE001 - a side measurement must not take the bench line down
+                sys.stderr.write("eager_api_resident side measurement failed: %s\n" % (e,))
+        if ctx.rank == 0 and ctx.world == 1 and not args.no_cpu_baseline:
+            cores = host_threads()
+            n = min(CPU_SAMPLE_IMAGES, per_gpu)
+            ips, times = cpu_port_loss(batch, n, repeats=3, warmup=1, time_budget_s=60.0)
+            res["cpu_baseline"] = {"value": ips, "unit": UNIT, "cores": cores, "kind": "port",
+                                   "sample": "first %d images of the step's batch, fwd+bwd, median of %d after 1 "
+                                             "warm-up, %d threads" % (n, len(times), cores)}
+    del run
+    torch.cuda.empty_cache()
+    return res
 
+
+def loss_line(ctx, args):
+    other = "weak" if args.scaling == "strong" else "strong"
+    main = measure_loss(ctx, args, args.scaling, full=True)
+    side = None
+    if ctx.world > 1 and not args.no_side and not args.images_per_gpu:
+        side = measure_loss(ctx, args, other, full=False)
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, note=("CUDA graph replay" if graph is not None else "eager launches")),
-        "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 12,
-                "ms_per_step": max(e2e_ms, e2e_wall_ms) / args.steps},
-        # our kernels per step: assign_pass1, match_score, select_gmm, bulk_focal, positive_terms, finish_loss
-        # (+ norm_wait_kernel with more than one rank)
-        "gpu_launches": (6 + (1 if world > 1 else 0)) * args.steps,
-        "roofline": roofline,
-        "step_ms_min_med_max": [min(step_ms), statistics.median(step_ms), max(step_ms)],
+        "metric": LOSS_METRIC, "value": main["value"], "unit": UNIT, "n_gpus": ctx.world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": main["ms_per_step"], "higher_is_better": True,
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, args.scaling, main["per_gpu"], main["total"], ctx.world),
+        "launch": "CUDA graph replay" if main["graph"] else "eager launches",
+        "clocks": main["clocks"], "e2e": main["e2e"],
+        "gpu_launches": main["kernel_launches_per_step"] * args.steps,
+        "roofline": main["roofline"], "step_ms_min_med_max": main["step_ms_min_med_max"],
+        "num_gt_this_rank": main["num_gt"],
     }
-    # side measurements (single-GPU runs; not the headline): see the comments where they are taken
-    if clean_ms is not None:
-        line["cold_clean_l2"] = {"value": images / (clean_ms / 1000.0), "unit": UNIT,
-                                 "ms_per_step": clean_ms / args.steps,
-                                 "l2": "256 MiB write then 256 MiB read of another buffer before every step (untimed)"}
-    if eager_ms is not None:
-        line["eager_api_resident"] = {"value": images / (eager_ms / 1000.0), "unit": UNIT,
-                                      "ms_per_step": eager_ms / args.steps,
-                                      "what": "PAALossComputation.__call__ + torch.autograd.grad, inputs resident, "
-                                              "no graph, wall clock between two synchronisations"}
+    for key in ("exchange_check", "eager_api_resident", "cpu_baseline"):
+        if key in main:
+            line[key] = main[key]
+    if side is not None:
+        line[other + "_scaling"] = {"value": side["value"], "unit": UNIT, "ms_per_step": side["ms_per_step"],
+                                    "images_per_gpu": side["per_gpu"], "global_batch": side["total"],
+                                    "exchange_check": side.get("exchange_check")}
+    return line
 
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        n = min(CPU_SAMPLE_IMAGES, n_img)
-        ips, times = cpu_port_images_per_sec(batch, n, repeats=3, warmup=1)
-        line["cpu_baseline"] = {"value": ips, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                                "sample": "first %d images of the step's batch, fwd+bwd, median of 3 after 1 warm-up"
-                                          % n}
-    if rank == 0 and not args.no_post:
-        try:
-            from bench_post import measure_post
-            line["post"] = measure_post(dev, steps=min(args.steps, 10), warmup=3)
-        except Exception as e:  # noqa: BLE001
-            line["post"] = {"unavailable": str(e)[:200]}
-    if rank == 0:
+
+# ------------------------------------------------------------------------------------------------
+# NMS + score voting
+# ------------------------------------------------------------------------------------------------
+class PostRun(object):
+    def __init__(self, ctx, batch, no_graph):
+        import paa_b200
+        from paa_b200 import _lib
+        from paa_b200.structures import BoxList
+        self.ctx, self.batch = ctx, batch
+        dev = ctx.dev
+        self.n_img = batch.num_images
+        cfg = paa_b200.default_cfg()
+        self.pp = paa_b200.make_paa_postprocessor(cfg, paa_b200.BoxCoder(cfg))
+        self.lib = _lib.load()
+        self.cls = [t.to(dev) for t in batch.box_cls]
+        self.reg = [t.to(dev) for t in batch.box_regression]
+        self.iou = [t.to(dev) for t in batch.iou_pred]
+        anc = [a.to(dev) for a in batch.anchors]
+        self.anchors = [[BoxList(a, batch.image_sizes[i]) for a in anc] for i in range(self.n_img)]
+        for _ in range(3):
+            self.out = self.step_resident()
+        torch.cuda.synchronize()
+        self.graph = capture(self.step_resident, no_graph)
+
+    def step_resident(self):
+        return self.pp.run_device(self.cls, self.reg, self.iou, self.anchors)
+
+    def one_step(self):
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self.step_resident()
+
+    def e2e(self, steps, warmup):
+        """`PAAPostProcessor.forward` with host logits in and BoxLists out on the CPU: every step copies the head
+        outputs from pinned host memory (double-buffered on a copy stream), calls forward() and moves every image's
+        BoxList to the host the way engine/inference.py:38-39 does (`[o.to(cpu_device) for o in output]`)."""
+        ctx, dev = self.ctx, self.ctx.dev
+        heads_h = [t.contiguous() for t in self.batch.box_cls + self.batch.box_regression + self.batch.iou_pred]
+        sizes = [t.numel() for t in heads_h]
+        L = len(self.batch.box_cls)
+        h_pack = torch.empty(sum(sizes), dtype=torch.float32).pin_memory()
+        o = 0
+        for t, sz in zip(heads_h, sizes):
+            h_pack[o:o + sz].copy_(t.reshape(-1))
+            o += sz
+        copy_stream = torch.cuda.Stream()
+        slots = [dict(pack=torch.empty_like(h_pack, device=dev), copied=torch.cuda.Event(), free=torch.cuda.Event())
+                 for _ in range(2)]
+        state = {"k": 0, "d2h": 0}
+        cpu = torch.device("cpu")
+
+        def enqueue_copy(k):
+            sl = slots[k % 2]
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(sl["free"])
+                sl["pack"].copy_(h_pack, non_blocking=True)
+                sl["copied"].record(copy_stream)
+
+        def step():
+            k = state["k"]
+            state["k"] = k + 1
+            sl = slots[k % 2]
+            enqueue_copy(k + 1)
+            main = torch.cuda.current_stream()
+            main.wait_event(sl["copied"])
+            views, o = [], 0
+            for t, sz in zip(heads_h, sizes):
+                views.append(sl["pack"][o:o + sz].view(t.shape))
+                o += sz
+            out = self.pp(views[:L], views[L:2 * L], views[2 * L:], self.anchors)
+            host = [b.to(cpu) for b in out]
+            sl["free"].record(main)
+            state["d2h"] = sum(len(b) * (16 + 4 + 8) for b in host) + 4 * len(host)
+            return host
+
+        for sl in slots:
+            sl["free"].record(torch.cuda.current_stream())
+        enqueue_copy(0)
+        for _ in range(warmup):
+            step()
+        ctx.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step()
+        ctx.barrier()
+        wall_ms = 1000.0 * (time.perf_counter() - t0)
+        return wall_ms, h_pack.numel() * 4, state["d2h"]
+
+
+def measure_post(ctx, args, scaling, full, cfg_name="C4"):
+    pargs = argparse.Namespace(**vars(args))
+    pargs.config = cfg_name
+    if args.metric != "post":
+        pargs.images_per_gpu = None
+    batch, per_gpu, total = rank_batch(pargs, scaling, ctx.rank, ctx.world)
+    run = PostRun(ctx, batch, args.no_graph)
+    A = batch.num_anchors
+    steps = args.steps if args.metric == "post" else min(args.steps, 10)
+    sampler = ClockSampler(ctx.local_rank).start() if full else None
+    step_ms = timed_steps(ctx, run.one_step, steps, args.warmup)
+    clocks = sampler.stop() if sampler else None
+    total_ms, = ctx.max_over_ranks([sum(step_ms)])
+    res = {"metric": POST_METRIC, "value": total * steps / (total_ms / 1000.0), "unit": UNIT, "n_gpus": ctx.world,
+           "steps": steps, "warmup": args.warmup, "ms_per_step": total_ms / steps, "higher_is_better": True,
+           "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": workload_config(pargs, scaling, per_gpu, total, ctx.world),
+           "launch": "CUDA graph replay" if run.graph is not None else "eager launches",
+           "clocks": clocks, "detections_first_images": [int(c) for c in run.out[3][:4].tolist()]}
+    if full:
+        per_kernel = per_kernel_events(ctx, run.lib, POST_KERNELS, run.step_resident, 3)
+        res["roofline"] = roofline_report(POST_KERNELS, per_kernel, A, NUM_CLASSES, per_gpu, res["ms_per_step"],
+                                          A * (4 * NUM_CLASSES + 16 + 4 + 16), "r2_traffic_post.json")
+        res["gpu_launches"] = (sum(n for _, n in per_kernel.values()) + 1) * steps      # + post_class_rank_kernel
+        wall, h2d, d2h = run.e2e(steps, args.warmup)
+        wall, = ctx.max_over_ranks([wall])
+        res["e2e"] = {"value": total * steps / (wall / 1000.0), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                      "d2h_bytes_per_step": d2h, "ms_per_step": wall / steps,
+                      "what": "PAAPostProcessor.forward with the head outputs copied from pinned host memory and every "
+                              "BoxList moved to the CPU each step (per-rank bytes, wall clock)"}
+        if ctx.rank == 0 and ctx.world == 1 and not args.no_cpu_baseline:
+            cores = host_threads()
+            ips, times = cpu_port_post(batch, 1, repeats=3, warmup=1, time_budget_s=60.0)
+            res["cpu_baseline"] = {"value": ips, "unit": UNIT, "cores": cores, "kind": "port",
+                                   "sample": "first image of the step's batch, median of %d after 1 warm-up, %d threads"
+                                             % (len(times), cores)}
+    del run
+    torch.cuda.empty_cache()
+    return res
+
+
+def post_line(ctx, args):
+    other = "weak" if args.scaling == "strong" else "strong"
+    line = measure_post(ctx, args, args.scaling, full=True, cfg_name=args.config if args.metric == "post" else "C4")
+    if ctx.world > 1 and not args.no_side and not args.images_per_gpu:
+        s = measure_post(ctx, args, other, full=False, cfg_name=args.config if args.metric == "post" else "C4")
+        line[other + "_scaling"] = {k: s[k] for k in ("value", "unit", "ms_per_step")}
+        line[other + "_scaling"].update(images_per_gpu=s["config"]["images_per_gpu"],
+                                        global_batch=s["config"]["global_batch"])
+    return line
+
+
+def run_ours(args):
+    ctx = Ctx()
+    if args.metric == "post":
+        line = post_line(ctx, args)
+    else:
+        line = loss_line(ctx, args)
+        if not args.no_post:
+            try:
+                line["post"] = post_line(ctx, args)
+            except Exception as e:  # noqa: BLE001
+                line["post"] = {"unavailable": str(e)[:300]}
+    if ctx.rank == 0:
+        sys.stdout.flush()
         print(json.dumps(line), flush=True)
-    if world > 1:
+    if ctx.world > 1:
         # Leave without tearing NCCL down: destroying the process group while a captured CUDA graph still
         # references its communicator can block forever, and there is nothing left to clean up.
         torch.cuda.synchronize()

@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define PAA_ABI_VERSION 6
+#define PAA_ABI_VERSION 7
 #define PAA_MAX_LEVELS 8
 #define PAA_MAX_IMAGES 256      /* images per call (per rank) */
 #define PAA_MAX_CANDIDATES 128  /* num_levels * topk must not exceed this */
@@ -93,7 +93,7 @@ typedef struct PaaLossArgs {
     PaaLevel levels[PAA_MAX_LEVELS];
     const float* gt_boxes;        /* device [sum G, 4] xyxy */
     const int64_t* gt_labels;     /* device [sum G], 1..C */
-    int32_t gt_offsets[PAA_MAX_IMAGES + 1];  /* HOST values: image i owns GT [off[i], off[i+1]) */
+    int32_t gt_offsets[PAA_MAX_IMAGES + 1];  /* HOST values: image i owns GT [off[i], off[i+1]); see gt_offsets_dev */
     void* workspace;              /* device, >= paa_loss_workspace_bytes(), 256-byte aligned */
     size_t workspace_bytes;
     /* outputs (device) */
@@ -121,7 +121,7 @@ typedef struct PaaLossArgs {
      * kernel stores this rank's {num_pos, sum_iou} into every rank's buffer, paa_loss first waits (on its own
      * buffer only) until all world_size contributions of the step have arrived and leaves their sum, added
      * in rank order, in `normalisers`.  All ranks must make the same sequence of calls.  peer_norm[0] NULL
-     * = disabled. */
+     * = disabled.  See peer_timeout_s / peer_status below for what happens when a rank never arrives. */
     int32_t rank;
     int32_t reserved2;
     double* peer_norm[PAA_MAX_PEERS];
@@ -136,6 +136,25 @@ typedef struct PaaLossArgs {
     int32_t fcos_norm_reg_targets;/* cfg.MODEL.FCOS.NORM_REG_TARGETS: targets divided by the level's stride */
     /* PAA_LOSS_ATSS only: cfg.MODEL.ATSS.POSITIVE_TYPE (atss/loss.py:88-229) */
     int32_t atss_positive_type;   /* PAA_ATSS_POSITIVE_ATSS / _SSC / _IOU */
+    /* Peer exchange only.  The wait for the other ranks' normalisers has no deadline when peer_timeout_s <= 0 --
+     * the semantics of the all-reduce it replaces (loss.py:22-28): a rank that is late (checkpoint, data loader)
+     * is waited for.  With a deadline, a contribution that does not arrive in time is an error, never data:
+     * the waiting kernel writes {1, rank it waited for, step counter, 0} to peer_status -- four int32 in
+     * host-mapped (pinned) memory, nullable -- and traps, so every later CUDA call of the process fails. */
+    float peer_timeout_s;
+    int32_t reserved3;
+    int32_t* peer_status;
+    /* Optional: the per-image GT ranges kept on the DEVICE ([num_images + 1] int32, same meaning as gt_offsets).
+     * When set, every kernel of the step takes the ranges from here (the host copy in gt_offsets is only used to
+     * check the arguments), the per-GT grids and the workspace are sized by gt_capacity (an upper bound on the
+     * GTs of a call; use the same value for *_workspace_bytes) and the GT-list split of crowded images by
+     * gt_per_image_capacity.  No kernel parameter or grid size then depends on the batch's GT counts: a CUDA graph
+     * captured around paa_assign + paa_loss can be replayed after the caller has rewritten gt_offsets_dev, gt_boxes
+     * and gt_labels in place with another batch of num_images images within the capacities (training feeds new
+     * targets every step, paa.py:137-148).  The caller checks what the host path checks (an image without GT). */
+    const int32_t* gt_offsets_dev;
+    int32_t gt_capacity;
+    int32_t gt_per_image_capacity;
 } PaaLossArgs;
 
 typedef struct PaaPostArgs {
@@ -282,7 +301,10 @@ int paa_box_vote(const float* boxes, const float* scores, const float* labels, i
 #define PAA_KERNEL_PASS1        1   /* assign_pass1_kernel: IoU matching + class sums of the logits */
 #define PAA_KERNEL_MATCH_SCORE  2
 #define PAA_KERNEL_SELECT_GMM   3
-#define PAA_KERNEL_FINAL_LOSS   4
+#define PAA_KERNEL_FINAL_LOSS   4   /* bulk_focal_kernel: every logit read once, its gradient written once */
+#define PAA_KERNEL_POSITIVE_TERMS 5 /* positive_terms_kernel */
+#define PAA_KERNEL_FINISH_LOSS  6   /* finish_loss_kernel */
+#define PAA_KERNEL_NORM_WAIT    7   /* norm_wait_kernel (peer exchange only) */
 #define PAA_KERNEL_POST_CANDIDATES 10
 #define PAA_KERNEL_POST_FILTER  11
 #define PAA_KERNEL_POST_SELECT  12
@@ -291,6 +313,8 @@ int paa_box_vote(const float* boxes, const float* scores, const float* labels, i
 #define PAA_KERNEL_POST_NMS_SCAN 15
 #define PAA_KERNEL_POST_FINISH  16
 #define PAA_KERNEL_POST_VOTE    17
+#define PAA_KERNEL_POST_THRESHOLD 18
+#define PAA_KERNEL_POST_SEGMENTS 19
 int paa_kernel_timing_begin(int kernel_id);
 int paa_kernel_timing_end(float* total_ms, int32_t* launches);
 

@@ -317,6 +317,51 @@ def assign(box_cls, box_regression, iou_pred, gt_boxes, gt_labels, anchors_per_l
         params=prm)
 
 
+def with_labels(asg, paa_labels, box_regression, gt_boxes):
+    """Teacher-forces stage 4's output: a copy of the assignment `asg` whose PAA labels are `paa_labels`
+    ([N, A] integer array / tensor) instead of the oracle's own, with everything stage 5 derives from the
+    labels rebuilt the way loss.py:230-232,318-333 does (a positive's regression target is its matched GT --
+    candidates come from `matched == g`, loss.py:163 --, `pos_inds`, the aligned IoUs and both normalisers).
+    Lets a test compare losses / gradients when a documented tie flipped a positive set on the device."""
+    prm = asg.params
+    N, A = asg.N, asg.A
+    labels = torch.as_tensor(np.asarray(paa_labels)).reshape(N, A).to(torch.int32)
+    with torch.no_grad():
+        matched_boxes = [gt_boxes[i][asg.matched_idx[i].clamp(min=0)] for i in range(N)]          # :183-185,230
+        reg_targets_flat = torch.cat([encode(mb, asg.anchors_cat) for mb in matched_boxes])       # :232,319
+        labels_flat = labels.reshape(-1)
+        pos_inds = torch.nonzero(labels_flat > 0, as_tuple=False).squeeze(1)
+        if prm.use_iou_pred and pos_inds.numel() > 0:
+            reg_flat = torch.cat([flatten_level(x, 4) for x in box_regression], dim=1).reshape(-1, 4)
+            gt_dec = decode(reg_targets_flat[pos_inds], asg.anchors_flat[pos_inds])
+            pr_dec = decode(reg_flat.detach()[pos_inds], asg.anchors_flat[pos_inds])
+            ious = aligned_iou_plus1(gt_dec, pr_dec)
+        else:
+            ious = torch.zeros(0)
+    out = SimpleNamespace(**vars(asg))
+    out.paa_labels = labels
+    out.reg_targets = reg_targets_flat
+    out.pos_inds = pos_inds
+    out.pos_ious = ious
+    out.num_pos = int(pos_inds.numel())
+    out.sum_iou = float(ious.sum()) if ious.numel() else 0.0
+    return out
+
+
+def losses_and_grads(box_cls, box_regression, iou_pred, asg):
+    """Stage 5 + backward of the summed losses on fresh leaves; returns (losses, grads namespace)."""
+    box_cls = [x.detach().clone().requires_grad_(True) for x in box_cls]
+    box_regression = [x.detach().clone().requires_grad_(True) for x in box_regression]
+    if iou_pred is not None:
+        iou_pred = [x.detach().clone().requires_grad_(True) for x in iou_pred]
+    ls = losses(box_cls, box_regression, iou_pred, asg)
+    sum(ls).backward()
+    z = lambda xs: [x.grad if x.grad is not None else torch.zeros_like(x) for x in xs]       # noqa: E731
+    grads = SimpleNamespace(box_cls=z(box_cls), box_regression=z(box_regression),
+                            iou_pred=None if iou_pred is None else z(iou_pred))
+    return [l.detach() for l in ls], grads
+
+
 def losses(box_cls, box_regression, iou_pred, asg, total_num_pos=None, total_sum_iou=None,
            world_size=1):
     """Stage 5 (loss.py:317-358).  ``total_*`` are the all-reduced normalisers (loss.py:321,338);

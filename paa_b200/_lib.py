@@ -15,7 +15,7 @@ MAX_IMAGES = 256
 MAX_PEERS = 16
 PEER_BUFFER_DOUBLES = 256
 MAX_CANDIDATES = 128
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 ERR_BAD_ARGUMENT, ERR_WORKSPACE, ERR_EMPTY_TARGET, ERR_UNSUPPORTED = -1, -2, -3, -4
 
@@ -48,7 +48,9 @@ class PaaLossArgs(C.Structure):
                 ("box_code_weights", C.c_float * 4), ("smooth_l1_beta", C.c_float),
                 ("reg_norm_weight", C.c_float), ("fcos_strides", C.c_float * MAX_LEVELS),
                 ("fcos_center_radius", C.c_float), ("fcos_iou_loss_type", C.c_int32),
-                ("fcos_norm_reg_targets", C.c_int32), ("atss_positive_type", C.c_int32)]
+                ("fcos_norm_reg_targets", C.c_int32), ("atss_positive_type", C.c_int32),
+                ("peer_timeout_s", C.c_float), ("reserved3", C.c_int32), ("peer_status", C.c_void_p),
+                ("gt_offsets_dev", C.c_void_p), ("gt_capacity", C.c_int32), ("gt_per_image_capacity", C.c_int32)]
 
 
 class PaaPostArgs(C.Structure):
@@ -106,7 +108,8 @@ SYMBOLS = {
     "paa_kernel_timing_end": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
 }
 
-KERNEL_IDS = dict(pass1=1, match_score=2, select_gmm=3, final_loss=4, post_candidates=10, post_filter=11,
+KERNEL_IDS = dict(pass1=1, match_score=2, select_gmm=3, final_loss=4, positive_terms=5, finish_loss=6, norm_wait=7,
+                  post_threshold=18, post_segments=19, post_candidates=10, post_filter=11,
                   post_select=12, post_rank=13, post_nms_mask=14, post_nms_scan=15, post_finish=16, post_vote=17)
 
 _lib = None

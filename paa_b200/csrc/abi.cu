@@ -99,11 +99,11 @@ static int tiles_upper_bound(int anchors_per_image, int num_levels) {
 struct LossPlan {
     PeerExchange px;
     Geometry geo;
-    GtOffsets go;
+    GtOffsets go;          // host values (argument checks; uploaded by prep_step_kernel unless gt_offsets_dev is set)
     LossScalars sc;
     LossDebug dbg;
     LossWorkspace ws;
-    int sumG;
+    int sumG;              // GT capacity of the call: sizes the per-GT grids and the workspace
 };
 
 static int plan_loss(const PaaLossArgs* a, LossPlan* p) {
@@ -139,19 +139,25 @@ static int plan_loss(const PaaLossArgs* a, LossPlan* p) {
         }
     }
     p->go.v[a->num_images] = a->gt_offsets[a->num_images];
+    memset(p->go.by_load, 0, sizeof(p->go.by_load));       // the order by load is worked out on the device
+    // Capacities.  Without gt_offsets_dev the host offsets ARE the step's offsets; with it they only describe the
+    // batch the call was planned on, and everything sized here must hold for every batch the caller will put into
+    // gt_offsets_dev / gt_boxes / gt_labels before replaying a graph captured around the call.
+    int gmax = 1;
+    for (int i = 0; i < a->num_images; ++i)
+        gmax = gmax > a->gt_offsets[i + 1] - a->gt_offsets[i] ? gmax : a->gt_offsets[i + 1] - a->gt_offsets[i];
     p->sumG = a->gt_offsets[a->num_images];
-    // images with many GT boxes cost proportionally more in the IoU kernel: schedule them first
-    for (int i = 0; i < a->num_images; ++i) p->go.by_load[i] = (unsigned char)i;
-    for (int i = 1; i < a->num_images; ++i) {          // insertion sort, N <= 256
-        const unsigned char key = p->go.by_load[i];
-        const int kg = p->go.v[key + 1] - p->go.v[key];
-        int j = i - 1;
-        while (j >= 0 && (p->go.v[p->go.by_load[j] + 1] - p->go.v[p->go.by_load[j]]) < kg) {
-            p->go.by_load[j + 1] = p->go.by_load[j];
-            --j;
+    if (a->gt_offsets_dev) {
+        if (a->gt_capacity < p->sumG || a->gt_per_image_capacity < gmax) {
+            set_error("gt_offsets_dev: gt_capacity=%d / gt_per_image_capacity=%d below this batch's %d / %d",
+                      a->gt_capacity, a->gt_per_image_capacity, p->sumG, gmax);
+            return PAA_ERR_BAD_ARGUMENT;
         }
-        p->go.by_load[j + 1] = key;
+        p->sumG = a->gt_capacity;
+        gmax = a->gt_per_image_capacity;
     }
+    p->sc.gt_capacity = p->sumG;
+    p->sc.gt_parts = gt_parts_for(gmax);
     if (!a->gt_boxes || !a->gt_labels || !a->workspace || !a->normalisers || !a->losses) {
         set_error("null gt_boxes / gt_labels / workspace / normalisers / losses");
         return PAA_ERR_BAD_ARGUMENT;
@@ -260,6 +266,8 @@ static int plan_loss(const PaaLossArgs* a, LossPlan* p) {
         }
         p->px.rank = a->rank;
         p->px.world = a->world_size;
+        p->px.status = a->peer_status;
+        p->px.timeout_ns = a->peer_timeout_s > 0.0f ? (unsigned long long)((double)a->peer_timeout_s * 1e9) : 0ull;
     }
     p->dbg.matched_idx = a->dbg_matched_idx;
     p->dbg.iou_labels = a->dbg_iou_labels;
@@ -297,22 +305,16 @@ int paa_assign(const PaaLossArgs* args, void* stream_) {
     int rc = plan_loss(args, &p);
     if (rc) return rc;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    PAA_CUDA_CHECK(cudaMemsetAsync(args->workspace, 0, p.ws.zero_bytes, stream));
-    {
-        // the coarse levels' best-GT keys are merged with atomicMax when their GT list is cut into parts
-        const int hl = first_heavy_level(p.geo);
-        if (hl < p.geo.num_levels && gt_parts(p.go, args->num_images) > 1) {
-            const size_t a0 = (size_t)p.geo.lv[hl].a_off, n_heavy = (size_t)p.geo.A - a0;
-            PAA_CUDA_CHECK(cudaMemset2DAsync(reinterpret_cast<char*>(p.ws.best) + a0 * 8, (size_t)p.geo.A * 8, 0,
-                                             n_heavy * 8, (size_t)args->num_images, stream));
-        }
-    }
-    if ((rc = launch_assign_pass1(p.geo, p.go, args->gt_boxes, p.sc, p.ws, stream))) return rc;
+    // clears the zeroed prefix and the coarse levels' best-GT keys (merged with atomicMax when their GT list is cut
+    // into parts), uploads the GT ranges
+    if ((rc = launch_prep_step(p.geo, p.go, args->gt_offsets_dev, p.sc, p.ws, args->workspace, true, false, stream)))
+        return rc;
+    if ((rc = launch_assign_pass1(p.geo, args->gt_boxes, p.sc, p.ws, stream))) return rc;
     const float* score_src = args->teacher_combined_loss ? args->teacher_combined_loss : p.ws.score;
-    if ((rc = launch_match_score(p.geo, p.go, args->gt_boxes, args->gt_labels, p.sc, p.ws,
+    if ((rc = launch_match_score(p.geo, args->gt_boxes, args->gt_labels, p.sc, p.ws,
                                  args->teacher_combined_loss, p.dbg, stream)))
         return rc;
-    if ((rc = launch_select_gmm(p.geo, p.go, p.sumG, args->gt_boxes, args->gt_labels, p.sc, p.ws, score_src,
+    if ((rc = launch_select_gmm(p.geo, args->gt_boxes, args->gt_labels, p.sc, p.ws, score_src,
                                 args->normalisers, p.px, p.dbg, stream)))
         return rc;
     if (args->dbg_paa_labels)
@@ -328,17 +330,16 @@ int paa_atss_assign(const PaaLossArgs* args, void* stream_) {
     if (rc) return rc;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (p.sc.atss_type == PAA_ATSS_POSITIVE_SSC) {
-        rc = launch_fcos_assign(p.geo, p.go, args->gt_boxes, args->gt_labels, p.sc, p.ws, args->normalisers, p.px,
+        if ((rc = launch_prep_step(p.geo, p.go, args->gt_offsets_dev, p.sc, p.ws, args->workspace, false, false,
+                                   stream)))
+            return rc;
+        rc = launch_fcos_assign(p.geo, args->gt_boxes, args->gt_labels, p.sc, p.ws, args->normalisers, p.px,
                                 p.dbg, stream, /*ssc=*/true);
     } else if (p.sc.atss_type == PAA_ATSS_POSITIVE_IOU) {
-        PAA_CUDA_CHECK(cudaMemsetAsync(args->workspace, 0, p.ws.zero_bytes, stream));
-        const int hl = first_heavy_level(p.geo);
-        if (hl < p.geo.num_levels && gt_parts(p.go, args->num_images) > 1) {
-            const size_t a0 = (size_t)p.geo.lv[hl].a_off, n_heavy = (size_t)p.geo.A - a0;
-            PAA_CUDA_CHECK(cudaMemset2DAsync(reinterpret_cast<char*>(p.ws.best) + a0 * 8, (size_t)p.geo.A * 8, 0,
-                                             n_heavy * 8, (size_t)args->num_images, stream));
-        }
-        rc = launch_retinanet_assign(p.geo, p.go, args->gt_boxes, args->gt_labels, p.sc, p.ws, args->normalisers,
+        if ((rc = launch_prep_step(p.geo, p.go, args->gt_offsets_dev, p.sc, p.ws, args->workspace, true, false,
+                                   stream)))
+            return rc;
+        rc = launch_retinanet_assign(p.geo, args->gt_boxes, args->gt_labels, p.sc, p.ws, args->normalisers,
                                      p.dbg, stream, /*atss_iou=*/true, &p.px);
     } else {
         for (int l = 0; l < p.geo.num_levels; ++l)
@@ -348,9 +349,10 @@ int paa_atss_assign(const PaaLossArgs* args, void* stream_) {
                           p.geo.lv[l].n_anchor, args->topk);
                 return PAA_ERR_UNSUPPORTED;
             }
-        PAA_CUDA_CHECK(cudaMemsetAsync(args->workspace, 0, p.ws.zero_bytes, stream));
-        PAA_CUDA_CHECK(cudaMemsetAsync(p.ws.best, 0, sizeof(uint2) * (size_t)args->num_images * p.geo.A, stream));
-        rc = launch_atss_assign(p.geo, p.go, p.sumG, args->gt_boxes, args->gt_labels, p.sc, p.ws, args->normalisers,
+        if ((rc = launch_prep_step(p.geo, p.go, args->gt_offsets_dev, p.sc, p.ws, args->workspace, false, true,
+                                   stream)))
+            return rc;
+        rc = launch_atss_assign(p.geo, args->gt_boxes, args->gt_labels, p.sc, p.ws, args->normalisers,
                                 p.px, p.dbg, stream);
     }
     if (rc) return rc;
@@ -370,16 +372,9 @@ int paa_retinanet_assign(const PaaLossArgs* args, void* stream_) {
         return PAA_ERR_BAD_ARGUMENT;
     }
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    PAA_CUDA_CHECK(cudaMemsetAsync(args->workspace, 0, p.ws.zero_bytes, stream));
-    {
-        const int hl = first_heavy_level(p.geo);
-        if (hl < p.geo.num_levels && gt_parts(p.go, args->num_images) > 1) {
-            const size_t a0 = (size_t)p.geo.lv[hl].a_off, n_heavy = (size_t)p.geo.A - a0;
-            PAA_CUDA_CHECK(cudaMemset2DAsync(reinterpret_cast<char*>(p.ws.best) + a0 * 8, (size_t)p.geo.A * 8, 0,
-                                             n_heavy * 8, (size_t)args->num_images, stream));
-        }
-    }
-    if ((rc = launch_retinanet_assign(p.geo, p.go, args->gt_boxes, args->gt_labels, p.sc, p.ws, args->normalisers,
+    if ((rc = launch_prep_step(p.geo, p.go, args->gt_offsets_dev, p.sc, p.ws, args->workspace, true, false, stream)))
+        return rc;
+    if ((rc = launch_retinanet_assign(p.geo, args->gt_boxes, args->gt_labels, p.sc, p.ws, args->normalisers,
                                       p.dbg, stream)))
         return rc;
     if (args->dbg_paa_labels)
@@ -398,7 +393,9 @@ int paa_fcos_assign(const PaaLossArgs* args, void* stream_) {
         return PAA_ERR_BAD_ARGUMENT;
     }
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    if ((rc = launch_fcos_assign(p.geo, p.go, args->gt_boxes, args->gt_labels, p.sc, p.ws, args->normalisers, p.px,
+    if ((rc = launch_prep_step(p.geo, p.go, args->gt_offsets_dev, p.sc, p.ws, args->workspace, false, false, stream)))
+        return rc;
+    if ((rc = launch_fcos_assign(p.geo, args->gt_boxes, args->gt_labels, p.sc, p.ws, args->normalisers, p.px,
                                  p.dbg, stream)))
         return rc;
     if (args->dbg_paa_labels)
@@ -418,7 +415,7 @@ int paa_loss(const PaaLossArgs* args, void* stream_) {
     for (int l = 0; l < args->num_levels; ++l)
         write_grads = write_grads || args->levels[l].grad_box_cls || args->levels[l].grad_box_regression ||
                       args->levels[l].grad_iou_pred;
-    return launch_final_loss(p.geo, p.go, args->gt_boxes, p.sc, p.ws, args->normalisers, args->grad_losses,
+    return launch_final_loss(p.geo, args->gt_boxes, p.sc, p.ws, args->normalisers, args->grad_losses,
                              args->losses, write_grads, stream);
 }
 

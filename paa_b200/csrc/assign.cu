@@ -305,7 +305,7 @@ __device__ __forceinline__ void class_sum_block(const Geometry& geo, const Pass1
 
 template <bool kG2>
 __global__ void __launch_bounds__(kPassThreads, 6)
-assign_pass1_kernel(const Geometry geo, const GtOffsets go, const Pass1Plan plan, float gamma,
+assign_pass1_kernel(const Geometry geo, const GtOffsets* __restrict__ gop, const Pass1Plan plan, float gamma,
                     const float* __restrict__ gt_boxes, unsigned* __restrict__ gtmax,
                     unsigned long long* __restrict__ best, float* __restrict__ negsum) {
     pdl_launch_dependents();
@@ -322,8 +322,14 @@ assign_pass1_kernel(const Geometry geo, const GtOffsets go, const Pass1Plan plan
         is_iou = plan.iou_blocks > plan.sum_blocks;
         idx = b - m;
     }
-    if (is_iou) iou_best_block(geo, go, idx, plan, gt_boxes, gtmax, best, sm);
-    else class_sum_block<kG2>(geo, plan, idx, gamma, negsum, sm);
+    if (is_iou) {
+        // the GT ranges and the cleared maxima come from prep_step_kernel, whose programmatic dependent this launch
+        // is; the class-sum blocks read nothing of it and stream the logits while it still runs
+        pdl_wait();
+        iou_best_block(geo, *gop, idx, plan, gt_boxes, gtmax, best, sm);
+    } else {
+        class_sum_block<kG2>(geo, plan, idx, gamma, negsum, sm);
+    }
 }
 
 // Levels from this one on are "coarse": few, large anchors that overlap (nearly) every GT of the image.
@@ -333,16 +339,81 @@ int first_heavy_level(const Geometry& geo) {
     return l;
 }
 
-// Number of GT-list parts for the coarse tiles: about 128 GTs per part for the busiest image, at most 8
-// (one part, i.e. no split and no atomics, for the usual <= 100 GTs per image).
-int gt_parts(const GtOffsets& go, int num_images) {
-    int gmax = 1;
-    for (int i = 0; i < num_images; ++i) gmax = gmax > go.v[i + 1] - go.v[i] ? gmax : go.v[i + 1] - go.v[i];
-    int p = (gmax + 127) / 128;
+// Number of GT-list parts for the coarse tiles: about 128 GTs per part for the busiest image the call can hold, at
+// most 8 (one part, i.e. no split and no atomics, for the usual <= 100 GTs per image).
+int gt_parts_for(int max_gt_per_image) {
+    int p = (max_gt_per_image + 127) / 128;
     return p < 1 ? 1 : (p > 8 ? 8 : p);
 }
 
-int launch_assign_pass1(const Geometry& geo, const GtOffsets& go, const float* gt_boxes, const LossScalars& sc,
+// ---------------------------------------------------------------------------------------------
+// K0: first launch of every assign call.  All blocks clear the workspace's zeroed prefix (per-GT maxima, flags,
+// ticket, pool counters) and, where asked, the best-GT keys that are merged by atomicMax; block 0 leaves the
+// per-image GT ranges, the image order by load and every GT's image in device memory, where all later kernels
+// of the step read them.  Nothing downstream depends on HOST values of the GT counts any more, so a CUDA graph
+// captured around the step can be replayed on another batch (PaaLossArgs::gt_offsets_dev).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+prep_step_kernel(const GtOffsets host_go, const int* __restrict__ dev_offsets, int num_images, int capacity,
+                 GtOffsets* __restrict__ dst, int* __restrict__ gt_image, uint4* __restrict__ zero_base,
+                 size_t zero_vec, uint2* __restrict__ best, int A, int best_a0, int best_n) {
+    pdl_launch_dependents();
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = tid; i < zero_vec; i += nthr) zero_base[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (best_n > 0) {
+        const size_t total = (size_t)num_images * best_n;
+        for (size_t i = tid; i < total; i += nthr) {
+            const size_t n = i / best_n, a = i - n * best_n;
+            best[n * A + best_a0 + a] = make_uint2(0u, 0u);
+        }
+    }
+    if (blockIdx.x != 0) return;
+    __shared__ int s_v[PAA_MAX_IMAGES + 1];
+    for (int i = threadIdx.x; i <= num_images; i += blockDim.x) {
+        int v = dev_offsets ? __ldg(dev_offsets + i) : host_go.v[i];
+        s_v[i] = v < 0 ? 0 : (v > capacity ? capacity : v);          // never index past what the workspace holds
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i <= num_images; i += blockDim.x) dst->v[i] = s_v[i];
+    // images with many GT boxes cost proportionally more in the IoU kernel: most GTs first, ties by index
+    for (int i = threadIdx.x; i < num_images; i += blockDim.x) {
+        const int gi = s_v[i + 1] - s_v[i];
+        int rank = 0;
+        for (int j = 0; j < num_images; ++j) {
+            const int gj = s_v[j + 1] - s_v[j];
+            rank += (gj > gi || (gj == gi && j < i)) ? 1 : 0;
+        }
+        dst->by_load[rank] = (unsigned char)i;
+    }
+    for (int n = 0; n < num_images; ++n)
+        for (int g = s_v[n] + threadIdx.x; g < s_v[n + 1]; g += blockDim.x) gt_image[g] = n;
+}
+
+int launch_prep_step(const Geometry& geo, const GtOffsets& host_go, const int* dev_offsets, const LossScalars& sc,
+                     const LossWorkspace& ws, void* zero_base, bool clear_heavy_best, bool clear_all_best,
+                     cudaStream_t stream) {
+    const size_t zero_vec = ws.zero_bytes / sizeof(uint4);
+    int a0 = 0, n_best = 0;
+    if (clear_all_best) {
+        n_best = geo.A;
+    } else if (clear_heavy_best) {
+        const int hl = first_heavy_level(geo);
+        if (hl < geo.num_levels && sc.gt_parts > 1) {
+            a0 = geo.lv[hl].a_off;
+            n_best = geo.A - a0;
+        }
+    }
+    const size_t work = zero_vec + (size_t)geo.num_images * n_best;
+    int grid = (int)((work + 1023) / 1024);
+    grid = grid < 1 ? 1 : (grid > 148 * 4 ? 148 * 4 : grid);
+    prep_step_kernel<<<grid, 256, 0, stream>>>(host_go, dev_offsets, geo.num_images, sc.gt_capacity, ws.go, ws.gt_image,
+                                               reinterpret_cast<uint4*>(zero_base), zero_vec, ws.best, geo.A, a0,
+                                               n_best);
+    PAA_LAUNCH_CHECK("prep_step_kernel");
+    return 0;
+}
+
+int launch_assign_pass1(const Geometry& geo, const float* gt_boxes, const LossScalars& sc,
                         const LossWorkspace& ws, cudaStream_t stream, bool with_class_sums) {
     Pass1Plan plan;
     unsigned items = 0;
@@ -364,7 +435,7 @@ int launch_assign_pass1(const Geometry& geo, const GtOffsets& go, const float* g
     plan.light_tiles = heavy_level < geo.num_levels ? geo.lv[heavy_level].tile_off : geo.tiles_per_image;
     plan.light_pairs = (plan.light_tiles + 1) / 2;
     plan.heavy_pairs = (geo.tiles_per_image - plan.light_tiles + 1) / 2;
-    plan.parts = gt_parts(go, geo.num_images);
+    plan.parts = sc.gt_parts;
     // fine levels in 2-D patches when their grid widths are known
     plan.patches = geo.apl == 1 ? 1 : 0;
     unsigned regions = 0;
@@ -386,13 +457,14 @@ int launch_assign_pass1(const Geometry& geo, const GtOffsets& go, const float* g
     plan.iou_blocks = (unsigned)geo.num_images * (light_items + (unsigned)(plan.heavy_pairs * plan.parts));
     const unsigned grid = plan.sum_blocks + plan.iou_blocks;
     KernelTimer timer(PAA_KERNEL_PASS1, stream);
+    const GtOffsets* gop = ws.go;
+    unsigned long long* best = reinterpret_cast<unsigned long long*>(ws.best);
     if (sc.gamma == 2.0f)
-        assign_pass1_kernel<true><<<grid, kPassThreads, 0, stream>>>(
-            geo, go, plan, sc.gamma, gt_boxes, ws.gtmax, reinterpret_cast<unsigned long long*>(ws.best), ws.negsum);
+        PAA_PDL_LAUNCH(assign_pass1_kernel<true>, grid, kPassThreads, stream, geo, gop, plan, sc.gamma, gt_boxes,
+                       ws.gtmax, best, ws.negsum);
     else
-        assign_pass1_kernel<false><<<grid, kPassThreads, 0, stream>>>(
-            geo, go, plan, sc.gamma, gt_boxes, ws.gtmax, reinterpret_cast<unsigned long long*>(ws.best), ws.negsum);
-    PAA_LAUNCH_CHECK("assign_pass1_kernel");
+        PAA_PDL_LAUNCH(assign_pass1_kernel<false>, grid, kPassThreads, stream, geo, gop, plan, sc.gamma, gt_boxes,
+                       ws.gtmax, best, ws.negsum);
     return 0;
 }
 
@@ -416,7 +488,7 @@ __device__ __forceinline__ float from_ordered_bits(unsigned u) {
 }
 
 __global__ void __launch_bounds__(PAA_TILE)
-match_score_kernel(const Geometry geo, const GtOffsets go, const float* __restrict__ gt_boxes,
+match_score_kernel(const Geometry geo, const GtOffsets* __restrict__ gop, const float* __restrict__ gt_boxes,
                    const int64_t* __restrict__ gt_labels, const unsigned* __restrict__ gtmax,
                    const unsigned long long* __restrict__ best, const float* __restrict__ negsum,
                    const LossScalars sc,
@@ -425,6 +497,7 @@ match_score_kernel(const Geometry geo, const GtOffsets go, const float* __restri
                    const float* __restrict__ teacher_score, const LossDebug dbg) {
     pdl_wait();
     pdl_launch_dependents();
+    const GtOffsets& go = *gop;
     __shared__ int s_lq[PAA_TILE];
     __shared__ int s_nlq;
     __shared__ unsigned s_mask[4];
@@ -524,12 +597,13 @@ match_score_kernel(const Geometry geo, const GtOffsets go, const float* __restri
     if (dbg.combined_loss) dbg.combined_loss[flat] = s;
 }
 
-int launch_match_score(const Geometry& geo, const GtOffsets& go, const float* gt_boxes,
+int launch_match_score(const Geometry& geo, const float* gt_boxes,
                        const int64_t* gt_labels, const LossScalars& sc, const LossWorkspace& ws,
                        const float* teacher_score, const LossDebug& dbg, cudaStream_t stream) {
     int grid = geo.num_images * geo.tiles_per_image;
     KernelTimer timer(PAA_KERNEL_MATCH_SCORE, stream);
-    PAA_PDL_LAUNCH(match_score_kernel, grid, PAA_TILE, stream, geo, go, gt_boxes, gt_labels, ws.gtmax,
+    const GtOffsets* gop = ws.go;
+    PAA_PDL_LAUNCH(match_score_kernel, grid, PAA_TILE, stream, geo, gop, gt_boxes, gt_labels, ws.gtmax,
                    reinterpret_cast<const unsigned long long*>(ws.best), ws.negsum, sc, ws.matched, ws.score,
                    ws.paa_label, ws.tile_gtmask, ws.seg_count, ws.seg_pool, teacher_score, dbg);
     return 0;
@@ -812,7 +886,7 @@ __device__ __forceinline__ unsigned long long topk_first_batch(unsigned long lon
 template <int SPL>
 // (64 registers: with the usual five levels six blocks fit an SM, so ~900 GTs are one wave)
 __global__ void __launch_bounds__(PAA_MAX_LEVELS * PAA_WARP, 4)
-select_gmm_kernel(const Geometry geo, const GtOffsets go, int num_gt_total,
+select_gmm_kernel(const Geometry geo, const GtOffsets* __restrict__ gop, const int* __restrict__ gt_image,
                   const float* __restrict__ gt_boxes, const int64_t* __restrict__ gt_labels,
                   const LossScalars sc, const uint4* __restrict__ tile_gtmask,
                   const int* __restrict__ matched, const float* __restrict__ score,
@@ -833,11 +907,11 @@ select_gmm_kernel(const Geometry geo, const GtOffsets go, int num_gt_total,
     const int gi = blockIdx.x;
     const int K = sc.topk;
     const int cap = geo.num_levels * K;
-    // image of this GT
-    int n = 0;
-    for (int k = 1; k < geo.num_images; ++k)
-        if (gi >= go.v[k]) n = k;
-    const int g_local = gi - go.v[n];
+    // the grid covers the call's GT capacity; the step's own count lives in device memory
+    const int num_gt_total = __ldg(&gop->v[geo.num_images]);
+    if (gi >= num_gt_total) return;
+    const int n = __ldg(gt_image + gi);              // image of this GT
+    const int g_local = gi - __ldg(&gop->v[n]);
     const int cls_label = (int)gt_labels[gi];
 
 #ifdef PAA_PROFILE_GMM
@@ -1020,7 +1094,7 @@ select_gmm_kernel(const Geometry geo, const GtOffsets go, int num_gt_total,
         my_ticket = atomicAdd(&ticket[0], 1u);
     }
     my_ticket = __shfl_sync(PAA_FULL, my_ticket, 0);
-    if (my_ticket == gridDim.x - 1) {
+    if (my_ticket == (unsigned)num_gt_total - 1u) {
         __threadfence();
         // eight independent loads per lane in flight (this runs after the slowest fit: it is pure kernel tail);
         // the order of the additions is fixed, so the totals are reproducible
@@ -1071,8 +1145,17 @@ select_gmm_kernel(const Geometry geo, const GtOffsets go, int num_gt_total,
 
 // First kernel of paa_loss when the peer exchange is on: lane r waits for rank r's contribution of this
 // step in THIS rank's buffer (local memory, written remotely), then the totals are added in rank order --
-// the same order on every rank, so all ranks normalise by bit-identical values.  A contribution that does
-// not arrive within ~2 s turns the normalisers into NaN instead of hanging the stream.
+// the same order on every rank, so all ranks normalise by bit-identical values.  Like the all-reduce it
+// replaces (loss.py:22-28) the wait has no deadline by default: a rank that saves a checkpoint or stalls in
+// its data loader is simply waited for.  With a deadline (PaaLossArgs::peer_timeout_s > 0) a contribution
+// that does not arrive in time is an ERROR, never data: the kernel records {1, rank, epoch} in the
+// host-mapped status words and traps, which fails every later CUDA call of the process.
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
 __global__ void __launch_bounds__(PAA_WARP)
 norm_wait_kernel(const PeerExchange px, double* __restrict__ normalisers) {
     pdl_launch_dependents();
@@ -1080,48 +1163,58 @@ norm_wait_kernel(const PeerExchange px, double* __restrict__ normalisers) {
     const double* own = px.buf[px.rank];
     const unsigned long long epoch = (unsigned long long)own[kPeerEpochOffset];   // set by select_gmm_kernel
     double cnt = 0.0, sum = 0.0;
-    bool ok = true;
     if (lane < px.world) {
         const volatile double* src = own + ((size_t)(epoch & 1ull) * kPeerMaxRanks + lane) * 4;
-        const long long t0 = clock64();
+        const unsigned long long t0 = global_timer_ns();
+        unsigned polls = 0;
         while (src[2] != (double)epoch) {
-            if (clock64() - t0 > 4000000000ll) {
-                ok = false;
-                break;
+            if (++polls < 64u) continue;                  // the usual case: the peers are microseconds apart
+            __nanosleep(200);
+            if (px.timeout_ns != 0ull && global_timer_ns() - t0 > px.timeout_ns) {
+                if (px.status) {
+                    volatile int* st = px.status;
+                    st[1] = lane;
+                    st[2] = (int)epoch;
+                    __threadfence_system();
+                    st[0] = 1;
+                    __threadfence_system();
+                }
+                __trap();
             }
         }
         __threadfence_system();
         cnt = src[0];
         sum = src[1];
     }
-    ok = __all_sync(PAA_FULL, ok);
     double tc = 0.0, ts = 0.0;
     for (int r = 0; r < px.world; ++r) {
         tc += __shfl_sync(PAA_FULL, cnt, r);
         ts += __shfl_sync(PAA_FULL, sum, r);
     }
     if (lane == 0) {
-        normalisers[0] = ok ? tc : __longlong_as_double(0x7ff8000000000000ll);
-        normalisers[1] = ok ? ts : __longlong_as_double(0x7ff8000000000000ll);
+        normalisers[0] = tc;
+        normalisers[1] = ts;
     }
 }
 
 int launch_norm_wait(const PeerExchange& px, double* normalisers, cudaStream_t stream) {
+    KernelTimer timer(PAA_KERNEL_NORM_WAIT, stream);
     norm_wait_kernel<<<1, PAA_WARP, 0, stream>>>(px, normalisers);
     PAA_LAUNCH_CHECK("norm_wait_kernel");
     return 0;
 }
 
-int launch_select_gmm(const Geometry& geo, const GtOffsets& go, int num_gt_total, const float* gt_boxes,
+int launch_select_gmm(const Geometry& geo, const float* gt_boxes,
                       const int64_t* gt_labels, const LossScalars& sc, const LossWorkspace& ws,
                       const float* score_src, double* normalisers, const PeerExchange& px, const LossDebug& dbg,
                       cudaStream_t stream) {
     const int cap = geo.num_levels * sc.topk;
-    const int grid = num_gt_total;
+    const int grid = sc.gt_capacity;
     const int threads = geo.num_levels * PAA_WARP;
+    const GtOffsets* gop = ws.go;
     KernelTimer timer(PAA_KERNEL_SELECT_GMM, stream);
 #define PAA_SEL_LAUNCH(SPL)                                                                           \
-    PAA_PDL_LAUNCH(select_gmm_kernel<SPL>, grid, threads, stream, geo, go, num_gt_total, gt_boxes, gt_labels, sc, \
+    PAA_PDL_LAUNCH(select_gmm_kernel<SPL>, grid, threads, stream, geo, gop, ws.gt_image, gt_boxes, gt_labels, sc, \
         ws.tile_gtmask, ws.matched, score_src, ws.seg_count, ws.seg_pool, ws.paa_label, ws.part_npos,  \
         ws.part_siou,                                                                                  \
         ws.ticket, ws.local_norm, normalisers, px, dbg)

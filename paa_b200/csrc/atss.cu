@@ -39,16 +39,16 @@ __device__ __forceinline__ void nearest_offer(unsigned long long& mine, unsigned
 }
 
 __global__ void __launch_bounds__(PAA_MAX_LEVELS * PAA_WARP)
-atss_candidates_kernel(const Geometry geo, const GtOffsets go, const float* __restrict__ gt_boxes, const int K,
+atss_candidates_kernel(const Geometry geo, const GtOffsets* __restrict__ gop, const int* __restrict__ gt_image,
+                       const float* __restrict__ gt_boxes, const int K,
                        unsigned long long* __restrict__ best, const LossDebug dbg) {
     pdl_launch_dependents();
     __shared__ unsigned s_cand[PAA_MAX_LEVELS][PAA_WARP];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gi = blockIdx.x;
-    int n = 0;
-    for (int k = 1; k < geo.num_images; ++k)
-        if (gi >= go.v[k]) n = k;
-    const int g_local = gi - go.v[n];
+    if (gi >= __ldg(&gop->v[geo.num_images])) return;        // the grid covers the call's GT capacity
+    const int n = __ldg(gt_image + gi);
+    const int g_local = gi - __ldg(&gop->v[n]);
     const float4 gt = ldg4(gt_boxes + (size_t)gi * 4);
     const float gcx = __fdiv_rn(__fadd_rn(gt.z, gt.x), 2.0f), gcy = __fdiv_rn(__fadd_rn(gt.w, gt.y), 2.0f);
     {
@@ -137,12 +137,13 @@ atss_candidates_kernel(const Geometry geo, const GtOffsets go, const float* __re
 }
 
 __global__ void __launch_bounds__(PAA_TILE)
-atss_labels_kernel(const Geometry geo, const GtOffsets go, const float* __restrict__ gt_boxes,
+atss_labels_kernel(const Geometry geo, const GtOffsets* __restrict__ gop, const float* __restrict__ gt_boxes,
                    const int64_t* __restrict__ gt_labels, const unsigned long long* __restrict__ best,
                    int* __restrict__ matched, int* __restrict__ paa_label, double* __restrict__ tile_part,
                    const LossDebug dbg) {
     pdl_wait();
     pdl_launch_dependents();
+    const GtOffsets& go = *gop;
     __shared__ double s_part[PAA_TILE / PAA_WARP][2];
     const int n = blockIdx.x / geo.tiles_per_image;
     const int tile = blockIdx.x - n * geo.tiles_per_image;
@@ -237,11 +238,13 @@ atss_norm_kernel(const double* __restrict__ tile_part, int tiles, double* __rest
     }
 }
 
-int launch_atss_assign(const Geometry& geo, const GtOffsets& go, int num_gt_total, const float* gt_boxes,
+int launch_atss_assign(const Geometry& geo, const float* gt_boxes,
                        const int64_t* gt_labels, const LossScalars& sc, const LossWorkspace& ws, double* normalisers,
                        const PeerExchange& px, const LossDebug& dbg, cudaStream_t stream) {
     unsigned long long* best = reinterpret_cast<unsigned long long*>(ws.best);
-    atss_candidates_kernel<<<num_gt_total, geo.num_levels * PAA_WARP, 0, stream>>>(geo, go, gt_boxes, sc.topk, best, dbg);
+    const GtOffsets* go = ws.go;
+    atss_candidates_kernel<<<sc.gt_capacity, geo.num_levels * PAA_WARP, 0, stream>>>(geo, go, ws.gt_image, gt_boxes,
+                                                                                   sc.topk, best, dbg);
     PAA_LAUNCH_CHECK("atss_candidates_kernel");
     const int tiles = geo.num_images * geo.tiles_per_image;
     // the per-tile partials live where positive_terms_kernel later puts its own (it runs after the fold)

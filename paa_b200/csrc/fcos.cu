@@ -15,10 +15,11 @@ namespace paa {
 constexpr float kFcosInf = 100000000.0f;       // fcos/loss.py:19
 
 __global__ void __launch_bounds__(PAA_TILE)
-fcos_assign_kernel(const Geometry geo, const GtOffsets go, const float* __restrict__ gt_boxes,
+fcos_assign_kernel(const Geometry geo, const GtOffsets* __restrict__ gop, const float* __restrict__ gt_boxes,
                    const int64_t* __restrict__ gt_labels, const LossScalars sc, int* __restrict__ matched,
                    int* __restrict__ label_out, double* __restrict__ tile_part, const LossDebug dbg, bool ssc) {
     pdl_launch_dependents();
+    const GtOffsets& go = *gop;
     __shared__ float4 s_box[PAA_TILE];
     __shared__ float s_area[PAA_TILE];
     __shared__ double s_part[PAA_TILE / PAA_WARP][2];
@@ -139,11 +140,12 @@ fcos_assign_kernel(const Geometry geo, const GtOffsets go, const float* __restri
     }
 }
 
-int launch_fcos_assign(const Geometry& geo, const GtOffsets& go, const float* gt_boxes, const int64_t* gt_labels,
+int launch_fcos_assign(const Geometry& geo, const float* gt_boxes, const int64_t* gt_labels,
                        const LossScalars& sc, const LossWorkspace& ws, double* normalisers, const PeerExchange& px,
                        const LossDebug& dbg, cudaStream_t stream, bool ssc) {
     const int tiles = geo.num_images * geo.tiles_per_image;
     double* tile_part = ws.block_part;       // positive_terms_kernel reuses the slots after the fold
+    const GtOffsets* go = ws.go;
     fcos_assign_kernel<<<tiles, PAA_TILE, 0, stream>>>(geo, go, gt_boxes, gt_labels, sc, ws.matched, ws.paa_label,
                                                        tile_part, dbg, ssc);
     PAA_LAUNCH_CHECK("fcos_assign_kernel");

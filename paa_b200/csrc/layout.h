@@ -5,9 +5,11 @@
 
 namespace paa {
 
+struct GtOffsets;
+
 inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
-// Workspace of the assign+loss path.  The first `zero_bytes` are cleared by one memset at the start
+// Workspace of the assign+loss path.  The first `zero_bytes` are cleared by prep_step_kernel at the start
 // of paa_assign (per-GT IoU maxima, image flags, the completion ticket); everything else is fully
 // overwritten by the kernels before it is read.
 struct LossWorkspace {
@@ -29,12 +31,15 @@ struct LossWorkspace {
     double* local_norm;     // [2]      this rank's {num_pos, sum_iou} (before the all-reduce)
     double* block_part;     // [blocks*3] per-block partial loss sums of the final kernel
     unsigned long long* seg_pool;   // [sumG*L*kSegCap] (score bits, anchor) keys of the anchors matched to (GT, level)
+    GtOffsets* go;          // the step's per-image GT ranges as every kernel reads them (written by prep_step_kernel)
+    int* gt_image;          // [sumG]   image of every GT
     size_t total_bytes;
 };
 
 // Capacity of one (GT, level) candidate pool.  The anchors IoU-matched to one GT on one level number a few
 // hundred at most for PAA's anchor layout; a segment that overflows falls back to scanning the tiles.
 constexpr int kSegCap = 1024;
+constexpr size_t kGtOffsetsBytes = 4 * 257 + 256;      // sizeof(GtOffsets), checked where the type is complete
 
 inline LossWorkspace carve_loss_workspace(void* base, int N, int A, int sumG, int tiles_per_image,
                                           int loss_blocks, int L) {
@@ -64,6 +69,8 @@ inline LossWorkspace carve_loss_workspace(void* base, int N, int A, int sumG, in
     w.block_part = reinterpret_cast<double*>(take(sizeof(double) * 3 * (size_t)loss_blocks));
     w.seg_pool = reinterpret_cast<unsigned long long*>(
         take(sizeof(unsigned long long) * (size_t)(sumG > 0 ? sumG : 1) * L * kSegCap));
+    w.go = reinterpret_cast<GtOffsets*>(take(kGtOffsetsBytes));
+    w.gt_image = reinterpret_cast<int*>(take(sizeof(int) * (size_t)(sumG > 0 ? sumG : 1)));
     w.total_bytes = off;
     return w;
 }

@@ -490,7 +490,7 @@ constexpr int kMaxTileBlocks = 8192;
 
 template <bool kGrads, bool kG2>
 __global__ void __launch_bounds__(PAA_TILE)
-positive_terms_kernel(const Geometry geo, const GtOffsets go, const float* __restrict__ gt_boxes,
+positive_terms_kernel(const Geometry geo, const GtOffsets* __restrict__ gop, const float* __restrict__ gt_boxes,
                       const LossScalars sc, const int* __restrict__ paa_label, const int* __restrict__ matched,
                       const double* __restrict__ norm, const double* __restrict__ local_norm,
                       const float* __restrict__ gout, double* __restrict__ block_part, int tiles_total,
@@ -499,6 +499,7 @@ positive_terms_kernel(const Geometry geo, const GtOffsets go, const float* __res
     __shared__ int s_ign[PAA_TILE];                 // ignored anchors of the tile (index within the level)
     pdl_wait();
     pdl_launch_dependents();
+    const GtOffsets& go = *gop;
     __shared__ int s_wcnt[PAA_TILE / PAA_WARP];
     float fix_sum = 0.f, reg_sum = 0.f, bce_sum = 0.f, ign_sum = 0.f;
     const bool may_ignore = patch_ignored;                          // block-uniform
@@ -668,9 +669,10 @@ finish_loss_kernel(const double* __restrict__ part_a, int blocks_a, const double
     }
 }
 
-int launch_final_loss(const Geometry& geo, const GtOffsets& go, const float* gt_boxes,
+int launch_final_loss(const Geometry& geo, const float* gt_boxes,
                       const LossScalars& sc, const LossWorkspace& ws, const double* normalisers,
                       const float* grad_losses, float* losses, bool write_grads, cudaStream_t stream) {
+    const GtOffsets* gop = ws.go;
     BulkPlan plan;
     plan.n = geo.num_levels;
     unsigned chunks = 0;
@@ -760,17 +762,23 @@ int launch_final_loss(const Geometry& geo, const GtOffsets& go, const float* gt_
 #undef PAA_BULK
     }
 #define PAA_POS(G, T)                                                                                        \
-    PAA_PDL_LAUNCH((positive_terms_kernel<G, T>), tile_grid, PAA_TILE, stream, geo, go, gt_boxes, sc,        \
+    PAA_PDL_LAUNCH((positive_terms_kernel<G, T>), tile_grid, PAA_TILE, stream, geo, gop, gt_boxes, sc,       \
         ws.paa_label, ws.matched, normalisers, ws.local_norm, grad_losses, tile_part, tiles_total,           \
         tiles_per_block, zero_fill, has_ignored && !bulk_ignores)
-    if (write_grads) {
-        if (g2) PAA_POS(true, true); else PAA_POS(true, false);
-    } else {
-        if (g2) PAA_POS(false, true); else PAA_POS(false, false);
+    {
+        KernelTimer timer(PAA_KERNEL_POSITIVE_TERMS, stream);
+        if (write_grads) {
+            if (g2) PAA_POS(true, true); else PAA_POS(true, false);
+        } else {
+            if (g2) PAA_POS(false, true); else PAA_POS(false, false);
+        }
     }
 #undef PAA_POS
-    PAA_PDL_LAUNCH(finish_loss_kernel, 1, kFinishThreads, stream, bulk_part, bulk_grid, tile_part, tile_grid, sc,
-                   normalisers, losses);
+    {
+        KernelTimer timer(PAA_KERNEL_FINISH_LOSS, stream);
+        PAA_PDL_LAUNCH(finish_loss_kernel, 1, kFinishThreads, stream, bulk_part, bulk_grid, tile_part, tile_grid, sc,
+                       normalisers, losses);
+    }
     return 0;
 }
 

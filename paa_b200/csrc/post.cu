@@ -1232,7 +1232,10 @@ int run_postprocess(const Geometry& geo, const PaaPostArgs* a, cudaStream_t stre
                                                                                w.cand, w.cand_count, w.hist);
     }
     PAA_LAUNCH_CHECK("post_candidates_kernel");
-    post_threshold_kernel<<<N * L, 256, 0, stream>>>(w.cand_count, w.hist, topn, w.thr_bin, w.n_above, w.k_sel);
+    {
+        KernelTimer t(PAA_KERNEL_POST_THRESHOLD, stream);
+        post_threshold_kernel<<<N * L, 256, 0, stream>>>(w.cand_count, w.hist, topn, w.thr_bin, w.n_above, w.k_sel);
+    }
     PAA_LAUNCH_CHECK("post_threshold_kernel");
     {
         KernelTimer t(PAA_KERNEL_POST_FILTER, stream);
@@ -1273,7 +1276,10 @@ int run_postprocess(const Geometry& geo, const PaaPostArgs* a, cudaStream_t stre
                                                                 w.total);
         }
         PAA_LAUNCH_CHECK("post_rank_kernel");
-        post_segments_kernel<<<N, 1024, 0, stream>>>(capN, w.total, w.s_label, w.seg_start, w.n_seg);
+        {
+            KernelTimer t(PAA_KERNEL_POST_SEGMENTS, stream);
+            post_segments_kernel<<<N, 1024, 0, stream>>>(capN, w.total, w.s_label, w.seg_start, w.n_seg);
+        }
         PAA_LAUNCH_CHECK("post_segments_kernel");
     }
     if (!a->skip_nms) {

@@ -21,13 +21,14 @@ namespace paa {
 constexpr int kMaxLabelBlocks = 8192;
 
 __global__ void __launch_bounds__(PAA_TILE)
-retina_labels_kernel(const Geometry geo, const GtOffsets go, const float* __restrict__ gt_boxes,
+retina_labels_kernel(const Geometry geo, const GtOffsets* __restrict__ gop, const float* __restrict__ gt_boxes,
                      const int64_t* __restrict__ gt_labels, const unsigned* __restrict__ gtmax,
                      const unsigned long long* __restrict__ best, const LossScalars sc,
                      int* __restrict__ matched, int* __restrict__ label_out, unsigned* __restrict__ ignore_bits,
                      double* __restrict__ tile_part, const LossDebug dbg, int tiles_total, int tiles_per_block,
                      bool atss_iou) {
     pdl_launch_dependents();
+    const GtOffsets& go = *gop;
     __shared__ float4 s_box[PAA_TILE];
     __shared__ float s_max[PAA_TILE];
     __shared__ int s_nlq;
@@ -156,10 +157,10 @@ retina_labels_kernel(const Geometry geo, const GtOffsets go, const float* __rest
     }
 }
 
-int launch_retinanet_assign(const Geometry& geo, const GtOffsets& go, const float* gt_boxes, const int64_t* gt_labels,
+int launch_retinanet_assign(const Geometry& geo, const float* gt_boxes, const int64_t* gt_labels,
                             const LossScalars& sc, const LossWorkspace& ws, double* normalisers, const LossDebug& dbg,
                             cudaStream_t stream, bool atss_iou, const PeerExchange* px) {
-    int rc = launch_assign_pass1(geo, go, gt_boxes, sc, ws, stream, /*with_class_sums=*/false);
+    int rc = launch_assign_pass1(geo, gt_boxes, sc, ws, stream, /*with_class_sums=*/false);
     if (rc) return rc;
     const int tiles = geo.num_images * geo.tiles_per_image;
     const int tiles_per_block = (tiles + kMaxLabelBlocks - 1) / kMaxLabelBlocks;
@@ -168,6 +169,7 @@ int launch_retinanet_assign(const Geometry& geo, const GtOffsets& go, const floa
     // the ignore bitmap lives where PAA keeps its per-tile GT masks: 128 bits per tile = one per anchor
     unsigned* ignore_bits = reinterpret_cast<unsigned*>(ws.tile_gtmask);
     PAA_CUDA_CHECK(cudaMemsetAsync(ignore_bits, 0, sizeof(uint4) * (size_t)tiles, stream));
+    const GtOffsets* go = ws.go;
     retina_labels_kernel<<<grid, PAA_TILE, 0, stream>>>(geo, go, gt_boxes, gt_labels, ws.gtmax,
                                                         reinterpret_cast<const unsigned long long*>(ws.best), sc,
                                                         ws.matched, ws.paa_label, ignore_bits, tile_part, dbg, tiles,

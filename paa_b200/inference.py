@@ -19,7 +19,7 @@ import torch
 
 from paa_b200 import _lib
 from paa_b200.box_coder import coder_regression_type
-from paa_b200.loss import gather_levels
+from paa_b200.loss import gather_levels, points_of
 from paa_b200.structures import BoxList
 
 
@@ -243,12 +243,7 @@ class FCOSPostProcessor(PAAPostProcessor):
 
     def forward(self, locations, box_cls, box_regression, centerness, image_sizes):
         """locations: list[L] of [H*W, 2] tensors (fcos.py compute_locations); image_sizes: [(h, w), ...]."""
-        points = []
-        for loc in locations:
-            key = (loc.data_ptr(), tuple(loc.shape))
-            if key not in self._points:
-                self._points[key] = torch.cat([loc, loc], dim=1).to(torch.float32).contiguous()   # (x, y, x, y)
-            points.append(self._points[key])
+        points = points_of(self._points, locations)        # (x, y, x, y); validated, bounded cache
         anchors = [[BoxList(p, (int(w), int(h)), mode="xyxy") for p in points] for (h, w) in image_sizes]
         return super(FCOSPostProcessor, self).forward(box_cls, box_regression, centerness, anchors)
 

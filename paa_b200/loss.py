@@ -46,26 +46,49 @@ class PeerNormExchange(object):
     is written by the last block of the assignment kernel straight into the peers' memory and read by the
     first kernel of the loss pass: no collective launch on the stream (an NCCL all-reduce of this size costs
     ~14 us of a ~165 us step on B200).  Falls back to ``dist.all_reduce`` where symmetric memory is not
-    available (``PAA_NORM_EXCHANGE=nccl`` forces the fallback)."""
+    available (``PAA_NORM_EXCHANGE=nccl`` forces the fallback).
+
+    Like the all-reduce it replaces, the wait for the peers has no deadline by default: a rank that is busy
+    saving a checkpoint (engine/trainer.py:110-111) or waiting for its data loader is simply waited for.
+    ``PAA_PEER_TIMEOUT_S`` (seconds, default 0 = none) sets one; when it expires the waiting kernel records the
+    rank it was waiting for in `status` (pinned host memory) and traps -- an error, never NaN data -- and the
+    next call of an evaluator raises with that record (`raise_if_timed_out`)."""
     _by_device = {}
 
-    def __init__(self, device):
+    def __init__(self, device, buffer):
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm_mem
         self.world = dist.get_world_size()
         self.rank = dist.get_rank()
-        if self.world > _lib.MAX_PEERS:
-            raise RuntimeError("more than %d ranks" % _lib.MAX_PEERS)
-        self.buffer = symm_mem.empty(_lib.PEER_BUFFER_DOUBLES, dtype=torch.float64, device=device)
+        self.buffer = buffer
         self.buffer.zero_()
         self.handle = symm_mem.rendezvous(self.buffer, group=dist.group.WORLD.group_name)
         self.ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        self.status = torch.zeros(4, dtype=torch.int32).pin_memory()
+        self._status_np = self.status.numpy()
+        self.timeout_s = float(os.environ.get("PAA_PEER_TIMEOUT_S", "0") or 0.0)
         torch.cuda.synchronize(device)      # zeroed before the collective in get() lets anyone write into it
+
+    def raise_if_timed_out(self):
+        st = self._status_np
+        if st[0]:
+            raise RuntimeError("paa_b200: the peer exchange of the loss normalisers timed out after %g s waiting for "
+                               "rank %d (exchange step %d); the CUDA context of this process is no longer usable"
+                               % (self.timeout_s, int(st[1]), int(st[2])))
+
+    @staticmethod
+    def _allocate(device):
+        """The local, non-collective half of the set-up: anything that can fail on one rank alone (import,
+        unsupported device, allocation) fails here, BEFORE the collective rendezvous."""
+        import torch.distributed._symmetric_memory as symm_mem
+        return symm_mem.empty(_lib.PEER_BUFFER_DOUBLES, dtype=torch.float64, device=device)
 
     @classmethod
     def get(cls, device):
         """The exchange for `device`, or None when it cannot be used (then the caller all-reduces).  The
-        decision is collective: if the set-up fails on any rank, every rank falls back."""
+        decision is collective and taken before any rank enters the rendezvous: every rank first reports whether
+        its local allocation worked (all-reduce MIN), and only if all did do the ranks rendezvous -- a rank that
+        cannot allocate symmetric memory makes everybody fall back instead of leaving the others blocked."""
         key = (device.type, device.index)
         if key not in cls._by_device:
             state = None
@@ -74,20 +97,19 @@ class PeerNormExchange(object):
                       and dist.is_initialized() and dist.get_world_size() == get_num_gpus()
                       and dist.get_world_size() <= _lib.MAX_PEERS)
             if usable:
-                why = ""
+                why, buffer = "", None
                 try:
-                    state = cls(device)
+                    buffer = cls._allocate(device)
                 except Exception as e:  # noqa: BLE001 - symmetric memory unavailable on this rank
                     why = str(e)
-                    state = None
-                ok = torch.tensor([1 if state is not None else 0], dtype=torch.int32, device=device)
+                ok = torch.tensor([1 if buffer is not None else 0], dtype=torch.int32, device=device)
                 dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-                if int(ok.item()) == 0:
-                    if state is None:
-                        import warnings
-                        warnings.warn("paa_b200: peer-memory normaliser exchange unavailable (%s); "
-                                      "using all_reduce" % (why,))
-                    state = None
+                if int(ok.item()) == 1:
+                    state = cls(device, buffer)
+                elif buffer is None:
+                    import warnings
+                    warnings.warn("paa_b200: peer-memory normaliser exchange unavailable (%s); "
+                                  "using all_reduce" % (why,))
             cls._by_device[key] = state
         return cls._by_device[key]
 
@@ -212,6 +234,99 @@ class _PAALossFunction(torch.autograd.Function):
         return (None, None, None, None, None) + tuple(out)
 
 
+class _GraphedStep(object):
+    """One assign+loss step of an evaluator on a fixed set of head / anchor tensors, captured in a CUDA graph that is
+    replayed for every new set of targets (PaaLossArgs.gt_offsets_dev: no kernel parameter or grid size depends on
+    the ground-truth counts).  Per call the host only checks the targets, writes their ranges into a pinned buffer,
+    concatenates the boxes / labels into the graph's static buffers and launches the graph."""
+    RING = 4
+
+    def __init__(self, owner, box_cls, box_reg, iou_pred, anchors, need_grad):
+        lv = gather_levels(list(box_cls), list(box_reg), None if iou_pred is None else list(iou_pred), anchors)
+        self.owner, self.lv = owner, lv
+        N, L, A = lv["N"], lv["L"], lv["A"]
+        device = lv["cls"][0].device
+        self.device, self.N = device, N
+        self.cap_img = int(owner.gt_per_image_capacity)
+        self.cap = N * self.cap_img
+        self.has_iou = iou_pred is not None
+        self.world = owner._world()
+        self.grads = owner._alloc_grads(lv, self.has_iou) if need_grad else None
+        args = owner._make_args(lv, self.has_iou, self.world, self.grads)
+        self.gt_boxes = torch.zeros((self.cap, 4), dtype=torch.float32, device=device)
+        self.gt_labels = torch.ones(self.cap, dtype=torch.int64, device=device)
+        self.offsets_dev = torch.zeros(N + 1, dtype=torch.int32, device=device)
+        self.offsets_host = [torch.zeros(N + 1, dtype=torch.int32).pin_memory() for _ in range(self.RING)]
+        self.offsets_np = [t.numpy() for t in self.offsets_host]
+        self.copied = [None] * self.RING
+        self.calls = 0
+        args.gt_boxes, args.gt_labels = self.gt_boxes.data_ptr(), self.gt_labels.data_ptr()
+        args.gt_offsets_dev = self.offsets_dev.data_ptr()
+        args.gt_capacity, args.gt_per_image_capacity = self.cap, self.cap_img
+        nbytes = owner._lib.paa_loss_workspace_bytes(N, A, self.cap, L, owner.topk)
+        self.ws = torch.empty(nbytes + 512, dtype=torch.uint8, device=device)       # pinned by the graph: its own
+        base = (self.ws.data_ptr() + 255) // 256 * 256
+        args.workspace, args.workspace_bytes = base, self.ws.numel() - (base - self.ws.data_ptr())
+        self.normalisers = torch.empty(2, dtype=torch.float64, device=device)
+        self.losses = torch.empty(3, dtype=torch.float32, device=device)
+        args.normalisers, args.losses, args.grad_losses = self.normalisers.data_ptr(), self.losses.data_ptr(), None
+        self.args = args
+        self.graph = None
+
+    def _capture(self):
+        owner, dev = self.owner, self.device
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):          # loads the kernels, sets up the peer exchange: none of it capturable
+            owner._launch(self.args, dev, self.world, self.normalisers, None)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            owner._launch(self.args, dev, self.world, self.normalisers, None)
+        self.graph = graph
+
+    def run(self, targets, anchors):
+        owner, N = self.owner, self.N
+        offsets, boxes, labels, sum_g = owner._collect_targets(targets, anchors, N)
+        gmax = 0
+        for i in range(N):
+            g = offsets[i + 1] - offsets[i]
+            if g <= 0:                                               # matcher.py:53-58
+                raise ValueError("No ground-truth boxes available for one of the images during training "
+                                 "(image %d)" % i)
+            gmax = g if g > gmax else gmax
+        if sum_g > self.cap or gmax > self.cap_img:
+            return None                                              # does not fit the plan: eager path
+        slot = self.calls % self.RING
+        self.calls += 1
+        if self.copied[slot] is not None:
+            self.copied[slot].synchronize()                          # the copy that last read this buffer is done
+        else:
+            self.copied[slot] = torch.cuda.Event()
+        self.offsets_np[slot][:] = offsets
+        self.offsets_dev.copy_(self.offsets_host[slot], non_blocking=True)
+        self.copied[slot].record()
+        b0, l0 = boxes[0], labels[0]
+        if b0.dtype == torch.float32 and b0.device == self.device and l0.dtype == torch.int64 and \
+                l0.device == self.device:
+            torch.cat(boxes, dim=0, out=self.gt_boxes[:sum_g])
+            torch.cat(labels, dim=0, out=self.gt_labels[:sum_g])
+        else:
+            self.gt_boxes[:sum_g].copy_(torch.cat(boxes, dim=0))
+            self.gt_labels[:sum_g].copy_(torch.cat(labels, dim=0))
+        if self.graph is None:
+            self.args.gt_offsets[:N + 1] = offsets                   # the plan's host-side argument checks
+            self._capture()
+        peer = PeerNormExchange.get(self.device) if self.world > 1 else None
+        if peer is not None:
+            peer.raise_if_timed_out()
+        self.graph.replay()
+        # the three losses leave as a copy (a caller may keep them across steps); the gradients alias the graph's
+        # buffers until the next call on the same head tensors
+        return self.losses.clone(), self.grads, dict(args=self.args, keep=(), device=self.device)
+
+
 class PAALossComputation(object):
     """Drop-in for paa_core.modeling.rpn.paa.loss.PAALossComputation (loss.py:31-359)."""
 
@@ -233,15 +348,28 @@ class PAALossComputation(object):
             raise NotImplementedError("REG_LOSS_TYPE %r: only 'iou' is supported" % (self.reg_loss_type,))
         if coder_regression_type(box_coder) != "BOX":
             raise NotImplementedError("only the 'BOX' BoxCoder regression type is supported")
+        self._init_runtime()
+        self._flavour = _lib.LOSS_PAA       # which assignment / weighting the kernels apply (ATSS subclass)
+
+    # -- plumbing -------------------------------------------------------------------------------
+    def _init_runtime(self):
+        """State shared by every flavour of evaluator (the subclasses have their own constructors)."""
         self._lib = _lib.load()          # raises if the CUDA library is missing
         self.debug = False               # True: keep per-stage parity outputs of the last call
         self.last_debug = None
         self.teacher_combined_loss = None   # [N, A] float32 cuda tensor: stage-wise parity protocol
         self._workspace = None
         self._ones = None
-        self._flavour = _lib.LOSS_PAA       # which assignment / weighting the kernels apply (ATSS subclass)
+        # Graph mode (opt-in, `use_graph = True` or PAA_B200_GRAPH=1): the step is captured once per set of head /
+        # anchor tensors and REPLAYED for every later call on the same tensors, whatever the targets -- the GT ranges
+        # live in device memory (PaaLossArgs.gt_offsets_dev), so the captured grids do not depend on them.  Constraints:
+        # the returned gradients (and nothing else) alias buffers that the next call on the same tensors overwrites;
+        # one evaluator serves one stream; images hold at most `gt_per_image_capacity` ground-truth boxes (a batch
+        # that does not fit simply takes the eager path).
+        self.use_graph = os.environ.get("PAA_B200_GRAPH", "0") not in ("", "0")
+        self.gt_per_image_capacity = 128
+        self._graphs = {}
 
-    # -- plumbing -------------------------------------------------------------------------------
     def _workspace_for(self, device, nbytes):
         ws = self._workspace
         if ws is None or ws.device != device or ws.numel() < nbytes:
@@ -249,10 +377,8 @@ class PAALossComputation(object):
             self._workspace = ws
         return ws
 
-    def _run(self, box_cls, box_reg, iou_pred, targets, anchors, need_grad):
-        lv = gather_levels(box_cls, box_reg, iou_pred, anchors)
-        N, L, A = lv["N"], lv["L"], lv["A"]
-        device = lv["cls"][0].device
+    def _collect_targets(self, targets, anchors, N):
+        """Per-image GT ranges and the tensors to concatenate, with the reference's checks."""
         if len(targets) != N:
             raise RuntimeError("targets lists %d images, heads have batch %d" % (len(targets), N))
         if N > _lib.MAX_IMAGES:
@@ -267,16 +393,15 @@ class PAALossComputation(object):
             offsets.append(sum_g)
             boxes.append(b)
             labels.append(t.get_field("labels"))
-        gt_boxes = torch.cat(boxes, dim=0)
-        if gt_boxes.dtype != torch.float32 or gt_boxes.device != device:
-            gt_boxes = gt_boxes.to(device=device, dtype=torch.float32)
-        gt_labels = torch.cat(labels, dim=0)
-        if gt_labels.dtype != torch.int64 or gt_labels.device != device:
-            gt_labels = gt_labels.to(device=device, dtype=torch.int64)
-        has_iou = iou_pred is not None
-        # the RetinaNet loss normalises by this rank's own counts (retinanet/loss.py:70,79): no exchange
-        world = 1 if self._flavour == _lib.LOSS_RETINANET else get_num_gpus()
+        return offsets, boxes, labels, sum_g
 
+    def _world(self):
+        # the RetinaNet loss normalises by this rank's own counts (retinanet/loss.py:70,79): no exchange
+        return 1 if self._flavour == _lib.LOSS_RETINANET else get_num_gpus()
+
+    def _make_args(self, lv, has_iou, world, grads):
+        """PaaLossArgs with everything that does not depend on the targets."""
+        N, L = lv["N"], lv["L"]
         args = _lib.PaaLossArgs()
         args.num_images, args.num_levels, args.num_classes = N, L, lv["C"]
         args.anchors_per_loc, args.topk = lv["apl"], self.topk
@@ -299,11 +424,6 @@ class PAALossComputation(object):
             args.fcos_iou_loss_type = _lib.IOU_LOSS_TYPES[self.iou_loss_type]
             args.fcos_norm_reg_targets = int(self.norm_reg_targets)
         args.anchor_image_stride = lv["anchor_stride"]
-        grads = None
-        if need_grad:
-            grads = dict(cls=[torch.empty_like(t) for t in lv["cls"]],
-                         reg=[torch.empty_like(t) for t in lv["reg"]],
-                         iou=[torch.empty_like(t) for t in lv["iou"]] if has_iou else None)
         cls_l, reg_l, iou_l = lv["cls"], lv["reg"], lv["iou"]
         anchor_ptrs, hw_l, grid_w = lv["anchor_ptrs"], lv["hw"], lv["grid_w"]
         levels = args.levels
@@ -317,6 +437,74 @@ class PAALossComputation(object):
                 s.grad_box_cls, s.grad_box_regression = grads["cls"][l].data_ptr(), grads["reg"][l].data_ptr()
                 if has_iou:
                     s.grad_iou_pred = grads["iou"][l].data_ptr()
+        return args
+
+    @staticmethod
+    def _alloc_grads(lv, has_iou):
+        """Gradient tensors shaped like the heads, cut from ONE allocation (15 allocator calls -> 1)."""
+        groups = [lv["cls"], lv["reg"]] + ([lv["iou"]] if has_iou else [])
+        # every piece starts on a 16-byte boundary: the kernels write float4
+        sizes = [[(t.numel() + 3) // 4 * 4 for t in g] for g in groups]
+        flat = torch.empty(sum(sum(g) for g in sizes), dtype=torch.float32, device=lv["cls"][0].device)
+        out, o = [], 0
+        for g, sz in zip(groups, sizes):
+            views = []
+            for t, n in zip(g, sz):
+                views.append(flat[o:o + t.numel()].view(t.shape))
+                o += n
+            out.append(views)
+        return dict(cls=out[0], reg=out[1], iou=out[2] if has_iou else None, flat=flat)
+
+    def _assign_fn(self):
+        name = {_lib.LOSS_PAA: "paa_assign", _lib.LOSS_ATSS: "paa_atss_assign",
+                _lib.LOSS_RETINANET: "paa_retinanet_assign", _lib.LOSS_FCOS: "paa_fcos_assign"}[self._flavour]
+        return name, getattr(self._lib, name)
+
+    def _launch(self, args, device, world, normalisers, dbg):
+        """Enqueues the step described by `args` on torch's current stream."""
+        stream = _lib.stream_handle(device)
+        assign_name, assign = self._assign_fn()
+        with _lib.device_guard(device):
+            peer = PeerNormExchange.get(device) if world > 1 else None
+            if peer is not None:
+                peer.raise_if_timed_out()
+                args.rank = peer.rank
+                for r, ptr in enumerate(peer.ptrs):
+                    args.peer_norm[r] = ptr
+                args.peer_timeout_s = peer.timeout_s
+                args.peer_status = peer.status.data_ptr()
+            if world == 1 and self._flavour == _lib.LOSS_PAA:
+                # one rank: nothing crosses ranks between the two halves -- the single fused entry point
+                _lib.check(self._lib.paa_assign_loss(C.byref(args), stream), "paa_assign_loss")
+                if dbg is not None:
+                    dbg["local_normalisers"] = normalisers
+            else:
+                _lib.check(assign(C.byref(args), stream), assign_name)
+                if dbg is not None:
+                    dbg["local_normalisers"] = normalisers.clone()  # this rank's own pair, before the exchange
+                if world > 1 and peer is None:
+                    reduce_normalisers(normalisers)                     # loss.py:321,338 in one message
+                _lib.check(self._lib.paa_loss(C.byref(args), stream), "paa_loss")
+
+    def _run(self, box_cls, box_reg, iou_pred, targets, anchors, need_grad):
+        if self.use_graph and not self.debug and self.teacher_combined_loss is None:
+            out = self._run_graphed(box_cls, box_reg, iou_pred, targets, anchors, need_grad)
+            if out is not None:
+                return out
+        lv = gather_levels(box_cls, box_reg, iou_pred, anchors)
+        N, L, A = lv["N"], lv["L"], lv["A"]
+        device = lv["cls"][0].device
+        offsets, boxes, labels, sum_g = self._collect_targets(targets, anchors, N)
+        gt_boxes = torch.cat(boxes, dim=0)
+        if gt_boxes.dtype != torch.float32 or gt_boxes.device != device:
+            gt_boxes = gt_boxes.to(device=device, dtype=torch.float32)
+        gt_labels = torch.cat(labels, dim=0)
+        if gt_labels.dtype != torch.int64 or gt_labels.device != device:
+            gt_labels = gt_labels.to(device=device, dtype=torch.int64)
+        has_iou = iou_pred is not None
+        world = self._world()
+        grads = self._alloc_grads(lv, has_iou) if need_grad else None
+        args = self._make_args(lv, has_iou, world, grads)
         args.gt_boxes, args.gt_labels = gt_boxes.data_ptr(), gt_labels.data_ptr()
         args.gt_offsets[:N + 1] = offsets
         nbytes = self._lib.paa_loss_workspace_bytes(N, A, sum_g, L, self.topk)
@@ -346,20 +534,7 @@ class PAALossComputation(object):
             teacher = teacher.to(device=device, dtype=torch.float32).contiguous()
             assert teacher.shape == (N, A)
             args.teacher_combined_loss = teacher.data_ptr()
-        stream = _lib.stream_handle(device)
-        assign_name = {_lib.LOSS_PAA: "paa_assign", _lib.LOSS_ATSS: "paa_atss_assign",
-                       _lib.LOSS_RETINANET: "paa_retinanet_assign", _lib.LOSS_FCOS: "paa_fcos_assign"}[self._flavour]
-        assign = getattr(self._lib, assign_name)
-        with _lib.device_guard(device):
-            peer = PeerNormExchange.get(device) if world > 1 else None
-            if peer is not None:
-                args.rank = peer.rank
-                for r, ptr in enumerate(peer.ptrs):
-                    args.peer_norm[r] = ptr
-            _lib.check(assign(C.byref(args), stream), assign_name)
-            if world > 1 and peer is None:
-                reduce_normalisers(normalisers)                         # loss.py:321,338 in one message
-            _lib.check(self._lib.paa_loss(C.byref(args), stream), "paa_loss")
+        self._launch(args, device, world, normalisers, dbg)
         if dbg is not None:
             dbg["normalisers"] = normalisers
             dbg["gt_offsets"] = offsets
@@ -367,6 +542,24 @@ class PAALossComputation(object):
         # keep every tensor whose pointer the kernels use alive until the stream work is enqueued
         call = dict(args=args, keep=(lv, gt_boxes, gt_labels, ws, normalisers, teacher), device=device)
         return losses, grads, call
+
+    # -- graph mode -----------------------------------------------------------------------------
+    def _run_graphed(self, box_cls, box_reg, iou_pred, targets, anchors, need_grad):
+        """The step as ONE graph launch.  Returns None when this batch cannot take the captured path (too many
+        ground-truth boxes for the capacities the graph was planned with): the caller then runs eagerly."""
+        has_iou = iou_pred is not None
+        heads = list(box_cls) + list(box_reg) + (list(iou_pred) if has_iou else [])
+        if not heads or not _anchors_shared(anchors, len(anchors), len(box_cls)):
+            return None                  # per-image anchor tensors are stacked afresh on every call: nothing to pin
+        key = (tuple(t.data_ptr() for t in heads), heads[0].shape[0], tuple(b.bbox.data_ptr() for b in anchors[0]),
+               bool(need_grad), self._world())
+        entry = self._graphs.get(key)
+        if entry is None:
+            if len(self._graphs) >= 8:                       # bounded: a training loop cycles through few shapes
+                self._graphs.pop(next(iter(self._graphs)))
+            entry = _GraphedStep(self, box_cls, box_reg, iou_pred, anchors, need_grad)
+            self._graphs[key] = entry
+        return entry.run(targets, anchors)
 
     def _rescale(self, call, grad_losses):
         """Brings the gradients written by the forward pass (upstream gradients of one) to `grad_losses`.  A call
@@ -433,12 +626,7 @@ class ATSSLossComputation(PAALossComputation):
         self.reg_loss_type = "iou"
         self.iou_loss_weight = 1.0                   # centerness loss carries no extra weight (atss/loss.py:273)
         self.reg_loss_weight = float(atss.REG_LOSS_WEIGHT)
-        self._lib = _lib.load()
-        self.debug = False
-        self.last_debug = None
-        self.teacher_combined_loss = None
-        self._workspace = None
-        self._ones = None
+        self._init_runtime()
         self._flavour = _lib.LOSS_ATSS
 
     def __call__(self, box_cls, box_regression, centerness, targets, anchors):
@@ -488,12 +676,7 @@ class RetinaNetLossComputation(PAALossComputation):
         self.topk = 1                                # unused by this flavour
         self.iou_loss_weight = 0.0
         self.reg_loss_weight = 1.0
-        self._lib = _lib.load()
-        self.debug = False
-        self.last_debug = None
-        self.teacher_combined_loss = None
-        self._workspace = None
-        self._ones = None
+        self._init_runtime()
         self._flavour = _lib.LOSS_RETINANET
 
     def forward_backward(self, anchors, box_cls, box_regression, targets, grad_losses=None):
@@ -515,6 +698,28 @@ def make_retinanet_loss_evaluator(cfg, box_coder):
     focal = SimpleNamespace(gamma=rn.LOSS_GAMMA, alpha=rn.LOSS_ALPHA)
     return RetinaNetLossComputation(matcher, box_coder, generate_retinanet_labels, focal,
                                     bbox_reg_beta=rn.BBOX_REG_BETA, regress_norm=rn.BBOX_REG_WEIGHT)
+
+
+_POINTS_CACHE_ENTRIES = 16
+
+
+def points_of(cache, locations):
+    """The FCOS locations of every level as degenerate boxes (x, y, x, y).  The reference rebuilds its location
+    tensors on every forward (fcos/fcos.py:185-209) and frees them, so a cache keyed by address would return stale
+    points once the allocator hands the address to a different grid: an entry is only reused for the very same
+    tensor object at the same version (`entry[0] is loc`; holding `loc` also keeps its address from being recycled),
+    and the cache is bounded."""
+    out = []
+    for loc in locations:
+        key = id(loc)
+        hit = cache.get(key)
+        if hit is None or hit[0] is not loc or hit[1] != loc._version:
+            if len(cache) >= _POINTS_CACHE_ENTRIES:
+                cache.pop(next(iter(cache)))
+            hit = (loc, loc._version, torch.cat([loc, loc], dim=1).to(torch.float32).contiguous())
+            cache[key] = hit
+        out.append(hit[2])
+    return out
 
 
 class _Points(object):
@@ -546,25 +751,14 @@ class FCOSLossComputation(PAALossComputation):
         self.topk = 1
         self.iou_loss_weight = 1.0
         self.reg_loss_weight = 1.0
-        self._lib = _lib.load()
-        self.debug = False
-        self.last_debug = None
-        self.teacher_combined_loss = None
-        self._workspace = None
-        self._ones = None
+        self._init_runtime()
         self._flavour = _lib.LOSS_FCOS
         self._points = {}
 
     def _as_points(self, locations, targets):
         if len(locations) > len(self.fpn_strides) or len(locations) > 5:
             raise IndexError("list index out of range")               # object_sizes_of_interest[l], fcos/loss.py:116
-        points = []
-        for loc in locations:
-            key = (loc.data_ptr(), tuple(loc.shape))
-            if key not in self._points:
-                self._points[key] = torch.cat([loc, loc], dim=1).to(torch.float32).contiguous()
-            points.append(self._points[key])
-        return [[_Points(p, t.size) for p in points] for t in targets]
+        return [[_Points(p, t.size) for p in points_of(self._points, locations)] for t in targets]
 
     def forward_backward(self, locations, box_cls, box_regression, centerness, targets, grad_losses=None):
         return super(FCOSLossComputation, self).forward_backward(box_cls, box_regression, centerness, targets,

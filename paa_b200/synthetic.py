@@ -266,3 +266,16 @@ def to_device_inputs(batch, device="cuda", requires_grad=False):
         targets.append(t)
         anchors.append([BoxList(a, batch.image_sizes[i], mode="xyxy") for a in anc])
     return cls, reg, iou, targets, anchors
+
+
+def slice_batch(batch, start, stop):
+    """Images [start, stop) of a batch as a batch of its own (one rank's share of a global batch: the reference's
+    DistributedSampler split, data/build.py:110-115).  Anchors / grids are shared, head tensors are contiguous
+    copies."""
+    sl = slice(start, stop)
+    return SyntheticBatch(image_sizes=batch.image_sizes[sl], grids=batch.grids, anchors=batch.anchors,
+                          gt_boxes=batch.gt_boxes[sl], gt_labels=batch.gt_labels[sl],
+                          box_cls=[t[sl].contiguous() for t in batch.box_cls],
+                          box_regression=[t[sl].contiguous() for t in batch.box_regression],
+                          iou_pred=None if batch.iou_pred is None else [t[sl].contiguous() for t in batch.iou_pred],
+                          meta=dict(batch.meta, slice=(start, stop)))

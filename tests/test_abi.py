@@ -30,7 +30,8 @@ def test_struct_layout_matches_header(tmp_path):
     fields_loss = ["num_images", "gamma", "anchor_image_stride", "levels", "gt_boxes", "gt_offsets",
                    "workspace", "normalisers", "grad_losses", "dbg_matched_idx", "teacher_combined_loss", "rank",
                    "peer_norm", "bg_iou_threshold", "box_code_weights", "smooth_l1_beta", "reg_norm_weight", "fcos_strides",
-                   "fcos_center_radius", "fcos_iou_loss_type", "fcos_norm_reg_targets", "atss_positive_type"]
+                   "fcos_center_radius", "fcos_iou_loss_type", "fcos_norm_reg_targets", "atss_positive_type",
+                   "peer_timeout_s", "peer_status", "gt_offsets_dev", "gt_capacity", "gt_per_image_capacity"]
     fields_post = ["num_images", "pre_nms_thresh", "anchor_image_stride", "levels", "image_wh", "workspace",
                    "out_boxes", "out_count", "dbg_pre_boxes", "dbg_nms_keep", "box_decode", "decode_weights",
                    "decode_clip"]

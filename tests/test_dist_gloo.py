@@ -207,3 +207,38 @@ def test_reference_atss_and_fcos_under_two_ranks_match_the_oracles_normalisation
             ol = fcos_oracle.losses(s.box_cls, s.box_regression, s.iou_pred, asgs[r], total_num_pos=tot_pos,
                                     total_sum_centerness=tot_ctr, world_size=world)
         np.testing.assert_allclose([float(x) for x in ol], got[r]["fcos"], rtol=1e-6)
+
+
+# ---- the peer exchange's set-up falls back collectively, before anybody enters the rendezvous ---------------------
+def _fallback_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), WORLD_SIZE=str(world), RANK=str(rank))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from paa_b200 import loss as paa_loss
+
+        def rendezvous_must_not_run(self, device, buffer):
+            raise AssertionError("rank %d entered the rendezvous although a peer could not allocate" % rank)
+
+        paa_loss.PeerNormExchange.__init__ = rendezvous_must_not_run
+        if rank == 0:      # this rank could allocate; rank 1 runs the real allocation, which fails on a CPU device
+            paa_loss.PeerNormExchange._allocate = staticmethod(lambda device: torch.zeros(8, dtype=torch.float64))
+        import warnings
+        with warnings.catch_warnings(record=True) as caught:
+            warnings.simplefilter("always")
+            state = paa_loss.PeerNormExchange.get(torch.device("cpu"))
+        assert state is None
+        # only the rank that failed explains why; both go on to the all-reduce
+        assert (len([w for w in caught if "peer-memory" in str(w.message)]) > 0) == (rank == 1)
+        t = torch.tensor([1.0 + rank, 2.0], dtype=torch.float64)
+        paa_loss.reduce_normalisers(t)
+        np.save(os.path.join(out_dir, "fallback%d.npy" % rank), t.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_peer_exchange_falls_back_collectively_when_one_rank_cannot_allocate(tmp_path):
+    world = 2
+    mp.spawn(_fallback_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    for k in range(world):
+        np.testing.assert_array_equal(np.load(tmp_path / ("fallback%d.npy" % k)), [3.0, 4.0])

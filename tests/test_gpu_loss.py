@@ -8,8 +8,8 @@ import torch
 
 from oracle import make_golden, paa_oracle
 from paa_b200 import synthetic
-from tests.helpers import (flat_levels, gmm_tie_exempt, load_golden, loss_case_batch, to_device_inputs,
-                           topk_tie_exempt)
+from tests.helpers import (assert_grads_close, check_losses_and_grads_against_oracle, flat_levels, gmm_tie_exempt,
+                           load_golden, loss_case_batch, to_device_inputs, topk_tie_exempt)
 
 pytestmark = pytest.mark.gpu
 
@@ -84,26 +84,30 @@ def test_end_to_end_losses_and_grads_against_recorded_reference(name):
     losses, cls, reg, iou = _run(ev, b)
     got_labels = ev.last_debug["paa_labels"].cpu().numpy()
     same_labels = np.array_equal(got_labels, ref["paa_labels"])
-    if same_labels:   # otherwise a documented tie flipped a positive set; covered by the stage-wise test
+    _, _, asg = paa_oracle.assign_and_loss(b.box_cls, b.box_regression, b.iou_pred, b.gt_boxes,
+                                           b.gt_labels, b.anchors, with_grad=False)
+    if same_labels:
         np.testing.assert_allclose([float(x) for x in losses], ref["losses"], rtol=RTOL)
-        np.testing.assert_allclose(flat_levels([t.grad for t in cls]), ref["grad_cls"], rtol=RTOL, atol=1e-9)
-        np.testing.assert_allclose(flat_levels([t.grad for t in reg]), ref["grad_reg"], rtol=1e-3, atol=1e-7)
-        np.testing.assert_allclose(flat_levels([t.grad for t in iou])[..., 0], ref["grad_iou"], rtol=RTOL, atol=1e-8)
-    else:
-        _, _, asg = paa_oracle.assign_and_loss(b.box_cls, b.box_regression, b.iou_pred, b.gt_boxes,
-                                               b.gt_labels, b.anchors, with_grad=False)
+        assert_grads_close(flat_levels([t.grad for t in cls]), ref["grad_cls"], rtol=RTOL, atol=1e-9, what="grad_cls")
+        assert_grads_close(flat_levels([t.grad for t in reg]), ref["grad_reg"], rtol=RTOL, row_atol=1e-5,
+                           what="grad_reg")
+        assert_grads_close(flat_levels([t.grad for t in iou])[..., 0], ref["grad_iou"], rtol=RTOL,
+                           atol=2e-6 * float(np.abs(ref["grad_iou"]).max()), what="grad_iou")
+    else:          # a documented tie flipped a positive set: the flipped GTs must be exempt ...
         exempt = topk_tie_exempt(asg, rel=1e-4) | gmm_tie_exempt(asg, abs_tol=1e-4)
         diff = {(i, int(ref["matched_idx"][i][a])) for i, a in zip(*np.nonzero(got_labels != ref["paa_labels"]))}
         assert diff <= exempt, (name, diff - exempt)
+    # ... and in every case losses and gradients must be the oracle's for the labels the device chose
+    check_losses_and_grads_against_oracle(b, asg, got_labels, losses, cls, reg, iou)
 
 
 def _assert_matches_oracle(b, max_exempt, **cfg_overrides):
     """Free-running comparison of one batch with the oracle run on this machine's CPU."""
     names = {"LOSS_GAMMA": "gamma", "LOSS_ALPHA": "alpha"}
     oracle_kw = {names.get(k, k.lower()): v for k, v in cfg_overrides.items()}
-    ref_losses, ref_grads, asg = paa_oracle.assign_and_loss(b.box_cls, b.box_regression, b.iou_pred,
-                                                            b.gt_boxes, b.gt_labels, b.anchors,
-                                                            params=paa_oracle.default_params(**oracle_kw))
+    ref_losses, _, asg = paa_oracle.assign_and_loss(b.box_cls, b.box_regression, b.iou_pred,
+                                                    b.gt_boxes, b.gt_labels, b.anchors,
+                                                    params=paa_oracle.default_params(**oracle_kw), with_grad=False)
     ev = _evaluator(**cfg_overrides)
     ev.debug = True
     losses, cls, reg, iou = _run(ev, b)
@@ -116,12 +120,10 @@ def _assert_matches_oracle(b, max_exempt, **cfg_overrides):
     diff = {(i, int(asg.matched_idx[i][a])) for i, a in zip(*np.nonzero(got != asg.paa_labels.numpy()))}
     assert diff <= exempt, diff - exempt
     assert len(diff) <= max_exempt
+    # never skipped: with flipped (exempt) ties the oracle's stage 5 runs on the device's labels
+    check_losses_and_grads_against_oracle(b, asg, got, losses, cls, reg, iou)
     if not diff:
         np.testing.assert_allclose([float(x) for x in losses], [float(x) for x in ref_losses], rtol=RTOL)
-        np.testing.assert_allclose(flat_levels([t.grad for t in cls]), flat_levels(ref_grads.box_cls),
-                                   rtol=RTOL, atol=1e-9)
-        np.testing.assert_allclose(flat_levels([t.grad for t in reg]), flat_levels(ref_grads.box_regression),
-                                   rtol=1e-3, atol=1e-7)
     return len(diff)
 
 
@@ -131,6 +133,16 @@ def test_c1_against_oracle_full_resolution():
     _assert_matches_oracle(b, max_exempt=2)
 
 
+def test_c2_bench_batch_against_oracle():
+    """The exact batch bench.py times (config C2: seed 2000, 16 images of 800x1333, 1..100 GT each -- 861 GTs,
+    16 x 22 400 anchors) against the oracle: matched indices bit-exact, labels bit-exact modulo counted tie
+    exemptions, anchor scores, losses and all gradients to 1e-4."""
+    from bench import C2_BATCH_KW
+    b = synthetic.make_batch(**C2_BATCH_KW)
+    assert b.num_images == 16 and b.num_anchors == 22400
+    _assert_matches_oracle(b, max_exempt=8)
+
+
 def test_without_iou_pred():
     b = synthetic.make_batch(seed=32, num_images=1, image_hw=(256, 256), gt_per_image=5)
     ref_losses, _, asg = paa_oracle.assign_and_loss(b.box_cls, b.box_regression, None, b.gt_boxes, b.gt_labels,
@@ -138,9 +150,15 @@ def test_without_iou_pred():
                                                     with_grad=False)
     ev = _evaluator(USE_IOU_PRED=False)
     ev.debug = True
-    losses, *_ = _run(ev, b, requires_grad=True, use_iou=False)
+    losses, *_ = _run(ev, b, requires_grad=True, use_iou=False)      # _ = [cls, reg, iou]
     assert len(losses) == 2
-    if np.array_equal(ev.last_debug["paa_labels"].cpu().numpy(), asg.paa_labels.numpy()):
+    got = ev.last_debug["paa_labels"].cpu().numpy()
+    exempt = topk_tie_exempt(asg, rel=1e-4) | gmm_tie_exempt(asg, abs_tol=1e-4)
+    diff = {(i, int(asg.matched_idx[i][a])) for i, a in zip(*np.nonzero(got != asg.paa_labels.numpy()))}
+    assert diff <= exempt and len(diff) <= 1, diff - exempt
+    cls, reg = _[0], _[1]
+    check_losses_and_grads_against_oracle(b, asg, got, losses, cls, reg, None)
+    if not diff:
         np.testing.assert_allclose([float(x) for x in losses], [float(x) for x in ref_losses], rtol=RTOL)
 
 

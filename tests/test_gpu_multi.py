@@ -41,6 +41,11 @@ def _worker(rank, world, port, out):
     res["peer_losses"] = losses.cpu().numpy()
     res["peer_norm"] = ev.last_debug["normalisers"].cpu().numpy()
     res["peer_grad0"] = grads["cls"][0].cpu().numpy()
+    # a rank that arrives 3 s late (rank 0 saving a checkpoint, a data-loader stall) is simply waited for
+    if rank == 1:
+        import time
+        time.sleep(3.0)
+    res["peer_losses_delayed"] = ev.forward_backward(cls, reg, iou, targets, anchors)[0].cpu().numpy()
     # graph replay: the epoch counter lives in device memory, so replays stay in step across ranks
     ev.debug = False
     for _ in range(2):
@@ -128,6 +133,7 @@ def test_peer_exchange_matches_all_reduce_and_oracle(tmp_path):
         np.testing.assert_allclose(res[r]["peer_norm"], [tot_pos, tot_iou], rtol=1e-6)
         np.testing.assert_array_equal(res[r]["peer_losses"], res[r]["nccl_losses"])
         np.testing.assert_array_equal(res[r]["peer_losses"], res[r]["graph_losses"])
+        np.testing.assert_array_equal(res[r]["peer_losses"], res[r]["peer_losses_delayed"])
         np.testing.assert_array_equal(res[r]["peer_grad0"], res[r]["nccl_grad0"])
         np.testing.assert_array_equal(res[r]["atss_peer_losses"], res[r]["atss_nccl_losses"])
         assert np.isfinite(res[r]["atss_peer_losses"]).all()

@@ -135,3 +135,24 @@ def test_anchor_sharing_is_detected_by_identity_or_address():
     assert L._anchors_shared(views, 3, n_levels)
     views[2][1] = paa_b200.BoxList(anchors[2][1].bbox.clone(), anchors[2][1].size)               # own copy
     assert not L._anchors_shared(views, 3, n_levels)
+
+
+def test_fcos_points_cache_is_validated_and_bounded():
+    """a cache keyed by address returned stale points when the allocator reused an address; entries are
+    now tied to the tensor object and its version, and the cache is bounded."""
+    import torch
+    from paa_b200.loss import points_of, _POINTS_CACHE_ENTRIES
+    cache = {}
+    a = torch.rand(10, 2)
+    p1 = points_of(cache, [a])[0]
+    assert points_of(cache, [a])[0] is p1                 # same tensor, same version: reused
+    a.add_(1.0)                                           # in-place update bumps the version
+    p2 = points_of(cache, [a])[0]
+    assert p2 is not p1 and torch.equal(p2[:, :2], a) and torch.equal(p2[:, 2:], a)
+    seen = set()
+    for _ in range(3 * _POINTS_CACHE_ENTRIES):            # a new grid every forward, like fcos.py:185-209
+        loc = torch.rand(3, 2)
+        q = points_of(cache, [loc])[0]
+        assert torch.equal(q[:, :2], loc)
+        seen.add(id(loc))
+    assert len(cache) <= _POINTS_CACHE_ENTRIES

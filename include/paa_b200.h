@@ -298,13 +298,14 @@ int paa_box_vote(const float* boxes, const float* scores, const float* labels, i
 /* Measurement aid (not on the reference's interface): while enabled, every launch of the chosen kernel
  * is bracketed by CUDA events on its own stream; paa_kernel_timing_end waits for them and returns the
  * summed device time and the number of launches.  Do not enable during CUDA-graph capture. */
-#define PAA_KERNEL_PASS1        1   /* assign_pass1_kernel: IoU matching + class sums of the logits */
+#define PAA_KERNEL_PASS1        1   /* iou_match_kernel: every anchor's best GT, every GT's maximal IoU */
 #define PAA_KERNEL_MATCH_SCORE  2
 #define PAA_KERNEL_SELECT_GMM   3
 #define PAA_KERNEL_FINAL_LOSS   4   /* bulk_focal_kernel: every logit read once, its gradient written once */
 #define PAA_KERNEL_POSITIVE_TERMS 5 /* positive_terms_kernel */
 #define PAA_KERNEL_FINISH_LOSS  6   /* finish_loss_kernel */
 #define PAA_KERNEL_NORM_WAIT    7   /* norm_wait_kernel (peer exchange only) */
+#define PAA_KERNEL_PREP_STEP    8   /* prep_step_kernel: workspace prefix cleared, GT ranges to device memory */
 #define PAA_KERNEL_POST_CANDIDATES 10
 #define PAA_KERNEL_POST_FILTER  11
 #define PAA_KERNEL_POST_SELECT  12

@@ -309,7 +309,7 @@ int paa_assign(const PaaLossArgs* args, void* stream_) {
     // into parts), uploads the GT ranges
     if ((rc = launch_prep_step(p.geo, p.go, args->gt_offsets_dev, p.sc, p.ws, args->workspace, true, false, stream)))
         return rc;
-    if ((rc = launch_assign_pass1(p.geo, args->gt_boxes, p.sc, p.ws, stream))) return rc;
+    if ((rc = launch_iou_match(p.geo, args->gt_boxes, p.sc, p.ws, stream))) return rc;
     const float* score_src = args->teacher_combined_loss ? args->teacher_combined_loss : p.ws.score;
     if ((rc = launch_match_score(p.geo, args->gt_boxes, args->gt_labels, p.sc, p.ws,
                                  args->teacher_combined_loss, p.dbg, stream)))

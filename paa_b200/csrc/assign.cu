@@ -18,77 +18,93 @@
 namespace paa {
 
 // ---------------------------------------------------------------------------------------------
-// K1: the first pass of the assignment, two independent jobs in ONE launch (horizontal fusion):
+// K1: IoU matching -- every anchor's best GT (first maximum) and every GT's maximal IoU
+// (boxlist_iou + the two reductions of Matcher, boxlist_ops.py:81-116 / matcher.py:66,92), without the [G, A]
+// matrix.  Touches no head tensor.
 //
-//  (a) IoU matching -- every anchor's best GT (first maximum) and every GT's maximal IoU.  A block takes
-//      two tiles of 128 consecutive anchors of one image.  GT boxes are staged in shared memory in
-//      chunks; a warp only evaluates the GTs whose box intersects the warp's bounding box
-//      (non-intersecting pairs have IoU exactly +0 and can neither raise a maximum nor win the
-//      first-maximum rule against the initial (0, GT 0)).  Issue/latency-bound, touches no head tensor.
-//  (b) class sums -- negsum[n, a] = sum_c p_c^gamma * softplus(x_c) for EVERY anchor, all classes taken
-//      as negatives.  The anchor score of an IoU-positive anchor is this sum with the labelled class's
-//      term swapped for the positive one (match_score_kernel), so this streaming pass is the only one
-//      over the logits that the assignment needs.  Memory-bound (every logit read once).
-//      Fast path (one anchor per location, H*W a multiple of 4, 16-byte aligned base): a block takes 256
-//      consecutive anchors of one level of one image as 64 float4 columns x 4 class groups.  A thread
-//      walks its group's C/4 class rows of one column, four loads in flight; a warp reads 512 contiguous
-//      bytes per row.  The four partial sums of a column are combined in a fixed order through shared
-//      memory.  Generic path: one thread per anchor, classes in order.  (40 registers, six blocks per SM:
-//      measured better than deeper per-thread prefetching at four blocks per SM.)
-//
-// Blocks of the two jobs alternate in the grid, so every SM holds both kinds at once and the matching
-// arithmetic runs in the shadow of the logit stream.  (As two launches on two streams the second kernel
-// only got the SM resources the first one left over, i.e. its tail.)
+// Every WARP works on its own: 32 anchors (an 8 x 4 patch of a fine level's grid where the grid width is known --
+// a compact footprint intersects ~35 % fewer GT boxes than 32 neighbours in a row -- else 32 consecutive anchors),
+// the image's GT boxes 32 at a time, one per lane, straight from global memory (L1-resident after the first
+// warp).  A lane whose GT intersects the warp's bounding box raises a ballot bit (non-intersecting pairs have IoU
+// exactly +0 and can neither raise a maximum nor win the first-maximum rule against the initial (0, GT 0)); the
+// round's boxes are parked in the warp's own slice of shared memory and the hits evaluated from there (branch-free,
+// bit-exact IoU; broadcast reads).  Per-GT maxima go to global memory as one RED.MAX per (warp, hit GT).  No
+// block barrier: round 1's block-staged version spent its time waiting (30 us alone on the C2 batch).
+// For crowded images the coarse levels, whose anchors overlap every GT, are additionally cut into `parts` ranges
+// of the GT list whose per-anchor results meet in an atomicMax on packed (IoU, GT) keys.
 // ---------------------------------------------------------------------------------------------
-constexpr int kGtChunk = 256;
 constexpr int kPassThreads = 256;
-constexpr int kSumCols = 64;                 // float4 columns per block (fast path of the class sums)
-constexpr int kSumGroups = kPassThreads / kSumCols;
 
 struct Pass1Plan {
-    unsigned item_off[PAA_MAX_LEVELS + 1];   // class sums: first work item of each level
-    unsigned chunks[PAA_MAX_LEVELS];         //             chunks per image
-    unsigned char vec[PAA_MAX_LEVELS];       //             float4 path
-    unsigned sum_blocks, iou_blocks;
-    // IoU matching: tiles below `light_tiles` (fine levels) go two to a block over all GTs of the image; the
-    // tiles of the coarse levels, whose anchors overlap every GT, are additionally cut into `parts` ranges of
-    // the GT list (their per-anchor results meet in an atomicMax), so that no warp walks hundreds of GTs alone
+    unsigned iou_blocks;
+    // tiles below `light_tiles` (fine levels) go two to a block over all GTs of the image; the tiles of the coarse
+    // levels are additionally cut into `parts` ranges of the GT list
     int light_tiles, light_pairs, heavy_pairs, parts;
-    // With the grid width of the fine levels known (and one anchor per location) a block of the IoU matching
-    // takes a 32 x 8 region of a level's grid instead of two runs of 128 consecutive anchors, and a warp an
-    // 8 x 4 patch instead of 32 neighbours in a row: a compact footprint intersects ~35 % fewer GT boxes.
-    int patches;                                 // 1: fine levels are matched in patches
-    unsigned patch_off[PAA_MAX_LEVELS + 1];      // first region of each fine level (per image)
+    int patches;                                 // 1: fine levels are matched in 8 x 4 patches per warp
+    unsigned patch_off[PAA_MAX_LEVELS + 1];      // first 32 x 8 region of each fine level (per image)
     int patch_rx[PAA_MAX_LEVELS];                // regions per grid row
 };
 
-// One negative-class focal term without its (1-alpha) factor: p^gamma * softplus(x).
-__device__ __forceinline__ float neg_term_only(float x, float gamma, bool g2) {
-    const SigmoidLean sl = sigmoid_lean(x);
-    return focal_pow(sl.p, gamma, g2) * sl.sp;
+// order-preserving map float -> unsigned (and back), so that floats compare / reduce as integers
+__device__ __forceinline__ unsigned ordered_bits(float v) {
+    unsigned u = __float_as_uint(v);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float from_ordered_bits(unsigned u) {
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
 }
 
-template <bool kG2>
-__device__ __forceinline__ void add_terms(float4& acc, float4 x, float gamma) {
-    acc.x += neg_term_only(x.x, gamma, kG2);
-    acc.y += neg_term_only(x.y, gamma, kG2);
-    acc.z += neg_term_only(x.z, gamma, kG2);
-    acc.w += neg_term_only(x.w, gamma, kG2);
-}
-
-union Pass1Smem {
-    struct {
-        float4 gt[kGtChunk];
-        float area[kGtChunk];
-        unsigned max[kGtChunk];
-    } iou;
-    float4 part[kSumGroups - 1][kSumCols];
+// The GT boxes of one round as the warp staged them (one per lane) and their areas.
+struct WarpGts {
+    float4 box[PAA_WARP];
+    float area[PAA_WARP];
 };
 
-__device__ __forceinline__ void iou_best_block(const Geometry& geo, const GtOffsets& go, unsigned q,
-                                               const Pass1Plan& plan, const float* __restrict__ gt_boxes,
-                                               unsigned* __restrict__ gtmax, unsigned long long* __restrict__ best,
-                                               Pass1Smem& sm) {
+template <int kWide>
+__device__ __forceinline__ void iou_hits(unsigned m, int c0, int lane, bool valid, const float4& a, float area_a,
+                                         const WarpGts& gts, float& best_v, int& best_g,
+                                         unsigned* __restrict__ gtmax_image) {
+    while (m) {
+        int js[kWide];
+        float qv[kWide];
+#pragma unroll
+        for (int u = 0; u < kWide; ++u) {
+            js[u] = __ffs(m) - 1;          // -1 once the hits are used up
+            m &= m - 1u;
+        }
+#pragma unroll
+        for (int u = 0; u < kWide; ++u) {
+            const int j = js[u] >= 0 ? js[u] : 0;
+            const float v = iou_plus1_flat(gts.box[j], gts.area[j], a, area_a);      // broadcast reads
+            qv[u] = (js[u] >= 0 && valid) ? v : 0.0f;
+        }
+#pragma unroll
+        for (int u = 0; u < kWide; ++u) {          // ascending GT order: the first-maximum rule of torch.max
+            if (qv[u] > best_v) {
+                best_v = qv[u];
+                best_g = c0 + js[u];
+            }
+        }
+        unsigned wm[kWide];
+#pragma unroll
+        for (int u = 0; u < kWide; ++u) wm[u] = __reduce_max_sync(PAA_FULL, __float_as_uint(qv[u]));
+        if (lane == 0) {
+#pragma unroll
+            for (int u = 0; u < kWide; ++u)
+                if (js[u] >= 0 && wm[u] != 0u) atomicMax(gtmax_image + c0 + js[u], wm[u]);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kPassThreads)
+iou_match_kernel(const Geometry geo, const GtOffsets* __restrict__ gop, const Pass1Plan plan,
+                 const float* __restrict__ gt_boxes, unsigned* __restrict__ gtmax,
+                 unsigned long long* __restrict__ best) {
+    pdl_launch_dependents();
+    pdl_wait();                       // the GT ranges and the cleared maxima come from prep_step_kernel
+    __shared__ WarpGts s_gts[kPassThreads / PAA_WARP];
+    const GtOffsets& go = *gop;
+    const unsigned q = blockIdx.x;
     // heaviest blocks first: the coarse levels (last tiles of an image) intersect every GT, and the
     // cost of a block grows with the GT count of its image
     const unsigned heavy_items = (unsigned)geo.num_images * (unsigned)plan.heavy_pairs * (unsigned)plan.parts;
@@ -117,9 +133,17 @@ __device__ __forceinline__ void iou_best_block(const Geometry& geo, const GtOffs
 #pragma unroll
         for (int k = 1; k < PAA_MAX_LEVELS; ++k)
             if (k < geo.num_levels && plan.patch_off[k] <= reg && plan.patch_off[k] < per_image) l = k;
-        const int rr = (int)(reg - plan.patch_off[l]);
+        unsigned off_l = plan.patch_off[0];
+        int prx = plan.patch_rx[0];
+#pragma unroll
+        for (int k = 1; k < PAA_MAX_LEVELS; ++k)       // selects, not indexed reads: the plan stays in the constant bank
+            if (k == l) {
+                off_l = plan.patch_off[k];
+                prx = plan.patch_rx[k];
+            }
+        const int rr = (int)(reg - off_l);
         const int W = geo.lv[l].grid_w, H = geo.lv[l].hw / W;
-        const int ry = rr / plan.patch_rx[l], rx = rr - ry * plan.patch_rx[l];
+        const int ry = rr / prx, rx = rr - ry * prx;
         const int w = threadIdx.x >> 5, ln = threadIdx.x & 31;
         const int col = rx * 32 + 8 * (w & 3) + (ln & 7), row = ry * 8 + 4 * (w >> 2) + (ln >> 3);
         valid = col < W && row < H;
@@ -134,201 +158,52 @@ __device__ __forceinline__ void iou_best_block(const Geometry& geo, const GtOffs
     }
     const LevelView& lv = geo.lv[l];
     const int lane = threadIdx.x & 31;
+    if (!__any_sync(PAA_FULL, valid)) return;          // warp-uniform: nothing of this warp lies inside the level
 
     float4 a = make_float4(INFINITY, INFINITY, -INFINITY, -INFINITY);
     if (valid) a = ldg4(lv.anchors + (size_t)n * geo.anchor_image_stride + (size_t)i * 4);
     const float area_a = area_plus1(a);
-    const float wx1 = warp_min(a.x), wy1 = warp_min(a.y), wx2 = warp_max(a.z), wy2 = warp_max(a.w);
+    // the warp's bounding box: four integer reductions on order-preserving keys
+    const float wx1 = from_ordered_bits(__reduce_min_sync(PAA_FULL, ordered_bits(a.x)));
+    const float wy1 = from_ordered_bits(__reduce_min_sync(PAA_FULL, ordered_bits(a.y)));
+    const float wx2 = from_ordered_bits(__reduce_max_sync(PAA_FULL, ordered_bits(a.z)));
+    const float wy2 = from_ordered_bits(__reduce_max_sync(PAA_FULL, ordered_bits(a.w)));
 
     const int gbase = go.v[n];
     const int G_all = go.v[n + 1] - gbase;
     const int g_lo = (int)(((long long)G_all * part) / parts), G = (int)(((long long)G_all * (part + 1)) / parts);
     float best_v = 0.0f;
     int best_g = 0;
-    const bool crowded = G_all > 128;
+    const bool crowded = G_all > 128, heavy = q < heavy_items;
+    unsigned* gtmax_image = gtmax + gbase;
 
-    for (int c0 = g_lo; c0 < G; c0 += kGtChunk) {
-        const int cnt = min(kGtChunk, G - c0);
-        for (int t = threadIdx.x; t < cnt; t += kPassThreads) {
-            float4 b = ldg4(gt_boxes + (size_t)(gbase + c0 + t) * 4);
-            sm.iou.gt[t] = b;
-            sm.iou.area[t] = area_plus1(b);
-            sm.iou.max[t] = 0u;
+    for (int c0 = g_lo; c0 < G; c0 += PAA_WARP) {
+        const int g = c0 + lane;
+        float4 b = make_float4(0.f, 0.f, -1.f, -1.f);
+        bool hit = false;
+        if (g < G) {
+            b = ldg4(gt_boxes + (size_t)(gbase + g) * 4);
+            const float w = __fadd_rn(__fsub_rn(fminf(b.z, wx2), fmaxf(b.x, wx1)), 1.0f);
+            const float h = __fadd_rn(__fsub_rn(fminf(b.w, wy2), fmaxf(b.y, wy1)), 1.0f);
+            hit = (w > 0.0f) && (h > 0.0f);
         }
-        __syncthreads();
-        for (int g0 = 0; g0 < cnt; g0 += PAA_WARP) {
-            const int g = g0 + lane;
-            bool hit = false;
-            if (g < cnt) {
-                float4 b = sm.iou.gt[g];
-                float w = __fadd_rn(__fsub_rn(fminf(b.z, wx2), fmaxf(b.x, wx1)), 1.0f);
-                float h = __fadd_rn(__fsub_rn(fminf(b.w, wy2), fmaxf(b.y, wy1)), 1.0f);
-                hit = (w > 0.0f) && (h > 0.0f);
-            }
-            unsigned m = __ballot_sync(PAA_FULL, hit);
-            if (!crowded) {
-                // the usual image (up to ~100 GTs): a handful of hits per warp, one at a time
-                while (m) {
-                    const int j = g0 + __ffs(m) - 1;
-                    m &= m - 1;
-                    float qv = 0.0f;
-                    if (valid) qv = iou_plus1(sm.iou.gt[j], sm.iou.area[j], a, area_a);
-                    if (qv > best_v) {
-                        best_v = qv;
-                        best_g = c0 + j;
-                    }
-                    unsigned wm = __reduce_max_sync(PAA_FULL, __float_as_uint(qv));
-                    if (lane == 0 && wm != 0u) atomicMax(&sm.iou.max[j], wm);
-                }
-                continue;
-            }
-            // crowded image: four hit GTs per trip -- their IoUs (branch-free form), warp maxima and
-            // shared-memory updates are independent chains, so the walk over hundreds of hits is no longer one
-            // long dependent chain.  The first-maximum rule is kept by folding them in ascending order.
-            while (m) {
-                int js[4];
-                float qv[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    js[u] = -1;
-                    if (m) {
-                        js[u] = g0 + __ffs(m) - 1;
-                        m &= m - 1;
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int j = js[u] >= 0 ? js[u] : 0;
-                    const float v = iou_plus1_flat(sm.iou.gt[j], sm.iou.area[j], a, area_a);
-                    qv[u] = (js[u] >= 0 && valid) ? v : 0.0f;
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    if (qv[u] > best_v) {
-                        best_v = qv[u];
-                        best_g = c0 + js[u];
-                    }
-                }
-                unsigned wm[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) wm[u] = __reduce_max_sync(PAA_FULL, __float_as_uint(qv[u]));
-                if (lane == 0) {
-#pragma unroll
-                    for (int u = 0; u < 4; ++u)
-                        if (js[u] >= 0 && wm[u] != 0u) atomicMax(&sm.iou.max[js[u]], wm[u]);
-                }
-            }
-        }
-        __syncthreads();
-        for (int t = threadIdx.x; t < cnt; t += kPassThreads)
-            if (sm.iou.max[t] != 0u) atomicMax(&gtmax[gbase + c0 + t], sm.iou.max[t]);
-        __syncthreads();
+        const unsigned m = __ballot_sync(PAA_FULL, hit);
+        if (m == 0u) continue;                                   // warp-uniform
+        WarpGts& gts = s_gts[threadIdx.x >> 5];
+        __syncwarp();                                            // the previous round's reads are done
+        gts.box[lane] = b;
+        gts.area[lane] = area_plus1(b);
+        __syncwarp();
+        // the kernel is bound by instruction issue: a fine level's warp (a handful of hits per round) takes its
+        // hits one at a time (no idle slots); the coarse levels, whose anchors overlap every GT, and crowded images
+        // take four at a time as independent chains -- their walk over all the GTs is the kernel's longest path
+        if (crowded || heavy) iou_hits<4>(m, c0, lane, valid, a, area_a, gts, best_v, best_g, gtmax_image);
+        else iou_hits<1>(m, c0, lane, valid, a, area_a, gts, best_v, best_g, gtmax_image);
     }
     if (valid) {
         unsigned long long* dst = best + (size_t)n * geo.A + lv.a_off + i;
         if (!split) *dst = pack_best(best_v, best_g);
-        else if (best_v > 0.0f) atomicMax(dst, pack_best(best_v, best_g));     // pre-zeroed by paa_assign
-    }
-}
-
-template <bool kG2>
-__device__ __forceinline__ void class_sum_block(const Geometry& geo, const Pass1Plan& plan, unsigned b,
-                                                float gamma, float* __restrict__ negsum, Pass1Smem& sm) {
-    int l = 0;
-#pragma unroll
-    for (int k = 1; k < PAA_MAX_LEVELS; ++k)
-        if (k < geo.num_levels && b >= plan.item_off[k]) l = k;
-    const LevelView& lv = geo.lv[l];
-    const unsigned item = b - plan.item_off[l];
-    const int n = (int)(item / plan.chunks[l]);
-    const int chunk = (int)(item - (unsigned)n * plan.chunks[l]);
-    const int C = geo.C;
-    if (plan.vec[l]) {
-        const int col = threadIdx.x & (kSumCols - 1), grp = threadIdx.x / kSumCols;
-        const int i = (chunk * kSumCols + col) * 4;                       // first of this column's 4 anchors
-        const bool in = i < lv.n_anchor;
-        const int cg = (C + kSumGroups - 1) / kSumGroups;
-        const int c_begin = grp * cg, c_end = min(C, c_begin + cg);
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (in) {
-            const unsigned st = (unsigned)lv.hw >> 2;                     // float4 per class row
-            const float4* p = reinterpret_cast<const float4*>(lv.cls + (size_t)n * C * lv.hw + i);
-            int c0 = c_begin;
-            for (; c0 + 4 <= c_end; c0 += 4) {
-                float4 x[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) x[j] = __ldg(p + (size_t)(c0 + j) * st);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) add_terms<kG2>(acc, x[j], gamma);
-            }
-            for (; c0 < c_end; ++c0) add_terms<kG2>(acc, __ldg(p + (size_t)c0 * st), gamma);
-        }
-        if (grp > 0) sm.part[grp - 1][col] = acc;
-        __syncthreads();
-        if (grp == 0 && in) {
-#pragma unroll
-            for (int g = 0; g < kSumGroups - 1; ++g) {
-                const float4 o = sm.part[g][col];
-                acc.x += o.x;
-                acc.y += o.y;
-                acc.z += o.z;
-                acc.w += o.w;
-            }
-            const size_t flat = (size_t)n * geo.A + lv.a_off + i;
-            if ((flat & 3) == 0) {
-                *reinterpret_cast<float4*>(negsum + flat) = acc;
-            } else {
-                negsum[flat] = acc.x;
-                negsum[flat + 1] = acc.y;
-                negsum[flat + 2] = acc.z;
-                negsum[flat + 3] = acc.w;
-            }
-        }
-    } else {
-        const int i = chunk * kPassThreads + threadIdx.x;
-        if (i >= lv.n_anchor) return;
-        const float* p = lv.cls + head_offset(n, i, 0, C, geo.apl, lv.hw);
-        const unsigned st = (unsigned)lv.hw;
-        float acc = 0.f;
-        int c0 = 0;
-        for (; c0 + 8 <= C; c0 += 8) {
-            float x[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) x[j] = __ldg(p + (size_t)(c0 + j) * st);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) acc += neg_term_only(x[j], gamma, kG2);
-        }
-        for (; c0 < C; ++c0) acc += neg_term_only(__ldg(p + (size_t)c0 * st), gamma, kG2);
-        negsum[(size_t)n * geo.A + lv.a_off + i] = acc;
-    }
-}
-
-template <bool kG2>
-__global__ void __launch_bounds__(kPassThreads, 6)
-assign_pass1_kernel(const Geometry geo, const GtOffsets* __restrict__ gop, const Pass1Plan plan, float gamma,
-                    const float* __restrict__ gt_boxes, unsigned* __restrict__ gtmax,
-                    unsigned long long* __restrict__ best, float* __restrict__ negsum) {
-    pdl_launch_dependents();
-    __shared__ Pass1Smem sm;
-    // the first 2*min(sum_blocks, iou_blocks) blocks alternate between the jobs, the rest belong to the longer one
-    const unsigned m = min(plan.sum_blocks, plan.iou_blocks);
-    const unsigned b = blockIdx.x;
-    bool is_iou;
-    unsigned idx;
-    if (b < 2 * m) {
-        is_iou = (b & 1u) == 0u;
-        idx = b >> 1;
-    } else {
-        is_iou = plan.iou_blocks > plan.sum_blocks;
-        idx = b - m;
-    }
-    if (is_iou) {
-        // the GT ranges and the cleared maxima come from prep_step_kernel, whose programmatic dependent this launch
-        // is; the class-sum blocks read nothing of it and stream the logits while it still runs
-        pdl_wait();
-        iou_best_block(geo, *gop, idx, plan, gt_boxes, gtmax, best, sm);
-    } else {
-        class_sum_block<kG2>(geo, plan, idx, gamma, negsum, sm);
+        else if (best_v > 0.0f) atomicMax(dst, pack_best(best_v, best_g));     // pre-zeroed by prep_step_kernel
     }
 }
 
@@ -406,6 +281,7 @@ int launch_prep_step(const Geometry& geo, const GtOffsets& host_go, const int* d
     const size_t work = zero_vec + (size_t)geo.num_images * n_best;
     int grid = (int)((work + 1023) / 1024);
     grid = grid < 1 ? 1 : (grid > 148 * 4 ? 148 * 4 : grid);
+    KernelTimer timer(PAA_KERNEL_PREP_STEP, stream);
     prep_step_kernel<<<grid, 256, 0, stream>>>(host_go, dev_offsets, geo.num_images, sc.gt_capacity, ws.go, ws.gt_image,
                                                reinterpret_cast<uint4*>(zero_base), zero_vec, ws.best, geo.A, a0,
                                                n_best);
@@ -413,24 +289,9 @@ int launch_prep_step(const Geometry& geo, const GtOffsets& host_go, const int* d
     return 0;
 }
 
-int launch_assign_pass1(const Geometry& geo, const float* gt_boxes, const LossScalars& sc,
-                        const LossWorkspace& ws, cudaStream_t stream, bool with_class_sums) {
+int launch_iou_match(const Geometry& geo, const float* gt_boxes, const LossScalars& sc, const LossWorkspace& ws,
+                     cudaStream_t stream) {
     Pass1Plan plan;
-    unsigned items = 0;
-    for (int l = 0; l < PAA_MAX_LEVELS; ++l) {
-        plan.item_off[l] = items;
-        plan.chunks[l] = 0;
-        plan.vec[l] = 0;
-        if (l >= geo.num_levels) continue;
-        const LevelView& lv = geo.lv[l];
-        const bool vec = geo.apl == 1 && (lv.hw & 3) == 0 && (reinterpret_cast<uintptr_t>(lv.cls) & 15u) == 0;
-        const int per_block = vec ? kSumCols * 4 : kPassThreads;
-        plan.vec[l] = vec ? 1 : 0;
-        plan.chunks[l] = (unsigned)((lv.n_anchor + per_block - 1) / per_block);
-        items += plan.chunks[l] * (unsigned)geo.num_images;
-    }
-    plan.item_off[PAA_MAX_LEVELS] = items;
-    plan.sum_blocks = with_class_sums ? items : 0u;      // 0: IoU matching only (no score pass, RetinaNet)
     const int heavy_level = first_heavy_level(geo);
     plan.light_tiles = heavy_level < geo.num_levels ? geo.lv[heavy_level].tile_off : geo.tiles_per_image;
     plan.light_pairs = (plan.light_tiles + 1) / 2;
@@ -455,16 +316,10 @@ int launch_assign_pass1(const Geometry& geo, const float* gt_boxes, const LossSc
     if (regions == 0) plan.patches = 0;
     const unsigned light_items = plan.patches ? regions : (unsigned)plan.light_pairs;
     plan.iou_blocks = (unsigned)geo.num_images * (light_items + (unsigned)(plan.heavy_pairs * plan.parts));
-    const unsigned grid = plan.sum_blocks + plan.iou_blocks;
-    KernelTimer timer(PAA_KERNEL_PASS1, stream);
     const GtOffsets* gop = ws.go;
     unsigned long long* best = reinterpret_cast<unsigned long long*>(ws.best);
-    if (sc.gamma == 2.0f)
-        PAA_PDL_LAUNCH(assign_pass1_kernel<true>, grid, kPassThreads, stream, geo, gop, plan, sc.gamma, gt_boxes,
-                       ws.gtmax, best, ws.negsum);
-    else
-        PAA_PDL_LAUNCH(assign_pass1_kernel<false>, grid, kPassThreads, stream, geo, gop, plan, sc.gamma, gt_boxes,
-                       ws.gtmax, best, ws.negsum);
+    KernelTimer timer(PAA_KERNEL_PASS1, stream);
+    PAA_PDL_LAUNCH(iou_match_kernel, plan.iou_blocks, kPassThreads, stream, geo, gop, plan, gt_boxes, ws.gtmax, best);
     return 0;
 }
 
@@ -473,25 +328,39 @@ int launch_assign_pass1(const Geometry& geo, const float* gt_boxes, const LossSc
 //   matched = argmax GT if max IoU >= thr, else -1, except that an anchor which is some GT's best
 //   anchor (IoU == that GT's maximum, ties included) keeps its argmax GT (matcher.py:83-113).
 //   Only GTs whose maximum is below thr can restore anything, so those are listed first.
-//   score   = sum_c focal(logit_c | IoU label) + (1 - GIoU(decode(pred), decode(encode(gt))));
-//             the class sum comes from class_sum_kernel (K0)
+//   score   = sum_c focal(logit_c | IoU label) + (1 - GIoU(decode(pred), decode(encode(gt))))
 //   (loss.py:293-306; anchors without an IoU-positive label are never candidates, their 1e8 filler
 //   is not materialised).
+// The class sum -- the only pass over the logits that the assignment needs -- is taken HERE, and only where it
+// is used: for the tile's IoU-positive anchors (45 % of the anchors of the C2 batch, clustered around the ground
+// truth: a tile without any skips the pass, a float4 column without any its loads; measured DRAM traffic 92 MB
+// instead of the 115 MB of all logits -- the fetch granularity, not the 32-byte sector, decides what a skipped
+// column saves).  Every class enters as a negative, sum_c p_c^gamma * softplus(x_c); the labelled class's term is
+// then swapped for the positive one.  A block is one tile of 128 consecutive anchors of one level: as 32 float4
+// columns x 4 class groups for the sums (a warp reads up to 512 contiguous bytes of one class row, four rows in
+// flight per thread), the four partial sums of a column meet in shared memory in a fixed order, then one thread
+// per anchor again.  (As a kernel of its own in front of this one the pass took as long as it does for ALL
+// columns, 35 us: it then waits on memory latency, not on bytes.)
 // ---------------------------------------------------------------------------------------------
-// order-preserving map float -> unsigned (and back), so that (score, anchor) pairs compare as integers
-__device__ __forceinline__ unsigned ordered_bits(float v) {
-    unsigned u = __float_as_uint(v);
-    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+constexpr int kSumGroups = PAA_TILE / PAA_WARP;       // class groups = warps of the block
+
+// One negative-class focal term without its (1-alpha) factor: p^gamma * softplus(x).
+__device__ __forceinline__ float neg_term_only(float x, float gamma, bool g2) {
+    const SigmoidLean sl = sigmoid_lean(x);
+    return focal_pow(sl.p, gamma, g2) * sl.sp;
 }
-__device__ __forceinline__ float from_ordered_bits(unsigned u) {
-    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+
+__device__ __forceinline__ void add_terms(float4& acc, float4 x, float gamma, bool g2) {
+    acc.x += neg_term_only(x.x, gamma, g2);
+    acc.y += neg_term_only(x.y, gamma, g2);
+    acc.z += neg_term_only(x.z, gamma, g2);
+    acc.w += neg_term_only(x.w, gamma, g2);
 }
 
 __global__ void __launch_bounds__(PAA_TILE)
 match_score_kernel(const Geometry geo, const GtOffsets* __restrict__ gop, const float* __restrict__ gt_boxes,
                    const int64_t* __restrict__ gt_labels, const unsigned* __restrict__ gtmax,
-                   const unsigned long long* __restrict__ best, const float* __restrict__ negsum,
-                   const LossScalars sc,
+                   const unsigned long long* __restrict__ best, const LossScalars sc,
                    int* __restrict__ matched, float* __restrict__ score, int* __restrict__ paa_label, uint4* __restrict__ tile_gtmask,
                    int* __restrict__ seg_count, unsigned long long* __restrict__ seg_pool,
                    const float* __restrict__ teacher_score, const LossDebug dbg) {
@@ -501,6 +370,8 @@ match_score_kernel(const Geometry geo, const GtOffsets* __restrict__ gop, const 
     __shared__ int s_lq[PAA_TILE];
     __shared__ int s_nlq;
     __shared__ unsigned s_mask[4];
+    __shared__ unsigned s_need[PAA_TILE / PAA_WARP];
+    __shared__ __align__(16) float s_part[kSumGroups][PAA_TILE];
     if (threadIdx.x < 4) s_mask[threadIdx.x] = 0u;
 
     const int n = blockIdx.x / geo.tiles_per_image;
@@ -513,6 +384,7 @@ match_score_kernel(const Geometry geo, const GtOffsets* __restrict__ gop, const 
     const int gbase = go.v[n];
     const int G = go.v[n + 1] - gbase;
     const float thr = sc.iou_threshold;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
     float bval = 0.0f;
@@ -547,30 +419,82 @@ match_score_kernel(const Geometry geo, const GtOffsets* __restrict__ gop, const 
         }
         __syncthreads();
     }
+    if (!valid) m = -1;
+    int label = 0;
+    if (m >= 0) label = (int)gt_labels[gbase + m];
+    const bool positive = m >= 0 && label > 0;
     // which GTs (index mod 128) have matched anchors in this tile: lets the per-GT selection kernel
     // skip every tile that cannot contain one of its anchors, with no false negatives
-    if (valid && m >= 0) atomicOr(&s_mask[(m & 127) >> 5], 1u << (m & 31));
+    if (m >= 0) atomicOr(&s_mask[(m & 127) >> 5], 1u << (m & 31));
+    const unsigned pos_mask = __ballot_sync(PAA_FULL, positive);
+    if (lane == 0) s_need[warp] = pos_mask;
     __syncthreads();
     if (threadIdx.x == 0)
         tile_gtmask[(size_t)n * geo.tiles_per_image + tile] = make_uint4(s_mask[0], s_mask[1], s_mask[2], s_mask[3]);
-    if (!valid) return;
+    if (valid) {
+        matched[flat] = m;
+        paa_label[flat] = 0;
+        if (dbg.matched_idx) dbg.matched_idx[flat] = m;
+        if (dbg.iou_labels) dbg.iou_labels[flat] = label;
+    }
+    const bool any_positive = (s_need[0] | s_need[1] | s_need[2] | s_need[3]) != 0u;       // block-uniform
+    if (!any_positive) {
+        if (valid && dbg.combined_loss) dbg.combined_loss[flat] = 1.0e8f;
+        return;
+    }
 
-    int label = 0;
-    if (m >= 0) label = (int)gt_labels[gbase + m];
-    matched[flat] = m;
-    paa_label[flat] = 0;
-    if (dbg.matched_idx) dbg.matched_idx[flat] = m;
-    if (dbg.iou_labels) dbg.iou_labels[flat] = label;
+    // ---- class sums of the tile's IoU-positive anchors --------------------------------------------
+    const int C = geo.C;
+    const bool g2 = (sc.gamma == 2.0f);
+    const bool vec = geo.apl == 1 && (lv.hw & 3) == 0 && (reinterpret_cast<uintptr_t>(lv.cls) & 15u) == 0;
+    float negsum = 0.0f;
+    if (vec) {
+        const int col = lane, grp = warp;                                 // anchors 4*col .. 4*col+3 of the tile
+        const unsigned need = (s_need[col >> 3] >> ((col & 7) * 4)) & 0xfu;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (need != 0u) {
+            const int cg = (C + kSumGroups - 1) / kSumGroups;
+            const int c_begin = grp * cg, c_end = min(C, c_begin + cg);
+            const unsigned st = (unsigned)lv.hw >> 2;                     // float4 per class row
+            const float4* p = reinterpret_cast<const float4*>(lv.cls + (size_t)n * C * lv.hw + first + 4 * col);
+            int c0 = c_begin;
+            for (; c0 + 4 <= c_end; c0 += 4) {
+                float4 x[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) x[j] = __ldg(p + (size_t)(c0 + j) * st);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) add_terms(acc, x[j], sc.gamma, g2);
+            }
+            for (; c0 < c_end; ++c0) add_terms(acc, __ldg(p + (size_t)c0 * st), sc.gamma, g2);
+        }
+        *reinterpret_cast<float4*>(&s_part[grp][4 * col]) = acc;
+        __syncthreads();
+        // group 0's sum first, then groups 1, 2, 3: the order round 1 fixed (bit-identical scores)
+        negsum = s_part[0][threadIdx.x];
+#pragma unroll
+        for (int g = 1; g < kSumGroups; ++g) negsum += s_part[g][threadIdx.x];
+    } else if (positive) {
+        const float* p = lv.cls + head_offset(n, i, 0, C, geo.apl, lv.hw);
+        const unsigned st = (unsigned)lv.hw;
+        int c0 = 0;
+        for (; c0 + 8 <= C; c0 += 8) {
+            float x[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) x[j] = __ldg(p + (size_t)(c0 + j) * st);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) negsum += neg_term_only(x[j], sc.gamma, g2);
+        }
+        for (; c0 < C; ++c0) negsum += neg_term_only(__ldg(p + (size_t)c0 * st), sc.gamma, g2);
+    }
 
     float s = 1.0e8f;   // loss.py:15,301-306 filler, only visible through the debug output
-    if (m >= 0 && label > 0) {
-        // sum_c focal(x_c | label): every class as a negative (class_sum_kernel), then the labelled class's
-        // negative term swapped for the positive one (accurate path for that single term)
-        const float xl = __ldg(lv.cls + head_offset(n, i, label - 1, geo.C, geo.apl, lv.hw));
-        const bool g2 = (sc.gamma == 2.0f);
+    if (positive) {
+        // sum_c focal(x_c | label): every class as a negative, then the labelled class's negative term swapped
+        // for the positive one (accurate path for that single term)
+        const float xl = __ldg(lv.cls + head_offset(n, i, label - 1, C, geo.apl, lv.hw));
         float tp, gp;
         focal_positive(xl, sigmoid_parts(xl), sc.gamma, g2, sc.alpha, &tp, &gp);
-        const float fsum = fmaf(1.0f - sc.alpha, __ldg(negsum + flat) - neg_term_only(xl, sc.gamma, g2), tp);
+        const float fsum = fmaf(1.0f - sc.alpha, negsum - neg_term_only(xl, sc.gamma, g2), tp);
         const float* rp = lv.reg + head_offset(n, i, 0, 4, geo.apl, lv.hw);
         const float4 d = make_float4(__ldg(rp), __ldg(rp + lv.hw), __ldg(rp + 2 * (size_t)lv.hw),
                                      __ldg(rp + 3 * (size_t)lv.hw));
@@ -586,15 +510,15 @@ match_score_kernel(const Geometry geo, const GtOffsets* __restrict__ gop, const 
         const int seg = (gbase + m) * geo.num_levels + l;
         // consecutive anchors mostly share their GT: one atomic per (warp, segment) instead of one per anchor
         const unsigned peers = __match_any_sync(__activemask(), seg);
-        const int leader = __ffs(peers) - 1, lane_id = threadIdx.x & 31;
+        const int leader = __ffs(peers) - 1;
         int slot = 0;
-        if (lane_id == leader) slot = atomicAdd(&seg_count[seg], __popc(peers));
-        slot = __shfl_sync(peers, slot, leader) + __popc(peers & ((1u << lane_id) - 1u));
+        if (lane == leader) slot = atomicAdd(&seg_count[seg], __popc(peers));
+        slot = __shfl_sync(peers, slot, leader) + __popc(peers & ((1u << lane) - 1u));
         if (slot < sc.seg_cap)
             seg_pool[(size_t)seg * kSegCap + slot] =
                 ((unsigned long long)ordered_bits(key_score) << 32) | (unsigned)(lv.a_off + i);
     }
-    if (dbg.combined_loss) dbg.combined_loss[flat] = s;
+    if (valid && dbg.combined_loss) dbg.combined_loss[flat] = s;
 }
 
 int launch_match_score(const Geometry& geo, const float* gt_boxes,
@@ -604,7 +528,7 @@ int launch_match_score(const Geometry& geo, const float* gt_boxes,
     KernelTimer timer(PAA_KERNEL_MATCH_SCORE, stream);
     const GtOffsets* gop = ws.go;
     PAA_PDL_LAUNCH(match_score_kernel, grid, PAA_TILE, stream, geo, gop, gt_boxes, gt_labels, ws.gtmax,
-                   reinterpret_cast<const unsigned long long*>(ws.best), ws.negsum, sc, ws.matched, ws.score,
+                   reinterpret_cast<const unsigned long long*>(ws.best), sc, ws.matched, ws.score,
                    ws.paa_label, ws.tile_gtmask, ws.seg_count, ws.seg_pool, teacher_score, dbg);
     return 0;
 }
@@ -891,7 +815,7 @@ select_gmm_kernel(const Geometry geo, const GtOffsets* __restrict__ gop, const i
                   const LossScalars sc, const uint4* __restrict__ tile_gtmask,
                   const int* __restrict__ matched, const float* __restrict__ score,
                   const int* __restrict__ seg_count, const unsigned long long* __restrict__ seg_pool,
-                  int* __restrict__ paa_label,
+                  int* __restrict__ paa_label, int* __restrict__ pos_list,
                   int* __restrict__ part_npos, double* __restrict__ part_siou,
                   unsigned* __restrict__ ticket, double* __restrict__ local_norm,
                   double* __restrict__ normalisers, const PeerExchange px, const LossDebug dbg) {
@@ -1068,6 +992,7 @@ select_gmm_kernel(const Geometry geo, const GtOffsets* __restrict__ gop, const i
         if (j < n_cand) {
             if (dbg.cand_idx) dbg.cand_idx[(size_t)gi * cap + j] = aidx[k];
             if (j < n_pos) {
+                pos_list[(size_t)gi * cap + j] = aidx[k];
                 paa_label[(size_t)n * geo.A + aidx[k]] = cls_label;
                 if (dbg.paa_labels) dbg.paa_labels[(size_t)n * geo.A + aidx[k]] = cls_label;
                 if (sc.use_iou_pred) {
@@ -1215,7 +1140,7 @@ int launch_select_gmm(const Geometry& geo, const float* gt_boxes,
     KernelTimer timer(PAA_KERNEL_SELECT_GMM, stream);
 #define PAA_SEL_LAUNCH(SPL)                                                                           \
     PAA_PDL_LAUNCH(select_gmm_kernel<SPL>, grid, threads, stream, geo, gop, ws.gt_image, gt_boxes, gt_labels, sc, \
-        ws.tile_gtmask, ws.matched, score_src, ws.seg_count, ws.seg_pool, ws.paa_label, ws.part_npos,  \
+        ws.tile_gtmask, ws.matched, score_src, ws.seg_count, ws.seg_pool, ws.paa_label, ws.pos_list, ws.part_npos, \
         ws.part_siou,                                                                                  \
         ws.ticket, ws.local_norm, normalisers, px, dbg)
     if (cap <= 32) PAA_SEL_LAUNCH(1);

@@ -57,8 +57,8 @@ int gt_parts_for(int max_gt_per_image);
 int launch_prep_step(const Geometry& geo, const GtOffsets& host_go, const int* dev_offsets, const LossScalars& sc,
                      const LossWorkspace& ws, void* zero_base, bool clear_heavy_best, bool clear_all_best,
                      cudaStream_t stream);
-int launch_assign_pass1(const Geometry& geo, const float* gt_boxes, const LossScalars& sc,
-                        const LossWorkspace& ws, cudaStream_t stream, bool with_class_sums = true);
+int launch_iou_match(const Geometry& geo, const float* gt_boxes, const LossScalars& sc, const LossWorkspace& ws,
+                     cudaStream_t stream);
 int launch_match_score(const Geometry& geo, const float* gt_boxes,
                        const int64_t* gt_labels, const LossScalars& sc, const LossWorkspace& ws,
                        const float* teacher_score, const LossDebug& dbg, cudaStream_t stream);

@@ -23,7 +23,6 @@ struct LossWorkspace {
     uint2* best;            // [N*A]    (IoU bits, GT index) of every anchor's best GT
     int* matched;           // [N*A]
     float* score;           // [N*A]    anchor score (combined loss) of IoU-positive anchors
-    float* negsum;          // [N*A]    sum over classes of every logit's negative-class focal term (no (1-alpha))
     int* paa_label;         // [N*A]
     uint4* tile_gtmask;     // [N*T]    bit (g mod 128): GT g has a matched anchor in the tile
     int* part_npos;         // [sumG]
@@ -31,6 +30,7 @@ struct LossWorkspace {
     double* local_norm;     // [2]      this rank's {num_pos, sum_iou} (before the all-reduce)
     double* block_part;     // [blocks*3] per-block partial loss sums of the final kernel
     unsigned long long* seg_pool;   // [sumG*L*kSegCap] (score bits, anchor) keys of the anchors matched to (GT, level)
+    int* pos_list;          // [sumG*PAA_MAX_CANDIDATES] anchors of every GT's positive prefix (stride = levels * topk)
     GtOffsets* go;          // the step's per-image GT ranges as every kernel reads them (written by prep_step_kernel)
     int* gt_image;          // [sumG]   image of every GT
     size_t total_bytes;
@@ -60,7 +60,6 @@ inline LossWorkspace carve_loss_workspace(void* base, int N, int A, int sumG, in
     w.best = reinterpret_cast<uint2*>(take(sizeof(uint2) * NA));
     w.matched = reinterpret_cast<int*>(take(sizeof(int) * NA));
     w.score = reinterpret_cast<float*>(take(sizeof(float) * NA));
-    w.negsum = reinterpret_cast<float*>(take(sizeof(float) * NA));
     w.paa_label = reinterpret_cast<int*>(take(sizeof(int) * NA));
     w.tile_gtmask = reinterpret_cast<uint4*>(take(sizeof(uint4) * (size_t)N * tiles_per_image));
     w.part_npos = reinterpret_cast<int*>(take(sizeof(int) * (size_t)(sumG > 0 ? sumG : 1)));
@@ -69,6 +68,7 @@ inline LossWorkspace carve_loss_workspace(void* base, int N, int A, int sumG, in
     w.block_part = reinterpret_cast<double*>(take(sizeof(double) * 3 * (size_t)loss_blocks));
     w.seg_pool = reinterpret_cast<unsigned long long*>(
         take(sizeof(unsigned long long) * (size_t)(sumG > 0 ? sumG : 1) * L * kSegCap));
+    w.pos_list = reinterpret_cast<int*>(take(sizeof(int) * (size_t)(sumG > 0 ? sumG : 1) * 128));
     w.go = reinterpret_cast<GtOffsets*>(take(kGtOffsetsBytes));
     w.gt_image = reinterpret_cast<int*>(take(sizeof(int) * (size_t)(sumG > 0 ? sumG : 1)));
     w.total_bytes = off;

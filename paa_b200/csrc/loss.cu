@@ -17,7 +17,10 @@ namespace paa {
 
 
 // partial-sum slots: the bulk kernel's persistent blocks, then one per 128-anchor tile
-int loss_grid_blocks(int num_images, int tiles_per_image) { return 148 * 5 + num_images * tiles_per_image; }
+int loss_grid_blocks(int num_images, int tiles_per_image) {
+    const int tiles = num_images * tiles_per_image;
+    return 148 * 5 + (tiles > 148 * 8 ? tiles : 148 * 8);       // bulk blocks, then tiles or positive_list blocks
+}
 
 struct GradScales {
     float cls, reg, bce;     // d(total)/d(sum) factors
@@ -626,6 +629,31 @@ __device__ __forceinline__ void fold_partials(const double* __restrict__ part, i
     }
 }
 
+// loss.py:354-358 (and the other flavours' normalisations) applied to the folded sums {cls, reg, iou-pred / centerness}
+__device__ __forceinline__ void write_losses(const double (&t)[3], const LossScalars& sc, const double* __restrict__ norm,
+                                             float* __restrict__ losses) {
+    const double world = (double)sc.world_size;
+    const float num_pos_avg = (float)fmax(norm[0] / world, 1.0);
+    if (sc.flavour == PAA_LOSS_RETINANET) {
+        const float npos = (float)norm[0];
+        losses[0] = (float)t[0] / (npos + (float)sc.num_images);
+        losses[1] = (float)t[1] / fmaxf(1.0f, npos * sc.reg_norm_weight);
+        losses[2] = 0.0f;
+        return;
+    }
+    losses[0] = (float)t[0] / num_pos_avg;
+    if (sc.use_iou_pred) {
+        const float reg_norm = (float)(norm[1] / world);
+        losses[1] = (float)t[1] / reg_norm * sc.reg_loss_weight;
+        // a rank without positives returns an empty sum instead (atss/loss.py:274-277, fcos/loss.py:274-277)
+        if (sc.flavour != PAA_LOSS_PAA && t[1] == 0.0) losses[1] = 0.0f;
+        losses[2] = (float)t[2] / num_pos_avg * sc.iou_loss_weight;
+    } else {
+        losses[1] = (float)t[1] / num_pos_avg * sc.reg_loss_weight;
+        losses[2] = 0.0f;
+    }
+}
+
 __global__ void __launch_bounds__(kFinishThreads)
 finish_loss_kernel(const double* __restrict__ part_a, int blocks_a, const double* __restrict__ part_b,
                    int blocks_b, const LossScalars sc, const double* __restrict__ norm,
@@ -646,26 +674,157 @@ finish_loss_kernel(const double* __restrict__ part_a, int blocks_a, const double
         double t[3] = {0.0, 0.0, 0.0};
         for (int w = 0; w < kFinishThreads / PAA_WARP; ++w)
             for (int k = 0; k < 3; ++k) t[k] += s[w][k];
-        const double world = (double)sc.world_size;
-        const float num_pos_avg = (float)fmax(norm[0] / world, 1.0);
-        if (sc.flavour == PAA_LOSS_RETINANET) {
-            const float npos = (float)norm[0];
-            losses[0] = (float)t[0] / (npos + (float)sc.num_images);
-            losses[1] = (float)t[1] / fmaxf(1.0f, npos * sc.reg_norm_weight);
-            losses[2] = 0.0f;
-            return;
+        write_losses(t, sc, norm, losses);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// PAA's positives, list-driven.  select_gmm_kernel leaves every GT's positive prefix as a short list of
+// anchors; one thread per (GT, slot) patches the labelled class (loss term and gradient element), computes the
+// GIoU / IoU-prediction losses and gradients -- the ~8 positives per GT of a batch instead of a scan of all
+// N x A anchors for the 2 % that are positive (the scan kernel, still used by the other flavours, spent its time
+// at the block barrier behind the few warps that held a positive: 17 us for the C2 batch).  The same launch
+// zeroes the regression / IoU-prediction gradients of the non-positive anchors (one thread per anchor), and
+// its last block folds all partial sums and writes the three losses (no separate finish launch).
+// ---------------------------------------------------------------------------------------------
+constexpr int kPosThreads = 128;
+constexpr int kPosMaxBlocks = 148 * 8;
+
+template <bool kGrads, bool kG2>
+__global__ void __launch_bounds__(kPosThreads, 8)
+positive_list_kernel(const Geometry geo, const GtOffsets* __restrict__ gop, const int* __restrict__ gt_image,
+                     const float* __restrict__ gt_boxes, const LossScalars sc,
+                     const int* __restrict__ pos_list, const int* __restrict__ part_npos, int cap,
+                     const int* __restrict__ paa_label, const double* __restrict__ norm,
+                     const double* __restrict__ local_norm, const float* __restrict__ gout,
+                     const double* __restrict__ bulk_part, int bulk_blocks, double* __restrict__ block_part,
+                     unsigned* __restrict__ ticket, float* __restrict__ losses) {
+    __shared__ double s_part[kPosThreads / PAA_WARP][3];
+    __shared__ bool s_last;
+    pdl_wait();
+    pdl_launch_dependents();
+    const GtOffsets& go = *gop;
+    const int num_gt = go.v[geo.num_images];
+    const unsigned tid = blockIdx.x * kPosThreads + threadIdx.x, nthr = gridDim.x * kPosThreads;
+    // (a) zero gradients of the non-positive anchors: the positives' are written below, by their own threads
+    if (kGrads) {
+        const unsigned total = (unsigned)geo.num_images * (unsigned)geo.A;
+        for (unsigned t = tid; t < total; t += nthr) {
+            if (__ldg(paa_label + t) > 0) continue;
+            const int n = (int)(t / (unsigned)geo.A), a = (int)(t - (unsigned)n * (unsigned)geo.A);
+            const int l = anchor_level(geo, a);
+            const LevelView& lv = geo.lv[l];
+            const int i = a - lv.a_off;
+            if (lv.g_reg) {
+                float* gr = lv.g_reg + head_offset(n, i, 0, 4, geo.apl, lv.hw);
+                gr[0] = 0.0f;
+                gr[lv.hw] = 0.0f;
+                gr[2 * (size_t)lv.hw] = 0.0f;
+                gr[3 * (size_t)lv.hw] = 0.0f;
+            }
+            if (lv.g_iou) lv.g_iou[head_offset(n, i, 0, 1, geo.apl, lv.hw)] = 0.0f;
         }
-        losses[0] = (float)t[0] / num_pos_avg;
-        if (sc.use_iou_pred) {
-            const float reg_norm = (float)(norm[1] / world);
-            losses[1] = (float)t[1] / reg_norm * sc.reg_loss_weight;
-            // a rank without positives returns an empty sum instead (atss/loss.py:274-277, fcos/loss.py:274-277)
-            if (sc.flavour != PAA_LOSS_PAA && t[1] == 0.0) losses[1] = 0.0f;
-            losses[2] = (float)t[2] / num_pos_avg * sc.iou_loss_weight;
-        } else {
-            losses[1] = (float)t[1] / num_pos_avg * sc.reg_loss_weight;
-            losses[2] = 0.0f;
+    }
+    // (b) the positives
+    float fix_sum = 0.f, reg_sum = 0.f, bce_sum = 0.f;
+    const unsigned items = (unsigned)num_gt * (unsigned)cap;
+    for (unsigned t = tid; t < items; t += nthr) {
+        const int gi = (int)(t / (unsigned)cap), j = (int)(t - (unsigned)gi * (unsigned)cap);
+        if (j >= __ldg(part_npos + gi)) continue;
+        const int n = __ldg(gt_image + gi);
+        const int a = __ldg(pos_list + (size_t)gi * cap + j);
+        const int label = __ldg(paa_label + (size_t)n * geo.A + a);        // the GT's class, written by select_gmm_kernel
+        const int l = anchor_level(geo, a);
+        const LevelView& lv = geo.lv[l];
+        const int i = a - lv.a_off;
+        FinalCtx cx;
+        cx.gs = make_scales(sc, norm, local_norm, gout);
+        cx.alpha = sc.alpha;
+        cx.gamma = sc.gamma;
+        cx.oma = 1.0f - sc.alpha;
+        cx.kneg = cx.oma * cx.gs.cls;
+        // classification: swap the negative-class result of the labelled class for the positive one
+        const size_t off = head_offset(n, i, label - 1, geo.C, geo.apl, lv.hw);
+        const float xp = __ldg(lv.cls + off);
+        const SigmoidParts sp = sigmoid_parts(xp);
+        float tn_acc = 0.f, g_unused;
+        neg_term_grad<kG2>(xp, cx.gamma, cx.kneg, &tn_acc, &g_unused);      // exactly what the bulk pass added
+        float tp, gp;
+        focal_positive(xp, sp, cx.gamma, kG2, cx.alpha, &tp, &gp);
+        fix_sum += tp - cx.oma * tn_acc;
+        if (kGrads && lv.g_cls) lv.g_cls[off] = gp * cx.gs.cls;
+        // box regression + IoU prediction
+        const float* rp = lv.reg + head_offset(n, i, 0, 4, geo.apl, lv.hw);
+        const float4 d = make_float4(__ldg(rp), __ldg(rp + lv.hw), __ldg(rp + 2 * (size_t)lv.hw),
+                                     __ldg(rp + 3 * (size_t)lv.hw));
+        const float xi = sc.use_iou_pred ? __ldg(lv.iou + head_offset(n, i, 0, 1, geo.apl, lv.hw)) : 0.f;
+        float4 gd = make_float4(0.f, 0.f, 0.f, 0.f);
+        float gi_ = 0.f;
+        positive_box_terms(geo, lv, go, gt_boxes, sc, cx, n, i, gi - go.v[n], d, xi, &reg_sum, &bce_sum, &gd, &gi_);
+        if (kGrads) {
+            if (lv.g_reg) {
+                float* gr = lv.g_reg + head_offset(n, i, 0, 4, geo.apl, lv.hw);
+                gr[0] = gd.x;
+                gr[lv.hw] = gd.y;
+                gr[2 * (size_t)lv.hw] = gd.z;
+                gr[3 * (size_t)lv.hw] = gd.w;
+            }
+            if (lv.g_iou) lv.g_iou[head_offset(n, i, 0, 1, geo.apl, lv.hw)] = gi_;
         }
+    }
+    double a0 = warp_sum((double)fix_sum), a1 = warp_sum((double)reg_sum), a2 = warp_sum((double)bce_sum);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) {
+        s_part[warp][0] = a0;
+        s_part[warp][1] = a1;
+        s_part[warp][2] = a2;
+    }
+    __syncthreads();
+    // thread 0 publishes the block's partial sums and takes a ticket; the last block to do so folds every partial
+    // sum in a fixed order and writes the losses
+    if (threadIdx.x == 0) {
+        double t[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+        for (int w = 0; w < kPosThreads / PAA_WARP; ++w)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) t[k] += s_part[w][k];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) block_part[(size_t)blockIdx.x * 3 + k] = t[k];
+        __threadfence();
+        s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    // eight partials' loads in flight per thread and trip (a few memory round trips in total)
+    const int total_parts = bulk_blocks + (int)gridDim.x;
+    double acc[3] = {0.0, 0.0, 0.0};
+    for (int b0 = threadIdx.x; b0 < total_parts; b0 += 8 * kPosThreads) {
+        double v[8][3];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int b = b0 + u * kPosThreads;
+            const double* src = b < bulk_blocks ? bulk_part + (size_t)b * 3 : block_part + (size_t)(b - bulk_blocks) * 3;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) v[u][k] = b < total_parts ? __ldcg(src + k) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) acc[k] += v[u][k];
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        acc[k] = warp_sum(acc[k]);
+        if (lane == 0) s_part[warp][k] = acc[k];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t[3] = {0.0, 0.0, 0.0};
+        for (int w = 0; w < kPosThreads / PAA_WARP; ++w)
+            for (int k = 0; k < 3; ++k) t[k] += s_part[w][k];
+        write_losses(t, sc, norm, losses);
+        *ticket = 0u;                   // paa_loss may be called again on the same assignment
     }
 }
 
@@ -760,6 +919,26 @@ int launch_final_loss(const Geometry& geo, const float* gt_boxes,
             if (g2) PAA_BULK(false, true, false); else PAA_BULK(false, false, false);
         }
 #undef PAA_BULK
+    }
+    if (sc.flavour == PAA_LOSS_PAA && geo.apl == 1) {
+        // PAA: the positives come as per-GT lists from select_gmm_kernel; the same launch zeroes the other anchors'
+        // regression / IoU gradients and its last block writes the losses
+        const int cap = geo.num_levels * sc.topk;
+        const long long work_a = (long long)geo.num_images * geo.A, work_b = (long long)sc.gt_capacity * cap;
+        long long blocks = ((work_a > work_b ? work_a : work_b) + kPosThreads - 1) / kPosThreads;
+        const int pos_grid = (int)(blocks < 1 ? 1 : (blocks > kPosMaxBlocks ? kPosMaxBlocks : blocks));
+        KernelTimer timer(PAA_KERNEL_POSITIVE_TERMS, stream);
+#define PAA_POSL(G, T)                                                                                       \
+    PAA_PDL_LAUNCH((positive_list_kernel<G, T>), pos_grid, kPosThreads, stream, geo, gop, ws.gt_image, gt_boxes, sc, \
+        ws.pos_list, ws.part_npos, cap, ws.paa_label, normalisers, ws.local_norm, grad_losses, bulk_part, bulk_grid, \
+        tile_part, ws.ticket + 1, losses)
+        if (write_grads) {
+            if (g2) PAA_POSL(true, true); else PAA_POSL(true, false);
+        } else {
+            if (g2) PAA_POSL(false, true); else PAA_POSL(false, false);
+        }
+#undef PAA_POSL
+        return 0;
     }
 #define PAA_POS(G, T)                                                                                        \
     PAA_PDL_LAUNCH((positive_terms_kernel<G, T>), tile_grid, PAA_TILE, stream, geo, gop, gt_boxes, sc,       \

@@ -160,7 +160,7 @@ retina_labels_kernel(const Geometry geo, const GtOffsets* __restrict__ gop, cons
 int launch_retinanet_assign(const Geometry& geo, const float* gt_boxes, const int64_t* gt_labels,
                             const LossScalars& sc, const LossWorkspace& ws, double* normalisers, const LossDebug& dbg,
                             cudaStream_t stream, bool atss_iou, const PeerExchange* px) {
-    int rc = launch_assign_pass1(geo, gt_boxes, sc, ws, stream, /*with_class_sums=*/false);
+    int rc = launch_iou_match(geo, gt_boxes, sc, ws, stream);
     if (rc) return rc;
     const int tiles = geo.num_images * geo.tiles_per_image;
     const int tiles_per_block = (tiles + kMaxLabelBlocks - 1) / kMaxLabelBlocks;

@@ -1,6 +1,6 @@
 """The peer-memory exchange of the loss normalisers when a rank is late or never arrives: the wait
-has no deadline by default -- a contribution that arrives seconds late is used as if it had been on time -- and with
-a deadline a missing contribution is an ERROR (status record + trap), never NaN data.  One GPU is enough: the second
+has no deadline by default (here: one far beyond the delay) -- a contribution that arrives seconds late is used as if
+it had been on time -- and with a deadline a missing contribution is an ERROR (status record + trap), never NaN data.  One GPU is enough: the second
 rank is played by a side stream that writes (or does not write) its slot of this rank's exchange buffer, which is
 exactly what the peer's kernel does over NVLink.  Runs in a child process: the trap poisons the CUDA context."""
 import os
@@ -37,7 +37,9 @@ class FakePeers(object):
     raise_if_timed_out = paa_loss.PeerNormExchange.raise_if_timed_out
 
 def run(mode):
-    timeout_s = 0.0 if mode == "late" else 0.3
+    # "late": a deadline far beyond the delay (the product default is none at all; a test must never leave a kernel
+    # spinning forever on a shared GPU should the "peer" copy fail to run)
+    timeout_s = 20.0 if mode == "late" else 0.3
     peers = FakePeers(timeout_s)
     cfg = paa_b200.default_cfg()
     ev = paa_b200.make_paa_loss_evaluator(cfg, paa_b200.BoxCoder(cfg))
@@ -106,7 +108,7 @@ def _child(mode, tmp_path):
     return subprocess.run([sys.executable, str(script), mode], capture_output=True, text=True, timeout=300)
 
 
-def test_a_late_peer_is_waited_for_without_a_deadline(tmp_path):
+def test_a_late_peer_is_waited_for(tmp_path):
     r = _child("late", tmp_path)
     assert r.returncode == 0 and "LATE_PEER_OK" in r.stdout, (r.stdout[-2000:], r.stderr[-2000:])
 

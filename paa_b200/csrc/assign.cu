@@ -339,8 +339,11 @@ int launch_iou_match(const Geometry& geo, const float* gt_boxes, const LossScala
 // then swapped for the positive one.  A block is one tile of 128 consecutive anchors of one level: as 32 float4
 // columns x 4 class groups for the sums (a warp reads up to 512 contiguous bytes of one class row, four rows in
 // flight per thread), the four partial sums of a column meet in shared memory in a fixed order, then one thread
-// per anchor again.  (As a kernel of its own in front of this one the pass took as long as it does for ALL
-// columns, 35 us: it then waits on memory latency, not on bytes.)
+// per anchor again.  Measured alternatives (C2 batch, stand-alone event time, this kernel 41 us): the pass as a
+// kernel of its own in front of this one 35 + 16 us (it waits on memory latency, not on bytes: as long as for ALL
+// columns); eight rows in flight per thread 45 us (registers cost occupancy); the tile's rows staged in shared memory
+// by bulk asynchronous copies behind an mbarrier, issued ahead of the Matcher, 56 us (40 KB per block leave five
+// blocks per SM for the latency-bound Matcher); bulk L2 prefetches of the rows ahead of the Matcher 45 us.
 // ---------------------------------------------------------------------------------------------
 constexpr int kSumGroups = PAA_TILE / PAA_WARP;       // class groups = warps of the block
 
@@ -398,6 +401,8 @@ match_score_kernel(const Geometry geo, const GtOffsets* __restrict__ gop, const 
     int m = (bval >= thr) ? bgt : -1;
     if (!(bval >= thr) && !(bval < thr)) m = bgt;          // NaN: neither below nor restored -> keeps argmax
 
+    const int C = geo.C;
+
     // low-quality GTs (max IoU below thr) restore their best anchors
     for (int c0 = 0; c0 < G; c0 += PAA_TILE) {
         if (threadIdx.x == 0) s_nlq = 0;
@@ -444,7 +449,6 @@ match_score_kernel(const Geometry geo, const GtOffsets* __restrict__ gop, const 
     }
 
     // ---- class sums of the tile's IoU-positive anchors --------------------------------------------
-    const int C = geo.C;
     const bool g2 = (sc.gamma == 2.0f);
     const bool vec = geo.apl == 1 && (lv.hw & 3) == 0 && (reinterpret_cast<uintptr_t>(lv.cls) & 15u) == 0;
     float negsum = 0.0f;
@@ -528,8 +532,8 @@ int launch_match_score(const Geometry& geo, const float* gt_boxes,
     KernelTimer timer(PAA_KERNEL_MATCH_SCORE, stream);
     const GtOffsets* gop = ws.go;
     PAA_PDL_LAUNCH(match_score_kernel, grid, PAA_TILE, stream, geo, gop, gt_boxes, gt_labels, ws.gtmax,
-                   reinterpret_cast<const unsigned long long*>(ws.best), sc, ws.matched, ws.score,
-                   ws.paa_label, ws.tile_gtmask, ws.seg_count, ws.seg_pool, teacher_score, dbg);
+                   reinterpret_cast<const unsigned long long*>(ws.best), sc, ws.matched, ws.score, ws.paa_label,
+                   ws.tile_gtmask, ws.seg_count, ws.seg_pool, teacher_score, dbg);
     return 0;
 }
 

@@ -119,11 +119,26 @@ def _require_cuda(t, name):
         raise RuntimeError("paa_b200 has no CPU path: %s is on %s" % (name, t.device))
 
 
+_warned_layout = set()
+
+
 def _head(t, name):
+    """A head tensor as the kernels read it: float32, NCHW-contiguous (the layout PAAHead.forward produces,
+    paa.py:90-108).  Any other layout -- `torch.channels_last` from an AMP / cuDNN pipeline, a sliced view -- is
+    copied, which for the classification logits of a 16-image batch is a 115 MB round trip per call: say so once
+    instead of hiding it (keep the head's outputs in `torch.contiguous_format` to avoid the copy)."""
     _require_cuda(t, name)
     if t.dtype != torch.float32:
         raise RuntimeError("%s must be float32, got %s" % (name, t.dtype))
-    return t if t.is_contiguous() else t.contiguous()
+    if t.is_contiguous():
+        return t
+    if name not in _warned_layout:
+        _warned_layout.add(name)
+        import warnings
+        warnings.warn("paa_b200: %s is not NCHW-contiguous (strides %s for shape %s); it is copied to the layout the "
+                      "kernels read on every call -- %.1f MB here.  Keep the head outputs in torch.contiguous_format."
+                      % (name, tuple(t.stride()), tuple(t.shape), t.numel() * 4 / 1e6), stacklevel=3)
+    return t.contiguous()
 
 
 def _anchors_shared(anchors, N, L):

@@ -156,3 +156,24 @@ def test_fcos_points_cache_is_validated_and_bounded():
         assert torch.equal(q[:, :2], loc)
         seen.add(id(loc))
     assert len(cache) <= _POINTS_CACHE_ENTRIES
+
+
+def test_non_nchw_heads_are_copied_with_a_warning_not_silently():
+    """VERDICT r1 #8: a channels_last head used to be `.contiguous()`-copied without a word."""
+    import warnings
+    import torch
+    from paa_b200 import loss as paa_loss
+
+    class FakeCuda(torch.Tensor):
+        is_cuda = True
+
+    paa_loss._warned_layout.clear()
+    t = torch.zeros(2, 8, 4, 6).to(memory_format=torch.channels_last).as_subclass(FakeCuda)
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        out = paa_loss._head(t, "box_cls")
+        paa_loss._head(t, "box_cls")                       # warned once per head name
+    assert out.is_contiguous()
+    assert len([x for x in w if "not NCHW-contiguous" in str(x.message)]) == 1
+    c = torch.zeros(2, 8, 4, 6).as_subclass(FakeCuda)
+    assert paa_loss._head(c, "box_cls") is c               # the usual case costs nothing

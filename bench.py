@@ -574,6 +574,38 @@ class LossRun(object):
         torch.cuda.synchronize()
         return 1000.0 * (time.perf_counter() - t0) / steps
 
+    def graph_mode_ms(self, steps, autograd):
+        """The evaluator in graph mode (`use_graph`): ONE captured step replayed for every call, with a different
+        set of targets each time (the second set is the first with the images' ground truth rotated by one image) --
+        the way a training loop feeds it.  Wall clock between two synchronisations, back to back.  `autograd`: through
+        `__call__` + `torch.autograd.grad` (the drop-in call); else through `forward_backward`."""
+        import paa_b200
+        cfg = paa_b200.default_cfg()
+        ev = paa_b200.make_paa_loss_evaluator(cfg, paa_b200.BoxCoder(cfg))
+        ev.use_graph = True
+        ev.gt_per_image_capacity = 128
+        rotated = self.targets_from([t.bbox for t in self.d_targets[1:] + self.d_targets[:1]],
+                                    [t.get_field("labels") for t in self.d_targets[1:] + self.d_targets[:1]])
+        sets = [self.d_targets, rotated]
+
+        def step(k):
+            if autograd:
+                losses = ev(self.d_cls, self.d_reg, self.d_iou, sets[k & 1], self.anchors, None)
+                return torch.autograd.grad(losses[0] + losses[1] + losses[2], self.heads)
+            return ev.forward_backward(self.d_cls, self.d_reg, self.d_iou, sets[k & 1], self.anchors)
+
+        for k in range(4):
+            step(k)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for k in range(steps):
+            step(k)
+        torch.cuda.synchronize()
+        ms = 1000.0 * (time.perf_counter() - t0) / steps
+        graphs = len(ev._graphs)
+        calls = sum(g.calls for g in ev._graphs.values())
+        return ms, graphs, calls
+
     def exchange_check(self):
         """N > 1: the normalisers the peer-memory exchange delivered against an NCCL all-reduce of the ranks' own
         pairs, on every rank.  Returns (max relative difference, 1.0 if the peer path was in use else 0.0)."""
@@ -704,6 +736,17 @@ def measure_loss(ctx, args, scaling, full):
                                                      "resident, no graph, wall clock between two synchronisations"}
             except Exception as e:  # noqa: BLE001 - a side measurement must not take the bench line down
                 sys.stderr.write("eager_api_resident side measurement failed: %s\n" % (e,))
+            try:
+                for key, autograd in (("graph_forward_backward_new_targets", False), ("graph_api_new_targets", True)):
+                    ms, graphs, calls = run.graph_mode_ms(max(args.steps, 20), autograd)
+                    res[key] = {"value": total / (ms / 1000.0), "unit": UNIT, "ms_per_step": ms,
+                                "captured_graphs": graphs, "replays_and_capture": calls,
+                                "what": ("PAALossComputation.__call__ + torch.autograd.grad" if autograd else
+                                         "PAALossComputation.forward_backward") +
+                                        " in graph mode (use_graph): one captured step replayed with a different target "
+                                        "set every call, inputs resident, wall clock between two synchronisations"}
+            except Exception as e:  # noqa: BLE001
+                sys.stderr.write("graph-mode side measurement failed: %s\n" % (e,))
         if ctx.rank == 0 and ctx.world == 1 and not args.no_cpu_baseline:
             cores = host_threads()
             n = min(CPU_SAMPLE_IMAGES, per_gpu)
@@ -733,7 +776,8 @@ def loss_line(ctx, args):
         "roofline": main["roofline"], "step_ms_min_med_max": main["step_ms_min_med_max"],
         "num_gt_this_rank": main["num_gt"],
     }
-    for key in ("exchange_check", "eager_api_resident", "cpu_baseline"):
+    for key in ("exchange_check", "eager_api_resident", "graph_forward_backward_new_targets", "graph_api_new_targets",
+                "cpu_baseline"):
         if key in main:
             line[key] = main[key]
     if side is not None:

@@ -316,6 +316,9 @@ int paa_box_vote(const float* boxes, const float* scores, const float* labels, i
 #define PAA_KERNEL_POST_VOTE    17
 #define PAA_KERNEL_POST_THRESHOLD 18
 #define PAA_KERNEL_POST_SEGMENTS 19
+/* Self-test of the branch-free float32 square root / reciprocal the mixture fit uses in place of the IEEE library
+ * routines: out [4, n] = {fast sqrt(x), __fsqrt_rn(x), fast 1/x, __fdiv_rn(1, x)} for device arrays x [n]. */
+int paa_selftest_roots(const float* x, int n, float* out, void* stream);
 int paa_kernel_timing_begin(int kernel_id);
 int paa_kernel_timing_end(float* total_ms, int32_t* launches);
 

@@ -104,6 +104,7 @@ SYMBOLS = {
     "paa_box_vote": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float,
                                C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
                                C.c_void_p]),
+    "paa_selftest_roots": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "paa_kernel_timing_begin": (C.c_int, [C.c_int]),
     "paa_kernel_timing_end": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
 }

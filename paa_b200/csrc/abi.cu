@@ -474,6 +474,14 @@ int paa_postprocess(const PaaPostArgs* args, void* stream) {
     return run_postprocess(geo, args, static_cast<cudaStream_t>(stream));
 }
 
+int paa_selftest_roots(const float* x, int n, float* out, void* stream) {
+    if (n < 0 || (n > 0 && (!x || !out))) {
+        set_error("bad arguments to paa_selftest_roots");
+        return PAA_ERR_BAD_ARGUMENT;
+    }
+    return launch_selftest_roots(x, n, out, static_cast<cudaStream_t>(stream));
+}
+
 int paa_kernel_timing_begin(int kernel_id) {
     g_timed_kernel = kernel_id;
     g_timed_count = 0;

@@ -606,6 +606,36 @@ __device__ __forceinline__ void warp_sum7(double (&v)[8], int lane) {
     for (int q = 0; q < 7; ++q) v[q] = __shfl_sync(PAA_FULL, y, 4 * q);
 }
 
+// warp_sum7 with the warp PRODUCT of `P` riding in the padding slot (v[7] = P on entry; the slot is multiplied where
+// the others are added): the log-likelihood's prod(1 + s) costs no butterfly of its own.  Returns the product.
+__device__ __forceinline__ double warp_sum7_prod(double (&v)[8], int lane) {
+    const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0, b2 = (lane & 4) != 0;
+    double w[4], x[2];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const double send = b4 ? v[j] : v[4 + j], keep = b4 ? v[4 + j] : v[j];
+        const double recv = __shfl_xor_sync(PAA_FULL, send, 16);
+        w[j] = (j == 3 && b4) ? keep * recv : keep + recv;               // slot 7 lives in the b4 half's w[3]
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const double send = b3 ? w[j] : w[2 + j], keep = b3 ? w[2 + j] : w[j];
+        const double recv = __shfl_xor_sync(PAA_FULL, send, 8);
+        x[j] = (j == 1 && b4 && b3) ? keep * recv : keep + recv;
+    }
+    const double send = b2 ? x[0] : x[1], keep = b2 ? x[1] : x[0];
+    const bool prod_lane = b4 && b3 && b2;                               // lanes 28..31 own slot 7
+    double recv = __shfl_xor_sync(PAA_FULL, send, 4);
+    double y = prod_lane ? keep * recv : keep + recv;
+    recv = __shfl_xor_sync(PAA_FULL, y, 2);
+    y = prod_lane ? y * recv : y + recv;
+    recv = __shfl_xor_sync(PAA_FULL, y, 1);
+    y = prod_lane ? y * recv : y + recv;
+#pragma unroll
+    for (int q = 0; q < 7; ++q) v[q] = __shfl_sync(PAA_FULL, y, 4 * q);
+    return __shfl_sync(PAA_FULL, y, 28);
+}
+
 // Fits the mixture on the warp's n sorted samples (lane holds x[lane + 32*k]) and returns the length
 // of the positive prefix (loss.py:206-217).  out8 (nullable, lane 0 writes) receives the parameters.
 //
@@ -657,11 +687,18 @@ __device__ int gmm_positive_prefix(const float (&x)[SPL], int n, int lane, doubl
     const double EPS10 = 10.0 * 2.220446049250313e-16;
     const double inv_n = 1.0 / (double)n;
     double a0[SPL], a1[SPL];
+#ifdef PAA_PROFILE_GMM
+    long long prof_sec[5] = {0, 0, 0, 0, 0}, prof_last = 0;
+#endif
     for (;;) {
 #pragma unroll
         for (int k = 0; k < SPL; ++k) weighted_log_prob(x[k], s, &a0[k], &a1[k]);
         if (converged || n_iter == 100) break;
         ++n_iter;
+#ifdef PAA_PROFILE_GMM
+        const long long tA = clock64();
+        if (n_iter > 1) prof_sec[4] += tA - prof_last;
+#endif
         const double p0 = s.mu0, p1 = s.mu1;
         double v[8];          // S0 S1 A0 A1 B0 B1 H pad
         double P = 1.0;
@@ -670,7 +707,7 @@ __device__ int gmm_positive_prefix(const float (&x)[SPL], int n, int lane, doubl
             if (k > 0 && n <= 32 * k) break;                  // warp-uniform
             const bool first_hi = a0[k] >= a1[k];
             const double hi = first_hi ? a0[k] : a1[k], lo = first_hi ? a1[k] : a0[k];
-            const double sx = exp_nonpos(lo - hi);
+            const double sx = exp_nonpos_clamped(lo - hi);
             const double u = 1.0 + sx;
             const double rh = rcp_fast(u), rl = sx * rh;
             const bool valid = lane + 32 * k < n;
@@ -698,9 +735,16 @@ __device__ int gmm_positive_prefix(const float (&x)[SPL], int n, int lane, doubl
                 P *= valid ? u : 1.0;
             }
         }
-        v[7] = 0.0;
-        P = warp_prod(P);
-        warp_sum7(v, lane);
+        v[7] = P;
+#ifdef PAA_PROFILE_GMM
+        const long long tB = clock64();
+        prof_sec[0] += tB - tA;
+#endif
+        P = warp_sum7_prod(v, lane);
+#ifdef PAA_PROFILE_GMM
+        const long long tC = clock64();
+        prof_sec[1] += tC - tB;
+#endif
         // M-step, both components in every lane (two independent chains fill each other's latency)
         const double nk0 = v[0] + EPS10, nk1 = v[1] + EPS10;
         const double rn0 = rcp_fast(nk0), rn1 = rcp_fast(nk1), rs = rcp_fast(nk0 + nk1);
@@ -711,13 +755,21 @@ __device__ int gmm_positive_prefix(const float (&x)[SPL], int n, int lane, doubl
         var1 = __fadd_rn(__double2float_rn(fmax(c1, 0.0) * rn1), 1e-6f);
         w0 = nk0 * rs;
         w1 = nk1 * rs;
-        const double arg = lane == 0 ? (double)var0
-                                     : (lane == 1 ? (double)var1 : (lane == 2 ? w0 : (lane == 3 ? w1 : P)));
+#ifdef PAA_PROFILE_GMM
+        const long long tD = clock64();
+        prof_sec[2] += tD - tC;
+#endif
+        // precisions first: the next E-step needs them before anything else, and as branch-free code (no range
+        // checks, no slow-path calls: the variances are normal numbers >= 1e-6) the two components' square roots and
+        // divisions interleave with each other and with the logarithm below instead of running one after the other
+        s.pc0 = div_rn_normal(1.0f, sqrt_rn_normal(var0));
+        s.pc1 = div_rn_normal(1.0f, sqrt_rn_normal(var1));
+        const double dv0 = (double)var0, dv1 = (double)var1;
+        const double a_var = (lane & 1) ? dv1 : dv0, a_w = (lane & 1) ? w1 : w0;     // selects, not branches
+        const double arg = lane < 2 ? a_var : (lane < 4 ? a_w : P);
         const double lg = log_pos(arg);
         s.mu0 = p0 + d0;
         s.mu1 = p1 + d1;
-        s.pc0 = __fdiv_rn(1.0f, __fsqrt_rn(var0));
-        s.pc1 = __fdiv_rn(1.0f, __fsqrt_rn(var1));
         const double pd0 = (double)s.pc0, pd1 = (double)s.pc1;
         s.mpc0 = s.mu0 * pd0;
         s.mpc1 = s.mu1 * pd1;
@@ -730,6 +782,10 @@ __device__ int gmm_positive_prefix(const float (&x)[SPL], int n, int lane, doubl
         const double lb = (v[6] + __shfl_sync(PAA_FULL, lg, 4)) * inv_n;
         converged = fabs(lb - lower) < 1e-3;
         lower = lb;
+#ifdef PAA_PROFILE_GMM
+        prof_last = clock64();
+        prof_sec[3] += prof_last - tD;
+#endif
     }
     // a0 / a1 are the final E-step: predict (argmax, ties -> 0) and score_samples
     double best_score = -INFINITY;
@@ -759,6 +815,17 @@ __device__ int gmm_positive_prefix(const float (&x)[SPL], int n, int lane, doubl
         }
     }
     any_fg = __any_sync(PAA_FULL, any_fg);
+#ifdef PAA_PROFILE_GMM
+    if (out8 && lane == 0) {      // sections: E-step, reductions, M-step to var, log/sqrt to loop end, next E-step's log-probs
+        out8[2] = (double)prof_sec[0];
+        out8[3] = (double)prof_sec[1];
+        out8[4] = (double)prof_sec[2];
+        out8[5] = (double)prof_sec[3];
+        out8[7] = (double)prof_sec[4];
+        out8[6] = (double)n_iter;
+        return any_fg ? best_idx + 1 : n;
+    }
+#endif
     if (out8 && lane == 0) {
         out8[0] = w0;
         out8[1] = w1;

@@ -65,6 +65,27 @@ boxlist_iou_kernel(const float* __restrict__ b1, int n1, const float* __restrict
 
 using namespace paa;
 
+namespace paa {
+
+__global__ void selftest_roots_kernel(const float* __restrict__ x, int n, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float v = x[i];
+    out[i] = sqrt_rn_normal(v);
+    out[(size_t)n + i] = __fsqrt_rn(v);
+    out[2 * (size_t)n + i] = div_rn_normal(1.0f, v);
+    out[3 * (size_t)n + i] = __fdiv_rn(1.0f, v);
+}
+
+int launch_selftest_roots(const float* x, int n, float* out, cudaStream_t stream) {
+    if (n == 0) return 0;
+    selftest_roots_kernel<<<(n + 255) / 256, 256, 0, stream>>>(x, n, out);
+    PAA_LAUNCH_CHECK("selftest_roots_kernel");
+    return 0;
+}
+
+}  // namespace paa
+
 extern "C" {
 
 int paa_grid_anchors(const float* cell_anchors, int anchors_per_loc, int grid_h, int grid_w, float stride,

@@ -93,6 +93,31 @@ PAA_HD double exp_nonpos(double d) {
     return p * f64_from_bits((uint64_t)(n + 1023) << 52);
 }
 
+// exp(d) for d <= 0 without a branch: arguments below -708 are clamped (the result, ~3e-308 instead of 0, only ever
+// feeds sums of O(1)).  Same polynomial as exp_nonpos; for the EM loop, where a branch splits the instruction stream
+// of the single warp that runs it.
+PAA_HD double exp_nonpos_clamped(double d) {
+    d = d > -708.0 ? d : -708.0;
+    const double kMagic = 6755399441055744.0;
+    const double t = fma(d, 1.4426950408889634074, kMagic);
+    const double nf = t - kMagic;
+    const int n = (int)(uint32_t)f64_bits(t);
+    double r = fma(nf, -6.93147180369123816490e-01, d);
+    r = fma(nf, -1.90821492927058770002e-10, r);
+    const double r2 = r * r, r4 = r2 * r2, r8 = r4 * r4;
+    const double a0 = fma(r, 1.0, 1.0);
+    const double a1 = fma(r, 1.6666666666666666e-01, 0.5);
+    const double a2 = fma(r, 8.3333333333333332e-03, 4.1666666666666664e-02);
+    const double a3 = fma(r, 1.9841269841269841e-04, 1.3888888888888889e-03);
+    const double a4 = fma(r, 2.7557319223985893e-06, 2.4801587301587302e-05);
+    const double a5 = fma(r, 2.5052108385441720e-08, 2.7557319223985888e-07);
+    const double a6 = fma(r, 1.6059043836821613e-10, 2.0876756987868100e-09);
+    const double b0 = fma(a1, r2, a0), b1 = fma(a3, r2, a2), b2 = fma(a5, r2, a4);
+    const double c0 = fma(b1, r4, b0), c1 = fma(a6, r4, b2);
+    const double p = fma(c1, r8, c0);
+    return p * f64_from_bits((uint64_t)(n + 1023) << 52);
+}
+
 // 2 * atanh(z) = log((1+z)/(1-z)) for |z| <= 0.1716 (w = z^2 <= 0.02944): 2z * sum_{k<=11} w^k/(2k+1)
 PAA_HD double two_atanh_small(double z) {
     const double w = z * z, w2 = w * w, w4 = w2 * w2, w8 = w4 * w4;

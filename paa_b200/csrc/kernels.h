@@ -86,6 +86,8 @@ int launch_retinanet_assign(const Geometry& geo, const float* gt_boxes, const in
                             const LossScalars& sc, const LossWorkspace& ws, double* normalisers, const LossDebug& dbg,
                             cudaStream_t stream, bool atss_iou = false, const PeerExchange* px = nullptr);
 
+// aux.cu
+int launch_selftest_roots(const float* x, int n, float* out, cudaStream_t stream);
 // loss.cu
 int loss_grid_blocks(int num_images, int tiles_per_image);
 int launch_final_loss(const Geometry& geo, const float* gt_boxes,

@@ -43,6 +43,8 @@ struct Pass1Plan {
     int patches;                                 // 1: fine levels are matched in 8 x 4 patches per warp
     unsigned patch_off[PAA_MAX_LEVELS + 1];      // first 32 x 8 region of each fine level (per image)
     int patch_rx[PAA_MAX_LEVELS];                // regions per grid row
+    int patch_h[PAA_MAX_LEVELS];                 // grid height of the level
+    unsigned patch_magic[PAA_MAX_LEVELS];        // floor(2^16 / patch_rx) + 1: r / patch_rx == (r * magic) >> 16 while r * patch_rx < 2^16
 };
 
 // order-preserving map float -> unsigned (and back), so that floats compare / reduce as integers
@@ -104,46 +106,49 @@ iou_match_kernel(const Geometry geo, const GtOffsets* __restrict__ gop, const Pa
     pdl_wait();                       // the GT ranges and the cleared maxima come from prep_step_kernel
     __shared__ WarpGts s_gts[kPassThreads / PAA_WARP];
     const GtOffsets& go = *gop;
+    // grid: x = work item inside an image (the coarse levels first: their anchors intersect every GT), y = image in
+    // the order of decreasing GT count (the cost of a block grows with the GT count of its image) -- blocks are
+    // dispatched x-fastest, so the heaviest work of the heaviest image starts first.  No division by a run-time
+    // value on this path: the kernel is bound by instruction issue and every warp pays for the prologue.
     const unsigned q = blockIdx.x;
-    // heaviest blocks first: the coarse levels (last tiles of an image) intersect every GT, and the
-    // cost of a block grows with the GT count of its image
-    const unsigned heavy_items = (unsigned)geo.num_images * (unsigned)plan.heavy_pairs * (unsigned)plan.parts;
-    int n, tile0, tile_end, part = 0, parts = 1;
+    const int n = go.by_load[blockIdx.y];
+    const unsigned heavy_items = (unsigned)plan.heavy_pairs * (unsigned)plan.parts;       // per image
+    const bool heavy = q < heavy_items;
+    int tile0 = 0, tile_end = 0, part = 0, parts = 1;
     bool split = false;
-    if (q < heavy_items) {
-        n = go.by_load[q % geo.num_images];
-        const unsigned r = q / geo.num_images;
+    if (heavy) {
         parts = plan.parts;
-        part = (int)(r % (unsigned)parts);
-        tile0 = plan.light_tiles + 2 * (plan.heavy_pairs - 1 - (int)(r / (unsigned)parts));
+        const unsigned pair = parts > 1 ? q / (unsigned)parts : q;
+        part = (int)(q - pair * (unsigned)parts);
+        tile0 = plan.light_tiles + 2 * (plan.heavy_pairs - 1 - (int)pair);
         tile_end = geo.tiles_per_image;
         split = parts > 1;
     } else {
-        const unsigned r = q - heavy_items;
-        n = go.by_load[r % geo.num_images];
-        tile0 = 2 * (plan.light_pairs - 1 - (int)(r / geo.num_images));
+        tile0 = 2 * (plan.light_pairs - 1 - (int)(q - heavy_items));
         tile_end = plan.light_tiles;
     }
     int l = 0, i = 0;
     bool valid = false;
-    if (q >= heavy_items && plan.patches) {
+    if (!heavy && plan.patches) {
         // region index inside the image, coarsest fine level first
         const unsigned per_image = plan.patch_off[PAA_MAX_LEVELS];
-        const unsigned reg = per_image - 1u - (q - heavy_items) / geo.num_images;
+        const unsigned reg = per_image - 1u - (q - heavy_items);
 #pragma unroll
         for (int k = 1; k < PAA_MAX_LEVELS; ++k)
             if (k < geo.num_levels && plan.patch_off[k] <= reg && plan.patch_off[k] < per_image) l = k;
-        unsigned off_l = plan.patch_off[0];
-        int prx = plan.patch_rx[0];
+        unsigned off_l = plan.patch_off[0], magic = plan.patch_magic[0];
+        int prx = plan.patch_rx[0], H = plan.patch_h[0];
 #pragma unroll
         for (int k = 1; k < PAA_MAX_LEVELS; ++k)       // selects, not indexed reads: the plan stays in the constant bank
             if (k == l) {
                 off_l = plan.patch_off[k];
                 prx = plan.patch_rx[k];
+                magic = plan.patch_magic[k];
+                H = plan.patch_h[k];
             }
-        const int rr = (int)(reg - off_l);
-        const int W = geo.lv[l].grid_w, H = geo.lv[l].hw / W;
-        const int ry = rr / prx, rx = rr - ry * prx;
+        const unsigned rr = reg - off_l;
+        const int W = geo.lv[l].grid_w;
+        const int ry = (int)((rr * magic) >> 16), rx = (int)rr - ry * prx;       // rr / prx
         const int w = threadIdx.x >> 5, ln = threadIdx.x & 31;
         const int col = rx * 32 + 8 * (w & 3) + (ln & 7), row = ry * 8 + 4 * (w >> 2) + (ln >> 3);
         valid = col < W && row < H;
@@ -174,7 +179,7 @@ iou_match_kernel(const Geometry geo, const GtOffsets* __restrict__ gop, const Pa
     const int g_lo = (int)(((long long)G_all * part) / parts), G = (int)(((long long)G_all * (part + 1)) / parts);
     float best_v = 0.0f;
     int best_g = 0;
-    const bool crowded = G_all > 128, heavy = q < heavy_items;
+    const bool crowded = G_all > 128;
     unsigned* gtmax_image = gtmax + gbase;
 
     for (int c0 = g_lo; c0 < G; c0 += PAA_WARP) {
@@ -303,6 +308,8 @@ int launch_iou_match(const Geometry& geo, const float* gt_boxes, const LossScala
     for (int l = 0; l < PAA_MAX_LEVELS; ++l) {
         plan.patch_off[l] = regions;
         plan.patch_rx[l] = 1;
+        plan.patch_h[l] = 1;
+        plan.patch_magic[l] = 65537u;
         if (l >= heavy_level) continue;
         const LevelView& lv = geo.lv[l];
         if (lv.grid_w <= 0) {
@@ -310,16 +317,21 @@ int launch_iou_match(const Geometry& geo, const float* gt_boxes, const LossScala
             continue;
         }
         plan.patch_rx[l] = (lv.grid_w + 31) / 32;
-        regions += (unsigned)plan.patch_rx[l] * (unsigned)((lv.hw / lv.grid_w + 7) / 8);
+        plan.patch_h[l] = lv.hw / lv.grid_w;
+        plan.patch_magic[l] = 65536u / (unsigned)plan.patch_rx[l] + 1u;
+        const unsigned level_regions = (unsigned)plan.patch_rx[l] * (unsigned)((plan.patch_h[l] + 7) / 8);
+        if ((unsigned long long)level_regions * (unsigned)plan.patch_rx[l] >= 65536ull) plan.patches = 0;   // beyond the magic division's range (r * d < 2^16)
+        regions += level_regions;
     }
     plan.patch_off[PAA_MAX_LEVELS] = regions;
     if (regions == 0) plan.patches = 0;
     const unsigned light_items = plan.patches ? regions : (unsigned)plan.light_pairs;
-    plan.iou_blocks = (unsigned)geo.num_images * (light_items + (unsigned)(plan.heavy_pairs * plan.parts));
+    plan.iou_blocks = light_items + (unsigned)(plan.heavy_pairs * plan.parts);          // per image
     const GtOffsets* gop = ws.go;
     unsigned long long* best = reinterpret_cast<unsigned long long*>(ws.best);
     KernelTimer timer(PAA_KERNEL_PASS1, stream);
-    PAA_PDL_LAUNCH(iou_match_kernel, plan.iou_blocks, kPassThreads, stream, geo, gop, plan, gt_boxes, ws.gtmax, best);
+    PAA_PDL_LAUNCH(iou_match_kernel, dim3(plan.iou_blocks, (unsigned)geo.num_images), kPassThreads, stream, geo, gop,
+                   plan, gt_boxes, ws.gtmax, best);
     return 0;
 }
 

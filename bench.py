@@ -92,8 +92,9 @@ LOSS_KERNELS = [
      "top stalls wait / short_scoreboard)"),
     ("bulk_focal_kernel", "final_loss", "hbm", lambda A, C: A * (4 * C + 4 * C),
      "every logit read once, its gradient written once"),
-    ("positive_terms_kernel", "positive_terms", "hbm", lambda A, C: A * (4 + 20), "24 B per anchor"),
-    ("finish_loss_kernel", "finish_loss", "latency", lambda A, C: 0, "one block folds the partial sums"),
+    ("positive_list_kernel", "positive_terms", "latency", lambda A, C: A * (4 + 20),
+     "the positives from per-GT lists (dependent loads per positive), zero gradients elsewhere, loss fold in the "
+     "last block"),
 ]
 POST_KERNELS = [
     ("post_candidates_kernel", "post_candidates", "hbm", lambda A, C: A * (4 * C + 4 + 16 + 16),

@@ -29,7 +29,7 @@ def _check_roofline(r):
     assert r["bound"] == "hbm" and r["unit"] == "GB/s" and r["peak"] > 1000
     assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
     rows = r["per_kernel"]
-    assert len(rows) >= 6 and all(row["us"] > 0 for row in rows)
+    assert len(rows) >= 5 and all(row["us"] > 0 for row in rows)
     longest = max(rows, key=lambda row: row["us"])
     assert r["kernel"] == longest["kernel"]            # the dominant kernel is the longest one, not the best one
     assert all(row["bound"] in ("hbm", "latency", "alu") for row in rows)

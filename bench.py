@@ -625,13 +625,19 @@ class LossRun(object):
         used_peer = paa_loss.PeerNormExchange.get(self.ctx.dev) is not None
         return rel, (1.0 if used_peer else 0.0)
 
-    def e2e(self, steps, warmup):
-        """Host buffers in, losses out, eager, public API.  The step's inputs live in pinned host memory, packed the
+    def e2e(self, steps, warmup, graph_mode=True):
+        """Host buffers in, losses out, public API.  The step's inputs live in pinned host memory, packed the
         way a collate function would leave them (one block for the head outputs, one each for the boxes / labels of all
         images).  Every step copies them to the device on a copy stream into one of two device buffers (the copy of
         step k+1 overlaps the kernels of step k), calls the reference-facing evaluator + autograd on views of that
         buffer, and reads the three losses back into pinned memory.  Returns (device ms, wall ms, h2d bytes, d2h)."""
-        ctx, dev, L, ev = self.ctx, self.ctx.dev, self.L, self.ev
+        import paa_b200
+        ctx, dev, L = self.ctx, self.ctx.dev, self.L
+        # the evaluator in graph mode (a public switch of PAALossComputation): the two device input buffers alternate,
+        # so two captured steps serve all calls; targets change through the device-resident GT ranges
+        cfg = paa_b200.default_cfg()
+        ev = paa_b200.make_paa_loss_evaluator(cfg, paa_b200.BoxCoder(cfg))
+        ev.use_graph = graph_mode
         heads_h = self.h_cls + self.h_reg + self.h_iou
         sizes = [t.numel() for t in heads_h]
         h_pack = torch.empty(sum(sizes), dtype=torch.float32).pin_memory()
@@ -727,8 +733,14 @@ def measure_loss(ctx, args, scaling, full):
         res["e2e"] = {"value": total * args.steps / (max(e_ms, e_wall) / 1000.0), "unit": UNIT,
                       "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                       "ms_per_step": max(e_ms, e_wall) / args.steps,
-                      "what": "PAALossComputation.__call__ + torch.autograd.grad, inputs copied from pinned host "
-                              "memory and losses read back every step (per-rank bytes)"}
+                      "what": "PAALossComputation.__call__ + torch.autograd.grad (evaluator in graph mode, use_graph), "
+                              "inputs copied from pinned host memory and losses read back every step (per-rank bytes)"}
+        if not args.no_side:
+            g_ms, g_wall, _, _ = run.e2e(args.steps, args.warmup, graph_mode=False)
+            g_ms, g_wall = ctx.max_over_ranks([g_ms, g_wall])
+            res["e2e"]["eager_launches"] = {"value": total * args.steps / (max(g_ms, g_wall) / 1000.0), "unit": UNIT,
+                                            "ms_per_step": max(g_ms, g_wall) / args.steps,
+                                            "what": "the same with use_graph off (every kernel launched by the host)"}
         if ctx.world == 1 and not args.no_side:
             try:
                 ms = run.eager_api_ms(args.steps)

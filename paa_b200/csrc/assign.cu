@@ -219,10 +219,11 @@ int first_heavy_level(const Geometry& geo) {
     return l;
 }
 
-// Number of GT-list parts for the coarse tiles: about 128 GTs per part for the busiest image the call can hold, at
-// most 8 (one part, i.e. no split and no atomics, for the usual <= 100 GTs per image).
+// Number of GT-list parts for the coarse tiles, whose anchors overlap every GT of the image: their walk over the GT
+// list is the kernel's longest dependent path, so it is cut into ranges of about 32 GTs (at most 8 parts) whose
+// per-anchor results meet in an atomicMax -- one part, i.e. no split and no atomics, up to 32 GTs per image.
 int gt_parts_for(int max_gt_per_image) {
-    int p = (max_gt_per_image + 127) / 128;
+    int p = (max_gt_per_image + 31) / 32;
     return p < 1 ? 1 : (p > 8 ? 8 : p);
 }
 
@@ -892,7 +893,8 @@ __device__ __forceinline__ unsigned long long topk_first_batch(unsigned long lon
 
 template <int SPL>
 // (64 registers: with the usual five levels six blocks fit an SM, so ~900 GTs are one wave)
-__global__ void __launch_bounds__(PAA_MAX_LEVELS * PAA_WARP, 4)
+// (four samples per lane -- TOPK 20 -- need more than 64 registers: no spills at two 256-thread blocks per SM)
+__global__ void __launch_bounds__(PAA_MAX_LEVELS * PAA_WARP, SPL >= 4 ? 2 : 4)
 select_gmm_kernel(const Geometry geo, const GtOffsets* __restrict__ gop, const int* __restrict__ gt_image,
                   const float* __restrict__ gt_boxes, const int64_t* __restrict__ gt_labels,
                   const LossScalars sc, const uint4* __restrict__ tile_gtmask,

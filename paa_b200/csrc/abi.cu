@@ -284,6 +284,13 @@ static int plan_loss(const PaaLossArgs* a, LossPlan* p) {
 
 using namespace paa;
 
+#ifdef PAA_TRACE
+namespace paa {
+int trace_set_assign(unsigned long long* p);
+int trace_set_loss(unsigned long long* p);
+}
+#endif
+
 extern "C" {
 
 int paa_abi_version(void) { return PAA_ABI_VERSION; }
@@ -502,6 +509,15 @@ int paa_kernel_timing_end(float* total_ms, int32_t* launches) {
     g_timed_count = 0;
     return 0;
 }
+
+#ifdef PAA_TRACE
+// measurement build only (tools/step_trace.py): device buffer of 4 x 8 timestamps per kernel slot, see common.cuh
+int paa_trace_set(unsigned long long* device_buffer) {
+    int rc = paa::trace_set_assign(device_buffer);
+    if (!rc) rc = paa::trace_set_loss(device_buffer);
+    return rc;
+}
+#endif
 
 size_t paa_ml_nms_workspace_bytes(int n) { return ml_nms_workspace_bytes(n); }
 

@@ -102,8 +102,10 @@ __global__ void __launch_bounds__(kPassThreads)
 iou_match_kernel(const Geometry geo, const GtOffsets* __restrict__ gop, const Pass1Plan plan,
                  const float* __restrict__ gt_boxes, unsigned* __restrict__ gtmax,
                  unsigned long long* __restrict__ best) {
+    PAA_TRACE_SCOPE(1);
     pdl_launch_dependents();
     pdl_wait();                       // the GT ranges and the cleared maxima come from prep_step_kernel
+    PAA_TRACE_WAITED();
     __shared__ WarpGts s_gts[kPassThreads / PAA_WARP];
     const GtOffsets& go = *gop;
     // grid: x = work item inside an image (the coarse levels first: their anchors intersect every GT), y = image in
@@ -238,6 +240,7 @@ __global__ void __launch_bounds__(256)
 prep_step_kernel(const GtOffsets host_go, const int* __restrict__ dev_offsets, int num_images, int capacity,
                  GtOffsets* __restrict__ dst, int* __restrict__ gt_image, uint4* __restrict__ zero_base,
                  size_t zero_vec, uint2* __restrict__ best, int A, int best_a0, int best_n) {
+    PAA_TRACE_SCOPE(0);
     pdl_launch_dependents();
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (size_t)gridDim.x * blockDim.x;
     for (size_t i = tid; i < zero_vec; i += nthr) zero_base[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -269,6 +272,10 @@ prep_step_kernel(const GtOffsets host_go, const int* __restrict__ dev_offsets, i
     for (int n = 0; n < num_images; ++n)
         for (int g = s_v[n] + threadIdx.x; g < s_v[n + 1]; g += blockDim.x) gt_image[g] = n;
 }
+
+#ifdef PAA_TRACE
+PAA_TRACE_SETTER(trace_set_assign)
+#endif
 
 int launch_prep_step(const Geometry& geo, const GtOffsets& host_go, const int* dev_offsets, const LossScalars& sc,
                      const LossWorkspace& ws, void* zero_base, bool clear_heavy_best, bool clear_all_best,
@@ -380,7 +387,9 @@ match_score_kernel(const Geometry geo, const GtOffsets* __restrict__ gop, const 
                    int* __restrict__ matched, float* __restrict__ score, int* __restrict__ paa_label, uint4* __restrict__ tile_gtmask,
                    int* __restrict__ seg_count, unsigned long long* __restrict__ seg_pool,
                    const float* __restrict__ teacher_score, const LossDebug dbg) {
+    PAA_TRACE_SCOPE(2);
     pdl_wait();
+    PAA_TRACE_WAITED();
     pdl_launch_dependents();
     const GtOffsets& go = *gop;
     __shared__ int s_lq[PAA_TILE];
@@ -905,7 +914,9 @@ select_gmm_kernel(const Geometry geo, const GtOffsets* __restrict__ gop, const i
                   unsigned* __restrict__ ticket, double* __restrict__ local_norm,
                   double* __restrict__ normalisers, const PeerExchange px, const LossDebug dbg) {
     // lets the loss pass (a programmatic dependent launch) become resident and prefetch while the slowest fits run
+    PAA_TRACE_SCOPE(3);
     pdl_wait();
+    PAA_TRACE_WAITED();
     pdl_launch_dependents();
     __shared__ unsigned long long s_level[PAA_MAX_LEVELS][PAA_WARP];   // per-level top-K, ascending
     __shared__ int s_cnt[PAA_MAX_LEVELS];

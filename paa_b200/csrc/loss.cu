@@ -227,6 +227,7 @@ bulk_focal_kernel(const BulkPlan plan, const LossScalars sc, const double* __res
     __shared__ double s_part[kBulkThreads / PAA_WARP];
     const float gamma = sc.gamma, oma = 1.0f - sc.alpha;
     float neg_sum = 0.f;
+    PAA_TRACE_SCOPE(4);
     const unsigned n_chunks = plan.chunk_off[plan.n];
     unsigned ch = blockIdx.x;
     // Programmatic dependent launch: this grid may become resident while the kernel that produces the normalisers
@@ -270,6 +271,7 @@ bulk_focal_kernel(const BulkPlan plan, const LossScalars sc, const double* __res
         }
     }
     pdl_wait();
+    PAA_TRACE_WAITED();
     pdl_launch_dependents();        // after the wait: at most one future kernel sits resident behind the running one
     const GradScales gs = make_scales(sc, norm, local_norm, gout);
     const float kneg = oma * gs.cls;
@@ -701,7 +703,9 @@ positive_list_kernel(const Geometry geo, const GtOffsets* __restrict__ gop, cons
                      unsigned* __restrict__ ticket, float* __restrict__ losses) {
     __shared__ double s_part[kPosThreads / PAA_WARP][3];
     __shared__ bool s_last;
+    PAA_TRACE_SCOPE(5);
     pdl_wait();
+    PAA_TRACE_WAITED();
     pdl_launch_dependents();
     const GtOffsets& go = *gop;
     const int num_gt = go.v[geo.num_images];
@@ -827,6 +831,10 @@ positive_list_kernel(const Geometry geo, const GtOffsets* __restrict__ gop, cons
         *ticket = 0u;                   // paa_loss may be called again on the same assignment
     }
 }
+
+#ifdef PAA_TRACE
+PAA_TRACE_SETTER(trace_set_loss)
+#endif
 
 int launch_final_loss(const Geometry& geo, const float* gt_boxes,
                       const LossScalars& sc, const LossWorkspace& ws, const double* normalisers,

@@ -1,0 +1,93 @@
+"""Measurement aid: where each kernel of the loss step sits on the GPU's %globaltimer inside a CUDA-graph replay.
+
+Event pairs serialise the programmatic dependent launches they are meant to observe; this reads timestamps that the
+kernels of a -DPAA_TRACE build leave themselves (common.cuh: TraceScope).  Usage (GPU box):
+
+    python tools/step_trace.py [--images 16] [--config C2] [--replays 20]
+
+builds paa_b200/libpaa_b200_trace.so if needed, re-executes itself with PAA_B200_LIB pointing at it, and prints per
+kernel: first block start, first block past its dependency wait, last block start, last block end (us, relative to the
+start of the step's first kernel; median over the replays).
+"""
+import argparse
+import ctypes
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+TRACE_LIB = os.path.join(ROOT, "paa_b200", "libpaa_b200_trace.so")
+NAMES = ["prep_step", "iou_match", "match_score", "select_gmm", "bulk_focal", "positive_list"]
+
+
+def build_trace_lib():
+    from paa_b200 import build as b
+    cmd = [b._nvcc()] + b.NVCC_FLAGS + ["-DPAA_TRACE"] + [os.path.join(b.CSRC, s) for s in b.SOURCES] + ["-o", TRACE_LIB]
+    subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.STDOUT)
+    return TRACE_LIB
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--images", type=int, default=16)
+    ap.add_argument("--gt", type=int, nargs=2, default=[1, 100])
+    ap.add_argument("--replays", type=int, default=20)
+    ap.add_argument("--build-only", action="store_true")
+    args = ap.parse_args()
+    if args.build_only:
+        print(build_trace_lib())
+        return
+    if os.environ.get("PAA_B200_LIB") != TRACE_LIB:
+        if not os.path.exists(TRACE_LIB):
+            build_trace_lib()
+        env = dict(os.environ, PAA_B200_LIB=TRACE_LIB)
+        sys.exit(subprocess.call([sys.executable] + sys.argv, env=env))
+
+    import numpy as np
+    import torch
+    import paa_b200
+    from paa_b200 import _lib, synthetic
+    from paa_b200.synthetic import to_device_inputs
+    lib = _lib.load()
+    raw = ctypes.CDLL(TRACE_LIB)
+    raw.paa_trace_set.argtypes = [ctypes.c_void_p]
+    raw.paa_trace_set.restype = ctypes.c_int
+    b = synthetic.make_batch(seed=2000, num_images=args.images, image_hw=(800, 1333), gt_per_image=tuple(args.gt))
+    cfg = paa_b200.default_cfg()
+    ev = paa_b200.make_paa_loss_evaluator(cfg, paa_b200.BoxCoder(cfg))
+    cls, reg, iou, targets, anchors = to_device_inputs(b)
+    trace = torch.zeros(8 * 4, dtype=torch.int64, device="cuda")
+    assert raw.paa_trace_set(ctypes.c_void_p(trace.data_ptr())) == 0
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    for _ in range(3):
+        ev.forward_backward(cls, reg, iou, targets, anchors)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        ev.forward_backward(cls, reg, iou, targets, anchors)
+    init = torch.zeros(8, 4, dtype=torch.int64)
+    init[:, 0] = init[:, 1] = (1 << 62)
+    init = init.reshape(-1).cuda()
+    rows = []
+    for _ in range(args.replays):
+        flush.fill_(1)
+        trace.copy_(init)
+        torch.cuda.synchronize()
+        g.replay()
+        torch.cuda.synchronize()
+        t = trace.cpu().numpy().reshape(8, 4)[:len(NAMES)].astype(np.float64)
+        t0 = t[0, 0]
+        rows.append((t - t0) / 1000.0)
+    med = np.median(np.stack(rows), axis=0)
+    print("%d images, %d GT; us relative to the first block of prep_step_kernel (median of %d graph replays, L2 flushed)"
+          % (args.images, sum(len(x) for x in b.gt_boxes), args.replays))
+    print("%-16s %10s %12s %12s %10s %8s" % ("kernel", "first start", "first waited", "last start", "last end", "span"))
+    for i, nm in enumerate(NAMES):
+        s0, w, e, ls = med[i]
+        print("%-16s %10.1f %12.1f %12.1f %10.1f %8.1f" % (nm, s0, w if w < 1e9 else float("nan"), ls, e, e - (w if w < 1e9 else s0)))
+    print("step: %.1f us" % med[len(NAMES) - 1, 2])
+
+
+if __name__ == "__main__":
+    main()

@@ -288,6 +288,7 @@ using namespace paa;
 namespace paa {
 int trace_set_assign(unsigned long long* p);
 int trace_set_loss(unsigned long long* p);
+int trace_set_post(unsigned long long* p);
 }
 #endif
 
@@ -515,6 +516,7 @@ int paa_kernel_timing_end(float* total_ms, int32_t* launches) {
 int paa_trace_set(unsigned long long* device_buffer) {
     int rc = paa::trace_set_assign(device_buffer);
     if (!rc) rc = paa::trace_set_loss(device_buffer);
+    if (!rc) rc = paa::trace_set_post(device_buffer);
     return rc;
 }
 #endif

@@ -24,6 +24,8 @@
 //   vote       : one warp per output row averages the same-class pre-NMS boxes
 #include "post.h"
 
+#include <climits>
+
 namespace paa {
 
 constexpr int kHistBins = 2048;
@@ -213,6 +215,7 @@ __device__ __forceinline__ void divmod_small(unsigned n, unsigned d, float inv, 
 __global__ void __launch_bounds__(kCandThreads, kCandBlocksPerSM)
 post_candidates_kernel(const Geometry geo, const CandPlan plan, const float thr, const float logit_gate,
                        uint2* __restrict__ cand, int* __restrict__ cand_count, int* __restrict__ hist) {
+    PAA_TRACE_SCOPE(8);
     __shared__ float q_x[kCandQueue];              // gated logit
     __shared__ unsigned q_e[kCandQueue];           // its element index inside the image's [C, H*W] block
     __shared__ unsigned short q_where[kCandQueue]; // (image << 3) | level
@@ -361,6 +364,7 @@ post_candidates_kernel(const Geometry geo, const CandPlan plan, const float thr,
 __global__ void __launch_bounds__(256)
 post_threshold_kernel(const int* __restrict__ cand_count, const int* __restrict__ hist, int topn,
                       int* __restrict__ thr_bin, int* __restrict__ n_above, int* __restrict__ k_sel) {
+    PAA_TRACE_SCOPE(9);
     __shared__ int s_suffix[256];
     const int seg = blockIdx.x;
     const int count = cand_count[seg];
@@ -414,6 +418,7 @@ __global__ void __launch_bounds__(256)
 post_filter_kernel(const Geometry geo, const uint2* __restrict__ cand, const int* __restrict__ cand_count,
                    const int* __restrict__ thr_bin, int topn, uint2* __restrict__ sel,
                    int* __restrict__ sel_count, unsigned* __restrict__ bnd, int* __restrict__ bnd_count) {
+    PAA_TRACE_SCOPE(10);
     const int seg = blockIdx.x / kFilterBlocks;
     const int part = blockIdx.x - seg * kFilterBlocks;
     const int n = seg / geo.num_levels, l = seg - n * geo.num_levels;
@@ -497,15 +502,32 @@ __device__ __forceinline__ void radix_pick_digit(const int* s_hist, int need, in
 
 // ---------------------------------------------------------------------------------------------
 // select: finish top-k, canonical order, decode + clip
+//
+// One block of 256 threads per (image, level) -- every list of a 64-image call is resident at once (four blocks per
+// SM; the 1024-thread version ran 320 lists in three waves of 148).  A thread owns EPT = topn / 256 entries in
+// registers.  Order: the k survivors must come out by ascending candidate index (the order nonzero() enumerates
+// them, inference.py:66).  Instead of a bitonic sort (55 block barriers for 1024 keys) the entries are dealt into
+// 1024 buckets by the high bits of the index (counting sort: histogram, scan, scatter -- three barriers) and every
+// entry finds its rank inside its bucket by counting (a bucket holds a few entries: candidates of one object
+// cluster, but over many buckets); the thread that ranked an entry decodes its box and writes the row.
 // ---------------------------------------------------------------------------------------------
-constexpr int kSelectThreads = 1024;
+constexpr int kSelectThreads = 256;
+constexpr int kSelectBuckets = 1024;
 constexpr int kSelectCached = 2;            // boundary keys a thread keeps in registers
+constexpr int kSelectSmallB = 1024;         // boundary sets up to this size are ranked by counting
 
 // key of a candidate for "better first": higher score, then lower candidate index
 __device__ __forceinline__ unsigned long long better_key(uint2 v) {
     return ((unsigned long long)v.x << 32) | (unsigned long long)(0xffffffffu - v.y);
 }
 
+struct SelectSmem {                          // dynamic: [cap] index, [cap] score bits, [cap] keep flags
+    unsigned* idx;
+    unsigned* sc;
+    unsigned char* keep;
+};
+
+template <int EPT>
 __global__ void __launch_bounds__(kSelectThreads)
 post_select_kernel(const Geometry geo, const ImageSizes sizes, const uint2* __restrict__ cand,
                    const unsigned* __restrict__ bnd, const int* __restrict__ bnd_count,
@@ -514,13 +536,20 @@ post_select_kernel(const Geometry geo, const ImageSizes sizes, const uint2* __re
                    uint2* __restrict__ sel,
                    int* __restrict__ pre_cnt, float4* __restrict__ pre_box, float* __restrict__ pre_score,
                    int* __restrict__ pre_label) {
-    __shared__ unsigned s_idx[kMaxTopN];
-    __shared__ unsigned s_sc[kMaxTopN];
+    PAA_TRACE_SCOPE(11);
+    constexpr int kCap = EPT * kSelectThreads;
+    extern __shared__ __align__(16) unsigned char s_dyn[];
+    unsigned* s_idx = reinterpret_cast<unsigned*>(s_dyn);
+    unsigned* s_sc = s_idx + kCap;
+    unsigned char* s_keep = reinterpret_cast<unsigned char*>(s_sc + kCap);
+    __shared__ int s_bucket[kSelectBuckets + 1];       // counts, then exclusive starts
+    __shared__ unsigned long long s_bkey[kSelectSmallB];
     __shared__ int s_hist[256];
+    __shared__ int s_wsum[kSelectThreads / 32];
     __shared__ unsigned long long s_prefix;
     __shared__ int s_need, s_fill;
-    __shared__ unsigned char s_keep[kMaxTopN];
 
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int seg = blockIdx.x;
     const int n = seg / geo.num_levels, l = seg - n * geo.num_levels;
     const LevelView& lv = geo.lv[l];
@@ -533,7 +562,22 @@ post_select_kernel(const Geometry geo, const ImageSizes sizes, const uint2* __re
     const int B = (thr_bin[seg] >= 0) ? bnd_count[seg] : 0;
     const int need = k - above;                 // entries still to take from the boundary bin
 
-    if (B > 0 && need > 0) {
+    for (int b = threadIdx.x; b <= kSelectBuckets; b += kSelectThreads) s_bucket[b] = 0;
+    if (threadIdx.x == 0) s_fill = 0;
+
+    if (B > 0 && need > 0 && B <= kSelectSmallB) {
+        // the usual case (a histogram bin holds a handful of the list's scores): rank by counting
+        for (int e = threadIdx.x; e < B; e += kSelectThreads) s_bkey[e] = better_key(list[blist[e]]);
+        __syncthreads();
+        for (int e = threadIdx.x; e < B; e += kSelectThreads) {
+            const unsigned long long mine = s_bkey[e];
+            int better = 0;
+            for (int j = 0; j < B; ++j) better += s_bkey[j] > mine ? 1 : 0;          // keys are unique
+            if (better < need)
+                mysel[above + better] = make_uint2((unsigned)(mine >> 32), 0xffffffffu - (unsigned)mine);
+        }
+        __syncthreads();
+    } else if (B > 0 && need > 0) {
         // exact radix select (8 bits x 8 passes, most significant first) of the `need` best keys; a thread
         // keeps its first kSelectCached boundary keys in registers so that the passes do not go back to memory
         unsigned long long ck[kSelectCached];
@@ -577,8 +621,6 @@ post_select_kernel(const Geometry geo, const ImageSizes sizes, const uint2* __re
         }
         // keys are unique, so exactly `need` of them are >= the selected key
         const unsigned long long tkey = s_prefix;
-        if (threadIdx.x == 0) s_fill = 0;
-        __syncthreads();
 #pragma unroll
         for (int c = 0; c < kSelectCached; ++c)
             if (threadIdx.x + c * kSelectThreads < B && ck[c] >= tkey) mysel[above + atomicAdd(&s_fill, 1)] = cv[c];
@@ -587,46 +629,77 @@ post_select_kernel(const Geometry geo, const ImageSizes sizes, const uint2* __re
             if (better_key(v) >= tkey) mysel[above + atomicAdd(&s_fill, 1)] = v;
         }
         __syncthreads();
+    } else {
+        __syncthreads();
     }
 
-    // canonical order: ascending candidate index (the order nonzero() enumerates them, inference.py:66).
-    // Bitonic sort of the (index, score) pairs in shared memory, padded to a power of two with index ~0.
-    int n2 = 32;
-    while (n2 < k) n2 <<= 1;
-    for (int t = threadIdx.x; t < n2; t += kSelectThreads) {
-        uint2 v = make_uint2(0u, 0xffffffffu);
-        if (t < k) v = mysel[t];
-        s_sc[t] = v.x;
-        s_idx[t] = v.y;
-    }
-    __syncthreads();
-    for (int size = 2; size <= n2; size <<= 1) {
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            for (int i = threadIdx.x; i < (n2 >> 1); i += kSelectThreads) {
-                const int pos = 2 * i - (i & (stride - 1));
-                const unsigned a = s_idx[pos], b = s_idx[pos + stride];
-                const bool ascending = (pos & size) == 0;
-                if ((a > b) == ascending) {
-                    s_idx[pos] = b;
-                    s_idx[pos + stride] = a;
-                    const unsigned sa = s_sc[pos];
-                    s_sc[pos] = s_sc[pos + stride];
-                    s_sc[pos + stride] = sa;
-                }
-            }
-            __syncthreads();
+    // ---- canonical order: counting sort over index buckets + rank inside the bucket ----------------
+    // bucket = index >> shift with the level's index range (anchors * classes) spread over <= 1024 buckets
+    const unsigned range = (unsigned)lv.n_anchor * (unsigned)geo.C;
+    int shift = 0;
+    while ((range >> shift) >= (unsigned)kSelectBuckets) ++shift;
+    uint2 ent[EPT];
+    int slot[EPT];
+#pragma unroll
+    for (int i = 0; i < EPT; ++i) {
+        const int t = threadIdx.x + i * kSelectThreads;
+        slot[i] = -1;
+        if (t < k) {
+            ent[i] = mysel[t];
+            slot[i] = atomicAdd(&s_bucket[ent[i].y >> shift], 1);
         }
     }
+    __syncthreads();
+    // exclusive scan of the 1024 counts: four per thread, warp scan, warp totals
+    {
+        constexpr int per = kSelectBuckets / kSelectThreads;
+        int c[per];
+        int sum = 0;
+#pragma unroll
+        for (int j = 0; j < per; ++j) {
+            c[j] = s_bucket[threadIdx.x * per + j];
+            sum += c[j];
+        }
+        int incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(PAA_FULL, incl, o);
+            if (lane >= o) incl += v;
+        }
+        if (lane == 31) s_wsum[warp] = incl;
+        __syncthreads();
+        int before = 0;
+        for (int w = 0; w < warp; ++w) before += s_wsum[w];
+        int run = before + incl - sum;
+#pragma unroll
+        for (int j = 0; j < per; ++j) {
+            s_bucket[threadIdx.x * per + j] = run;
+            run += c[j];
+        }
+        if (threadIdx.x == kSelectThreads - 1) s_bucket[kSelectBuckets] = run;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < EPT; ++i)
+        if (slot[i] >= 0) {
+            const int p = s_bucket[ent[i].y >> shift] + slot[i];
+            s_idx[p] = ent[i].y;
+            s_sc[p] = ent[i].x;
+        }
+    __syncthreads();
     const float img_w = sizes.wh[n][0], img_h = sizes.wh[n][1];
-    int dropped = 0;
-    for (int t0 = 0; t0 < k; t0 += kSelectThreads) {
-        const int t = t0 + threadIdx.x;            // = rank of the candidate
-        bool drop = false;
-        if (t < k) {
-            const unsigned my_idx = s_idx[t];
-            const int i = (int)(my_idx / (unsigned)geo.C);
-            const float4 a = ldg4(lv.anchors + (size_t)n * geo.anchor_image_stride + (size_t)i * 4);
-            const float* rp = lv.reg + head_offset(n, i, 0, 4, geo.apl, lv.hw);
+    bool any_drop = false;
+#pragma unroll
+    for (int i = 0; i < EPT; ++i) {
+        const int p = threadIdx.x + i * kSelectThreads;           // position in bucket order
+        if (p < k) {
+            const unsigned my_idx = s_idx[p];
+            const int b0 = s_bucket[my_idx >> shift], b1 = s_bucket[(my_idx >> shift) + 1];
+            int t = b0;                                           // = rank of the candidate
+            for (int j = b0; j < b1; ++j) t += s_idx[j] < my_idx ? 1 : 0;
+            const int ai = (int)(my_idx / (unsigned)geo.C);
+            const float4 a = ldg4(lv.anchors + (size_t)n * geo.anchor_image_stride + (size_t)ai * 4);
+            const float* rp = lv.reg + head_offset(n, ai, 0, 4, geo.apl, lv.hw);
             const float4 d = make_float4(__ldg(rp), __ldg(rp + lv.hw), __ldg(rp + 2 * (size_t)lv.hw),
                                          __ldg(rp + 3 * (size_t)lv.hw));
             float4 box;
@@ -640,18 +713,19 @@ post_select_kernel(const Geometry geo, const ImageSizes sizes, const uint2* __re
             box.w = fminf(fmaxf(box.w, 0.0f), img_h - 1.0f);
             const float ws = __fadd_rn(__fsub_rn(box.z, box.x), 1.0f);    // boxlist_ops.py:62-76
             const float hs = __fadd_rn(__fsub_rn(box.w, box.y), 1.0f);
-            drop = !((ws >= min_size) && (hs >= min_size));
+            const bool drop = !((ws >= min_size) && (hs >= min_size));
+            any_drop |= drop;
             s_keep[t] = drop ? 0 : 1;
             const size_t o = (size_t)seg * topn + t;
             pre_box[o] = box;
-            pre_score[o] = __uint_as_float(s_sc[t]);
+            pre_score[o] = __uint_as_float(s_sc[p]);
             pre_label[o] = (int)(my_idx % (unsigned)geo.C) + 1;           // inference.py:69
         }
-        dropped += __syncthreads_count(drop);
     }
+    const int dropped = __syncthreads_or(any_drop ? 1 : 0);
     if (threadIdx.x == 0) {
         int cnt = k;
-        if (dropped > 0) {
+        if (dropped) {
             // remove_small_boxes dropped something (non-finite boxes only when min_size == 0): close the
             // gaps in order.  Serial on purpose -- this path is not expected to run.
             cnt = 0;
@@ -670,6 +744,8 @@ post_select_kernel(const Geometry geo, const ImageSizes sizes, const uint2* __re
     }
 }
 
+static size_t select_smem_bytes(int ept) { return (size_t)ept * kSelectThreads * 9; }
+
 // ---------------------------------------------------------------------------------------------
 // rank: per image, order all boxes by (label asc, score desc, position asc) by counting
 // ---------------------------------------------------------------------------------------------
@@ -686,6 +762,7 @@ post_rank_kernel(int L, int topn, const int* __restrict__ pre_cnt, const float4*
                  const float* __restrict__ pre_score, const int* __restrict__ pre_label,
                  float4* __restrict__ s_box, float* __restrict__ s_score, int* __restrict__ s_label,
                  int* __restrict__ s_pos, int* __restrict__ total) {
+    PAA_TRACE_SCOPE(12);
     __shared__ unsigned long long s_keys[kRankThreads];
     __shared__ int s_cnt[PAA_MAX_LEVELS];
     const int n = blockIdx.y;
@@ -732,6 +809,7 @@ __global__ void __launch_bounds__(1024)
 post_group_kernel(int L, int topn, int C, const int* __restrict__ pre_cnt, const float* __restrict__ pre_score,
                   const int* __restrict__ pre_label, int* __restrict__ g_pos, float* __restrict__ g_score,
                   int* __restrict__ seg_start, int* __restrict__ n_seg, int* __restrict__ total) {
+    PAA_TRACE_SCOPE(13);
     extern __shared__ int s_lab[];          // [C+2] run starts, then [C+2] fill cursors
     __shared__ int s_cnt[PAA_MAX_LEVELS];
     const int n = blockIdx.x;
@@ -781,6 +859,7 @@ post_class_rank_kernel(int capN, const int* __restrict__ total, const int* __res
                        const float4* __restrict__ pre_box, const int* __restrict__ pre_label,
                        float4* __restrict__ s_box, float* __restrict__ s_score, int* __restrict__ s_label,
                        int* __restrict__ s_pos) {
+    PAA_TRACE_SCOPE(14);
     const int n = blockIdx.y;
     const int e = blockIdx.x * 256 + threadIdx.x;
     if (e >= total[n]) return;
@@ -809,6 +888,7 @@ post_class_rank_kernel(int capN, const int* __restrict__ total, const int* __res
 __global__ void __launch_bounds__(1024)
 post_segments_kernel(int capN, const int* __restrict__ total, const int* __restrict__ s_label,
                      int* __restrict__ seg_start, int* __restrict__ n_seg) {
+    PAA_TRACE_SCOPE(15);
     __shared__ int s_warp[32];
     __shared__ int s_running;
     const int n = blockIdx.x;
@@ -846,23 +926,29 @@ post_segments_kernel(int capN, const int* __restrict__ total, const int* __restr
 // (csrc/cuda/ml_nms.cu:13-24,55-70).  Tiles whose row and column label ranges are disjoint are
 // skipped and never read by the scan.
 // ---------------------------------------------------------------------------------------------
-// One block per (image, 64-row block); it walks the column blocks to its right for as long as their
-// first label does not exceed the row block's last label (boxes are sorted by label).
-__global__ void __launch_bounds__(64)
+// One WARP per (image, 32 consecutive sorted rows, column piece p of kMaskPieces): it walks the 64-column tiles
+// tile(first row) + p, + p + kMaskPieces, ... for as long as their first label does not exceed the warp's last label
+// (boxes are sorted by label).  A tile's boxes are staged in the warp's own slice of shared memory (no block barrier);
+// of its 64 columns only the contiguous range whose labels occur among the warp's rows is visited.  Splitting the
+// walk into pieces keeps a long run (a class with a thousand boxes: 16 tiles) off the critical path of small batches.
+constexpr int kMaskWarps = 4;
+constexpr int kMaskPieces = 4;
+
+__global__ void __launch_bounds__(kMaskWarps * 32)
 post_nms_mask_kernel(int capN, int nbw, float thr, const int* __restrict__ total,
                      const float4* __restrict__ s_box, const int* __restrict__ s_label,
                      unsigned long long* __restrict__ mask) {
-    __shared__ float4 s_cb[64];
-    __shared__ float s_ca[64];
-    __shared__ int s_cl[64];
-    const int n = blockIdx.y;
-    const int rb = blockIdx.x;
+    PAA_TRACE_SCOPE(16);
+    __shared__ float4 s_cb[kMaskWarps][64];
+    __shared__ float s_ca[kMaskWarps][64];
+    __shared__ int s_cl[kMaskWarps][64];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n = blockIdx.z;
     const int cnt = total[n];
-    const int r0 = rb * 64;
+    const int r0 = (blockIdx.x * kMaskWarps + warp) * 32;
     if (r0 >= cnt) return;
     const size_t base = (size_t)n * capN;
-    const int last_label = s_label[base + min(cnt, r0 + 64) - 1];
-    const int r = r0 + threadIdx.x;
+    const int r = r0 + lane;
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
     int al = -1;
     if (r < cnt) {
@@ -870,28 +956,54 @@ post_nms_mask_kernel(int capN, int nbw, float thr, const int* __restrict__ total
         al = s_label[base + r];
     }
     const float aa = area_plus1(a);
-    for (int cb = rb; cb * 64 < cnt; ++cb) {
+    const int first_label = __shfl_sync(PAA_FULL, al, 0);
+    const int last_label = __shfl_sync(PAA_FULL, al, min(cnt - r0, 32) - 1);
+    float4* cbx = s_cb[warp];
+    float* cba = s_ca[warp];
+    int* cbl = s_cl[warp];
+    for (int cb = (r0 >> 6) + (int)blockIdx.y; cb * 64 < cnt; cb += kMaskPieces) {
         const int c0 = cb * 64;
         if (s_label[base + c0] > last_label) break;               // no shared label from here on
         const int csize = min(64, cnt - c0);
-        __syncthreads();
-        if (threadIdx.x < csize) {
-            const float4 b = s_box[base + c0 + threadIdx.x];
-            s_cb[threadIdx.x] = b;
-            s_ca[threadIdx.x] = area_plus1(b);
-            s_cl[threadIdx.x] = s_label[base + c0 + threadIdx.x];
+        __syncwarp();
+        int l0 = INT_MAX, l1 = INT_MAX;                           // past-the-end columns sort after every label
+        if (lane < csize) {
+            const float4 b = s_box[base + c0 + lane];
+            cbx[lane] = b;
+            cba[lane] = area_plus1(b);
+            l0 = s_label[base + c0 + lane];
+            cbl[lane] = l0;
         }
-        __syncthreads();
-        if (r < cnt) {
-            unsigned long long bits = 0ull;
-            const int start = (rb == cb) ? threadIdx.x + 1 : 0;
-            for (int j = start; j < csize; ++j) {
-                if (s_cl[j] != al) continue;
-                if (iou_plus1(a, aa, s_cb[j], s_ca[j]) > thr) bits |= 1ull << j;
+        if (lane + 32 < csize) {
+            const float4 b = s_box[base + c0 + 32 + lane];
+            cbx[lane + 32] = b;
+            cba[lane + 32] = area_plus1(b);
+            l1 = s_label[base + c0 + 32 + lane];
+            cbl[lane + 32] = l1;
+        }
+        __syncwarp();
+        // columns whose label lies in [first_label, last_label]: one contiguous range of the sorted tile
+        const unsigned long long ge = (unsigned long long)__ballot_sync(PAA_FULL, l0 >= first_label) |
+                                      ((unsigned long long)__ballot_sync(PAA_FULL, l1 >= first_label) << 32);
+        const unsigned long long le = (unsigned long long)__ballot_sync(PAA_FULL, l0 <= last_label) |
+                                      ((unsigned long long)__ballot_sync(PAA_FULL, l1 <= last_label) << 32);
+        const unsigned long long live = ge & le;
+        unsigned long long bits = 0ull;
+        if (live) {
+            int j_lo = __ffsll((long long)live) - 1;
+            const int j_hi = 64 - __clzll((long long)live);
+            if (c0 + j_lo <= r0) j_lo = r0 + 1 - c0;              // nothing at or left of the warp's first row
+            for (int j = j_lo; j < j_hi; ++j) {
+                if (cbl[j] != al || c0 + j <= r) continue;
+                if (iou_plus1(a, aa, cbx[j], cba[j]) > thr) bits |= 1ull << j;
             }
-            mask[(base + r) * nbw + cb] = bits;
         }
+        if (r < cnt) mask[(base + r) * nbw + cb] = bits;
     }
+}
+
+static inline dim3 nms_mask_grid(int capN, int num_images) {
+    return dim3((capN + kMaskWarps * 32 - 1) / (kMaskWarps * 32), kMaskPieces, num_images);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -913,6 +1025,7 @@ post_nms_scan_kernel(int capN, int nbw, int segs_per_image, int num_images,
                      const int* __restrict__ seg_start,
                      const int* __restrict__ n_seg, const unsigned long long* __restrict__ mask,
                      unsigned char* __restrict__ keep_sorted) {
+    PAA_TRACE_SCOPE(17);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gw = blockIdx.x * kScanWarps + warp;
     const int n = gw / segs_per_image;
@@ -951,20 +1064,31 @@ post_nms_scan_kernel(int capN, int nbw, int segs_per_image, int num_images,
 // (csrc/cuda/ml_nms.cu:132-135 + boxlist[keep]), output rows.  One block per image.
 // ---------------------------------------------------------------------------------------------
 constexpr int kFinishThreads = 1024;
+constexpr int kFinishCached = 8;          // sorted rows a thread keeps in registers (covers capN <= 8192)
+constexpr int kFinishTaken = 1024;        // output rows the fast path can order in shared memory
 
+// The usual call keeps D = 100 rows of a few thousand: the cut is a radix select over the survivors' scores in SORTED
+// order (coalesced reads, the first rows of every thread cached in registers), and only the rows that pass it are
+// ordered by pre-NMS position (rank by counting among <= 1024 of them).  Calls that keep more rows than that (no cut,
+// or a tie at the D-th score wider than the buffer) take the general path below: survivor flags by position and an
+// ordered compaction over all positions.
 __global__ void __launch_bounds__(kFinishThreads)
 post_finish_kernel(int L, int topn, int det_per_img, int skip_nms, const int* __restrict__ pre_cnt,
                    const int* __restrict__ total, const float4* __restrict__ pre_box,
                    const float* __restrict__ pre_score, const int* __restrict__ pre_label,
-                   const int* __restrict__ s_pos, const unsigned char* __restrict__ keep_sorted,
+                   const int* __restrict__ s_pos, const float* __restrict__ s_score,
+                   const unsigned char* __restrict__ keep_sorted,
                    unsigned char* __restrict__ flag_by_pos, int* __restrict__ rank_by_pos,
                    float* __restrict__ out_boxes, float* __restrict__ out_scores,
                    long long* __restrict__ out_labels, int* __restrict__ out_count, int* __restrict__ out_rank,
                    unsigned char* __restrict__ dbg_keep) {
+    PAA_TRACE_SCOPE(18);
     __shared__ int s_hist[256];
     __shared__ int s_warp[32];
     __shared__ int s_running, s_need;
     __shared__ unsigned s_prefix;
+    __shared__ int s_tp[kFinishTaken], s_tr[kFinishTaken];
+    __shared__ int s_taken;
     const int n = blockIdx.x;
     const int capN = L * topn;
     const size_t base = (size_t)n * capN;
@@ -973,6 +1097,116 @@ post_finish_kernel(int L, int topn, int det_per_img, int skip_nms, const int* __
     unsigned char* flag = flag_by_pos + base;
     int* rpos = rank_by_pos + base;
 
+    // ---- fast path ---------------------------------------------------------------------------------
+    // key of sorted row r: the score's bit pattern (scores are > 0) if the row survived, else 0
+    auto row_key = [&](int r) -> unsigned {
+        const bool k = skip_nms ? true : keep_sorted[base + r] != 0;
+        return k ? __float_as_uint(s_score[base + r]) : 0u;
+    };
+    unsigned ck[kFinishCached];
+    int kept_fast = 0;
+#pragma unroll
+    for (int c = 0; c < kFinishCached; ++c) {
+        const int r = threadIdx.x + c * kFinishThreads;
+        ck[c] = r < cnt ? row_key(r) : 0u;
+        kept_fast += ck[c] != 0u;
+    }
+    for (int r = threadIdx.x + kFinishCached * kFinishThreads; r < cnt; r += kFinishThreads) kept_fast += row_key(r) != 0u;
+    if (threadIdx.x == 0) s_taken = 0;
+    int wk = kept_fast;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wk += __shfl_xor_sync(PAA_FULL, wk, o);
+    if (lane == 0) s_warp[warp] = wk;
+    __syncthreads();
+    int n_kept_f = 0;
+    for (int w = 0; w < kFinishThreads / 32; ++w) n_kept_f += s_warp[w];
+    __syncthreads();
+    unsigned cut = 1u;                                        // every survivor (keys of survivors are >= 1)
+    if (!skip_nms && det_per_img > 0 && n_kept_f > det_per_img) {
+        if (threadIdx.x == 0) {
+            s_prefix = 0u;
+            s_need = det_per_img;
+        }
+        __syncthreads();
+        for (int pass = 0; pass < 4; ++pass) {
+            const int shift = 24 - 8 * pass;
+            for (int b = threadIdx.x; b < 256; b += kFinishThreads) s_hist[b] = 0;
+            __syncthreads();
+            const unsigned prefix = s_prefix;
+            const unsigned hi_mask = (pass == 0) ? 0u : (~0u << (shift + 8));
+#pragma unroll
+            for (int c = 0; c < kFinishCached; ++c)
+                if (ck[c] != 0u && (ck[c] & hi_mask) == prefix) atomicAdd(&s_hist[(ck[c] >> shift) & 0xff], 1);
+            for (int r = threadIdx.x + kFinishCached * kFinishThreads; r < cnt; r += kFinishThreads) {
+                const unsigned key = row_key(r);
+                if (key != 0u && (key & hi_mask) == prefix) atomicAdd(&s_hist[(key >> shift) & 0xff], 1);
+            }
+            __syncthreads();
+            if (threadIdx.x < 32) {
+                int d, remaining;
+                radix_pick_digit(s_hist, s_need, threadIdx.x, &d, &remaining);
+                if (threadIdx.x == 0) {
+                    s_need = remaining;
+                    s_prefix = prefix | ((unsigned)d << shift);
+                }
+            }
+            __syncthreads();
+        }
+        cut = s_prefix;            // bit pattern of the D-th largest surviving score (ties keep more, inference.py:118-121)
+    }
+    // the rows that pass the cut, in arbitrary order; their number decides the path
+    int mine = 0;
+#pragma unroll
+    for (int c = 0; c < kFinishCached; ++c) mine += (ck[c] != 0u && ck[c] >= cut) ? 1 : 0;
+    for (int r = threadIdx.x + kFinishCached * kFinishThreads; r < cnt; r += kFinishThreads) {
+        const unsigned key = row_key(r);
+        mine += (key != 0u && key >= cut) ? 1 : 0;
+    }
+    int wm = mine;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wm += __shfl_xor_sync(PAA_FULL, wm, o);
+    if (lane == 0) s_warp[warp] = wm;
+    __syncthreads();
+    int n_taken = 0;
+    for (int w = 0; w < kFinishThreads / 32; ++w) n_taken += s_warp[w];
+    __syncthreads();
+    if (n_taken <= kFinishTaken && dbg_keep == nullptr) {
+#pragma unroll
+        for (int c = 0; c < kFinishCached; ++c)
+            if (ck[c] != 0u && ck[c] >= cut) {
+                const int r = threadIdx.x + c * kFinishThreads;
+                const int slot = atomicAdd(&s_taken, 1);
+                s_tr[slot] = r;
+                s_tp[slot] = s_pos[base + r];
+            }
+        for (int r = threadIdx.x + kFinishCached * kFinishThreads; r < cnt; r += kFinishThreads) {
+            const unsigned key = row_key(r);
+            if (key != 0u && key >= cut) {
+                const int slot = atomicAdd(&s_taken, 1);
+                s_tr[slot] = r;
+                s_tp[slot] = s_pos[base + r];
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < n_taken) {
+            const int p = s_tp[threadIdx.x];
+            int row = 0;
+            for (int j = 0; j < n_taken; ++j) row += s_tp[j] < p ? 1 : 0;      // positions are unique
+            const float4 b = pre_box[base + p];
+            float* ob = out_boxes + (base + row) * 4;
+            ob[0] = b.x;
+            ob[1] = b.y;
+            ob[2] = b.z;
+            ob[3] = b.w;
+            out_scores[base + row] = pre_score[base + p];
+            out_labels[base + row] = (long long)pre_label[base + p];
+            out_rank[base + row] = s_tr[threadIdx.x];
+        }
+        if (threadIdx.x == 0) out_count[n] = n_taken;
+        return;
+    }
+
+    // ---- general path ------------------------------------------------------------------------------
     // survivors by position
     for (int p = threadIdx.x; p < capN; p += kFinishThreads) flag[p] = 0;
     __syncthreads();
@@ -1082,6 +1316,7 @@ post_vote_kernel(int capN, const int* __restrict__ out_count, const int* __restr
                  const int* __restrict__ seg_start, const int* __restrict__ n_seg,
                  const float4* __restrict__ s_box, const float* __restrict__ s_score,
                  float* __restrict__ out_boxes) {
+    PAA_TRACE_SCOPE(19);
     const int n = blockIdx.y;
     const int lane = threadIdx.x & 31;
     const int gw = blockIdx.x * kVoteWarps + (threadIdx.x >> 5);
@@ -1160,6 +1395,10 @@ __global__ void post_debug_pre_kernel(int L, int topn, const int* __restrict__ p
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
+#ifdef PAA_TRACE
+PAA_TRACE_SETTER(trace_set_post)
+#endif
+
 int run_postprocess(const Geometry& geo, const PaaPostArgs* a, cudaStream_t stream) {
     const int N = a->num_images, L = a->num_levels, topn = a->pre_nms_top_n, C = a->num_classes;
     if (topn < 1 || topn > kMaxTopN) {
@@ -1245,9 +1484,24 @@ int run_postprocess(const Geometry& geo, const PaaPostArgs* a, cudaStream_t stre
     PAA_LAUNCH_CHECK("post_filter_kernel");
     {
         KernelTimer t(PAA_KERNEL_POST_SELECT, stream);
-        post_select_kernel<<<N * L, kSelectThreads, 0, stream>>>(geo, sizes, w.cand, w.bnd, w.bnd_count, w.n_above,
-                                                                 w.k_sel, w.thr_bin, topn, 0.0f, dec, w.sel, w.pre_cnt,
-                                                                 w.pre_box, w.pre_score, w.pre_label);
+        const int ept = topn <= 4 * kSelectThreads ? 4 : (topn <= 8 * kSelectThreads ? 8 : 16);
+        const size_t smem = select_smem_bytes(ept);
+#define PAA_SELECT(E)                                                                                         \
+    do {                                                                                                      \
+        static bool attr_set = false;                                                                         \
+        if (!attr_set && smem > 48 * 1024) {                                                                  \
+            PAA_CUDA_CHECK(cudaFuncSetAttribute(post_select_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                                (int)select_smem_bytes(E)));                                  \
+            attr_set = true;                                                                                  \
+        }                                                                                                     \
+        post_select_kernel<E><<<N * L, kSelectThreads, smem, stream>>>(geo, sizes, w.cand, w.bnd, w.bnd_count, w.n_above, \
+                                                                 w.k_sel, w.thr_bin, topn, 0.0f, dec, w.sel, w.pre_cnt, \
+                                                                 w.pre_box, w.pre_score, w.pre_label);                  \
+    } while (0)
+        if (ept == 4) PAA_SELECT(4);
+        else if (ept == 8) PAA_SELECT(8);
+        else PAA_SELECT(16);
+#undef PAA_SELECT
     }
     PAA_LAUNCH_CHECK("post_select_kernel");
     if (a->dbg_pre_boxes || a->dbg_pre_scores || a->dbg_pre_labels || a->dbg_pre_count) {
@@ -1285,8 +1539,7 @@ int run_postprocess(const Geometry& geo, const PaaPostArgs* a, cudaStream_t stre
     if (!a->skip_nms) {
         {
             KernelTimer t(PAA_KERNEL_POST_NMS_MASK, stream);
-            dim3 grid(nbw, N);
-            post_nms_mask_kernel<<<grid, 64, 0, stream>>>(capN, nbw, a->nms_thresh, w.total, w.s_box, w.s_label,
+            post_nms_mask_kernel<<<nms_mask_grid(capN, N), kMaskWarps * 32, 0, stream>>>(capN, nbw, a->nms_thresh, w.total, w.s_box, w.s_label,
                                                           w.mask);
         }
         PAA_LAUNCH_CHECK("post_nms_mask_kernel");
@@ -1305,7 +1558,7 @@ int run_postprocess(const Geometry& geo, const PaaPostArgs* a, cudaStream_t stre
         int* rpos = w.rank_by_pos;
         post_finish_kernel<<<N, kFinishThreads, 0, stream>>>(
             L, topn, a->detections_per_img, a->skip_nms, w.pre_cnt, w.total, w.pre_box, w.pre_score, w.pre_label,
-            w.s_pos, w.keep_sorted, flag, rpos, a->out_boxes, a->out_scores,
+            w.s_pos, w.s_score, w.keep_sorted, flag, rpos, a->out_boxes, a->out_scores,
             reinterpret_cast<long long*>(a->out_labels), a->out_count, w.out_rank, a->dbg_nms_keep);
     }
     PAA_LAUNCH_CHECK("post_finish_kernel");
@@ -1414,8 +1667,7 @@ int run_ml_nms(const float* boxes, const float* scores, const float* labels, int
     PAA_LAUNCH_CHECK("post_rank_kernel");
     post_segments_kernel<<<1, 1024, 0, stream>>>(n, w.total, w.s_label, w.seg_start, w.n_seg);
     PAA_LAUNCH_CHECK("post_segments_kernel");
-    dim3 mgrid(nbw, 1);
-    post_nms_mask_kernel<<<mgrid, 64, 0, stream>>>(n, nbw, thresh, w.total, w.s_box, w.s_label, w.mask);
+    post_nms_mask_kernel<<<nms_mask_grid(n, 1), kMaskWarps * 32, 0, stream>>>(n, nbw, thresh, w.total, w.s_box, w.s_label, w.mask);
     PAA_LAUNCH_CHECK("post_nms_mask_kernel");
     post_nms_scan_kernel<<<(n + kScanWarps - 1) / kScanWarps, kScanWarps * 32, 0, stream>>>(
         n, nbw, n, 1, w.seg_start, w.n_seg, w.mask, w.keep_sorted);
@@ -1762,8 +2014,7 @@ int run_box_vote(const float* boxes, const float* scores, const float* labels, i
     post_segments_kernel<<<1, 1024, 0, stream>>>(n, w.nms.total, w.nms.s_label, w.nms.seg_start, w.nms.n_seg);
     PAA_LAUNCH_CHECK("post_segments_kernel");
     if (mode == 0) {
-        dim3 mgrid(nbw, 1);
-        post_nms_mask_kernel<<<mgrid, 64, 0, stream>>>(n, nbw, nms_thresh, w.nms.total, w.nms.s_box, w.nms.s_label,
+        post_nms_mask_kernel<<<nms_mask_grid(n, 1), kMaskWarps * 32, 0, stream>>>(n, nbw, nms_thresh, w.nms.total, w.nms.s_box, w.nms.s_label,
                                                        w.nms.mask);
         PAA_LAUNCH_CHECK("post_nms_mask_kernel");
         post_nms_scan_kernel<<<(n + kScanWarps - 1) / kScanWarps, kScanWarps * 32, 0, stream>>>(

@@ -19,6 +19,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 TRACE_LIB = os.path.join(ROOT, "paa_b200", "libpaa_b200_trace.so")
 NAMES = ["prep_step", "iou_match", "match_score", "select_gmm", "bulk_focal", "positive_list"]
+POST_FIRST = 8
+POST_NAMES = ["post_candidates", "post_threshold", "post_filter", "post_select", "post_rank", "post_group",
+              "post_class_rank", "post_segments", "post_nms_mask", "post_nms_scan", "post_finish", "post_vote"]
+SLOTS = 24
 
 
 def build_trace_lib():
@@ -34,6 +38,7 @@ def main():
     ap.add_argument("--gt", type=int, nargs=2, default=[1, 100])
     ap.add_argument("--replays", type=int, default=20)
     ap.add_argument("--build-only", action="store_true")
+    ap.add_argument("--post", action="store_true", help="trace the NMS + voting step (C4 shapes) instead of the loss step")
     args = ap.parse_args()
     if args.build_only:
         print(build_trace_lib())
@@ -53,20 +58,36 @@ def main():
     raw = ctypes.CDLL(TRACE_LIB)
     raw.paa_trace_set.argtypes = [ctypes.c_void_p]
     raw.paa_trace_set.restype = ctypes.c_int
-    b = synthetic.make_batch(seed=2000, num_images=args.images, image_hw=(800, 1333), gt_per_image=tuple(args.gt))
-    cfg = paa_b200.default_cfg()
-    ev = paa_b200.make_paa_loss_evaluator(cfg, paa_b200.BoxCoder(cfg))
-    cls, reg, iou, targets, anchors = to_device_inputs(b)
-    trace = torch.zeros(8 * 4, dtype=torch.int64, device="cuda")
+    trace = torch.zeros(SLOTS * 4, dtype=torch.int64, device="cuda")
     assert raw.paa_trace_set(ctypes.c_void_p(trace.data_ptr())) == 0
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    cfg = paa_b200.default_cfg()
+    if args.post:
+        from paa_b200.structures import BoxList
+        b = synthetic.make_inference_batch(seed=4000, num_images=args.images, image_hw=(800, 1333), candidates_per_level=4000)
+        pp = paa_b200.make_paa_postprocessor(cfg, paa_b200.BoxCoder(cfg))
+        cls = [t.cuda() for t in b.box_cls]
+        reg = [t.cuda() for t in b.box_regression]
+        iou = [t.cuda() for t in b.iou_pred]
+        anc = [a.cuda() for a in b.anchors]
+        anchors = [[BoxList(a, b.image_sizes[i]) for a in anc] for i in range(args.images)]
+        step = lambda: pp.run_device(cls, reg, iou, anchors)
+        names, first = POST_NAMES, POST_FIRST
+        what = "%d images (C4 shapes)" % args.images
+    else:
+        b = synthetic.make_batch(seed=2000, num_images=args.images, image_hw=(800, 1333), gt_per_image=tuple(args.gt))
+        ev = paa_b200.make_paa_loss_evaluator(cfg, paa_b200.BoxCoder(cfg))
+        cls, reg, iou, targets, anchors = to_device_inputs(b)
+        step = lambda: ev.forward_backward(cls, reg, iou, targets, anchors)
+        names, first = NAMES, 0
+        what = "%d images, %d GT" % (args.images, sum(len(x) for x in b.gt_boxes))
     for _ in range(3):
-        ev.forward_backward(cls, reg, iou, targets, anchors)
+        step()
     torch.cuda.synchronize()
     g = torch.cuda.CUDAGraph()
     with torch.cuda.graph(g):
-        ev.forward_backward(cls, reg, iou, targets, anchors)
-    init = torch.zeros(8, 4, dtype=torch.int64)
+        step()
+    init = torch.zeros(SLOTS, 4, dtype=torch.int64)
     init[:, 0] = init[:, 1] = (1 << 62)
     init = init.reshape(-1).cuda()
     rows = []
@@ -76,17 +97,23 @@ def main():
         torch.cuda.synchronize()
         g.replay()
         torch.cuda.synchronize()
-        t = trace.cpu().numpy().reshape(8, 4)[:len(NAMES)].astype(np.float64)
-        t0 = t[0, 0]
-        rows.append((t - t0) / 1000.0)
-    med = np.median(np.stack(rows), axis=0)
-    print("%d images, %d GT; us relative to the first block of prep_step_kernel (median of %d graph replays, L2 flushed)"
-          % (args.images, sum(len(x) for x in b.gt_boxes), args.replays))
+        t = trace.cpu().numpy().reshape(SLOTS, 4)[first:first + len(names)].astype(np.float64)
+        ran = t[:, 2] > 0
+        t0 = t[ran, 0].min()
+        rows.append(np.where(ran[:, None], (t - t0) / 1000.0, np.nan))
+    med = np.nanmedian(np.stack(rows), axis=0)
+    print("%s; us relative to the first block of the step's first kernel (median of %d graph replays, L2 flushed)"
+          % (what, args.replays))
     print("%-16s %10s %12s %12s %10s %8s" % ("kernel", "first start", "first waited", "last start", "last end", "span"))
-    for i, nm in enumerate(NAMES):
+    end = 0.0
+    for i, nm in enumerate(names):
         s0, w, e, ls = med[i]
-        print("%-16s %10.1f %12.1f %12.1f %10.1f %8.1f" % (nm, s0, w if w < 1e9 else float("nan"), ls, e, e - (w if w < 1e9 else s0)))
-    print("step: %.1f us" % med[len(NAMES) - 1, 2])
+        if not np.isfinite(e):
+            continue
+        w = w if w < 1e9 else float("nan")
+        print("%-16s %10.1f %12.1f %12.1f %10.1f %8.1f" % (nm, s0, w, ls, e, e - (w if np.isfinite(w) else s0)))
+        end = max(end, e)
+    print("step: %.1f us" % end)
 
 
 if __name__ == "__main__":

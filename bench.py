@@ -120,6 +120,9 @@ def parse_args(argv=None):
     ap.add_argument("--config", default=None, choices=sorted(CONFIGS))
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
     ap.add_argument("--images-per-gpu", type=int, default=None, help="override the config's per-GPU share")
+    ap.add_argument("--layout", default="nchw", choices=["nchw", "nhwc"],
+                    help="memory layout of the head tensors: nchw = what the reference's heads produce (default); "
+                         "nhwc = torch.channels_last heads, consumed in place")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-post", action="store_true", help="loss metric: skip the NMS+voting object")
@@ -185,6 +188,8 @@ def workload_config(args, scaling, per_gpu, total, world):
            "split": ("BASELINE's split: the global batch of %d sharded over the ranks" % c["images"]) if scaling == "strong"
            else "weak scaling: every rank runs a whole %d-image batch of its own" % per_gpu,
            "l2": "flushed between timed steps (256 MiB write, untimed)",
+           "head_layout": "NCHW (contiguous, what the reference's heads produce)" if LAYOUT == "nchw"
+           else "NHWC (torch.channels_last heads, consumed in place)",
            "collective": ("none (one rank)" if world == 1 else
                           "nvlink-peer: 16 bytes per rank stored into every peer's symmetric-memory buffer by the last "
                           "block of select_gmm_kernel, read by norm_wait_kernel (no NCCL call on the data path)")
@@ -507,6 +512,29 @@ def roofline_report(kernel_table, per_kernel, A, C, n_img, step_ms, step_bytes_p
 
 
 # ------------------------------------------------------------------------------------------------
+# head layout of the run (--layout)
+# ------------------------------------------------------------------------------------------------
+LAYOUT = "nchw"
+
+
+def head_format():
+    return torch.channels_last if LAYOUT == "nhwc" else torch.contiguous_format
+
+
+def head_bytes_in_order(t):
+    """The values of a logical [N, C, H, W] head tensor in the order the run's layout keeps them in memory."""
+    return t.permute(0, 2, 3, 1).reshape(-1) if LAYOUT == "nhwc" else t.reshape(-1)
+
+
+def head_view(flat, shape):
+    """A logical [N, C, H, W] view of a flat buffer holding the tensor in the run's layout."""
+    if LAYOUT == "nhwc":
+        n, c, h, w = shape
+        return flat.view(n, h, w, c).permute(0, 3, 1, 2)
+    return flat.view(shape)
+
+
+# ------------------------------------------------------------------------------------------------
 # assign + loss
 # ------------------------------------------------------------------------------------------------
 class LossRun(object):
@@ -523,7 +551,7 @@ class LossRun(object):
         cfg = paa_b200.default_cfg()
         self.ev = paa_b200.make_paa_loss_evaluator(cfg, paa_b200.BoxCoder(cfg))
         self.lib = _lib.load()
-        pin = lambda ts: [t.contiguous().pin_memory() for t in ts]       # noqa: E731
+        pin = lambda ts: [t.contiguous(memory_format=head_format()).pin_memory() for t in ts]       # noqa: E731
         self.h_cls, self.h_reg, self.h_iou = pin(batch.box_cls), pin(batch.box_regression), pin(batch.iou_pred)
         self.h_gtb = [t.pin_memory() for t in batch.gt_boxes]
         self.h_gtl = [t.pin_memory() for t in batch.gt_labels]
@@ -643,7 +671,7 @@ class LossRun(object):
         h_pack = torch.empty(sum(sizes), dtype=torch.float32).pin_memory()
         o = 0
         for t, sz in zip(heads_h, sizes):
-            h_pack[o:o + sz].copy_(t.reshape(-1))
+            h_pack[o:o + sz].copy_(head_bytes_in_order(t))
             o += sz
         gt_counts = [int(t.shape[0]) for t in self.h_gtb]
         h_boxes = torch.cat(self.h_gtb, 0).contiguous().pin_memory()
@@ -674,7 +702,7 @@ class LossRun(object):
             main.wait_event(sl["copied"])
             views, o = [], 0
             for t, sz in zip(heads_h, sizes):
-                views.append(sl["pack"][o:o + sz].view(t.shape).requires_grad_(True))
+                views.append(head_view(sl["pack"][o:o + sz], t.shape).requires_grad_(True))
                 o += sz
             cls, reg, iou = views[:L], views[L:2 * L], views[2 * L:]
             tg = self.targets_from(list(sl["boxes"].split(gt_counts)), list(sl["labels"].split(gt_counts)))
@@ -814,9 +842,9 @@ class PostRun(object):
         cfg = paa_b200.default_cfg()
         self.pp = paa_b200.make_paa_postprocessor(cfg, paa_b200.BoxCoder(cfg))
         self.lib = _lib.load()
-        self.cls = [t.to(dev) for t in batch.box_cls]
-        self.reg = [t.to(dev) for t in batch.box_regression]
-        self.iou = [t.to(dev) for t in batch.iou_pred]
+        self.cls = [t.to(dev).contiguous(memory_format=head_format()) for t in batch.box_cls]
+        self.reg = [t.to(dev).contiguous(memory_format=head_format()) for t in batch.box_regression]
+        self.iou = [t.to(dev).contiguous(memory_format=head_format()) for t in batch.iou_pred]
         anc = [a.to(dev) for a in batch.anchors]
         self.anchors = [[BoxList(a, batch.image_sizes[i]) for a in anc] for i in range(self.n_img)]
         for _ in range(3):
@@ -844,7 +872,7 @@ class PostRun(object):
         h_pack = torch.empty(sum(sizes), dtype=torch.float32).pin_memory()
         o = 0
         for t, sz in zip(heads_h, sizes):
-            h_pack[o:o + sz].copy_(t.reshape(-1))
+            h_pack[o:o + sz].copy_(head_bytes_in_order(t))
             o += sz
         copy_stream = torch.cuda.Stream()
         slots = [dict(pack=torch.empty_like(h_pack, device=dev), copied=torch.cuda.Event(), free=torch.cuda.Event())
@@ -868,7 +896,7 @@ class PostRun(object):
             main.wait_event(sl["copied"])
             views, o = [], 0
             for t, sz in zip(heads_h, sizes):
-                views.append(sl["pack"][o:o + sz].view(t.shape))
+                views.append(head_view(sl["pack"][o:o + sz], t.shape))
                 o += sz
             out = self.pp(views[:L], views[L:2 * L], views[2 * L:], self.anchors)
             host = [b.to(cpu) for b in out]
@@ -968,7 +996,9 @@ def run_ours(args):
 
 
 def main():
+    global LAYOUT
     args = parse_args()
+    LAYOUT = args.layout
     if args.impl == "reference":
         return run_reference_arm(args)
     return run_ours(args)

@@ -26,7 +26,10 @@
  * never allocates device memory -- the caller passes a workspace of *_workspace_bytes(); return
  * value 0 = OK, >0 = cudaError_t, <0 = PAA_ERR_*; paa_last_error() gives a thread-local message.
  * One caller thread per (device, stream); calls on different streams must use different
- * workspaces.  All floating tensors are float32, head tensors are NCHW-contiguous.
+ * workspaces.  All floating tensors are float32.  Head tensors (and their gradients) are dense in one of two
+ * memory layouts, the same for every tensor of a call (`head_layout`): NCHW-contiguous as PAAHead.forward produces
+ * them (paa.py:90-108), or channels-last (NHWC: what a `torch.channels_last` / AMP pipeline hands over) -- in memory
+ * the [N, H*W*a, ch] tensor that permute_and_flatten (rpn/utils.py:10-14) would build, consumed in place.
  */
 #ifndef PAA_B200_H_
 #define PAA_B200_H_
@@ -38,7 +41,7 @@
 extern "C" {
 #endif
 
-#define PAA_ABI_VERSION 7
+#define PAA_ABI_VERSION 8
 #define PAA_MAX_LEVELS 8
 #define PAA_MAX_IMAGES 256      /* images per call (per rank) */
 #define PAA_MAX_CANDIDATES 128  /* num_levels * topk must not exceed this */
@@ -49,6 +52,9 @@ extern "C" {
 #define PAA_ERR_WORKSPACE    (-2)
 #define PAA_ERR_EMPTY_TARGET (-3)   /* an image without GT: matcher.py:53-58 raises ValueError */
 #define PAA_ERR_UNSUPPORTED  (-4)
+
+#define PAA_LAYOUT_NCHW 0       /* head tensors [N, a*ch, H, W], W fastest */
+#define PAA_LAYOUT_NHWC 1       /* same logical shape, channels fastest (torch.channels_last) */
 
 /* One FPN level of the head outputs (paa.py:90-108) and its anchors
  * (anchor_generator.py:112-125).  hw = H*W; with anchors_per_loc = a the level holds hw*a anchors,
@@ -155,6 +161,9 @@ typedef struct PaaLossArgs {
     const int32_t* gt_offsets_dev;
     int32_t gt_capacity;
     int32_t gt_per_image_capacity;
+    int32_t head_layout;          /* PAA_LAYOUT_NCHW (0) or PAA_LAYOUT_NHWC: layout of every box_cls / box_regression /
+                                     iou_pred / grad_* tensor of the call */
+    int32_t reserved4;
 } PaaLossArgs;
 
 typedef struct PaaPostArgs {
@@ -192,6 +201,7 @@ typedef struct PaaPostArgs {
     int32_t box_decode;
     float decode_weights[4];      /* PAA_DECODE_LEGACY: wx, wy, ww, wh */
     float decode_clip;            /* PAA_DECODE_LEGACY: bbox_xform_clip (log(1000/16)) */
+    int32_t head_layout;          /* PAA_LAYOUT_NCHW (0) or PAA_LAYOUT_NHWC */
 } PaaPostArgs;
 #define PAA_LOSS_PAA  0
 #define PAA_LOSS_ATSS 1

@@ -15,8 +15,9 @@ MAX_IMAGES = 256
 MAX_PEERS = 16
 PEER_BUFFER_DOUBLES = 256
 MAX_CANDIDATES = 128
-ABI_VERSION = 7
+ABI_VERSION = 8
 
+LAYOUT_NCHW, LAYOUT_NHWC = 0, 1
 ERR_BAD_ARGUMENT, ERR_WORKSPACE, ERR_EMPTY_TARGET, ERR_UNSUPPORTED = -1, -2, -3, -4
 
 _fp = C.POINTER(C.c_float)
@@ -50,7 +51,8 @@ class PaaLossArgs(C.Structure):
                 ("fcos_center_radius", C.c_float), ("fcos_iou_loss_type", C.c_int32),
                 ("fcos_norm_reg_targets", C.c_int32), ("atss_positive_type", C.c_int32),
                 ("peer_timeout_s", C.c_float), ("reserved3", C.c_int32), ("peer_status", C.c_void_p),
-                ("gt_offsets_dev", C.c_void_p), ("gt_capacity", C.c_int32), ("gt_per_image_capacity", C.c_int32)]
+                ("gt_offsets_dev", C.c_void_p), ("gt_capacity", C.c_int32), ("gt_per_image_capacity", C.c_int32),
+                ("head_layout", C.c_int32), ("reserved4", C.c_int32)]
 
 
 class PaaPostArgs(C.Structure):
@@ -67,7 +69,8 @@ class PaaPostArgs(C.Structure):
                 ("dbg_pre_boxes", C.c_void_p), ("dbg_pre_scores", C.c_void_p),
                 ("dbg_pre_labels", C.c_void_p), ("dbg_pre_count", C.c_void_p),
                 ("dbg_nms_keep", C.c_void_p),
-                ("box_decode", C.c_int32), ("decode_weights", C.c_float * 4), ("decode_clip", C.c_float)]
+                ("box_decode", C.c_int32), ("decode_weights", C.c_float * 4), ("decode_clip", C.c_float),
+                ("head_layout", C.c_int32)]
 
 DECODE_ATSS_BOX, DECODE_LEGACY, DECODE_LTRB = 0, 1, 2
 LOSS_PAA, LOSS_ATSS, LOSS_RETINANET, LOSS_FCOS = 0, 1, 2, 3

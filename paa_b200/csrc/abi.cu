@@ -45,7 +45,11 @@ static int tiles_of(int n_anchor) { return (n_anchor + PAA_TILE - 1) / PAA_TILE;
 // Validates the caller's description of the head tensors and builds the kernel-side view.
 static int build_geometry(int num_images, int num_levels, int num_classes, int anchors_per_loc,
                           long long anchor_image_stride, const PaaLevel* levels, bool need_iou,
-                          Geometry* geo) {
+                          int head_layout, Geometry* geo) {
+    if (head_layout != PAA_LAYOUT_NCHW && head_layout != PAA_LAYOUT_NHWC) {
+        set_error("head_layout=%d (PAA_LAYOUT_NCHW or PAA_LAYOUT_NHWC)", head_layout);
+        return PAA_ERR_BAD_ARGUMENT;
+    }
     if (num_images < 1 || num_images > PAA_MAX_IMAGES) {
         set_error("num_images=%d outside [1, %d]", num_images, PAA_MAX_IMAGES);
         return PAA_ERR_BAD_ARGUMENT;
@@ -64,6 +68,7 @@ static int build_geometry(int num_images, int num_levels, int num_classes, int a
     geo->C = num_classes;
     geo->apl = anchors_per_loc;
     geo->anchor_image_stride = anchor_image_stride;
+    geo->nhwc = head_layout == PAA_LAYOUT_NHWC ? 1 : 0;
     int a_off = 0, t_off = 0;
     for (int l = 0; l < num_levels; ++l) {
         const PaaLevel& s = levels[l];
@@ -112,7 +117,7 @@ static int plan_loss(const PaaLossArgs* a, LossPlan* p) {
         return PAA_ERR_BAD_ARGUMENT;
     }
     int rc = build_geometry(a->num_images, a->num_levels, a->num_classes, a->anchors_per_loc,
-                            a->anchor_image_stride, a->levels, a->use_iou_pred != 0, &p->geo);
+                            a->anchor_image_stride, a->levels, a->use_iou_pred != 0, a->head_layout, &p->geo);
     if (rc) return rc;
     if (a->topk < 1 || a->topk > 32 || a->num_levels * a->topk > PAA_MAX_CANDIDATES) {
         set_error("topk=%d unsupported (1..32, num_levels*topk <= %d)", a->topk, PAA_MAX_CANDIDATES);
@@ -477,7 +482,7 @@ int paa_postprocess(const PaaPostArgs* args, void* stream) {
     }
     Geometry geo;
     int rc = build_geometry(args->num_images, args->num_levels, args->num_classes, args->anchors_per_loc,
-                            args->anchor_image_stride, args->levels, false, &geo);
+                            args->anchor_image_stride, args->levels, false, args->head_layout, &geo);
     if (rc) return rc;
     return run_postprocess(geo, args, static_cast<cudaStream_t>(stream));
 }

@@ -380,6 +380,13 @@ __device__ __forceinline__ void add_terms(float4& acc, float4 x, float gamma, bo
     acc.w += neg_term_only(x.w, gamma, g2);
 }
 
+// kNhwc: the channels-last instantiation.  An anchor's C logits are contiguous there, a warp's 32 anchors one
+// contiguous run of 32*C floats: the class sums are a flat, fully coalesced stream (512 bytes per warp instruction,
+// four in flight per lane) whose per-float4 partial sums meet per anchor in the warp's slice of shared memory -- no
+// block barrier, no strided class rows.
+constexpr int kFlatQ = 20;                            // float4 per anchor the flat path handles (C <= 80, C % 4 == 0)
+
+template <bool kNhwc>
 __global__ void __launch_bounds__(PAA_TILE)
 match_score_kernel(const Geometry geo, const GtOffsets* __restrict__ gop, const float* __restrict__ gt_boxes,
                    const int64_t* __restrict__ gt_labels, const unsigned* __restrict__ gtmax,
@@ -396,7 +403,8 @@ match_score_kernel(const Geometry geo, const GtOffsets* __restrict__ gop, const 
     __shared__ int s_nlq;
     __shared__ unsigned s_mask[4];
     __shared__ unsigned s_need[PAA_TILE / PAA_WARP];
-    __shared__ __align__(16) float s_part[kSumGroups][PAA_TILE];
+    __shared__ __align__(16) float s_part[kNhwc ? 1 : kSumGroups][PAA_TILE];
+    __shared__ float s_flat[kNhwc ? PAA_TILE * (kFlatQ + 1) : 1];
     if (threadIdx.x < 4) s_mask[threadIdx.x] = 0u;
 
     const int n = blockIdx.x / geo.tiles_per_image;
@@ -472,9 +480,44 @@ match_score_kernel(const Geometry geo, const GtOffsets* __restrict__ gop, const 
 
     // ---- class sums of the tile's IoU-positive anchors --------------------------------------------
     const bool g2 = (sc.gamma == 2.0f);
-    const bool vec = geo.apl == 1 && (lv.hw & 3) == 0 && (reinterpret_cast<uintptr_t>(lv.cls) & 15u) == 0;
+    const bool vec = !kNhwc && geo.apl == 1 && (lv.hw & 3) == 0 && (reinterpret_cast<uintptr_t>(lv.cls) & 15u) == 0;
+    const bool flat_rows = kNhwc && (C & 3) == 0 && C <= 4 * kFlatQ && (reinterpret_cast<uintptr_t>(lv.cls) & 15u) == 0;
     float negsum = 0.0f;
-    if (vec) {
+    if (flat_rows) {
+        const int q = C >> 2;                                             // float4 per anchor
+        const unsigned magic = (65536u + (unsigned)q - 1u) / (unsigned)q; // f / q for f < 32 * q <= 640
+        float* wbuf = s_flat + warp * PAA_WARP * (kFlatQ + 1);
+        if (pos_mask != 0u) {                                             // warp-uniform
+            const float4* p = reinterpret_cast<const float4*>(
+                lv.cls + ((size_t)n * lv.n_anchor + first + PAA_WARP * warp) * C);
+            for (int k0 = 0; k0 < q; k0 += 4) {
+                float4 x[4];
+                int slot[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const unsigned f = (unsigned)lane + 32u * (unsigned)(k0 + j);
+                    const unsigned an = (f * magic) >> 16;                 // anchor of the warp this float4 belongs to
+                    slot[j] = -1;
+                    if (k0 + j < q && ((pos_mask >> an) & 1u)) {
+                        x[j] = __ldg(p + f);
+                        slot[j] = (int)(an * (kFlatQ + 1) + (f - an * (unsigned)q));
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (slot[j] >= 0) {
+                        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                        add_terms(acc, x[j], sc.gamma, g2);
+                        wbuf[slot[j]] = (acc.x + acc.y) + (acc.z + acc.w);
+                    }
+            }
+            __syncwarp();
+            if (positive) {
+                const float* row = wbuf + lane * (kFlatQ + 1);
+                for (int t = 0; t < q; ++t) negsum += row[t];
+            }
+        }
+    } else if (vec) {
         const int col = lane, grp = warp;                                 // anchors 4*col .. 4*col+3 of the tile
         const unsigned need = (s_need[col >> 3] >> ((col & 7) * 4)) & 0xfu;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -500,8 +543,8 @@ match_score_kernel(const Geometry geo, const GtOffsets* __restrict__ gop, const 
 #pragma unroll
         for (int g = 1; g < kSumGroups; ++g) negsum += s_part[g][threadIdx.x];
     } else if (positive) {
-        const float* p = lv.cls + head_offset(n, i, 0, C, geo.apl, lv.hw);
-        const unsigned st = (unsigned)lv.hw;
+        const float* p = lv.cls + head_offset(geo, lv, n, i, 0, C);
+        const size_t st = head_cstride(geo, lv);
         int c0 = 0;
         for (; c0 + 8 <= C; c0 += 8) {
             float x[8];
@@ -517,13 +560,12 @@ match_score_kernel(const Geometry geo, const GtOffsets* __restrict__ gop, const 
     if (positive) {
         // sum_c focal(x_c | label): every class as a negative, then the labelled class's negative term swapped
         // for the positive one (accurate path for that single term)
-        const float xl = __ldg(lv.cls + head_offset(n, i, label - 1, C, geo.apl, lv.hw));
+        const float xl = __ldg(lv.cls + head_offset(geo, lv, n, i, label - 1, C));
         float tp, gp;
         focal_positive(xl, sigmoid_parts(xl), sc.gamma, g2, sc.alpha, &tp, &gp);
         const float fsum = fmaf(1.0f - sc.alpha, negsum - neg_term_only(xl, sc.gamma, g2), tp);
-        const float* rp = lv.reg + head_offset(n, i, 0, 4, geo.apl, lv.hw);
-        const float4 d = make_float4(__ldg(rp), __ldg(rp + lv.hw), __ldg(rp + 2 * (size_t)lv.hw),
-                                     __ldg(rp + 3 * (size_t)lv.hw));
+        const float* rp = lv.reg + head_offset(geo, lv, n, i, 0, 4);
+        const float4 d = load_channels4(rp, head_cstride(geo, lv));
         const AnchorFrame f = anchor_frame(a);
         const float4 pred = decode_box(d, f);
         const float4 gt = ldg4(gt_boxes + (size_t)(gbase + m) * 4);
@@ -553,9 +595,14 @@ int launch_match_score(const Geometry& geo, const float* gt_boxes,
     int grid = geo.num_images * geo.tiles_per_image;
     KernelTimer timer(PAA_KERNEL_MATCH_SCORE, stream);
     const GtOffsets* gop = ws.go;
-    PAA_PDL_LAUNCH(match_score_kernel, grid, PAA_TILE, stream, geo, gop, gt_boxes, gt_labels, ws.gtmax,
-                   reinterpret_cast<const unsigned long long*>(ws.best), sc, ws.matched, ws.score, ws.paa_label,
-                   ws.tile_gtmask, ws.seg_count, ws.seg_pool, teacher_score, dbg);
+    if (geo.nhwc)
+        PAA_PDL_LAUNCH(match_score_kernel<true>, grid, PAA_TILE, stream, geo, gop, gt_boxes, gt_labels, ws.gtmax,
+                       reinterpret_cast<const unsigned long long*>(ws.best), sc, ws.matched, ws.score, ws.paa_label,
+                       ws.tile_gtmask, ws.seg_count, ws.seg_pool, teacher_score, dbg);
+    else
+        PAA_PDL_LAUNCH(match_score_kernel<false>, grid, PAA_TILE, stream, geo, gop, gt_boxes, gt_labels, ws.gtmax,
+                       reinterpret_cast<const unsigned long long*>(ws.best), sc, ws.matched, ws.score, ws.paa_label,
+                       ws.tile_gtmask, ws.seg_count, ws.seg_pool, teacher_score, dbg);
     return 0;
 }
 
@@ -1060,9 +1107,8 @@ select_gmm_kernel(const Geometry geo, const GtOffsets* __restrict__ gop, const i
                 const LevelView& lv = geo.lv[l];
                 const int i = aidx[k] - lv.a_off;
                 pa[k] = ldg4(lv.anchors + (size_t)n * geo.anchor_image_stride + (size_t)i * 4);
-                const float* rp = lv.reg + head_offset(n, i, 0, 4, geo.apl, lv.hw);
-                pd[k] = make_float4(__ldg(rp), __ldg(rp + lv.hw), __ldg(rp + 2 * (size_t)lv.hw),
-                                    __ldg(rp + 3 * (size_t)lv.hw));
+                const float* rp = lv.reg + head_offset(geo, lv, n, i, 0, 4);
+                pd[k] = load_channels4(rp, head_cstride(geo, lv));
             }
         }
     }

@@ -530,7 +530,7 @@ positive_terms_kernel(const Geometry geo, const GtOffsets* __restrict__ gop, con
             cx.oma = 1.0f - sc.alpha;
             cx.kneg = cx.oma * cx.gs.cls;
             // classification: swap the negative-class result of the labelled class for the positive one
-            const size_t off = head_offset(n, i, label - 1, geo.C, geo.apl, lv.hw);
+            const size_t off = head_offset(geo, lv, n, i, label - 1, geo.C);
             const float xp = __ldg(lv.cls + off);
             const SigmoidParts sp = sigmoid_parts(xp);
             float tn_acc = 0.f, g_unused;
@@ -543,10 +543,9 @@ positive_terms_kernel(const Geometry geo, const GtOffsets* __restrict__ gop, con
             fix_sum += tp - cx.oma * tn_acc;
             if (kGrads && lv.g_cls) lv.g_cls[off] = gp * cx.gs.cls;
             // box regression + IoU prediction
-            const float* rp = lv.reg + head_offset(n, i, 0, 4, geo.apl, lv.hw);
-            const float4 d = make_float4(__ldg(rp), __ldg(rp + lv.hw), __ldg(rp + 2 * (size_t)lv.hw),
-                                         __ldg(rp + 3 * (size_t)lv.hw));
-            const float xi = sc.use_iou_pred ? __ldg(lv.iou + head_offset(n, i, 0, 1, geo.apl, lv.hw)) : 0.f;
+            const float* rp = lv.reg + head_offset(geo, lv, n, i, 0, 4);
+            const float4 d = load_channels4(rp, head_cstride(geo, lv));
+            const float xi = sc.use_iou_pred ? __ldg(lv.iou + head_offset(geo, lv, n, i, 0, 1)) : 0.f;
             if (sc.flavour == PAA_LOSS_RETINANET)
                 positive_smooth_l1(geo, lv, go, gt_boxes, sc, cx, n, i, matched[flat], d, &reg_sum, &gd);
             else if (sc.flavour == PAA_LOSS_FCOS)
@@ -558,13 +557,10 @@ positive_terms_kernel(const Geometry geo, const GtOffsets* __restrict__ gop, con
         }
         if (kGrads && valid && (zero_fill || label > 0)) {
             if (lv.g_reg) {
-                float* gr = lv.g_reg + head_offset(n, i, 0, 4, geo.apl, lv.hw);
-                gr[0] = gd.x;
-                gr[lv.hw] = gd.y;
-                gr[2 * (size_t)lv.hw] = gd.z;
-                gr[3 * (size_t)lv.hw] = gd.w;
+                float* gr = lv.g_reg + head_offset(geo, lv, n, i, 0, 4);
+                store_channels4(gr, head_cstride(geo, lv), make_float4(gd.x, gd.y, gd.z, gd.w));
             }
-            if (lv.g_iou) lv.g_iou[head_offset(n, i, 0, 1, geo.apl, lv.hw)] = gi;
+            if (lv.g_iou) lv.g_iou[head_offset(geo, lv, n, i, 0, 1)] = gi;
         }
         if (may_ignore) {
             // Ignored anchors (RetinaNet, between the Matcher thresholds) when the bulk pass could not skip them
@@ -586,7 +582,7 @@ positive_terms_kernel(const Geometry geo, const GtOffsets* __restrict__ gop, con
             const int items = total * geo.C;
             for (int it = threadIdx.x; it < items; it += PAA_TILE) {
                 const int c = it / total, k = it - c * total;
-                const size_t off = head_offset(n, s_ign[k], c, geo.C, geo.apl, lv.hw);
+                const size_t off = head_offset(geo, lv, n, s_ign[k], c, geo.C);
                 float g_unused;
                 neg_term_grad<kG2>(__ldg(lv.cls + off), sc.gamma, 0.0f, &ign_sum, &g_unused);
                 if (kGrads && lv.g_cls) lv.g_cls[off] = 0.0f;
@@ -720,13 +716,10 @@ positive_list_kernel(const Geometry geo, const GtOffsets* __restrict__ gop, cons
             const LevelView& lv = geo.lv[l];
             const int i = a - lv.a_off;
             if (lv.g_reg) {
-                float* gr = lv.g_reg + head_offset(n, i, 0, 4, geo.apl, lv.hw);
-                gr[0] = 0.0f;
-                gr[lv.hw] = 0.0f;
-                gr[2 * (size_t)lv.hw] = 0.0f;
-                gr[3 * (size_t)lv.hw] = 0.0f;
+                float* gr = lv.g_reg + head_offset(geo, lv, n, i, 0, 4);
+                store_channels4(gr, head_cstride(geo, lv), make_float4(0.0f, 0.0f, 0.0f, 0.0f));
             }
-            if (lv.g_iou) lv.g_iou[head_offset(n, i, 0, 1, geo.apl, lv.hw)] = 0.0f;
+            if (lv.g_iou) lv.g_iou[head_offset(geo, lv, n, i, 0, 1)] = 0.0f;
         }
     }
     // (b) the positives
@@ -748,7 +741,7 @@ positive_list_kernel(const Geometry geo, const GtOffsets* __restrict__ gop, cons
         cx.oma = 1.0f - sc.alpha;
         cx.kneg = cx.oma * cx.gs.cls;
         // classification: swap the negative-class result of the labelled class for the positive one
-        const size_t off = head_offset(n, i, label - 1, geo.C, geo.apl, lv.hw);
+        const size_t off = head_offset(geo, lv, n, i, label - 1, geo.C);
         const float xp = __ldg(lv.cls + off);
         const SigmoidParts sp = sigmoid_parts(xp);
         float tn_acc = 0.f, g_unused;
@@ -758,22 +751,18 @@ positive_list_kernel(const Geometry geo, const GtOffsets* __restrict__ gop, cons
         fix_sum += tp - cx.oma * tn_acc;
         if (kGrads && lv.g_cls) lv.g_cls[off] = gp * cx.gs.cls;
         // box regression + IoU prediction
-        const float* rp = lv.reg + head_offset(n, i, 0, 4, geo.apl, lv.hw);
-        const float4 d = make_float4(__ldg(rp), __ldg(rp + lv.hw), __ldg(rp + 2 * (size_t)lv.hw),
-                                     __ldg(rp + 3 * (size_t)lv.hw));
-        const float xi = sc.use_iou_pred ? __ldg(lv.iou + head_offset(n, i, 0, 1, geo.apl, lv.hw)) : 0.f;
+        const float* rp = lv.reg + head_offset(geo, lv, n, i, 0, 4);
+        const float4 d = load_channels4(rp, head_cstride(geo, lv));
+        const float xi = sc.use_iou_pred ? __ldg(lv.iou + head_offset(geo, lv, n, i, 0, 1)) : 0.f;
         float4 gd = make_float4(0.f, 0.f, 0.f, 0.f);
         float gi_ = 0.f;
         positive_box_terms(geo, lv, go, gt_boxes, sc, cx, n, i, gi - go.v[n], d, xi, &reg_sum, &bce_sum, &gd, &gi_);
         if (kGrads) {
             if (lv.g_reg) {
-                float* gr = lv.g_reg + head_offset(n, i, 0, 4, geo.apl, lv.hw);
-                gr[0] = gd.x;
-                gr[lv.hw] = gd.y;
-                gr[2 * (size_t)lv.hw] = gd.z;
-                gr[3 * (size_t)lv.hw] = gd.w;
+                float* gr = lv.g_reg + head_offset(geo, lv, n, i, 0, 4);
+                store_channels4(gr, head_cstride(geo, lv), make_float4(gd.x, gd.y, gd.z, gd.w));
             }
-            if (lv.g_iou) lv.g_iou[head_offset(n, i, 0, 1, geo.apl, lv.hw)] = gi_;
+            if (lv.g_iou) lv.g_iou[head_offset(geo, lv, n, i, 0, 1)] = gi_;
         }
     }
     double a0 = warp_sum((double)fix_sum), a1 = warp_sum((double)reg_sum), a2 = warp_sum((double)bce_sum);
@@ -868,6 +857,7 @@ int launch_final_loss(const Geometry& geo, const float* gt_boxes,
                              (sc.flavour == PAA_LOSS_ATSS && sc.atss_type == PAA_ATSS_POSITIVE_IOU);
     bool bulk_ignores = has_ignored && geo.C >= 2;
     if (getenv("PAA_RETINA_PATCH")) bulk_ignores = false;      // test hook: force the per-anchor fallback
+    if (geo.nhwc) bulk_ignores = false;      // the ignore bits are in NCHW plane order: channels-last calls patch per anchor
     for (int l = 0; l < geo.num_levels && bulk_ignores; ++l)
         if (plan.count[l] >= (1ull << 32) || geo.lv[l].hw < 2 || geo.lv[l].hw == 4) bulk_ignores = false;
     plan.C = (unsigned)geo.C;
@@ -894,7 +884,7 @@ int launch_final_loss(const Geometry& geo, const float* gt_boxes,
     const int tile_grid = (tiles_total + tiles_per_block - 1) / tiles_per_block;
     // several anchors per location: an anchor's regression channels are hw floats apart from its neighbour's, so
     // zeroing them anchor by anchor scatters 4-byte writes; clear the tensors up front and write positives only
-    const bool zero_fill = geo.apl == 1;
+    const bool zero_fill = geo.apl == 1 || geo.nhwc;      // (channels-last: an anchor's channels are contiguous)
     if (write_grads && !zero_fill) {
         for (int l = 0; l < geo.num_levels; ++l) {
             const LevelView& lv = geo.lv[l];

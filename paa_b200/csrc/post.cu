@@ -255,12 +255,21 @@ post_candidates_kernel(const Geometry geo, const CandPlan plan, const float thr,
                     const LevelView& lv = geo.lv[l];
                     const unsigned hw = (unsigned)lv.hw;
                     unsigned chn, loc, a, c;
-                    divmod_small(q_e[t], hw, 1.0f / (float)hw, &chn, &loc);
-                    divmod_small(chn, (unsigned)geo.C, inv_c, &a, &c);
-                    entry = (loc * (unsigned)geo.apl + a) * (unsigned)geo.C + c;   // anchor * C + class
+                    size_t iou_at;
+                    if (geo.nhwc) {
+                        // channels-last: the element index inside the image's block IS anchor * C + class
+                        entry = q_e[t];
+                        divmod_small(entry, (unsigned)geo.C, inv_c, &a, &c);       // a = anchor of the level
+                        iou_at = (size_t)n * lv.n_anchor + a;
+                    } else {
+                        divmod_small(q_e[t], hw, 1.0f / (float)hw, &chn, &loc);
+                        divmod_small(chn, (unsigned)geo.C, inv_c, &a, &c);
+                        entry = (loc * (unsigned)geo.apl + a) * (unsigned)geo.C + c;   // anchor * C + class
+                        iou_at = ((size_t)n * geo.apl + a) * hw + loc;
+                    }
                     score = p;
                     if (lv.iou != nullptr) {
-                        const float xi = __ldg(lv.iou + ((size_t)n * geo.apl + a) * hw + loc);
+                        const float xi = __ldg(lv.iou + iou_at);
                         const float q = 1.0f / (1.0f + expf(-xi));             // inference.py:55
                         score = sqrtf(__fmul_rn(p, q));                        // inference.py:56
                     }
@@ -699,9 +708,8 @@ post_select_kernel(const Geometry geo, const ImageSizes sizes, const uint2* __re
             for (int j = b0; j < b1; ++j) t += s_idx[j] < my_idx ? 1 : 0;
             const int ai = (int)(my_idx / (unsigned)geo.C);
             const float4 a = ldg4(lv.anchors + (size_t)n * geo.anchor_image_stride + (size_t)ai * 4);
-            const float* rp = lv.reg + head_offset(n, ai, 0, 4, geo.apl, lv.hw);
-            const float4 d = make_float4(__ldg(rp), __ldg(rp + lv.hw), __ldg(rp + 2 * (size_t)lv.hw),
-                                         __ldg(rp + 3 * (size_t)lv.hw));
+            const float* rp = lv.reg + head_offset(geo, lv, n, ai, 0, 4);
+            const float4 d = load_channels4(rp, head_cstride(geo, lv));
             float4 box;
             if (dec.mode == PAA_DECODE_LEGACY) box = decode_box_legacy(d, a, dec.wx, dec.wy, dec.ww, dec.wh, dec.clip);
             else if (dec.mode == PAA_DECODE_LTRB)                         // fcos/inference.py:93-98

@@ -76,6 +76,7 @@ class PAAPostProcessor(torch.nn.Module):
         args.skip_nms = int(bool(self.bbox_aug_enabled and not self.bbox_aug_vote))      # inference.py:96
         args.pre_nms_thresh, args.nms_thresh = float(self.pre_nms_thresh), float(self.nms_thresh)
         args.anchor_image_stride = lv["anchor_stride"]
+        args.head_layout = lv["layout"]          # NCHW or channels-last heads, consumed in place
         args.box_decode = self._decode[0]
         for k in range(4):
             args.decode_weights[k] = float(self._decode[1][k])

@@ -122,23 +122,41 @@ def _require_cuda(t, name):
 _warned_layout = set()
 
 
-def _head(t, name):
-    """A head tensor as the kernels read it: float32, NCHW-contiguous (the layout PAAHead.forward produces,
-    paa.py:90-108).  Any other layout -- `torch.channels_last` from an AMP / cuDNN pipeline, a sliced view -- is
-    copied, which for the classification logits of a 16-image batch is a 115 MB round trip per call: say so once
-    instead of hiding it (keep the head's outputs in `torch.contiguous_format` to avoid the copy)."""
+def _dense_both_ways(t):
+    """One channel or one location: the NCHW and the channels-last arrangement are the same bytes."""
+    return t.is_contiguous() and t.is_contiguous(memory_format=torch.channels_last)
+
+
+def call_layout(box_cls):
+    """The memory layout of a call: channels-last (NHWC) when the classification logits -- the tensors that carry
+    the bytes -- are dense `torch.channels_last` tensors, else NCHW (what PAAHead.forward produces, paa.py:90-108).
+    Both are consumed in place (include/paa_b200.h, `head_layout`); tensors of the call in any other arrangement are
+    copied to the call's layout by `_head`, with a warning."""
+    telling = [t for t in box_cls if t.dim() == 4 and not _dense_both_ways(t)]
+    if telling and all(t.is_contiguous(memory_format=torch.channels_last) for t in telling):
+        return _lib.LAYOUT_NHWC
+    return _lib.LAYOUT_NCHW
+
+
+def _head(t, name, layout=0):
+    """A head tensor as the kernels read it: float32, dense in the call's layout (NCHW-contiguous or channels-last).
+    Anything else -- a sliced view, a tensor in the other layout than the call's logits -- is copied, which for the
+    classification logits of a 16-image batch is a 115 MB round trip per call: say so once instead of hiding it."""
     _require_cuda(t, name)
     if t.dtype != torch.float32:
         raise RuntimeError("%s must be float32, got %s" % (name, t.dtype))
-    if t.is_contiguous():
+    fmt = torch.channels_last if layout == _lib.LAYOUT_NHWC else torch.contiguous_format
+    if t.is_contiguous(memory_format=fmt):
         return t
     if name not in _warned_layout:
         _warned_layout.add(name)
         import warnings
-        warnings.warn("paa_b200: %s is not NCHW-contiguous (strides %s for shape %s); it is copied to the layout the "
-                      "kernels read on every call -- %.1f MB here.  Keep the head outputs in torch.contiguous_format."
-                      % (name, tuple(t.stride()), tuple(t.shape), t.numel() * 4 / 1e6), stacklevel=3)
-    return t.contiguous()
+        warnings.warn("paa_b200: %s is not dense in the call's layout (%s; strides %s for shape %s); it is copied on "
+                      "every call -- %.1f MB here.  Keep all head outputs of a call either in torch.contiguous_format "
+                      "or in torch.channels_last."
+                      % (name, "channels-last" if layout == _lib.LAYOUT_NHWC else "NCHW", tuple(t.stride()),
+                         tuple(t.shape), t.numel() * 4 / 1e6), stacklevel=3)
+    return t.contiguous(memory_format=fmt)
 
 
 def _anchors_shared(anchors, N, L):
@@ -170,9 +188,10 @@ def gather_levels(box_cls, box_regression, iou_pred, anchors):
         raise RuntimeError("anchors lists %d images, heads have batch %d" % (len(anchors), N))
     apl = box_regression[0].shape[1] // 4
     num_classes = box_cls[0].shape[1] // apl
-    cls = [_head(t, "box_cls") for t in box_cls]
-    reg = [_head(t, "box_regression") for t in box_regression]
-    iou = None if iou_pred is None else [_head(t, "iou_pred") for t in iou_pred]
+    layout = call_layout(box_cls)
+    cls = [_head(t, "box_cls", layout) for t in box_cls]
+    reg = [_head(t, "box_regression", layout) for t in box_regression]
+    iou = None if iou_pred is None else [_head(t, "iou_pred", layout) for t in iou_pred]
     hw, grid_w = [], []
     first = anchors[0]
     for l in range(L):
@@ -207,7 +226,7 @@ def gather_levels(box_cls, box_regression, iou_pred, anchors):
         stride = A * 4
         keep = [stacked]
     return dict(L=L, N=N, apl=apl, C=num_classes, hw=hw, grid_w=grid_w, A=A, cls=cls, reg=reg, iou=iou,
-                anchor_ptrs=level_ptrs, anchor_stride=stride, keep=keep)
+                anchor_ptrs=level_ptrs, anchor_stride=stride, keep=keep, layout=layout)
 
 
 class _PAALossFunction(torch.autograd.Function):
@@ -439,6 +458,7 @@ class PAALossComputation(object):
             args.fcos_iou_loss_type = _lib.IOU_LOSS_TYPES[self.iou_loss_type]
             args.fcos_norm_reg_targets = int(self.norm_reg_targets)
         args.anchor_image_stride = lv["anchor_stride"]
+        args.head_layout = lv["layout"]
         cls_l, reg_l, iou_l = lv["cls"], lv["reg"], lv["iou"]
         anchor_ptrs, hw_l, grid_w = lv["anchor_ptrs"], lv["hw"], lv["grid_w"]
         levels = args.levels
@@ -456,7 +476,9 @@ class PAALossComputation(object):
 
     @staticmethod
     def _alloc_grads(lv, has_iou):
-        """Gradient tensors shaped like the heads, cut from ONE allocation (15 allocator calls -> 1)."""
+        """Gradient tensors shaped (and laid out in memory) like the heads, cut from ONE allocation (15 allocator
+        calls -> 1)."""
+        nhwc = lv["layout"] == _lib.LAYOUT_NHWC
         groups = [lv["cls"], lv["reg"]] + ([lv["iou"]] if has_iou else [])
         # every piece starts on a 16-byte boundary: the kernels write float4
         sizes = [[(t.numel() + 3) // 4 * 4 for t in g] for g in groups]
@@ -465,7 +487,12 @@ class PAALossComputation(object):
         for g, sz in zip(groups, sizes):
             views = []
             for t, n in zip(g, sz):
-                views.append(flat[o:o + t.numel()].view(t.shape))
+                piece = flat[o:o + t.numel()]
+                if nhwc:       # the channels-last arrangement of the same logical [N, ch, H, W] tensor
+                    b, ch, h, w = t.shape
+                    views.append(piece.view(b, h, w, ch).permute(0, 3, 1, 2))
+                else:
+                    views.append(piece.view(t.shape))
                 o += n
             out.append(views)
         return dict(cls=out[0], reg=out[1], iou=out[2] if has_iou else None, flat=flat)
@@ -567,7 +594,7 @@ class PAALossComputation(object):
         if not heads or not _anchors_shared(anchors, len(anchors), len(box_cls)):
             return None                  # per-image anchor tensors are stacked afresh on every call: nothing to pin
         key = (tuple(t.data_ptr() for t in heads), heads[0].shape[0], tuple(b.bbox.data_ptr() for b in anchors[0]),
-               bool(need_grad), self._world())
+               bool(need_grad), self._world(), tuple(heads[0].stride()))
         entry = self._graphs.get(key)
         if entry is None:
             if len(self._graphs) >= 8:                       # bounded: a training loop cycles through few shapes

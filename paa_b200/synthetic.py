@@ -250,14 +250,20 @@ def fcos_locations(grids, strides=STRIDES):
     return out
 
 
-def to_device_inputs(batch, device="cuda", requires_grad=False):
+def to_device_inputs(batch, device="cuda", requires_grad=False, channels_last=False):
     """SyntheticBatch -> (box_cls, box_regression, iou_pred, targets, anchors) in the reference's API
     shapes, on the device, with the per-level anchor tensors shared by all images like
-    anchor_generator.py:112-125 does."""
+    anchor_generator.py:112-125 does.  `channels_last`: the head tensors in torch.channels_last memory format (the
+    same logical [N, C, H, W] values), as an AMP / cuDNN NHWC pipeline hands them over."""
+    import torch
     from paa_b200.structures import BoxList
-    cls = [t.to(device).requires_grad_(requires_grad) for t in batch.box_cls]
-    reg = [t.to(device).requires_grad_(requires_grad) for t in batch.box_regression]
-    iou = None if batch.iou_pred is None else [t.to(device).requires_grad_(requires_grad) for t in batch.iou_pred]
+    fmt = torch.channels_last if channels_last else torch.contiguous_format
+
+    def head(t):
+        return t.to(device).contiguous(memory_format=fmt).requires_grad_(requires_grad)
+    cls = [head(t) for t in batch.box_cls]
+    reg = [head(t) for t in batch.box_regression]
+    iou = None if batch.iou_pred is None else [head(t) for t in batch.iou_pred]
     anc = [a.to(device) for a in batch.anchors]
     targets, anchors = [], []
     for i in range(batch.num_images):

@@ -31,10 +31,11 @@ def test_struct_layout_matches_header(tmp_path):
                    "workspace", "normalisers", "grad_losses", "dbg_matched_idx", "teacher_combined_loss", "rank",
                    "peer_norm", "bg_iou_threshold", "box_code_weights", "smooth_l1_beta", "reg_norm_weight", "fcos_strides",
                    "fcos_center_radius", "fcos_iou_loss_type", "fcos_norm_reg_targets", "atss_positive_type",
-                   "peer_timeout_s", "peer_status", "gt_offsets_dev", "gt_capacity", "gt_per_image_capacity"]
+                   "peer_timeout_s", "peer_status", "gt_offsets_dev", "gt_capacity", "gt_per_image_capacity",
+                   "head_layout"]
     fields_post = ["num_images", "pre_nms_thresh", "anchor_image_stride", "levels", "image_wh", "workspace",
                    "out_boxes", "out_count", "dbg_pre_boxes", "dbg_nms_keep", "box_decode", "decode_weights",
-                   "decode_clip"]
+                   "decode_clip", "head_layout"]
     src = ['#include <stdio.h>', '#include <stddef.h>', '#include "paa_b200.h"', 'int main(void){',
            'printf("%zu %zu %zu\\n", sizeof(PaaLevel), sizeof(PaaLossArgs), sizeof(PaaPostArgs));']
     for f in fields_loss:

@@ -158,22 +158,38 @@ def test_fcos_points_cache_is_validated_and_bounded():
     assert len(cache) <= _POINTS_CACHE_ENTRIES
 
 
-def test_non_nchw_heads_are_copied_with_a_warning_not_silently():
-    """VERDICT r1 #8: a channels_last head used to be `.contiguous()`-copied without a word."""
+def test_head_layouts_consumed_in_place_and_odd_ones_copied_with_a_warning():
+    """a channels_last head used to be `.contiguous()`-copied without a word.  Now a call whose logits
+    are channels-last runs in that layout (no copy); only a tensor that is dense in neither the call's layout is copied,
+    and the user is told once."""
     import warnings
     import torch
-    from paa_b200 import loss as paa_loss
+    from paa_b200 import _lib, loss as paa_loss
 
     class FakeCuda(torch.Tensor):
         is_cuda = True
 
+    nhwc = [torch.zeros(2, 8, 4, 6).to(memory_format=torch.channels_last).as_subclass(FakeCuda),
+            torch.zeros(2, 8, 1, 1).as_subclass(FakeCuda)]          # a 1x1 map is dense both ways
+    nchw = [torch.zeros(2, 8, 4, 6).as_subclass(FakeCuda), torch.zeros(2, 8, 1, 1).as_subclass(FakeCuda)]
+    assert paa_loss.call_layout(nhwc) == _lib.LAYOUT_NHWC
+    assert paa_loss.call_layout(nchw) == _lib.LAYOUT_NCHW
+    assert paa_loss.call_layout([nchw[0], nhwc[0]]) == _lib.LAYOUT_NCHW       # mixed: the reference's layout
+    assert paa_loss.call_layout([nchw[1]]) == _lib.LAYOUT_NCHW
     paa_loss._warned_layout.clear()
-    t = torch.zeros(2, 8, 4, 6).to(memory_format=torch.channels_last).as_subclass(FakeCuda)
     with warnings.catch_warnings(record=True) as w:
         warnings.simplefilter("always")
-        out = paa_loss._head(t, "box_cls")
-        paa_loss._head(t, "box_cls")                       # warned once per head name
-    assert out.is_contiguous()
-    assert len([x for x in w if "not NCHW-contiguous" in str(x.message)]) == 1
-    c = torch.zeros(2, 8, 4, 6).as_subclass(FakeCuda)
+        for t in nhwc:
+            assert paa_loss._head(t, "box_cls", _lib.LAYOUT_NHWC) is t         # consumed in place
+        for t in nchw:
+            assert paa_loss._head(t, "box_cls", _lib.LAYOUT_NCHW) is t
+        assert not w
+        out = paa_loss._head(nhwc[0], "box_cls", _lib.LAYOUT_NCHW)
+        paa_loss._head(nhwc[0], "box_cls", _lib.LAYOUT_NCHW)                   # warned once per head name
+        back = paa_loss._head(nchw[0], "box_regression", _lib.LAYOUT_NHWC)
+        sliced = paa_loss._head(torch.zeros(2, 16, 4, 6)[:, ::2].as_subclass(FakeCuda), "iou_pred", _lib.LAYOUT_NCHW)
+    assert out.is_contiguous() and sliced.is_contiguous()
+    assert back.is_contiguous(memory_format=torch.channels_last)
+    assert len([x for x in w if "not dense in the call's layout" in str(x.message)]) == 3
+    c = nchw[0]
     assert paa_loss._head(c, "box_cls") is c               # the usual case costs nothing

@@ -101,10 +101,15 @@ POST_KERNELS = [
      "flat stream over the logits; gated elements drained through a block queue"),
     ("post_threshold_kernel", "post_threshold", "latency", lambda A, C: 0, "histogram walk"),
     ("post_filter_kernel", "post_filter", "latency", lambda A, C: 0, "8 B per candidate"),
-    ("post_select_kernel", "post_select", "latency", lambda A, C: 0, "radix select + bitonic sort + decode per (image, level)"),
+    ("post_select_kernel", "post_select", "latency", lambda A, C: 0,
+     "rank the boundary bin, counting sort by candidate index, decode per (image, level)"),
     ("post_group_kernel+post_class_rank_kernel", "post_rank", "latency", lambda A, C: 0, "order by (label, score)"),
-    ("post_nms_mask_kernel", "post_nms_mask", "alu", lambda A, C: 0, "64x64 bit tiles of pair IoUs where labels match"),
-    ("post_nms_scan_kernel", "post_nms_scan", "latency", lambda A, C: 0, "one warp per label run scans greedily"),
+    ("post_nms_runs_kernel", "post_nms_runs", "alu", lambda A, C: 0,
+     "greedy NMS of every label run (<= 256 boxes) by one warp: candidates against the run's kept boxes, no mask in memory"),
+    ("post_nms_mask_kernel", "post_nms_mask", "latency", lambda A, C: 0,
+     "longer runs only (64x64 bit tiles of pair IoUs); images without one return at once"),
+    ("post_nms_scan_kernel", "post_nms_scan", "latency", lambda A, C: 0,
+     "longer runs only (one warp per label run scans the mask greedily); images without one return at once"),
     ("post_finish_kernel", "post_finish", "latency", lambda A, C: 0, "top-100 cut by radix select, ordered compaction"),
     ("post_vote_kernel", "post_vote", "alu", lambda A, C: 0, "one warp per detection votes"),
 ]

@@ -326,6 +326,7 @@ int paa_box_vote(const float* boxes, const float* scores, const float* labels, i
 #define PAA_KERNEL_POST_VOTE    17
 #define PAA_KERNEL_POST_THRESHOLD 18
 #define PAA_KERNEL_POST_SEGMENTS 19
+#define PAA_KERNEL_POST_NMS_RUNS 20  /* post_nms_runs_kernel: greedy NMS of every label run by one warp, no mask in memory */
 /* Self-test of the branch-free float32 square root / reciprocal the mixture fit uses in place of the IEEE library
  * routines: out [4, n] = {fast sqrt(x), __fsqrt_rn(x), fast 1/x, __fdiv_rn(1, x)} for device arrays x [n]. */
 int paa_selftest_roots(const float* x, int n, float* out, void* stream);

@@ -115,7 +115,8 @@ SYMBOLS = {
 KERNEL_IDS = dict(pass1=1, match_score=2, select_gmm=3, final_loss=4, positive_terms=5, finish_loss=6, norm_wait=7,
                   prep_step=8,
                   post_threshold=18, post_segments=19, post_candidates=10, post_filter=11,
-                  post_select=12, post_rank=13, post_nms_mask=14, post_nms_scan=15, post_finish=16, post_vote=17)
+                  post_select=12, post_rank=13, post_nms_mask=14, post_nms_scan=15, post_finish=16, post_vote=17,
+                  post_nms_runs=20)
 
 _lib = None
 

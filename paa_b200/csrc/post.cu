@@ -30,7 +30,9 @@ namespace paa {
 
 constexpr int kHistBins = 2048;
 constexpr int kMaxTopN = 4096;
-constexpr int kFilterBlocks = 32;      // blocks per (image, level) list in the filter pass
+constexpr int kFilterBlocks = 8;       // blocks per (image, level) list in the filter pass
+constexpr int kFilterPer = 4;          // entries per thread and trip
+constexpr int kFilterChunk = 256 * kFilterPer;
 
 struct PostWorkspace {
     // cleared at the start of every call
@@ -38,6 +40,7 @@ struct PostWorkspace {
     int* sel_count;       // [N*L]
     int* bnd_count;       // [N*L]
     int* hist;            // [N*L*kHistBins]
+    int* nms_big;         // [N]        image has a label run too long for the fused NMS kernel
     size_t zero_bytes;
     // fully written before read
     uint2* cand;          // [N * A*C]  (score bits, anchor*C + class) per (image, level) list
@@ -59,6 +62,7 @@ struct PostWorkspace {
     int* n_seg;           // [N]
     unsigned long long* mask;   // [N * capN * nbw]
     unsigned char* keep_sorted; // [N*capN]
+    unsigned char* row_long;    // [N*capN]   1 = the row's label run is left to the mask + scan pair
     int* out_rank;        // [N*capN]   sorted index of every output row (for voting)
     unsigned char* flag_by_pos; // [N*capN] survivor flag by pre-NMS position
     int* rank_by_pos;     // [N*capN]   sorted index by pre-NMS position
@@ -82,6 +86,7 @@ static PostWorkspace carve_post(void* base, int N, int A, int C, int L, int topn
     w.sel_count = (int*)take(NL * 4);
     w.bnd_count = (int*)take(NL * 4);
     w.hist = (int*)take(NL * kHistBins * 4);
+    w.nms_big = (int*)take((size_t)N * 4);
     w.zero_bytes = off;
     w.cand = (uint2*)take(NAC * 8);
     w.bnd = (unsigned*)take(NAC * 4);
@@ -102,6 +107,7 @@ static PostWorkspace carve_post(void* base, int N, int A, int C, int L, int topn
     w.n_seg = (int*)take((size_t)N * 4);
     w.mask = (unsigned long long*)take((size_t)N * capN * nbw * 8);
     w.keep_sorted = (unsigned char*)take((size_t)N * capN);
+    w.row_long = (unsigned char*)take((size_t)N * capN);
     w.out_rank = (int*)take((size_t)N * capN * 4);
     w.flag_by_pos = (unsigned char*)take((size_t)N * capN);
     w.rank_by_pos = (int*)take((size_t)N * capN * 4);
@@ -432,35 +438,45 @@ post_filter_kernel(const Geometry geo, const uint2* __restrict__ cand, const int
     const int part = blockIdx.x - seg * kFilterBlocks;
     const int n = seg / geo.num_levels, l = seg - n * geo.num_levels;
     const int count = cand_count[seg];
+    if (part * kFilterChunk >= count) return;
     const int tb = thr_bin[seg];
     const size_t list_off = ((size_t)n * geo.A + geo.lv[l].a_off) * geo.C;
     const uint2* list = cand + list_off;
     unsigned* blist = bnd + list_off;
     uint2* out = sel + (size_t)seg * topn;
     const int lane = threadIdx.x & 31;
-    for (int e0 = part * 256; e0 < count; e0 += kFilterBlocks * 256) {
-        const int e = e0 + threadIdx.x;
-        bool is_sel = false, is_bnd = false;
-        uint2 v = make_uint2(0u, 0u);
-        if (e < count) {
-            v = list[e];
-            const int b = score_bin(__uint_as_float(v.x));
-            is_sel = b > tb;
-            is_bnd = b == tb;
+    // a block takes 1024 consecutive entries at a time: four coalesced loads per thread in flight, then ONE atomic per
+    // warp and output list for all four (the kernel is a chain of memory round trips, not bandwidth)
+    for (int e0 = part * kFilterChunk; e0 < count; e0 += kFilterBlocks * kFilterChunk) {
+        uint2 v[kFilterPer];
+        int e[kFilterPer];
+#pragma unroll
+        for (int k = 0; k < kFilterPer; ++k) {
+            e[k] = e0 + k * 256 + threadIdx.x;
+            v[k] = e[k] < count ? list[e[k]] : make_uint2(0u, 0u);
         }
-        unsigned m = __ballot_sync(PAA_FULL, is_sel);
-        if (m) {
-            int base = 0;
-            if (lane == 0) base = atomicAdd(&sel_count[seg], __popc(m));
-            base = __shfl_sync(PAA_FULL, base, 0);
-            if (is_sel) out[base + __popc(m & ((1u << lane) - 1u))] = v;
+        unsigned ms[kFilterPer], mb[kFilterPer];
+        int n_sel = 0, n_bnd = 0;
+#pragma unroll
+        for (int k = 0; k < kFilterPer; ++k) {
+            const int b = score_bin(__uint_as_float(v[k].x));
+            ms[k] = __ballot_sync(PAA_FULL, e[k] < count && b > tb);
+            mb[k] = __ballot_sync(PAA_FULL, e[k] < count && b == tb);
+            n_sel += __popc(ms[k]);
+            n_bnd += __popc(mb[k]);
         }
-        m = __ballot_sync(PAA_FULL, is_bnd);
-        if (m) {
-            int base = 0;
-            if (lane == 0) base = atomicAdd(&bnd_count[seg], __popc(m));
-            base = __shfl_sync(PAA_FULL, base, 0);
-            if (is_bnd) blist[base + __popc(m & ((1u << lane) - 1u))] = (unsigned)e;
+        int base_s = 0, base_b = 0;
+        if (lane == 0 && n_sel) base_s = atomicAdd(&sel_count[seg], n_sel);
+        if (lane == 0 && n_bnd) base_b = atomicAdd(&bnd_count[seg], n_bnd);
+        base_s = __shfl_sync(PAA_FULL, base_s, 0);
+        base_b = __shfl_sync(PAA_FULL, base_b, 0);
+        const unsigned below = (1u << lane) - 1u;
+#pragma unroll
+        for (int k = 0; k < kFilterPer; ++k) {
+            if ((ms[k] >> lane) & 1u) out[base_s + __popc(ms[k] & below)] = v[k];
+            if ((mb[k] >> lane) & 1u) blist[base_b + __popc(mb[k] & below)] = (unsigned)e[k];
+            base_s += __popc(ms[k]);
+            base_b += __popc(mb[k]);
         }
     }
 }
@@ -834,11 +850,20 @@ post_group_kernel(int L, int topn, int C, const int* __restrict__ pre_cnt, const
             atomicAdd(&s_start[lab + 1], 1);                     // counts shifted by one: scan gives starts
         }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        int run = 0;
-        for (int c = 0; c < C + 2; ++c) {                        // s_start[c] = first sorted index of label c
-            run += s_start[c];
-            s_start[c] = run;
+    if (threadIdx.x < 32) {
+        // inclusive scan of the C + 2 counts by one warp, 32 at a time: s_start[c] = first sorted index of label c
+        int carry = 0;
+        for (int c0 = 0; c0 < C + 2; c0 += 32) {
+            const int c = c0 + (int)threadIdx.x;
+            int v = c < C + 2 ? s_start[c] : 0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(PAA_FULL, v, o);
+                if ((int)threadIdx.x >= o) v += t;
+            }
+            v += carry;
+            if (c < C + 2) s_start[c] = v;
+            carry = __shfl_sync(PAA_FULL, v, 31);
         }
     }
     __syncthreads();
@@ -930,6 +955,174 @@ post_segments_kernel(int capN, const int* __restrict__ total, const int* __restr
 }
 
 // ---------------------------------------------------------------------------------------------
+// nms_runs: greedy suppression of one label run by ONE warp, without a bit mask in memory
+// (csrc/cuda/ml_nms.cu:13-24,55-70,116-128 -- same pairs, same comparison, same keep set).
+//
+// Boxes are sorted by (label, score desc).  The warp walks its run 32 boxes at a time; lane = box.  (1) every box of
+// the group is tested against the run's boxes KEPT so far (their coordinates wait in the warp's slice of shared
+// memory, broadcast reads): a suppressed box never suppresses anything, so rows of suppressed boxes -- most of a
+// crowded run -- are never evaluated, which the mask formulation cannot know; (2) the 32 x 32 triangle inside the
+// group as one 32-bit word per lane, columns that (1) already removed skipped; (3) the serial greedy scan of the
+// group over those words (shuffles); (4) the kept boxes join the list.  Against the two-kernel mask + scan pair
+// (34.7 M warp instructions and a 64-bit word per (row, 64 columns) through memory at 64 images): no global
+// intermediate, no lanes looping over other labels' columns, one launch less.  Runs longer than kRunMax boxes (a
+// crowd of one class) flag their image for the mask + scan pair below, which is parallel over the rows of a run.
+// ---------------------------------------------------------------------------------------------
+constexpr int kRunWarps = 4;
+constexpr int kRunMax = 128;
+
+// iou_plus1(a, b) > thr, decided without the division wherever the operands leave no doubt: with t = thr * union,
+// inter > t * (1 + 2^-20) makes the rounded quotient exceed thr and inter < t * (1 - 2^-20) keeps it below (the
+// quotient and t each carry a relative rounding error of 2^-24); only pairs inside that band -- and anything
+// degenerate (non-positive union or threshold, NaN) -- take the exact IEEE division.  Same decision as
+// `iou_plus1(...) > thr` for every input.
+struct IouGate {
+    float thr, hi, lo;
+    bool fast;
+};
+__device__ __forceinline__ IouGate iou_gate(float thr) {
+    IouGate g;
+    g.thr = thr;
+    g.hi = thr * (1.0f + 9.5367431640625e-7f);
+    g.lo = thr * (1.0f - 9.5367431640625e-7f);
+    g.fast = thr > 0.0f;
+    return g;
+}
+// The branch-free part: returns "certainly above", *unsure = neither certain answer applies.
+__device__ __forceinline__ bool iou_certain(float4 a, float area_a, float4 b, float area_b, const IouGate& g,
+                                            bool* unsure) {
+    const float w = __fadd_rn(__fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)), 1.0f);
+    const float h = __fadd_rn(__fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)), 1.0f);
+    const float inter = __fmul_rn(w, h);
+    const float uni = __fsub_rn(__fadd_rn(area_a, area_b), inter);
+    const bool overlap = (w > 0.0f) && (h > 0.0f);
+    const bool pos = g.fast && uni > 0.0f;
+    // no overlap (or a NaN coordinate): the quotient is 0 (or NaN), which never exceeds a positive threshold
+    const bool yes = overlap && pos && inter > g.hi * uni;
+    const bool no = g.fast && (!overlap || (pos && inter < g.lo * uni));
+    *unsure = !(yes || no);
+    return yes;
+}
+__device__ __forceinline__ bool iou_exceeds(float4 a, float area_a, float4 b, float area_b, const IouGate& g) {
+    bool unsure;
+    const bool yes = iou_certain(a, area_a, b, area_b, g, &unsure);
+    if (!unsure) return yes;
+    return iou_plus1(a, area_a, b, area_b) > g.thr;          // inside the band / degenerate: the reference's own test
+}
+
+__global__ void __launch_bounds__(kRunWarps * 32)
+post_nms_runs_kernel(int capN, int segs_per_image, int num_images, float thr, const int* __restrict__ seg_start,
+                     const int* __restrict__ n_seg, const float4* __restrict__ s_box,
+                     unsigned char* __restrict__ keep_sorted, unsigned char* __restrict__ row_long,
+                     int* __restrict__ big) {
+    PAA_TRACE_SCOPE(16);
+    __shared__ float4 s_kb[kRunWarps][kRunMax + 4];   // kept boxes of the run so far (+ padding: see below)
+    __shared__ float s_ka[kRunWarps][kRunMax + 4];    // their areas
+    __shared__ float4 s_gb[kRunWarps][32];            // the current group
+    __shared__ float s_ga[kRunWarps][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gw = blockIdx.x * kRunWarps + warp;
+    const int n = gw / segs_per_image;
+    if (n >= num_images) return;
+    const int s = gw - n * segs_per_image;
+    if (s >= n_seg[n]) return;
+    const int* ss = seg_start + (size_t)n * (capN + 1);
+    const int a = ss[s], b = ss[s + 1];
+    if (b <= a) return;
+    const size_t base = (size_t)n * capN;
+    if (b - a > kRunMax) {                             // a long run: its rows go through the mask + scan pair
+        for (int r = a + lane; r < b; r += 32) row_long[base + r] = 1;
+        if (lane == 0) big[n] = 1;
+        return;
+    }
+    const IouGate gate = iou_gate(thr);
+    float4* kb = s_kb[warp];
+    float* ka = s_ka[warp];
+    float4* gb = s_gb[warp];
+    float* ga = s_ga[warp];
+    // The kept list is read four entries at a time; the up to three entries past its end hold a box that overlaps
+    // nothing (and is never "unsure"): no tail loop.
+    const float4 nowhere = make_float4(3.0e38f, 3.0e38f, -3.0e38f, -3.0e38f);
+    if (lane < 4) {
+        kb[lane] = nowhere;
+        ka[lane] = 1.0f;
+    }
+    int nk = 0;                                        // kept so far (warp-uniform)
+    for (int g0 = a; g0 < b; g0 += 32) {
+        const int r = g0 + lane;
+        const bool valid = r < b;
+        const float4 box = valid ? s_box[base + r] : nowhere;
+        const float area = valid ? area_plus1(box) : 1.0f;
+        gb[lane] = box;
+        ga[lane] = area;
+        __syncwarp();
+        // (1) suppressed by a box kept earlier in the run?  Four independent tests per trip.
+        bool dead = !valid;
+        for (int i = 0; i < nk; i += 4) {
+            bool u0, u1, u2, u3;
+            const bool y0 = iou_certain(kb[i], ka[i], box, area, gate, &u0);
+            const bool y1 = iou_certain(kb[i + 1], ka[i + 1], box, area, gate, &u1);
+            const bool y2 = iou_certain(kb[i + 2], ka[i + 2], box, area, gate, &u2);
+            const bool y3 = iou_certain(kb[i + 3], ka[i + 3], box, area, gate, &u3);
+            dead = dead || y0 || y1 || y2 || y3;
+            if (u0 || u1 || u2 || u3) {                // rare: a pair inside the rounding band of the threshold
+                if (u0) dead = dead || (iou_plus1(kb[i], ka[i], box, area) > thr);
+                if (u1) dead = dead || (iou_plus1(kb[i + 1], ka[i + 1], box, area) > thr);
+                if (u2) dead = dead || (iou_plus1(kb[i + 2], ka[i + 2], box, area) > thr);
+                if (u3) dead = dead || (iou_plus1(kb[i + 3], ka[i + 3], box, area) > thr);
+            }
+        }
+        const unsigned removed0 = __ballot_sync(PAA_FULL, dead);
+        // (2) the pairs inside the group, each evaluated once: in trip t lane l takes the pair (l, (l + t) mod 32);
+        // trips 1..15 cover every pair whose cyclic distance is below 16 exactly once, trip 16 (lanes 0..15) the
+        // rest.  Bit j of lane i's word <=> box j > i overlaps box i by more than thr; the lane that evaluated a pair
+        // whose smaller index is not its own hands the result over through the trip's ballot.
+        unsigned m = 0u;
+#pragma unroll 4
+        for (int t = 1; t <= 16; ++t) {
+            const int c = (lane + t) & 31;
+            const bool active = (t < 16 || lane < 16) && !dead && (((removed0 >> c) & 1u) == 0u);
+            bool unsure;
+            bool hit = iou_certain(box, area, gb[c], ga[c], gate, &unsure);
+            if (active && unsure) hit = iou_plus1(box, area, gb[c], ga[c]) > thr;
+            hit = hit && active;
+            const unsigned hits = __ballot_sync(PAA_FULL, hit);
+            if (hit && c > lane) m |= 1u << c;
+            const int from = (lane - t) & 31;          // the lane whose pair of this trip has me as its column
+            if (from > lane && ((hits >> from) & 1u)) m |= 1u << from;
+        }
+        // (3) greedy scan of the group, best score first: the 32 words are fetched up front (independent shuffles),
+        // what is left is a chain of bit operations
+        unsigned removed = removed0, kept = 0u;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const unsigned mj = __shfl_sync(PAA_FULL, m, j);
+            const bool alive = ((removed >> j) & 1u) == 0u;
+            kept |= alive ? (1u << j) : 0u;
+            removed |= alive ? mj : 0u;
+        }
+        // (4) results; the kept boxes join the list the later groups are tested against
+        const bool mine = (kept >> lane) & 1u;
+        if (valid) {
+            keep_sorted[base + r] = mine ? 1 : 0;
+            row_long[base + r] = 0;
+        }
+        __syncwarp();
+        if (mine) {
+            const int at = nk + __popc(kept & ((1u << lane) - 1u));
+            kb[at] = box;
+            ka[at] = area;
+        }
+        nk += __popc(kept);
+        if (lane < 4) {                                // padding behind the new end (nk <= kRunMax)
+            kb[nk + lane] = nowhere;
+            ka[nk + lane] = 1.0f;
+        }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // nms_mask: bit (i, j) set when sorted box j > i has the same label and IoU(+1) > thr
 // (csrc/cuda/ml_nms.cu:13-24,55-70).  Tiles whose row and column label ranges are disjoint are
 // skipped and never read by the scan.
@@ -939,37 +1132,46 @@ post_segments_kernel(int capN, const int* __restrict__ total, const int* __restr
 // (boxes are sorted by label).  A tile's boxes are staged in the warp's own slice of shared memory (no block barrier);
 // of its 64 columns only the contiguous range whose labels occur among the warp's rows is visited.  Splitting the
 // walk into pieces keeps a long run (a class with a thousand boxes: 16 tiles) off the critical path of small batches.
-constexpr int kMaskWarps = 4;
-constexpr int kMaskPieces = 4;
+constexpr int kMaskWarps = 4;                        // row groups (of 32 rows) per block
+constexpr int kMaskPieces = 4;                       // column pieces per row group: a block is kMaskWarps * kMaskPieces warps
 
-__global__ void __launch_bounds__(kMaskWarps * 32)
+__global__ void __launch_bounds__(kMaskWarps * kMaskPieces * 32)
 post_nms_mask_kernel(int capN, int nbw, float thr, const int* __restrict__ total,
                      const float4* __restrict__ s_box, const int* __restrict__ s_label,
-                     unsigned long long* __restrict__ mask) {
-    PAA_TRACE_SCOPE(16);
-    __shared__ float4 s_cb[kMaskWarps][64];
-    __shared__ float s_ca[kMaskWarps][64];
-    __shared__ int s_cl[kMaskWarps][64];
+                     unsigned long long* __restrict__ mask, const unsigned char* __restrict__ row_long,
+                     const int* __restrict__ big) {
+    PAA_TRACE_SCOPE(20);
+    // only the rows of label runs too long for post_nms_runs_kernel are left (it flagged them and their image)
+    if (!big[blockIdx.z]) return;
+    __shared__ float4 s_cb[kMaskWarps * kMaskPieces][64];
+    __shared__ float s_ca[kMaskWarps * kMaskPieces][64];
+    __shared__ int s_cl[kMaskWarps * kMaskPieces][64];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int piece = warp % kMaskPieces, group = warp / kMaskPieces;
     const int n = blockIdx.z;
     const int cnt = total[n];
-    const int r0 = (blockIdx.x * kMaskWarps + warp) * 32;
+    const int r0 = (blockIdx.x * kMaskWarps + group) * 32;
     if (r0 >= cnt) return;
     const size_t base = (size_t)n * capN;
     const int r = r0 + lane;
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
     int al = -1;
+    bool mine = false;
     if (r < cnt) {
         a = s_box[base + r];
         al = s_label[base + r];
+        mine = row_long[base + r] != 0;
     }
+    const unsigned lm = __ballot_sync(PAA_FULL, mine);
+    if (lm == 0u) return;
     const float aa = area_plus1(a);
-    const int first_label = __shfl_sync(PAA_FULL, al, 0);
-    const int last_label = __shfl_sync(PAA_FULL, al, min(cnt - r0, 32) - 1);
+    const IouGate gate = iou_gate(thr);
+    const int first_label = __shfl_sync(PAA_FULL, al, __ffs(lm) - 1);
+    const int last_label = __shfl_sync(PAA_FULL, al, 31 - __clz(lm));
     float4* cbx = s_cb[warp];
     float* cba = s_ca[warp];
     int* cbl = s_cl[warp];
-    for (int cb = (r0 >> 6) + (int)blockIdx.y; cb * 64 < cnt; cb += kMaskPieces) {
+    for (int cb = (r0 >> 6) + piece; cb * 64 < cnt; cb += kMaskPieces) {
         const int c0 = cb * 64;
         if (s_label[base + c0] > last_label) break;               // no shared label from here on
         const int csize = min(64, cnt - c0);
@@ -997,21 +1199,21 @@ post_nms_mask_kernel(int capN, int nbw, float thr, const int* __restrict__ total
                                       ((unsigned long long)__ballot_sync(PAA_FULL, l1 <= last_label) << 32);
         const unsigned long long live = ge & le;
         unsigned long long bits = 0ull;
-        if (live) {
+        if (live && mine) {
             int j_lo = __ffsll((long long)live) - 1;
             const int j_hi = 64 - __clzll((long long)live);
-            if (c0 + j_lo <= r0) j_lo = r0 + 1 - c0;              // nothing at or left of the warp's first row
+            if (c0 + j_lo <= r) j_lo = r + 1 - c0;                // nothing at or left of the row itself
             for (int j = j_lo; j < j_hi; ++j) {
-                if (cbl[j] != al || c0 + j <= r) continue;
-                if (iou_plus1(a, aa, cbx[j], cba[j]) > thr) bits |= 1ull << j;
+                if (cbl[j] != al) continue;
+                if (iou_exceeds(a, aa, cbx[j], cba[j], gate)) bits |= 1ull << j;
             }
         }
-        if (r < cnt) mask[(base + r) * nbw + cb] = bits;
+        if (mine) mask[(base + r) * nbw + cb] = bits;
     }
 }
 
 static inline dim3 nms_mask_grid(int capN, int num_images) {
-    return dim3((capN + kMaskWarps * 32 - 1) / (kMaskWarps * 32), kMaskPieces, num_images);
+    return dim3((capN + kMaskWarps * 32 - 1) / (kMaskWarps * 32), 1, num_images);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1032,17 +1234,18 @@ __global__ void __launch_bounds__(kScanWarps * 32)
 post_nms_scan_kernel(int capN, int nbw, int segs_per_image, int num_images,
                      const int* __restrict__ seg_start,
                      const int* __restrict__ n_seg, const unsigned long long* __restrict__ mask,
-                     unsigned char* __restrict__ keep_sorted) {
+                     unsigned char* __restrict__ keep_sorted, const int* __restrict__ big) {
     PAA_TRACE_SCOPE(17);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gw = blockIdx.x * kScanWarps + warp;
     const int n = gw / segs_per_image;
     if (n >= num_images) return;
+    if (!big[n]) return;
     const int s = gw - n * segs_per_image;
     if (s >= n_seg[n]) return;
     const int* ss = seg_start + (size_t)n * (capN + 1);
     const int a = ss[s], b = ss[s + 1];
-    if (b <= a) return;
+    if (b - a <= kRunMax) return;                       // short runs were finished by post_nms_runs_kernel
     const size_t base = (size_t)n * capN;
     const int w_lo = a >> 6, w_hi = (b - 1) >> 6;
     for (int w = w_lo; w <= w_hi; ++w) {
@@ -1545,18 +1748,26 @@ int run_postprocess(const Geometry& geo, const PaaPostArgs* a, cudaStream_t stre
         PAA_LAUNCH_CHECK("post_segments_kernel");
     }
     if (!a->skip_nms) {
+        const int segs = grouped ? C + 1 : (capN < C ? capN : C);   // label runs per image (upper bound)
+        const int warps = N * segs;
         {
+            // every label run of up to kRunMax boxes: one warp, no mask in memory
+            KernelTimer t(PAA_KERNEL_POST_NMS_RUNS, stream);
+            post_nms_runs_kernel<<<(warps + kRunWarps - 1) / kRunWarps, kRunWarps * 32, 0, stream>>>(
+                capN, segs, N, a->nms_thresh, w.seg_start, w.n_seg, w.s_box, w.keep_sorted, w.row_long, w.nms_big);
+        }
+        PAA_LAUNCH_CHECK("post_nms_runs_kernel");
+        {
+            // images with a longer run (flagged by the kernel above; the others return at once)
             KernelTimer t(PAA_KERNEL_POST_NMS_MASK, stream);
-            post_nms_mask_kernel<<<nms_mask_grid(capN, N), kMaskWarps * 32, 0, stream>>>(capN, nbw, a->nms_thresh, w.total, w.s_box, w.s_label,
-                                                          w.mask);
+            post_nms_mask_kernel<<<nms_mask_grid(capN, N), kMaskWarps * kMaskPieces * 32, 0, stream>>>(capN, nbw, a->nms_thresh, w.total, w.s_box, w.s_label,
+                                                          w.mask, w.row_long, w.nms_big);
         }
         PAA_LAUNCH_CHECK("post_nms_mask_kernel");
         {
             KernelTimer t(PAA_KERNEL_POST_NMS_SCAN, stream);
-            const int segs = grouped ? C + 1 : (capN < C ? capN : C);   // label runs per image (upper bound)
-            const int warps = N * segs;
             post_nms_scan_kernel<<<(warps + kScanWarps - 1) / kScanWarps, kScanWarps * 32, 0, stream>>>(
-                capN, nbw, segs, N, w.seg_start, w.n_seg, w.mask, w.keep_sorted);
+                capN, nbw, segs, N, w.seg_start, w.n_seg, w.mask, w.keep_sorted, w.nms_big);
         }
         PAA_LAUNCH_CHECK("post_nms_scan_kernel");
     }
@@ -1584,7 +1795,7 @@ int run_postprocess(const Geometry& geo, const PaaPostArgs* a, cudaStream_t stre
 // stand-alone label-aware NMS behind `_C.ml_nms` (csrc/ml_nms.h:10-27)
 // ---------------------------------------------------------------------------------------------
 struct MlNmsWorkspace {
-    int* cnt;             // [1]
+    int* cnt;             // [2]  number of boxes; long-run flag of the fused NMS
     float4* box;          // [n]
     int* label;           // [n]
     float4* s_box;
@@ -1596,6 +1807,7 @@ struct MlNmsWorkspace {
     int* n_seg;
     unsigned long long* mask;
     unsigned char* keep_sorted;
+    unsigned char* row_long;
     size_t total_bytes;
 };
 
@@ -1621,6 +1833,7 @@ static MlNmsWorkspace carve_ml_nms(void* base, int n) {
     w.n_seg = (int*)take(4);
     w.mask = (unsigned long long*)take(nn * nbw * 8);
     w.keep_sorted = (unsigned char*)take(nn);
+    w.row_long = (unsigned char*)take(nn);
     w.total_bytes = off;
     return w;
 }
@@ -1630,7 +1843,10 @@ size_t ml_nms_workspace_bytes(int n) { return carve_ml_nms(nullptr, n).total_byt
 __global__ void ml_nms_prepare_kernel(int n, const float* __restrict__ boxes, const float* __restrict__ labels,
                                       float4* __restrict__ box, int* __restrict__ label, int* __restrict__ cnt) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i == 0) *cnt = n;
+    if (i == 0) {
+        cnt[0] = n;
+        cnt[1] = 0;                  // "a label run too long for post_nms_runs_kernel" flag of the call
+    }
     if (i < n) {
         box[i] = make_float4(boxes[i * 4], boxes[i * 4 + 1], boxes[i * 4 + 2], boxes[i * 4 + 3]);
         label[i] = (int)labels[i];
@@ -1675,10 +1891,14 @@ int run_ml_nms(const float* boxes, const float* scores, const float* labels, int
     PAA_LAUNCH_CHECK("post_rank_kernel");
     post_segments_kernel<<<1, 1024, 0, stream>>>(n, w.total, w.s_label, w.seg_start, w.n_seg);
     PAA_LAUNCH_CHECK("post_segments_kernel");
-    post_nms_mask_kernel<<<nms_mask_grid(n, 1), kMaskWarps * 32, 0, stream>>>(n, nbw, thresh, w.total, w.s_box, w.s_label, w.mask);
+    post_nms_runs_kernel<<<(n + kRunWarps - 1) / kRunWarps, kRunWarps * 32, 0, stream>>>(
+        n, n, 1, thresh, w.seg_start, w.n_seg, w.s_box, w.keep_sorted, w.row_long, w.cnt + 1);
+    PAA_LAUNCH_CHECK("post_nms_runs_kernel");
+    post_nms_mask_kernel<<<nms_mask_grid(n, 1), kMaskWarps * kMaskPieces * 32, 0, stream>>>(n, nbw, thresh, w.total, w.s_box, w.s_label, w.mask,
+                                                                             w.row_long, w.cnt + 1);
     PAA_LAUNCH_CHECK("post_nms_mask_kernel");
     post_nms_scan_kernel<<<(n + kScanWarps - 1) / kScanWarps, kScanWarps * 32, 0, stream>>>(
-        n, nbw, n, 1, w.seg_start, w.n_seg, w.mask, w.keep_sorted);
+        n, nbw, n, 1, w.seg_start, w.n_seg, w.mask, w.keep_sorted, w.cnt + 1);
     PAA_LAUNCH_CHECK("post_nms_scan_kernel");
     ml_nms_scatter_kernel<<<(n + 255) / 256, 256, 0, stream>>>(n, w.s_pos, w.keep_sorted, keep, num_keep);
     PAA_LAUNCH_CHECK("ml_nms_scatter_kernel");
@@ -2022,11 +2242,14 @@ int run_box_vote(const float* boxes, const float* scores, const float* labels, i
     post_segments_kernel<<<1, 1024, 0, stream>>>(n, w.nms.total, w.nms.s_label, w.nms.seg_start, w.nms.n_seg);
     PAA_LAUNCH_CHECK("post_segments_kernel");
     if (mode == 0) {
-        post_nms_mask_kernel<<<nms_mask_grid(n, 1), kMaskWarps * 32, 0, stream>>>(n, nbw, nms_thresh, w.nms.total, w.nms.s_box, w.nms.s_label,
-                                                       w.nms.mask);
+        post_nms_runs_kernel<<<(n + kRunWarps - 1) / kRunWarps, kRunWarps * 32, 0, stream>>>(
+            n, n, 1, nms_thresh, w.nms.seg_start, w.nms.n_seg, w.nms.s_box, w.nms.keep_sorted, w.nms.row_long, w.nms.cnt + 1);
+        PAA_LAUNCH_CHECK("post_nms_runs_kernel");
+        post_nms_mask_kernel<<<nms_mask_grid(n, 1), kMaskWarps * kMaskPieces * 32, 0, stream>>>(n, nbw, nms_thresh, w.nms.total, w.nms.s_box, w.nms.s_label,
+                                                       w.nms.mask, w.nms.row_long, w.nms.cnt + 1);
         PAA_LAUNCH_CHECK("post_nms_mask_kernel");
         post_nms_scan_kernel<<<(n + kScanWarps - 1) / kScanWarps, kScanWarps * 32, 0, stream>>>(
-            n, nbw, n, 1, w.nms.seg_start, w.nms.n_seg, w.nms.mask, w.nms.keep_sorted);
+            n, nbw, n, 1, w.nms.seg_start, w.nms.n_seg, w.nms.mask, w.nms.keep_sorted, w.nms.cnt + 1);
         PAA_LAUNCH_CHECK("post_nms_scan_kernel");
     }
     box_vote_kernel<<<(n + kVoteWarpsPerBlock - 1) / kVoteWarpsPerBlock, kVoteWarpsPerBlock * 32, 0, stream>>>(

@@ -96,18 +96,44 @@ def test_nms_known_answers_from_reference_tests():
 
 
 def test_nms_random_against_oracle_including_single_class_crowd():
+    """Label runs on both sides of the fused kernel's limit (post_nms_runs_kernel: one warp per run of up to 256
+    boxes, longer runs flag the call for the mask + scan pair), sparse and crowded (most boxes suppressed, so the
+    kept-list test of the fused kernel does the work)."""
     from paa_b200.inference import ml_nms
     rng = np.random.default_rng(3)
-    for n, n_cls in ((1, 1), (63, 3), (64, 1), (65, 80), (700, 5), (3000, 1)):
-        ctr = rng.uniform(0, 400, (n, 2))
+    cases = [(1, 1, 400), (63, 3, 400), (64, 1, 400), (65, 80, 400), (700, 5, 400), (3000, 1, 400),
+             (255, 1, 400), (256, 1, 300), (257, 1, 300), (1000, 4, 150), (1500, 6, 80), (33, 1, 40), (512, 2, 60)]
+    for n, n_cls, spread in cases:
+        ctr = rng.uniform(0, spread, (n, 2))
         wh = rng.uniform(10, 120, (n, 2))
         boxes = np.concatenate([ctr - wh / 2, ctr + wh / 2], axis=1).astype(np.float32)
         scores = rng.permutation(n).astype(np.float32) / n          # distinct scores: no tie ambiguity
         labels = rng.integers(1, n_cls + 1, n).astype(np.float32)
+        if n == 1500:                                               # one long run among short ones
+            labels[:700] = 1.0
         want = nms_oracle.ml_nms_cpu(boxes, scores, labels, 0.5)
         got = ml_nms(torch.from_numpy(boxes).cuda(), torch.from_numpy(scores).cuda(),
                      torch.from_numpy(labels).cuda(), 0.5)
         assert np.array_equal(got.cpu().numpy(), want), (n, n_cls)
+
+
+def test_postprocess_with_one_long_label_run():
+    """One image whose candidates are dominated by a single class (a run of more than 256 boxes: the mask + scan
+    pair) next to an ordinary image (fused per-run kernel) in the same call, against the oracle."""
+    b = synthetic.make_inference_batch(seed=4200, num_images=2, image_hw=(384, 512), candidates_per_level=1500)
+    for t in b.box_cls[:2]:
+        t[0, 7] += 4.0                                              # image 0: class 8 everywhere on P3 / P4
+    want = post_oracle.postprocess(b.box_cls, b.box_regression, b.iou_pred, b.anchors, b.image_sizes)
+    assert int((want[0].pre_labels == 8).sum()) > 256 and int(np.bincount(want[1].pre_labels.numpy()).max()) <= 256
+    pp = _postprocessor()
+    pp.debug = True
+    out = _run(pp, b)
+    for i, r in enumerate(out):
+        w = want[i]
+        _assert_rows_match(_pre_lists(pp, i), (w.pre_boxes.numpy(), w.pre_scores.numpy(), w.pre_labels.numpy()))
+        _assert_rows_match((r.bbox.cpu().numpy(), r.get_field("scores").cpu().numpy(),
+                            r.get_field("labels").cpu().numpy()),
+                           (w.boxes.numpy(), w.scores.numpy(), w.labels.numpy()))
 
 
 @pytest.mark.parametrize("per_level", [None, 4000])

@@ -21,7 +21,8 @@ TRACE_LIB = os.path.join(ROOT, "paa_b200", "libpaa_b200_trace.so")
 NAMES = ["prep_step", "iou_match", "match_score", "select_gmm", "bulk_focal", "positive_list"]
 POST_FIRST = 8
 POST_NAMES = ["post_candidates", "post_threshold", "post_filter", "post_select", "post_rank", "post_group",
-              "post_class_rank", "post_segments", "post_nms_mask", "post_nms_scan", "post_finish", "post_vote"]
+              "post_class_rank", "post_segments", "post_nms_runs", "post_nms_scan", "post_finish", "post_vote",
+              "post_nms_mask"]
 SLOTS = 24
 
 

@@ -218,97 +218,165 @@ __device__ __forceinline__ void divmod_small(unsigned n, unsigned d, float inv, 
     *r = (unsigned)rr;
 }
 
+// The block's queue of gated elements (shared memory) and what every kernel variant does with it.
+struct CandQueue {
+    float* x;                 // [kCandQueue] gated logit
+    unsigned* e;              // [kCandQueue] its element index inside the image's [C, H*W] block
+    unsigned short* where;    // [kCandQueue] (image << 3) | level
+    unsigned* hist2;          // [kHistBins / 2] score histogram of one list (big drains), two 16-bit bins a word
+    int* cnt;
+};
+
+// all threads: exact test + score + append for every queued element (block-uniform call).  A big drain
+// (a dense chunk: thousands of candidates of ONE list) counts its scores into a shared-memory histogram
+// that is added to the list's global one at the end; small drains update the global histogram directly.
+__device__ __forceinline__ void cand_drain(const Geometry& geo, const CandQueue& q, float thr, uint2* __restrict__ cand,
+                                           int* __restrict__ cand_count, int* __restrict__ hist) {
+    const int lane = threadIdx.x & 31;
+    const float inv_c = 1.0f / (float)geo.C;
+    const int total = *q.cnt;
+    const bool big = total >= 4 * kCandThreads;
+    int hist_seg = -1;
+    if (big) {
+        const unsigned where0 = q.where[0];
+        hist_seg = (int)(where0 >> 3) * geo.num_levels + (int)(where0 & 7u);
+        for (int b = threadIdx.x; b < kHistBins / 2; b += kCandThreads) q.hist2[b] = 0u;
+        __syncthreads();
+    }
+    for (int t0 = 0; t0 < total; t0 += kCandThreads) {
+        const int t = t0 + threadIdx.x;
+        bool is = false;
+        float score = 0.0f;
+        unsigned entry = 0u;
+        int seg = -1, n = 0, l = 0;
+        if (t < total) {
+            const float xval = q.x[t];
+            const float p = 1.0f / (1.0f + expf(-xval));                   // inference.py:43
+            if (p > thr) {                                                 // inference.py:48
+                const unsigned where = q.where[t];
+                n = (int)(where >> 3);
+                l = (int)(where & 7u);
+                const LevelView& lv = geo.lv[l];
+                const unsigned hw = (unsigned)lv.hw;
+                unsigned chn, loc, a, c;
+                size_t iou_at;
+                if (geo.nhwc) {
+                    // channels-last: the element index inside the image's block IS anchor * C + class
+                    entry = q.e[t];
+                    divmod_small(entry, (unsigned)geo.C, inv_c, &a, &c);       // a = anchor of the level
+                    iou_at = (size_t)n * lv.n_anchor + a;
+                } else {
+                    divmod_small(q.e[t], hw, 1.0f / (float)hw, &chn, &loc);
+                    divmod_small(chn, (unsigned)geo.C, inv_c, &a, &c);
+                    entry = (loc * (unsigned)geo.apl + a) * (unsigned)geo.C + c;   // anchor * C + class
+                    iou_at = ((size_t)n * geo.apl + a) * hw + loc;
+                }
+                score = p;
+                if (lv.iou != nullptr) {
+                    const float xi = __ldg(lv.iou + iou_at);
+                    const float qq = 1.0f / (1.0f + expf(-xi));            // inference.py:55
+                    score = sqrtf(__fmul_rn(p, qq));                       // inference.py:56
+                }
+                seg = n * geo.num_levels + l;
+                is = true;
+            }
+        }
+        // one global atomic per (warp, list); queue neighbours mostly share their list
+        const unsigned act = __ballot_sync(PAA_FULL, is);
+        if (is) {
+            const unsigned peers = __match_any_sync(act, seg);
+            const int leader = __ffs(peers) - 1;
+            int pos = 0;
+            if (lane == leader) pos = atomicAdd(&cand_count[seg], __popc(peers));
+            pos = __shfl_sync(peers, pos, leader) + __popc(peers & ((1u << lane) - 1u));
+            cand[((size_t)n * geo.A + geo.lv[l].a_off) * geo.C + pos] = make_uint2(__float_as_uint(score), entry);
+            const int bin = score_bin(score);
+            if (seg == hist_seg) atomicAdd(&q.hist2[bin >> 1], 1u << (16 * (bin & 1)));   // <= kCandQueue < 65536 per bin
+            else atomicAdd(&hist[(size_t)seg * kHistBins + bin], 1);
+        }
+    }
+    __syncthreads();
+    if (big) {
+        int* gh = hist + (size_t)hist_seg * kHistBins;
+        for (int b = threadIdx.x; b < kHistBins / 2; b += kCandThreads) {
+            const unsigned v = q.hist2[b];
+            if (v & 0xffffu) atomicAdd(&gh[2 * b], (int)(v & 0xffffu));
+            if (v >> 16) atomicAdd(&gh[2 * b + 1], (int)(v >> 16));
+        }
+    }
+    if (threadIdx.x == 0) *q.cnt = 0;
+    __syncthreads();
+}
+
+// The gate over the kCandVecs float4 a thread holds (float4 j = elements e_first + (j * kCandThreads + threadIdx.x) * 4
+// .. + 3 of image n, level l) and the push of the gated ones into the block's queue.  Warp-uniform control flow.
+// Returns the queue's fill as this warp last saw it: right after its own push, or a plain read if it pushed nothing.
+// The warp that pushes last in a round sees the round's final fill, so `__syncthreads_or(seen >= limit)` gives every
+// thread of the block the same answer to "does the queue have to be drained" -- reading the counter after the barrier
+// would race with the next round's pushes of faster warps.
+__device__ __forceinline__ int cand_gate(const float4 (&x)[kCandVecs], float logit_gate, int n, int l, unsigned e_first,
+                                          const CandQueue& q) {
+    const int lane = threadIdx.x & 31;
+    // bit 4j+t: element t of float4 j passes the gate (16 compares, no transcendental)
+    // (most threads hold no gated element at all: one maximum over the 16 values decides that first)
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < kCandVecs; ++j) mx = fmaxf(mx, fmaxf(fmaxf(x[j].x, x[j].y), fmaxf(x[j].z, x[j].w)));
+    unsigned mask = 0u;
+    if (mx > logit_gate) {
+#pragma unroll
+        for (int j = 0; j < kCandVecs; ++j) {
+            mask |= (x[j].x > logit_gate ? 1u : 0u) << (4 * j);
+            mask |= (x[j].y > logit_gate ? 1u : 0u) << (4 * j + 1);
+            mask |= (x[j].z > logit_gate ? 1u : 0u) << (4 * j + 2);
+            mask |= (x[j].w > logit_gate ? 1u : 0u) << (4 * j + 3);
+        }
+    }
+    int seen;
+    if (__any_sync(PAA_FULL, mask != 0u)) {
+        // queue slots for the warp's gated elements: warp scan of the per-lane counts, one shared atomic
+        const int mine = __popc(mask);
+        int incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(PAA_FULL, incl, o);
+            if (lane >= o) incl += v;
+        }
+        int base = 0;
+        if (lane == 31) base = atomicAdd(q.cnt, incl);
+        base = __shfl_sync(PAA_FULL, base, 31);
+        seen = base + __shfl_sync(PAA_FULL, incl, 31);
+        int slot = base + incl - mine;
+        const unsigned short where = (unsigned short)((n << 3) | l);
+#pragma unroll 1
+        while (mask) {
+            const int b = __ffs(mask) - 1;
+            mask &= mask - 1u;
+            const int j = b >> 2, t = b & 3;
+            const float4 xs = j == 0 ? x[0] : (j == 1 ? x[1] : (j == 2 ? x[2] : x[3]));
+            q.x[slot] = t == 0 ? xs.x : (t == 1 ? xs.y : (t == 2 ? xs.z : xs.w));
+            q.e[slot] = e_first + (unsigned)(j * kCandThreads + threadIdx.x) * 4u + (unsigned)t;
+            q.where[slot] = where;
+            ++slot;
+        }
+    } else {
+        seen = *reinterpret_cast<volatile int*>(q.cnt);
+    }
+    return seen;
+}
+
 __global__ void __launch_bounds__(kCandThreads, kCandBlocksPerSM)
 post_candidates_kernel(const Geometry geo, const CandPlan plan, const float thr, const float logit_gate,
                        uint2* __restrict__ cand, int* __restrict__ cand_count, int* __restrict__ hist) {
     PAA_TRACE_SCOPE(8);
-    __shared__ float q_x[kCandQueue];              // gated logit
-    __shared__ unsigned q_e[kCandQueue];           // its element index inside the image's [C, H*W] block
-    __shared__ unsigned short q_where[kCandQueue]; // (image << 3) | level
-    __shared__ unsigned s_hist2[kHistBins / 2];    // score histogram of one list (big drains), two 16-bit bins a word
+    __shared__ float q_x[kCandQueue];
+    __shared__ unsigned q_e[kCandQueue];
+    __shared__ unsigned short q_where[kCandQueue];
+    __shared__ unsigned s_hist2[kHistBins / 2];
     __shared__ int q_cnt;
-    const int lane = threadIdx.x & 31;
+    const CandQueue q = {q_x, q_e, q_where, s_hist2, &q_cnt};
     if (threadIdx.x == 0) q_cnt = 0;
     __syncthreads();
-    const float inv_c = 1.0f / (float)geo.C;
-
-    // all threads: exact test + score + append for every queued element (block-uniform call).  A big drain
-    // (a dense chunk: thousands of candidates of ONE list) counts its scores into a shared-memory histogram
-    // that is added to the list's global one at the end; small drains update the global histogram directly.
-    auto drain = [&]() {
-        const int total = q_cnt;
-        const bool big = total >= 4 * kCandThreads;
-        int hist_seg = -1;
-        if (big) {
-            const unsigned where0 = q_where[0];
-            hist_seg = (int)(where0 >> 3) * geo.num_levels + (int)(where0 & 7u);
-            for (int b = threadIdx.x; b < kHistBins / 2; b += kCandThreads) s_hist2[b] = 0u;
-            __syncthreads();
-        }
-        for (int t0 = 0; t0 < total; t0 += kCandThreads) {
-            const int t = t0 + threadIdx.x;
-            bool is = false;
-            float score = 0.0f;
-            unsigned entry = 0u;
-            int seg = -1, n = 0, l = 0;
-            if (t < total) {
-                const float xval = q_x[t];
-                const float p = 1.0f / (1.0f + expf(-xval));                   // inference.py:43
-                if (p > thr) {                                                 // inference.py:48
-                    const unsigned where = q_where[t];
-                    n = (int)(where >> 3);
-                    l = (int)(where & 7u);
-                    const LevelView& lv = geo.lv[l];
-                    const unsigned hw = (unsigned)lv.hw;
-                    unsigned chn, loc, a, c;
-                    size_t iou_at;
-                    if (geo.nhwc) {
-                        // channels-last: the element index inside the image's block IS anchor * C + class
-                        entry = q_e[t];
-                        divmod_small(entry, (unsigned)geo.C, inv_c, &a, &c);       // a = anchor of the level
-                        iou_at = (size_t)n * lv.n_anchor + a;
-                    } else {
-                        divmod_small(q_e[t], hw, 1.0f / (float)hw, &chn, &loc);
-                        divmod_small(chn, (unsigned)geo.C, inv_c, &a, &c);
-                        entry = (loc * (unsigned)geo.apl + a) * (unsigned)geo.C + c;   // anchor * C + class
-                        iou_at = ((size_t)n * geo.apl + a) * hw + loc;
-                    }
-                    score = p;
-                    if (lv.iou != nullptr) {
-                        const float xi = __ldg(lv.iou + iou_at);
-                        const float q = 1.0f / (1.0f + expf(-xi));             // inference.py:55
-                        score = sqrtf(__fmul_rn(p, q));                        // inference.py:56
-                    }
-                    seg = n * geo.num_levels + l;
-                    is = true;
-                }
-            }
-            // one global atomic per (warp, list); queue neighbours mostly share their list
-            const unsigned act = __ballot_sync(PAA_FULL, is);
-            if (is) {
-                const unsigned peers = __match_any_sync(act, seg);
-                const int leader = __ffs(peers) - 1;
-                int pos = 0;
-                if (lane == leader) pos = atomicAdd(&cand_count[seg], __popc(peers));
-                pos = __shfl_sync(peers, pos, leader) + __popc(peers & ((1u << lane) - 1u));
-                cand[((size_t)n * geo.A + geo.lv[l].a_off) * geo.C + pos] = make_uint2(__float_as_uint(score), entry);
-                const int bin = score_bin(score);
-                if (seg == hist_seg) atomicAdd(&s_hist2[bin >> 1], 1u << (16 * (bin & 1)));   // <= kCandQueue < 65536 per bin
-                else atomicAdd(&hist[(size_t)seg * kHistBins + bin], 1);
-            }
-        }
-        __syncthreads();
-        if (big) {
-            int* gh = hist + (size_t)hist_seg * kHistBins;
-            for (int b = threadIdx.x; b < kHistBins / 2; b += kCandThreads) {
-                const unsigned v = s_hist2[b];
-                if (v & 0xffffu) atomicAdd(&gh[2 * b], (int)(v & 0xffffu));
-                if (v >> 16) atomicAdd(&gh[2 * b + 1], (int)(v >> 16));
-            }
-        }
-        if (threadIdx.x == 0) q_cnt = 0;
-        __syncthreads();
-    };
 
     unsigned ch = blockIdx.x;
     if (ch >= plan.total) return;
@@ -323,53 +391,152 @@ post_candidates_kernel(const Geometry geo, const CandPlan plan, const float thr,
             nxt = cand_chunk(geo, plan, ch_next);
             cand_load(nxt, plan.vec[nxt.l] != 0, nx);
         }
-        // bit 4j+t: element t of float4 j passes the gate (16 compares, no transcendental)
-        // (most threads hold no gated element at all: one maximum over the 16 values decides that first)
-        float mx = -INFINITY;
-#pragma unroll
-        for (int j = 0; j < kCandVecs; ++j) mx = fmaxf(mx, fmaxf(fmaxf(x[j].x, x[j].y), fmaxf(x[j].z, x[j].w)));
-        unsigned mask = 0u;
-        if (mx > logit_gate) {
-#pragma unroll
-            for (int j = 0; j < kCandVecs; ++j) {
-                mask |= (x[j].x > logit_gate ? 1u : 0u) << (4 * j);
-                mask |= (x[j].y > logit_gate ? 1u : 0u) << (4 * j + 1);
-                mask |= (x[j].z > logit_gate ? 1u : 0u) << (4 * j + 2);
-                mask |= (x[j].w > logit_gate ? 1u : 0u) << (4 * j + 3);
-            }
-        }
-        if (__any_sync(PAA_FULL, mask != 0u)) {
-            // queue slots for the warp's gated elements: warp scan of the per-lane counts, one shared atomic
-            const int mine = __popc(mask);
-            int incl = mine;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int v = __shfl_up_sync(PAA_FULL, incl, o);
-                if (lane >= o) incl += v;
-            }
-            int base = 0;
-            if (lane == 31) base = atomicAdd(&q_cnt, incl);
-            int slot = __shfl_sync(PAA_FULL, base, 31) + incl - mine;
-            const unsigned short where = (unsigned short)((cur.n << 3) | cur.l);
-#pragma unroll 1
-            while (mask) {
-                const int b = __ffs(mask) - 1;
-                mask &= mask - 1u;
-                const int j = b >> 2, t = b & 3;
-                const float4 xs = j == 0 ? x[0] : (j == 1 ? x[1] : (j == 2 ? x[2] : x[3]));
-                q_x[slot] = t == 0 ? xs.x : (t == 1 ? xs.y : (t == 2 ? xs.z : xs.w));
-                q_e[slot] = cur.e_base + (unsigned)(j * kCandThreads + threadIdx.x) * 4u + (unsigned)t;
-                q_where[slot] = where;
-                ++slot;
-            }
-        }
-        __syncthreads();
-        if (q_cnt >= kCandDrainAt || !more) drain();      // q_cnt is stable between the barriers
+        const int seen = cand_gate(x, logit_gate, cur.n, cur.l, cur.e_base, q);
+        if (__syncthreads_or(seen >= kCandDrainAt) || !more) cand_drain(geo, q, thr, cand, cand_count, hist);
         if (!more) break;
         ch = ch_next;
         cur = nxt;
 #pragma unroll
         for (int j = 0; j < kCandVecs; ++j) x[j] = nx[j];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// candidates, bulk-copy variant: the same pass with the logits brought on chip by 1-D bulk asynchronous copies
+// (cp.async.bulk.shared.global + mbarrier: the copy engine behind TMA) instead of per-thread loads.
+//
+// One persistent block per SM; thread 0 keeps kRingStages copies of kRingStageBytes in flight (pieces of one image's
+// block of one level, dealt to the blocks round-robin like the chunks above), all threads wait on a stage's mbarrier
+// and walk it in rounds of kCandChunk elements with the gate / queue / drain code of the kernel above.  The block
+// barrier that closes a round also releases the stage: thread 0 refills it right away.  Why: straight after the
+// bench's flush the register-staged kernel reads at 3.5 TB/s (tools/stream_probe.cu: every register-staged variant,
+// whatever its blocks per SM and loads in flight, stays between 3.6 and 3.9 TB/s on this buffer), the bulk-copy ring
+// with one block per SM and >= 32 KB stages at 4.45 TB/s -- the requests of a whole stage reach the memory system as
+// one descriptor, with no warp waiting on a scoreboard for them.  Needs every level's image block to be a multiple of
+// 16 bytes at a 16-byte aligned address (C % 4 == 0: the usual 80 classes).
+// MEASURED AND NOT KEPT AS THE DEFAULT (PAA_POST_RING=1 selects it): C4, 64 images, 254 us against 134 us for the
+// kernel above (8 images: 52 against 31 us).  The copy side delivers; the consumer side cannot hide its own latencies
+// with one block per SM -- every drain (an IoU-prediction load and an atomic with a returned value per candidate, ~2 us
+// a trip; three dense P6 / P7 rounds of up to 4096 candidates per block) stalls the only block the SM has, where the
+// four-blocks-per-SM kernel overlaps one block's drain with the others' streaming.  Two blocks per SM do not fit
+// (2 x (96 KB ring + 49 KB queue)), and the probe's 3 x 32 KB x 2 blocks variant is no faster than register staging.
+// ---------------------------------------------------------------------------------------------
+constexpr int kRingStageBytes = 32 * 1024;
+constexpr int kRingStageElems = kRingStageBytes / 4;
+constexpr int kRingStages = 5;
+
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* b, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(b)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* b, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity) {
+    asm volatile(
+        "{\n.reg .pred p;\nPAA_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra PAA_DONE;\n"
+        "bra PAA_WAIT;\nPAA_DONE:\n}\n" ::"r"(smem_addr(b)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_addr(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+
+struct RingPlan {
+    unsigned piece_off[PAA_MAX_LEVELS + 1];     // first piece of each level in the global piece order
+    unsigned pieces_per_image[PAA_MAX_LEVELS];
+    float inv_ppi[PAA_MAX_LEVELS];              // 1 / pieces_per_image
+    unsigned total;
+};
+
+struct RingPiece {
+    int l, n;
+    unsigned e_base, count;                     // first element inside the image's block, elements in the piece
+    const float* src;
+};
+
+__device__ __forceinline__ RingPiece ring_piece(const Geometry& geo, const RingPlan& plan, unsigned p) {
+    RingPiece k;
+    k.l = 0;
+#pragma unroll
+    for (int q = 1; q < PAA_MAX_LEVELS; ++q)
+        if (q < geo.num_levels && p >= plan.piece_off[q]) k.l = q;
+    const unsigned rel = p - plan.piece_off[k.l];
+    unsigned n, in_image;
+    divmod_small(rel, plan.pieces_per_image[k.l], plan.inv_ppi[k.l], &n, &in_image);
+    k.n = (int)n;
+    k.e_base = in_image * kRingStageElems;
+    const unsigned per_image = (unsigned)(geo.apl * geo.C) * (unsigned)geo.lv[k.l].hw;
+    k.count = min((unsigned)kRingStageElems, per_image - k.e_base);
+    k.src = geo.lv[k.l].cls + (size_t)k.n * per_image + k.e_base;
+    return k;
+}
+
+__global__ void __launch_bounds__(kCandThreads, 1)
+post_candidates_ring_kernel(const Geometry geo, const RingPlan plan, const float thr, const float logit_gate,
+                            uint2* __restrict__ cand, int* __restrict__ cand_count, int* __restrict__ hist) {
+    PAA_TRACE_SCOPE(8);
+    extern __shared__ __align__(128) unsigned char s_ring[];       // kRingStages x kRingStageBytes
+    __shared__ unsigned long long s_full[kRingStages];
+    __shared__ float q_x[kCandQueue];
+    __shared__ unsigned q_e[kCandQueue];
+    __shared__ unsigned short q_where[kCandQueue];
+    __shared__ unsigned s_hist2[kHistBins / 2];
+    __shared__ int q_cnt;
+    const CandQueue q = {q_x, q_e, q_where, s_hist2, &q_cnt};
+    if (threadIdx.x == 0) {
+        q_cnt = 0;
+#pragma unroll
+        for (int s = 0; s < kRingStages; ++s) mbar_init(&s_full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (blockIdx.x >= plan.total) return;
+    // producer state (thread 0): the next piece to request and the stage it goes to
+    unsigned p_issue = blockIdx.x;
+    int s_issue = 0;
+    auto issue = [&]() {
+        if (p_issue < plan.total) {
+            const RingPiece pc = ring_piece(geo, plan, p_issue);
+            mbar_expect_tx(&s_full[s_issue], pc.count * 4u);
+            bulk_load(s_ring + (size_t)s_issue * kRingStageBytes, pc.src, pc.count * 4u, &s_full[s_issue]);
+        }
+        p_issue += gridDim.x;
+        s_issue = s_issue + 1 == kRingStages ? 0 : s_issue + 1;
+    };
+    if (threadIdx.x == 0)
+        for (int s = 0; s < kRingStages; ++s) issue();
+
+    int stage = 0;
+    unsigned parity = 0u;
+    for (unsigned p = blockIdx.x; p < plan.total; p += gridDim.x) {
+        const RingPiece pc = ring_piece(geo, plan, p);
+        const bool last_piece = p + gridDim.x >= plan.total;
+        mbar_wait(&s_full[stage], parity);
+        const float4* sp = reinterpret_cast<const float4*>(s_ring + (size_t)stage * kRingStageBytes);
+        for (unsigned r0 = 0; r0 < pc.count; r0 += kCandChunk) {
+            float4 x[kCandVecs];
+#pragma unroll
+            for (int j = 0; j < kCandVecs; ++j) {
+                const unsigned e = r0 + (unsigned)(j * kCandThreads + threadIdx.x) * 4u;     // count is a multiple of 4
+                x[j] = e < pc.count ? sp[e >> 2] : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+            }
+            const bool last_round = r0 + kCandChunk >= pc.count;
+            const int seen = cand_gate(x, logit_gate, pc.n, pc.l, pc.e_base + r0, q);
+            const int full = __syncthreads_or(seen >= kCandDrainAt);     // every thread has its part of the round in registers
+            if (last_round && threadIdx.x == 0) {
+                // the stage is free: order the block's reads of it before the copy engine's writes, refill
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                issue();
+            }
+            if (full || (last_piece && last_round)) cand_drain(geo, q, thr, cand, cand_count, hist);
+        }
+        stage = stage + 1 == kRingStages ? 0 : stage + 1;
+        parity ^= (stage == 0) ? 1u : 0u;
     }
 }
 
@@ -1675,11 +1842,41 @@ int run_postprocess(const Geometry& geo, const PaaPostArgs* a, cudaStream_t stre
         }
         plan.chunk_off[PAA_MAX_LEVELS] = chunks;
         plan.total = chunks;
-        unsigned grid = 148u * kCandBlocksPerSM;
-        if (grid > chunks) grid = chunks;
+        // opt-in (measurement switch): see the kernel's comment for why the register-staged kernel stays the default
+        bool ring = getenv("PAA_POST_RING") != nullptr;
+        for (int l = 0; l < L; ++l) ring = ring && plan.vec[l] != 0;
         KernelTimer t(PAA_KERNEL_POST_CANDIDATES, stream);
-        post_candidates_kernel<<<grid, kCandThreads, 0, stream>>>(geo, plan, a->pre_nms_thresh, gate,
-                                                                               w.cand, w.cand_count, w.hist);
+        if (ring) {
+            RingPlan rp;
+            unsigned pieces = 0;
+            for (int l = 0; l < PAA_MAX_LEVELS; ++l) {
+                rp.piece_off[l] = pieces;
+                rp.pieces_per_image[l] = 1;
+                rp.inv_ppi[l] = 1.0f;
+                if (l >= L) continue;
+                const unsigned long long per_image = (unsigned long long)geo.apl * C * geo.lv[l].hw;
+                rp.pieces_per_image[l] = (unsigned)((per_image + kRingStageElems - 1) / kRingStageElems);
+                rp.inv_ppi[l] = 1.0f / (float)rp.pieces_per_image[l];
+                pieces += rp.pieces_per_image[l] * (unsigned)N;
+            }
+            rp.piece_off[PAA_MAX_LEVELS] = pieces;
+            rp.total = pieces;
+            static bool attr_set = false;
+            if (!attr_set) {
+                PAA_CUDA_CHECK(cudaFuncSetAttribute(post_candidates_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                    kRingStages * kRingStageBytes));
+                attr_set = true;
+            }
+            unsigned grid = 148u;
+            if (grid > pieces) grid = pieces;
+            post_candidates_ring_kernel<<<grid, kCandThreads, kRingStages * kRingStageBytes, stream>>>(
+                geo, rp, a->pre_nms_thresh, gate, w.cand, w.cand_count, w.hist);
+        } else {
+            unsigned grid = 148u * kCandBlocksPerSM;
+            if (grid > chunks) grid = chunks;
+            post_candidates_kernel<<<grid, kCandThreads, 0, stream>>>(geo, plan, a->pre_nms_thresh, gate,
+                                                                      w.cand, w.cand_count, w.hist);
+        }
     }
     PAA_LAUNCH_CHECK("post_candidates_kernel");
     {

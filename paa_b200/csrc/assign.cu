@@ -947,10 +947,29 @@ __device__ __forceinline__ unsigned long long topk_first_batch(unsigned long lon
     return mine;
 }
 
-template <int SPL>
+// MODE 0: the whole per-GT program in one block (warp l selects level l, warp 0 fits): what runs.
+// MODE 1 / MODE 2: the same program cut in two launches -- MODE 1 the selection alone (block per GT, sorted candidates
+//         to memory), MODE 2 the fit alone with ONE WARP per GT, four GTs per block, i.e. 24 resident fits per SM
+//         instead of the 6 that MODE 0's five-warp blocks allow.  Built for the throughput-bound calls (C3: 16 000 GTs,
+//         216 us in this kernel) on the assumption that the fit is a latency chain that more resident warps would hide.
+//         MEASURED AND NOT KEPT AS A DEFAULT (PAA_GMM_SPLIT_ABOVE=<n> selects it for calls sized for more than n GTs;
+//         bit-identical results, tests/test_gpu_loss.py): C3 216 us against 212 us fused, C5 83 against 79 us.  Per-GT
+//         cycle counts (tools/gmm_profile.py, GMM_PROFILE_SHAPE=C3) show why: an EM iteration costs 2290 cycles in
+//         BOTH forms on the loaded GPU (1480 when a fit has its SM sub-partition to itself), and 16 000 fits x 11.3 us
+//         / 216 us = ~840 fits in flight either way -- the fit is bound by the issue rate of the FP64 pipe (a warp-wide
+//         DFMA / DADD / DMUL every 8 cycles per sub-partition, the figure tools/lat_probe.cu reads as "dependent issue"),
+//         not by latency: more resident fits just queue on that pipe.  What would help is fewer FP64 instructions per
+//         iteration, which sklearn's float64 responsibilities / log-sum-exp (oracle/gmm_oracle.py) do not leave room for
+//         at equal iteration counts.
+constexpr int kSelectFused = 0, kSelectOnly = 1, kFitOnly = 2;
+constexpr int kSplitAboveGts = 0x7fffffff; // two-launch form off unless PAA_GMM_SPLIT_ABOVE asks for it (see above)
+constexpr int kFitWarps = 4;
+
+template <int SPL, int MODE>
 // (64 registers: with the usual five levels six blocks fit an SM, so ~900 GTs are one wave)
 // (four samples per lane -- TOPK 20 -- need more than 64 registers: no spills at two 256-thread blocks per SM)
-__global__ void __launch_bounds__(PAA_MAX_LEVELS * PAA_WARP, SPL >= 4 ? 2 : 4)
+__global__ void __launch_bounds__(MODE == kFitOnly ? kFitWarps * PAA_WARP : PAA_MAX_LEVELS * PAA_WARP,
+                                  MODE == kFitOnly ? (SPL >= 4 ? 3 : 6) : (SPL >= 4 ? 2 : 4))
 select_gmm_kernel(const Geometry geo, const GtOffsets* __restrict__ gop, const int* __restrict__ gt_image,
                   const float* __restrict__ gt_boxes, const int64_t* __restrict__ gt_labels,
                   const LossScalars sc, const uint4* __restrict__ tile_gtmask,
@@ -959,7 +978,8 @@ select_gmm_kernel(const Geometry geo, const GtOffsets* __restrict__ gop, const i
                   int* __restrict__ paa_label, int* __restrict__ pos_list,
                   int* __restrict__ part_npos, double* __restrict__ part_siou,
                   unsigned* __restrict__ ticket, double* __restrict__ local_norm,
-                  double* __restrict__ normalisers, const PeerExchange px, const LossDebug dbg) {
+                  double* __restrict__ normalisers, const PeerExchange px, const LossDebug dbg,
+                  unsigned long long* __restrict__ cand_sorted, int* __restrict__ cand_n) {
     // lets the loss pass (a programmatic dependent launch) become resident and prefetch while the slowest fits run
     PAA_TRACE_SCOPE(3);
     pdl_wait();
@@ -971,7 +991,7 @@ select_gmm_kernel(const Geometry geo, const GtOffsets* __restrict__ gop, const i
     __shared__ unsigned long long s_sorted[PAA_MAX_CANDIDATES];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int gi = blockIdx.x;
+    const int gi = MODE == kFitOnly ? blockIdx.x * kFitWarps + warp : blockIdx.x;
     const int K = sc.topk;
     const int cap = geo.num_levels * K;
     // the grid covers the call's GT capacity; the step's own count lives in device memory
@@ -984,6 +1004,8 @@ select_gmm_kernel(const Geometry geo, const GtOffsets* __restrict__ gop, const i
 #ifdef PAA_PROFILE_GMM
     const long long prof_t0 = clock64();
 #endif
+    int n_cand = 0;
+    if (MODE != kFitOnly) {
     // ---- phase 1: warp l = level l (loss.py:160-172) ------------------------------------------------
     {
         const int l = warp;
@@ -1066,7 +1088,6 @@ select_gmm_kernel(const Geometry geo, const GtOffsets* __restrict__ gop, const i
     if (warp != 0) return;
 
     // ---- phase 2 (warp 0): concatenate the levels, sort, fit, label --------------------------------
-    int n_cand = 0;
     for (int l = 0; l < geo.num_levels; ++l) {
         const int cnt = s_cnt[l];
         if (lane < cnt) s_key[n_cand + lane] = s_level[l][lane];
@@ -1079,8 +1100,16 @@ select_gmm_kernel(const Geometry geo, const GtOffsets* __restrict__ gop, const i
         int rank = 0;
         for (int q = 0; q < n_cand; ++q) rank += (s_key[q] < kj) ? 1 : 0;
         s_sorted[rank] = kj;
+        if (MODE == kSelectOnly) cand_sorted[(size_t)gi * PAA_MAX_CANDIDATES + rank] = kj;
     }
     __syncwarp();
+    if (MODE == kSelectOnly) {
+        if (lane == 0) cand_n[gi] = n_cand;
+        return;
+    }
+    } else {
+        n_cand = __ldg(cand_n + gi);
+    }
 
 #ifdef PAA_PROFILE_GMM
     const long long prof_t1 = clock64();
@@ -1099,7 +1128,8 @@ select_gmm_kernel(const Geometry geo, const GtOffsets* __restrict__ gop, const i
         pa[k] = make_float4(0.f, 0.f, 1.f, 1.f);
         pd[k] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (j < n_cand) {
-            const unsigned long long key = s_sorted[j];
+            const unsigned long long key = MODE == kFitOnly ? __ldg(cand_sorted + (size_t)gi * PAA_MAX_CANDIDATES + j)
+                                                            : s_sorted[j];
             aidx[k] = (int)(key & 0xffffffffu);
             x[k] = from_ordered_bits((unsigned)(key >> 32));
             if (sc.use_iou_pred) {
@@ -1280,14 +1310,28 @@ int launch_select_gmm(const Geometry& geo, const float* gt_boxes,
     const int threads = geo.num_levels * PAA_WARP;
     const GtOffsets* gop = ws.go;
     KernelTimer timer(PAA_KERNEL_SELECT_GMM, stream);
-#define PAA_SEL_LAUNCH(SPL)                                                                           \
-    PAA_PDL_LAUNCH(select_gmm_kernel<SPL>, grid, threads, stream, geo, gop, ws.gt_image, gt_boxes, gt_labels, sc, \
+#define PAA_SEL_LAUNCH_MODE(SPL, MODE, G, T)                                                           \
+    PAA_PDL_LAUNCH((select_gmm_kernel<SPL, MODE>), G, T, stream, geo, gop, ws.gt_image, gt_boxes, gt_labels, sc, \
         ws.tile_gtmask, ws.matched, score_src, ws.seg_count, ws.seg_pool, ws.paa_label, ws.pos_list, ws.part_npos, \
         ws.part_siou,                                                                                  \
-        ws.ticket, ws.local_norm, normalisers, px, dbg)
+        ws.ticket, ws.local_norm, normalisers, px, dbg, ws.cand_sorted, ws.cand_n)
+    // measurement switch: selection and fit as two launches (see the kernel's comment for the verdict)
+    int split_above = kSplitAboveGts;
+    if (const char* e = getenv("PAA_GMM_SPLIT_ABOVE")) split_above = atoi(e);       // measurement switch
+    const bool split = grid > split_above;
+#define PAA_SEL_LAUNCH(SPL)                                                                            \
+    do {                                                                                               \
+        if (split) {                                                                                   \
+            PAA_SEL_LAUNCH_MODE(SPL, kSelectOnly, grid, threads);                                      \
+            PAA_SEL_LAUNCH_MODE(SPL, kFitOnly, (grid + kFitWarps - 1) / kFitWarps, kFitWarps * PAA_WARP); \
+        } else {                                                                                       \
+            PAA_SEL_LAUNCH_MODE(SPL, kSelectFused, grid, threads);                                     \
+        }                                                                                              \
+    } while (0)
     if (cap <= 32) PAA_SEL_LAUNCH(1);
     else if (cap <= 64) PAA_SEL_LAUNCH(2);
     else PAA_SEL_LAUNCH(4);
+#undef PAA_SEL_LAUNCH_MODE
 #undef PAA_SEL_LAUNCH
     return 0;
 }

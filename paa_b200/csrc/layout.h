@@ -33,6 +33,8 @@ struct LossWorkspace {
     int* pos_list;          // [sumG*PAA_MAX_CANDIDATES] anchors of every GT's positive prefix (stride = levels * topk)
     GtOffsets* go;          // the step's per-image GT ranges as every kernel reads them (written by prep_step_kernel)
     int* gt_image;          // [sumG]   image of every GT
+    unsigned long long* cand_sorted;   // [sumG*PAA_MAX_CANDIDATES] two-launch selection: every GT's sorted candidate keys
+    int* cand_n;            // [sumG]   ... and their number
     size_t total_bytes;
 };
 
@@ -71,6 +73,9 @@ inline LossWorkspace carve_loss_workspace(void* base, int N, int A, int sumG, in
     w.pos_list = reinterpret_cast<int*>(take(sizeof(int) * (size_t)(sumG > 0 ? sumG : 1) * 128));
     w.go = reinterpret_cast<GtOffsets*>(take(kGtOffsetsBytes));
     w.gt_image = reinterpret_cast<int*>(take(sizeof(int) * (size_t)(sumG > 0 ? sumG : 1)));
+    w.cand_sorted = reinterpret_cast<unsigned long long*>(
+        take(sizeof(unsigned long long) * (size_t)(sumG > 0 ? sumG : 1) * 128));
+    w.cand_n = reinterpret_cast<int*>(take(sizeof(int) * (size_t)(sumG > 0 ? sumG : 1)));
     w.total_bytes = off;
     return w;
 }

@@ -196,6 +196,30 @@ def test_c5_multiscale_against_oracle():
     _assert_matches_oracle(b, max_exempt=2)
 
 
+@pytest.mark.parametrize("topk", [3, 9, 20])
+def test_two_launch_selection_equals_fused(monkeypatch, topk):
+    """Calls sized for thousands of GTs run the per-GT program as two launches (selection, then the fit with one
+    warp per GT: select_gmm_kernel MODE 1 / 2); it must give bit for bit what the fused block-per-GT form gives --
+    labels, per-GT fit parameters, losses and gradients -- here forced on a small batch, and against the oracle."""
+    b = synthetic.make_batch(seed=333 + topk, num_images=3, image_hw=(416, 512), gt_per_image=(2, 25))
+    outs = []
+    for split_above in ("1000000", "0"):
+        monkeypatch.setenv("PAA_GMM_SPLIT_ABOVE", split_above)
+        ev = _evaluator(TOPK=topk)
+        ev.debug = True
+        losses, cls, reg, iou = _run(ev, b)
+        d = ev.last_debug
+        outs.append((d, [float(x) for x in losses], [t.grad.clone() for t in cls + reg + iou]))
+    (d0, l0, g0), (d1, l1, g1) = outs
+    for k in ("matched_idx", "paa_labels", "cand_idx", "cand_cnt", "num_pos", "gmm", "normalisers"):
+        assert torch.equal(d0[k], d1[k]), k
+    assert l0 == l1
+    for a, c in zip(g0, g1):
+        assert torch.equal(a, c)
+    monkeypatch.setenv("PAA_GMM_SPLIT_ABOVE", "0")
+    _assert_matches_oracle(b, max_exempt=2, TOPK=topk)
+
+
 def _check_full_size_properties(b):
     """Size-independent checks: determinism, positives are candidates matched to their GT, every GT with
     candidates gets >= 1 positive, and the batch splits into halves with identical labels and additive

@@ -6,7 +6,11 @@ import numpy as np, torch
 import paa_b200
 from paa_b200 import synthetic
 from paa_b200.synthetic import to_device_inputs
-b = synthetic.make_batch(seed=2000, num_images=16, image_hw=(800, 1333), gt_per_image=(1, 100))
+if os.environ.get("GMM_PROFILE_SHAPE", "C2") == "C3":        # the dense-crowd shape, throughput-bound
+    b = synthetic.make_batch(seed=3000, num_images=int(os.environ.get("GMM_PROFILE_IMAGES", "32")),
+                             image_hw=(1333, 1333), gt_per_image=500)
+else:
+    b = synthetic.make_batch(seed=2000, num_images=16, image_hw=(800, 1333), gt_per_image=(1, 100))
 cfg = paa_b200.default_cfg()
 ev = paa_b200.make_paa_loss_evaluator(cfg, paa_b200.BoxCoder(cfg))
 ev.debug = True
@@ -14,6 +18,13 @@ cls, reg, iou, targets, anchors = to_device_inputs(b)
 for _ in range(3):
     ev(cls, reg, iou, targets, anchors, None)
 torch.cuda.synchronize()
+ev.debug = False
+t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+t0.record()
+for _ in range(5):
+    ev(cls, reg, iou, targets, anchors, None)
+t1.record(); torch.cuda.synchronize()
+print("eager step (no debug outputs): %.1f us" % (t0.elapsed_time(t1) * 200))
 g = ev.last_debug["gmm"].cpu().numpy()
 cnt = ev.last_debug["cand_cnt"].cpu().numpy()
 scan, em, it = g[:, 0], g[:, 1], g[:, 6]

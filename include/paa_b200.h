@@ -203,6 +203,28 @@ typedef struct PaaPostArgs {
     float decode_clip;            /* PAA_DECODE_LEGACY: bbox_xform_clip (log(1000/16)) */
     int32_t head_layout;          /* PAA_LAYOUT_NCHW (0) or PAA_LAYOUT_NHWC */
 } PaaPostArgs;
+/* The plain RPN loss (paa_core/modeling/rpn/loss.py:98-137) over a GIVEN sample of anchors.  The Matcher result comes
+ * from paa_retinanet_assign (unit GT labels; dbg_matched_idx), the sample from the caller's balanced sampler
+ * (balanced_positive_negative_sampler.py: torch.randperm).  Enqueues memsets of the gradient tensors and one kernel. */
+typedef struct PaaRpnArgs {
+    int32_t num_images;
+    int32_t num_levels;
+    int32_t anchors_per_loc;
+    int32_t head_layout;          /* PAA_LAYOUT_NCHW / PAA_LAYOUT_NHWC */
+    int64_t anchor_image_stride;
+    PaaLevel levels[PAA_MAX_LEVELS];  /* box_cls = objectness [N, a, H, W], box_regression [N, a*4, H, W], iou_pred NULL;
+                                         grad_box_cls / grad_box_regression nullable (no gradients) */
+    const float* gt_boxes;        /* device [sum G, 4] xyxy */
+    int32_t gt_offsets[PAA_MAX_IMAGES + 1];   /* HOST values */
+    const int32_t* matched_idx;   /* device [N, A]: GT index within the image of every anchor (>= 0 for the positives) */
+    const int64_t* sampled;       /* device [n_pos + n_neg]: image * A + anchor of the sampled anchors, positives first */
+    int32_t n_pos, n_neg;
+    float box_code_weights[4];    /* BoxCoder weights (1, 1, 1, 1 for the RPN) */
+    float smooth_l1_beta;         /* 1 / 9 */
+    int32_t reserved;
+    float* losses;                /* device [2] = objectness_loss, box_loss */
+    const float* grad_losses;     /* device [2] upstream gradients or NULL for ones */
+} PaaRpnArgs;
 #define PAA_LOSS_PAA  0
 #define PAA_LOSS_ATSS 1
 #define PAA_LOSS_RETINANET 2
@@ -239,6 +261,7 @@ int paa_assign_loss(const PaaLossArgs* args, void* stream);
  * grad_x *= new_grad_losses[j] / old_grad_losses[j]; both are device [3]. */
 int paa_rescale_grads(const PaaLossArgs* args, const float* old_grad_losses,
                       const float* new_grad_losses, void* stream);
+int paa_rpn_loss(const PaaRpnArgs* args, void* stream);
 
 int paa_postprocess(const PaaPostArgs* args, void* stream);
 

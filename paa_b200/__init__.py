@@ -14,7 +14,8 @@ __all__ = ["BoxCoder", "BoxList", "boxlist_iou", "cat_boxlist", "default_cfg", "
            "AnchorGenerator", "make_atss_postprocessor", "ATSSPostProcessor", "make_retinanet_postprocessor",
            "RetinaNetPostProcessor", "make_fcos_postprocessor", "FCOSPostProcessor", "make_atss_loss_evaluator",
            "ATSSLossComputation", "make_retinanet_loss_evaluator", "RetinaNetLossComputation",
-           "make_fcos_loss_evaluator", "FCOSLossComputation"]
+           "make_fcos_loss_evaluator", "FCOSLossComputation", "make_rpn_loss_evaluator", "RPNLossComputation",
+           "BalancedPositiveNegativeSampler"]
 
 
 def __getattr__(name):
@@ -30,6 +31,9 @@ def __getattr__(name):
                 "FCOSPostProcessor"):
         from paa_b200 import inference
         return getattr(inference, name)
+    if name in ("make_rpn_loss_evaluator", "RPNLossComputation", "BalancedPositiveNegativeSampler"):
+        from paa_b200 import rpn_loss
+        return getattr(rpn_loss, name)
     if name in ("make_anchor_generator_paa", "AnchorGenerator"):
         from paa_b200 import anchor_generator
         return getattr(anchor_generator, name)

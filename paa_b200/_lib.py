@@ -74,6 +74,15 @@ class PaaPostArgs(C.Structure):
 
 DECODE_ATSS_BOX, DECODE_LEGACY, DECODE_LTRB = 0, 1, 2
 LOSS_PAA, LOSS_ATSS, LOSS_RETINANET, LOSS_FCOS = 0, 1, 2, 3
+class PaaRpnArgs(C.Structure):
+    _fields_ = [("num_images", C.c_int32), ("num_levels", C.c_int32), ("anchors_per_loc", C.c_int32),
+                ("head_layout", C.c_int32), ("anchor_image_stride", C.c_int64), ("levels", PaaLevel * MAX_LEVELS),
+                ("gt_boxes", C.c_void_p), ("gt_offsets", C.c_int32 * (MAX_IMAGES + 1)), ("matched_idx", C.c_void_p),
+                ("sampled", C.c_void_p), ("n_pos", C.c_int32), ("n_neg", C.c_int32),
+                ("box_code_weights", C.c_float * 4), ("smooth_l1_beta", C.c_float), ("reserved", C.c_int32),
+                ("losses", C.c_void_p), ("grad_losses", C.c_void_p)]
+
+
 ATSS_POSITIVE_TYPES = {"ATSS": 0, "SSC": 1, "IoU": 2}
 IOU_LOSS_TYPES = {"iou": 0, "linear_iou": 1, "giou": 2}
 
@@ -91,6 +100,7 @@ SYMBOLS = {
     "paa_fcos_assign": (C.c_int, [C.POINTER(PaaLossArgs), C.c_void_p]),
     "paa_assign_loss": (C.c_int, [C.POINTER(PaaLossArgs), C.c_void_p]),
     "paa_rescale_grads": (C.c_int, [C.POINTER(PaaLossArgs), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "paa_rpn_loss": (C.c_int, [C.POINTER(PaaRpnArgs), C.c_void_p]),
     "paa_postprocess": (C.c_int, [C.POINTER(PaaPostArgs), C.c_void_p]),
     "paa_ml_nms_workspace_bytes": (C.c_size_t, [C.c_int]),
     "paa_ml_nms": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_void_p,

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libpaa_b200.so")
 STAMP_PATH = LIB_PATH + ".stamp"
-SOURCES = ["abi.cu", "assign.cu", "loss.cu", "post.cu", "aux.cu", "atss.cu", "retina.cu", "fcos.cu"]
+SOURCES = ["abi.cu", "assign.cu", "loss.cu", "post.cu", "aux.cu", "atss.cu", "retina.cu", "fcos.cu", "rpn.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xptxas=-v", "-Xcompiler", "-fPIC", "-shared",
               "-cudart", "shared"]

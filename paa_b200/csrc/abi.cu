@@ -475,6 +475,32 @@ size_t paa_postprocess_workspace_bytes(int num_images, int anchors_per_image, in
     return post_workspace_bytes(num_images, anchors_per_image, num_classes, num_levels, pre_nms_top_n);
 }
 
+int paa_rpn_loss(const PaaRpnArgs* a, void* stream) {
+    if (!a) {
+        set_error("null PaaRpnArgs");
+        return PAA_ERR_BAD_ARGUMENT;
+    }
+    Geometry geo;
+    int rc = build_geometry(a->num_images, a->num_levels, 1, a->anchors_per_loc, a->anchor_image_stride, a->levels,
+                            false, a->head_layout, &geo);
+    if (rc) return rc;
+    if (a->n_pos < 0 || a->n_neg < 0 || !a->losses || !a->gt_boxes || !a->matched_idx ||
+        ((a->n_pos + a->n_neg) > 0 && !a->sampled)) {
+        set_error("paa_rpn_loss: null pointer or negative sample size (n_pos=%d, n_neg=%d)", a->n_pos, a->n_neg);
+        return PAA_ERR_BAD_ARGUMENT;
+    }
+    if (!(a->smooth_l1_beta > 0.0f)) {
+        set_error("paa_rpn_loss: smooth_l1_beta=%g must be positive", (double)a->smooth_l1_beta);
+        return PAA_ERR_BAD_ARGUMENT;
+    }
+    GtOffsets go;
+    memset(&go, 0, sizeof(go));
+    for (int i = 0; i <= a->num_images; ++i) go.v[i] = a->gt_offsets[i];
+    return launch_rpn_loss(geo, go, a->gt_boxes, a->matched_idx, reinterpret_cast<const long long*>(a->sampled),
+                           a->n_pos, a->n_neg, a->box_code_weights, a->smooth_l1_beta, a->grad_losses, a->losses,
+                           static_cast<cudaStream_t>(stream));
+}
+
 int paa_postprocess(const PaaPostArgs* args, void* stream) {
     if (!args) {
         set_error("null PaaPostArgs");

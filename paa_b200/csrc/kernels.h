@@ -86,6 +86,10 @@ int launch_retinanet_assign(const Geometry& geo, const float* gt_boxes, const in
                             const LossScalars& sc, const LossWorkspace& ws, double* normalisers, const LossDebug& dbg,
                             cudaStream_t stream, bool atss_iou = false, const PeerExchange* px = nullptr);
 
+// rpn.cu
+int launch_rpn_loss(const Geometry& geo, const GtOffsets& go, const float* gt_boxes, const int* matched,
+                    const long long* sampled, int n_pos, int n_neg, const float* weights, float beta,
+                    const float* grad_losses, float* losses, cudaStream_t stream);
 // aux.cu
 int launch_selftest_roots(const float* x, int n, float* out, cudaStream_t stream);
 // loss.cu

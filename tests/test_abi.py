@@ -36,12 +36,17 @@ def test_struct_layout_matches_header(tmp_path):
     fields_post = ["num_images", "pre_nms_thresh", "anchor_image_stride", "levels", "image_wh", "workspace",
                    "out_boxes", "out_count", "dbg_pre_boxes", "dbg_nms_keep", "box_decode", "decode_weights",
                    "decode_clip", "head_layout"]
+    fields_rpn = ["num_images", "head_layout", "anchor_image_stride", "levels", "gt_boxes", "gt_offsets", "matched_idx",
+                  "sampled", "n_pos", "box_code_weights", "smooth_l1_beta", "losses", "grad_losses"]
     src = ['#include <stdio.h>', '#include <stddef.h>', '#include "paa_b200.h"', 'int main(void){',
            'printf("%zu %zu %zu\\n", sizeof(PaaLevel), sizeof(PaaLossArgs), sizeof(PaaPostArgs));']
     for f in fields_loss:
         src.append('printf("%%zu\\n", offsetof(PaaLossArgs, %s));' % f)
     for f in fields_post:
         src.append('printf("%%zu\\n", offsetof(PaaPostArgs, %s));' % f)
+    src.append('printf("%zu\\n", sizeof(PaaRpnArgs));')
+    for f in fields_rpn:
+        src.append('printf("%%zu\\n", offsetof(PaaRpnArgs, %s));' % f)
     src.append("return 0;}")
     c = tmp_path / "layout.c"
     c.write_text("\n".join(src))
@@ -57,6 +62,11 @@ def test_struct_layout_matches_header(tmp_path):
         k += 1
     for f in fields_post:
         assert sizes[k] == getattr(_lib.PaaPostArgs, f).offset, f
+        k += 1
+    assert sizes[k] == ctypes.sizeof(_lib.PaaRpnArgs)
+    k += 1
+    for f in fields_rpn:
+        assert sizes[k] == getattr(_lib.PaaRpnArgs, f).offset, f
         k += 1
 
 

@@ -45,7 +45,12 @@ struct Pass1Plan {
     int patch_rx[PAA_MAX_LEVELS];                // regions per grid row
     int patch_h[PAA_MAX_LEVELS];                 // grid height of the level
     unsigned patch_magic[PAA_MAX_LEVELS];        // floor(2^16 / patch_rx) + 1: r / patch_rx == (r * magic) >> 16 while r * patch_rx < 2^16
+    // L2 prefetch of the classification logits for match_score_kernel (PAA only; 0 pieces = off): image-major pieces
+    // of kPfPiece bytes, `pf_level_off[l]` = first piece of level l inside an image
+    unsigned pf_pieces, pf_per_image;
+    unsigned pf_level_off[PAA_MAX_LEVELS + 1];
 };
+constexpr unsigned kPfPiece = 16384;
 
 // order-preserving map float -> unsigned (and back), so that floats compare / reduce as integers
 __device__ __forceinline__ unsigned ordered_bits(float v) {
@@ -104,6 +109,28 @@ iou_match_kernel(const Geometry geo, const GtOffsets* __restrict__ gop, const Pa
                  unsigned long long* __restrict__ best) {
     PAA_TRACE_SCOPE(1);
     pdl_launch_dependents();
+    // This kernel is bound by instruction issue and moves half a megabyte: the memory system idles under it.  The next
+    // kernel (match_score_kernel) waits on the latency of its class-row loads, so the logits it will read first --
+    // image by image, in its own block order -- are pulled towards the L2 from here (bulk prefetch, one instruction
+    // per 16 KB piece, issued by one thread per block before the dependency wait: the logits do not depend on
+    // anything this step computes).
+    if (plan.pf_pieces && threadIdx.x == 0) {
+        const unsigned nblk = gridDim.x * gridDim.y;
+        for (unsigned p = blockIdx.y * gridDim.x + blockIdx.x; p < plan.pf_pieces; p += nblk) {
+            const unsigned img = p / plan.pf_per_image, r = p - img * plan.pf_per_image;
+            int l = 0;
+#pragma unroll 1
+            for (int k = 1; k < geo.num_levels; ++k)
+                if (r >= plan.pf_level_off[k]) l = k;
+            const unsigned long long level_bytes = (unsigned long long)geo.lv[l].n_anchor * geo.C * 4ull;
+            const unsigned long long first = (unsigned long long)(r - plan.pf_level_off[l]) * kPfPiece;
+            const unsigned long long left = level_bytes - first;
+            const unsigned bytes = (unsigned)(left < kPfPiece ? left : kPfPiece) & ~15u;
+            const char* src = reinterpret_cast<const char*>(geo.lv[l].cls) + (unsigned long long)img * level_bytes + first;
+            if (bytes && (reinterpret_cast<uintptr_t>(src) & 15u) == 0)
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+        }
+    }
     pdl_wait();                       // the GT ranges and the cleared maxima come from prep_step_kernel
     PAA_TRACE_WAITED();
     __shared__ WarpGts s_gts[kPassThreads / PAA_WARP];
@@ -335,6 +362,28 @@ int launch_iou_match(const Geometry& geo, const float* gt_boxes, const LossScala
     if (regions == 0) plan.patches = 0;
     const unsigned light_items = plan.patches ? regions : (unsigned)plan.light_pairs;
     plan.iou_blocks = light_items + (unsigned)(plan.heavy_pairs * plan.parts);          // per image
+    // PAA: the logits of the first images of the call towards the L2 while this kernel runs (see the kernel)
+    plan.pf_pieces = 0;
+    plan.pf_per_image = 1;
+    for (int l = 0; l <= PAA_MAX_LEVELS; ++l) plan.pf_level_off[l] = 0;
+    if (sc.flavour == PAA_LOSS_PAA) {
+        unsigned per_image = 0;
+        for (int l = 0; l < PAA_MAX_LEVELS; ++l) {
+            plan.pf_level_off[l] = per_image;
+            if (l < geo.num_levels)
+                per_image += (unsigned)(((unsigned long long)geo.lv[l].n_anchor * geo.C * 4ull + kPfPiece - 1) / kPfPiece);
+        }
+        plan.pf_level_off[PAA_MAX_LEVELS] = per_image;
+        plan.pf_per_image = per_image ? per_image : 1;
+        // Measured (C2, tools/step_trace.py, profiles/r2_match_prefetch.txt): with 2 images per rank (14 MB of logits)
+        // match_score_kernel 13.8 -> 11.3 us and the step 73.7 -> 72.4 us; with 16 images any budget from 16 to 128 MB
+        // gives back in this kernel's issue slots (13.1 -> 14-16.6 us) what it saves in the next (36.2 -> 34.3 us).
+        int budget_mb = 16;
+        if (const char* e = getenv("PAA_MATCH_PREFETCH_MB")) budget_mb = atoi(e);      // measurement switch
+        const unsigned long long want = (unsigned long long)budget_mb * (1ull << 20) / kPfPiece;
+        const unsigned long long all = (unsigned long long)per_image * (unsigned)geo.num_images;
+        plan.pf_pieces = (unsigned)(want < all ? want : all);
+    }
     const GtOffsets* gop = ws.go;
     unsigned long long* best = reinterpret_cast<unsigned long long*>(ws.best);
     KernelTimer timer(PAA_KERNEL_PASS1, stream);

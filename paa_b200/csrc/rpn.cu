@@ -55,7 +55,7 @@ rpn_loss_kernel(const Geometry geo, const GtOffsets go, const float* __restrict_
             lv.g_cls[o_off] = (sig - y) * inv * g_obj;
         }
         if (positive) {
-            const int m = matched[flat];
+            const int m = max(matched[flat], 0);          // rpn/loss.py:51: matched_idxs.clamp(min=0)
             const float4 anc = ldg4(lv.anchors + (size_t)n * geo.anchor_image_stride + (size_t)i * 4);
             const float4 gt = ldg4(gt_boxes + (size_t)(go.v[n] + m) * 4);
             const float4 t = encode_box_legacy(gt, anc, wx, wy, ww, wh);

@@ -191,3 +191,31 @@ def test_channels_last_postprocessor_equals_nchw():
         assert torch.equal(a.get_field("scores"), c.get_field("scores"))
         assert torch.equal(a.get_field("labels"), c.get_field("labels"))
     assert sum(len(a.bbox) for a in outs[0]) > 0
+
+
+def test_channels_last_graph_mode_replays_on_new_targets():
+    """Graph mode (one captured step replayed for every new target set) on channels-last heads: bit-identical to the
+    eager launches, gradients in the heads' memory format."""
+    import dataclasses
+    import paa_b200
+    kw = dict(num_images=2, image_hw=(384, 512))
+    heads = synthetic.make_batch(seed=821, gt_per_image=(3, 9), **kw)
+    other = synthetic.make_batch(seed=822, gt_per_image=(5, 30), **kw)
+    batches = [heads, dataclasses.replace(heads, gt_boxes=other.gt_boxes, gt_labels=other.gt_labels)]
+    cfg = paa_b200.default_cfg()
+    ev_g = paa_b200.make_paa_loss_evaluator(cfg, paa_b200.BoxCoder(cfg))
+    ev_g.use_graph = True
+    ev_e = paa_b200.make_paa_loss_evaluator(cfg, paa_b200.BoxCoder(cfg))
+    cls, reg, iou, _, anchors = to_device_inputs(heads, channels_last=True)
+    for b in batches:
+        _, _, _, targets, _ = to_device_inputs(b)
+        lg, gg = ev_g.forward_backward(cls, reg, iou, targets, anchors)
+        lg = lg.clone()
+        gg = [t.clone() for t in gg["cls"] + gg["reg"] + gg["iou"]]
+        le, ge = ev_e.forward_backward(cls, reg, iou, targets, anchors)
+        torch.cuda.synchronize()
+        assert torch.equal(lg, le)
+        for a, c in zip(gg, ge["cls"] + ge["reg"] + ge["iou"]):
+            assert a.shape == c.shape and torch.equal(a, c)
+        assert all(t.is_contiguous(memory_format=torch.channels_last) for t in ge["cls"] + ge["reg"])
+    assert len(ev_g._graphs) == 1

@@ -1002,7 +1002,9 @@ __device__ __forceinline__ unsigned long long topk_first_batch(unsigned long lon
 //         instead of the 6 that MODE 0's five-warp blocks allow.  Built for the throughput-bound calls (C3: 16 000 GTs,
 //         216 us in this kernel) on the assumption that the fit is a latency chain that more resident warps would hide.
 //         MEASURED AND NOT KEPT AS A DEFAULT (PAA_GMM_SPLIT_ABOVE=<n> selects it for calls sized for more than n GTs;
-//         bit-identical results, tests/test_gpu_loss.py): C3 216 us against 212 us fused, C5 83 against 79 us.  Per-GT
+//         bit-identical results, tests/test_gpu_loss.py): C3 216 us against 212 us fused, C5 83 against 79 us (event-timed;
+//         inside a graph replay of 32 x 500 GT on 800x1333 images the pair takes 161 us against 243 us and the step 565
+//         against 593 us, but bench.py's C3 step does not move: 0.7259 against 0.7263 ms).  Per-GT
 //         cycle counts (tools/gmm_profile.py, GMM_PROFILE_SHAPE=C3) show why: an EM iteration costs 2290 cycles in
 //         BOTH forms on the loaded GPU (1480 when a fit has its SM sub-partition to itself), and 16 000 fits x 11.3 us
 //         / 216 us = ~840 fits in flight either way -- the fit is bound by the issue rate of the FP64 pipe (a warp-wide
@@ -1030,7 +1032,7 @@ select_gmm_kernel(const Geometry geo, const GtOffsets* __restrict__ gop, const i
                   double* __restrict__ normalisers, const PeerExchange px, const LossDebug dbg,
                   unsigned long long* __restrict__ cand_sorted, int* __restrict__ cand_n) {
     // lets the loss pass (a programmatic dependent launch) become resident and prefetch while the slowest fits run
-    PAA_TRACE_SCOPE(3);
+    PAA_TRACE_SCOPE(MODE == kFitOnly ? 6 : 3);
     pdl_wait();
     PAA_TRACE_WAITED();
     pdl_launch_dependents();
@@ -1134,6 +1136,8 @@ select_gmm_kernel(const Geometry geo, const GtOffsets* __restrict__ gop, const i
         if (lane == 0) s_cnt[l] = __popc(have);
     }
     __syncthreads();
+    // (Letting the block index pick the warp that fits -- in case "always warp 0" puts the fits of all resident blocks
+    // on one sub-partition's FP64 pipe -- was measured and is slower, profiles/r2_gmm_split_trace.txt.)
     if (warp != 0) return;
 
     // ---- phase 2 (warp 0): concatenate the levels, sort, fit, label --------------------------------

@@ -164,6 +164,7 @@ constexpr int kCandBlocksPerSM = 4;
 struct CandPlan {
     unsigned chunk_off[PAA_MAX_LEVELS + 1];     // first chunk of each level in the global chunk order
     unsigned chunks_per_image[PAA_MAX_LEVELS];
+    float inv_cpi[PAA_MAX_LEVELS];              // 1 / chunks_per_image (divmod_small)
     unsigned char vec[PAA_MAX_LEVELS];          // 16-byte loads allowed
     unsigned total;
 };
@@ -174,6 +175,8 @@ struct CandChunk {
     const float* src;
 };
 
+__device__ __forceinline__ void divmod_small(unsigned n, unsigned d, float inv, unsigned* q, unsigned* r);
+
 __device__ __forceinline__ CandChunk cand_chunk(const Geometry& geo, const CandPlan& plan, unsigned ch) {
     CandChunk k;
     k.l = 0;
@@ -181,14 +184,23 @@ __device__ __forceinline__ CandChunk cand_chunk(const Geometry& geo, const CandP
     for (int q = 1; q < PAA_MAX_LEVELS; ++q)
         if (q < geo.num_levels && ch >= plan.chunk_off[q]) k.l = q;
     const unsigned rel = ch - plan.chunk_off[k.l];
-    k.n = (int)(rel / plan.chunks_per_image[k.l]);
-    k.e_base = (rel - (unsigned)k.n * plan.chunks_per_image[k.l]) * kCandChunk;
+    unsigned n, in_image;
+    divmod_small(rel, plan.chunks_per_image[k.l], plan.inv_cpi[k.l], &n, &in_image);      // no integer division here
+    k.n = (int)n;
+    k.e_base = in_image * kCandChunk;
     k.per_image = (unsigned)(geo.apl * geo.C) * (unsigned)geo.lv[k.l].hw;      // elements of one image
     k.src = geo.lv[k.l].cls + (size_t)k.n * k.per_image;
     return k;
 }
 
 __device__ __forceinline__ void cand_load(const CandChunk& k, bool vec, float4 (&x)[kCandVecs]) {
+    if (vec && k.e_base + (unsigned)kCandChunk <= k.per_image) {
+        // the usual chunk, whole inside its image: one pointer, four loads at constant offsets (block-uniform branch)
+        const float4* p = reinterpret_cast<const float4*>(k.src + k.e_base) + threadIdx.x;
+#pragma unroll
+        for (int j = 0; j < kCandVecs; ++j) x[j] = __ldcs(p + j * kCandThreads);
+        return;
+    }
 #pragma unroll
     for (int j = 0; j < kCandVecs; ++j) {
         const unsigned e = k.e_base + (unsigned)(j * kCandThreads + threadIdx.x) * 4u;
@@ -1832,11 +1844,13 @@ int run_postprocess(const Geometry& geo, const PaaPostArgs* a, cudaStream_t stre
         for (int l = 0; l < PAA_MAX_LEVELS; ++l) {
             plan.chunk_off[l] = chunks;
             plan.chunks_per_image[l] = 1;
+            plan.inv_cpi[l] = 1.0f;
             plan.vec[l] = 0;
             if (l >= L) continue;
             const LevelView& lv = geo.lv[l];
             const unsigned long long per_image = (unsigned long long)geo.apl * C * lv.hw;
             plan.chunks_per_image[l] = (unsigned)((per_image + kCandChunk - 1) / kCandChunk);
+            plan.inv_cpi[l] = 1.0f / (float)plan.chunks_per_image[l];
             plan.vec[l] = ((per_image & 3ull) == 0 && (reinterpret_cast<uintptr_t>(lv.cls) & 15u) == 0) ? 1 : 0;
             chunks += plan.chunks_per_image[l] * (unsigned)N;
         }
@@ -1873,7 +1887,9 @@ int run_postprocess(const Geometry& geo, const PaaPostArgs* a, cudaStream_t stre
                 geo, rp, a->pre_nms_thresh, gate, w.cand, w.cand_count, w.hist);
         } else {
             unsigned grid = 148u * kCandBlocksPerSM;
+            if (const char* e = getenv("PAA_CAND_BLOCKS")) grid = 148u * (unsigned)atoi(e);     // measurement switch
             if (grid > chunks) grid = chunks;
+            if (grid < 1) grid = 1;
             post_candidates_kernel<<<grid, kCandThreads, 0, stream>>>(geo, plan, a->pre_nms_thresh, gate,
                                                                       w.cand, w.cand_count, w.hist);
         }

@@ -1000,18 +1000,22 @@ __device__ __forceinline__ unsigned long long topk_first_batch(unsigned long lon
 // MODE 1 / MODE 2: the same program cut in two launches -- MODE 1 the selection alone (block per GT, sorted candidates
 //         to memory), MODE 2 the fit alone with ONE WARP per GT, four GTs per block, i.e. 24 resident fits per SM
 //         instead of the 6 that MODE 0's five-warp blocks allow.  Built for the throughput-bound calls (C3: 16 000 GTs,
-//         216 us in this kernel) on the assumption that the fit is a latency chain that more resident warps would hide.
-//         MEASURED AND NOT KEPT AS A DEFAULT (PAA_GMM_SPLIT_ABOVE=<n> selects it for calls sized for more than n GTs;
-//         bit-identical results, tests/test_gpu_loss.py): C3 216 us against 212 us fused, C5 83 against 79 us (event-timed;
-//         inside a graph replay of 32 x 500 GT on 800x1333 images the pair takes 161 us against 243 us and the step 565
-//         against 593 us, but bench.py's C3 step does not move: 0.7259 against 0.7263 ms).  Per-GT
-//         cycle counts (tools/gmm_profile.py, GMM_PROFILE_SHAPE=C3) show why: an EM iteration costs 2290 cycles in
-//         BOTH forms on the loaded GPU (1480 when a fit has its SM sub-partition to itself), and 16 000 fits x 11.3 us
-//         / 216 us = ~840 fits in flight either way -- the fit is bound by the issue rate of the FP64 pipe (a warp-wide
-//         DFMA / DADD / DMUL every 8 cycles per sub-partition, the figure tools/lat_probe.cu reads as "dependent issue"),
-//         not by latency: more resident fits just queue on that pipe.  What would help is fewer FP64 instructions per
-//         iteration, which sklearn's float64 responsibilities / log-sum-exp (oracle/gmm_oracle.py) do not leave room for
-//         at equal iteration counts.
+//         216 us in this kernel).  MEASURED AND NOT KEPT AS A DEFAULT (PAA_GMM_SPLIT_ABOVE=<n> selects it for calls
+//         sized for more than n GTs; bit-identical results, tests/test_gpu_loss.py): event-timed, C3 216 us against
+//         212 us fused, C5 83 against 79 us; inside a graph replay of 32 x 500 GT on 800x1333 images the pair takes
+//         54 + 106 us against 243 us (step 565 against 593 us, profiles/r2_gmm_split_trace.txt), but bench.py's C3 step
+//         does not move (0.7259 against 0.7263 ms).  What the measurements say about the fit:
+//         * tools/fp64_rate_probe.cu: a dependent DFMA takes 8 cycles, a sub-partition's FP64 pipe accepts a warp-wide
+//           DFMA every 2 cycles (64 FMA/clk/SM).  A lone fit -- the tail of every step -- is a latency chain with idle
+//           issue slots (its transcendental pieces are Estrin-evaluated already, fastmath64.cuh); from four resident
+//           fits per sub-partition on, the pipe is the limit: 6 fits x ~185 FP64 instructions x 2 cycles = 2220 cycles
+//           per iteration, which is what MODE 2 measures on C3 (2290; 1480 for a fit alone; tools/gmm_profile.py,
+//           profiles/r2_gmm_c3_fused_vs_split.txt).  More residency than that buys nothing.
+//         * MODE 2's blocks live as long as the slowest of their four fits (p95 24 us against a mean of 11 us), which
+//           is most of the gap between its 106 us and the 51 us that 3552 resident fits would allow.
+//         * MODE 0 shows the same 2290 cycles per iteration under load for a reason that was not isolated (its fits
+//           share their SM with the selection warps of the blocks that keep arriving); letting the block index pick the
+//           fitting warp, in case warp 0 of every block lands on one sub-partition, changed nothing.
 constexpr int kSelectFused = 0, kSelectOnly = 1, kFitOnly = 2;
 constexpr int kSplitAboveGts = 0x7fffffff; // two-launch form off unless PAA_GMM_SPLIT_ABOVE asks for it (see above)
 constexpr int kFitWarps = 4;

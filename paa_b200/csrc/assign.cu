@@ -481,6 +481,23 @@ match_score_kernel(const Geometry geo, const GtOffsets* __restrict__ gop, const 
     if (!(bval >= thr) && !(bval < thr)) m = bgt;          // NaN: neither below nor restored -> keeps argmax
 
     const int C = geo.C;
+    // The kernel is a chain of memory round trips (ten per block before this reordering), so everything whose
+    // address is known early is requested early.  The matched GT can only be the best GT (`m` ends up as bgt or -1):
+    // its label, its box and this anchor's regression outputs are asked for now -- the label as a load that completes
+    // under the low-quality pass, the others as L2 prefetches (no registers held across the class sums).
+    int label_of_best = 0;
+    if (valid) {
+        label_of_best = (int)__ldg(gt_labels + gbase + bgt);
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(gt_boxes + (size_t)(gbase + bgt) * 4));
+        const float* rp0 = lv.reg + head_offset(geo, lv, n, i, 0, 4);
+        const size_t cs0 = head_cstride(geo, lv);
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(rp0));
+        if (cs0 > 8) {                                     // NCHW: the four channels live in four planes
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(rp0 + cs0));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(rp0 + 2 * cs0));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(rp0 + 3 * cs0));
+        }
+    }
 
     // low-quality GTs (max IoU below thr) restore their best anchors
     for (int c0 = 0; c0 < G; c0 += PAA_TILE) {
@@ -504,9 +521,21 @@ match_score_kernel(const Geometry geo, const GtOffsets* __restrict__ gop, const 
         __syncthreads();
     }
     if (!valid) m = -1;
-    int label = 0;
-    if (m >= 0) label = (int)gt_labels[gbase + m];
+    const int label = m >= 0 ? label_of_best : 0;           // m is bgt or -1
     const bool positive = m >= 0 && label > 0;
+    // the candidate-pool slot is reserved here (its atomic returns under the class sums), the key is stored at the end
+    int pool_slot = -1;
+    const int seg = positive ? (gbase + m) * geo.num_levels + l : -1;
+    {
+        // consecutive anchors mostly share their GT: one atomic per (warp, segment) instead of one per anchor
+        const unsigned peers = __match_any_sync(PAA_FULL, seg);
+        const int leader = __ffs(peers) - 1;
+        int first = 0;
+        if (positive && lane == leader) first = atomicAdd(&seg_count[seg], __popc(peers));
+        first = __shfl_sync(PAA_FULL, first, leader);
+        if (positive) pool_slot = first + __popc(peers & ((1u << lane) - 1u));
+        if (positive) asm volatile("prefetch.global.L2 [%0];" ::"l"(lv.cls + head_offset(geo, lv, n, i, label - 1, C)));
+    }
     // which GTs (index mod 128) have matched anchors in this tile: lets the per-GT selection kernel
     // skip every tile that cannot contain one of its anchors, with no false negatives
     if (m >= 0) atomicOr(&s_mask[(m & 127) >> 5], 1u << (m & 31));
@@ -624,15 +653,8 @@ match_score_kernel(const Geometry geo, const GtOffsets* __restrict__ gop, const 
         // hand the anchor to its (GT, level) candidate pool: the per-GT selection then reads one short
         // contiguous list instead of searching the image for its anchors
         const float key_score = teacher_score ? teacher_score[flat] : s;
-        const int seg = (gbase + m) * geo.num_levels + l;
-        // consecutive anchors mostly share their GT: one atomic per (warp, segment) instead of one per anchor
-        const unsigned peers = __match_any_sync(__activemask(), seg);
-        const int leader = __ffs(peers) - 1;
-        int slot = 0;
-        if (lane == leader) slot = atomicAdd(&seg_count[seg], __popc(peers));
-        slot = __shfl_sync(peers, slot, leader) + __popc(peers & ((1u << lane) - 1u));
-        if (slot < sc.seg_cap)
-            seg_pool[(size_t)seg * kSegCap + slot] =
+        if (pool_slot < sc.seg_cap)
+            seg_pool[(size_t)seg * kSegCap + pool_slot] =
                 ((unsigned long long)ordered_bits(key_score) << 32) | (unsigned)(lv.a_off + i);
     }
     if (valid && dbg.combined_loss) dbg.combined_loss[flat] = s;

@@ -511,7 +511,9 @@ def roofline_report(kernel_table, per_kernel, A, C, n_img, step_ms, step_bytes_p
             "algorithmic_bytes_per_step": step_bytes_per_image * n_img,
             "traffic": (sum(r.get("traffic", 0) for r in rows) or None) if same_shape else None,
             "traffic_source": ("static: dram__bytes_read.sum + dram__bytes_write.sum summed over the step's kernels, "
-                               "ncu --set full capture of this command, profiles/%s" % traffic_file) if same_shape and traffic
+                               "from the committed ncu --set full capture of the same kernels on the same batch "
+                               "(tools/loss_once.py / tools/post_once.py, tools/capture_r2z.sh), profiles/%s"
+                               % traffic_file) if same_shape and traffic
             else "no capture of this shape committed",
             "peak_source": peak_src, "per_kernel": rows}
 

@@ -725,6 +725,16 @@ class LossRun(object):
         for _ in range(warmup):
             step()
         ctx.barrier()
+        if os.environ.get("PAA_BENCH_PROFILE"):          # measurement aid: where the host time of an e2e step goes
+            import cProfile
+            import pstats
+            prof = cProfile.Profile()
+            prof.enable()
+            for _ in range(50):
+                step()
+            prof.disable()
+            torch.cuda.synchronize()
+            pstats.Stats(prof, stream=sys.stderr).sort_stats("cumulative").print_stats(35)
         e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         e_start.record()

@@ -38,6 +38,59 @@ __global__ void __launch_bounds__(1024) flat_kernel(const float4* __restrict__ s
     if (cnt) atomicAdd(out, (unsigned long long)cnt);
 }
 
+// load flavours: 0 = __ldcs (ld.global.cs), 1 = __ldg (ld.global.nc), 2 = ld.global.nc.L1::no_allocate.L2::256B,
+// 3 = ld.global.nc.L2::256B, 4 = plain ld.global
+template <int F>
+__device__ __forceinline__ float4 load_f(const float4* p) {
+    float4 v;
+    if (F == 0) return __ldcs(p);
+    if (F == 1) return __ldg(p);
+    if (F == 2)
+        asm volatile("ld.global.nc.L1::no_allocate.L2::256B.v4.f32 {%0,%1,%2,%3}, [%4];"
+                     : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    if (F == 3)
+        asm volatile("ld.global.nc.L2::256B.v4.f32 {%0,%1,%2,%3}, [%4];"
+                     : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    if (F == 4)
+        asm volatile("ld.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+
+template <int U, int F>
+__global__ void __launch_bounds__(1024) flavour_kernel(const float4* __restrict__ src, size_t n4, float gate,
+                                                       unsigned long long* __restrict__ out) {
+    unsigned cnt = 0;
+    const size_t T = blockDim.x;
+    const size_t stride = (size_t)gridDim.x * T * U;
+    size_t base = (size_t)blockIdx.x * T * U + threadIdx.x;
+    const float4 pad = make_float4(-1e30f, -1e30f, -1e30f, -1e30f);
+    float4 x[U], nx[U];
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+        const size_t i = base + (size_t)j * T;
+        x[j] = i < n4 ? load_f<F>(src + i) : pad;
+    }
+    for (; base < n4; base += stride) {
+        const size_t nb = base + stride;
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            const size_t i = nb + (size_t)j * T;
+            nx[j] = i < n4 ? load_f<F>(src + i) : pad;
+        }
+        float mx = -1e30f;
+#pragma unroll
+        for (int j = 0; j < U; ++j) mx = fmaxf(mx, fmaxf(fmaxf(x[j].x, x[j].y), fmaxf(x[j].z, x[j].w)));
+        if (mx > gate) {
+#pragma unroll
+            for (int j = 0; j < U; ++j)
+                cnt += (x[j].x > gate) + (x[j].y > gate) + (x[j].z > gate) + (x[j].w > gate);
+        }
+#pragma unroll
+        for (int j = 0; j < U; ++j) x[j] = nx[j];
+    }
+    if (cnt) atomicAdd(out, (unsigned long long)cnt);
+}
+
 // prefetch-one-chunk-ahead variant (the structure of post_candidates_kernel without its queue)
 template <int U>
 __global__ void __launch_bounds__(1024) ahead_kernel(const float4* __restrict__ src, size_t n4, float gate,
@@ -208,6 +261,8 @@ int main() {
 #define AHEAD(U, B, T) timeit("one chunk ahead U=" #U " blocks/SM=" #B " threads=" #T, [&] { ahead_kernel<U><<<148 * B, T>>>(s4, n4, gate, out); })
     AHEAD(4, 4, 256); AHEAD(4, 2, 256); AHEAD(8, 2, 256); AHEAD(8, 1, 256); AHEAD(4, 1, 512); AHEAD(8, 1, 512); AHEAD(4, 1, 1024);
     AHEAD(8, 1, 1024); AHEAD(4, 2, 512); AHEAD(4, 3, 256);
+#define FLAV(F) timeit("one chunk ahead U=4 blocks/SM=4 threads=256 flavour " #F, [&] { flavour_kernel<4, F><<<148 * 4, 256>>>(s4, n4, gate, out); })
+    FLAV(0); FLAV(1); FLAV(2); FLAV(3); FLAV(4);
 #define RING(S, KB, B)                                                                                            \
     do {                                                                                                          \
         CK(cudaFuncSetAttribute(ring_kernel<S, KB * 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, S * KB * 1024)); \

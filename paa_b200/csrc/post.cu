@@ -1232,9 +1232,6 @@ post_nms_runs_kernel(int capN, int segs_per_image, int num_images, float thr, co
         const bool valid = r < b;
         const float4 box = valid ? s_box[base + r] : nowhere;
         const float area = valid ? area_plus1(box) : 1.0f;
-        gb[lane] = box;
-        ga[lane] = area;
-        __syncwarp();
         // (1) suppressed by a box kept earlier in the run?  Four independent tests per trip.
         bool dead = !valid;
         for (int i = 0; i < nk; i += 4) {
@@ -1251,48 +1248,70 @@ post_nms_runs_kernel(int capN, int segs_per_image, int num_images, float thr, co
                 if (u3) dead = dead || (iou_plus1(kb[i + 3], ka[i + 3], box, area) > thr);
             }
         }
-        const unsigned removed0 = __ballot_sync(PAA_FULL, dead);
-        // (2) the pairs inside the group, each evaluated once: in trip t lane l takes the pair (l, (l + t) mod 32);
-        // trips 1..15 cover every pair whose cyclic distance is below 16 exactly once, trip 16 (lanes 0..15) the
-        // rest.  Bit j of lane i's word <=> box j > i overlaps box i by more than thr; the lane that evaluated a pair
-        // whose smaller index is not its own hands the result over through the trip's ballot.
-        unsigned m = 0u;
-#pragma unroll 4
-        for (int t = 1; t <= 16; ++t) {
-            const int c = (lane + t) & 31;
-            const bool active = (t < 16 || lane < 16) && !dead && (((removed0 >> c) & 1u) == 0u);
-            bool unsure;
-            bool hit = iou_certain(box, area, gb[c], ga[c], gate, &unsure);
-            if (active && unsure) hit = iou_plus1(box, area, gb[c], ga[c]) > thr;
-            hit = hit && active;
-            const unsigned hits = __ballot_sync(PAA_FULL, hit);
-            if (hit && c > lane) m |= 1u << c;
-            const int from = (lane - t) & 31;          // the lane whose pair of this trip has me as its column
-            if (from > lane && ((hits >> from) & 1u)) m |= 1u << from;
+        // The boxes that are still alive are packed to the front (order kept: best score first): what follows works
+        // on n_a <= 32 of them, usually about half a group.
+        const unsigned alive = ~__ballot_sync(PAA_FULL, dead);
+        const int n_a = __popc(alive);
+        const int mine_c = __popc(alive & ((1u << lane) - 1u));           // my packed index if I am alive
+        if (!dead) {
+            gb[mine_c] = box;
+            ga[mine_c] = area;
         }
-        // (3) greedy scan of the group, best score first: the 32 words are fetched up front (independent shuffles),
+        __syncwarp();
+        const bool act = lane < n_a;
+        const float4 cbox = act ? gb[lane] : nowhere;
+        const float carea = act ? ga[lane] : 1.0f;
+        // (2) the pairs among them, each evaluated once: in trip t lane c takes the pair (c, (c + t) mod n_a); trips
+        // 1 .. (n_a - 1) / 2 cover every pair whose cyclic distance is below n_a / 2 exactly once, and for even n_a the
+        // trip n_a / 2 (lanes below n_a / 2) the rest.  Bit j of lane i's word <=> packed box j > i overlaps packed
+        // box i by more than thr; the lane that evaluated a pair whose smaller index is not its own hands the result
+        // over through the trip's ballot.
+        unsigned m = 0u;
+        const int trips = n_a >> 1;
+#pragma unroll 2
+        for (int t = 1; t <= trips; ++t) {
+            int d = lane + t;
+            d = d >= n_a ? d - n_a : d;
+            const bool last_half = (2 * t == n_a);                            // even n_a: every pair of this trip twice
+            const bool on = act && (!last_half || lane < t);
+            bool unsure;
+            bool hit = iou_certain(cbox, carea, gb[on ? d : 0], ga[on ? d : 0], gate, &unsure);
+            if (on && unsure) hit = iou_plus1(cbox, carea, gb[d], ga[d]) > thr;
+            hit = hit && on;
+            const unsigned hits = __ballot_sync(PAA_FULL, hit);
+            if (hit && d > lane) m |= 1u << d;
+            int from = lane - t;                       // the lane whose pair of this trip has me as its second box
+            from = from < 0 ? from + n_a : from;
+            if (act && from > lane && ((hits >> from) & 1u)) m |= 1u << from;
+        }
+        // (3) greedy scan in packed order, best score first: the words are fetched up front (independent shuffles),
         // what is left is a chain of bit operations
-        unsigned removed = removed0, kept = 0u;
+        unsigned removed = 0u, kept_c = 0u;
+#pragma unroll 1
+        for (int j0 = 0; j0 < n_a; j0 += 8) {          // eight at a time: no trips past the last packed box
+            unsigned mj[8];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            const unsigned mj = __shfl_sync(PAA_FULL, m, j);
-            const bool alive = ((removed >> j) & 1u) == 0u;
-            kept |= alive ? (1u << j) : 0u;
-            removed |= alive ? mj : 0u;
+            for (int u = 0; u < 8; ++u) mj[u] = __shfl_sync(PAA_FULL, m, j0 + u);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int j = j0 + u;
+                const bool free_j = j < n_a && ((removed >> j) & 1u) == 0u;
+                kept_c |= free_j ? (1u << j) : 0u;
+                removed |= free_j ? mj[u] : 0u;
+            }
         }
         // (4) results; the kept boxes join the list the later groups are tested against
-        const bool mine = (kept >> lane) & 1u;
+        const bool mine = !dead && ((kept_c >> mine_c) & 1u);
         if (valid) {
             keep_sorted[base + r] = mine ? 1 : 0;
             row_long[base + r] = 0;
         }
-        __syncwarp();
-        if (mine) {
-            const int at = nk + __popc(kept & ((1u << lane) - 1u));
-            kb[at] = box;
-            ka[at] = area;
+        if (act && ((kept_c >> lane) & 1u)) {                                 // packed lane -> list, order kept
+            const int at = nk + __popc(kept_c & ((1u << lane) - 1u));
+            kb[at] = cbox;
+            ka[at] = carea;
         }
-        nk += __popc(kept);
+        nk += __popc(kept_c);
         if (lane < 4) {                                // padding behind the new end (nk <= kRunMax)
             kb[nk + lane] = nowhere;
             ka[nk + lane] = 1.0f;

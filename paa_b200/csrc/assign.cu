@@ -1018,35 +1018,36 @@ __device__ __forceinline__ unsigned long long topk_first_batch(unsigned long lon
     return mine;
 }
 
-// MODE 0: the whole per-GT program in one block (warp l selects level l, warp 0 fits): what runs.
-// MODE 1 / MODE 2: the same program cut in two launches -- MODE 1 the selection alone (block per GT, sorted candidates
-//         to memory), MODE 2 the fit alone with ONE WARP per GT, four GTs per block, i.e. 24 resident fits per SM
-//         instead of the 6 that MODE 0's five-warp blocks allow.  Built for the throughput-bound calls (C3: 16 000 GTs,
-//         216 us in this kernel).  MEASURED AND NOT KEPT AS A DEFAULT (PAA_GMM_SPLIT_ABOVE=<n> selects it for calls
-//         sized for more than n GTs; bit-identical results, tests/test_gpu_loss.py): event-timed, C3 216 us against
-//         212 us fused, C5 83 against 79 us; inside a graph replay of 32 x 500 GT on 800x1333 images the pair takes
-//         54 + 106 us against 243 us (step 565 against 593 us, profiles/r2_gmm_split_trace.txt), but bench.py's C3 step
-//         does not move (0.7259 against 0.7263 ms).  What the measurements say about the fit:
+// MODE 0: the whole per-GT program in one block (warp l selects level l, warp 0 fits): the latency-optimal form, what
+//         runs for calls sized for up to kSplitAboveGts GTs.
+// MODE 1 / MODE 2: the same program cut in two launches for calls sized for more GTs than that (crowded or large
+//         batches: throughput, not latency) -- MODE 1 the selection alone (block per GT, sorted candidates to memory),
+//         MODE 2 the fit alone with ONE WARP per block and GT: up to 24 resident fits per SM instead of the 6 that MODE
+//         0's five-warp blocks allow.  Bit-identical results (tests/test_gpu_loss.py).  Measured (B200, graph replay):
+//         C3 (16 000 GTs) 0.7005 against 0.7290 ms per step, C5 (3327 GTs) 0.4036 against 0.4085; C2 (861 GTs) gets
+//         slower (149.1 against 146.8 us: one more launch on the latency path) -- hence the threshold.  With four GTs
+//         per block the fit launch was no faster than MODE 0 (a block lives as long as its slowest fit).
+//         What the measurements say about the fit:
 //         * tools/fp64_rate_probe.cu: a dependent DFMA takes 8 cycles, a sub-partition's FP64 pipe accepts a warp-wide
 //           DFMA every 2 cycles (64 FMA/clk/SM).  A lone fit -- the tail of every step -- is a latency chain with idle
 //           issue slots (its transcendental pieces are Estrin-evaluated already, fastmath64.cuh); from four resident
 //           fits per sub-partition on, the pipe is the limit: 6 fits x ~185 FP64 instructions x 2 cycles = 2220 cycles
 //           per iteration, which is what MODE 2 measures on C3 (2290; 1480 for a fit alone; tools/gmm_profile.py,
-//           profiles/r2_gmm_c3_fused_vs_split.txt).  More residency than that buys nothing.
-//         * MODE 2's blocks live as long as the slowest of their four fits (p95 24 us against a mean of 11 us), which
-//           is most of the gap between its 106 us and the 51 us that 3552 resident fits would allow.
-//         * MODE 0 shows the same 2290 cycles per iteration under load for a reason that was not isolated (its fits
-//           share their SM with the selection warps of the blocks that keep arriving); letting the block index pick the
-//           fitting warp, in case warp 0 of every block lands on one sub-partition, changed nothing.
+//           profiles/r2_gmm_c3_fused_vs_split.txt).
+//         * Even so MODE 2's launch takes 142 us on C3 where 3552 resident fits of 11.3 us each would need 51 us: on
+//           average a third of the warp slots hold a fit in its pipe-bound phase; the rest of a block's life (the
+//           dependent loads in front of the fit, the fence + ticket atomic behind it) was not broken down further.
+//         * Letting the block index pick the fitting warp of MODE 0, in case warp 0 of every block lands on one
+//           sub-partition, changed nothing (profiles/r2_gmm_split_trace.txt).
 constexpr int kSelectFused = 0, kSelectOnly = 1, kFitOnly = 2;
-constexpr int kSplitAboveGts = 0x7fffffff; // two-launch form off unless PAA_GMM_SPLIT_ABOVE asks for it (see above)
-constexpr int kFitWarps = 4;
+constexpr int kSplitAboveGts = 4096;       // calls sized for more GTs than this take the two-launch form (see above)
+constexpr int kFitWarps = 1;
 
 template <int SPL, int MODE>
 // (64 registers: with the usual five levels six blocks fit an SM, so ~900 GTs are one wave)
 // (four samples per lane -- TOPK 20 -- need more than 64 registers: no spills at two 256-thread blocks per SM)
 __global__ void __launch_bounds__(MODE == kFitOnly ? kFitWarps * PAA_WARP : PAA_MAX_LEVELS * PAA_WARP,
-                                  MODE == kFitOnly ? (SPL >= 4 ? 3 : 6) : (SPL >= 4 ? 2 : 4))
+                                  MODE == kFitOnly ? (SPL >= 4 ? 12 : 24) : (SPL >= 4 ? 2 : 4))
 select_gmm_kernel(const Geometry geo, const GtOffsets* __restrict__ gop, const int* __restrict__ gt_image,
                   const float* __restrict__ gt_boxes, const int64_t* __restrict__ gt_labels,
                   const LossScalars sc, const uint4* __restrict__ tile_gtmask,
@@ -1270,6 +1271,9 @@ select_gmm_kernel(const Geometry geo, const GtOffsets* __restrict__ gop, const i
         my_ticket = atomicAdd(&ticket[0], 1u);
     }
     my_ticket = __shfl_sync(PAA_FULL, my_ticket, 0);
+#ifdef PAA_PROFILE_GMM        // measurement build only: the fitting warp's whole life (up to its ticket) in the w0 slot
+    if (dbg.gmm && lane == 0 && MODE == kFitOnly) dbg.gmm[(size_t)gi * 8 + 0] = (double)(clock64() - prof_t0);
+#endif
     if (my_ticket == (unsigned)num_gt_total - 1u) {
         __threadfence();
         // eight independent loads per lane in flight (this runs after the slowest fit: it is pure kernel tail);
@@ -1394,7 +1398,7 @@ int launch_select_gmm(const Geometry& geo, const float* gt_boxes,
         ws.tile_gtmask, ws.matched, score_src, ws.seg_count, ws.seg_pool, ws.paa_label, ws.pos_list, ws.part_npos, \
         ws.part_siou,                                                                                  \
         ws.ticket, ws.local_norm, normalisers, px, dbg, ws.cand_sorted, ws.cand_n)
-    // measurement switch: selection and fit as two launches (see the kernel's comment for the verdict)
+    // selection and fit as two launches for calls sized for many GTs (PAA_GMM_SPLIT_ABOVE overrides the threshold)
     int split_above = kSplitAboveGts;
     if (const char* e = getenv("PAA_GMM_SPLIT_ABOVE")) split_above = atoi(e);       // measurement switch
     const bool split = grid > split_above;

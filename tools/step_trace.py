@@ -37,6 +37,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--images", type=int, default=16)
     ap.add_argument("--gt", type=int, nargs=2, default=[1, 100])
+    ap.add_argument("--hw", type=int, nargs=2, default=[800, 1333], help="image height and width of the loss batch")
     ap.add_argument("--replays", type=int, default=20)
     ap.add_argument("--build-only", action="store_true")
     ap.add_argument("--post", action="store_true", help="trace the NMS + voting step (C4 shapes) instead of the loss step")
@@ -76,7 +77,7 @@ def main():
         names, first = POST_NAMES, POST_FIRST
         what = "%d images (C4 shapes)" % args.images
     else:
-        b = synthetic.make_batch(seed=2000, num_images=args.images, image_hw=(800, 1333), gt_per_image=tuple(args.gt))
+        b = synthetic.make_batch(seed=2000, num_images=args.images, image_hw=tuple(args.hw), gt_per_image=tuple(args.gt))
         ev = paa_b200.make_paa_loss_evaluator(cfg, paa_b200.BoxCoder(cfg))
         cls, reg, iou, targets, anchors = to_device_inputs(b)
         step = lambda: ev.forward_backward(cls, reg, iou, targets, anchors)

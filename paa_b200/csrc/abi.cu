@@ -428,7 +428,7 @@ int paa_loss(const PaaLossArgs* args, void* stream_) {
     for (int l = 0; l < args->num_levels; ++l)
         write_grads = write_grads || args->levels[l].grad_box_cls || args->levels[l].grad_box_regression ||
                       args->levels[l].grad_iou_pred;
-    return launch_final_loss(p.geo, args->gt_boxes, p.sc, p.ws, args->normalisers, args->grad_losses,
+    return launch_final_loss(p.geo, args->gt_boxes, args->gt_labels, p.sc, p.ws, args->normalisers, args->grad_losses,
                              args->losses, write_grads, stream);
 }
 

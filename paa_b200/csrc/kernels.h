@@ -94,7 +94,7 @@ int launch_rpn_loss(const Geometry& geo, const GtOffsets& go, const float* gt_bo
 int launch_selftest_roots(const float* x, int n, float* out, cudaStream_t stream);
 // loss.cu
 int loss_grid_blocks(int num_images, int tiles_per_image);
-int launch_final_loss(const Geometry& geo, const float* gt_boxes,
+int launch_final_loss(const Geometry& geo, const float* gt_boxes, const int64_t* gt_labels,
                       const LossScalars& sc, const LossWorkspace& ws, const double* normalisers,
                       const float* grad_losses, float* losses, bool write_grads, cudaStream_t stream);
 int launch_rescale_grads(const Geometry& geo, const float* old_g, const float* new_g, cudaStream_t stream);

@@ -691,7 +691,7 @@ constexpr int kPosMaxBlocks = 148 * 8;
 template <bool kGrads, bool kG2>
 __global__ void __launch_bounds__(kPosThreads, 8)
 positive_list_kernel(const Geometry geo, const GtOffsets* __restrict__ gop, const int* __restrict__ gt_image,
-                     const float* __restrict__ gt_boxes, const LossScalars sc,
+                     const float* __restrict__ gt_boxes, const int64_t* __restrict__ gt_labels, const LossScalars sc,
                      const int* __restrict__ pos_list, const int* __restrict__ part_npos, int cap,
                      const int* __restrict__ paa_label, const double* __restrict__ norm,
                      const double* __restrict__ local_norm, const float* __restrict__ gout,
@@ -727,10 +727,13 @@ positive_list_kernel(const Geometry geo, const GtOffsets* __restrict__ gop, cons
     const unsigned items = (unsigned)num_gt * (unsigned)cap;
     for (unsigned t = tid; t < items; t += nthr) {
         const int gi = (int)(t / (unsigned)cap), j = (int)(t - (unsigned)gi * (unsigned)cap);
-        if (j >= __ldg(part_npos + gi)) continue;
+        // one memory round trip for everything that only depends on (GT, slot): the prefix length, the GT's image and
+        // class (= the label select_gmm_kernel wrote for its positives), the slot's anchor (stale past the prefix)
+        const int npos = __ldg(part_npos + gi);
         const int n = __ldg(gt_image + gi);
         const int a = __ldg(pos_list + (size_t)gi * cap + j);
-        const int label = __ldg(paa_label + (size_t)n * geo.A + a);        // the GT's class, written by select_gmm_kernel
+        const int label = (int)__ldg(gt_labels + gi);
+        if (j >= npos) continue;
         const int l = anchor_level(geo, a);
         const LevelView& lv = geo.lv[l];
         const int i = a - lv.a_off;
@@ -825,7 +828,7 @@ positive_list_kernel(const Geometry geo, const GtOffsets* __restrict__ gop, cons
 PAA_TRACE_SETTER(trace_set_loss)
 #endif
 
-int launch_final_loss(const Geometry& geo, const float* gt_boxes,
+int launch_final_loss(const Geometry& geo, const float* gt_boxes, const int64_t* gt_labels,
                       const LossScalars& sc, const LossWorkspace& ws, const double* normalisers,
                       const float* grad_losses, float* losses, bool write_grads, cudaStream_t stream) {
     const GtOffsets* gop = ws.go;
@@ -927,7 +930,7 @@ int launch_final_loss(const Geometry& geo, const float* gt_boxes,
         const int pos_grid = (int)(blocks < 1 ? 1 : (blocks > kPosMaxBlocks ? kPosMaxBlocks : blocks));
         KernelTimer timer(PAA_KERNEL_POSITIVE_TERMS, stream);
 #define PAA_POSL(G, T)                                                                                       \
-    PAA_PDL_LAUNCH((positive_list_kernel<G, T>), pos_grid, kPosThreads, stream, geo, gop, ws.gt_image, gt_boxes, sc, \
+    PAA_PDL_LAUNCH((positive_list_kernel<G, T>), pos_grid, kPosThreads, stream, geo, gop, ws.gt_image, gt_boxes, gt_labels, sc, \
         ws.pos_list, ws.part_npos, cap, ws.paa_label, normalisers, ws.local_norm, grad_losses, bulk_part, bulk_grid, \
         tile_part, ws.ticket + 1, losses)
         if (write_grads) {

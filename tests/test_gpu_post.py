@@ -233,3 +233,37 @@ def smoke_post():
                             r.get_field("labels").cpu().numpy()),
                            (want[i].boxes.numpy(), want[i].scores.numpy(), want[i].labels.numpy()))
     print("smoke post: detections", [len(r) for r in out])
+
+
+def test_nms_degenerate_thresholds_take_the_exact_path():
+    """A threshold of zero or below switches the division-free IoU gate off (every pair goes through the reference's own
+    quotient test): threshold 0 suppresses every overlapping pair, a negative one everything behind a class's best box."""
+    from paa_b200.inference import ml_nms
+    rng = np.random.default_rng(11)
+    for n, n_cls, thr in ((200, 3, 0.0), (300, 2, -0.5), (90, 1, 1.0), (150, 4, 0.999)):
+        ctr = rng.uniform(0, 200, (n, 2))
+        wh = rng.uniform(10, 80, (n, 2))
+        boxes = np.concatenate([ctr - wh / 2, ctr + wh / 2], axis=1).astype(np.float32)
+        scores = rng.permutation(n).astype(np.float32) / n
+        labels = rng.integers(1, n_cls + 1, n).astype(np.float32)
+        want = nms_oracle.ml_nms_cpu(boxes, scores, labels, thr)
+        got = ml_nms(torch.from_numpy(boxes).cuda(), torch.from_numpy(scores).cuda(), torch.from_numpy(labels).cuda(), thr)
+        assert np.array_equal(got.cpu().numpy(), want), (n, n_cls, thr)
+
+
+def test_bulk_copy_candidate_kernel_matches_the_default(monkeypatch):
+    """The opt-in cp.async.bulk ring variant of the candidate pass (PAA_POST_RING=1; measured slower, kept as a switch)
+    selects exactly the same detections as the register-staged kernel."""
+    b = synthetic.make_inference_batch(seed=4300, num_images=3, image_hw=(512, 672), candidates_per_level=2500)
+    outs = []
+    for ring in (False, True):
+        if ring:
+            monkeypatch.setenv("PAA_POST_RING", "1")
+        else:
+            monkeypatch.delenv("PAA_POST_RING", raising=False)
+        outs.append(_run(_postprocessor(), b))
+    for a, c in zip(*outs):
+        assert torch.equal(a.bbox, c.bbox)
+        assert torch.equal(a.get_field("scores"), c.get_field("scores"))
+        assert torch.equal(a.get_field("labels"), c.get_field("labels"))
+    assert sum(len(a) for a in outs[0]) > 0

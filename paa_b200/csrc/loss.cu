@@ -700,9 +700,13 @@ positive_list_kernel(const Geometry geo, const GtOffsets* __restrict__ gop, cons
     __shared__ double s_part[kPosThreads / PAA_WARP][3];
     __shared__ bool s_last;
     PAA_TRACE_SCOPE(5);
-    pdl_wait();
-    PAA_TRACE_WAITED();
-    pdl_launch_dependents();
+    // Only two things here depend on bulk_focal_kernel, the programmatic predecessor: the labelled class's gradient
+    // element (bulk_focal wrote the negative-class value there) and the fold of its partial sums.  Everything else
+    // reads what select_gmm_kernel and its predecessors left -- complete and visible before this grid's first block
+    // starts, because every bulk_focal block calls launch_dependents AFTER its own dependency wait -- and is done
+    // before the wait, in the shadow of the bulk pass: the zero fill, the positives' losses and regression / IoU
+    // gradients, the block's partial sums and its ticket.  (Reads of that data go to the L2: ld.cg.)  After the
+    // wait: one store per positive and the last block's fold.  13 -> ~5 us behind bulk_focal's end on C2.
     const GtOffsets& go = *gop;
     const int num_gt = go.v[geo.num_images];
     const unsigned tid = blockIdx.x * kPosThreads + threadIdx.x, nthr = gridDim.x * kPosThreads;
@@ -710,7 +714,7 @@ positive_list_kernel(const Geometry geo, const GtOffsets* __restrict__ gop, cons
     if (kGrads) {
         const unsigned total = (unsigned)geo.num_images * (unsigned)geo.A;
         for (unsigned t = tid; t < total; t += nthr) {
-            if (__ldg(paa_label + t) > 0) continue;
+            if (__ldcg(paa_label + t) > 0) continue;
             const int n = (int)(t / (unsigned)geo.A), a = (int)(t - (unsigned)n * (unsigned)geo.A);
             const int l = anchor_level(geo, a);
             const LevelView& lv = geo.lv[l];
@@ -725,24 +729,27 @@ positive_list_kernel(const Geometry geo, const GtOffsets* __restrict__ gop, cons
     // (b) the positives
     float fix_sum = 0.f, reg_sum = 0.f, bce_sum = 0.f;
     const unsigned items = (unsigned)num_gt * (unsigned)cap;
+    const double nrm[2] = {__ldcg(norm), __ldcg(norm + 1)}, lnrm[2] = {0.0, __ldcg(local_norm + 1)};
+    FinalCtx cx;
+    cx.gs = make_scales(sc, nrm, lnrm, gout);
+    cx.alpha = sc.alpha;
+    cx.gamma = sc.gamma;
+    cx.oma = 1.0f - sc.alpha;
+    cx.kneg = cx.oma * cx.gs.cls;
+    float* patch_dst = nullptr;         // the thread's first positive: its class gradient element, stored after the wait
+    float patch_val = 0.f;
     for (unsigned t = tid; t < items; t += nthr) {
         const int gi = (int)(t / (unsigned)cap), j = (int)(t - (unsigned)gi * (unsigned)cap);
         // one memory round trip for everything that only depends on (GT, slot): the prefix length, the GT's image and
         // class (= the label select_gmm_kernel wrote for its positives), the slot's anchor (stale past the prefix)
-        const int npos = __ldg(part_npos + gi);
-        const int n = __ldg(gt_image + gi);
-        const int a = __ldg(pos_list + (size_t)gi * cap + j);
+        const int npos = __ldcg(part_npos + gi);
+        const int n = __ldcg(gt_image + gi);
+        const int a = __ldcg(pos_list + (size_t)gi * cap + j);
         const int label = (int)__ldg(gt_labels + gi);
         if (j >= npos) continue;
         const int l = anchor_level(geo, a);
         const LevelView& lv = geo.lv[l];
         const int i = a - lv.a_off;
-        FinalCtx cx;
-        cx.gs = make_scales(sc, norm, local_norm, gout);
-        cx.alpha = sc.alpha;
-        cx.gamma = sc.gamma;
-        cx.oma = 1.0f - sc.alpha;
-        cx.kneg = cx.oma * cx.gs.cls;
         // classification: swap the negative-class result of the labelled class for the positive one
         const size_t off = head_offset(geo, lv, n, i, label - 1, geo.C);
         const float xp = __ldg(lv.cls + off);
@@ -752,7 +759,10 @@ positive_list_kernel(const Geometry geo, const GtOffsets* __restrict__ gop, cons
         float tp, gp;
         focal_positive(xp, sp, cx.gamma, kG2, cx.alpha, &tp, &gp);
         fix_sum += tp - cx.oma * tn_acc;
-        if (kGrads && lv.g_cls) lv.g_cls[off] = gp * cx.gs.cls;
+        if (kGrads && lv.g_cls && t == tid) {
+            patch_dst = lv.g_cls + off;
+            patch_val = gp * cx.gs.cls;
+        }
         // box regression + IoU prediction
         const float* rp = lv.reg + head_offset(geo, lv, n, i, 0, 4);
         const float4 d = load_channels4(rp, head_cstride(geo, lv));
@@ -788,6 +798,28 @@ positive_list_kernel(const Geometry geo, const GtOffsets* __restrict__ gop, cons
         for (int k = 0; k < 3; ++k) block_part[(size_t)blockIdx.x * 3 + k] = t[k];
         __threadfence();
         s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    }
+    pdl_wait();
+    PAA_TRACE_WAITED();
+    pdl_launch_dependents();
+    // (c) behind the bulk pass: the labelled class's gradient element of every positive
+    if (kGrads) {
+        if (patch_dst) *patch_dst = patch_val;
+        for (unsigned t = tid + nthr; t < items; t += nthr) {      // calls with more (GT, slot) items than threads
+            const int gi = (int)(t / (unsigned)cap), j = (int)(t - (unsigned)gi * (unsigned)cap);
+            const int npos = __ldcg(part_npos + gi);
+            const int n = __ldcg(gt_image + gi);
+            const int a = __ldcg(pos_list + (size_t)gi * cap + j);
+            const int label = (int)__ldg(gt_labels + gi);
+            if (j >= npos) continue;
+            const LevelView& lv = geo.lv[anchor_level(geo, a)];
+            if (!lv.g_cls) continue;
+            const size_t off = head_offset(geo, lv, n, a - lv.a_off, label - 1, geo.C);
+            const float xp = __ldg(lv.cls + off);
+            float tp, gp;
+            focal_positive(xp, sigmoid_parts(xp), cx.gamma, kG2, cx.alpha, &tp, &gp);
+            lv.g_cls[off] = gp * cx.gs.cls;
+        }
     }
     __syncthreads();
     if (!s_last) return;

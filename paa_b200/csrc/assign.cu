@@ -1075,6 +1075,13 @@ select_gmm_kernel(const Geometry geo, const GtOffsets* __restrict__ gop, const i
     // the grid covers the call's GT capacity; the step's own count lives in device memory
     const int num_gt_total = __ldg(&gop->v[geo.num_images]);
     if (gi >= num_gt_total) return;
+    // one more fit lives on this SM (a hint for bulk_focal_early_kernel, which keeps off the SMs where a fit runs:
+    // a fit is one dependent instruction chain and every other ready warp on its sub-partition stretches it)
+    unsigned smid = 0;
+    if (MODE == kSelectFused) {
+        asm("mov.u32 %0, %%smid;" : "=r"(smid));
+        if (threadIdx.x == 0) atomicAdd(ticket + kCtlSmLive + (smid & (kCtlMaxSms - 1)), 1u);
+    }
     const int n = __ldg(gt_image + gi);              // image of this GT
     const int g_local = gi - __ldg(&gop->v[n]);
     const int cls_label = (int)gt_labels[gi];
@@ -1228,6 +1235,7 @@ select_gmm_kernel(const Geometry geo, const GtOffsets* __restrict__ gop, const i
     } else if (n_cand > 1) {
         n_pos = gmm_positive_prefix<SPL>(x, n_cand, lane, dbg.gmm ? dbg.gmm + (size_t)gi * 8 : nullptr);
     }
+    if (MODE == kSelectFused && lane == 0) atomicSub(ticket + kCtlSmLive + (smid & (kCtlMaxSms - 1)), 1u);
     if (dbg.gmm && n_cand <= 1 && lane < 8) dbg.gmm[(size_t)gi * 8 + lane] = 0.0;
 #ifdef PAA_PROFILE_GMM        // measurement build only: cycles of scan+sort / EM in the w0 / w1 debug slots
     if (dbg.gmm && lane == 0) {
@@ -1301,6 +1309,8 @@ select_gmm_kernel(const Geometry geo, const GtOffsets* __restrict__ gop, const i
             local_norm[1] = sum;
             normalisers[0] = cnt;
             normalisers[1] = sum;
+            __threadfence();
+            ticket[kCtlReady] = 1u;         // hint: early bulk chunks stop here (the dependency wait is what orders)
         }
         // publish this rank's pair to every rank's exchange buffer over NVLink (lane r -> rank r): data,
         // system-scope fence, then the epoch that makes it visible to norm_wait_kernel over there
@@ -1384,6 +1394,12 @@ int launch_norm_wait(const PeerExchange& px, double* normalisers, cudaStream_t s
     return 0;
 }
 
+bool select_gmm_two_launch(const LossScalars& sc) {
+    int split_above = kSplitAboveGts;
+    if (const char* e = getenv("PAA_GMM_SPLIT_ABOVE")) split_above = atoi(e);       // measurement switch
+    return sc.gt_capacity > split_above;
+}
+
 int launch_select_gmm(const Geometry& geo, const float* gt_boxes,
                       const int64_t* gt_labels, const LossScalars& sc, const LossWorkspace& ws,
                       const float* score_src, double* normalisers, const PeerExchange& px, const LossDebug& dbg,
@@ -1399,9 +1415,7 @@ int launch_select_gmm(const Geometry& geo, const float* gt_boxes,
         ws.part_siou,                                                                                  \
         ws.ticket, ws.local_norm, normalisers, px, dbg, ws.cand_sorted, ws.cand_n)
     // selection and fit as two launches for calls sized for many GTs (PAA_GMM_SPLIT_ABOVE overrides the threshold)
-    int split_above = kSplitAboveGts;
-    if (const char* e = getenv("PAA_GMM_SPLIT_ABOVE")) split_above = atoi(e);       // measurement switch
-    const bool split = grid > split_above;
+    const bool split = select_gmm_two_launch(sc);
 #define PAA_SEL_LAUNCH(SPL)                                                                            \
     do {                                                                                               \
         if (split) {                                                                                   \

@@ -66,6 +66,8 @@ int launch_select_gmm(const Geometry& geo, const float* gt_boxes,
                       const int64_t* gt_labels, const LossScalars& sc, const LossWorkspace& ws,
                       const float* score_src, double* normalisers, const PeerExchange& px, const LossDebug& dbg,
                       cudaStream_t stream);
+// true when launch_select_gmm takes the two-launch form for this call (many GTs: the fits run as a launch of their own)
+bool select_gmm_two_launch(const LossScalars& sc);
 // atss.cu
 int launch_atss_assign(const Geometry& geo, const float* gt_boxes,
                        const int64_t* gt_labels, const LossScalars& sc, const LossWorkspace& ws, double* normalisers,

@@ -16,7 +16,8 @@ struct LossWorkspace {
     // zeroed region
     unsigned* gtmax;        // [sumG]   bit pattern of the per-GT maximal IoU
     int* img_flags;         // [N]      bit0: some GT of the image overlaps no anchor (culling off)
-    unsigned* ticket;       // [4]      completion counters
+    unsigned* ticket;       // [kTicketWords] completion counters; [kCtlReady] / [kCtlChunk] / [kCtlSmLive + sm]: the
+                            //          hints that let bulk_focal_early_kernel work in select_gmm_kernel's shadow
     int* seg_count;         // [sumG*L] anchors matched to (GT, level)
     size_t zero_bytes;
     // plain region
@@ -41,6 +42,9 @@ struct LossWorkspace {
 // Capacity of one (GT, level) candidate pool.  The anchors IoU-matched to one GT on one level number a few
 // hundred at most for PAA's anchor layout; a segment that overflows falls back to scanning the tiles.
 constexpr int kSegCap = 1024;
+// ticket[]: 0 = select_gmm_kernel's completion ticket, 1 = positive_list_kernel's; then the control words of the early
+// bulk pass: "the normalisers exist", the bulk pass's chunk counter, and per SM the number of EM fits still running there
+constexpr int kCtlReady = 4, kCtlChunk = 5, kCtlSmLive = 8, kCtlMaxSms = 256, kTicketWords = kCtlSmLive + kCtlMaxSms;
 constexpr size_t kGtOffsetsBytes = 4 * 257 + 256;      // sizeof(GtOffsets), checked where the type is complete
 
 inline LossWorkspace carve_loss_workspace(void* base, int N, int A, int sumG, int tiles_per_image,
@@ -55,7 +59,7 @@ inline LossWorkspace carve_loss_workspace(void* base, int N, int A, int sumG, in
     };
     w.gtmax = reinterpret_cast<unsigned*>(take(sizeof(unsigned) * (size_t)(sumG > 0 ? sumG : 1)));
     w.img_flags = reinterpret_cast<int*>(take(sizeof(int) * (size_t)N));
-    w.ticket = reinterpret_cast<unsigned*>(take(sizeof(unsigned) * 4));
+    w.ticket = reinterpret_cast<unsigned*>(take(sizeof(unsigned) * kTicketWords));
     w.seg_count = reinterpret_cast<int*>(take(sizeof(int) * (size_t)(sumG > 0 ? sumG : 1) * L));
     w.zero_bytes = off;
     size_t NA = (size_t)N * A;

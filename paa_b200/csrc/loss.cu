@@ -376,6 +376,271 @@ bulk_focal_kernel(const BulkPlan plan, const LossScalars sc, const double* __res
     }
 }
 
+// Zero regression / IoU-prediction gradients of the non-positive anchors: thread `tid` of `nthr` takes anchors tid,
+// tid + nthr, ... four labels requested per trip (under the bulk pass's traffic a dependent round trip takes
+// microseconds).  The positives' elements are written by positive_list_kernel's threads: disjoint sets.
+__device__ __forceinline__ void zero_one_anchor(const Geometry& geo, unsigned t) {
+    const int n = (int)(t / (unsigned)geo.A), a = (int)(t - (unsigned)n * (unsigned)geo.A);
+    const int l = anchor_level(geo, a);
+    const LevelView& lv = geo.lv[l];
+    const int i = a - lv.a_off;
+    if (lv.g_reg) {
+        float* gr = lv.g_reg + head_offset(geo, lv, n, i, 0, 4);
+        store_channels4(gr, head_cstride(geo, lv), make_float4(0.0f, 0.0f, 0.0f, 0.0f));
+    }
+    if (lv.g_iou) lv.g_iou[head_offset(geo, lv, n, i, 0, 1)] = 0.0f;
+}
+
+// labels of anchors tid + u * nthr, u < 4 (1 past the end) -> their zeroes
+__device__ __forceinline__ void zero_from_labels(const Geometry& geo, const int (&lab)[4], unsigned tid, unsigned nthr) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+        if (lab[u] <= 0) zero_one_anchor(geo, tid + (unsigned)u * nthr);
+}
+
+__device__ __forceinline__ void zero_nonpositive_grads(const Geometry& geo, const int* __restrict__ paa_label,
+                                                       unsigned first, unsigned nthr, unsigned total) {
+    for (unsigned t0 = first; t0 < total; t0 += 4u * nthr) {
+        int lab[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const unsigned t = t0 + (unsigned)u * nthr;
+            lab[u] = t < total ? __ldcg(paa_label + t) : 1;
+        }
+        zero_from_labels(geo, lab, t0, nthr);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// bulk_focal_early_kernel: the bulk pass of the PAA step, with part of its work done in select_gmm_kernel's shadow.
+//
+// The gradients are scaled by 1 / num_pos, which exists only after the slowest EM fit -- for the last ~30 us of
+// select_gmm_kernel most SMs hold no fit any more and the memory system idles.  An earlier attempt let every resident
+// bulk block work on unscaled gradients during that time and lost what it gained: a fit is one dependent instruction
+// chain, and every other ready warp on its SM sub-partition stretches it (profiles/r2_step_trace.txt).  Here a block
+// works early only while NO fit lives on its SM (select_gmm_kernel counts the fits per SM in ticket[kCtlSmLive + sm]):
+//   before the dependency wait   thread 0 polls {normalisers ready, fits on this SM}; on a free SM the block claims
+//                                the next chunk from a global counter, computes the loss terms and stores the
+//                                UNSCALED gradients (plain stores: they stay in the L2), up to kEarlyMax chunks;
+//   after the wait               it scales its own early chunks in place (the same thread re-reads what it stored;
+//                                (h * 1) * k == h * k bit for bit), then claims the remaining chunks one by one.
+// Chunks are handed out dynamically, so the order in which a block sums loss terms changes from run to run; the sum
+// is therefore taken in fixed point (2^-30 units, exact integer additions: any order gives the same total).  The
+// flags are hints only -- what orders memory is the dependency wait.
+// ---------------------------------------------------------------------------------------------
+constexpr int kEarlyMax = 10;
+constexpr unsigned kClaimStop = 0xffffffffu;
+constexpr float kFixScale = 1073741824.0f;            // 2^30
+
+struct EarlyCtl {
+    unsigned* ctl;          // LossWorkspace::ticket
+    unsigned limit;         // chunks [0, limit) may be processed early
+    int max_early;          // ... at most this many by one block (<= kEarlyMax): a block scales its early chunks itself
+                            //     after the wait, so what a few early-free SMs may take is bounded by twice the fair share
+};
+
+__device__ __forceinline__ unsigned ld_relaxed(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// one whole chunk: loss terms of this thread's 16 logits (returned), gradients h * k stored
+template <bool kG2, bool kKeepInL2>
+__device__ __forceinline__ float bulk_chunk(const float4* __restrict__ src4, float4* __restrict__ dst4,
+                                            unsigned long long base4, float gamma, float k) {
+    float4 x[kBulkVecs];
+#pragma unroll
+    for (int j = 0; j < kBulkVecs; ++j) x[j] = __ldcs(src4 + base4 + j * kBulkThreads + threadIdx.x);
+    float t = 0.f;
+#pragma unroll
+    for (int j = 0; j < kBulkVecs; ++j) {
+        float4 g;
+        neg_term_grad<kG2>(x[j].x, gamma, k, &t, &g.x);
+        neg_term_grad<kG2>(x[j].y, gamma, k, &t, &g.y);
+        neg_term_grad<kG2>(x[j].z, gamma, k, &t, &g.z);
+        neg_term_grad<kG2>(x[j].w, gamma, k, &t, &g.w);
+        if (kKeepInL2) dst4[base4 + j * kBulkThreads + threadIdx.x] = g;
+        else __stcs(dst4 + base4 + j * kBulkThreads + threadIdx.x, g);
+    }
+    return t;
+}
+
+__device__ __forceinline__ int bulk_level_of(const BulkPlan& plan, unsigned ch) {
+    int l = 0;
+#pragma unroll 1
+    for (int k = 1; k < plan.n; ++k)
+        if (ch >= plan.chunk_off[k]) l = k;
+    return l;
+}
+
+template <bool kG2>
+__global__ void __launch_bounds__(kBulkThreads, kBulkBlocksPerSM)
+bulk_focal_early_kernel(const BulkPlan plan, const LossScalars sc, const double* __restrict__ norm,
+                        const double* __restrict__ local_norm, const float* __restrict__ gout,
+                        double* __restrict__ block_part, const EarlyCtl ec, const Geometry geo,
+                        const int* __restrict__ paa_label) {
+    __shared__ long long s_part[kBulkThreads / PAA_WARP];
+    __shared__ unsigned s_claim[2];
+    __shared__ unsigned s_mine[kEarlyMax];
+    const float gamma = sc.gamma, oma = 1.0f - sc.alpha;
+    long long acc = 0;
+    PAA_TRACE_SCOPE(4);
+    const unsigned n_chunks = plan.chunk_off[plan.n];
+    unsigned* const counter = ec.ctl + kCtlChunk;
+    if (plan.l2_prefetch && threadIdx.x == 0) {
+        unsigned pf_end = (unsigned)(((unsigned long long)n_chunks * (unsigned)plan.l2_prefetch) / 100u);
+        pf_end = pf_end < 6144u ? pf_end : 6144u;
+        for (unsigned c = blockIdx.x; c < pf_end; c += gridDim.x) {
+            const int l = bulk_level_of(plan, c);
+            const unsigned long long first = (unsigned long long)(c - plan.chunk_off[l]) * kBulkChunk * 4ull;   // floats
+            const unsigned long long left = plan.count[l] - first;
+            const unsigned bytes = (unsigned)((left < (unsigned long long)kBulkChunk * 4ull ? left : kBulkChunk * 4ull) * 4ull) & ~15u;
+            if (bytes)
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(plan.src[l] + first), "r"(bytes) : "memory");
+        }
+    }
+    // ---- before the wait: unscaled chunks while no fit lives on this SM ----
+    int par = 0, n_mine = 0;
+    unsigned carried = kClaimStop;          // a chunk claimed early that has to wait for the normalisers
+    if (ec.limit) {
+        unsigned smid;
+        asm("mov.u32 %0, %%smid;" : "=r"(smid));
+        const unsigned* live = ec.ctl + kCtlSmLive + (smid & (kCtlMaxSms - 1));
+        for (;;) {
+            if (threadIdx.x == 0) {
+                unsigned c = kClaimStop;
+                for (int polls = 0; polls < 4096; ++polls) {        // bounded: a hint must never hang the step
+                    if (ld_relaxed(ec.ctl + kCtlReady)) break;
+                    if (ld_relaxed(live) == 0u) {
+                        c = atomicAdd(counter, 1u);
+                        break;
+                    }
+                    __nanosleep(250);
+                }
+                s_claim[par] = c;
+            }
+            __syncthreads();
+            const unsigned c = s_claim[par];
+            par ^= 1;
+            if (c == kClaimStop) break;
+            if (c >= ec.limit) {
+                carried = c;
+                break;
+            }
+            const int l = bulk_level_of(plan, c);
+            const unsigned long long base4 = (unsigned long long)(c - plan.chunk_off[l]) * kBulkChunk;
+            if (base4 + kBulkChunk > (plan.count[l] >> 2)) {          // a level's last, partial chunk
+                carried = c;
+                break;
+            }
+            const float t = bulk_chunk<kG2, true>(reinterpret_cast<const float4*>(plan.src[l]),
+                                                  reinterpret_cast<float4*>(plan.dst[l]), base4, gamma, 1.0f);
+            acc += __float2ll_rn(t * kFixScale);
+            if (threadIdx.x == 0) s_mine[n_mine] = c;
+            if (++n_mine >= ec.max_early) break;
+        }
+    }
+    pdl_wait();
+    PAA_TRACE_WAITED();
+    pdl_launch_dependents();
+    const GradScales gs = make_scales(sc, norm, local_norm, gout);
+    const float kneg = oma * gs.cls;
+    __syncthreads();                        // s_mine
+    // ---- zero regression / IoU gradients of the non-positive anchors (7 MB on C2).  Here and not in
+    // positive_list_kernel: that kernel then needs one thread per (GT, slot) only, few enough blocks to be resident
+    // beside this pass from its start, and its loads under this pass's traffic take microseconds each ----
+    // The first four labels per thread are requested here and used after the block's first pieces of work.
+    const unsigned z_tid = blockIdx.x * kBulkThreads + threadIdx.x, z_nthr = gridDim.x * kBulkThreads;
+    const unsigned z_total = paa_label ? (unsigned)geo.num_images * (unsigned)geo.A : 0u;
+    int z_lab[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const unsigned t = z_tid + (unsigned)u * z_nthr;
+        z_lab[u] = t < z_total ? __ldcg(paa_label + t) : 1;
+    }
+    bool z_pending = true;
+    // ---- the early chunks get their scale (L2 hits: this thread re-reads exactly what it stored) ----
+    for (int m = 0; m < n_mine; ++m) {
+        const unsigned c = s_mine[m];
+        const int l = bulk_level_of(plan, c);
+        float4* __restrict__ dst4 = reinterpret_cast<float4*>(plan.dst[l]) +
+                                    (unsigned long long)(c - plan.chunk_off[l]) * kBulkChunk + threadIdx.x;
+        float4 g[kBulkVecs];
+#pragma unroll
+        for (int j = 0; j < kBulkVecs; ++j) g[j] = __ldcg(dst4 + j * kBulkThreads);
+#pragma unroll
+        for (int j = 0; j < kBulkVecs; ++j) {
+            g[j].x *= kneg;
+            g[j].y *= kneg;
+            g[j].z *= kneg;
+            g[j].w *= kneg;
+            __stcs(dst4 + j * kBulkThreads, g[j]);
+        }
+    }
+    // ---- the remaining chunks, claimed one ahead ----
+    if (threadIdx.x == 0) s_claim[par] = carried != kClaimStop ? carried : atomicAdd(counter, 1u);
+    __syncthreads();
+    for (;;) {
+        const unsigned c = s_claim[par];
+        if (c >= n_chunks) break;
+        unsigned next = 0;
+        if (threadIdx.x == 0) next = atomicAdd(counter, 1u);
+        const int l = bulk_level_of(plan, c);
+        const unsigned long long count = plan.count[l];
+        const unsigned long long n4 = count >> 2;                                  // whole float4s
+        const unsigned long long base4 = (unsigned long long)(c - plan.chunk_off[l]) * kBulkChunk;
+        const float4* __restrict__ src4 = reinterpret_cast<const float4*>(plan.src[l]);
+        float4* __restrict__ dst4 = reinterpret_cast<float4*>(plan.dst[l]);
+        float t = 0.f;
+        if (base4 + kBulkChunk <= n4) {
+            t = bulk_chunk<kG2, false>(src4, dst4, base4, gamma, kneg);
+        } else {
+            for (int j = 0; j < kBulkVecs; ++j) {
+                const unsigned long long i4 = base4 + j * kBulkThreads + threadIdx.x;
+                if (i4 < n4) {
+                    const float4 x = __ldcs(src4 + i4);
+                    float4 g;
+                    neg_term_grad<kG2>(x.x, gamma, kneg, &t, &g.x);
+                    neg_term_grad<kG2>(x.y, gamma, kneg, &t, &g.y);
+                    neg_term_grad<kG2>(x.z, gamma, kneg, &t, &g.z);
+                    neg_term_grad<kG2>(x.w, gamma, kneg, &t, &g.w);
+                    __stcs(dst4 + i4, g);
+                }
+            }
+            const unsigned long long tail = (n4 << 2) + threadIdx.x;
+            if (threadIdx.x < 4 && tail < count) {
+                float g;
+                neg_term_grad<kG2>(plan.src[l][tail], gamma, kneg, &t, &g);
+                plan.dst[l][tail] = g;
+            }
+        }
+        acc += __float2ll_rn(t * kFixScale);
+        if (z_pending) {
+            zero_from_labels(geo, z_lab, z_tid, z_nthr);
+            z_pending = false;
+        }
+        if (threadIdx.x == 0) s_claim[par ^ 1] = next;
+        __syncthreads();
+        par ^= 1;
+    }
+    if (z_pending) zero_from_labels(geo, z_lab, z_tid, z_nthr);
+    if (z_total > 4u * z_nthr) zero_nonpositive_grads(geo, paa_label, z_tid + 4u * z_nthr, z_nthr, z_total);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(PAA_FULL, acc, o);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) s_part[warp] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        long long t = 0;
+#pragma unroll
+        for (int w = 0; w < kBulkThreads / PAA_WARP; ++w) t += s_part[w];
+        block_part[(size_t)blockIdx.x * 3 + 0] = (double)oma * ((double)t * (1.0 / (double)kFixScale));
+        block_part[(size_t)blockIdx.x * 3 + 1] = 0.0;
+        block_part[(size_t)blockIdx.x * 3 + 2] = 0.0;
+    }
+}
+
 struct FinalCtx {
     float alpha, gamma, oma, kneg;
     GradScales gs;
@@ -693,7 +958,7 @@ __global__ void __launch_bounds__(kPosThreads, 8)
 positive_list_kernel(const Geometry geo, const GtOffsets* __restrict__ gop, const int* __restrict__ gt_image,
                      const float* __restrict__ gt_boxes, const int64_t* __restrict__ gt_labels, const LossScalars sc,
                      const int* __restrict__ pos_list, const int* __restrict__ part_npos, int cap,
-                     const int* __restrict__ paa_label, const double* __restrict__ norm,
+                     const int* __restrict__ paa_label, bool zero_here, const double* __restrict__ norm,
                      const double* __restrict__ local_norm, const float* __restrict__ gout,
                      const double* __restrict__ bulk_part, int bulk_blocks, double* __restrict__ block_part,
                      unsigned* __restrict__ ticket, float* __restrict__ losses) {
@@ -710,22 +975,8 @@ positive_list_kernel(const Geometry geo, const GtOffsets* __restrict__ gop, cons
     const GtOffsets& go = *gop;
     const int num_gt = go.v[geo.num_images];
     const unsigned tid = blockIdx.x * kPosThreads + threadIdx.x, nthr = gridDim.x * kPosThreads;
-    // (a) zero gradients of the non-positive anchors: the positives' are written below, by their own threads
-    if (kGrads) {
-        const unsigned total = (unsigned)geo.num_images * (unsigned)geo.A;
-        for (unsigned t = tid; t < total; t += nthr) {
-            if (__ldcg(paa_label + t) > 0) continue;
-            const int n = (int)(t / (unsigned)geo.A), a = (int)(t - (unsigned)n * (unsigned)geo.A);
-            const int l = anchor_level(geo, a);
-            const LevelView& lv = geo.lv[l];
-            const int i = a - lv.a_off;
-            if (lv.g_reg) {
-                float* gr = lv.g_reg + head_offset(geo, lv, n, i, 0, 4);
-                store_channels4(gr, head_cstride(geo, lv), make_float4(0.0f, 0.0f, 0.0f, 0.0f));
-            }
-            if (lv.g_iou) lv.g_iou[head_offset(geo, lv, n, i, 0, 1)] = 0.0f;
-        }
-    }
+    // (a) zero gradients of the non-positive anchors (unless the bulk pass did it): the positives' are written below
+    if (kGrads && zero_here) zero_nonpositive_grads(geo, paa_label, tid, nthr, (unsigned)geo.num_images * (unsigned)geo.A);
     // (b) the positives
     float fix_sum = 0.f, reg_sum = 0.f, bce_sum = 0.f;
     const unsigned items = (unsigned)num_gt * (unsigned)cap;
@@ -736,8 +987,8 @@ positive_list_kernel(const Geometry geo, const GtOffsets* __restrict__ gop, cons
     cx.gamma = sc.gamma;
     cx.oma = 1.0f - sc.alpha;
     cx.kneg = cx.oma * cx.gs.cls;
-    float* patch_dst = nullptr;         // the thread's first positive: its class gradient element, stored after the wait
-    float patch_val = 0.f;
+    float* patch_dst[2] = {nullptr, nullptr};     // the thread's first two positives: their class gradient elements,
+    float patch_val[2] = {0.f, 0.f};              // stored after the wait
     for (unsigned t = tid; t < items; t += nthr) {
         const int gi = (int)(t / (unsigned)cap), j = (int)(t - (unsigned)gi * (unsigned)cap);
         // one memory round trip for everything that only depends on (GT, slot): the prefix length, the GT's image and
@@ -759,9 +1010,14 @@ positive_list_kernel(const Geometry geo, const GtOffsets* __restrict__ gop, cons
         float tp, gp;
         focal_positive(xp, sp, cx.gamma, kG2, cx.alpha, &tp, &gp);
         fix_sum += tp - cx.oma * tn_acc;
-        if (kGrads && lv.g_cls && t == tid) {
-            patch_dst = lv.g_cls + off;
-            patch_val = gp * cx.gs.cls;
+        if (kGrads && lv.g_cls) {
+            if (t == tid) {
+                patch_dst[0] = lv.g_cls + off;
+                patch_val[0] = gp * cx.gs.cls;
+            } else if (t == tid + nthr) {
+                patch_dst[1] = lv.g_cls + off;
+                patch_val[1] = gp * cx.gs.cls;
+            }
         }
         // box regression + IoU prediction
         const float* rp = lv.reg + head_offset(geo, lv, n, i, 0, 4);
@@ -799,13 +1055,40 @@ positive_list_kernel(const Geometry geo, const GtOffsets* __restrict__ gop, cons
         __threadfence();
         s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
     }
+    __syncthreads();
+    // the block that took the last ticket folds this grid's partial sums, still in front of the wait ...
+    __shared__ double s_own[kPosThreads / PAA_WARP][3];
+    if (s_last) {
+        double acc[3] = {0.0, 0.0, 0.0};
+        __threadfence();
+        for (int b0 = threadIdx.x; b0 < (int)gridDim.x; b0 += 4 * kPosThreads) {
+            double v[4][3];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int b = b0 + u * kPosThreads;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) v[u][k] = b < (int)gridDim.x ? __ldcg(block_part + (size_t)b * 3 + k) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int k = 0; k < 3; ++k) acc[k] += v[u][k];
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            acc[k] = warp_sum(acc[k]);
+            if (lane == 0) s_own[warp][k] = acc[k];
+        }
+    }
+    PAA_TRACE_POINT(7);                 // when the blocks are done with the work in front of the wait
     pdl_wait();
     PAA_TRACE_WAITED();
     pdl_launch_dependents();
     // (c) behind the bulk pass: the labelled class's gradient element of every positive
     if (kGrads) {
-        if (patch_dst) *patch_dst = patch_val;
-        for (unsigned t = tid + nthr; t < items; t += nthr) {      // calls with more (GT, slot) items than threads
+        if (patch_dst[0]) *patch_dst[0] = patch_val[0];
+        if (patch_dst[1]) *patch_dst[1] = patch_val[1];
+        for (unsigned t = tid + 2u * nthr; t < items; t += nthr) {      // calls with more (GT, slot) items than that
             const int gi = (int)(t / (unsigned)cap), j = (int)(t - (unsigned)gi * (unsigned)cap);
             const int npos = __ldcg(part_npos + gi);
             const int n = __ldcg(gt_image + gi);
@@ -821,38 +1104,31 @@ positive_list_kernel(const Geometry geo, const GtOffsets* __restrict__ gop, cons
             lv.g_cls[off] = gp * cx.gs.cls;
         }
     }
-    __syncthreads();
     if (!s_last) return;
-    __threadfence();
-    // eight partials' loads in flight per thread and trip (a few memory round trips in total)
-    const int total_parts = bulk_blocks + (int)gridDim.x;
-    double acc[3] = {0.0, 0.0, 0.0};
-    for (int b0 = threadIdx.x; b0 < total_parts; b0 += 8 * kPosThreads) {
-        double v[8][3];
+    // ... and the bulk pass's behind it (its blocks leave their sum in slot 0; eight loads in flight per thread)
+    double bulk = 0.0;
+    for (int b0 = threadIdx.x; b0 < bulk_blocks; b0 += 8 * kPosThreads) {
+        double v[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             const int b = b0 + u * kPosThreads;
-            const double* src = b < bulk_blocks ? bulk_part + (size_t)b * 3 : block_part + (size_t)(b - bulk_blocks) * 3;
-#pragma unroll
-            for (int k = 0; k < 3; ++k) v[u][k] = b < total_parts ? __ldcg(src + k) : 0.0;
+            v[u] = b < bulk_blocks ? __ldcg(bulk_part + (size_t)b * 3) : 0.0;
         }
 #pragma unroll
-        for (int u = 0; u < 8; ++u)
-#pragma unroll
-            for (int k = 0; k < 3; ++k) acc[k] += v[u][k];
+        for (int u = 0; u < 8; ++u) bulk += v[u];
     }
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        acc[k] = warp_sum(acc[k]);
-        if (lane == 0) s_part[warp][k] = acc[k];
-    }
+    bulk = warp_sum(bulk);
+    if (lane == 0) s_part[warp][0] = bulk;
     __syncthreads();
     if (threadIdx.x == 0) {
         double t[3] = {0.0, 0.0, 0.0};
-        for (int w = 0; w < kPosThreads / PAA_WARP; ++w)
-            for (int k = 0; k < 3; ++k) t[k] += s_part[w][k];
+        for (int w = 0; w < kPosThreads / PAA_WARP; ++w) {
+            t[0] += s_part[w][0];
+            for (int k = 0; k < 3; ++k) t[k] += s_own[w][k];
+        }
         write_losses(t, sc, norm, losses);
         *ticket = 0u;                   // paa_loss may be called again on the same assignment
+        ticket[kCtlChunk - 1] = 0u;     // ... and so may the bulk pass's chunk counter (ticket = LossWorkspace::ticket + 1)
     }
 }
 
@@ -929,6 +1205,7 @@ int launch_final_loss(const Geometry& geo, const float* gt_boxes, const int64_t*
         }
     }
     const bool g2 = (sc.gamma == 2.0f);
+    bool bulk_zeroes = false;        // bulk_focal_early_kernel zeroed the non-positive anchors' regression / IoU gradients
     double* bulk_part = ws.block_part;
     double* tile_part = ws.block_part + (size_t)kBulkMaxBlocks * 3;
     {
@@ -940,7 +1217,40 @@ int launch_final_loss(const Geometry& geo, const float* gt_boxes, const int64_t*
 #define PAA_BULK(G, T, I)                                                                                    \
     PAA_PDL_LAUNCH((bulk_focal_kernel<G, T, I>), bulk_grid, kBulkThreads, stream, plan, sc, normalisers,     \
                    ws.local_norm, grad_losses, bulk_part)
-        if (bulk_ignores) {
+        // PAA with one fused select_gmm launch in front, single rank: bulk_focal_early_kernel (dynamic chunks,
+        // fixed-point loss sum), part of the pass in the shadow of the last EM fits.  PAA_BULK_EARLY_PCT = share of the
+        // chunks that may be taken early (0 = none; negative = the static kernel, for comparisons).  The two-launch
+        // form keeps no per-SM fit count, and with several ranks norm_wait_kernel sits in between: static kernel.
+        // Four blocks per SM instead of five: the registers left over let positive_list_kernel's first blocks
+        // become resident (and do their work that does not depend on this pass) while the pass runs.
+        bulk_zeroes = false;
+        bool dynamic = sc.flavour == PAA_LOSS_PAA && geo.apl == 1 && write_grads && !bulk_ignores &&
+                       !select_gmm_two_launch(sc) && sc.world_size <= 1;
+        for (int l = 0; l < geo.num_levels; ++l)
+            if (!plan.dst[l]) dynamic = false;
+        int early_pct = 60;
+        if (const char* e = getenv("PAA_BULK_EARLY_PCT")) early_pct = atoi(e);
+        if (early_pct < 0) dynamic = false;
+        // small calls (a few chunks per block): the claims and the in-place scaling cost more than they hide
+        unsigned min_chunks = 4u * 148u * 4u;
+        if (const char* e = getenv("PAA_BULK_EARLY_MIN_CHUNKS")) min_chunks = (unsigned)atoi(e);      // test / measurement switch
+        if (chunks < min_chunks) dynamic = false;
+        EarlyCtl ec;
+        ec.ctl = ws.ticket;
+        ec.limit = (unsigned)((unsigned long long)chunks * (unsigned)(early_pct < 0 ? 0 : (early_pct > 100 ? 100 : early_pct)) / 100u);
+        ec.max_early = kEarlyMax;
+        if (dynamic) {
+            int bps = 4;
+            if (const char* e = getenv("PAA_BULK_BPS")) bps = atoi(e);          // measurement switch
+            if (bps >= 1 && bps <= kBulkBlocksPerSM && (unsigned)(148 * bps) < chunks) bulk_grid = 148 * bps;
+            const int fair = (int)((ec.limit + (unsigned)bulk_grid - 1u) / (unsigned)bulk_grid);
+            ec.max_early = 2 * fair < kEarlyMax ? (2 * fair < 1 ? 1 : 2 * fair) : kEarlyMax;
+            if (g2) PAA_PDL_LAUNCH((bulk_focal_early_kernel<true>), bulk_grid, kBulkThreads, stream, plan, sc, normalisers,
+                                   ws.local_norm, grad_losses, bulk_part, ec, geo, (const int*)ws.paa_label);
+            else PAA_PDL_LAUNCH((bulk_focal_early_kernel<false>), bulk_grid, kBulkThreads, stream, plan, sc, normalisers,
+                                ws.local_norm, grad_losses, bulk_part, ec, geo, (const int*)ws.paa_label);
+            bulk_zeroes = true;
+        } else if (bulk_ignores) {
             if (write_grads) {
                 if (g2) PAA_BULK(true, true, true); else PAA_BULK(true, false, true);
             } else {
@@ -957,13 +1267,20 @@ int launch_final_loss(const Geometry& geo, const float* gt_boxes, const int64_t*
         // PAA: the positives come as per-GT lists from select_gmm_kernel; the same launch zeroes the other anchors'
         // regression / IoU gradients and its last block writes the losses
         const int cap = geo.num_levels * sc.topk;
-        const long long work_a = (long long)geo.num_images * geo.A, work_b = (long long)sc.gt_capacity * cap;
+        const long long work_a = bulk_zeroes ? 0 : (long long)geo.num_images * geo.A, work_b = (long long)sc.gt_capacity * cap;
         long long blocks = ((work_a > work_b ? work_a : work_b) + kPosThreads - 1) / kPosThreads;
-        const int pos_grid = (int)(blocks < 1 ? 1 : (blocks > kPosMaxBlocks ? kPosMaxBlocks : blocks));
+        int pos_grid = (int)(blocks < 1 ? 1 : (blocks > kPosMaxBlocks ? kPosMaxBlocks : blocks));
+        // beside bulk_focal_early_kernel's four blocks per SM two of this kernel's are resident: no more than that,
+        // so that all of them work in the bulk pass's shadow (a thread keeps two positives' class elements for later)
+        if (bulk_zeroes && pos_grid > 148 * 2) pos_grid = 148 * 2;
+        if (const char* e = getenv("PAA_POS_BLOCKS")) {             // measurement switch
+            const int pb = atoi(e);
+            if (pb >= 1 && pb < pos_grid) pos_grid = pb;
+        }
         KernelTimer timer(PAA_KERNEL_POSITIVE_TERMS, stream);
 #define PAA_POSL(G, T)                                                                                       \
     PAA_PDL_LAUNCH((positive_list_kernel<G, T>), pos_grid, kPosThreads, stream, geo, gop, ws.gt_image, gt_boxes, gt_labels, sc, \
-        ws.pos_list, ws.part_npos, cap, ws.paa_label, normalisers, ws.local_norm, grad_losses, bulk_part, bulk_grid, \
+        ws.pos_list, ws.part_npos, cap, ws.paa_label, !bulk_zeroes, normalisers, ws.local_norm, grad_losses, bulk_part, bulk_grid, \
         tile_part, ws.ticket + 1, losses)
         if (write_grads) {
             if (g2) PAA_POSL(true, true); else PAA_POSL(true, false);

@@ -203,6 +203,9 @@ def test_two_launch_selection_equals_fused(monkeypatch, topk):
     labels, per-GT fit parameters, losses and gradients -- here forced on a small batch, and against the oracle."""
     b = synthetic.make_batch(seed=333 + topk, num_images=3, image_hw=(416, 512), gt_per_image=(2, 25))
     outs = []
+    # (the same bulk kernel behind both forms: the dynamic one only runs behind the fused form and sums the
+    # classification loss in fixed point -- test_bulk_pass_in_the_em_shadow_equals_the_static_pass)
+    monkeypatch.setenv("PAA_BULK_EARLY_PCT", "-1")
     for split_above in ("1000000", "0"):
         monkeypatch.setenv("PAA_GMM_SPLIT_ABOVE", split_above)
         ev = _evaluator(TOPK=topk)
@@ -218,6 +221,34 @@ def test_two_launch_selection_equals_fused(monkeypatch, topk):
         assert torch.equal(a, c)
     monkeypatch.setenv("PAA_GMM_SPLIT_ABOVE", "0")
     _assert_matches_oracle(b, max_exempt=2, TOPK=topk)
+
+
+def test_bulk_pass_in_the_em_shadow_equals_the_static_pass(monkeypatch):
+    """bulk_focal_early_kernel (chunks handed out dynamically; some processed unscaled while the last EM fits run and
+    scaled in place afterwards) against the static bulk_focal_kernel: every gradient bit for bit, the regression / IoU
+    losses bit for bit, the classification loss to float rounding (it is summed in fixed point) -- and bit for bit
+    among all dynamic settings and from run to run, whatever the split into early and late chunks was."""
+    b = synthetic.make_batch(seed=4242, num_images=4, image_hw=(800, 1333), gt_per_image=(1, 100))
+    outs = {}
+    monkeypatch.setenv("PAA_BULK_EARLY_MIN_CHUNKS", "0")        # (calls of this size take the static kernel by default)
+    for pct in ("-1", "0", "60", "100", "60"):
+        monkeypatch.setenv("PAA_BULK_EARLY_PCT", pct)
+        ev = _evaluator()
+        losses, cls, reg, iou = _run(ev, b)
+        out = ([float(x) for x in losses], [t.grad.clone() for t in cls + reg + iou])
+        if pct in outs:
+            assert out[0] == outs[pct][0]
+        outs.setdefault(pct, out)
+    l_static, g_static = outs["-1"]
+    for pct in ("0", "60", "100"):
+        l_dyn, g_dyn = outs[pct]
+        for a, c in zip(g_static, g_dyn):
+            assert torch.equal(a, c), pct
+        assert l_dyn[1:] == l_static[1:]
+        np.testing.assert_allclose(l_dyn[0], l_static[0], rtol=2e-6)
+        assert l_dyn == outs["0"][0]
+    monkeypatch.setenv("PAA_BULK_EARLY_PCT", "60")
+    _assert_matches_oracle(b, max_exempt=2)
 
 
 def _check_full_size_properties(b):

@@ -18,7 +18,8 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 TRACE_LIB = os.path.join(ROOT, "paa_b200", "libpaa_b200_trace.so")
-NAMES = ["prep_step", "iou_match", "match_score", "select_gmm", "bulk_focal", "positive_list", "gmm_fit_only"]
+NAMES = ["prep_step", "iou_match", "match_score", "select_gmm", "bulk_focal", "positive_list", "gmm_fit_only",
+         "pos_at_wait"]       # slot 7: positive_list_kernel's blocks arriving at their dependency wait (first / last)
 POST_FIRST = 8
 POST_NAMES = ["post_candidates", "post_threshold", "post_filter", "post_select", "post_rank", "post_group",
               "post_class_rank", "post_segments", "post_nms_runs", "post_nms_scan", "post_finish", "post_vote",

@@ -90,11 +90,14 @@ LOSS_KERNELS = [
     ("select_gmm_kernel", "select_gmm", "latency", lambda A, C: A * 12,
      "one warp per GT runs a serial f64 EM chain; the slowest GT of the batch decides (ncu: warps active ~14 %, "
      "top stalls wait / short_scoreboard)"),
-    ("bulk_focal_kernel", "final_loss", "hbm", lambda A, C: A * (4 * C + 4 * C),
-     "every logit read once, its gradient written once"),
-    ("positive_list_kernel", "positive_terms", "latency", lambda A, C: A * (4 + 20),
-     "the positives from per-GT lists (dependent loads per positive), zero gradients elsewhere, loss fold in the "
-     "last block"),
+    ("bulk_focal_early_kernel", "final_loss", "hbm", lambda A, C: A * (4 * C + 4 * C + 4 + 20),
+     "every logit read once, its gradient written once (chunks handed out dynamically; in the graph some are processed "
+     "unscaled in the shadow of the last EM fits and scaled in place afterwards -- an event-timed launch has no shadow), "
+     "plus the zero fill of the non-positive anchors' regression / IoU gradients; calls with few chunks, several ranks "
+     "or the two-launch fit take the static bulk_focal_kernel"),
+    ("positive_list_kernel", "positive_terms", "latency", lambda A, C: 0,
+     "the positives from per-GT lists (dependent loads per positive) -- in the graph in front of its dependency wait, in "
+     "the shadow of the bulk pass; behind it one store per positive and the loss fold in the last block"),
 ]
 POST_KERNELS = [
     ("post_candidates_kernel", "post_candidates", "hbm", lambda A, C: A * (4 * C + 4 + 16 + 16),

@@ -251,6 +251,43 @@ def test_bulk_pass_in_the_em_shadow_equals_the_static_pass(monkeypatch):
     _assert_matches_oracle(b, max_exempt=2)
 
 
+@pytest.mark.parametrize("variant", ["default", "no_iou_pred", "gamma", "channels_last", "one_image_one_gt"])
+def test_dynamic_bulk_kernel_on_small_calls_equals_static(monkeypatch, variant):
+    """Small calls take the static bulk kernel by default; forced onto bulk_focal_early_kernel (fewer chunks than
+    blocks, partial last chunks of every level, levels without a whole chunk) they must give the same gradients bit
+    for bit and the same losses (classification loss to float rounding), in every configuration the kernel's
+    arguments depend on."""
+    kw, use_iou, channels_last = {}, True, False
+    shape = dict(seed=515, num_images=3, image_hw=(416, 544), gt_per_image=(1, 12))
+    if variant == "no_iou_pred":
+        kw, use_iou = dict(USE_IOU_PRED=False), False
+    elif variant == "gamma":
+        kw = dict(LOSS_GAMMA=1.5, LOSS_ALPHA=0.4)
+    elif variant == "channels_last":
+        channels_last = True
+    elif variant == "one_image_one_gt":
+        shape = dict(seed=516, num_images=1, image_hw=(256, 320), gt_per_image=1)
+    b = synthetic.make_batch(**shape)
+    outs = []
+    for min_chunks, pct in (("1000000000", "60"), ("0", "60"), ("0", "100"), ("0", "0")):
+        monkeypatch.setenv("PAA_BULK_EARLY_MIN_CHUNKS", min_chunks)
+        monkeypatch.setenv("PAA_BULK_EARLY_PCT", pct)
+        ev = _evaluator(**kw)
+        cls, reg, iou, targets, anchors = to_device_inputs(b, requires_grad=True, channels_last=channels_last)
+        losses = ev(cls, reg, iou if use_iou else None, targets, anchors, None)
+        sum(losses).backward()
+        torch.cuda.synchronize()
+        grads = [t.grad.clone() for t in cls + reg + (iou if use_iou else [])]
+        outs.append(([float(x) for x in losses], grads))
+    l_static, g_static = outs[0]
+    for l_dyn, g_dyn in outs[1:]:
+        for a, c in zip(g_static, g_dyn):
+            assert torch.equal(a, c)
+        assert l_dyn[1:] == l_static[1:]
+        np.testing.assert_allclose(l_dyn[0], l_static[0], rtol=2e-6)
+        assert l_dyn == outs[1][0]
+
+
 def _check_full_size_properties(b):
     """Size-independent checks: determinism, positives are candidates matched to their GT, every GT with
     candidates gets >= 1 positive, and the batch splits into halves with identical labels and additive

@@ -1348,7 +1348,11 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
 
 __global__ void __launch_bounds__(PAA_WARP)
 norm_wait_kernel(const PeerExchange px, double* __restrict__ normalisers) {
+    // A programmatic dependent launch itself, and the loss pass behind it may start at once: its blocks become
+    // resident, prefetch (and work on unscaled chunks, bulk_focal_early_kernel) while this rank's last EM fits run
+    // and the peers' contributions travel; they wait for THIS kernel's end before they touch the normalisers.
     pdl_launch_dependents();
+    pdl_wait();                       // the epoch and this rank's own contribution come from select_gmm_kernel
     const int lane = threadIdx.x;
     const double* own = px.buf[px.rank];
     const unsigned long long epoch = (unsigned long long)own[kPeerEpochOffset];   // set by select_gmm_kernel
@@ -1389,8 +1393,7 @@ norm_wait_kernel(const PeerExchange px, double* __restrict__ normalisers) {
 
 int launch_norm_wait(const PeerExchange& px, double* normalisers, cudaStream_t stream) {
     KernelTimer timer(PAA_KERNEL_NORM_WAIT, stream);
-    norm_wait_kernel<<<1, PAA_WARP, 0, stream>>>(px, normalisers);
-    PAA_LAUNCH_CHECK("norm_wait_kernel");
+    PAA_PDL_LAUNCH(norm_wait_kernel, 1, PAA_WARP, stream, px, normalisers);
     return 0;
 }
 

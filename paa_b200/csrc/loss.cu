@@ -1217,15 +1217,16 @@ int launch_final_loss(const Geometry& geo, const float* gt_boxes, const int64_t*
 #define PAA_BULK(G, T, I)                                                                                    \
     PAA_PDL_LAUNCH((bulk_focal_kernel<G, T, I>), bulk_grid, kBulkThreads, stream, plan, sc, normalisers,     \
                    ws.local_norm, grad_losses, bulk_part)
-        // PAA with one fused select_gmm launch in front, single rank: bulk_focal_early_kernel (dynamic chunks,
-        // fixed-point loss sum), part of the pass in the shadow of the last EM fits.  PAA_BULK_EARLY_PCT = share of the
-        // chunks that may be taken early (0 = none; negative = the static kernel, for comparisons).  The two-launch
-        // form keeps no per-SM fit count, and with several ranks norm_wait_kernel sits in between: static kernel.
+        // PAA with one fused select_gmm launch in front: bulk_focal_early_kernel (dynamic chunks, fixed-point loss
+        // sum), part of the pass in the shadow of the last EM fits.  PAA_BULK_EARLY_PCT = share of the chunks that may
+        // be taken early (0 = none; negative = the static kernel, for comparisons).  The two-launch form keeps no
+        // per-SM fit count: static kernel.  (Several ranks: norm_wait_kernel in between is a programmatic dependent
+        // launch that lets this one start at once; behind an NCCL all-reduce there is no shadow and no early chunk.)
         // Four blocks per SM instead of five: the registers left over let positive_list_kernel's first blocks
         // become resident (and do their work that does not depend on this pass) while the pass runs.
         bulk_zeroes = false;
         bool dynamic = sc.flavour == PAA_LOSS_PAA && geo.apl == 1 && write_grads && !bulk_ignores &&
-                       !select_gmm_two_launch(sc) && sc.world_size <= 1;
+                       !select_gmm_two_launch(sc);
         for (int l = 0; l < geo.num_levels; ++l)
             if (!plan.dst[l]) dynamic = false;
         int early_pct = 60;

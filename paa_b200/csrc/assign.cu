@@ -776,6 +776,45 @@ __device__ __forceinline__ double warp_sum7_prod(double (&v)[8], int lane) {
     return __shfl_sync(PAA_FULL, y, 28);
 }
 
+// The seven sums through shared memory (`red`: kGmmRedDoubles doubles owned by the fitting warp; the other warps of a
+// select_gmm block have exited by then): every lane parks its seven values, lane (q = lane & 7, part = lane >> 3) adds
+// entries 8 part .. 8 part + 7 of quantity q as a three-level tree, two shuffle rounds join the four parts, and the
+// totals travel back through seven words that every lane reads.  Two shared-memory round trips + two shuffle rounds on
+// the dependent path instead of five shuffle rounds + a broadcast round of seven more; the product of slot 7 is a
+// five-round butterfly of its own, an independent chain hidden behind them.  Measured (tools/gmm_sections.py, C2):
+// 1534 -> 1395 cycles per iteration (E-step 378 -> 342, reduction 341 -> 329, M-step 277 -> 179: the totals no longer
+// arrive one shuffle at a time), select_gmm_kernel 46.8 -> 42.0 us in the C2 step; every fit of C2 / C3 / C5 still stops
+// at scikit-learn's iteration.  Row stride 33 doubles: the half-warp's rows x parts fall on different bank pairs.
+constexpr int kGmmRedStride = 33;
+constexpr int kGmmRedDoubles = 8 * kGmmRedStride + 8;
+__device__ __forceinline__ double warp_sum7_prod_smem(double (&v)[8], int lane, double* red) {
+#pragma unroll
+    for (int q = 0; q < 7; ++q) red[q * kGmmRedStride + lane] = v[q];
+    __syncwarp();
+    // the product of slot 7 as a butterfly of its own: an independent chain that the sums' two memory round trips hide
+    double P = v[7];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) P *= __shfl_xor_sync(PAA_FULL, P, o);
+    const int q = (lane & 7) < 7 ? (lane & 7) : 0, part = lane >> 3;         // (lanes 7, 15, 23, 31 repeat quantity 0)
+    const double* row = red + q * kGmmRedStride + part * 8;
+    double e[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) e[j] = row[j];
+#pragma unroll
+    for (int w = 4; w > 0; w >>= 1)
+#pragma unroll
+        for (int j = 0; j < w; ++j) e[j] = e[2 * j] + e[2 * j + 1];
+    double y = e[0];
+    y += __shfl_xor_sync(PAA_FULL, y, 8);
+    y += __shfl_xor_sync(PAA_FULL, y, 16);
+    double* tot = red + 8 * kGmmRedStride;
+    if (lane < 7) tot[lane] = y;
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 7; ++k) v[k] = tot[k];
+    return P;
+}
+
 // Fits the mixture on the warp's n sorted samples (lane holds x[lane + 32*k]) and returns the length
 // of the positive prefix (loss.py:206-217).  out8 (nullable, lane 0 writes) receives the parameters.
 //
@@ -801,7 +840,7 @@ __device__ __forceinline__ double warp_sum7_prod(double (&v)[8], int lane) {
 //    stopping rule, so the rule's own chain (log prod -> mean -> difference) is off the critical path; on
 //    exit they are exactly the final E-step's.
 template <int SPL>
-__device__ int gmm_positive_prefix(const float (&x)[SPL], int n, int lane, double* out8) {
+__device__ int gmm_positive_prefix(const float (&x)[SPL], int n, int lane, double* out8, double* red) {
     GmmState s;
     s.lw0 = s.lw1 = -0.6931471805599453094;                              // log 0.5
     s.mu0 = (double)__shfl_sync(PAA_FULL, x[0], 0);                       // min (sorted ascending)
@@ -880,7 +919,7 @@ __device__ int gmm_positive_prefix(const float (&x)[SPL], int n, int lane, doubl
         const long long tB = clock64();
         prof_sec[0] += tB - tA;
 #endif
-        P = warp_sum7_prod(v, lane);
+        P = red ? warp_sum7_prod_smem(v, lane, red) : warp_sum7_prod(v, lane);      // (shuffle-only form: no scratch space)
 #ifdef PAA_PROFILE_GMM
         const long long tC = clock64();
         prof_sec[1] += tC - tB;
@@ -1067,6 +1106,7 @@ select_gmm_kernel(const Geometry geo, const GtOffsets* __restrict__ gop, const i
     __shared__ int s_cnt[PAA_MAX_LEVELS];
     __shared__ unsigned long long s_key[PAA_MAX_CANDIDATES];
     __shared__ unsigned long long s_sorted[PAA_MAX_CANDIDATES];
+    __shared__ double s_red[MODE == kFitOnly ? kFitWarps : 1][kGmmRedDoubles];      // the fitting warp's reduction space
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gi = MODE == kFitOnly ? blockIdx.x * kFitWarps + warp : blockIdx.x;
@@ -1233,7 +1273,8 @@ select_gmm_kernel(const Geometry geo, const GtOffsets* __restrict__ gop, const i
     if (n_cand == 1) {
         n_pos = 1;                                     // loss.py:218-219
     } else if (n_cand > 1) {
-        n_pos = gmm_positive_prefix<SPL>(x, n_cand, lane, dbg.gmm ? dbg.gmm + (size_t)gi * 8 : nullptr);
+        n_pos = gmm_positive_prefix<SPL>(x, n_cand, lane, dbg.gmm ? dbg.gmm + (size_t)gi * 8 : nullptr,
+                                         s_red[MODE == kFitOnly ? warp : 0]);
     }
     if (MODE == kSelectFused && lane == 0) atomicSub(ticket + kCtlSmLive + (smid & (kCtlMaxSms - 1)), 1u);
     if (dbg.gmm && n_cand <= 1 && lane < 8) dbg.gmm[(size_t)gi * 8 + lane] = 0.0;

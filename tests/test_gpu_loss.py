@@ -288,6 +288,25 @@ def test_dynamic_bulk_kernel_on_small_calls_equals_static(monkeypatch, variant):
         assert l_dyn == outs[1][0]
 
 
+def test_dynamic_bulk_kernel_on_a_large_call_equals_static(monkeypatch):
+    """More anchors than four per thread of the early bulk kernel's grid (30 images of 800x1333: 672 000 anchors against
+    4 x 592 x 256 threads): the tail loop of its zero fill, many chunks per block, positives spread over more than two
+    trips of positive_list_kernel's 296 blocks.  Gradients bit for bit, losses as in the small-call test."""
+    b = synthetic.make_batch(seed=606, num_images=30, image_hw=(800, 1333), gt_per_image=(60, 100))
+    outs = []
+    for pct in ("-1", "60"):
+        monkeypatch.setenv("PAA_BULK_EARLY_PCT", pct)
+        ev = _evaluator()
+        losses, cls, reg, iou = _run(ev, b)
+        outs.append(([float(x) for x in losses], [t.grad.clone() for t in cls + reg + iou]))
+        del cls, reg, iou
+    (l_static, g_static), (l_dyn, g_dyn) = outs
+    for a, c in zip(g_static, g_dyn):
+        assert torch.equal(a, c)
+    assert l_dyn[1:] == l_static[1:]
+    np.testing.assert_allclose(l_dyn[0], l_static[0], rtol=2e-6)
+
+
 def _check_full_size_properties(b):
     """Size-independent checks: determinism, positives are candidates matched to their GT, every GT with
     candidates gets >= 1 positive, and the batch splits into halves with identical labels and additive
